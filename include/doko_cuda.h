@@ -1,0 +1,233 @@
+/*
+ * doko_cuda.h — C ABI of libdoko_cuda.so, the B200 (sm_100a) batched Doppelkopf simulator.
+ *
+ * This is the drop-in boundary for ONE hot path of theodm/master_doko_reinforcement_learning:
+ * game transition -> determinization -> random rollouts -> observation encode.
+ * The reference has no FFI boundary; its seam is a set of Rust traits over by-value state structs.
+ * Each entry point below names the reference interface it replaces (paths relative to the
+ * reference checkout).  Everything is batch-first, works on caller-owned buffers, takes an explicit
+ * CUDA stream and reports errors through integer codes (it never aborts across the FFI).
+ *
+ * There is NO CPU fallback: every compute entry point launches sm_100a kernels and returns
+ * DK_ERR_NO_DEVICE / DK_ERR_CUDA if that is impossible.
+ *
+ * Memory spaces: pointers marked [dev] are device pointers on the context's GPU; the *_host entry
+ * points take [host] pointers and perform the host<->device copies themselves (they are what a
+ * Rust/ctypes caller with ordinary slices binds).
+ */
+#ifndef DOKO_CUDA_H
+#define DOKO_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DK_VERSION_MAJOR 0
+#define DK_VERSION_MINOR 1
+
+typedef struct dk_ctx dk_ctx;
+typedef int32_t dk_status;
+typedef void* dk_stream; /* cudaStream_t; NULL = the context's own stream */
+
+enum {
+    DK_OK = 0,
+    DK_ERR_INVALID_ARGUMENT = 1,
+    DK_ERR_CUDA = 2,       /* a CUDA runtime call or kernel failed; see dk_last_error() */
+    DK_ERR_NO_DEVICE = 3,  /* no usable sm_100 GPU: the library has no CPU path */
+    DK_ERR_NCCL = 4,
+    DK_ERR_UNSUPPORTED = 5
+};
+
+/* Rule engines. */
+enum {
+    DK_DOKO = 0, /* rs-doko: normal game + wedding, no solos, no announcements (rs-doko/src/state/state.rs) */
+    DK_FDO = 1   /* rs-full-doko: full DKV rules (rs-full-doko/src/state/state.rs) */
+};
+
+/* ------------------------------------------------------------------------------------------------
+ * Domain encoding (identical to the reference's).
+ *
+ * Card id c = suit*6 + rank; suits Diamond 0, Heart 1, Club 2, Spade 3; ranks 9,10,J,Q,K,A = 0..5
+ * (rs-full-doko/src/card/cards.rs:7-36).  A hand is a 48-bit board: copy A of card c is bit c,
+ * copy B is bit c+24 (rs-full-doko/src/hand/hand.rs:20,107).  Seats: BOTTOM 0, LEFT 1, TOP 2,
+ * RIGHT 3, play proceeds +1 mod 4 (rs-full-doko/src/player/player.rs:11-16,67-72).
+ *
+ * Action index = bit index of the reference's FdoAction / DoAction (rs-full-doko/src/action/action.rs:9-54,
+ * rs-doko/src/action/action.rs:7-38): 0..23 play card c; 24 Healthy; 25 Wedding; 26 Diamonds-, 27 Hearts-,
+ * 28 Spades-, 29 Clubs-, 30 Trumpless-, 31 Queens-, 32 Jacks-Solo; 33 Re/Kontra; 34 No90; 35 No60; 36 No30;
+ * 37 Black; 38 NoAnnouncement.  DK_DOKO uses 0..25 only.  A legal mask has bit i set iff action i is legal.
+ * ------------------------------------------------------------------------------------------------ */
+#define DK_NUM_ACTIONS_FDO 39
+#define DK_NUM_ACTIONS_DOKO 26
+#define DK_ACTION_HEALTHY 24
+#define DK_ACTION_WEDDING 25
+#define DK_ACTION_RE_CONTRA 33
+#define DK_ACTION_NO_ANNOUNCEMENT 38
+
+/* FdoPhase (rs-full-doko/src/basic/phase.rs:6-11).  DK_DOKO states use the same codes (its own enum
+ * is Reservation 0, PlayCard 1, Finished 2 — rs-doko/src/basic/phase.rs; dk_encode emits that). */
+enum { DK_PHASE_RESERVATION = 0, DK_PHASE_ANNOUNCEMENT = 1, DK_PHASE_PLAY_CARD = 2, DK_PHASE_FINISHED = 3 };
+
+/* FdoGameType (rs-full-doko/src/game_type/game_type.rs:6-20). */
+enum {
+    DK_GT_NORMAL = 0, DK_GT_WEDDING = 1, DK_GT_DIAMONDS_SOLO = 2, DK_GT_HEARTS_SOLO = 3, DK_GT_SPADES_SOLO = 4,
+    DK_GT_CLUBS_SOLO = 5, DK_GT_TRUMPLESS_SOLO = 6, DK_GT_QUEENS_SOLO = 7, DK_GT_JACKS_SOLO = 8, DK_GT_NONE = 15
+};
+
+/* FdoReservation (rs-full-doko/src/reservation/reservation.rs:11-24) — note: NOT the action order. */
+enum {
+    DK_RES_HEALTHY = 0, DK_RES_WEDDING = 1, DK_RES_DIAMONDS_SOLO = 2, DK_RES_HEARTS_SOLO = 3, DK_RES_SPADES_SOLO = 4,
+    DK_RES_CLUBS_SOLO = 5, DK_RES_QUEENS_SOLO = 6, DK_RES_JACKS_SOLO = 7, DK_RES_TRUMPLESS_SOLO = 8, DK_RES_NONE = 0xFF
+};
+
+/* Announcement level codes (FdoAnnouncement, rs-full-doko/src/announcement/announcement.rs:12-22). */
+enum { DK_ANN_NONE = 0, DK_ANN_RE_CONTRA = 1, DK_ANN_NO90 = 2, DK_ANN_NO60 = 3, DK_ANN_NO30 = 4, DK_ANN_BLACK = 5, DK_ANN_COUNTER = 6 };
+
+/* FdoTeamState tag (rs-full-doko/src/team/team_logic.rs:11-28). */
+enum { DK_TEAM_IN_RESERVATIONS = 0, DK_TEAM_WEDDING_UNSOLVED = 1, DK_TEAM_WEDDING_SOLVED = 2, DK_TEAM_NO_WEDDING = 3 };
+
+/* ------------------------------------------------------------------------------------------------
+ * dk_state — one game, 128 bytes, 16-byte aligned POD.  Replaces the by-value `FdoState`
+ * (rs-full-doko/src/state/state.rs:24-75, ~1.2 KB) and `DoState` (rs-doko/src/state/state.rs:29-76).
+ * It holds the complete history needed by the encoders and the determinizer.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct dk_state {
+    uint64_t hands[4];          /*   0: current hands by absolute seat (48-bit boards) */
+    uint8_t cards[48];          /*  32: played cards in play order, card id 0..23; 0xFF = not played yet */
+    uint16_t announcements[12]; /*  80: k-th call: bits 0-5 card_index, 6-7 seat, 8-10 level code; 0xFFFF = unused
+                                 *      (FdoAnnouncementOccurrence, announcement.rs:38-43) */
+    uint8_t reservations[4];    /* 104: reservations in PLAY order from the game's start seat; DK_RES_NONE = not made.
+                                 *      DK_FDO: DK_RES_* codes; DK_DOKO: DoReservation (Wedding 0, Healthy 1) */
+    uint32_t tricks;            /* 108: bits 2t..2t+1 start seat of trick t (t<12); bits 24-27 #tricks started; bits 28-31 #calls */
+    uint8_t eyes[4];            /* 112: eyes captured per absolute seat (completed tricks only) */
+    uint16_t num_tricks;        /* 116: bits 4p..4p+3 tricks won by seat p */
+    uint8_t card_index;         /* 118: number of cards played (0..48) */
+    uint8_t n_reservations;     /* 119: number of reservations made (0..4) */
+    int8_t points[4];           /* 120: player_points per absolute seat; valid iff phase == DK_PHASE_FINISHED */
+    uint32_t meta;              /* 124: bits 0-1 phase | 2-3 current seat | 4-5 game start seat | 6-9 game type |
+                                 *      10-11 team tag | 12-13 wedding seat | 14-15 solved_trick_index | 16-19 re seats mask |
+                                 *      20-22 re lowest call | 23-25 kontra lowest call | 26-28 turns without call |
+                                 *      29-30 start seat of the running announcement round | 31 last-trick winner card is ♣J */
+} dk_state;
+
+/* Observation layouts for dk_encode. */
+enum {
+    DK_LAYOUT_DO110 = 0,    /* rs-doko-embeddings/src/encode_state.rs:84-187  (110 tokens, DK_DOKO) */
+    DK_LAYOUT_DO114 = 1,    /* rs-doko-embeddings/src/encode_state.rs:189-317 (114 tokens, DK_DOKO) */
+    DK_LAYOUT_FDO_PI311 = 2 /* rs-doko-networks/src/full_doko/var1/encode_pi.rs:27-216 ([i64;311], DK_FDO) */
+};
+#define DK_OBS_LEN_DO110 110
+#define DK_OBS_LEN_DO114 114
+#define DK_OBS_LEN_FDO_PI311 311
+
+/* Flags. */
+#define DK_PLAYOUT_WITH_ANNOUNCEMENTS 1u /* FdoState::random_action_for_current_player (state.rs:378-399); without it the
+                                            _no_announcement variant (state.rs:401-431) as used by random_rollout */
+#define DK_APPLY_SKIP_SINGLE 1u          /* FdoAzEnvState::take_action_by_action_index(.., skip_single=true, ..)
+                                            (rs-doko-alpha-zero/src/env/envs/full_doko/full_doko.rs:121-154) */
+
+/* Random stream: Philox4x32-10, key = seed, counter = (unit_lo, unit_hi, site<<16 | block, epoch).
+ * unit = first_id + index of the game / info-state / leaf in the batch, so results do not depend on
+ * how a batch is sharded across GPUs.  See DESIGN.md "Philox parity contract". */
+typedef struct dk_rng {
+    uint64_t seed;
+    uint64_t first_id;
+    uint32_t epoch;
+    uint32_t reserved;
+} dk_rng;
+
+/* ---- context ------------------------------------------------------------------------------- */
+dk_status dk_init(int device, dk_ctx** out);
+dk_status dk_destroy(dk_ctx* ctx);
+const char* dk_last_error(const dk_ctx* ctx); /* message of the last failing call on this context */
+const char* dk_version(void);
+dk_status dk_device_info(const dk_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, size_t* total_mem);
+dk_status dk_synchronize(dk_ctx* ctx, dk_stream stream);
+/* Number of kernels this library has launched on this context since dk_init (bench.py's gpu_launches). */
+uint64_t dk_launch_count(const dk_ctx* ctx);
+
+/* ---- game construction -----------------------------------------------------------------------
+ * replaces FdoState::new_game (rs-full-doko/src/state/state.rs:169-178) /
+ *          DoState::new_game  (rs-doko/src/state/state.rs:159-168): start seat, then a 48-card shuffle. */
+dk_status dk_new_games(dk_ctx* ctx, int engine, size_t n, const dk_rng* rng, dk_state* out /*[dev] n*/, dk_stream stream);
+/* replaces new_game_from_hand_and_start_player (rs-full-doko/src/state/state.rs:125-166) */
+dk_status dk_from_deals(dk_ctx* ctx, int engine, size_t n, const uint64_t* hands /*[dev] n*4*/,
+                        const uint8_t* start /*[dev] n*/, dk_state* out /*[dev] n*/, dk_stream stream);
+
+/* ---- transition --------------------------------------------------------------------------------
+ * replaces FdoAllowedActions::calculate_allowed_actions (rs-full-doko/src/action/allowed_actions.rs:68-169) as
+ *          surfaced by McEnvState::allowed_actions(first_expansion=true) (rs-doko-mcts/src/env/env_state.rs:15)
+ *          and AzEnvState::allowed_actions_by_action_index (rs-doko-alpha-zero/src/env/env_state.rs:20-24);
+ *          rs-doko: calculate_allowed_actions_in_normal_game (rs-doko/src/action/allowed_actions.rs:131-198).
+ * A finished game yields mask 0. */
+dk_status dk_legal_mask(dk_ctx* ctx, int engine, size_t n, const dk_state* states /*[dev]*/, uint64_t* mask_out /*[dev] n*/,
+                        dk_stream stream);
+/* replaces FdoState::play_action (rs-full-doko/src/state/state.rs:208-358) / McEnvState::by_action /
+ *          AzEnvState::take_action_by_action_index; rs-doko: DoState::play_action (rs-doko/src/state/state.rs:189-309).
+ * An illegal action (the reference would panic) sets err_out[i] != 0 and leaves state i unchanged. */
+dk_status dk_apply(dk_ctx* ctx, int engine, size_t n, dk_state* states /*[dev] in/out*/, const uint8_t* action_idx /*[dev] n*/,
+                   uint32_t flags, uint8_t* err_out /*[dev] n, may be NULL*/, dk_stream stream);
+/* replaces McEnvState::{is_terminal, rewards_or_none} (rs-doko-mcts/src/env/envs/env_state_full_doko.rs:75-79,191-196):
+ * done_out[i] = phase == Finished; points_out[i] = player_points (0 when not finished). */
+dk_status dk_terminal(dk_ctx* ctx, int engine, size_t n, const dk_state* states /*[dev]*/, uint8_t* done_out /*[dev] n*/,
+                      int32_t* points_out /*[dev] n*4*/, dk_stream stream);
+
+/* ---- observation encode --------------------------------------------------------------------------
+ * replaces AzEnvState::encode_into_memory (rs-doko-alpha-zero/src/env/envs/full_doko/full_doko.rs:71-78) =
+ *          encode_state_pi(state, state.observation_for_current_player()); rs-doko: encode_state[_with_reservations].
+ * Row i is written at out + i*row_stride (in elements, >= layout length); batch-major like the reference's
+ * flattened Vec<i64> (rs-doko-alpha-zero/src/alpha_zero/batch_processor/network_batch_processor.rs:85-91). */
+dk_status dk_encode(dk_ctx* ctx, int layout, size_t n, const dk_state* states /*[dev]*/, int64_t* out /*[dev]*/,
+                    size_t row_stride, dk_stream stream);
+/* One lock-step self-play env step: legal mask -> one Philox draw -> play_action -> encode_state_pi of the new
+ * state (self_play.rs:76-190 without the NN).  action_out may be NULL. */
+dk_status dk_step_random_encode(dk_ctx* ctx, size_t n, dk_state* states /*[dev] in/out*/, const dk_rng* rng, uint32_t flags,
+                                int64_t* obs_out /*[dev]*/, size_t row_stride, uint8_t* action_out /*[dev] n*/,
+                                dk_stream stream);
+
+/* ---- playouts --------------------------------------------------------------------------------------
+ * replaces the loop `while !state.random_action_for_current_player[_no_announcement](rng) {}` and
+ *          McEnvState::random_rollout (rs-doko-mcts/src/env/envs/env_state_full_doko.rs:198-220,
+ *          env_state_doko.rs:150-169).  states == NULL plays fresh games dealt from the stream
+ *          (new_game + playout fused on-chip).  points_out[i] = player_points; steps_out[i] = number of
+ *          play_action calls ("game steps"); either may be NULL. */
+dk_status dk_playout(dk_ctx* ctx, int engine, uint32_t flags, size_t n, const dk_state* states /*[dev] or NULL*/,
+                     const dk_rng* rng, int32_t* points_out /*[dev] n*4*/, uint32_t* steps_out /*[dev] n*/,
+                     dk_stream stream);
+/* Same, results copied to HOST buffers inside the call (what a plain Rust slice caller binds). */
+dk_status dk_playout_host(dk_ctx* ctx, int engine, uint32_t flags, size_t n, const dk_state* states_host /*[host] or NULL*/,
+                          const dk_rng* rng, int32_t* points_out_host /*[host] n*4*/, uint32_t* steps_out_host /*[host] n*/);
+
+/* ---- determinization ---------------------------------------------------------------------------------
+ * replaces card_matching (rs-full-doko/src/matching/card_matching.rs:241-467) as called by CAPSampling::sample
+ *          (rs-doko-py-bridge/src/compare_impi/compare_impi.rs:64-83); observer = seat to move.
+ * For info-state i and sample s (unit = first_id + i, unit_hi = s):
+ *   hands_out[(i*S+s)*4 + seat], reservations_out[(i*S+s)*4 + seat] (DK_RES_* by ABSOLUTE seat, DK_RES_NONE if the
+ *   seat has not declared yet), status_out[i*S+s] != 0 for a dead end (the reference would panic). */
+dk_status dk_determinize(dk_ctx* ctx, int engine, size_t n_info, size_t samples_per_info, const dk_state* states /*[dev]*/,
+                         const dk_rng* rng, uint64_t* hands_out /*[dev]*/, uint8_t* reservations_out /*[dev]*/,
+                         uint8_t* status_out /*[dev]*/, dk_stream stream);
+/* Leaf-parallel rollouts (new design over random_rollout): for leaf i run R rollouts (unit = first_id + i,
+ * unit_hi = r), each first determinized when `determinize` != 0, then played with the _no_announcement policy.
+ * point_sum_out[i*4 + seat] = exact integer sum of player_points over the R rollouts. */
+dk_status dk_leaf_rollouts(dk_ctx* ctx, size_t n_leaves, size_t rollouts_per_leaf, int determinize,
+                           const dk_state* states /*[dev]*/, const dk_rng* rng, int64_t* point_sum_out /*[dev] n_leaves*4*/,
+                           dk_stream stream);
+
+/* ---- multi-GPU root statistics (the only exchange step) --------------------------------------
+ * replaces the per-determinization fuse of PolicyFusion* (rs-doko-py-bridge/src/compare_impi/policy_fusion.rs:18-123):
+ * integer sums over ranks, order-independent and bit-reproducible.  NCCL is loaded lazily (dlopen). */
+typedef struct dk_nccl_id { char bytes[128]; } dk_nccl_id;
+dk_status dk_comm_unique_id(dk_ctx* ctx, dk_nccl_id* out);
+dk_status dk_comm_init(dk_ctx* ctx, int n_ranks, int rank, const dk_nccl_id* id);
+dk_status dk_comm_destroy(dk_ctx* ctx);
+dk_status dk_allreduce_root_stats(dk_ctx* ctx, size_t n_values, int64_t* values /*[dev] in/out, sum over ranks*/,
+                                  dk_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DOKO_CUDA_H */

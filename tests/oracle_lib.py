@@ -1,0 +1,304 @@
+"""ctypes binding of oracle/liboracle.so — TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may import this.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+LIB = os.path.join(ORACLE_DIR, "liboracle.so")
+
+SUITS = {"D": 0, "H": 1, "C": 2, "S": 3, "♦": 0, "♥": 1, "♣": 2, "♠": 3}
+RANKS = {"9": 0, "10": 1, "J": 2, "Q": 3, "K": 4, "A": 5}
+CARD_NAMES = [s + r for s in "DHCS" for r in ("9", "10", "J", "Q", "K", "A")]
+RUST_CARD_NAMES = [s + r for s in ("Diamond", "Heart", "Club", "Spade") for r in ("Nine", "Ten", "Jack", "Queen", "King", "Ace")]
+GAME_TYPES = ["Normal", "Wedding", "DiamondsSolo", "HeartsSolo", "SpadesSolo", "ClubsSolo", "TrumplessSolo", "QueensSolo", "JacksSolo"]
+RESERVATIONS = ["Healthy", "Wedding", "DiamondsSolo", "HeartsSolo", "SpadesSolo", "ClubsSolo", "QueensSolo", "JacksSolo", "TrumplessSolo"]
+RES_ACTION = {"Healthy": 24, "Wedding": 25, "DiamondsSolo": 26, "HeartsSolo": 27, "SpadesSolo": 28, "ClubsSolo": 29,
+              "TrumplessSolo": 30, "QueensSolo": 31, "JacksSolo": 32}
+ANN_ACTION = {"ReContra": 33, "No90": 34, "No60": 35, "No30": 36, "Black": 37, "NoAnnouncement": 38}
+ANN_BITS = {None: 0, "ReContra": 1, "No90": 2, "No60": 4, "No30": 8, "Black": 16, "CounterReContra": 32, "NoAnnouncement": 64}
+COLORS = {"Trump": 0, "Diamond": 1, "Heart": 2, "Spade": 3, "Club": 4, "T": 0, "♦": 1, "♥": 2, "♠": 3, "♣": 4}
+PLAYERS = {"BOTTOM": 0, "LEFT": 1, "TOP": 2, "RIGHT": 3, "B": 0, "L": 1, "T": 2, "R": 3}
+
+
+def card_id(name):
+    """'D9', 'H10', '♦9', '♥10' → 0..23."""
+    return SUITS[name[0]] * 6 + RANKS[name[1:]]
+
+
+def hand_from_cards(cards):
+    """FdoHand::from_vec / hand_from_vec: add → copy A first, then copy B."""
+    h = 0
+    for c in cards:
+        if isinstance(c, str):
+            c = card_id(c)
+        if (h >> c) & 1:
+            h |= 1 << (c + 24)
+        else:
+            h |= 1 << c
+    return h
+
+
+class DkState(C.Structure):
+    _fields_ = [("hands", C.c_uint64 * 4), ("cards", C.c_uint8 * 48), ("announcements", C.c_uint16 * 12),
+                ("reservations", C.c_uint8 * 4), ("tricks", C.c_uint32), ("eyes", C.c_uint8 * 4), ("num_tricks", C.c_uint16),
+                ("card_index", C.c_uint8), ("n_reservations", C.c_uint8), ("points", C.c_int8 * 4), ("meta", C.c_uint32)]
+
+
+assert C.sizeof(DkState) == 128
+
+DK_STATE_DTYPE = np.dtype([("hands", "<u8", 4), ("cards", "u1", 48), ("announcements", "<u2", 12), ("reservations", "u1", 4),
+                           ("tricks", "<u4"), ("eyes", "u1", 4), ("num_tricks", "<u2"), ("card_index", "u1"),
+                           ("n_reservations", "u1"), ("points", "i1", 4), ("meta", "<u4")])
+assert DK_STATE_DTYPE.itemsize == 128
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", ORACLE_DIR])
+
+
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB) or any(
+            os.path.getmtime(os.path.join(ORACLE_DIR, f)) > os.path.getmtime(LIB)
+            for f in os.listdir(ORACLE_DIR) if f.endswith((".hpp", ".cpp"))):
+        build()
+    L = C.CDLL(LIB)
+    vp, u64, u32, i32, dbl = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int, C.c_double
+    L.orc_last_error.restype = C.c_char_p
+    L.orc_select_by_rank.restype = u64
+    L.orc_select_by_rank.argtypes = [u64, u64]
+    L.orc_philox_word.restype = u32
+    L.orc_philox_word.argtypes = [u64, u32, u32, u32, u32, u32]
+    for name in ("orc_fdo_new", "orc_fdo_new_game_philox", "orc_fdo_new_game_smallrng", "orc_fdo_clone", "orc_fdo_import",
+                 "orc_doko_new", "orc_doko_new_game_philox", "orc_doko_new_game_smallrng_play", "orc_doko_clone",
+                 "orc_fdo_with_hands_and_reservations"):
+        getattr(L, name).restype = vp
+    L.orc_fdo_new.argtypes = [C.POINTER(u64), i32]
+    L.orc_doko_new.argtypes = [C.POINTER(u64), i32]
+    L.orc_fdo_new_game_philox.argtypes = [u64, u64, u32]
+    L.orc_doko_new_game_philox.argtypes = [u64, u64, u32]
+    L.orc_fdo_new_game_smallrng.argtypes = [u64]
+    L.orc_doko_new_game_smallrng_play.argtypes = [u64, i32]
+    for name in ("orc_fdo_clone", "orc_fdo_free", "orc_doko_clone", "orc_doko_free"):
+        getattr(L, name).argtypes = [vp]
+    L.orc_fdo_import.argtypes = [vp]
+    L.orc_fdo_play.argtypes = [vp, i32]
+    L.orc_doko_play.argtypes = [vp, i32]
+    L.orc_fdo_allowed.restype = u64
+    L.orc_fdo_allowed.argtypes = [vp]
+    L.orc_doko_allowed.restype = u64
+    L.orc_doko_allowed.argtypes = [vp]
+    for name in ("orc_fdo_info", "orc_fdo_hands", "orc_fdo_tricks", "orc_fdo_additional", "orc_fdo_encode_pi", "orc_fdo_export",
+                 "orc_doko_info", "orc_doko_hands", "orc_doko_export"):
+        getattr(L, name).argtypes = [vp, vp]
+    L.orc_fdo_visible_reservations.argtypes = [vp, i32, vp]
+    L.orc_doko_encode.argtypes = [vp, i32, vp]
+    L.orc_fdo_random_step_philox.argtypes = [vp, u64, u64, u32, i32, u32]
+    L.orc_doko_random_step_philox.argtypes = [vp, u64, u64, u32]
+    L.orc_fdo_hand_plus.restype = u64
+    L.orc_fdo_hand_plus.argtypes = [u64, u64]
+    L.orc_fdo_hand_minus.restype = u64
+    L.orc_fdo_hand_minus.argtypes = [u64, u64]
+    L.orc_fdo_hand_remove_color.restype = u64
+    L.orc_fdo_hand_remove_color.argtypes = [u64, i32, i32]
+    L.orc_fdo_hand_iter.argtypes = [u64, vp]
+    L.orc_fdo_hand_op.argtypes = [C.POINTER(u64), i32, i32]
+    L.orc_doko_hand_op.restype = u64
+    L.orc_doko_hand_op.argtypes = [u64, i32, i32]
+    L.orc_doko_allowed_actions.restype = u64
+    L.orc_doko_allowed_actions.argtypes = [i32, i32, u64]
+    L.orc_fdo_all_higher_than.restype = u32
+    L.orc_fdo_internal_calc_allowed.restype = u32
+    L.orc_fdo_internal_calc_allowed.argtypes = [i32, u32, i32, i32]
+    L.orc_fdo_calc_allowed.restype = u32
+    L.orc_fdo_calc_allowed.argtypes = [i32, i32, i32, i32, i32, u32, i32, i32]
+    L.orc_fdo_card_matching_philox.argtypes = [vp, u64, u64, u32, u32, vp, vp]
+    L.orc_fdo_is_consistent.argtypes = [vp, vp, vp]
+    L.orc_fdo_with_hands_and_reservations.argtypes = [vp, vp, vp]
+    L.orc_fdo_random_rollout_philox.argtypes = [vp, u64, u64, u32, u32, i32, vp, vp]
+    L.orc_playout_philox.restype = dbl
+    L.orc_playout_philox.argtypes = [i32, i32, u64, u32, u64, u64, i32, vp, vp, vp, vp, i32]
+    L.orc_smallrng_distribute_cards.argtypes = [u64, i32, vp]
+    L.orc_smallrng_bitflag_picks.argtypes = [u64, u64, i32, i32, vp]
+    L.orc_smallrng_ranges.argtypes = [u64, i32, vp, vp]
+    _lib = L
+    return L
+
+
+# ---- convenience wrappers -------------------------------------------------------------------------------
+FDO_INFO_FIELDS = ["phase", "current_player", "game_type", "card_index", "n_tricks", "team_tag", "wedding_player", "solved_idx",
+                   "re_players", "re_lowest", "contra_lowest", "turns_without", "ann_start", "n_announcements", "current_allowed"]
+
+
+class Fdo:
+    """Handle on one oracle rs-full-doko state."""
+
+    def __init__(self, L, handle):
+        self.L, self.h = L, C.c_void_p(handle)
+
+    @classmethod
+    def from_hands(cls, L, hands, start):
+        arr = (C.c_uint64 * 4)(*hands)
+        return cls(L, L.orc_fdo_new(arr, start))
+
+    @classmethod
+    def new_game_philox(cls, L, seed, unit, epoch=0):
+        return cls(L, L.orc_fdo_new_game_philox(seed, unit, epoch))
+
+    @classmethod
+    def from_dk_state(cls, L, rec):
+        buf = np.ascontiguousarray(rec).tobytes()
+        h = L.orc_fdo_import(C.c_char_p(buf))
+        if not h:
+            raise RuntimeError(L.orc_last_error().decode())
+        return cls(L, h)
+
+    def clone(self):
+        return Fdo(self.L, self.L.orc_fdo_clone(self.h))
+
+    def __del__(self):
+        try:
+            self.L.orc_fdo_free(self.h)
+        except Exception:
+            pass
+
+    def play(self, action):
+        if self.L.orc_fdo_play(self.h, action):
+            raise RuntimeError(self.L.orc_last_error().decode())
+
+    def allowed(self):
+        return int(self.L.orc_fdo_allowed(self.h))
+
+    def info(self):
+        o = (C.c_int32 * 36)()
+        self.L.orc_fdo_info(self.h, o)
+        o = list(o)
+        d = dict(zip(FDO_INFO_FIELDS, o[:15]))
+        d["eyes"], d["num_tricks"], d["points"] = o[15:19], o[19:23], o[23:27]
+        d["n_play_actions"], d["is_solo"], d["re_eyes"], d["kontra_eyes"], d["re_points"], d["kontra_points"] = o[27:33]
+        return d
+
+    def hands(self):
+        o = (C.c_uint64 * 4)()
+        self.L.orc_fdo_hands(self.h, o)
+        return [int(x) for x in o]
+
+    def tricks(self):
+        o = (C.c_int32 * 72)()
+        self.L.orc_fdo_tricks(self.h, o)
+        return np.array(o, dtype=np.int32).reshape(12, 6)
+
+    def additional(self):
+        o = (C.c_int32 * 8)()
+        self.L.orc_fdo_additional(self.h, o)
+        return list(o)
+
+    def encode_pi(self):
+        o = (C.c_int64 * 311)()
+        if self.L.orc_fdo_encode_pi(self.h, o):
+            raise RuntimeError(self.L.orc_last_error().decode())
+        return np.array(o, dtype=np.int64)
+
+    def export(self):
+        rec = np.zeros(1, dtype=DK_STATE_DTYPE)
+        self.L.orc_fdo_export(self.h, rec.ctypes.data_as(C.c_void_p))
+        return rec[0]
+
+    def random_step(self, seed, unit, epoch=0, with_announcements=True, ann_ordinal=0):
+        return self.L.orc_fdo_random_step_philox(self.h, seed, unit, epoch, int(with_announcements), ann_ordinal)
+
+    def card_matching(self, seed, unit, sample, epoch=0):
+        hands = (C.c_uint64 * 4)()
+        res = (C.c_uint8 * 4)()
+        st = self.L.orc_fdo_card_matching_philox(self.h, seed, unit, sample, epoch, hands, res)
+        return st, [int(x) for x in hands], list(res)
+
+    def is_consistent(self, hands, res):
+        return self.L.orc_fdo_is_consistent(self.h, (C.c_uint64 * 4)(*hands), (C.c_uint8 * 4)(*res))
+
+    def rollout(self, seed, unit, rollout, epoch=0, with_announcements=False):
+        pts = (C.c_int32 * 4)()
+        steps = C.c_uint32()
+        self.L.orc_fdo_random_rollout_philox(self.h, seed, unit, rollout, epoch, int(with_announcements), pts, C.byref(steps))
+        return list(pts), steps.value
+
+
+DOKO_INFO_FIELDS = ["phase", "current_player", "trick_index", "team_tag", "wedding_player", "solved_idx", "re_players"]
+
+
+class Doko:
+    """Handle on one oracle rs-doko state."""
+
+    def __init__(self, L, handle):
+        self.L, self.h = L, C.c_void_p(handle)
+
+    @classmethod
+    def from_hands(cls, L, hands, start):
+        return cls(L, L.orc_doko_new((C.c_uint64 * 4)(*hands), start))
+
+    @classmethod
+    def new_game_philox(cls, L, seed, unit, epoch=0):
+        return cls(L, L.orc_doko_new_game_philox(seed, unit, epoch))
+
+    def __del__(self):
+        try:
+            self.L.orc_doko_free(self.h)
+        except Exception:
+            pass
+
+    def play(self, action):
+        if self.L.orc_doko_play(self.h, action):
+            raise RuntimeError(self.L.orc_last_error().decode())
+
+    def allowed(self):
+        return int(self.L.orc_doko_allowed(self.h))
+
+    def info(self):
+        o = (C.c_int32 * 21)()
+        self.L.orc_doko_info(self.h, o)
+        o = list(o)
+        d = dict(zip(DOKO_INFO_FIELDS, o[:7]))
+        d["eyes"], d["num_tricks"], d["points"], d["n_play_actions"], d["start_player"] = o[7:11], o[11:15], o[15:19], o[19], o[20]
+        return d
+
+    def hands(self):
+        o = (C.c_uint64 * 4)()
+        self.L.orc_doko_hands(self.h, o)
+        return [int(x) for x in o]
+
+    def encode(self, with_reservations=False):
+        o = (C.c_int64 * 114)()
+        n = self.L.orc_doko_encode(self.h, int(with_reservations), o)
+        return np.array(o[:n], dtype=np.int64)
+
+    def export(self):
+        rec = np.zeros(1, dtype=DK_STATE_DTYPE)
+        self.L.orc_doko_export(self.h, rec.ctypes.data_as(C.c_void_p))
+        return rec[0]
+
+    def random_step(self, seed, unit, epoch=0):
+        return self.L.orc_doko_random_step_philox(self.h, seed, unit, epoch)
+
+
+def playout_philox(L, engine, n, seed, first_id=0, epoch=0, with_announcements=True, n_threads=0, want_aux=False, trace_stride=0):
+    """Bulk oracle playouts from fresh Philox deals.  Returns dict(points, steps, aux, trace, seconds)."""
+    points = np.zeros((n, 4), dtype=np.int32)
+    steps = np.zeros(n, dtype=np.uint32)
+    aux = np.zeros((n, 8), dtype=np.int32) if want_aux else None
+    trace = np.zeros((n, trace_stride), dtype=np.uint8) if trace_stride else None
+    sec = L.orc_playout_philox(engine, int(with_announcements), seed, epoch, first_id, n, n_threads,
+                               points.ctypes.data_as(C.c_void_p), steps.ctypes.data_as(C.c_void_p),
+                               aux.ctypes.data_as(C.c_void_p) if want_aux else None,
+                               trace.ctypes.data_as(C.c_void_p) if trace_stride else None, trace_stride)
+    return dict(points=points, steps=steps, aux=aux, trace=trace, seconds=sec)
