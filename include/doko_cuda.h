@@ -25,6 +25,12 @@
 extern "C" {
 #endif
 
+#if defined(__GNUC__)
+#define DK_API __attribute__((visibility("default")))
+#else
+#define DK_API
+#endif
+
 #define DK_VERSION_MAJOR 0
 #define DK_VERSION_MINOR 1
 
@@ -110,7 +116,7 @@ typedef struct dk_state {
     uint32_t meta;              /* 124: bits 0-1 phase | 2-3 current seat | 4-5 game start seat | 6-9 game type |
                                  *      10-11 team tag | 12-13 wedding seat | 14-15 solved_trick_index | 16-19 re seats mask |
                                  *      20-22 re lowest call | 23-25 kontra lowest call | 26-28 turns without call |
-                                 *      29-30 start seat of the running announcement round | 31 last-trick winner card is ♣J */
+                                 *      29-30 start seat of the running announcement round | 31 reserved (0) */
 } dk_state;
 
 /* Observation layouts for dk_encode. */
@@ -140,21 +146,21 @@ typedef struct dk_rng {
 } dk_rng;
 
 /* ---- context ------------------------------------------------------------------------------- */
-dk_status dk_init(int device, dk_ctx** out);
-dk_status dk_destroy(dk_ctx* ctx);
-const char* dk_last_error(const dk_ctx* ctx); /* message of the last failing call on this context */
-const char* dk_version(void);
-dk_status dk_device_info(const dk_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, size_t* total_mem);
-dk_status dk_synchronize(dk_ctx* ctx, dk_stream stream);
+DK_API dk_status dk_init(int device, dk_ctx** out);
+DK_API dk_status dk_destroy(dk_ctx* ctx);
+DK_API const char* dk_last_error(const dk_ctx* ctx); /* message of the last failing call on this context */
+DK_API const char* dk_version(void);
+DK_API dk_status dk_device_info(const dk_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, size_t* total_mem);
+DK_API dk_status dk_synchronize(dk_ctx* ctx, dk_stream stream);
 /* Number of kernels this library has launched on this context since dk_init (bench.py's gpu_launches). */
-uint64_t dk_launch_count(const dk_ctx* ctx);
+DK_API uint64_t dk_launch_count(const dk_ctx* ctx);
 
 /* ---- game construction -----------------------------------------------------------------------
  * replaces FdoState::new_game (rs-full-doko/src/state/state.rs:169-178) /
  *          DoState::new_game  (rs-doko/src/state/state.rs:159-168): start seat, then a 48-card shuffle. */
-dk_status dk_new_games(dk_ctx* ctx, int engine, size_t n, const dk_rng* rng, dk_state* out /*[dev] n*/, dk_stream stream);
+DK_API dk_status dk_new_games(dk_ctx* ctx, int engine, size_t n, const dk_rng* rng, dk_state* out /*[dev] n*/, dk_stream stream);
 /* replaces new_game_from_hand_and_start_player (rs-full-doko/src/state/state.rs:125-166) */
-dk_status dk_from_deals(dk_ctx* ctx, int engine, size_t n, const uint64_t* hands /*[dev] n*4*/,
+DK_API dk_status dk_from_deals(dk_ctx* ctx, int engine, size_t n, const uint64_t* hands /*[dev] n*4*/,
                         const uint8_t* start /*[dev] n*/, dk_state* out /*[dev] n*/, dk_stream stream);
 
 /* ---- transition --------------------------------------------------------------------------------
@@ -163,16 +169,16 @@ dk_status dk_from_deals(dk_ctx* ctx, int engine, size_t n, const uint64_t* hands
  *          and AzEnvState::allowed_actions_by_action_index (rs-doko-alpha-zero/src/env/env_state.rs:20-24);
  *          rs-doko: calculate_allowed_actions_in_normal_game (rs-doko/src/action/allowed_actions.rs:131-198).
  * A finished game yields mask 0. */
-dk_status dk_legal_mask(dk_ctx* ctx, int engine, size_t n, const dk_state* states /*[dev]*/, uint64_t* mask_out /*[dev] n*/,
+DK_API dk_status dk_legal_mask(dk_ctx* ctx, int engine, size_t n, const dk_state* states /*[dev]*/, uint64_t* mask_out /*[dev] n*/,
                         dk_stream stream);
 /* replaces FdoState::play_action (rs-full-doko/src/state/state.rs:208-358) / McEnvState::by_action /
  *          AzEnvState::take_action_by_action_index; rs-doko: DoState::play_action (rs-doko/src/state/state.rs:189-309).
  * An illegal action (the reference would panic) sets err_out[i] != 0 and leaves state i unchanged. */
-dk_status dk_apply(dk_ctx* ctx, int engine, size_t n, dk_state* states /*[dev] in/out*/, const uint8_t* action_idx /*[dev] n*/,
+DK_API dk_status dk_apply(dk_ctx* ctx, int engine, size_t n, dk_state* states /*[dev] in/out*/, const uint8_t* action_idx /*[dev] n*/,
                    uint32_t flags, uint8_t* err_out /*[dev] n, may be NULL*/, dk_stream stream);
 /* replaces McEnvState::{is_terminal, rewards_or_none} (rs-doko-mcts/src/env/envs/env_state_full_doko.rs:75-79,191-196):
  * done_out[i] = phase == Finished; points_out[i] = player_points (0 when not finished). */
-dk_status dk_terminal(dk_ctx* ctx, int engine, size_t n, const dk_state* states /*[dev]*/, uint8_t* done_out /*[dev] n*/,
+DK_API dk_status dk_terminal(dk_ctx* ctx, int engine, size_t n, const dk_state* states /*[dev]*/, uint8_t* done_out /*[dev] n*/,
                       int32_t* points_out /*[dev] n*4*/, dk_stream stream);
 
 /* ---- observation encode --------------------------------------------------------------------------
@@ -180,11 +186,11 @@ dk_status dk_terminal(dk_ctx* ctx, int engine, size_t n, const dk_state* states 
  *          encode_state_pi(state, state.observation_for_current_player()); rs-doko: encode_state[_with_reservations].
  * Row i is written at out + i*row_stride (in elements, >= layout length); batch-major like the reference's
  * flattened Vec<i64> (rs-doko-alpha-zero/src/alpha_zero/batch_processor/network_batch_processor.rs:85-91). */
-dk_status dk_encode(dk_ctx* ctx, int layout, size_t n, const dk_state* states /*[dev]*/, int64_t* out /*[dev]*/,
+DK_API dk_status dk_encode(dk_ctx* ctx, int layout, size_t n, const dk_state* states /*[dev]*/, int64_t* out /*[dev]*/,
                     size_t row_stride, dk_stream stream);
 /* One lock-step self-play env step: legal mask -> one Philox draw -> play_action -> encode_state_pi of the new
  * state (self_play.rs:76-190 without the NN).  action_out may be NULL. */
-dk_status dk_step_random_encode(dk_ctx* ctx, size_t n, dk_state* states /*[dev] in/out*/, const dk_rng* rng, uint32_t flags,
+DK_API dk_status dk_step_random_encode(dk_ctx* ctx, size_t n, dk_state* states /*[dev] in/out*/, const dk_rng* rng, uint32_t flags,
                                 int64_t* obs_out /*[dev]*/, size_t row_stride, uint8_t* action_out /*[dev] n*/,
                                 dk_stream stream);
 
@@ -194,11 +200,11 @@ dk_status dk_step_random_encode(dk_ctx* ctx, size_t n, dk_state* states /*[dev] 
  *          env_state_doko.rs:150-169).  states == NULL plays fresh games dealt from the stream
  *          (new_game + playout fused on-chip).  points_out[i] = player_points; steps_out[i] = number of
  *          play_action calls ("game steps"); either may be NULL. */
-dk_status dk_playout(dk_ctx* ctx, int engine, uint32_t flags, size_t n, const dk_state* states /*[dev] or NULL*/,
+DK_API dk_status dk_playout(dk_ctx* ctx, int engine, uint32_t flags, size_t n, const dk_state* states /*[dev] or NULL*/,
                      const dk_rng* rng, int32_t* points_out /*[dev] n*4*/, uint32_t* steps_out /*[dev] n*/,
                      dk_stream stream);
 /* Same, results copied to HOST buffers inside the call (what a plain Rust slice caller binds). */
-dk_status dk_playout_host(dk_ctx* ctx, int engine, uint32_t flags, size_t n, const dk_state* states_host /*[host] or NULL*/,
+DK_API dk_status dk_playout_host(dk_ctx* ctx, int engine, uint32_t flags, size_t n, const dk_state* states_host /*[host] or NULL*/,
                           const dk_rng* rng, int32_t* points_out_host /*[host] n*4*/, uint32_t* steps_out_host /*[host] n*/);
 
 /* ---- determinization ---------------------------------------------------------------------------------
@@ -207,13 +213,13 @@ dk_status dk_playout_host(dk_ctx* ctx, int engine, uint32_t flags, size_t n, con
  * For info-state i and sample s (unit = first_id + i, unit_hi = s):
  *   hands_out[(i*S+s)*4 + seat], reservations_out[(i*S+s)*4 + seat] (DK_RES_* by ABSOLUTE seat, DK_RES_NONE if the
  *   seat has not declared yet), status_out[i*S+s] != 0 for a dead end (the reference would panic). */
-dk_status dk_determinize(dk_ctx* ctx, int engine, size_t n_info, size_t samples_per_info, const dk_state* states /*[dev]*/,
+DK_API dk_status dk_determinize(dk_ctx* ctx, int engine, size_t n_info, size_t samples_per_info, const dk_state* states /*[dev]*/,
                          const dk_rng* rng, uint64_t* hands_out /*[dev]*/, uint8_t* reservations_out /*[dev]*/,
                          uint8_t* status_out /*[dev]*/, dk_stream stream);
 /* Leaf-parallel rollouts (new design over random_rollout): for leaf i run R rollouts (unit = first_id + i,
  * unit_hi = r), each first determinized when `determinize` != 0, then played with the _no_announcement policy.
  * point_sum_out[i*4 + seat] = exact integer sum of player_points over the R rollouts. */
-dk_status dk_leaf_rollouts(dk_ctx* ctx, size_t n_leaves, size_t rollouts_per_leaf, int determinize,
+DK_API dk_status dk_leaf_rollouts(dk_ctx* ctx, size_t n_leaves, size_t rollouts_per_leaf, int determinize,
                            const dk_state* states /*[dev]*/, const dk_rng* rng, int64_t* point_sum_out /*[dev] n_leaves*4*/,
                            dk_stream stream);
 
@@ -221,10 +227,10 @@ dk_status dk_leaf_rollouts(dk_ctx* ctx, size_t n_leaves, size_t rollouts_per_lea
  * replaces the per-determinization fuse of PolicyFusion* (rs-doko-py-bridge/src/compare_impi/policy_fusion.rs:18-123):
  * integer sums over ranks, order-independent and bit-reproducible.  NCCL is loaded lazily (dlopen). */
 typedef struct dk_nccl_id { char bytes[128]; } dk_nccl_id;
-dk_status dk_comm_unique_id(dk_ctx* ctx, dk_nccl_id* out);
-dk_status dk_comm_init(dk_ctx* ctx, int n_ranks, int rank, const dk_nccl_id* id);
-dk_status dk_comm_destroy(dk_ctx* ctx);
-dk_status dk_allreduce_root_stats(dk_ctx* ctx, size_t n_values, int64_t* values /*[dev] in/out, sum over ranks*/,
+DK_API dk_status dk_comm_unique_id(dk_ctx* ctx, dk_nccl_id* out);
+DK_API dk_status dk_comm_init(dk_ctx* ctx, int n_ranks, int rank, const dk_nccl_id* id);
+DK_API dk_status dk_comm_destroy(dk_ctx* ctx);
+DK_API dk_status dk_allreduce_root_stats(dk_ctx* ctx, size_t n_values, int64_t* values /*[dev] in/out, sum over ranks*/,
                                   dk_stream stream);
 
 #ifdef __cplusplus

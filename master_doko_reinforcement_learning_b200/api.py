@@ -1,0 +1,162 @@
+"""ctypes binding of libdoko_cuda.so + thin torch-tensor helpers.  Plumbing only: all game logic runs in CUDA."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _build
+
+DK_DOKO, DK_FDO = 0, 1
+DK_PLAYOUT_WITH_ANNOUNCEMENTS = 1
+DK_APPLY_SKIP_SINGLE = 1
+DK_LAYOUT_DO110, DK_LAYOUT_DO114, DK_LAYOUT_FDO_PI311 = 0, 1, 2
+OBS_LEN = {DK_LAYOUT_DO110: 110, DK_LAYOUT_DO114: 114, DK_LAYOUT_FDO_PI311: 311}
+STATUS = {0: "DK_OK", 1: "DK_ERR_INVALID_ARGUMENT", 2: "DK_ERR_CUDA", 3: "DK_ERR_NO_DEVICE", 4: "DK_ERR_NCCL", 5: "DK_ERR_UNSUPPORTED"}
+
+# numpy view of include/doko_cuda.h:dk_state (128 bytes)
+DK_STATE_DTYPE = np.dtype([("hands", "<u8", 4), ("cards", "u1", 48), ("announcements", "<u2", 12), ("reservations", "u1", 4),
+                           ("tricks", "<u4"), ("eyes", "u1", 4), ("num_tricks", "<u2"), ("card_index", "u1"),
+                           ("n_reservations", "u1"), ("points", "i1", 4), ("meta", "<u4")])
+assert DK_STATE_DTYPE.itemsize == 128
+
+
+class DokoCudaError(RuntimeError):
+    pass
+
+
+class DkRng(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("first_id", C.c_uint64), ("epoch", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+def library_path():
+    return _build.LIB_PATH
+
+
+_LIB = None
+
+
+def load_library():
+    """dlopen libdoko_cuda.so.  Fails loudly when it is missing — there is no fallback implementation."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not os.path.exists(path):
+        raise DokoCudaError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                            "(needs nvcc); master_doko_reinforcement_learning_b200 has no CPU fallback")
+    L = C.CDLL(path)
+    vp, sz, u32, u64, i32 = C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint64, C.c_int
+    L.dk_version.restype = C.c_char_p
+    L.dk_last_error.restype = C.c_char_p
+    L.dk_last_error.argtypes = [vp]
+    L.dk_init.argtypes = [i32, C.POINTER(vp)]
+    L.dk_destroy.argtypes = [vp]
+    L.dk_device_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(sz)]
+    L.dk_synchronize.argtypes = [vp, vp]
+    L.dk_launch_count.restype = u64
+    L.dk_launch_count.argtypes = [vp]
+    L.dk_playout.argtypes = [vp, i32, u32, sz, vp, C.POINTER(DkRng), vp, vp, vp]
+    L.dk_playout_host.argtypes = [vp, i32, u32, sz, vp, C.POINTER(DkRng), vp, vp]
+    for name, args in (
+        ("dk_new_games", [vp, i32, sz, C.POINTER(DkRng), vp, vp]),
+        ("dk_from_deals", [vp, i32, sz, vp, vp, vp, vp]),
+        ("dk_legal_mask", [vp, i32, sz, vp, vp, vp]),
+        ("dk_apply", [vp, i32, sz, vp, vp, u32, vp, vp]),
+        ("dk_terminal", [vp, i32, sz, vp, vp, vp, vp]),
+        ("dk_encode", [vp, i32, sz, vp, vp, sz, vp]),
+        ("dk_step_random_encode", [vp, sz, vp, C.POINTER(DkRng), u32, vp, sz, vp, vp]),
+        ("dk_determinize", [vp, i32, sz, sz, vp, C.POINTER(DkRng), vp, vp, vp, vp]),
+        ("dk_leaf_rollouts", [vp, sz, sz, i32, vp, C.POINTER(DkRng), vp, vp]),
+        ("dk_comm_unique_id", [vp, vp]),
+        ("dk_comm_init", [vp, i32, i32, vp]),
+        ("dk_comm_destroy", [vp]),
+        ("dk_allreduce_root_stats", [vp, sz, vp, vp]),
+    ):
+        if hasattr(L, name):
+            getattr(L, name).argtypes = args
+    _LIB = L
+    return L
+
+
+def _ptr(t):
+    """Device/host pointer of a torch tensor, numpy array or None."""
+    if t is None:
+        return None
+    if isinstance(t, np.ndarray):
+        return t.ctypes.data_as(C.c_void_p)
+    return C.c_void_p(t.data_ptr())
+
+
+class DokoCuda:
+    """One context per process/GPU (dk_init).  Methods mirror the C ABI one to one."""
+
+    def __init__(self, device=0):
+        self.L = load_library()
+        self.ctx = C.c_void_p()
+        st = self.L.dk_init(int(device), C.byref(self.ctx))
+        if st != 0:
+            raise DokoCudaError(f"dk_init(device={device}) failed with {STATUS.get(st, st)}: an sm_100 (B200) GPU is required; "
+                                "there is no CPU fallback")
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.L.dk_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, st, what):
+        if st != 0:
+            raise DokoCudaError(f"{what}: {STATUS.get(st, st)}: {self.L.dk_last_error(self.ctx).decode()}")
+
+    @staticmethod
+    def rng(seed, first_id=0, epoch=0):
+        return DkRng(int(seed) & 0xFFFFFFFFFFFFFFFF, int(first_id), int(epoch), 0)
+
+    @staticmethod
+    def _stream():
+        import torch
+
+        # torch's default stream is the legacy NULL stream; the C ABI reserves NULL for "the context's own stream",
+        # so pass the explicit cudaStreamLegacy handle (0x1) to stay ordered with torch work and torch CUDA events.
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream or 1)
+
+    def device_info(self):
+        sm, ma, mi, mem = C.c_int(), C.c_int(), C.c_int(), C.c_size_t()
+        self._check(self.L.dk_device_info(self.ctx, C.byref(sm), C.byref(ma), C.byref(mi), C.byref(mem)), "dk_device_info")
+        return dict(sm_count=sm.value, cc=(ma.value, mi.value), total_mem=mem.value)
+
+    def launch_count(self):
+        return int(self.L.dk_launch_count(self.ctx))
+
+    def synchronize(self, stream=None):
+        self._check(self.L.dk_synchronize(self.ctx, stream), "dk_synchronize")
+
+    # ---- playouts ----------------------------------------------------------------------------------------
+    def playout(self, engine, n, rng, states=None, flags=0, points_out=None, steps_out=None, stream=None):
+        """Device-resident playouts (dk_playout).  points_out int32 [n,4], steps_out uint32/int32 [n] (torch, cuda)."""
+        import torch
+
+        dev = torch.device("cuda", self.device)
+        if points_out is None:
+            points_out = torch.empty((n, 4), dtype=torch.int32, device=dev)
+        if steps_out is None:
+            steps_out = torch.empty((n,), dtype=torch.int32, device=dev)
+        self._check(self.L.dk_playout(self.ctx, engine, flags, n, _ptr(states), C.byref(rng), _ptr(points_out), _ptr(steps_out),
+                                      stream if stream is not None else self._stream()), "dk_playout")
+        return points_out, steps_out
+
+    def playout_host(self, engine, n, rng, states=None, flags=0, points_out=None, steps_out=None):
+        """Host-buffer playouts (dk_playout_host): numpy in/out, copies inside the call."""
+        if points_out is None:
+            points_out = np.empty((n, 4), dtype=np.int32)
+        if steps_out is None:
+            steps_out = np.empty((n,), dtype=np.uint32)
+        self._check(self.L.dk_playout_host(self.ctx, engine, flags, n, _ptr(states), C.byref(rng), _ptr(points_out), _ptr(steps_out)),
+                    "dk_playout_host")
+        return points_out, steps_out

@@ -1,0 +1,162 @@
+// cabi.cu — the extern "C" boundary of libdoko_cuda.so (include/doko_cuda.h).
+// No torch types, no CPU fallback: every compute entry point launches sm_100a kernels or fails with a status code.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+
+#include "../../include/doko_cuda.h"
+#include "kernels.cuh"
+
+struct dk_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;   // the context's own stream
+    uint64_t launches = 0;
+    std::string last_error;
+    int sm_count = 0, cc_major = 0, cc_minor = 0;
+    size_t total_mem = 0;
+    // scratch for the *_host entry points
+    void* d_scratch = nullptr;
+    size_t d_scratch_bytes = 0;
+    // NCCL (loaded lazily)
+    void* nccl_lib = nullptr;
+    void* nccl_comm = nullptr;
+    int nccl_ranks = 0, nccl_rank = 0;
+};
+
+namespace {
+
+dk_status fail(dk_ctx* ctx, dk_status st, const std::string& msg) {
+    if (ctx) ctx->last_error = msg;
+    return st;
+}
+#define DK_CUDA(ctx, call)                                                                              \
+    do {                                                                                                \
+        cudaError_t e__ = (call);                                                                       \
+        if (e__ != cudaSuccess)                                                                         \
+            return fail((ctx), DK_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));       \
+    } while (0)
+
+cudaStream_t pick_stream(dk_ctx* ctx, dk_stream s) { return s ? (cudaStream_t)s : ctx->stream; }
+
+dk::RngParams to_params(const dk_rng* r) {
+    dk::RngParams p;
+    p.seed_lo = (uint32_t)r->seed; p.seed_hi = (uint32_t)(r->seed >> 32); p.first_id = r->first_id; p.epoch = r->epoch;
+    return p;
+}
+
+dk_status ensure_scratch(dk_ctx* ctx, size_t bytes) {
+    if (ctx->d_scratch_bytes >= bytes) return DK_OK;
+    if (ctx->d_scratch) { cudaFree(ctx->d_scratch); ctx->d_scratch = nullptr; ctx->d_scratch_bytes = 0; }
+    DK_CUDA(ctx, cudaMalloc(&ctx->d_scratch, bytes));
+    ctx->d_scratch_bytes = bytes;
+    return DK_OK;
+}
+
+dk_status check_launch(dk_ctx* ctx, const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(ctx, DK_ERR_CUDA, std::string(what) + " launch: " + cudaGetErrorString(e));
+    ctx->launches++;
+    return DK_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* dk_version(void) { return "doko_cuda 0.1 (sm_100a)"; }
+
+dk_status dk_init(int device, dk_ctx** out) {
+    if (!out) return DK_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0 || device < 0 || device >= count) return DK_ERR_NO_DEVICE;
+    dk_ctx* ctx = new (std::nothrow) dk_ctx();
+    if (!ctx) return DK_ERR_INVALID_ARGUMENT;
+    ctx->device = device;
+    cudaDeviceProp prop;
+    if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return DK_ERR_NO_DEVICE; }
+    ctx->sm_count = prop.multiProcessorCount; ctx->cc_major = prop.major; ctx->cc_minor = prop.minor; ctx->total_mem = prop.totalGlobalMem;
+    if (prop.major != 10) {   // the fatbin only holds sm_100a code
+        delete ctx;
+        return DK_ERR_NO_DEVICE;
+    }
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return DK_ERR_CUDA; }
+    *out = ctx;
+    return DK_OK;
+}
+
+dk_status dk_destroy(dk_ctx* ctx) {
+    if (!ctx) return DK_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(ctx->device);
+    if (ctx->d_scratch) cudaFree(ctx->d_scratch);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return DK_OK;
+}
+
+const char* dk_last_error(const dk_ctx* ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
+
+dk_status dk_device_info(const dk_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, size_t* total_mem) {
+    if (!ctx) return DK_ERR_INVALID_ARGUMENT;
+    if (sm_count) *sm_count = ctx->sm_count;
+    if (cc_major) *cc_major = ctx->cc_major;
+    if (cc_minor) *cc_minor = ctx->cc_minor;
+    if (total_mem) *total_mem = ctx->total_mem;
+    return DK_OK;
+}
+
+dk_status dk_synchronize(dk_ctx* ctx, dk_stream stream) {
+    if (!ctx) return DK_ERR_INVALID_ARGUMENT;
+    DK_CUDA(ctx, cudaSetDevice(ctx->device));
+    DK_CUDA(ctx, cudaStreamSynchronize(pick_stream(ctx, stream)));
+    return DK_OK;
+}
+
+uint64_t dk_launch_count(const dk_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+dk_status dk_playout(dk_ctx* ctx, int engine, uint32_t flags, size_t n, const dk_state* states, const dk_rng* rng,
+                     int32_t* points_out, uint32_t* steps_out, dk_stream stream) {
+    if (!ctx || !rng) return DK_ERR_INVALID_ARGUMENT;
+    if (n == 0) return DK_OK;
+    DK_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = pick_stream(ctx, stream);
+    dk::RngParams rp = to_params(rng);
+    unsigned grid = (unsigned)((n + dk::PLAYOUT_THREADS - 1) / dk::PLAYOUT_THREADS);
+    if (engine == DK_FDO && states == nullptr) {
+        if (flags & DK_PLAYOUT_WITH_ANNOUNCEMENTS)
+            dk::fdo_playout_fresh_kernel<true><<<grid, dk::PLAYOUT_THREADS, 0, s>>>(rp, (uint64_t)n, (int4*)points_out, steps_out);
+        else
+            dk::fdo_playout_fresh_kernel<false><<<grid, dk::PLAYOUT_THREADS, 0, s>>>(rp, (uint64_t)n, (int4*)points_out, steps_out);
+        return check_launch(ctx, "fdo_playout_fresh_kernel");
+    }
+    return fail(ctx, DK_ERR_UNSUPPORTED, "dk_playout: this engine/state combination is not built yet");
+}
+
+dk_status dk_playout_host(dk_ctx* ctx, int engine, uint32_t flags, size_t n, const dk_state* states_host, const dk_rng* rng,
+                          int32_t* points_out_host, uint32_t* steps_out_host) {
+    if (!ctx || !rng) return DK_ERR_INVALID_ARGUMENT;
+    if (n == 0) return DK_OK;
+    DK_CUDA(ctx, cudaSetDevice(ctx->device));
+    size_t b_states = states_host ? n * sizeof(dk_state) : 0, b_pts = n * 16, b_steps = n * 4;
+    dk_status st = ensure_scratch(ctx, b_states + b_pts + b_steps);
+    if (st != DK_OK) return st;
+    char* base = (char*)ctx->d_scratch;
+    dk_state* d_states = states_host ? (dk_state*)base : nullptr;
+    int32_t* d_pts = (int32_t*)(base + b_states);
+    uint32_t* d_steps = (uint32_t*)(base + b_states + b_pts);
+    if (states_host) DK_CUDA(ctx, cudaMemcpyAsync(d_states, states_host, b_states, cudaMemcpyHostToDevice, ctx->stream));
+    st = dk_playout(ctx, engine, flags, n, d_states, rng, d_pts, d_steps, ctx->stream);
+    if (st != DK_OK) return st;
+    if (points_out_host) DK_CUDA(ctx, cudaMemcpyAsync(points_out_host, d_pts, b_pts, cudaMemcpyDeviceToHost, ctx->stream));
+    if (steps_out_host) DK_CUDA(ctx, cudaMemcpyAsync(steps_out_host, d_steps, b_steps, cudaMemcpyDeviceToHost, ctx->stream));
+    DK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return DK_OK;
+}
+
+}  // extern "C"

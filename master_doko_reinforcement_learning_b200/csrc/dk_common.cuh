@@ -1,0 +1,167 @@
+// dk_common.cuh — shared device helpers for the B200 Doppelkopf kernels: Philox4x32-10, bit select,
+// card attribute arithmetic.  Everything is integer / bitwise; no tensor-core path exists or is wanted
+// (the hot path is integer-issue bound).
+//
+// The functions are __host__ __device__ so that tests/hostsim can compile the SAME per-thread logic with
+// g++ and run it on the CPU of the build container (which has no GPU).  That simulator is test
+// infrastructure; the product library (libdoko_cuda.so) only ever launches the __global__ kernels.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define DK_HD __host__ __device__ __forceinline__
+#define DK_D __device__ __forceinline__
+#else
+#define DK_HD inline
+#define DK_D inline
+#endif
+
+namespace dk {
+
+// ---- intrinsics with host shims ------------------------------------------------------------------
+DK_HD uint32_t popc(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__popc(x);
+#else
+    return (uint32_t)__builtin_popcount(x);
+#endif
+}
+DK_HD uint32_t popcll(uint64_t x) {
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__popcll(x);
+#else
+    return (uint32_t)__builtin_popcountll(x);
+#endif
+}
+DK_HD uint32_t mulhi(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+    return __umulhi(a, b);
+#else
+    return (uint32_t)(((uint64_t)a * b) >> 32);
+#endif
+}
+DK_HD uint32_t ffs0(uint32_t x) {  // index of lowest set bit (x != 0)
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)(__ffs((int)x) - 1);
+#else
+    return (uint32_t)__builtin_ctz(x);
+#endif
+}
+DK_HD uint32_t ffs0ll(uint64_t x) {
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)(__ffsll((long long)x) - 1);
+#else
+    return (uint32_t)__builtin_ctzll(x);
+#endif
+}
+
+// ---- Philox4x32-10 ----------------------------------------------------------------------------------
+// Parity stream shared with the oracle (DESIGN.md "Philox parity contract"):
+//   counter = (unit_lo, unit_hi, site<<16 | block, epoch), key = (seed_lo, seed_hi);
+//   decision k of call-site class `site` inside one unit uses word (k & 3) of block (k >> 2),
+//   mapped onto n choices by idx = mulhi(word, n).
+enum Site : uint32_t {
+    SITE_DEAL = 0, SITE_RESERVATION = 1, SITE_ANNOUNCEMENT = 2, SITE_CARD = 3,
+    SITE_MATCH_CARD = 4, SITE_MATCH_RESERVATION = 5, SITE_ASSIGN = 6, SITE_STEP = 7
+};
+
+struct U4 { uint32_t x, y, z, w; };
+
+struct RngKey {
+    uint32_t seed_lo, seed_hi, unit_lo, unit_hi, epoch;
+};
+
+DK_HD U4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = mulhi(M0, c0), lo0 = M0 * c0;
+        uint32_t hi1 = mulhi(M1, c2), lo1 = M1 * c2;
+        uint32_t n0 = hi1 ^ c1 ^ k0;
+        uint32_t n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += W0; k1 += W1;
+    }
+    U4 o; o.x = c0; o.y = c1; o.z = c2; o.w = c3;
+    return o;
+}
+DK_HD U4 rng_block(const RngKey& k, uint32_t site, uint32_t block) {
+    return philox4x32_10(k.unit_lo, k.unit_hi, (site << 16) | block, k.epoch, k.seed_lo, k.seed_hi);
+}
+DK_HD uint32_t u4_word(const U4& b, uint32_t i) {  // dynamic word pick without local memory
+    uint32_t lo = (i & 1) ? b.y : b.x;
+    uint32_t hi = (i & 1) ? b.w : b.z;
+    return (i & 2) ? hi : lo;
+}
+
+// ---- rank select ---------------------------------------------------------------------------------------
+// Position of the k-th (0-based, counted from the LSB) set bit of a 32-bit mask; k < popc(x).
+// The reference picks MSB-first (rs-game-utils/src/bit_flag.rs:104-171: rank 0 = highest set bit), so
+// callers pass k = popc(x) - 1 - idx.
+DK_HD uint32_t select_lsb(uint32_t x, uint32_t k) {
+    uint32_t pos = 0, c;
+    c = popc(x & 0xFFFFu); if (k >= c) { k -= c; x >>= 16; pos += 16; }
+    c = popc(x & 0xFFu);   if (k >= c) { k -= c; x >>= 8;  pos += 8; }
+    c = popc(x & 0xFu);    if (k >= c) { k -= c; x >>= 4;  pos += 4; }
+    c = popc(x & 0x3u);    if (k >= c) { k -= c; x >>= 2;  pos += 2; }
+    c = x & 1u;            if (k >= c) { pos += 1; }
+    return pos;
+}
+// 24-bit card masks: three levels of 12/6/3 then two single-bit steps.
+DK_HD uint32_t select_lsb24(uint32_t x, uint32_t k) {
+    uint32_t pos = 0, c;
+    c = popc(x & 0xFFFu); if (k >= c) { k -= c; x >>= 12; pos += 12; }
+    c = popc(x & 0x3Fu);  if (k >= c) { k -= c; x >>= 6;  pos += 6; }
+    c = popc(x & 0x7u);   if (k >= c) { k -= c; x >>= 3;  pos += 3; }
+    c = x & 1u;           if (k >= c) { k -= c; x >>= 1;  pos += 1; }
+    c = x & 1u;           if (k >= c) { pos += 1; }
+    return pos;
+}
+// The reference's random pick: index idx counted from the MOST significant set bit.
+DK_HD uint32_t pick_msb_rank24(uint32_t mask, uint32_t idx) { return select_lsb24(mask, popc(mask) - 1u - idx); }
+
+// ---- card arithmetic ------------------------------------------------------------------------------------
+// card id c = suit*6 + rank; suits ♦0 ♥1 ♣2 ♠3; ranks 9,10,J,Q,K,A = 0..5 (rs-full-doko/src/card/cards.rs:7-36)
+DK_HD uint32_t card_suit(uint32_t c) { return (c * 43u) >> 8; }           // c / 6 for c < 24
+DK_HD uint32_t card_eyes_by_rank(uint32_t rank) { return (0xB432A0u >> (4u * rank)) & 15u; }  // 0,10,2,3,4,11 (card_to_eyes.rs:8-40)
+
+// Trump masks per FdoGameType (rs-full-doko/src/card/card_color_masks.rs:7-246); plain colours are the
+// natural suits minus the trumps (equivalent to card_to_color.rs:11-258, checked by tests/test_rules_tables.py).
+DK_HD uint32_t trump_mask_for_game_type(uint32_t gt) {
+    const uint32_t JACKS = (1u << 2) | (1u << 8) | (1u << 14) | (1u << 20);
+    const uint32_t QUEENS = (1u << 3) | (1u << 9) | (1u << 15) | (1u << 21);
+    const uint32_t H10 = 1u << 7;
+    const uint32_t JQ10 = JACKS | QUEENS | H10;
+    // suit trumps: all six cards of the suit (J/Q already trump; the ♥10 is trump anyway)
+    uint32_t m;
+    switch (gt) {
+        case 0: case 1: case 2: m = JQ10 | 0x00003Fu; break;   // Normal, Wedding, ♦-Solo
+        case 3: m = JQ10 | 0x000FC0u; break;                   // ♥-Solo
+        case 4: m = JQ10 | 0xFC0000u; break;                   // ♠-Solo (suit 3)
+        case 5: m = JQ10 | 0x03F000u; break;                   // ♣-Solo (suit 2)
+        case 6: m = 0u; break;                                 // Trumpless
+        case 7: m = QUEENS; break;                             // Queens-Solo
+        default: m = JACKS; break;                             // Jacks-Solo
+    }
+    return m;
+}
+// Mask of the cards that FOLLOW a trick led with card `first`:
+// trump lead → all trumps; plain lead → the cards of its suit that are not trump.
+DK_HD uint32_t follow_mask(uint32_t first_card, uint32_t trump) {
+    uint32_t suit_cards = 0x3Fu << (6u * card_suit(first_card));
+    return ((trump >> first_card) & 1u) ? trump : (suit_cards & ~trump);
+}
+// Strength of a card inside a trick.  `power(b) > power(a)` (strict) <=> is_greater_in_trick(b, a, colour, game_type)
+// (rs-full-doko/src/card/card_in_trick_logic.rs:17-141): trumps beat plain cards and are ordered by trump_to_rank
+// (:37-77), cards of the led plain colour are ordered by eyes (:135), anything else never wins.
+DK_HD uint32_t card_power(uint32_t c, uint32_t trump, uint32_t follow) {
+    uint32_t suit = card_suit(c), rank = c - 6u * suit;
+    uint32_t bit = 1u << c;
+    uint32_t so = suit ^ (suit >> 1);                       // ♦0 ♥1 ♠2 ♣3  (J/Q order ♦<♥<♠<♣)
+    uint32_t plain = (0x310020u >> (4u * rank)) & 15u;      // 9:0 10:2 K:1 A:3
+    uint32_t tp = rank == 2u ? 4u + so : (rank == 3u ? 8u + so : (c == 7u ? 12u : plain));
+    uint32_t cp = 1u + card_eyes_by_rank(rank);
+    return (trump & bit) ? 16u + tp : ((follow & bit) ? cp : 0u);
+}
+
+}  // namespace dk

@@ -1,0 +1,398 @@
+// fdo_rules.cuh — full-rules Doppelkopf (rs-full-doko) as a register-resident, thread-per-game program.
+//
+// Design (B200-first, not a translation of the reference's Vec/enum state):
+//   * The four hands live in FOUR 24-bit registers held in a ROTATING FRAME: frame index 0 is always the seat
+//     that leads the current trick, so inside the (unrolled) trick the seat to move is a compile-time register —
+//     no dynamic register indexing, no local memory.  One extra register `dup` marks card types whose two copies
+//     sit in the same hand (then copy B ⊆ copy A, rs-full-doko/src/hand/hand.rs:217-247).
+//   * All warp lanes execute card step (t,k) together (48 lock-step card steps, no divergent control flow).  The
+//     announcement protocol — the data-dependent part of full rules (SURVEY.md §7 "hard parts") — does not depend on
+//     WHICH cards are played, so it is replayed afterwards as a flat per-lane state machine
+//     (fdo_replay_announcements): first measured version interleaved it and ran at 17.7/32 active lanes.
+//   * Scoring inputs (eyes, tricks, Doppelkopf tricks, caught foxes, Karlchen) are accumulated while playing;
+//     the reference re-walks all 12 tricks at the end (rs-full-doko/src/stats/stats.rs:46-240).
+//   * Random decisions come from per-site Philox sub-streams so the card draws of trick t are the four words of
+//     ONE Philox block with static indices.
+#pragma once
+#include "dk_common.cuh"
+
+namespace dk {
+
+enum : uint32_t { TEAM_IN_RESERVATIONS = 0, TEAM_WEDDING_UNSOLVED = 1, TEAM_WEDDING_SOLVED = 2, TEAM_NO_WEDDING = 3 };
+enum : uint32_t { GT_NORMAL = 0, GT_WEDDING = 1 };
+enum : uint32_t { CARD_DA = 5, CARD_CJ = 14, CARD_CQ = 15 };
+
+// ---- announcements ------------------------------------------------------------------------------------------
+// Closed form of calc_allowed_announcements (rs-full-doko/src/announcement/calc_announcement.rs:51-228):
+// levels 0 none, 1 Re/Kontra, 2 No90, 3 No60, 4 No30, 5 Black; 6 = CounterReContra (only reachable through
+// hand-built states: action 33 always records ReContra, action/action.rs:297-299).
+// Returns the level the seat may call next (1..5), or 0 if its allowed set is empty (the seat is auto-skipped,
+// announcement.rs:156-165).  `m` = own team's lowest call, `e` = enemy team's, `c` = cards on hand,
+// `w` = solved_trick_index of a solved wedding else 0.  Both a regular Re/Kontra and the counter map to action 33.
+DK_HD uint32_t fdo_allowed_call(uint32_t c, uint32_t m, uint32_t e, uint32_t w) {
+    uint32_t ml = m == 6u ? 0u : m;                      // all_higher_than(Counter) = {Counter}: no regular level made
+    if (ml < 5u && c + ml + w >= 11u) return ml + 1u;    // exactly the next level (calc_announcement.rs:88-141)
+    // counter (:146-170): no regular call possible, enemy called a regular level, own team called nothing at all
+    if (e >= 1u && e <= 5u && m == 0u && c + e + w >= 11u) return 1u;
+    return 0u;
+}
+// Smallest hand size with which some seat of a team (own lowest m, enemy lowest e) could still call.
+DK_HD uint32_t fdo_min_cards_to_call(uint32_t m, uint32_t e, uint32_t w) {
+    uint32_t ml = m == 6u ? 0u : m;
+    uint32_t a = ml < 5u ? 11u - ml - w : 99u;
+    uint32_t b = (e >= 1u && e <= 5u && m == 0u) ? 11u - e - w : 99u;
+    return a < b ? a : b;
+}
+
+// ---- scoring ----------------------------------------------------------------------------------------------------
+// Closed form of FdoEndOfGameStats::calculate (stats/stats.rs:46-240) and its callees re_won (win_conditions/re_won.rs),
+// kontra_won, FdoBasicWinningPointsDetails::calculate (basic_points/basic_winning_points.rs:48-284),
+// FdoBasicDrawPointsDetails::calculate (basic_points/basic_draw_points.rs:27-174) and
+// FdoAdditionalPointsDetails (additional_points/additional_points.rs:57-127).
+// rl/kl: lowest calls (0..6); extras = (doko_re - doko_ko) + (fox_re - fox_ko) + (karl_re - karl_ko), ignored in a solo.
+// Returns re points; kontra points are written to *kontra_points.
+DK_HD int32_t fdo_score(uint32_t re_eyes, uint32_t re_tricks, uint32_t n_re_players, uint32_t rl, uint32_t kl, int32_t extras,
+                        int32_t* kontra_points) {
+    uint32_t ko_eyes = 240u - re_eyes;
+    bool re_all = re_tricks == 12u, ko_all = re_tricks == 0u;
+    uint32_t R = rl == 6u ? 1u : rl, K = kl == 6u ? 1u : kl;   // Counter counts as "Re/Kontra said"
+    bool re_won, ko_won;
+    if (R >= 2u) re_won = R == 5u ? re_all : re_eyes >= 121u + 30u * (R - 1u);          // 151 / 181 / 211 / all tricks
+    else if (K >= 2u) re_won = K == 5u ? !ko_all : re_eyes >= 150u - 30u * K;            // 90 / 60 / 30 / one trick
+    else re_won = re_eyes >= ((R == 0u && K == 1u) ? 120u : 121u);
+    if (K >= 2u) ko_won = K == 5u ? ko_all : ko_eyes >= 121u + 30u * (K - 1u);
+    else if (R >= 2u) ko_won = R == 5u ? !re_all : ko_eyes >= 150u - 30u * R;
+    else ko_won = ko_eyes >= ((R == 0u && K == 1u) ? 121u : 120u);
+    bool solo = n_re_players == 1u;
+    int32_t re_pts;
+    // (e)/(f): points for reaching 120/90/60/30 against the other side's No90/No60/No30/Black
+    int32_t re_reached = (int32_t)((re_eyes >= 120u && K >= 2u) + (re_eyes >= 90u && K >= 3u) + (re_eyes >= 60u && K >= 4u) + (re_eyes >= 30u && K >= 5u));
+    int32_t ko_reached = (int32_t)((ko_eyes >= 120u && R >= 2u) + (ko_eyes >= 90u && R >= 3u) + (ko_eyes >= 60u && R >= 4u) + (ko_eyes >= 30u && R >= 5u));
+    if (!re_won && !ko_won) {                            // draw: stats.rs:120-147
+        int32_t re_b = -(int32_t)((re_eyes < 90u) + (re_eyes < 60u) + (re_eyes < 30u)) +
+                       (int32_t)((ko_eyes < 90u) + (ko_eyes < 60u) + (ko_eyes < 30u)) + re_reached - ko_reached;
+        re_pts = re_b + (solo ? 0 : extras);
+    } else {
+        uint32_t loser = re_won ? ko_eyes : re_eyes;
+        bool winner_all = re_won ? re_all : ko_all;
+        int32_t w = 1 + (int32_t)((loser < 90u) + (loser < 60u) + (loser < 30u)) + (winner_all ? 1 : 0) + (R >= 1u ? 2 : 0) +
+                    (K >= 1u ? 2 : 0) + (R >= 2u ? (int32_t)R - 1 : 0) + (K >= 2u ? (int32_t)K - 1 : 0) + re_reached + ko_reached;
+        int32_t re_b = re_won ? w : -w;
+        int32_t x = solo ? 0 : extras - (re_won ? 0 : 1);  // "against the club queens" when Kontra wins (:77-82)
+        re_pts = re_b + x;
+    }
+    *kontra_points = -re_pts;
+    return solo ? 3 * re_pts : re_pts;                   // stats.rs:215-218
+}
+
+// ---- live game ------------------------------------------------------------------------------------------------------
+struct FdoLive {
+    uint32_t h0, h1, h2, h3;  // frame-relative hands ("at least one copy"), 24 bits
+    uint32_t dup;             // card types with both copies in one hand
+    uint32_t base;            // absolute seat of frame index 0
+    uint32_t eyes;            // 8 bits per absolute seat
+    uint32_t ntricks;         // 4 bits per absolute seat
+    uint32_t dkc;             // 4 bits per absolute seat: tricks with >= 40 eyes (Doppelkopf)
+    uint32_t foxes;           // up to two 5-bit records (1, seat that played ♦A : 2, seat that won it : 2)
+    uint32_t trump;           // trump mask of the game type
+    uint32_t gt;              // FdoGameType
+    uint32_t team_tag, re_mask, wed_seat, solved_idx;
+    uint32_t re_low, ko_low;  // lowest call per team (level codes)
+    uint32_t karl;            // last trick won with the ♣J
+    uint32_t last_winner;     // absolute seat that won the last completed trick
+    uint32_t steps;           // play_action calls so far
+    uint32_t ann_count;       // announcement decisions so far in this call (ordinal of SITE_ANNOUNCEMENT)
+    U4 ann_blk;               // cached Philox block of the announcement stream
+    uint32_t ann_blk_id;
+};
+
+DK_HD void fdo_rotate(FdoLive& g, uint32_t r) {  // new frame index i = old index (i + r) & 3
+    uint32_t a0 = g.h0, a1 = g.h1, a2 = g.h2, a3 = g.h3;
+    if (r & 1u) { uint32_t t = a0; a0 = a1; a1 = a2; a2 = a3; a3 = t; }
+    if (r & 2u) { uint32_t t0 = a0, t1 = a1; a0 = a2; a1 = a3; a2 = t0; a3 = t1; }
+    g.h0 = a0; g.h1 = a1; g.h2 = a2; g.h3 = a3;
+    g.base = (g.base + r) & 3u;
+}
+
+DK_HD void fdo_live_clear(FdoLive& g) {
+    g.h0 = g.h1 = g.h2 = g.h3 = g.dup = 0; g.base = 0; g.eyes = g.ntricks = g.dkc = g.foxes = 0; g.trump = 0; g.gt = 15;
+    g.team_tag = TEAM_IN_RESERVATIONS; g.re_mask = 0; g.wed_seat = 0; g.solved_idx = 0; g.re_low = g.ko_low = 0; g.karl = 0;
+    g.last_winner = 0; g.steps = 0; g.ann_count = 0; g.ann_blk_id = 0xFFFFFFFFu; g.ann_blk.x = g.ann_blk.y = g.ann_blk.z = g.ann_blk.w = 0;
+}
+
+// Deal: start seat = draw(4) from word 0 of SITE_DEAL, then a Durstenfeld shuffle (i = 47..1, j = draw(i+1), swap) of
+// [c0,c0,c1,c1,...] using words 1..47; seat p receives positions 12p..12p+11 (add: copy A first, then copy B)
+// (rs-full-doko/src/state/state.rs:169-178, hand/hand.rs:116-188).  `Deck` provides 12 words of per-thread scratch
+// (shared memory on the device).  Position i is final after step i, so its card goes straight into seat i/12's hand.
+template <class Deck>
+DK_HD void fdo_deal(FdoLive& g, const RngKey& key, Deck& deck, uint32_t abs_hand[4], uint32_t& dup, uint32_t& start) {
+#pragma unroll
+    for (uint32_t w = 0; w < 12; ++w) deck.set(w, (2u * w) * 0x0101u + (2u * w + 1u) * 0x01010000u);
+    uint32_t h[4] = {0, 0, 0, 0};
+    uint32_t d = 0;
+    start = 0;
+#pragma unroll
+    for (uint32_t b = 0; b < 12; ++b) {
+        U4 blk = rng_block(key, SITE_DEAL, b);
+        uint32_t ws[4] = {blk.x, blk.y, blk.z, blk.w};
+#pragma unroll
+        for (uint32_t q = 0; q < 4; ++q) {
+            uint32_t ord = 4u * b + q;
+            if (ord == 0u) { start = mulhi(ws[q], 4u); continue; }
+            uint32_t i = 48u - ord;                       // 47 .. 1
+            uint32_t j = mulhi(ws[q], i + 1u);
+            uint32_t wi = i >> 2, si = (i & 3u) * 8u;
+            uint32_t wj = j >> 2, sj = (j & 3u) * 8u;
+            uint32_t vi = deck.get(wi);
+            uint32_t vj = deck.get(wj);
+            uint32_t ci = (vi >> si) & 0xFFu;             // card currently at position i
+            uint32_t cj = (vj >> sj) & 0xFFu;             // card that ends up at position i
+            deck.set(wj, (vj & ~(0xFFu << sj)) | (ci << sj));
+            uint32_t bit = 1u << cj;
+            uint32_t seat = i / 12u;
+            d |= h[seat] & bit;
+            h[seat] |= bit;
+        }
+    }
+    {   // position 0
+        uint32_t c0 = deck.get(0) & 0xFFu;
+        uint32_t bit = 1u << c0;
+        d |= h[0] & bit;
+        h[0] |= bit;
+    }
+    abs_hand[0] = h[0]; abs_hand[1] = h[1]; abs_hand[2] = h[2]; abs_hand[3] = h[3];
+    dup = d;
+    (void)g;
+}
+
+// Outcome of the reservation round (reservation/reservation_winning_logic.rs:36-73, team/team_logic.rs:37-122):
+// the FIRST solo in seat order from the start seat wins; else the LAST wedding; else a normal game.
+// res_action[i] = action index (24..32) chosen by frame seat i (frame base = game start seat).
+DK_HD void fdo_finish_reservations(FdoLive& g, const uint32_t res_action[4]) {
+    uint32_t solo_i = 4, wed_i = 4;
+#pragma unroll
+    for (uint32_t i = 0; i < 4; ++i) {
+        if (res_action[i] >= 26u && solo_i == 4u) solo_i = i;
+        if (res_action[i] == 25u) wed_i = i;
+    }
+    if (solo_i < 4u) {
+        uint32_t a = res_action[0];
+        a = solo_i == 1u ? res_action[1] : a; a = solo_i == 2u ? res_action[2] : a; a = solo_i == 3u ? res_action[3] : a;
+        g.gt = a - 24u;                                   // 26..32 → ♦,♥,♠,♣,Trumpless,Queens,Jacks solo = 2..8
+        g.team_tag = TEAM_NO_WEDDING;
+        g.re_mask = 1u << ((g.base + solo_i) & 3u);
+    } else if (wed_i < 4u) {
+        g.gt = GT_WEDDING;
+        g.team_tag = TEAM_WEDDING_UNSOLVED;
+        g.wed_seat = (g.base + wed_i) & 3u;
+        g.re_mask = 0;
+    } else {
+        g.gt = GT_NORMAL;
+        g.team_tag = TEAM_NO_WEDDING;
+        uint32_t m = 0;                                   // holders of a ♣Q at the end of the reservation round
+        m |= ((g.h0 >> CARD_CQ) & 1u) << (g.base & 3u);
+        m |= ((g.h1 >> CARD_CQ) & 1u) << ((g.base + 1u) & 3u);
+        m |= ((g.h2 >> CARD_CQ) & 1u) << ((g.base + 2u) & 3u);
+        m |= ((g.h3 >> CARD_CQ) & 1u) << ((g.base + 3u) & 3u);
+        g.re_mask = m;
+    }
+    g.trump = trump_mask_for_game_type(g.gt);
+}
+
+// One reservation decision of frame seat i with hand `h` (action/allowed_actions.rs:76-96; MSB-first pick over
+// Healthy 24, [Wedding 25], solos 26..32).
+DK_HD uint32_t fdo_pick_reservation(uint32_t h, uint32_t dup, uint32_t word) {
+    uint32_t has_wedding = ((h & dup) >> CARD_CQ) & 1u;
+    uint32_t n = 8u + has_wedding;
+    uint32_t idx = mulhi(word, n);
+    uint32_t a = 32u - idx;                               // rank 0 = bit 32 (Jacks) ... rank 6 = bit 26 (♦-Solo)
+    return (!has_wedding && idx == 7u) ? 24u : a;         // without Wedding the 8th choice is Healthy
+}
+
+// Announcement protocol (state.rs:184-206, announcement.rs:83-215, calc_announcement.rs:176-228), replayed AFTER the card
+// play of the game.  With the random policy the calls never influence which cards are legal, and the cards influence the
+// calls only through (a) the hand sizes, which are a function of the card index, and (b) the moment a wedding is solved —
+// so the rounds can be run as one per-lane state machine once the tricks are known.  This keeps the 48 card steps of a
+// warp in perfect lock-step and makes the cost of the (data-dependent) rounds max-over-lanes of the SUM of visits instead
+// of the sum over card positions of the max.
+//   ci      card index whose round is running (the round before card ci), p = absolute seat to ask next,
+//   turns   consecutive "no" so far (auto-skipped seats count, announcement.rs:156-165)
+//   starts  2 bits per trick: absolute seat that leads trick t
+// Every decision that actually reaches a seat is one play_action ("game step") and consumes one word of SITE_ANNOUNCEMENT.
+template <bool WITH_ANN>
+DK_HD void fdo_replay_announcements(FdoLive& g, const RngKey& key, uint32_t starts, uint32_t ci, uint32_t p, uint32_t turns) {
+    const bool wedding = g.team_tag == TEAM_WEDDING_SOLVED;       // (an unsolved wedding cannot survive trick 2)
+    const uint32_t w = wedding ? g.solved_idx : 0u;
+    const uint32_t first_ci = wedding ? 4u * (g.solved_idx + 1u) : 0u;   // no calls while the wedding is unsolved
+    if (ci < first_ci) { ci = first_ci; p = (starts >> (2u * (ci >> 2))) & 3u; turns = 0; }
+    const uint32_t re = g.re_mask & 15u;
+    while (ci < 48u) {
+        uint32_t t = ci >> 2, k = ci & 3u;
+        uint32_t cmax = 12u - t;
+        uint32_t thr_re = fdo_min_cards_to_call(g.re_low, g.ko_low, w), thr_ko = fdo_min_cards_to_call(g.ko_low, g.re_low, w);
+        if (cmax < (thr_re < thr_ko ? thr_re : thr_ko)) break;     // monotone: nobody can ever call again
+        uint32_t base = (starts >> (2u * t)) & 3u;
+        uint32_t played = (((1u << k) - 1u) << base); played = (played | (played >> 4)) & 15u;   // seats that already played in trick t
+        // eligibility by absolute seat: cards on hand >= the team's threshold
+        uint32_t e_re = cmax >= thr_re ? (cmax - 1u >= thr_re ? 15u : (~played & 15u)) : 0u;
+        uint32_t e_ko = cmax >= thr_ko ? (cmax - 1u >= thr_ko ? 15u : (~played & 15u)) : 0u;
+        uint32_t elig = (e_re & re) | (e_ko & ~re & 15u);
+        uint32_t rot = ((elig | (elig << 4)) >> p) & 15u;
+        uint32_t d = rot ? ffs0(rot) : 4u;                        // seats skipped before the next eligible one
+        if (turns + d >= 4u) {                                    // RoundIsOver → card ci is played; next round
+            ci++;
+            p = (((starts >> (2u * (ci >> 2))) & 3u) + (ci & 3u)) & 3u;
+            turns = 0;
+            continue;
+        }
+        p = (p + d) & 3u; turns += d;
+        uint32_t is_re = (re >> p) & 1u;
+        uint32_t c = cmax - ((played >> p) & 1u);
+        uint32_t m = is_re ? g.re_low : g.ko_low, e = is_re ? g.ko_low : g.re_low;
+        uint32_t call = fdo_allowed_call(c, m, e, w);
+        g.steps++;
+        uint32_t ord = g.ann_count++;
+        bool says = false;
+        if (WITH_ANN) {                                           // allowed = {call, NoAnnouncement}: MSB rank 0 = NoAnnouncement
+            if ((ord >> 2) != g.ann_blk_id) { g.ann_blk_id = ord >> 2; g.ann_blk = rng_block(key, SITE_ANNOUNCEMENT, ord >> 2); }
+            says = mulhi(u4_word(g.ann_blk, ord & 3u), 2u) == 1u;
+        }
+        if (says) { if (is_re) g.re_low = call; else g.ko_low = call; turns = 0; }   // announcement.rs:203-210
+        else turns++;
+        p = (p + 1u) & 3u;
+    }
+}
+
+struct TrickAcc { uint32_t follow, best, bestk, bestc, teyes, foxm; };
+
+// Card step of frame seat K (compile-time) with hand register `h` (action/allowed_actions.rs:97-140, state.rs:274-357).
+template <int K>
+DK_HD void fdo_card_step(FdoLive& g, uint32_t& h, TrickAcc& a, uint32_t word, bool last_trick) {
+    uint32_t mask = h;
+    if (K > 0 && !last_trick) {                           // state.rs:360-372: no colour is enforced in the 12th trick
+        uint32_t f = h & a.follow;
+        mask = f ? f : h;
+    }
+    uint32_t n = popc(mask);
+    uint32_t idx = mulhi(word, n);
+    uint32_t c = pick_msb_rank24(mask, idx);
+    uint32_t bit = 1u << c;
+    if (g.dup & bit) g.dup ^= bit; else h ^= bit;         // hand.remove: a doubled card stays in the hand once
+    if (K == 0) a.follow = follow_mask(c, g.trump);
+    uint32_t pw = card_power(c, g.trump, a.follow);
+    if (K == 0 || pw > a.best) { a.best = pw; a.bestk = (uint32_t)K; a.bestc = c; }   // strict: first of equals wins
+    uint32_t suit = card_suit(c);
+    a.teyes += card_eyes_by_rank(c - 6u * suit);
+    if (c == CARD_DA) a.foxm |= 1u << K;
+    g.steps++;
+}
+
+// Book-keeping when a trick is complete (state.rs:293-352, team/team_logic.rs:59-112, additional_points/*.rs).
+DK_HD void fdo_trick_done(FdoLive& g, const TrickAcc& a, uint32_t t) {
+    uint32_t w = (g.base + a.bestk) & 3u;
+    g.eyes += a.teyes << (8u * w);
+    g.ntricks += 1u << (4u * w);
+    if (a.teyes >= 40u) g.dkc += 1u << (4u * w);
+#pragma unroll
+    for (uint32_t k = 0; k < 4; ++k)
+        if ((a.foxm >> k) & 1u) g.foxes = (g.foxes << 5) | 16u | (((g.base + k) & 3u) << 2) | w;
+    if (g.team_tag == TEAM_WEDDING_UNSOLVED) {
+        if (w != g.wed_seat) { g.team_tag = TEAM_WEDDING_SOLVED; g.solved_idx = t; g.re_mask = (1u << g.wed_seat) | (1u << w); }
+        else if (t == 2u) { g.team_tag = TEAM_WEDDING_SOLVED; g.solved_idx = 2u; g.re_mask = 1u << g.wed_seat; }
+    }
+    if (t == 11u) g.karl = a.bestc == CARD_CJ ? 1u : 0u;
+    g.last_winner = w;
+    fdo_rotate(g, a.bestk);
+}
+
+// Final scoring from the accumulated trackers → player_points per ABSOLUTE seat.
+DK_HD void fdo_final_points(const FdoLive& g, int32_t pts[4]) {
+    uint32_t re_eyes = 0, re_tricks = 0;
+    int32_t extras = 0;
+#pragma unroll
+    for (uint32_t s = 0; s < 4; ++s) {
+        bool re = (g.re_mask >> s) & 1u;
+        uint32_t e = (g.eyes >> (8u * s)) & 255u, n = (g.ntricks >> (4u * s)) & 15u, d = (g.dkc >> (4u * s)) & 15u;
+        if (re) { re_eyes += e; re_tricks += n; extras += (int32_t)d; } else { extras -= (int32_t)d; }
+    }
+#pragma unroll
+    for (uint32_t f = 0; f < 2; ++f) {
+        uint32_t rec = (g.foxes >> (5u * f)) & 31u;
+        if (rec & 16u) {
+            bool played_re = (g.re_mask >> ((rec >> 2) & 3u)) & 1u, won_re = (g.re_mask >> (rec & 3u)) & 1u;
+            if (played_re != won_re) extras += won_re ? 1 : -1;
+        }
+    }
+    if (g.karl) extras += ((g.re_mask >> g.last_winner) & 1u) ? 1 : -1;
+    int32_t ko;
+    int32_t re = fdo_score(re_eyes, re_tricks, popc(g.re_mask), g.re_low, g.ko_low, extras, &ko);
+#pragma unroll
+    for (uint32_t s = 0; s < 4; ++s) pts[s] = ((g.re_mask >> s) & 1u) ? re : ko;
+}
+
+// Resume descriptor for playouts that start from a stored state.
+struct FdoResume {
+    uint32_t n_res;        // reservations already made (0..4); < 4 means we are still in the reservation phase
+    uint32_t res_action[4];// actions of the reservations already made, by frame seat (frame base = game start seat)
+    uint32_t t0, k0;       // trick index / cards already in that trick
+    uint32_t starts;       // lead seats of the tricks 0..t0-1 (2 bits each); trick t0's is g.base
+    uint32_t ann_ci, ann_p, ann_turns;   // where the announcement protocol resumes: round before card ann_ci, next ABSOLUTE
+                           // seat to ask, turns without call.  Phase PlayCard (round already over) → ann_ci = card_index + 1.
+    TrickAcc acc;          // partial trick accumulator (valid when k0 > 0)
+};
+
+// Plays the game to the end.  FRESH: hands/base already set by the deal, nothing played yet.
+template <bool WITH_ANN, bool FRESH>
+DK_HD void fdo_play_to_end(FdoLive& g, const RngKey& key, const FdoResume* rs) {
+    uint32_t n_res = FRESH ? 0u : rs->n_res;
+    if (n_res < 4u) {
+        U4 blk = rng_block(key, SITE_RESERVATION, 0);
+        uint32_t ra[4];
+        ra[0] = (!FRESH && n_res > 0u) ? rs->res_action[0] : fdo_pick_reservation(g.h0, g.dup, blk.x);
+        ra[1] = (!FRESH && n_res > 1u) ? rs->res_action[1] : fdo_pick_reservation(g.h1, g.dup, blk.y);
+        ra[2] = (!FRESH && n_res > 2u) ? rs->res_action[2] : fdo_pick_reservation(g.h2, g.dup, blk.z);
+        ra[3] = fdo_pick_reservation(g.h3, g.dup, blk.w);
+        g.steps += 4u - n_res;
+        fdo_finish_reservations(g, ra);
+    }
+    uint32_t t0 = FRESH ? 0u : rs->t0;
+    uint32_t starts = FRESH ? 0u : rs->starts;
+    for (uint32_t t = t0; t < 12u; ++t) {
+        starts |= g.base << (2u * t);
+        U4 blk = rng_block(key, SITE_CARD, t);
+        TrickAcc a;
+        a.follow = 0; a.best = 0; a.bestk = 0; a.bestc = 0; a.teyes = 0; a.foxm = 0;
+        uint32_t k0 = 0;
+        bool first = !FRESH && t == t0;
+        if (first) { k0 = rs->k0; if (k0 > 0u) a = rs->acc; }
+        bool last = t == 11u;
+#define DK_FDO_POS(K, HREG, WORD)                                                                      \
+        if (!first || k0 <= (uint32_t)(K)) fdo_card_step<K>(g, HREG, a, WORD, last);
+        DK_FDO_POS(0, g.h0, blk.x)
+        DK_FDO_POS(1, g.h1, blk.y)
+        DK_FDO_POS(2, g.h2, blk.z)
+        DK_FDO_POS(3, g.h3, blk.w)
+#undef DK_FDO_POS
+        fdo_trick_done(g, a, t);
+    }
+    // announcement rounds (see fdo_replay_announcements): fresh games start with the round before card 0
+    if (FRESH) fdo_replay_announcements<WITH_ANN>(g, key, starts, 0u, starts & 3u, 0u);
+    else fdo_replay_announcements<WITH_ANN>(g, key, starts, rs->ann_ci, rs->ann_p, rs->ann_turns);
+}
+
+// Fresh game: deal + reservations + 12 tricks + scoring.
+template <bool WITH_ANN, class Deck>
+DK_HD void fdo_playout_fresh(const RngKey& key, Deck& deck, int32_t pts[4], uint32_t& steps) {
+    FdoLive g;
+    fdo_live_clear(g);
+    uint32_t ah[4], start;
+    fdo_deal(g, key, deck, ah, g.dup, start);
+    g.h0 = ah[0]; g.h1 = ah[1]; g.h2 = ah[2]; g.h3 = ah[3];
+    g.base = 0;
+    fdo_rotate(g, start);
+    fdo_play_to_end<WITH_ANN, true>(g, key, nullptr);
+    fdo_final_points(g, pts);
+    steps = g.steps;
+}
+
+}  // namespace dk

@@ -1,0 +1,58 @@
+// hostsim — TEST INFRASTRUCTURE ONLY.
+// Compiles the per-thread device logic of master_doko_reinforcement_learning_b200/csrc/*.cuh with g++ and runs it
+// on the CPU, one "thread" at a time, so that kernel logic can be parity-checked against the oracle in the build
+// container (which has no GPU).  It is NOT a CPU fallback: the product library never contains or calls this file,
+// and the GPU parity tests (-m gpu) exercise the real kernels through the C ABI.
+#include <cstdint>
+#include <cstring>
+
+#include "../../include/doko_cuda.h"
+#include "../../master_doko_reinforcement_learning_b200/csrc/dk_common.cuh"
+#include "../../master_doko_reinforcement_learning_b200/csrc/fdo_rules.cuh"
+#include "../../master_doko_reinforcement_learning_b200/csrc/doko_rules.cuh"
+
+#define SIM_API extern "C" __attribute__((visibility("default")))
+
+namespace {
+struct LocalDeck {
+    uint32_t w[12];
+    uint32_t get(uint32_t i) const { return w[i]; }
+    void set(uint32_t i, uint32_t v) { w[i] = v; }
+};
+dk::RngKey make_key(uint64_t seed, uint64_t unit, uint32_t epoch) {
+    dk::RngKey k; k.seed_lo = (uint32_t)seed; k.seed_hi = (uint32_t)(seed >> 32); k.unit_lo = (uint32_t)unit; k.unit_hi = (uint32_t)(unit >> 32); k.epoch = epoch;
+    return k;
+}
+}  // namespace
+
+SIM_API void sim_fdo_playout_fresh(uint64_t seed, uint32_t epoch, uint64_t first_id, uint64_t n, int with_ann, int32_t* points, uint32_t* steps) {
+    for (uint64_t i = 0; i < n; ++i) {
+        LocalDeck deck;
+        dk::RngKey key = make_key(seed, first_id + i, epoch);
+        int32_t p[4]; uint32_t s;
+        if (with_ann) dk::fdo_playout_fresh<true>(key, deck, p, s); else dk::fdo_playout_fresh<false>(key, deck, p, s);
+        for (int q = 0; q < 4; ++q) points[i * 4 + q] = p[q];
+        steps[i] = s;
+    }
+}
+SIM_API void sim_doko_playout_fresh(uint64_t seed, uint32_t epoch, uint64_t first_id, uint64_t n, int32_t* points, uint32_t* steps, uint8_t* trace, uint32_t* aux) {
+    for (uint64_t i = 0; i < n; ++i) {
+        LocalDeck deck;
+        dk::RngKey key = make_key(seed, first_id + i, epoch);
+        int32_t p[4]; uint32_t s; uint8_t tr[52]; uint32_t ax[4];
+        dk::doko_playout_fresh<true>(key, deck, p, s, tr, ax);
+        for (int q = 0; q < 4; ++q) points[i * 4 + q] = p[q];
+        steps[i] = s;
+        if (trace) std::memcpy(trace + i * 52, tr, 52);
+        if (aux) std::memcpy(aux + i * 4, ax, 16);
+    }
+}
+SIM_API uint32_t sim_fdo_allowed_call(uint32_t c, uint32_t m, uint32_t e, uint32_t w) { return dk::fdo_allowed_call(c, m, e, w); }
+SIM_API int32_t sim_fdo_score(uint32_t re_eyes, uint32_t re_tricks, uint32_t n_re, uint32_t rl, uint32_t kl, int32_t extras, int32_t* ko) {
+    return dk::fdo_score(re_eyes, re_tricks, n_re, rl, kl, extras, ko);
+}
+SIM_API uint32_t sim_select_lsb24(uint32_t x, uint32_t k) { return dk::select_lsb24(x, k); }
+SIM_API uint32_t sim_select_lsb(uint32_t x, uint32_t k) { return dk::select_lsb(x, k); }
+SIM_API uint32_t sim_card_power(uint32_t c, uint32_t trump, uint32_t follow) { return dk::card_power(c, trump, follow); }
+SIM_API uint32_t sim_trump_mask(uint32_t gt) { return dk::trump_mask_for_game_type(gt); }
+SIM_API uint32_t sim_follow_mask(uint32_t c, uint32_t trump) { return dk::follow_mask(c, trump); }
