@@ -132,6 +132,7 @@ enum {
 /* Flags. */
 #define DK_PLAYOUT_WITH_ANNOUNCEMENTS 1u /* FdoState::random_action_for_current_player (state.rs:378-399); without it the
                                             _no_announcement variant (state.rs:401-431) as used by random_rollout */
+#define DK_STEP_SKIP_SINGLE 0x100u       /* dk_step_random_encode: apply with skip_single (same meaning as DK_APPLY_SKIP_SINGLE) */
 #define DK_APPLY_SKIP_SINGLE 1u          /* FdoAzEnvState::take_action_by_action_index(.., skip_single=true, ..)
                                             (rs-doko-alpha-zero/src/env/envs/full_doko/full_doko.rs:121-154) */
 
@@ -203,6 +204,11 @@ DK_API dk_status dk_step_random_encode(dk_ctx* ctx, size_t n, dk_state* states /
 DK_API dk_status dk_playout(dk_ctx* ctx, int engine, uint32_t flags, size_t n, const dk_state* states /*[dev] or NULL*/,
                      const dk_rng* rng, int32_t* points_out /*[dev] n*4*/, uint32_t* steps_out /*[dev] n*/,
                      dk_stream stream);
+/* Verification entry (DK_DOKO): fresh playouts that also record the 52 action ids per game (trace_out[n*52]) and
+ * aux_out[n*4] = (wedding flag, re seats mask, eyes packed 8 bits/seat, tricks packed 4 bits/seat) — the per-game outputs
+ * BASELINE config 1 is checked on. */
+DK_API dk_status dk_playout_trace(dk_ctx* ctx, int engine, size_t n, const dk_rng* rng, int32_t* points_out /*[dev] n*4*/,
+                                  uint8_t* trace_out /*[dev] n*52*/, uint32_t* aux_out /*[dev] n*4*/, dk_stream stream);
 /* Same, results copied to HOST buffers inside the call (what a plain Rust slice caller binds). */
 DK_API dk_status dk_playout_host(dk_ctx* ctx, int engine, uint32_t flags, size_t n, const dk_state* states_host /*[host] or NULL*/,
                           const dk_rng* rng, int32_t* points_out_host /*[host] n*4*/, uint32_t* steps_out_host /*[host] n*/);

@@ -57,6 +57,7 @@ def load_library():
     L.dk_launch_count.argtypes = [vp]
     L.dk_playout.argtypes = [vp, i32, u32, sz, vp, C.POINTER(DkRng), vp, vp, vp]
     L.dk_playout_host.argtypes = [vp, i32, u32, sz, vp, C.POINTER(DkRng), vp, vp]
+    L.dk_playout_trace.argtypes = [vp, i32, sz, C.POINTER(DkRng), vp, vp, vp, vp]
     for name, args in (
         ("dk_new_games", [vp, i32, sz, C.POINTER(DkRng), vp, vp]),
         ("dk_from_deals", [vp, i32, sz, vp, vp, vp, vp]),
@@ -160,3 +161,86 @@ class DokoCuda:
         self._check(self.L.dk_playout_host(self.ctx, engine, flags, n, _ptr(states), C.byref(rng), _ptr(points_out), _ptr(steps_out)),
                     "dk_playout_host")
         return points_out, steps_out
+
+    # ---- state records ---------------------------------------------------------------------------------------------------
+    def _dev(self):
+        import torch
+
+        return torch.device("cuda", self.device)
+
+    def alloc_states(self, n):
+        """Device buffer of n dk_state records (torch uint8 [n,128])."""
+        import torch
+
+        return torch.empty((n, 128), dtype=torch.uint8, device=self._dev())
+
+    def new_games(self, engine, n, rng, out=None, stream=None):
+        out = self.alloc_states(n) if out is None else out
+        self._check(self.L.dk_new_games(self.ctx, engine, n, C.byref(rng), _ptr(out), stream if stream is not None else self._stream()), "dk_new_games")
+        return out
+
+    def from_deals(self, engine, hands, start, out=None, stream=None):
+        """hands: int64/uint64 cuda tensor [n,4]; start: uint8 cuda tensor [n]."""
+        n = hands.shape[0]
+        out = self.alloc_states(n) if out is None else out
+        self._check(self.L.dk_from_deals(self.ctx, engine, n, _ptr(hands), _ptr(start), _ptr(out), stream if stream is not None else self._stream()),
+                    "dk_from_deals")
+        return out
+
+    def legal_mask(self, engine, states, out=None, stream=None):
+        import torch
+
+        n = states.shape[0]
+        out = torch.empty((n,), dtype=torch.int64, device=self._dev()) if out is None else out
+        self._check(self.L.dk_legal_mask(self.ctx, engine, n, _ptr(states), _ptr(out), stream if stream is not None else self._stream()), "dk_legal_mask")
+        return out
+
+    def apply(self, engine, states, actions, flags=0, err_out=None, stream=None):
+        """In-place play_action.  actions: uint8 cuda tensor [n].  Returns err flags (uint8 [n])."""
+        import torch
+
+        n = states.shape[0]
+        err_out = torch.empty((n,), dtype=torch.uint8, device=self._dev()) if err_out is None else err_out
+        self._check(self.L.dk_apply(self.ctx, engine, n, _ptr(states), _ptr(actions), flags, _ptr(err_out), stream if stream is not None else self._stream()),
+                    "dk_apply")
+        return err_out
+
+    def terminal(self, engine, states, stream=None):
+        import torch
+
+        n = states.shape[0]
+        done = torch.empty((n,), dtype=torch.uint8, device=self._dev())
+        pts = torch.empty((n, 4), dtype=torch.int32, device=self._dev())
+        self._check(self.L.dk_terminal(self.ctx, engine, n, _ptr(states), _ptr(done), _ptr(pts), stream if stream is not None else self._stream()), "dk_terminal")
+        return done, pts
+
+    def encode(self, layout, states, out=None, row_stride=None, stream=None):
+        import torch
+
+        n = states.shape[0]
+        row_stride = OBS_LEN[layout] if row_stride is None else row_stride
+        out = torch.empty((n, row_stride), dtype=torch.int64, device=self._dev()) if out is None else out
+        self._check(self.L.dk_encode(self.ctx, layout, n, _ptr(states), _ptr(out), row_stride, stream if stream is not None else self._stream()), "dk_encode")
+        return out
+
+    def step_random_encode(self, states, rng, flags=DK_PLAYOUT_WITH_ANNOUNCEMENTS, obs_out=None, row_stride=311, action_out=None, want_obs=True, stream=None):
+        import torch
+
+        n = states.shape[0]
+        if want_obs and obs_out is None:
+            obs_out = torch.empty((n, row_stride), dtype=torch.int64, device=self._dev())
+        if action_out is None:
+            action_out = torch.empty((n,), dtype=torch.uint8, device=self._dev())
+        self._check(self.L.dk_step_random_encode(self.ctx, n, _ptr(states), C.byref(rng), flags, _ptr(obs_out), row_stride, _ptr(action_out),
+                                                 stream if stream is not None else self._stream()), "dk_step_random_encode")
+        return obs_out, action_out
+
+    def playout_trace(self, engine, n, rng, stream=None):
+        import torch
+
+        pts = torch.empty((n, 4), dtype=torch.int32, device=self._dev())
+        trace = torch.empty((n, 52), dtype=torch.uint8, device=self._dev())
+        aux = torch.empty((n, 4), dtype=torch.int32, device=self._dev())
+        self._check(self.L.dk_playout_trace(self.ctx, engine, n, C.byref(rng), _ptr(pts), _ptr(trace), _ptr(aux), stream if stream is not None else self._stream()),
+                    "dk_playout_trace")
+        return pts, trace, aux

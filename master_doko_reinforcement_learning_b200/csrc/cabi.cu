@@ -122,20 +122,113 @@ uint64_t dk_launch_count(const dk_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 dk_status dk_playout(dk_ctx* ctx, int engine, uint32_t flags, size_t n, const dk_state* states, const dk_rng* rng,
                      int32_t* points_out, uint32_t* steps_out, dk_stream stream) {
-    if (!ctx || !rng) return DK_ERR_INVALID_ARGUMENT;
+    if (!ctx || !rng || (engine != DK_FDO && engine != DK_DOKO)) return DK_ERR_INVALID_ARGUMENT;
     if (n == 0) return DK_OK;
     DK_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t s = pick_stream(ctx, stream);
     dk::RngParams rp = to_params(rng);
-    unsigned grid = (unsigned)((n + dk::PLAYOUT_THREADS - 1) / dk::PLAYOUT_THREADS);
-    if (engine == DK_FDO && states == nullptr) {
-        if (flags & DK_PLAYOUT_WITH_ANNOUNCEMENTS)
-            dk::fdo_playout_fresh_kernel<true><<<grid, dk::PLAYOUT_THREADS, 0, s>>>(rp, (uint64_t)n, (int4*)points_out, steps_out);
-        else
-            dk::fdo_playout_fresh_kernel<false><<<grid, dk::PLAYOUT_THREADS, 0, s>>>(rp, (uint64_t)n, (int4*)points_out, steps_out);
-        return check_launch(ctx, "fdo_playout_fresh_kernel");
+    const bool with_ann = (flags & DK_PLAYOUT_WITH_ANNOUNCEMENTS) != 0;
+    if (states == nullptr) {
+        unsigned grid = (unsigned)((n + dk::PLAYOUT_THREADS - 1) / dk::PLAYOUT_THREADS);
+        if (engine == DK_FDO) {
+            if (with_ann) dk::fdo_playout_fresh_kernel<true><<<grid, dk::PLAYOUT_THREADS, 0, s>>>(rp, (uint64_t)n, (int4*)points_out, steps_out);
+            else dk::fdo_playout_fresh_kernel<false><<<grid, dk::PLAYOUT_THREADS, 0, s>>>(rp, (uint64_t)n, (int4*)points_out, steps_out);
+            return check_launch(ctx, "fdo_playout_fresh_kernel");
+        }
+        dk::doko_playout_fresh_kernel<false><<<grid, dk::PLAYOUT_THREADS, 0, s>>>(rp, (uint64_t)n, (int4*)points_out, steps_out, nullptr, nullptr);
+        return check_launch(ctx, "doko_playout_fresh_kernel");
     }
-    return fail(ctx, DK_ERR_UNSUPPORTED, "dk_playout: this engine/state combination is not built yet");
+    unsigned grid = (unsigned)((n + dk::STATE_THREADS - 1) / dk::STATE_THREADS);
+    if (engine == DK_FDO) {
+        if (with_ann) dk::playout_state_kernel<DK_FDO, true><<<grid, dk::STATE_THREADS, 0, s>>>(rp, (uint64_t)n, states, 1u, (int4*)points_out, steps_out);
+        else dk::playout_state_kernel<DK_FDO, false><<<grid, dk::STATE_THREADS, 0, s>>>(rp, (uint64_t)n, states, 1u, (int4*)points_out, steps_out);
+    } else {
+        dk::playout_state_kernel<DK_DOKO, false><<<grid, dk::STATE_THREADS, 0, s>>>(rp, (uint64_t)n, states, 1u, (int4*)points_out, steps_out);
+    }
+    return check_launch(ctx, "playout_state_kernel");
+}
+
+dk_status dk_playout_trace(dk_ctx* ctx, int engine, size_t n, const dk_rng* rng, int32_t* points_out, uint8_t* trace_out, uint32_t* aux_out,
+                           dk_stream stream) {
+    if (!ctx || !rng) return DK_ERR_INVALID_ARGUMENT;
+    if (engine != DK_DOKO) return fail(ctx, DK_ERR_UNSUPPORTED, "dk_playout_trace: only DK_DOKO records traces");
+    if (n == 0) return DK_OK;
+    DK_CUDA(ctx, cudaSetDevice(ctx->device));
+    unsigned grid = (unsigned)((n + dk::PLAYOUT_THREADS - 1) / dk::PLAYOUT_THREADS);
+    dk::doko_playout_fresh_kernel<true><<<grid, dk::PLAYOUT_THREADS, 0, pick_stream(ctx, stream)>>>(to_params(rng), (uint64_t)n, (int4*)points_out, nullptr,
+                                                                                                    trace_out, (uint4*)aux_out);
+    return check_launch(ctx, "doko_playout_fresh_kernel<trace>");
+}
+
+dk_status dk_new_games(dk_ctx* ctx, int engine, size_t n, const dk_rng* rng, dk_state* out, dk_stream stream) {
+    if (!ctx || !rng || !out || (engine != DK_FDO && engine != DK_DOKO)) return DK_ERR_INVALID_ARGUMENT;
+    if (n == 0) return DK_OK;
+    DK_CUDA(ctx, cudaSetDevice(ctx->device));
+    unsigned grid = (unsigned)((n + dk::PLAYOUT_THREADS - 1) / dk::PLAYOUT_THREADS);
+    dk::new_games_kernel<<<grid, dk::PLAYOUT_THREADS, 0, pick_stream(ctx, stream)>>>(to_params(rng), (uint64_t)n, out);
+    return check_launch(ctx, "new_games_kernel");
+}
+
+dk_status dk_from_deals(dk_ctx* ctx, int engine, size_t n, const uint64_t* hands, const uint8_t* start, dk_state* out, dk_stream stream) {
+    if (!ctx || !hands || !start || !out || (engine != DK_FDO && engine != DK_DOKO)) return DK_ERR_INVALID_ARGUMENT;
+    if (n == 0) return DK_OK;
+    DK_CUDA(ctx, cudaSetDevice(ctx->device));
+    unsigned grid = (unsigned)((n + dk::STATE_THREADS - 1) / dk::STATE_THREADS);
+    dk::from_deals_kernel<<<grid, dk::STATE_THREADS, 0, pick_stream(ctx, stream)>>>((uint64_t)n, hands, start, out);
+    return check_launch(ctx, "from_deals_kernel");
+}
+
+dk_status dk_legal_mask(dk_ctx* ctx, int engine, size_t n, const dk_state* states, uint64_t* mask_out, dk_stream stream) {
+    if (!ctx || !states || !mask_out || (engine != DK_FDO && engine != DK_DOKO)) return DK_ERR_INVALID_ARGUMENT;
+    if (n == 0) return DK_OK;
+    DK_CUDA(ctx, cudaSetDevice(ctx->device));
+    unsigned grid = (unsigned)((n + dk::STATE_THREADS - 1) / dk::STATE_THREADS);
+    if (engine == DK_FDO) dk::legal_mask_kernel<DK_FDO><<<grid, dk::STATE_THREADS, 0, pick_stream(ctx, stream)>>>((uint64_t)n, states, mask_out);
+    else dk::legal_mask_kernel<DK_DOKO><<<grid, dk::STATE_THREADS, 0, pick_stream(ctx, stream)>>>((uint64_t)n, states, mask_out);
+    return check_launch(ctx, "legal_mask_kernel");
+}
+
+dk_status dk_apply(dk_ctx* ctx, int engine, size_t n, dk_state* states, const uint8_t* action_idx, uint32_t flags, uint8_t* err_out, dk_stream stream) {
+    if (!ctx || !states || !action_idx || (engine != DK_FDO && engine != DK_DOKO)) return DK_ERR_INVALID_ARGUMENT;
+    if (n == 0) return DK_OK;
+    DK_CUDA(ctx, cudaSetDevice(ctx->device));
+    unsigned grid = (unsigned)((n + dk::STATE_THREADS - 1) / dk::STATE_THREADS);
+    if (engine == DK_FDO) dk::apply_kernel<DK_FDO><<<grid, dk::STATE_THREADS, 0, pick_stream(ctx, stream)>>>((uint64_t)n, states, action_idx, flags, err_out);
+    else dk::apply_kernel<DK_DOKO><<<grid, dk::STATE_THREADS, 0, pick_stream(ctx, stream)>>>((uint64_t)n, states, action_idx, flags, err_out);
+    return check_launch(ctx, "apply_kernel");
+}
+
+dk_status dk_terminal(dk_ctx* ctx, int engine, size_t n, const dk_state* states, uint8_t* done_out, int32_t* points_out, dk_stream stream) {
+    if (!ctx || !states || (engine != DK_FDO && engine != DK_DOKO)) return DK_ERR_INVALID_ARGUMENT;
+    if (n == 0) return DK_OK;
+    DK_CUDA(ctx, cudaSetDevice(ctx->device));
+    unsigned grid = (unsigned)((n + dk::STATE_THREADS - 1) / dk::STATE_THREADS);
+    dk::terminal_kernel<<<grid, dk::STATE_THREADS, 0, pick_stream(ctx, stream)>>>((uint64_t)n, states, done_out, (int4*)points_out);
+    return check_launch(ctx, "terminal_kernel");
+}
+
+dk_status dk_encode(dk_ctx* ctx, int layout, size_t n, const dk_state* states, int64_t* out, size_t row_stride, dk_stream stream) {
+    if (!ctx || !states || !out) return DK_ERR_INVALID_ARGUMENT;
+    size_t len = layout == DK_LAYOUT_FDO_PI311 ? 311 : (layout == DK_LAYOUT_DO114 ? 114 : (layout == DK_LAYOUT_DO110 ? 110 : 0));
+    if (len == 0 || row_stride < len) return DK_ERR_INVALID_ARGUMENT;
+    if (n == 0) return DK_OK;
+    DK_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = pick_stream(ctx, stream);
+    unsigned grid = (unsigned)((n + dk::ENC_THREADS - 1) / dk::ENC_THREADS);
+    if (layout == DK_LAYOUT_FDO_PI311) dk::encode_kernel<DK_LAYOUT_FDO_PI311><<<grid, dk::ENC_THREADS, 0, s>>>((uint64_t)n, states, out, row_stride);
+    else if (layout == DK_LAYOUT_DO114) dk::encode_kernel<DK_LAYOUT_DO114><<<grid, dk::ENC_THREADS, 0, s>>>((uint64_t)n, states, out, row_stride);
+    else dk::encode_kernel<DK_LAYOUT_DO110><<<grid, dk::ENC_THREADS, 0, s>>>((uint64_t)n, states, out, row_stride);
+    return check_launch(ctx, "encode_kernel");
+}
+
+dk_status dk_step_random_encode(dk_ctx* ctx, size_t n, dk_state* states, const dk_rng* rng, uint32_t flags, int64_t* obs_out, size_t row_stride,
+                                uint8_t* action_out, dk_stream stream) {
+    if (!ctx || !states || !rng || (obs_out && row_stride < 311)) return DK_ERR_INVALID_ARGUMENT;
+    if (n == 0) return DK_OK;
+    DK_CUDA(ctx, cudaSetDevice(ctx->device));
+    unsigned grid = (unsigned)((n + dk::ENC_THREADS - 1) / dk::ENC_THREADS);
+    dk::fdo_step_encode_kernel<<<grid, dk::ENC_THREADS, 0, pick_stream(ctx, stream)>>>(to_params(rng), (uint64_t)n, states, flags, obs_out, row_stride, action_out);
+    return check_launch(ctx, "fdo_step_encode_kernel");
 }
 
 dk_status dk_playout_host(dk_ctx* ctx, int engine, uint32_t flags, size_t n, const dk_state* states_host, const dk_rng* rng,

@@ -1,0 +1,106 @@
+// encode.cuh — observation encoders on the dk_state record.  Each produces the token VALUES (all < 256) through an
+// output functor; the kernels stage them as bytes in shared memory and then widen to the reference's i64 rows with
+// coalesced 64-bit stores (the HBM-bound part, SURVEY.md §8d: 2488 B per observation).
+#pragma once
+#include "state_ops.cuh"
+
+namespace dk {
+
+// 24 five-bit entries packed into two 60-bit constants.
+DK_HD uint32_t lut24x5(uint64_t lo, uint64_t hi, uint32_t c) {
+    uint64_t w = c < 12u ? lo : hi;
+    uint32_t sh = 5u * (c < 12u ? c : c - 12u);
+    return (uint32_t)(w >> sh) & 31u;
+}
+#define DK_PACK12(a, b, c, d, e, f, g, h, i, j, k, l)                                                                              \
+    ((uint64_t)(a) | ((uint64_t)(b) << 5) | ((uint64_t)(c) << 10) | ((uint64_t)(d) << 15) | ((uint64_t)(e) << 20) | ((uint64_t)(f) << 25) | \
+     ((uint64_t)(g) << 30) | ((uint64_t)(h) << 35) | ((uint64_t)(i) << 40) | ((uint64_t)(j) << 45) | ((uint64_t)(k) << 50) | ((uint64_t)(l) << 55))
+
+// encode_reservation_or_card_or_none_card (rs-doko-networks/src/full_doko/var2/encode_reservation_or_card_or_none.rs:70-107)
+DK_HD uint32_t fdo_card_token(uint32_t c) {
+    //                 ♦9  ♦10 ♦J ♦Q ♦K  ♦A  ♥9  ♥10 ♥J ♥Q ♥K  ♥A
+    const uint64_t lo = DK_PACK12(13, 11, 9, 5, 12, 10, 24, 1, 8, 4, 23, 22);
+    //                 ♣9  ♣10 ♣J ♣Q ♣K  ♣A  ♠9  ♠10 ♠J ♠Q ♠K  ♠A
+    const uint64_t hi = DK_PACK12(17, 15, 6, 2, 16, 14, 21, 19, 7, 3, 20, 18);
+    return lut24x5(lo, hi, c);
+}
+
+// encode_state_pi (rs-doko-networks/src/full_doko/var1/encode_pi.rs:27-216) with obs = observation_for_current_player():
+// 62 slots x 5 channels (token, position, player, sub-position, team) + phase = 311 values.
+// out(i, v) receives value v for row element i (0..310).
+template <class Out>
+DK_HD void fdo_encode_pi(const dk_state& s, Out& out) {
+    const uint32_t cur = st_phase(s) == DK_PHASE_FINISHED ? 0u : st_cur(s);   // current_player.unwrap_or(BOTTOM) (:31-33)
+    uint32_t n = 0;
+    auto push = [&](uint32_t tok, uint32_t pos, uint32_t ply, uint32_t sub, uint32_t team) {
+        out(n, tok); out(62u + n, pos); out(124u + n, ply); out(186u + n, sub); out(248u + n, team);
+        n++;
+    };
+    const uint32_t start = st_game_start(s);
+    for (uint32_t i = 0; i < 4u; ++i) {                                       // real reservations in play order (:43-81)
+        if (i < s.n_reservations) push(25u + s.reservations[i], i + 1u, ((start + i - cur) & 3u) + 1u, 0u, 0u);
+        else push(36u, 0u, 0u, 0u, 0u);
+    }
+    const uint32_t ci = s.card_index;
+    for (uint32_t j = 0; j < ci; ++j) {                                       // played cards (:83-99)
+        uint32_t seat = (st_trick_start(s, j >> 2) + (j & 3u)) & 3u;
+        push(fdo_card_token(s.cards[j]), j + 5u, ((seat - cur) & 3u) + 1u, 0u, 0u);
+    }
+    for (uint32_t i = 0; i < 4u; ++i) {                                       // all four hands from the seat to move (:102-121)
+        uint64_t h = s.hands[(cur + i) & 3u], b = h;
+        while (b) {
+            uint32_t pos = ffs0ll(b);
+            b &= b - 1ull;
+            uint32_t c = pos < 24u ? pos : pos - 24u;
+            uint32_t second = (pos >= 24u && ((h >> c) & 1ull)) ? 1u : 0u;     // already_encoded_cards.contains(card)
+            push(fdo_card_token(c), 53u + i, 0u, 11u + second, 0u);
+        }
+    }
+    const uint32_t n_calls = st_n_calls(s), re = st_re_mask(s);
+    uint32_t sub = 0, last = 0xFFFFFFFFu;
+    for (uint32_t a = 0; a < n_calls && a < 10u; ++a) {                       // calls (:139-165); position = raw card_index + 1
+        uint32_t v = s.announcements[a], cidx = v & 63u, seat = (v >> 6) & 3u, lvl = (v >> 8) & 7u;
+        if (cidx != last) { last = cidx; sub = 0; }
+        push(lvl == 6u ? 38u : 37u + lvl, cidx + 1u, ((seat - cur) & 3u) + 1u, sub + 1u, ((re >> seat) & 1u) ? 1u : 2u);
+        sub++;
+    }
+    for (uint32_t a = n_calls; a < 10u; ++a) push(37u, 0u, 0u, 0u, 0u);         // (:167-179)
+    out(310u, st_phase(s));                                                   // encode_phase (var1/phase.rs:9-18)
+}
+
+// encode_state / encode_state_with_reservations (rs-doko-embeddings/src/encode_state.rs:84-317): 110 / 114 values.
+template <class Out>
+DK_HD void doko_encode(const dk_state& s, bool with_reservations, Out& out) {
+    const uint32_t phase = st_phase(s);
+    const uint32_t cur = phase == DK_PHASE_FINISHED ? 0u : st_cur(s);
+    out(0u, phase == DK_PHASE_RESERVATION ? 0u : (phase == DK_PHASE_PLAY_CARD ? 1u : 2u));   // DoPhase
+    out(1u, ((st_game_start(s) - cur) & 3u) + 1u);
+    const uint32_t nt = st_n_tricks(s);
+    for (uint32_t t = 0; t < 12u; ++t) out(2u + t, t < nt ? ((st_trick_start(s, t) - cur) & 3u) + 1u : 0u);
+    const uint32_t ci = s.card_index;
+    for (uint32_t j = 0; j < 48u; ++j) out(14u + j, j < ci ? (uint32_t)s.cards[j] + 1u : 0u);
+    // hands: descending card_to_rank_in_normal_game (:17-50), doubles adjacent, seats relative to the seat to move
+    //   ♥10 ♣Q ♠Q ♥Q ♦Q ♣J ♠J ♥J ♦J ♦A ♦10 ♦K ♦9 ♣A ♣10 ♣K ♣9 ♠A ♠10 ♠K ♠9 ♥A ♥K ♥9
+    const uint64_t lo = DK_PACK12(7, 15, 21, 9, 3, 14, 20, 8, 2, 5, 1, 4), hi = DK_PACK12(0, 17, 13, 16, 12, 23, 19, 22, 18, 11, 10, 6);
+    for (uint32_t p = 0; p < 4u; ++p) {
+        uint32_t any = hand_any24(s.hands[p]), both = hand_both24(s.hands[p]);
+        uint32_t base = 62u + 12u * ((p - cur) & 3u), m = 0;
+        for (uint32_t r = 0; r < 24u; ++r) {
+            uint32_t c = lut24x5(lo, hi, r);
+            if ((any >> c) & 1u) { out(base + m, c + 1u); m++; if ((both >> c) & 1u) { out(base + m, c + 1u); m++; } }
+        }
+        for (; m < 12u; ++m) out(base + m, 0u);
+    }
+    if (with_reservations) {
+        // get_visible_reservations quirk (rs-doko/src/reservation/visible_reservations_logic.rs:6-34): slots are
+        // compared with the ABSOLUTE observing seat and stored by slot.
+        bool completed = s.n_reservations == 4u;
+        for (uint32_t i = 0; i < 4u; ++i) {
+            uint32_t v = 0;
+            if (i < s.n_reservations) v = s.reservations[i] == 1u ? 2u : ((completed || i == cur) ? 3u : 1u);
+            out(110u + i, v);
+        }
+    }
+}
+
+}  // namespace dk

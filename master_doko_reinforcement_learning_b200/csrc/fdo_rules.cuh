@@ -224,7 +224,11 @@ DK_HD void fdo_replay_announcements(FdoLive& g, const RngKey& key, uint32_t star
     const bool wedding = g.team_tag == TEAM_WEDDING_SOLVED;       // (an unsolved wedding cannot survive trick 2)
     const uint32_t w = wedding ? g.solved_idx : 0u;
     const uint32_t first_ci = wedding ? 4u * (g.solved_idx + 1u) : 0u;   // no calls while the wedding is unsolved
-    if (ci < first_ci) { ci = first_ci; p = (starts >> (2u * (ci >> 2))) & 3u; turns = 0; }
+    if (ci < first_ci) { ci = first_ci; turns = 0xFFFFFFFFu; }
+    if (turns == 0xFFFFFFFFu) {                                   // a fresh round: the seat that plays card ci is asked first
+        p = (((starts >> (2u * (ci >> 2))) & 3u) + (ci & 3u)) & 3u;
+        turns = 0;
+    }
     const uint32_t re = g.re_mask & 15u;
     while (ci < 48u) {
         uint32_t t = ci >> 2, k = ci & 3u;

@@ -4,7 +4,10 @@
 #include <stdint.h>
 
 #include "dk_common.cuh"
+#include "doko_rules.cuh"
+#include "encode.cuh"
 #include "fdo_rules.cuh"
+#include "state_ops.cuh"
 
 namespace dk {
 
@@ -53,6 +56,209 @@ fdo_playout_fresh_kernel(RngParams rp, uint64_t n, int4* __restrict__ points, ui
         if (points) points[i] = make_int4(p[0], p[1], p[2], p[3]);
         if (steps) steps[i] = s;
     }
+}
+
+
+// K1: fresh simplified-rules playouts (DoState::new_game + 52 random actions, rs-doko/src/state/state.rs:159-168,315-334).
+// TRACE additionally writes the 52 action ids and (wedding flag, re mask, packed eyes, packed tricks) per game.
+template <bool TRACE>
+__global__ void __launch_bounds__(PLAYOUT_THREADS)
+doko_playout_fresh_kernel(RngParams rp, uint64_t n, int4* __restrict__ points, uint32_t* __restrict__ steps,
+                          uint8_t* __restrict__ trace, uint4* __restrict__ aux) {
+    __shared__ uint32_t smem[12 * PLAYOUT_THREADS];
+    uint64_t i = (uint64_t)blockIdx.x * PLAYOUT_THREADS + threadIdx.x;
+    uint64_t gi = i < n ? i : n - 1;
+    SharedDeck deck;
+    deck.base = smem + threadIdx.x;
+    RngKey key = make_key(rp, gi, 0, false);
+    int32_t p[4];
+    uint32_t s, ax[4];
+    uint8_t tr[52];
+    doko_playout_fresh<TRACE>(key, deck, p, s, tr, ax);
+    if (i < n) {
+        if (points) points[i] = make_int4(p[0], p[1], p[2], p[3]);
+        if (steps) steps[i] = s;
+        if (TRACE) {
+            if (trace) for (int k = 0; k < 52; ++k) trace[i * 52 + k] = tr[k];
+            if (aux) aux[i] = make_uint4(ax[0], ax[1], ax[2], ax[3]);
+        }
+    }
+}
+
+// ---- state record I/O --------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load_state(const dk_state* __restrict__ src, dk_state& dst) {
+    const uint4* s4 = reinterpret_cast<const uint4*>(src);
+    uint4* d4 = reinterpret_cast<uint4*>(&dst);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) d4[q] = __ldg(s4 + q);
+}
+__device__ __forceinline__ void store_state(dk_state* __restrict__ dst, const dk_state& src) {
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+    const uint4* s4 = reinterpret_cast<const uint4*>(&src);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) d4[q] = s4[q];
+}
+
+constexpr int STATE_THREADS = 128;
+
+// dk_new_games: FdoState::new_game / DoState::new_game (deal from the stream) → records.
+__global__ void __launch_bounds__(PLAYOUT_THREADS)
+new_games_kernel(RngParams rp, uint64_t n, dk_state* __restrict__ out) {
+    __shared__ uint32_t smem[12 * PLAYOUT_THREADS];
+    uint64_t i = (uint64_t)blockIdx.x * PLAYOUT_THREADS + threadIdx.x;
+    uint64_t gi = i < n ? i : n - 1;
+    SharedDeck deck;
+    deck.base = smem + threadIdx.x;
+    RngKey key = make_key(rp, gi, 0, false);
+    FdoLive dummy;
+    uint32_t ah[4], dup, start;
+    fdo_deal(dummy, key, deck, ah, dup, start);
+    if (i < n) {
+        uint64_t hands[4];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) hands[p] = (uint64_t)ah[p] | ((uint64_t)(ah[p] & dup) << 24);   // copy B = doubled cards
+        alignas(16) dk_state s;
+        st_new_game(s, hands, start);
+        store_state(out + i, s);
+    }
+}
+__global__ void __launch_bounds__(STATE_THREADS)
+from_deals_kernel(uint64_t n, const uint64_t* __restrict__ hands, const uint8_t* __restrict__ start, dk_state* __restrict__ out) {
+    uint64_t i = (uint64_t)blockIdx.x * STATE_THREADS + threadIdx.x;
+    if (i >= n) return;
+    uint64_t h[4] = {hands[4 * i], hands[4 * i + 1], hands[4 * i + 2], hands[4 * i + 3]};
+    alignas(16) dk_state s;
+    st_new_game(s, h, start[i] & 3u);
+    store_state(out + i, s);
+}
+template <int ENGINE>
+__global__ void __launch_bounds__(STATE_THREADS)
+legal_mask_kernel(uint64_t n, const dk_state* __restrict__ states, uint64_t* __restrict__ mask_out) {
+    uint64_t i = (uint64_t)blockIdx.x * STATE_THREADS + threadIdx.x;
+    if (i >= n) return;
+    alignas(16) dk_state s;
+    load_state(states + i, s);
+    mask_out[i] = ENGINE == DK_FDO ? fdo_state_legal_mask(s) : doko_state_legal_mask(s);
+}
+template <int ENGINE>
+__global__ void __launch_bounds__(STATE_THREADS)
+apply_kernel(uint64_t n, dk_state* __restrict__ states, const uint8_t* __restrict__ action, uint32_t flags, uint8_t* __restrict__ err_out) {
+    uint64_t i = (uint64_t)blockIdx.x * STATE_THREADS + threadIdx.x;
+    if (i >= n) return;
+    alignas(16) dk_state s;
+    load_state(states + i, s);
+    uint32_t err = ENGINE == DK_FDO ? fdo_state_apply_az(s, action[i], (flags & DK_APPLY_SKIP_SINGLE) != 0) : doko_state_apply(s, action[i]);
+    if (!err) store_state(states + i, s);
+    if (err_out) err_out[i] = (uint8_t)err;
+}
+__global__ void __launch_bounds__(STATE_THREADS)
+terminal_kernel(uint64_t n, const dk_state* __restrict__ states, uint8_t* __restrict__ done_out, int4* __restrict__ points_out) {
+    uint64_t i = (uint64_t)blockIdx.x * STATE_THREADS + threadIdx.x;
+    if (i >= n) return;
+    uint4 last = __ldg(reinterpret_cast<const uint4*>(states + i) + 7);       // bytes 112..127: eyes, counters, points, meta
+    bool done = (last.w & 3u) == DK_PHASE_FINISHED;
+    if (done_out) done_out[i] = done ? 1 : 0;
+    if (points_out) {
+        uint32_t p = last.z;
+        points_out[i] = done ? make_int4((int8_t)(p & 255u), (int8_t)((p >> 8) & 255u), (int8_t)((p >> 16) & 255u), (int8_t)(p >> 24)) : make_int4(0, 0, 0, 0);
+    }
+}
+
+// ---- observation encode ----------------------------------------------------------------------------------------------------
+// Token values are staged as bytes in shared memory (one padded row per game, odd word pitch → conflict-free when the 32
+// lanes of a warp write the same column), then every warp widens whole rows to i64 with 256-byte-contiguous stores.
+constexpr int ENC_THREADS = 128;
+constexpr int ENC_ROW = 316;   // bytes; 79 words (odd)
+struct SmemRowOut {
+    uint8_t* row;
+    __device__ __forceinline__ void operator()(uint32_t i, uint32_t v) const { row[i] = (uint8_t)v; }
+};
+__device__ __forceinline__ void write_rows(const uint8_t* __restrict__ tok, int len, uint64_t first, uint64_t n, int64_t* __restrict__ out, size_t row_stride) {
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int r = warp; r < ENC_THREADS; r += ENC_THREADS / 32) {
+        uint64_t g = first + r;
+        if (g >= n) break;
+        const uint8_t* src = tok + r * ENC_ROW;
+        int64_t* dst = out + g * row_stride;
+        for (int i = lane; i < len; i += 32) dst[i] = (int64_t)src[i];
+    }
+}
+template <int LAYOUT>
+__global__ void __launch_bounds__(ENC_THREADS)
+encode_kernel(uint64_t n, const dk_state* __restrict__ states, int64_t* __restrict__ out, size_t row_stride) {
+    __shared__ __align__(16) uint8_t tok[ENC_THREADS * ENC_ROW];
+    uint64_t first = (uint64_t)blockIdx.x * ENC_THREADS;
+    uint64_t i = first + threadIdx.x;
+    if (i < n) {
+        alignas(16) dk_state s;
+        load_state(states + i, s);
+        SmemRowOut o{tok + threadIdx.x * ENC_ROW};
+        if (LAYOUT == DK_LAYOUT_FDO_PI311) fdo_encode_pi(s, o); else doko_encode(s, LAYOUT == DK_LAYOUT_DO114, o);
+    }
+    __syncthreads();
+    write_rows(tok, LAYOUT == DK_LAYOUT_FDO_PI311 ? 311 : (LAYOUT == DK_LAYOUT_DO114 ? 114 : 110), first, n, out, row_stride);
+}
+
+// The reference's random pick on a 39-bit mask: index from the most significant set bit (bit_flag.rs:86-94,104-171).
+__device__ __forceinline__ uint32_t pick_msb_rank64(uint64_t mask, uint32_t idx) {
+    uint32_t lo = (uint32_t)mask, hi = (uint32_t)(mask >> 32);
+    uint32_t k = popc(lo) + popc(hi) - 1u - idx, cl = popc(lo);
+    return k < cl ? select_lsb(lo, k) : 32u + select_lsb(hi, k - cl);
+}
+// K5: one lock-step self-play env step + observation: legal mask → one draw (SITE_STEP word 0, unit = game id,
+// epoch = caller's step counter) → play_action [→ skip forced moves] → encode_state_pi of the new state.
+// Algorithmic HBM bytes per game: 128 read + 128 written + 2488 written.
+__global__ void __launch_bounds__(ENC_THREADS)
+fdo_step_encode_kernel(RngParams rp, uint64_t n, dk_state* __restrict__ states, uint32_t flags, int64_t* __restrict__ obs, size_t row_stride,
+                       uint8_t* __restrict__ action_out) {
+    __shared__ __align__(16) uint8_t tok[ENC_THREADS * ENC_ROW];
+    uint64_t first = (uint64_t)blockIdx.x * ENC_THREADS;
+    uint64_t i = first + threadIdx.x;
+    if (i < n) {
+        alignas(16) dk_state s;
+        load_state(states + i, s);
+        uint64_t legal = fdo_state_legal_mask(s);
+        if (!(flags & DK_PLAYOUT_WITH_ANNOUNCEMENTS)) legal &= ~(0x1Full << 33);
+        uint32_t a = 0xFF;
+        if (legal) {
+            RngKey key = make_key(rp, i, 0, false);
+            U4 blk = rng_block(key, SITE_STEP, 0);
+            a = pick_msb_rank64(legal, mulhi(blk.x, popcll(legal)));
+            fdo_state_apply_az(s, a, (flags & DK_STEP_SKIP_SINGLE) != 0);
+            store_state(states + i, s);
+        }
+        if (action_out) action_out[i] = (uint8_t)a;
+        if (obs) { SmemRowOut o{tok + threadIdx.x * ENC_ROW}; fdo_encode_pi(s, o); }
+    }
+    __syncthreads();
+    if (obs) write_rows(tok, 311, first, n, obs, row_stride);
+}
+
+// K2/K4 from stored states: McEnvState::random_rollout (rs-doko-mcts/src/env/envs/env_state_full_doko.rs:198-220) and the
+// with-announcement loop.  unit = first_id + (i / per_unit), unit_hi = i % per_unit when per_unit > 1 (leaf rollouts).
+template <int ENGINE, bool WITH_ANN>
+__global__ void __launch_bounds__(STATE_THREADS)
+playout_state_kernel(RngParams rp, uint64_t n, const dk_state* __restrict__ states, uint32_t per_unit, int4* __restrict__ points,
+                     uint32_t* __restrict__ steps) {
+    uint64_t i = (uint64_t)blockIdx.x * STATE_THREADS + threadIdx.x;
+    if (i >= n) return;
+    uint64_t unit = per_unit > 1u ? i / per_unit : i;
+    RngKey key = make_key(rp, unit, per_unit > 1u ? (uint32_t)(i % per_unit) : 0u, per_unit > 1u);
+    alignas(16) dk_state s;
+    load_state(states + unit, s);
+    int32_t p[4];
+    uint32_t st = 0;
+    if (ENGINE == DK_FDO) {
+        FdoLive g; FdoResume rs;
+        if (fdo_state_to_live(s, g, rs)) { fdo_play_to_end<WITH_ANN, false>(g, key, &rs); fdo_final_points(g, p); st = g.steps; }
+        else { p[0] = s.points[0]; p[1] = s.points[1]; p[2] = s.points[2]; p[3] = s.points[3]; }
+    } else {
+        DokoLive g; DokoResume rs;
+        if (doko_state_to_live(s, g, rs)) { doko_play_to_end<false, false>(g, key, &rs, nullptr); doko_final_points(g, p); st = g.steps; }
+        else { p[0] = s.points[0]; p[1] = s.points[1]; p[2] = s.points[2]; p[3] = s.points[3]; }
+    }
+    if (points) points[i] = make_int4(p[0], p[1], p[2], p[3]);
+    if (steps) steps[i] = st;
 }
 
 }  // namespace dk

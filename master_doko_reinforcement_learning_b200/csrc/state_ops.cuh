@@ -1,0 +1,419 @@
+// state_ops.cuh — operations on the 128-byte dk_state record (include/doko_cuda.h): the batch form of the reference's
+// by-value FdoState / DoState seam (legal-action query, apply action, terminal check, rewards) plus the bridges between the
+// stored record and the register-resident playout form (fdo_rules.cuh / doko_rules.cuh).
+#pragma once
+#include "../../include/doko_cuda.h"
+#include "dk_common.cuh"
+#include "doko_rules.cuh"
+#include "fdo_rules.cuh"
+
+namespace dk {
+
+// ---- field accessors -------------------------------------------------------------------------------------------------------
+DK_HD uint32_t st_phase(const dk_state& s) { return s.meta & 3u; }
+DK_HD uint32_t st_cur(const dk_state& s) { return (s.meta >> 2) & 3u; }
+DK_HD uint32_t st_game_start(const dk_state& s) { return (s.meta >> 4) & 3u; }
+DK_HD uint32_t st_gt(const dk_state& s) { return (s.meta >> 6) & 15u; }
+DK_HD uint32_t st_team_tag(const dk_state& s) { return (s.meta >> 10) & 3u; }
+DK_HD uint32_t st_wed_seat(const dk_state& s) { return (s.meta >> 12) & 3u; }
+DK_HD uint32_t st_solved_idx(const dk_state& s) { return (s.meta >> 14) & 3u; }
+DK_HD uint32_t st_re_mask(const dk_state& s) { return (s.meta >> 16) & 15u; }
+DK_HD uint32_t st_re_low(const dk_state& s) { return (s.meta >> 20) & 7u; }
+DK_HD uint32_t st_ko_low(const dk_state& s) { return (s.meta >> 23) & 7u; }
+DK_HD uint32_t st_turns(const dk_state& s) { return (s.meta >> 26) & 7u; }
+DK_HD uint32_t st_ann_start(const dk_state& s) { return (s.meta >> 29) & 3u; }
+DK_HD uint32_t st_n_tricks(const dk_state& s) { return (s.tricks >> 24) & 15u; }
+DK_HD uint32_t st_n_calls(const dk_state& s) { return (s.tricks >> 28) & 15u; }
+DK_HD uint32_t st_trick_start(const dk_state& s, uint32_t t) { return (s.tricks >> (2u * t)) & 3u; }
+DK_HD void st_set(uint32_t& word, uint32_t shift, uint32_t width, uint32_t v) {
+    uint32_t m = ((1u << width) - 1u) << shift;
+    word = (word & ~m) | ((v << shift) & m);
+}
+DK_HD uint32_t hand_any24(uint64_t h) { return (uint32_t)((h | (h >> 24)) & 0xFFFFFFull); }
+DK_HD uint32_t hand_both24(uint64_t h) { return (uint32_t)((h & (h >> 24)) & 0xFFFFFFull); }
+
+DK_HD void st_clear(dk_state& s) {
+    for (int p = 0; p < 4; ++p) { s.hands[p] = 0; s.reservations[p] = 0xFF; s.eyes[p] = 0; s.points[p] = 0; }
+    for (int i = 0; i < 48; ++i) s.cards[i] = 0xFF;
+    for (int i = 0; i < 12; ++i) s.announcements[i] = 0xFFFF;
+    s.tricks = 0; s.num_tricks = 0; s.card_index = 0; s.n_reservations = 0; s.meta = 0;
+}
+// new_game_from_hand_and_start_player (rs-full-doko/src/state/state.rs:125-166, rs-doko/src/state/state.rs:115-157)
+DK_HD void st_new_game(dk_state& s, const uint64_t hands[4], uint32_t start) {
+    st_clear(s);
+    for (int p = 0; p < 4; ++p) s.hands[p] = hands[p];
+    uint32_t m = 0;
+    m |= (uint32_t)DK_PHASE_RESERVATION;
+    m |= start << 2; m |= start << 4; m |= (uint32_t)DK_GT_NONE << 6; m |= (uint32_t)DK_TEAM_IN_RESERVATIONS << 10;
+    s.meta = m;
+}
+
+// =====================================================================================================================
+// rs-full-doko
+// =====================================================================================================================
+DK_HD uint32_t fdo_res_code_from_action(uint32_t a) {   // action 24..32 → FdoReservation code (reservation.rs:11-24)
+    // 24 Healthy 0, 25 Wedding 1, 26 ♦ 2, 27 ♥ 3, 28 ♠ 4, 29 ♣ 5, 30 Trumpless 8, 31 Queens 6, 32 Jacks 7
+    return a <= 29u ? a - 24u : (a == 30u ? 8u : a - 25u);
+}
+DK_HD uint32_t fdo_action_from_res_code(uint32_t r) { return r <= 5u ? r + 24u : (r == 8u ? 30u : r + 25u); }
+DK_HD uint32_t fdo_gt_from_res_code(uint32_t r) {       // solo reservation → FdoGameType (reservation_winning_logic.rs:16-32)
+    // ♦2→2 ♥3→3 ♠4→4 ♣5→5 Queens6→7 Jacks7→8 Trumpless8→6
+    return r <= 5u ? r : (r == 8u ? 6u : r + 1u);
+}
+// The call a seat may make in the announcement phase (level 1..5) or 0.
+DK_HD uint32_t fdo_state_allowed_call(const dk_state& s, uint32_t seat) {
+    uint32_t tag = st_team_tag(s);
+    if (tag == TEAM_WEDDING_UNSOLVED || tag == TEAM_IN_RESERVATIONS) return 0;
+    uint32_t w = tag == TEAM_WEDDING_SOLVED ? st_solved_idx(s) : 0u;
+    bool is_re = (st_re_mask(s) >> seat) & 1u;
+    uint32_t m = is_re ? st_re_low(s) : st_ko_low(s), e = is_re ? st_ko_low(s) : st_re_low(s);
+    return fdo_allowed_call(popcll(s.hands[seat]), m, e, w);
+}
+// FdoAllowedActions::calculate_allowed_actions (rs-full-doko/src/action/allowed_actions.rs:68-169); Finished → 0.
+DK_HD uint64_t fdo_state_legal_mask(const dk_state& s) {
+    uint32_t phase = st_phase(s), cur = st_cur(s);
+    if (phase == DK_PHASE_RESERVATION) {
+        uint64_t m = (1ull << 24) | (0x7Full << 26);
+        if ((hand_both24(s.hands[cur]) >> CARD_CQ) & 1u) m |= 1ull << 25;
+        return m;
+    }
+    if (phase == DK_PHASE_ANNOUNCEMENT) {
+        uint32_t call = fdo_state_allowed_call(s, cur);
+        return (1ull << 38) | (call ? (1ull << (32u + call)) : 0ull);
+    }
+    if (phase == DK_PHASE_PLAY_CARD) {
+        uint32_t single = hand_any24(s.hands[cur]);
+        uint32_t ci = s.card_index, k = ci & 3u;
+        if (k == 0u || st_n_tricks(s) >= 12u) return single;       // state.rs:360-372: no colour in the 12th trick
+        uint32_t first = s.cards[ci - k];
+        uint32_t f = single & follow_mask(first, trump_mask_for_game_type(st_gt(s)));
+        return f ? f : single;
+    }
+    return 0;
+}
+// internal_progress (announcement.rs:130-175) from seat p; sets phase / current seat / turns.
+DK_HD void fdo_state_progress(dk_state& s, uint32_t p) {
+    uint32_t turns = st_turns(s);
+    for (;;) {
+        if (turns == 4u) {                                          // RoundIsOver(starting_player)
+            st_set(s.meta, 0, 2, DK_PHASE_PLAY_CARD);
+            st_set(s.meta, 2, 2, st_ann_start(s));
+            break;
+        }
+        if (fdo_state_allowed_call(s, p) == 0u) { turns++; p = (p + 1u) & 3u; continue; }
+        st_set(s.meta, 0, 2, DK_PHASE_ANNOUNCEMENT);
+        st_set(s.meta, 2, 2, p);
+        break;
+    }
+    st_set(s.meta, 26, 3, turns);
+}
+// progress_next_card_or_announcement (state.rs:184-206) = start_round(current seat)
+DK_HD void fdo_state_start_round(dk_state& s) {
+    st_set(s.meta, 26, 3, 0u);
+    st_set(s.meta, 29, 2, st_cur(s));
+    fdo_state_progress(s, st_cur(s));
+}
+// Winner of completed trick t from the history (trick_winning_player_logic.rs:15-45).
+DK_HD uint32_t fdo_state_trick_winner(const dk_state& s, uint32_t t, uint32_t trump, uint32_t* win_card, uint32_t* eyes, uint32_t* fox_mask) {
+    uint32_t c0 = s.cards[4u * t];
+    uint32_t follow = follow_mask(c0, trump);
+    uint32_t best = 0, bestk = 0, bestc = c0, e = 0, fm = 0;
+    for (uint32_t k = 0; k < 4u; ++k) {
+        uint32_t c = s.cards[4u * t + k];
+        uint32_t pw = card_power(c, trump, follow);
+        if (k == 0u || pw > best) { best = pw; bestk = k; bestc = c; }
+        e += card_eyes_by_rank(c - 6u * card_suit(c));
+        if (c == CARD_DA) fm |= 1u << k;
+    }
+    if (win_card) *win_card = bestc;
+    if (eyes) *eyes = e;
+    if (fox_mask) *fox_mask = fm;
+    return (st_trick_start(s, t) + bestk) & 3u;
+}
+// FdoEndOfGameStats::calculate (stats/stats.rs:46-240) from the stored history.
+DK_HD void fdo_state_final_points(dk_state& s, uint32_t last_winner, uint32_t last_win_card) {
+    uint32_t re = st_re_mask(s), trump = trump_mask_for_game_type(st_gt(s));
+    uint32_t re_eyes = 0, re_tricks = 0;
+    for (uint32_t p = 0; p < 4u; ++p)
+        if ((re >> p) & 1u) { re_eyes += s.eyes[p]; re_tricks += (s.num_tricks >> (4u * p)) & 15u; }
+    int32_t extras = 0;
+    if (popc(re) != 1u) {
+        for (uint32_t t = 0; t < 12u; ++t) {
+            uint32_t e, fm;
+            uint32_t w = t < 11u ? st_trick_start(s, t + 1u) : last_winner;
+            (void)fdo_state_trick_winner(s, t, trump, nullptr, &e, &fm);
+            bool won_re = (re >> w) & 1u;
+            if (e >= 40u) extras += won_re ? 1 : -1;                                  // doppelkopf.rs:8-26
+            for (uint32_t k = 0; k < 4u; ++k)
+                if ((fm >> k) & 1u) {                                                  // fuchs_gefangen.rs:9-60
+                    bool played_re = (re >> ((st_trick_start(s, t) + k) & 3u)) & 1u;
+                    if (played_re != won_re) extras += won_re ? 1 : -1;
+                }
+        }
+        if (last_win_card == CARD_CJ) extras += ((re >> last_winner) & 1u) ? 1 : -1;  // last_trick_karlchen.rs:6-27
+    }
+    int32_t ko;
+    int32_t rp = fdo_score(re_eyes, re_tricks, popc(re), st_re_low(s), st_ko_low(s), extras, &ko);
+    for (uint32_t p = 0; p < 4u; ++p) s.points[p] = (int8_t)(((re >> p) & 1u) ? rp : ko);
+}
+// FdoState::play_action (rs-full-doko/src/state/state.rs:208-358).  Returns 0, or 1 if the action is not legal
+// (the reference would panic); the state is unchanged in that case.
+DK_HD uint32_t fdo_state_apply(dk_state& s, uint32_t action) {
+    if (action >= 39u || !((fdo_state_legal_mask(s) >> action) & 1ull)) return 1;
+    uint32_t phase = st_phase(s), cur = st_cur(s);
+    if (phase == DK_PHASE_RESERVATION) {
+        s.reservations[s.n_reservations++] = (uint8_t)fdo_res_code_from_action(action);
+        uint32_t next = (cur + 1u) & 3u;
+        st_set(s.meta, 2, 2, next);
+        if (s.n_reservations == 4u) {
+            uint32_t start = st_game_start(s);
+            uint32_t solo_i = 4, wed_i = 4;
+            for (uint32_t i = 0; i < 4u; ++i) {
+                uint32_t r = s.reservations[i];
+                if (r >= 2u && solo_i == 4u) solo_i = i;
+                if (r == 1u) wed_i = i;
+            }
+            uint32_t gt, tag, re = 0, wed = 0;
+            if (solo_i < 4u) { gt = fdo_gt_from_res_code(s.reservations[solo_i]); tag = TEAM_NO_WEDDING; re = 1u << ((start + solo_i) & 3u); }
+            else if (wed_i < 4u) { gt = GT_WEDDING; tag = TEAM_WEDDING_UNSOLVED; wed = (start + wed_i) & 3u; }
+            else {
+                gt = GT_NORMAL; tag = TEAM_NO_WEDDING;
+                for (uint32_t p = 0; p < 4u; ++p) if ((hand_any24(s.hands[p]) >> CARD_CQ) & 1u) re |= 1u << p;
+            }
+            st_set(s.meta, 6, 4, gt); st_set(s.meta, 10, 2, tag); st_set(s.meta, 12, 2, wed); st_set(s.meta, 16, 4, re);
+            s.tricks = (s.tricks & 0xF0000000u) | next | (1u << 24);        // trick 0 led by the start seat
+            fdo_state_start_round(s);
+        }
+        return 0;
+    }
+    if (phase == DK_PHASE_ANNOUNCEMENT) {
+        uint32_t turns = st_turns(s);
+        if (action == 38u) turns++;
+        else {
+            turns = 0;
+            uint32_t level = action - 32u;                                   // 33 → ReContra even for a counter (action.rs:297-299)
+            uint32_t n = st_n_calls(s);
+            if (n < 12u) { s.announcements[n] = (uint16_t)(s.card_index | (cur << 6) | (level << 8)); st_set(s.tricks, 28, 4, n + 1u); }
+            if ((st_re_mask(s) >> cur) & 1u) st_set(s.meta, 20, 3, level); else st_set(s.meta, 23, 3, level);
+        }
+        st_set(s.meta, 26, 3, turns);
+        fdo_state_progress(s, (cur + 1u) & 3u);
+        return 0;
+    }
+    // card
+    uint32_t c = action;
+    uint64_t h = s.hands[cur];
+    if ((h >> (c + 24u)) & 1ull) h &= ~(1ull << (c + 24u)); else h &= ~(1ull << c);   // hand.remove: copy B first
+    s.hands[cur] = h;
+    uint32_t ci = s.card_index;
+    s.cards[ci] = (uint8_t)c;
+    s.card_index = (uint8_t)(ci + 1u);
+    if (((ci + 1u) & 3u) == 0u) {
+        uint32_t t = ci >> 2, trump = trump_mask_for_game_type(st_gt(s)), wc, e;
+        uint32_t w = fdo_state_trick_winner(s, t, trump, &wc, &e, nullptr);
+        s.eyes[w] = (uint8_t)(s.eyes[w] + e);
+        s.num_tricks = (uint16_t)(s.num_tricks + (1u << (4u * w)));
+        if (st_team_tag(s) == TEAM_WEDDING_UNSOLVED) {                       // team_logic.rs:59-112
+            uint32_t wed = st_wed_seat(s);
+            if (w != wed) { st_set(s.meta, 10, 2, TEAM_WEDDING_SOLVED); st_set(s.meta, 14, 2, t); st_set(s.meta, 16, 4, (1u << wed) | (1u << w)); }
+            else if (t == 2u) { st_set(s.meta, 10, 2, TEAM_WEDDING_SOLVED); st_set(s.meta, 14, 2, 2u); st_set(s.meta, 16, 4, 1u << wed); }
+        }
+        if (t == 11u) {
+            st_set(s.meta, 0, 2, DK_PHASE_FINISHED);
+            st_set(s.meta, 2, 2, 0u);
+            fdo_state_final_points(s, w, wc);
+            return 0;
+        }
+        st_set(s.meta, 2, 2, w);
+        st_set(s.tricks, 2u * (t + 1u), 2, w);
+        st_set(s.tricks, 24, 4, t + 2u);
+        fdo_state_start_round(s);
+        return 0;
+    }
+    st_set(s.meta, 2, 2, (cur + 1u) & 3u);
+    fdo_state_start_round(s);
+    return 0;
+}
+// FdoAzEnvState::take_action_by_action_index(action, skip_single, _) (rs-doko-alpha-zero/src/env/envs/full_doko/full_doko.rs:121-154):
+// after the action, keep playing while exactly one non-call action is legal.
+DK_HD uint32_t fdo_state_apply_az(dk_state& s, uint32_t action, bool skip_single) {
+    uint32_t err = fdo_state_apply(s, action);
+    if (err || !skip_single) return err;
+    const uint64_t calls = 0x1Full << 33;
+    for (;;) {
+        if (st_phase(s) == DK_PHASE_FINISHED) break;
+        uint64_t m = fdo_state_legal_mask(s) & ~calls;
+        if (popcll(m) != 1u) break;
+        fdo_state_apply(s, ffs0ll(m));
+    }
+    return 0;
+}
+
+// Bridge: stored state → register-resident playout form.  Returns false when the game is already finished.
+DK_HD bool fdo_state_to_live(const dk_state& s, FdoLive& g, FdoResume& rs) {
+    fdo_live_clear(g);
+    uint32_t phase = st_phase(s);
+    if (phase == DK_PHASE_FINISHED) return false;
+    uint32_t any[4], dup = 0;
+    for (uint32_t p = 0; p < 4u; ++p) { any[p] = hand_any24(s.hands[p]); dup |= hand_both24(s.hands[p]); }
+    g.dup = dup;
+    rs.n_res = s.n_reservations;
+    rs.t0 = 0; rs.k0 = 0; rs.starts = 0; rs.ann_ci = 0; rs.ann_p = 0; rs.ann_turns = 0xFFFFFFFFu;
+    rs.acc.follow = 0; rs.acc.best = 0; rs.acc.bestk = 0; rs.acc.bestc = 0; rs.acc.teyes = 0; rs.acc.foxm = 0;
+    for (uint32_t i = 0; i < 4u; ++i) rs.res_action[i] = i < s.n_reservations ? fdo_action_from_res_code(s.reservations[i]) : 0u;
+    uint32_t base;
+    if (phase == DK_PHASE_RESERVATION) {
+        base = st_game_start(s);
+    } else {
+        uint32_t ci = s.card_index, t0 = ci >> 2, k0 = ci & 3u;
+        g.gt = st_gt(s); g.trump = trump_mask_for_game_type(g.gt);
+        g.team_tag = st_team_tag(s); g.re_mask = st_re_mask(s); g.wed_seat = st_wed_seat(s); g.solved_idx = st_solved_idx(s);
+        g.re_low = st_re_low(s); g.ko_low = st_ko_low(s);
+        for (uint32_t p = 0; p < 4u; ++p) { g.eyes |= (uint32_t)s.eyes[p] << (8u * p); }
+        g.ntricks = s.num_tricks;
+        for (uint32_t t = 0; t < t0; ++t) {                                  // trackers of the completed tricks
+            uint32_t e, fm, w = st_trick_start(s, t + 1u);
+            (void)fdo_state_trick_winner(s, t, g.trump, nullptr, &e, &fm);
+            if (e >= 40u) g.dkc += 1u << (4u * w);
+            for (uint32_t k = 0; k < 4u; ++k)
+                if ((fm >> k) & 1u) g.foxes = (g.foxes << 5) | 16u | (((st_trick_start(s, t) + k) & 3u) << 2) | w;
+            rs.starts |= st_trick_start(s, t) << (2u * t);
+            g.last_winner = w;
+        }
+        base = st_trick_start(s, t0);
+        rs.t0 = t0; rs.k0 = k0;
+        for (uint32_t k = 0; k < k0; ++k) {                                  // partial trick
+            uint32_t c = s.cards[4u * t0 + k];
+            if (k == 0u) rs.acc.follow = follow_mask(c, g.trump);
+            uint32_t pw = card_power(c, g.trump, rs.acc.follow);
+            if (k == 0u || pw > rs.acc.best) { rs.acc.best = pw; rs.acc.bestk = k; rs.acc.bestc = c; }
+            rs.acc.teyes += card_eyes_by_rank(c - 6u * card_suit(c));
+            if (c == CARD_DA) rs.acc.foxm |= 1u << k;
+        }
+        if (phase == DK_PHASE_ANNOUNCEMENT) { rs.ann_ci = ci; rs.ann_p = st_cur(s); rs.ann_turns = st_turns(s); }
+        else { rs.ann_ci = ci + 1u; rs.ann_turns = 0xFFFFFFFFu; }            // the round before card ci is over
+    }
+    g.base = base;
+    g.h0 = any[base]; g.h1 = any[(base + 1u) & 3u]; g.h2 = any[(base + 2u) & 3u]; g.h3 = any[(base + 3u) & 3u];
+    return true;
+}
+
+// =====================================================================================================================
+// rs-doko
+// =====================================================================================================================
+// calculate_allowed_actions_in_normal_game (rs-doko/src/action/allowed_actions.rs:131-198)
+DK_HD uint64_t doko_state_legal_mask(const dk_state& s) {
+    uint32_t phase = st_phase(s), cur = st_cur(s);
+    if (phase == DK_PHASE_RESERVATION) return (1ull << 24) | (((hand_both24(s.hands[cur]) >> CARD_CQ) & 1u) ? (1ull << 25) : 0ull);
+    if (phase == DK_PHASE_PLAY_CARD) {
+        uint32_t single = hand_any24(s.hands[cur]);
+        uint32_t ci = s.card_index, k = ci & 3u;
+        if (k == 0u) return single;
+        uint32_t f = single & follow_mask(s.cards[ci - k], DOKO_TRUMP_MASK);
+        return f ? f : single;
+    }
+    return 0;
+}
+DK_HD uint32_t doko_state_trick_winner(const dk_state& s, uint32_t t, uint32_t* eyes) {
+    uint32_t follow = follow_mask(s.cards[4u * t], DOKO_TRUMP_MASK);
+    uint32_t best = 0, bestk = 0, e = 0;
+    for (uint32_t k = 0; k < 4u; ++k) {
+        uint32_t c = s.cards[4u * t + k];
+        uint32_t pw = card_power(c, DOKO_TRUMP_MASK, follow);
+        if (k == 0u || pw > best) { best = pw; bestk = k; }
+        e += card_eyes_by_rank(c - 6u * card_suit(c));
+    }
+    *eyes = e;
+    return (st_trick_start(s, t) + bestk) & 3u;
+}
+// DoState::play_action (rs-doko/src/state/state.rs:189-309)
+DK_HD uint32_t doko_state_apply(dk_state& s, uint32_t action) {
+    if (action >= 26u || !((doko_state_legal_mask(s) >> action) & 1ull)) return 1;
+    uint32_t phase = st_phase(s), cur = st_cur(s);
+    if (phase == DK_PHASE_RESERVATION) {
+        s.reservations[s.n_reservations++] = (uint8_t)(action == 25u ? 0u : 1u);   // DoReservation: Wedding 0, Healthy 1
+        uint32_t next = (cur + 1u) & 3u;
+        st_set(s.meta, 2, 2, next);
+        if (s.n_reservations == 4u) {
+            uint32_t start = st_game_start(s), wed_i = 4;
+            for (uint32_t i = 0; i < 4u; ++i) if (s.reservations[i] == 0u) wed_i = i;
+            uint32_t re = 0;
+            if (wed_i < 4u) { st_set(s.meta, 6, 4, GT_WEDDING); st_set(s.meta, 10, 2, TEAM_WEDDING_UNSOLVED); st_set(s.meta, 12, 2, (start + wed_i) & 3u); }
+            else {
+                for (uint32_t p = 0; p < 4u; ++p) if ((hand_any24(s.hands[p]) >> CARD_CQ) & 1u) re |= 1u << p;
+                st_set(s.meta, 6, 4, GT_NORMAL); st_set(s.meta, 10, 2, TEAM_NO_WEDDING); st_set(s.meta, 16, 4, re);
+            }
+            s.tricks = next | (1u << 24);
+            st_set(s.meta, 0, 2, DK_PHASE_PLAY_CARD);
+        }
+        return 0;
+    }
+    uint32_t c = action;
+    uint64_t h = s.hands[cur];
+    if ((h >> c) & 1ull) h &= ~(1ull << c); else h &= ~(1ull << (c + 24u));       // hand_remove: copy A first (rs-doko/src/hand/hand.rs:38-46)
+    s.hands[cur] = h;
+    uint32_t ci = s.card_index;
+    s.cards[ci] = (uint8_t)c;
+    s.card_index = (uint8_t)(ci + 1u);
+    if (((ci + 1u) & 3u) == 0u) {
+        uint32_t t = ci >> 2, e;
+        uint32_t w = doko_state_trick_winner(s, t, &e);
+        s.eyes[w] = (uint8_t)(s.eyes[w] + e);
+        s.num_tricks = (uint16_t)(s.num_tricks + (1u << (4u * w)));
+        if (st_team_tag(s) == TEAM_WEDDING_UNSOLVED) {
+            uint32_t wed = st_wed_seat(s);
+            if (w != wed) { st_set(s.meta, 10, 2, TEAM_WEDDING_SOLVED); st_set(s.meta, 14, 2, t); st_set(s.meta, 16, 4, (1u << wed) | (1u << w)); }
+            else if (t == 2u) { st_set(s.meta, 10, 2, TEAM_WEDDING_SOLVED); st_set(s.meta, 14, 2, 2u); st_set(s.meta, 16, 4, 1u << wed); }
+        }
+        if (t == 11u) {
+            st_set(s.meta, 0, 2, DK_PHASE_FINISHED);
+            st_set(s.meta, 2, 2, 0u);
+            DokoLive g; doko_live_clear(g);
+            g.re_mask = st_re_mask(s); g.ntricks = s.num_tricks;
+            for (uint32_t p = 0; p < 4u; ++p) g.eyes |= (uint32_t)s.eyes[p] << (8u * p);
+            int32_t pts[4]; doko_final_points(g, pts);
+            for (uint32_t p = 0; p < 4u; ++p) s.points[p] = (int8_t)pts[p];
+            return 0;
+        }
+        st_set(s.meta, 2, 2, w);
+        st_set(s.tricks, 2u * (t + 1u), 2, w);
+        st_set(s.tricks, 24, 4, t + 2u);
+        return 0;
+    }
+    st_set(s.meta, 2, 2, (cur + 1u) & 3u);
+    return 0;
+}
+DK_HD bool doko_state_to_live(const dk_state& s, DokoLive& g, DokoResume& rs) {
+    doko_live_clear(g);
+    uint32_t phase = st_phase(s);
+    if (phase == DK_PHASE_FINISHED) return false;
+    uint32_t any[4], dup = 0;
+    for (uint32_t p = 0; p < 4u; ++p) { any[p] = hand_any24(s.hands[p]); dup |= hand_both24(s.hands[p]); }
+    g.dup = dup;
+    rs.n_res = s.n_reservations; rs.t0 = 0; rs.k0 = 0;
+    rs.acc.follow = 0; rs.acc.best = 0; rs.acc.bestk = 0; rs.acc.teyes = 0;
+    for (uint32_t i = 0; i < 4u; ++i) rs.res_action[i] = i < s.n_reservations ? (s.reservations[i] == 0u ? 25u : 24u) : 0u;
+    uint32_t base;
+    if (phase == DK_PHASE_RESERVATION) base = st_game_start(s);
+    else {
+        uint32_t ci = s.card_index, t0 = ci >> 2, k0 = ci & 3u;
+        g.team_tag = st_team_tag(s); g.re_mask = st_re_mask(s); g.wed_seat = st_wed_seat(s); g.solved_idx = st_solved_idx(s);
+        g.wedding = st_gt(s) == GT_WEDDING ? 1u : 0u;
+        for (uint32_t p = 0; p < 4u; ++p) g.eyes |= (uint32_t)s.eyes[p] << (8u * p);
+        g.ntricks = s.num_tricks;
+        base = st_trick_start(s, t0);
+        rs.t0 = t0; rs.k0 = k0;
+        for (uint32_t k = 0; k < k0; ++k) {
+            uint32_t c = s.cards[4u * t0 + k];
+            if (k == 0u) rs.acc.follow = follow_mask(c, DOKO_TRUMP_MASK);
+            uint32_t pw = card_power(c, DOKO_TRUMP_MASK, rs.acc.follow);
+            if (k == 0u || pw > rs.acc.best) { rs.acc.best = pw; rs.acc.bestk = k; }
+            rs.acc.teyes += card_eyes_by_rank(c - 6u * card_suit(c));
+        }
+    }
+    g.base = base;
+    g.h0 = any[base]; g.h1 = any[(base + 1u) & 3u]; g.h2 = any[(base + 2u) & 3u]; g.h3 = any[(base + 3u) & 3u];
+    return true;
+}
+
+}  // namespace dk

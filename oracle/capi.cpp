@@ -129,6 +129,29 @@ ORC_API int orc_fdo_random_step_philox(void* h, uint64_t seed, uint64_t unit, ui
     return fin ? -1 : a;
 }
 
+// One lock-step env step with the SITE_STEP contract (word 0, unit = game id, epoch = caller's step counter):
+// allowed actions (minus the five call actions unless with_announcements) → MSB-rank pick → play_action
+// [→ skip_single: keep playing while exactly one non-call action is legal, full_doko.rs:127-151].  Returns the action or -1.
+ORC_API int orc_fdo_step_site(void* h, uint64_t seed, uint64_t unit, uint32_t epoch, int with_announcements, int skip_single) {
+    fdo::State& s = *(fdo::State*)h;
+    if (s.current_phase == fdo::PH_FINISHED) return -1;
+    uint64_t allowed = s.allowed_actions();
+    if (!with_announcements) allowed &= ~fdo::ANNOUNCEMENT_CALL_ACTIONS;
+    uint32_t w = philox_word(seed, (uint32_t)unit, (uint32_t)(unit >> 32), epoch, SITE_STEP, 0);
+    uint64_t bit = select_by_rank(allowed, mul_shift(w, popcount64(allowed)));
+    int a = __builtin_ctzll(bit);
+    s.play_action(a);
+    if (skip_single) {
+        for (;;) {
+            if (s.current_phase == fdo::PH_FINISHED) break;
+            uint64_t m = s.allowed_actions() & ~fdo::ANNOUNCEMENT_CALL_ACTIONS;
+            if (popcount64(m) != 1) break;
+            s.play_action(__builtin_ctzll(m));
+        }
+    }
+    return a;
+}
+
 // ---- dk_state export / import (layout documented in include/doko_cuda.h) -----------------------------
 static void export_fdo(const fdo::State& s, dk_state* o) {
     std::memset(o, 0, sizeof *o);

@@ -10,6 +10,8 @@
 #include "../../master_doko_reinforcement_learning_b200/csrc/dk_common.cuh"
 #include "../../master_doko_reinforcement_learning_b200/csrc/fdo_rules.cuh"
 #include "../../master_doko_reinforcement_learning_b200/csrc/doko_rules.cuh"
+#include "../../master_doko_reinforcement_learning_b200/csrc/state_ops.cuh"
+#include "../../master_doko_reinforcement_learning_b200/csrc/encode.cuh"
 
 #define SIM_API extern "C" __attribute__((visibility("default")))
 
@@ -56,3 +58,31 @@ SIM_API uint32_t sim_select_lsb(uint32_t x, uint32_t k) { return dk::select_lsb(
 SIM_API uint32_t sim_card_power(uint32_t c, uint32_t trump, uint32_t follow) { return dk::card_power(c, trump, follow); }
 SIM_API uint32_t sim_trump_mask(uint32_t gt) { return dk::trump_mask_for_game_type(gt); }
 SIM_API uint32_t sim_follow_mask(uint32_t c, uint32_t trump) { return dk::follow_mask(c, trump); }
+
+// ---- state record ops ------------------------------------------------------------------------------------------------
+SIM_API void sim_new_game(dk_state* s, const uint64_t hands[4], uint32_t start) { dk::st_new_game(*s, hands, start); }
+SIM_API uint64_t sim_legal_mask(int engine, const dk_state* s) { return engine == DK_FDO ? dk::fdo_state_legal_mask(*s) : dk::doko_state_legal_mask(*s); }
+SIM_API uint32_t sim_apply(int engine, dk_state* s, uint32_t action, uint32_t flags) {
+    return engine == DK_FDO ? dk::fdo_state_apply_az(*s, action, (flags & DK_APPLY_SKIP_SINGLE) != 0) : dk::doko_state_apply(*s, action);
+}
+namespace { struct RowOut { int64_t* row; void operator()(uint32_t i, uint32_t v) { row[i] = (int64_t)v; } }; }
+SIM_API void sim_encode(int layout, const dk_state* s, int64_t* out) {
+    RowOut o{out};
+    if (layout == DK_LAYOUT_FDO_PI311) dk::fdo_encode_pi(*s, o); else dk::doko_encode(*s, layout == DK_LAYOUT_DO114, o);
+}
+SIM_API int sim_playout_from_state(int engine, const dk_state* s, uint64_t seed, uint64_t unit_lo_hi, uint32_t unit_hi, uint32_t epoch, int with_ann, int32_t* points, uint32_t* steps) {
+    dk::RngKey key = make_key(seed, unit_lo_hi, epoch);
+    key.unit_hi = unit_hi;
+    if (engine == DK_FDO) {
+        dk::FdoLive g; dk::FdoResume rs;
+        if (!dk::fdo_state_to_live(*s, g, rs)) { for (int p = 0; p < 4; ++p) points[p] = s->points[p]; *steps = 0; return 0; }
+        if (with_ann) dk::fdo_play_to_end<true, false>(g, key, &rs); else dk::fdo_play_to_end<false, false>(g, key, &rs);
+        dk::fdo_final_points(g, points); *steps = g.steps;
+    } else {
+        dk::DokoLive g; dk::DokoResume rs;
+        if (!dk::doko_state_to_live(*s, g, rs)) { for (int p = 0; p < 4; ++p) points[p] = s->points[p]; *steps = 0; return 0; }
+        dk::doko_play_to_end<false, false>(g, key, &rs, nullptr);
+        dk::doko_final_points(g, points); *steps = g.steps;
+    }
+    return 1;
+}

@@ -1,0 +1,38 @@
+"""ctypes binding of tests/hostsim/libhostsim.so — TEST INFRASTRUCTURE ONLY (CPU execution of the per-thread kernel logic)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+DIR = os.path.join(HERE, "hostsim")
+LIB = os.path.join(DIR, "libhostsim.so")
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is None:
+        subprocess.check_call(["make", "-s", "-C", DIR])
+        L = C.CDLL(LIB)
+        vp, u64, u32, i32 = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int
+        L.sim_legal_mask.restype = u64
+        L.sim_legal_mask.argtypes = [i32, vp]
+        L.sim_apply.restype = u32
+        L.sim_apply.argtypes = [i32, vp, u32, u32]
+        L.sim_new_game.argtypes = [vp, vp, u32]
+        L.sim_encode.argtypes = [i32, vp, vp]
+        L.sim_playout_from_state.argtypes = [i32, vp, u64, u64, u32, u32, i32, vp, vp]
+        L.sim_fdo_playout_fresh.argtypes = [u64, u32, u64, u64, i32, vp, vp]
+        L.sim_doko_playout_fresh.argtypes = [u64, u32, u64, u64, vp, vp, vp, vp]
+        L.sim_fdo_score.restype = i32
+        L.sim_fdo_score.argtypes = [u32, u32, u32, u32, u32, i32, vp]
+        for n in ("sim_fdo_allowed_call", "sim_select_lsb24", "sim_select_lsb", "sim_card_power", "sim_trump_mask", "sim_follow_mask"):
+            getattr(L, n).restype = u32
+        _lib = L
+    return _lib
+
+
+def ptr(a):
+    return a.ctypes.data_as(C.c_void_p)

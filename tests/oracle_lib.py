@@ -105,6 +105,7 @@ def load():
     L.orc_fdo_visible_reservations.argtypes = [vp, i32, vp]
     L.orc_doko_encode.argtypes = [vp, i32, vp]
     L.orc_fdo_random_step_philox.argtypes = [vp, u64, u64, u32, i32, u32]
+    L.orc_fdo_step_site.argtypes = [vp, u64, u64, u32, i32, i32]
     L.orc_doko_random_step_philox.argtypes = [vp, u64, u64, u32]
     L.orc_fdo_hand_plus.restype = u64
     L.orc_fdo_hand_plus.argtypes = [u64, u64]
@@ -217,6 +218,9 @@ class Fdo:
 
     def random_step(self, seed, unit, epoch=0, with_announcements=True, ann_ordinal=0):
         return self.L.orc_fdo_random_step_philox(self.h, seed, unit, epoch, int(with_announcements), ann_ordinal)
+
+    def step_site(self, seed, unit, epoch, with_announcements=True, skip_single=False):
+        return self.L.orc_fdo_step_site(self.h, seed, unit, epoch, int(with_announcements), int(skip_single))
 
     def card_matching(self, seed, unit, sample, epoch=0):
         hands = (C.c_uint64 * 4)()

@@ -1,0 +1,161 @@
+"""GPU parity of the state-record API (new games, legal mask, apply, terminal, encode, lock-step step+encode, playouts from
+states) against the oracle, batch-wise through the C ABI."""
+import numpy as np
+import pytest
+
+import oracle_lib
+from oracle_lib import DK_STATE_DTYPE, Doko, Fdo
+
+pytestmark = pytest.mark.gpu
+SEED = 0xD0C05EED
+
+
+@pytest.fixture(scope="module")
+def dk():
+    import master_doko_reinforcement_learning_b200 as pkg
+
+    return pkg.DokoCuda(0)
+
+
+def recs(t):
+    return np.frombuffer(t.cpu().numpy().tobytes(), dtype=DK_STATE_DTYPE)
+
+
+def oracle_recs(objs):
+    return np.array([o.export() for o in objs], dtype=DK_STATE_DTYPE)
+
+
+@pytest.mark.parametrize("engine", [0, 1])
+def test_new_games_and_lockstep_walk(dk, orc, engine):
+    """Walk n games to the end with oracle-chosen random legal actions; compare every record, mask, encoding each step."""
+    import torch
+
+    import master_doko_reinforcement_learning_b200 as pkg
+
+    n = 192
+    rng = dk.rng(SEED, 5000, 3)
+    states = dk.new_games(engine, n, rng)
+    cls = Fdo if engine == 1 else Doko
+    objs = [cls.new_game_philox(orc, SEED, 5000 + i, 3) for i in range(n)]
+    prng = np.random.default_rng(7)
+    layouts = [pkg.DK_LAYOUT_FDO_PI311] if engine == 1 else [pkg.DK_LAYOUT_DO110, pkg.DK_LAYOUT_DO114]
+    for step in range(400):
+        torch.cuda.synchronize()
+        assert recs(states).tobytes() == oracle_recs(objs).tobytes(), f"step {step}"
+        masks = dk.legal_mask(engine, states).cpu().numpy().astype(np.uint64)
+        exp = np.array([o.allowed() for o in objs], dtype=np.uint64)
+        assert np.array_equal(masks, exp)
+        if step % 5 == 0:
+            for lay in layouts:
+                enc = dk.encode(lay, states).cpu().numpy()
+                if engine == 1:
+                    ref = np.stack([o.encode_pi() for o in objs])
+                else:
+                    ref = np.stack([o.encode(lay == pkg.DK_LAYOUT_DO114) for o in objs])
+                assert np.array_equal(enc, ref)
+        done, pts = dk.terminal(engine, states)
+        done = done.cpu().numpy()
+        assert np.array_equal(done != 0, exp == 0)
+        if (exp == 0).all():
+            assert np.array_equal(pts.cpu().numpy(), np.array([o.info()["points"] for o in objs], dtype=np.int32))
+            break
+        acts = np.zeros(n, dtype=np.uint8)
+        for i, m in enumerate(exp):
+            m = int(m)
+            if m == 0:
+                acts[i] = 0        # illegal on a finished game → err flag, state unchanged
+                continue
+            legal = [a for a in range(39) if (m >> a) & 1]
+            a = int(prng.choice(legal))
+            if i % 3 == 0 and (m >> 24) & 1:
+                a = 25 if (m >> 25) & 1 else 24      # every third game: no solos (reach Normal / Wedding)
+            acts[i] = a
+            objs[i].play(a)
+        err = dk.apply(engine, states, torch.from_numpy(acts).cuda()).cpu().numpy()
+        assert np.array_equal(err != 0, exp == 0)
+    else:
+        raise AssertionError("games did not finish")
+
+
+def test_step_random_encode_matches_oracle(dk, orc):
+    import torch
+
+    import master_doko_reinforcement_learning_b200 as pkg
+
+    n = 160
+    states = dk.new_games(1, n, dk.rng(SEED, 0, 0))
+    objs = [Fdo.new_game_philox(orc, SEED, i, 0) for i in range(n)]
+    for step in range(130):
+        for variant, flags in enumerate((pkg.DK_PLAYOUT_WITH_ANNOUNCEMENTS, 0, 0x100)):
+            if step % 3 != variant:
+                continue
+            obs, act = dk.step_random_encode(states, dk.rng(SEED, 0, 100 + step), flags=flags)
+            torch.cuda.synchronize()
+            exp_act = np.array([o.step_site(SEED, i, 100 + step, flags & 1, bool(flags & 0x100)) for i, o in enumerate(objs)])
+            assert np.array_equal(act.cpu().numpy().astype(np.int64), np.where(exp_act < 0, 255, exp_act))
+            assert recs(states).tobytes() == oracle_recs(objs).tobytes()
+            assert np.array_equal(obs.cpu().numpy(), np.stack([o.encode_pi() for o in objs]))
+    assert all(o.allowed() == 0 for o in objs)
+
+
+@pytest.mark.parametrize("engine", [0, 1])
+def test_playout_from_states_matches_oracle(dk, orc, engine):
+    import torch
+
+    n = 256
+    states = dk.new_games(engine, n, dk.rng(SEED, 77, 1))
+    cls = Fdo if engine == 1 else Doko
+    objs = [cls.new_game_philox(orc, SEED, 77 + i, 1) for i in range(n)]
+    prng = np.random.default_rng(3)
+    # advance game i by a game-specific number of random steps (mid-reservation, mid-round, mid-trick, ...)
+    for i, o in enumerate(objs):
+        for _ in range(int(prng.integers(0, 70))):
+            m = o.allowed()
+            if m == 0:
+                break
+            legal = [a for a in range(39) if (m >> a) & 1]
+            a = int(prng.choice(legal))
+            if i % 2 == 0 and (m >> 24) & 1:
+                a = 25 if (m >> 25) & 1 else 24
+            o.play(a)
+    st = torch.from_numpy(np.frombuffer(oracle_recs(objs).tobytes(), dtype=np.uint8).reshape(n, 128).copy()).cuda()
+    for with_ann in ((True, False) if engine == 1 else (False,)):
+        pts, steps = dk.playout(engine, n, dk.rng(SEED, 900, 4), states=st, flags=1 if with_ann else 0)
+        torch.cuda.synchronize()
+        pts, steps = pts.cpu().numpy(), steps.cpu().numpy()
+        for i, o in enumerate(objs):
+            if engine == 1:
+                rp, rs = o.rollout(SEED, 900 + i, 0, 4, with_ann)
+            else:
+                c = Doko(orc, orc.orc_doko_clone(o.h))
+                while c.random_step(SEED, 900 + i, 4) >= 0:
+                    pass
+                rp, rs = c.info()["points"], c.info()["n_play_actions"] - o.info()["n_play_actions"]
+            assert list(pts[i]) == rp and int(steps[i]) == rs, f"game {i}"
+
+
+def test_doko_trace_config1(dk, orc):
+    """BASELINE config 1 outputs: 52 action ids, player_eyes, re_players, player_points per game — bit-exact."""
+    import torch
+
+    n = 1 << 16
+    pts, trace, aux = dk.playout_trace(0, n, dk.rng(SEED, 0, 1))
+    torch.cuda.synchronize()
+    ref = oracle_lib.playout_philox(orc, 0, n, SEED, 0, 1, True, 0, want_aux=True, trace_stride=52)
+    assert np.array_equal(pts.cpu().numpy(), ref["points"])
+    assert np.array_equal(trace.cpu().numpy(), ref["trace"])
+    aux = aux.cpu().numpy().astype(np.uint32)
+    eyes = np.stack([(aux[:, 2] >> (8 * s)) & 255 for s in range(4)], 1)
+    assert np.array_equal(eyes, ref["aux"][:, 4:8].astype(np.uint32))
+    assert np.array_equal(aux[:, 1], ref["aux"][:, 1].astype(np.uint32))
+
+
+def test_doko_one_million_playouts_config1(dk, orc):
+    import torch
+
+    n = 1_000_000
+    pts, steps = dk.playout(0, n, dk.rng(SEED, 0, 1))
+    torch.cuda.synchronize()
+    ref = oracle_lib.playout_philox(orc, 0, n, SEED, 0, 1, True, 0)
+    assert np.array_equal(pts.cpu().numpy(), ref["points"])
+    assert int(steps.min()) == 52 and int(steps.max()) == 52
