@@ -244,3 +244,50 @@ class DokoCuda:
         self._check(self.L.dk_playout_trace(self.ctx, engine, n, C.byref(rng), _ptr(pts), _ptr(trace), _ptr(aux), stream if stream is not None else self._stream()),
                     "dk_playout_trace")
         return pts, trace, aux
+
+    # ---- determinization / leaf rollouts ----------------------------------------------------------------------------------
+    def determinize(self, engine, states, samples_per_info, rng, stream=None):
+        """card_matching samples: returns (hands int64 [n,S,4], reservations uint8 [n,S,4], status uint8 [n,S])."""
+        import torch
+
+        n = states.shape[0]
+        hands = torch.empty((n, samples_per_info, 4), dtype=torch.int64, device=self._dev())
+        res = torch.empty((n, samples_per_info, 4), dtype=torch.uint8, device=self._dev())
+        status = torch.empty((n, samples_per_info), dtype=torch.uint8, device=self._dev())
+        self._check(self.L.dk_determinize(self.ctx, engine, n, samples_per_info, _ptr(states), C.byref(rng), _ptr(hands), _ptr(res), _ptr(status),
+                                          stream if stream is not None else self._stream()), "dk_determinize")
+        return hands, res, status
+
+    def leaf_rollouts(self, states, rollouts_per_leaf, rng, determinize=True, out=None, stream=None):
+        """Exact integer sums of player_points over R rollouts per leaf: int64 [n,4]."""
+        import torch
+
+        n = states.shape[0]
+        out = torch.empty((n, 4), dtype=torch.int64, device=self._dev()) if out is None else out
+        self._check(self.L.dk_leaf_rollouts(self.ctx, n, rollouts_per_leaf, int(determinize), _ptr(states), C.byref(rng), _ptr(out),
+                                            stream if stream is not None else self._stream()), "dk_leaf_rollouts")
+        return out
+
+    # ---- multi-GPU root statistics ----------------------------------------------------------------------------------------
+    def comm_init(self, group=None):
+        """Create the library's NCCL communicator over the ranks of a torch.distributed group (torch is only the rendezvous)."""
+        import torch
+        import torch.distributed as dist
+
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        ident = (C.c_char * 128)()
+        if rank == 0:
+            self._check(self.L.dk_comm_unique_id(self.ctx, ident), "dk_comm_unique_id")
+        box = [bytes(ident.raw)]
+        dist.broadcast_object_list(box, src=0, group=group)
+        ident = (C.c_char * 128).from_buffer_copy(box[0])
+        self._check(self.L.dk_comm_init(self.ctx, world, rank, ident), "dk_comm_init")
+
+    def comm_destroy(self):
+        self._check(self.L.dk_comm_destroy(self.ctx), "dk_comm_destroy")
+
+    def allreduce_root_stats(self, values, stream=None):
+        """In-place sum over ranks of an int64 cuda tensor (ncclAllReduce on the library's communicator)."""
+        self._check(self.L.dk_allreduce_root_stats(self.ctx, values.numel(), _ptr(values), stream if stream is not None else self._stream()),
+                    "dk_allreduce_root_stats")
+        return values

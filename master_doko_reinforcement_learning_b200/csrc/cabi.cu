@@ -4,6 +4,7 @@
 #include <dlfcn.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -229,6 +230,93 @@ dk_status dk_step_random_encode(dk_ctx* ctx, size_t n, dk_state* states, const d
     unsigned grid = (unsigned)((n + dk::ENC_THREADS - 1) / dk::ENC_THREADS);
     dk::fdo_step_encode_kernel<<<grid, dk::ENC_THREADS, 0, pick_stream(ctx, stream)>>>(to_params(rng), (uint64_t)n, states, flags, obs_out, row_stride, action_out);
     return check_launch(ctx, "fdo_step_encode_kernel");
+}
+
+dk_status dk_determinize(dk_ctx* ctx, int engine, size_t n_info, size_t samples_per_info, const dk_state* states, const dk_rng* rng,
+                         uint64_t* hands_out, uint8_t* reservations_out, uint8_t* status_out, dk_stream stream) {
+    if (!ctx || !states || !rng) return DK_ERR_INVALID_ARGUMENT;
+    if (engine != DK_FDO) return fail(ctx, DK_ERR_UNSUPPORTED, "dk_determinize: DK_DOKO (rs-doko-assignment) is not built yet");
+    if (n_info == 0 || samples_per_info == 0) return DK_OK;
+    if (samples_per_info > 0xFFFFFFFFull || n_info > 0x7FFFFFFFull) return DK_ERR_INVALID_ARGUMENT;
+    DK_CUDA(ctx, cudaSetDevice(ctx->device));
+    dk::fdo_determinize_kernel<<<(unsigned)n_info, dk::MATCH_THREADS, 0, pick_stream(ctx, stream)>>>(to_params(rng), (uint64_t)n_info, (uint32_t)samples_per_info,
+                                                                                                   states, hands_out, reservations_out, status_out);
+    return check_launch(ctx, "fdo_determinize_kernel");
+}
+
+dk_status dk_leaf_rollouts(dk_ctx* ctx, size_t n_leaves, size_t rollouts_per_leaf, int determinize, const dk_state* states, const dk_rng* rng,
+                           int64_t* point_sum_out, dk_stream stream) {
+    if (!ctx || !states || !rng || !point_sum_out) return DK_ERR_INVALID_ARGUMENT;
+    if (n_leaves == 0) return DK_OK;
+    if (rollouts_per_leaf > 0x1000000ull || n_leaves > 0x7FFFFFFFull) return DK_ERR_INVALID_ARGUMENT;   // int32 block sums: |points| < 128
+    DK_CUDA(ctx, cudaSetDevice(ctx->device));
+    dk::fdo_leaf_rollouts_kernel<<<(unsigned)n_leaves, dk::MATCH_THREADS, 0, pick_stream(ctx, stream)>>>(to_params(rng), (uint64_t)n_leaves, (uint32_t)rollouts_per_leaf,
+                                                                                                      determinize, states, (long long*)point_sum_out);
+    return check_launch(ctx, "fdo_leaf_rollouts_kernel");
+}
+
+// ---- NCCL (dlopen; the only exchange step of the path) ---------------------------------------------------------------------
+namespace {
+struct NcclApi {
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(void**, int, dk_nccl_id, int) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    void* lib = nullptr;
+} g_nccl;
+std::mutex g_nccl_mu;
+dk_status load_nccl(dk_ctx* ctx) {
+    std::lock_guard<std::mutex> lk(g_nccl_mu);
+    if (g_nccl.lib) return DK_OK;
+    const char* names[] = {getenv("DK_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    void* lib = nullptr;
+    for (const char* nm : names) { if (nm && (lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL))) break; }
+    if (!lib) return fail(ctx, DK_ERR_NCCL, "libnccl.so.2 not found (set DK_NCCL_LIB)");
+    g_nccl.GetUniqueId = (int (*)(void*))dlsym(lib, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (int (*)(void**, int, dk_nccl_id, int))dlsym(lib, "ncclCommInitRank");
+    g_nccl.CommDestroy = (int (*)(void*))dlsym(lib, "ncclCommDestroy");
+    g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(lib, "ncclAllReduce");
+    g_nccl.GetErrorString = (const char* (*)(int))dlsym(lib, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.AllReduce) { dlclose(lib); return fail(ctx, DK_ERR_NCCL, "NCCL symbols missing"); }
+    g_nccl.lib = lib;
+    return DK_OK;
+}
+dk_status nccl_fail(dk_ctx* ctx, const char* what, int rc) {
+    return fail(ctx, DK_ERR_NCCL, std::string(what) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "nccl error"));
+}
+}  // namespace
+
+dk_status dk_comm_unique_id(dk_ctx* ctx, dk_nccl_id* out) {
+    if (!ctx || !out) return DK_ERR_INVALID_ARGUMENT;
+    dk_status st = load_nccl(ctx);
+    if (st != DK_OK) return st;
+    int rc = g_nccl.GetUniqueId(out);
+    return rc ? nccl_fail(ctx, "ncclGetUniqueId", rc) : DK_OK;
+}
+dk_status dk_comm_init(dk_ctx* ctx, int n_ranks, int rank, const dk_nccl_id* id) {
+    if (!ctx || !id || n_ranks < 1 || rank < 0 || rank >= n_ranks) return DK_ERR_INVALID_ARGUMENT;
+    dk_status st = load_nccl(ctx);
+    if (st != DK_OK) return st;
+    DK_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = g_nccl.CommInitRank(&ctx->nccl_comm, n_ranks, *id, rank);
+    if (rc) return nccl_fail(ctx, "ncclCommInitRank", rc);
+    ctx->nccl_ranks = n_ranks; ctx->nccl_rank = rank;
+    return DK_OK;
+}
+dk_status dk_comm_destroy(dk_ctx* ctx) {
+    if (!ctx) return DK_ERR_INVALID_ARGUMENT;
+    if (ctx->nccl_comm) { g_nccl.CommDestroy(ctx->nccl_comm); ctx->nccl_comm = nullptr; }
+    return DK_OK;
+}
+// Sum of int64 root statistics over all ranks (ncclAllReduce, ncclInt64 = 4, ncclSum = 0), in place.
+dk_status dk_allreduce_root_stats(dk_ctx* ctx, size_t n_values, int64_t* values, dk_stream stream) {
+    if (!ctx || !values) return DK_ERR_INVALID_ARGUMENT;
+    if (!ctx->nccl_comm) return fail(ctx, DK_ERR_NCCL, "dk_comm_init has not been called");
+    if (n_values == 0) return DK_OK;
+    DK_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = g_nccl.AllReduce(values, values, n_values, 4, 0, ctx->nccl_comm, pick_stream(ctx, stream));
+    return rc ? nccl_fail(ctx, "ncclAllReduce", rc) : DK_OK;
 }
 
 dk_status dk_playout_host(dk_ctx* ctx, int engine, uint32_t flags, size_t n, const dk_state* states_host, const dk_rng* rng,

@@ -7,6 +7,7 @@
 #include "doko_rules.cuh"
 #include "encode.cuh"
 #include "fdo_rules.cuh"
+#include "matching.cuh"
 #include "state_ops.cuh"
 
 namespace dk {
@@ -259,6 +260,85 @@ playout_state_kernel(RngParams rp, uint64_t n, const dk_state* __restrict__ stat
     }
     if (points) points[i] = make_int4(p[0], p[1], p[2], p[3]);
     if (steps) steps[i] = st;
+}
+
+
+// K3: determinization.  One block per info-state; the constraint tables are built once (thread 0) and staged in shared
+// memory, then each thread draws samples s = tid, tid + blockDim, ...  (card_matching, rs-full-doko/src/matching/card_matching.rs:241-467).
+// HBM per sample: 32 B hands + 4 B reservations + 1 B status written; 128 B read per info-state.
+constexpr int MATCH_THREADS = 128;
+__global__ void __launch_bounds__(MATCH_THREADS)
+fdo_determinize_kernel(RngParams rp, uint64_t n_info, uint32_t samples, const dk_state* __restrict__ states, uint64_t* __restrict__ hands_out,
+                       uint8_t* __restrict__ res_out, uint8_t* __restrict__ status_out) {
+    __shared__ MatchPrep prep;
+    uint64_t i = blockIdx.x;
+    if (i >= n_info) return;
+    if (threadIdx.x == 0) {
+        alignas(16) dk_state s;
+        load_state(states + i, s);
+        fdo_match_prepare(s, prep);
+    }
+    __syncthreads();
+    for (uint32_t smp = threadIdx.x; smp < samples; smp += MATCH_THREADS) {
+        RngKey key = make_key(rp, i, smp, true);
+        uint64_t h[4];
+        uint8_t r[4];
+        uint32_t st = prep.valid ? fdo_match_sample(prep, key, h, r) : 2u;
+        if (!prep.valid) { h[0] = h[1] = h[2] = h[3] = 0; r[0] = r[1] = r[2] = r[3] = 0xFF; }
+        uint64_t o = i * samples + smp;
+        if (hands_out) {
+            ulonglong2* dst = reinterpret_cast<ulonglong2*>(hands_out + 4 * o);
+            dst[0] = make_ulonglong2(h[0], h[1]);
+            dst[1] = make_ulonglong2(h[2], h[3]);
+        }
+        if (res_out) reinterpret_cast<uint32_t*>(res_out)[o] = (uint32_t)r[0] | ((uint32_t)r[1] << 8) | ((uint32_t)r[2] << 16) | ((uint32_t)r[3] << 24);
+        if (status_out) status_out[o] = (uint8_t)st;
+    }
+}
+
+// K4: leaf-parallel rollouts, fused determinize → rollout → block reduction.  One block per leaf; rollout r uses the Philox
+// unit (leaf id, r).  point_sum[leaf][seat] = exact integer sum of player_points over the rollouts (dead-end samples add 0).
+__global__ void __launch_bounds__(MATCH_THREADS)
+fdo_leaf_rollouts_kernel(RngParams rp, uint64_t n_leaves, uint32_t rollouts, int determinize, const dk_state* __restrict__ states,
+                         long long* __restrict__ point_sum) {
+    __shared__ MatchPrep prep;
+    __shared__ __align__(16) dk_state leaf;
+    __shared__ int red[4];
+    uint64_t i = blockIdx.x;
+    if (i >= n_leaves) return;
+    if (threadIdx.x < 8) reinterpret_cast<uint4*>(&leaf)[threadIdx.x] = __ldg(reinterpret_cast<const uint4*>(states + i) + threadIdx.x);
+    if (threadIdx.x < 4) red[threadIdx.x] = 0;
+    __syncthreads();
+    if (determinize && threadIdx.x == 0) fdo_match_prepare(leaf, prep);
+    __syncthreads();
+    int acc[4] = {0, 0, 0, 0};
+    for (uint32_t r = threadIdx.x; r < rollouts; r += MATCH_THREADS) {
+        RngKey key = make_key(rp, i, r, true);
+        alignas(16) dk_state s = leaf;
+        uint32_t status = 0;
+        if (determinize && prep.valid) {
+            uint64_t h[4];
+            uint8_t res[4];
+            status = fdo_match_sample(prep, key, h, res);
+            fdo_state_with_hands_and_reservations(s, h, res);
+        }
+        if (status == 0u) {
+            FdoLive g; FdoResume rs;
+            int32_t p[4];
+            if (fdo_state_to_live(s, g, rs)) { fdo_play_to_end<false, false>(g, key, &rs); fdo_final_points(g, p); }
+            else { p[0] = s.points[0]; p[1] = s.points[1]; p[2] = s.points[2]; p[3] = s.points[3]; }
+            acc[0] += p[0]; acc[1] += p[1]; acc[2] += p[2]; acc[3] += p[3];
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        int v = acc[q];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+        if ((threadIdx.x & 31) == 0) atomicAdd(&red[q], v);
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) point_sum[4 * i + threadIdx.x] = (long long)red[threadIdx.x];
 }
 
 }  // namespace dk

@@ -1,0 +1,211 @@
+// matching.cuh — full-rules determinizer (rs-full-doko/src/matching/card_matching.rs:31-467) as a thread-per-sample program.
+//
+// A multiset hand is two 24-bit planes: A = "at least one copy", B = "both copies" (B ⊆ A, which is exactly the invariant the
+// reference's add/remove keep: add fills copy A first, remove takes copy B first, hand.rs:217-247).  The constraint tables of an
+// info-state (available cards, per-seat possible cards, open slots, ♣Q obligations, visible reservations) are computed ONCE per
+// block and staged in shared memory; every thread then runs the greedy rule loop for its own sample with its own Philox stream.
+#pragma once
+#include "state_ops.cuh"
+
+namespace dk {
+
+struct Hand2 { uint32_t a, b; };
+DK_HD bool h2_has(const Hand2& h, uint32_t bit) { return (h.a & bit) != 0u; }
+DK_HD void h2_add(Hand2& h, uint32_t bit) { if (h.a & bit) h.b |= bit; else h.a |= bit; }
+DK_HD void h2_remove_one(Hand2& h, uint32_t bit) { if (h.b & bit) h.b &= ~bit; else h.a &= ~bit; }   // also "remove_ignore"
+DK_HD uint32_t h2_len(const Hand2& h) { return popc(h.a) + popc(h.b); }
+
+// Constraint tables of one info-state.  The three hidden seats are kept in ABSOLUTE seat order in slots 0..2
+// (seat of slot j = j + (j >= observer)), which is the order every rule of the reference walks them in.
+struct MatchPrep {
+    Hand2 avail;
+    Hand2 possible[3];
+    uint32_t slots[3];
+    uint32_t must_q;        // bit j: slot j must still receive a ♣Q
+    uint32_t observer;
+    uint32_t played_q;      // 2 bits per ABSOLUTE seat: ♣Q already played by that seat
+    uint32_t visible;       // 4 bits per ABSOLUTE seat: 0 NoneYet, 1 NotRevealed, else 2 + FdoReservation code (revealed)
+    uint32_t obs_a, obs_b;  // the observer's real hand
+    uint32_t valid;         // 0 when the game is finished (card_matching would panic)
+};
+
+// card_matching.rs:241-395 — everything before `execute`.
+DK_HD void fdo_match_prepare(const dk_state& s, MatchPrep& m) {
+    const uint32_t obs = st_cur(s), start = st_game_start(s), nres = s.n_reservations;
+    m.valid = st_phase(s) != DK_PHASE_FINISHED;
+    m.observer = obs;
+    uint32_t any[4], both[4];
+    for (uint32_t p = 0; p < 4u; ++p) { any[p] = hand_any24(s.hands[p]); both[p] = hand_both24(s.hands[p]); }
+    m.obs_a = any[obs]; m.obs_b = both[obs];
+    uint32_t A = 0, B = 0;
+    for (uint32_t p = 0; p < 4u; ++p) {                      // plus_hand over the three hidden hands (:258-265)
+        if (p == obs) continue;
+        B |= both[p] | (A & any[p]);
+        A |= any[p];
+    }
+    m.avail.a = A; m.avail.b = B;
+    const bool completed = nres == 4u;
+    uint32_t vis = 0, wedding_seats = 0;
+    bool solo_seen = false;
+    for (uint32_t i = 0; i < nres; ++i) {                    // get_visible_reservations(observer) (visible_reservations_logic.rs:7-70)
+        uint32_t seat = (start + i) & 3u, code = s.reservations[i], v;
+        if (code == 0u) v = 2u;                              // Healthy
+        else if (code == 1u) { v = (completed || seat == obs) ? 3u : 1u; if (v == 3u) wedding_seats |= 1u << seat; }
+        else if (completed && !solo_seen) { v = 2u + code; solo_seen = true; }
+        else v = 1u;
+        vis |= v << (4u * seat);
+    }
+    m.visible = vis;
+    uint32_t pq = 0;
+    const uint32_t ci = s.card_index;
+    for (uint32_t j = 0; j < ci; ++j)
+        if (s.cards[j] == CARD_CQ) pq += 1u << (2u * ((st_trick_start(s, j >> 2) + (j & 3u)) & 3u));
+    m.played_q = pq;
+    const uint32_t CQ = 1u << CARD_CQ;
+    uint32_t must = 0;
+    uint32_t drop[4] = {0, 0, 0, 0};                         // cards a seat cannot hold (both planes)
+    for (uint32_t p = 0; p < 4u; ++p)                        // a visible wedding: nobody else holds a ♣Q (:289-310)
+        if (wedding_seats & ~(1u << p)) drop[p] |= CQ;
+    const uint32_t gt = st_gt(s);
+    if (gt != (uint32_t)DK_GT_NONE) {
+        const uint32_t trump = trump_mask_for_game_type(gt);
+        for (uint32_t j = 0; j < ci; ++j) {                  // gather_impossible_colors (gather_impossible_colors.rs:11-43)
+            uint32_t f = follow_mask(s.cards[j & ~3u], trump);
+            if (!((f >> s.cards[j]) & 1u)) drop[(st_trick_start(s, j >> 2) + (j & 3u)) & 3u] |= f;
+        }
+        if (gt == GT_NORMAL) {                               // calls reveal the ♣Q (:357-379)
+            const uint32_t re = st_re_mask(s), n_calls = st_n_calls(s);
+            for (uint32_t a = 0; a < n_calls; ++a) {
+                uint32_t seat = (s.announcements[a] >> 6) & 3u;
+                if ((re >> seat) & 1u) { if ((pq >> (2u * seat)) & 3u) must &= ~(1u << seat); else must |= 1u << seat; }
+                else drop[seat] |= CQ;
+            }
+        }
+    }
+    m.must_q = 0;
+    for (uint32_t j = 0; j < 3u; ++j) {
+        uint32_t seat = j + (j >= obs ? 1u : 0u);
+        m.slots[j] = popcll(s.hands[seat]);
+        m.possible[j].a = m.slots[j] ? (A & ~drop[seat]) : 0u;
+        m.possible[j].b = m.slots[j] ? (B & ~drop[seat]) : 0u;
+        if ((must >> seat) & 1u) m.must_q |= 1u << j;
+    }
+}
+
+struct MatchState {
+    Hand2 avail, possible[3], assigned[3];
+    uint32_t slots[3], must_q, status;
+};
+
+// CardMatchingState::assign_card (:49-76)
+DK_HD void fdo_match_assign(MatchState& m, uint32_t j, uint32_t c) {
+    const uint32_t bit = 1u << c;
+    h2_add(m.assigned[j], bit);
+    m.slots[j] -= 1u;
+    h2_remove_one(m.avail, bit);
+#pragma unroll
+    for (uint32_t o = 0; o < 3u; ++o)
+        if (o == j || (m.possible[o].a & bit)) h2_remove_one(m.possible[o], bit);
+    if (m.slots[j] == 0u) { m.possible[j].a = 0; m.possible[j].b = 0; }
+    if (c == CARD_CQ) m.must_q &= ~(1u << j);
+}
+// rule 1 (:78-113): walk a SNAPSHOT of the available cards (copy-A bits ascending, then copy-B bits) and hand every card that
+// exactly one hidden seat can hold to that seat.
+DK_HD void fdo_match_rule1(MatchState& m) {
+    uint32_t snap[2] = {m.avail.a, m.avail.b};
+    for (uint32_t plane = 0; plane < 2u; ++plane) {
+        uint32_t bits = snap[plane];
+        while (bits) {
+            uint32_t c = ffs0(bits), bit = 1u << c;
+            bits &= bits - 1u;
+            uint32_t h0 = (m.possible[0].a & bit) ? 1u : 0u, h1 = (m.possible[1].a & bit) ? 1u : 0u, h2 = (m.possible[2].a & bit) ? 1u : 0u;
+            if (h0 + h1 + h2 == 1u) fdo_match_assign(m, h0 ? 0u : (h1 ? 1u : 2u), c);
+        }
+    }
+}
+// rule 2 (:115-145): a seat whose open slots equal its possible cards takes them all.
+DK_HD bool fdo_match_rule2(MatchState& m) {
+    bool changed = false;
+#pragma unroll
+    for (uint32_t j = 0; j < 3u; ++j) {
+        if (m.slots[j] > 0u && m.slots[j] == h2_len(m.possible[j])) {
+            changed = true;
+            uint32_t snap[2] = {m.possible[j].a, m.possible[j].b};
+            for (uint32_t plane = 0; plane < 2u; ++plane) {
+                uint32_t bits = snap[plane];
+                while (bits) { uint32_t c = ffs0(bits); bits &= bits - 1u; fdo_match_assign(m, j, c); }
+            }
+        }
+    }
+    return changed;
+}
+// rule 3 (:147-172): a seat that must hold a ♣Q gets one.
+DK_HD bool fdo_match_rule3(MatchState& m) {
+    bool changed = false;
+#pragma unroll
+    for (uint32_t j = 0; j < 3u; ++j)
+        if (((m.must_q >> j) & 1u) && (m.possible[j].a & (1u << CARD_CQ))) { changed = true; fdo_match_assign(m, j, CARD_CQ); }
+    return changed;
+}
+
+struct MatchRng { U4 blk; uint32_t blk_id, count; };
+
+// One sample: execute (:207-238) + hidden reservations (:418-464).  hands_out / res_out by ABSOLUTE seat.
+DK_HD uint32_t fdo_match_sample(const MatchPrep& p, const RngKey& key, uint64_t hands_out[4], uint8_t res_out[4]) {
+    MatchState m;
+    m.avail = p.avail; m.must_q = p.must_q; m.status = 0;
+#pragma unroll
+    for (uint32_t j = 0; j < 3u; ++j) { m.possible[j] = p.possible[j]; m.slots[j] = p.slots[j]; m.assigned[j].a = 0; m.assigned[j].b = 0; }
+    MatchRng r; r.blk_id = 0xFFFFFFFFu; r.count = 0; r.blk.x = r.blk.y = r.blk.z = r.blk.w = 0;
+    for (;;) {
+        if ((m.avail.a | m.avail.b) == 0u) break;
+        fdo_match_rule1(m);
+        if (fdo_match_rule2(m)) continue;
+        if (fdo_match_rule3(m)) continue;
+        if ((m.avail.a | m.avail.b) == 0u) break;
+        // rule 4 (:174-204): a uniformly chosen available card (ascending-bit index over both planes) goes to the FIRST seat
+        // in seat order that can hold it
+        uint32_t na = popc(m.avail.a), n = na + popc(m.avail.b);
+        uint32_t ord = r.count++;
+        if ((ord >> 2) != r.blk_id) { r.blk_id = ord >> 2; r.blk = rng_block(key, SITE_MATCH_CARD, ord >> 2); }
+        uint32_t idx = mulhi(u4_word(r.blk, ord & 3u), n);
+        uint32_t c = idx < na ? select_lsb24(m.avail.a, idx) : select_lsb24(m.avail.b, idx - na);
+        uint32_t bit = 1u << c;
+        uint32_t j = (m.possible[0].a & bit) ? 0u : ((m.possible[1].a & bit) ? 1u : ((m.possible[2].a & bit) ? 2u : 3u));
+        if (j == 3u) { m.status = 1u; break; }                // `.first().unwrap()` would panic: dead end
+        fdo_match_assign(m, j, c);
+    }
+    const uint32_t obs = p.observer;
+    uint32_t oa[4], ob[4];
+#pragma unroll
+    for (uint32_t j = 0; j < 3u; ++j) { uint32_t seat = j + (j >= obs ? 1u : 0u); oa[seat] = m.assigned[j].a; ob[seat] = m.assigned[j].b; }
+    oa[obs] = p.obs_a; ob[obs] = p.obs_b;
+    U4 rb = rng_block(key, SITE_MATCH_RESERVATION, 0);
+    const uint32_t CQ = 1u << CARD_CQ;
+    for (uint32_t seat = 0; seat < 4u; ++seat) {
+        hands_out[seat] = (uint64_t)oa[seat] | ((uint64_t)ob[seat] << 24);
+        uint32_t v = (p.visible >> (4u * seat)) & 15u, code;
+        if (v == 0u) code = 0xFFu;
+        else if (v >= 2u) code = v - 2u;
+        else {                                                // NotRevealed: draw among [Wedding?] + the seven solos
+            uint32_t pq = (p.played_q >> (2u * seat)) & 3u;
+            bool wed_ok = (ob[seat] & CQ) || ((oa[seat] & CQ) && pq == 1u) || pq == 2u;
+            uint32_t idx = mulhi(u4_word(rb, seat), wed_ok ? 8u : 7u);
+            code = wed_ok ? (idx == 0u ? 1u : idx + 1u) : idx + 2u;
+        }
+        res_out[seat] = (uint8_t)code;
+    }
+    return m.status;
+}
+
+// clone_with_different_hands_and_reservations (state.rs:96-119) on the record.
+DK_HD void fdo_state_with_hands_and_reservations(dk_state& s, const uint64_t hands[4], const uint8_t res[4]) {
+    const uint32_t start = st_game_start(s);
+    uint32_t n = 0;
+    for (uint32_t p = 0; p < 4u; ++p) s.hands[p] = hands[p];
+    for (uint32_t i = 0; i < 4u; ++i) { uint8_t r = res[(start + i) & 3u]; if (r != 0xFFu) s.reservations[n++] = r; }
+    for (uint32_t i = n; i < 4u; ++i) s.reservations[i] = 0xFF;
+    s.n_reservations = (uint8_t)n;
+}
+
+}  // namespace dk

@@ -437,6 +437,28 @@ ORC_API void orc_fdo_random_rollout_philox(const void* h, uint64_t seed, uint64_
     if (steps) *steps = s.n_play_actions - before;
 }
 
+// One leaf rollout: [card_matching → clone_with_different_hands_and_reservations →] random_rollout, all on the Philox unit (unit, rollout).
+// Returns the determinization status (0 ok).
+ORC_API int orc_fdo_leaf_rollout_philox(const void* h, uint64_t seed, uint64_t unit, uint32_t rollout, uint32_t epoch, int determinize,
+                                        int32_t points[4], uint32_t* steps) {
+    fdo::State s = *(const fdo::State*)h;
+    PhiloxStream r(seed, (uint32_t)unit, rollout, epoch);
+    int status = 0;
+    if (determinize) {
+        fdo::Hand oh[4]; int ores[4];
+        status = fdo::card_matching(s, r, oh, ores);
+        s = fdo::with_hands_and_reservations(s, oh, ores);
+    }
+    r.set_ordinal(SITE_CARD, (uint32_t)s.card_index); r.set_ordinal(SITE_RESERVATION, (uint32_t)s.reservations_round.len);
+    uint32_t before = s.n_play_actions;
+    if (status == 0) {
+        for (;;) { if (s.random_action_for_current_player_no_announcement(r)) break; }
+        for (int p = 0; p < 4; ++p) points[p] = s.end_of_game_stats.player_points[p];
+    } else for (int p = 0; p < 4; ++p) points[p] = 0;
+    if (steps) *steps = s.n_play_actions - before;
+    return status;
+}
+
 // ---- bulk playouts (parity checks at scale + CPU baseline) --------------------------------------------------------
 // Plays games first_id .. first_id+n-1 from fresh Philox deals.  points[n*4], steps[n] (may be NULL), aux[n*8] (may be NULL):
 // aux = [game_type, re_players, re_lowest code, contra_lowest code, eyes0..3];  trace (may be NULL): trace_stride bytes per game, 0xFF padded.

@@ -1,0 +1,107 @@
+#!/usr/bin/env python3
+"""Per-kernel timings (CUDA events, warm, inputs > L2 where it matters) for K1..K5; prints one JSON object."""
+import argparse
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+SEED = 0xD0C05EED
+
+
+def timed(fn, iters=5, warm=2):
+    import torch
+
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters / 1e3
+
+
+def main():
+    import torch
+
+    import master_doko_reinforcement_learning_b200 as pkg
+
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--scale", type=float, default=1.0)
+    a = ap.parse_args()
+    dk = pkg.DokoCuda(0)
+    out = {}
+    peaks = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json"))) if os.path.exists("MEASURED_PEAKS.json") else {}
+    hbm = peaks.get("hbm_gbs", 6650.0)
+
+    # K1 rs-doko fresh playouts, 1M games (config 1)
+    n = 1_000_000
+    pts = torch.empty((n, 4), dtype=torch.int32, device="cuda"); st = torch.empty((n,), dtype=torch.int32, device="cuda")
+    t = timed(lambda: dk.playout(pkg.DK_DOKO, n, dk.rng(SEED, 0, 1), points_out=pts, steps_out=st))
+    out["K1_doko_playout_1M"] = {"sec": t, "games_per_s": n / t, "game_steps_per_s": 52 * n / t}
+
+    # K2 fdo fresh playouts 2^24 (config 2), both policies
+    n = int((1 << 24) * a.scale)
+    pts = torch.empty((n, 4), dtype=torch.int32, device="cuda"); st = torch.empty((n,), dtype=torch.int32, device="cuda")
+    for name, fl in (("with_announcements", 1), ("no_announcement_policy", 0)):
+        t = timed(lambda: dk.playout(pkg.DK_FDO, n, dk.rng(SEED, 0, 2), flags=fl, points_out=pts, steps_out=st), iters=3)
+        steps = int(st.sum(dtype=torch.int64))
+        out[f"K2_fdo_playout_2p24_{name}"] = {"sec": t, "games_per_s": n / t, "game_steps_per_s": steps / t, "mean_steps": steps / n}
+    del pts, st
+
+    # K5 lock-step step + encode, 2^22 games (config 5): states mid-game
+    n = int((1 << 22) * a.scale)
+    states = dk.new_games(pkg.DK_FDO, n, dk.rng(SEED, 0, 5))
+    for k in range(30):
+        dk.step_random_encode(states, dk.rng(SEED, 0, k), want_obs=False)
+    obs = torch.empty((n, 311), dtype=torch.int64, device="cuda")
+    act = torch.empty((n,), dtype=torch.uint8, device="cuda")
+    ctr = [100]
+
+    def k5():
+        ctr[0] += 1
+        dk.step_random_encode(states, dk.rng(SEED, 0, ctr[0]), obs_out=obs, action_out=act)
+
+    t = timed(k5, iters=5)
+    out["K5_step_encode_2p22"] = {"sec": t, "step_encodes_per_s": n / t, "algorithmic_GBps": n * 2744 / t / 1e9, "hbm_frac_of_measured": n * 2744 / t / 1e9 / hbm,
+                                  "bytes_per_unit": 2744}
+    t = timed(lambda: dk.encode(pkg.DK_LAYOUT_FDO_PI311, states, out=obs), iters=5)
+    out["encode_pi311_2p22"] = {"sec": t, "encodes_per_s": n / t, "algorithmic_GBps": n * 2616 / t / 1e9, "hbm_frac_of_measured": n * 2616 / t / 1e9 / hbm}
+    ms = torch.empty((n,), dtype=torch.int64, device="cuda")
+    t = timed(lambda: dk.legal_mask(pkg.DK_FDO, states, out=ms), iters=5)
+    out["legal_mask_2p22"] = {"sec": t, "states_per_s": n / t, "algorithmic_GBps": n * 136 / t / 1e9}
+    del obs
+
+    # K3 determinization: 64K info-states x 4096 samples is 2.7e8 samples = 10 GB of hands; run 4096 states x 4096 samples and scale
+    n_info = int(4096 * a.scale); S = 4096
+    sub = states[:n_info].clone()
+    for k in range(12):
+        dk.step_random_encode(sub, dk.rng(SEED, 0, 500 + k), want_obs=False)
+    hands = torch.empty((n_info, S, 4), dtype=torch.int64, device="cuda")
+    res = torch.empty((n_info, S, 4), dtype=torch.uint8, device="cuda")
+    status = torch.empty((n_info, S), dtype=torch.uint8, device="cuda")
+
+    def k3():
+        dk._check(dk.L.dk_determinize(dk.ctx, pkg.DK_FDO, n_info, S, pkg.api._ptr(sub), __import__("ctypes").byref(dk.rng(SEED, 0, 9)), pkg.api._ptr(hands),
+                                      pkg.api._ptr(res), pkg.api._ptr(status), dk._stream()), "dk_determinize")
+
+    t = timed(k3, iters=3)
+    out["K3_determinize_4096x4096"] = {"sec": t, "samples_per_s": n_info * S / t, "dead_ends": int((status != 0).sum()), "out_GBps": n_info * S * 37 / t / 1e9}
+    del hands, res, status
+
+    # K4 leaf rollouts: 1024 leaves x 1024 rollouts (per-GPU share of config 4)
+    n_leaves, R = int(1024 * a.scale), 1024
+    leaves = sub[:n_leaves]
+    sums = torch.empty((n_leaves, 4), dtype=torch.int64, device="cuda")
+    for det in (True, False):
+        t = timed(lambda: dk.leaf_rollouts(leaves, R, dk.rng(SEED, 0, 11), determinize=det, out=sums), iters=3)
+        out[f"K4_leaf_rollouts_1024x1024_det{int(det)}"] = {"sec": t, "rollouts_per_s": n_leaves * R / t}
+    out["launches"] = dk.launch_count()
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

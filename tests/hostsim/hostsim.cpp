@@ -12,6 +12,7 @@
 #include "../../master_doko_reinforcement_learning_b200/csrc/doko_rules.cuh"
 #include "../../master_doko_reinforcement_learning_b200/csrc/state_ops.cuh"
 #include "../../master_doko_reinforcement_learning_b200/csrc/encode.cuh"
+#include "../../master_doko_reinforcement_learning_b200/csrc/matching.cuh"
 
 #define SIM_API extern "C" __attribute__((visibility("default")))
 
@@ -85,4 +86,30 @@ SIM_API int sim_playout_from_state(int engine, const dk_state* s, uint64_t seed,
         dk::doko_final_points(g, points); *steps = g.steps;
     }
     return 1;
+}
+
+// ---- determinization ---------------------------------------------------------------------------------------------------
+SIM_API uint32_t sim_fdo_determinize(const dk_state* s, uint64_t seed, uint64_t unit, uint32_t sample, uint32_t epoch, uint64_t hands[4], uint8_t res[4]) {
+    dk::MatchPrep prep; dk::fdo_match_prepare(*s, prep);
+    dk::RngKey key = make_key(seed, unit, epoch); key.unit_hi = sample;
+    return dk::fdo_match_sample(prep, key, hands, res);
+}
+SIM_API uint32_t sim_fdo_leaf_rollout(const dk_state* s, uint64_t seed, uint64_t unit, uint32_t rollout, uint32_t epoch, int determinize, int32_t* points, uint32_t* steps) {
+    dk::RngKey key = make_key(seed, unit, epoch); key.unit_hi = rollout;
+    dk_state st = *s;
+    uint32_t status = 0;
+    if (determinize) {
+        dk::MatchPrep prep; dk::fdo_match_prepare(st, prep);
+        uint64_t hands[4]; uint8_t res[4];
+        status = dk::fdo_match_sample(prep, key, hands, res);
+        dk::fdo_state_with_hands_and_reservations(st, hands, res);
+    }
+    for (int p = 0; p < 4; ++p) points[p] = 0;
+    *steps = 0;
+    if (status) return status;
+    dk::FdoLive g; dk::FdoResume rs;
+    if (!dk::fdo_state_to_live(st, g, rs)) { for (int p = 0; p < 4; ++p) points[p] = st.points[p]; return 0; }
+    dk::fdo_play_to_end<false, false>(g, key, &rs);
+    dk::fdo_final_points(g, points); *steps = g.steps;
+    return 0;
 }

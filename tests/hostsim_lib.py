@@ -26,6 +26,10 @@ def load():
         L.sim_playout_from_state.argtypes = [i32, vp, u64, u64, u32, u32, i32, vp, vp]
         L.sim_fdo_playout_fresh.argtypes = [u64, u32, u64, u64, i32, vp, vp]
         L.sim_doko_playout_fresh.argtypes = [u64, u32, u64, u64, vp, vp, vp, vp]
+        L.sim_fdo_determinize.restype = u32
+        L.sim_fdo_determinize.argtypes = [vp, u64, u64, u32, u32, vp, vp]
+        L.sim_fdo_leaf_rollout.restype = u32
+        L.sim_fdo_leaf_rollout.argtypes = [vp, u64, u64, u32, u32, i32, vp, vp]
         L.sim_fdo_score.restype = i32
         L.sim_fdo_score.argtypes = [u32, u32, u32, u32, u32, i32, vp]
         for n in ("sim_fdo_allowed_call", "sim_select_lsb24", "sim_select_lsb", "sim_card_power", "sim_trump_mask", "sim_follow_mask"):

@@ -106,6 +106,7 @@ def load():
     L.orc_doko_encode.argtypes = [vp, i32, vp]
     L.orc_fdo_random_step_philox.argtypes = [vp, u64, u64, u32, i32, u32]
     L.orc_fdo_step_site.argtypes = [vp, u64, u64, u32, i32, i32]
+    L.orc_fdo_leaf_rollout_philox.argtypes = [vp, u64, u64, u32, u32, i32, vp, vp]
     L.orc_doko_random_step_philox.argtypes = [vp, u64, u64, u32]
     L.orc_fdo_hand_plus.restype = u64
     L.orc_fdo_hand_plus.argtypes = [u64, u64]
@@ -230,6 +231,12 @@ class Fdo:
 
     def is_consistent(self, hands, res):
         return self.L.orc_fdo_is_consistent(self.h, (C.c_uint64 * 4)(*hands), (C.c_uint8 * 4)(*res))
+
+    def leaf_rollout(self, seed, unit, rollout, epoch=0, determinize=True):
+        pts = (C.c_int32 * 4)()
+        steps = C.c_uint32()
+        st = self.L.orc_fdo_leaf_rollout_philox(self.h, seed, unit, rollout, epoch, int(determinize), pts, C.byref(steps))
+        return st, list(pts), steps.value
 
     def rollout(self, seed, unit, rollout, epoch=0, with_announcements=False):
         pts = (C.c_int32 * 4)()
