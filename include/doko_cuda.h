@@ -143,7 +143,8 @@ typedef struct dk_rng {
     uint64_t seed;
     uint64_t first_id;
     uint32_t epoch;
-    uint32_t reserved;
+    uint32_t first_sub; /* offset added to the sample / rollout number (unit_hi) of dk_determinize and dk_leaf_rollouts, so that the
+                           samples of one unit can be split over several calls or GPUs; 0 elsewhere */
 } dk_rng;
 
 /* ---- context ------------------------------------------------------------------------------- */
@@ -212,6 +213,11 @@ DK_API dk_status dk_playout_trace(dk_ctx* ctx, int engine, size_t n, const dk_rn
 /* Same, results copied to HOST buffers inside the call (what a plain Rust slice caller binds). */
 DK_API dk_status dk_playout_host(dk_ctx* ctx, int engine, uint32_t flags, size_t n, const dk_state* states_host /*[host] or NULL*/,
                           const dk_rng* rng, int32_t* points_out_host /*[host] n*4*/, uint32_t* steps_out_host /*[host] n*/);
+
+/* Same with the compact, lossless host-transfer form: int8 points (|points| < 128) and uint8 step counts (< 256) — 5 bytes per game
+ * instead of 20 over PCIe. */
+DK_API dk_status dk_playout_host_compact(dk_ctx* ctx, int engine, uint32_t flags, size_t n, const dk_state* states_host /*[host] or NULL*/,
+                                         const dk_rng* rng, int8_t* points_out_host /*[host] n*4*/, uint8_t* steps_out_host /*[host] n*/);
 
 /* ---- determinization ---------------------------------------------------------------------------------
  * replaces card_matching (rs-full-doko/src/matching/card_matching.rs:241-467) as called by CAPSampling::sample

@@ -25,7 +25,7 @@ class DokoCudaError(RuntimeError):
 
 
 class DkRng(C.Structure):
-    _fields_ = [("seed", C.c_uint64), ("first_id", C.c_uint64), ("epoch", C.c_uint32), ("reserved", C.c_uint32)]
+    _fields_ = [("seed", C.c_uint64), ("first_id", C.c_uint64), ("epoch", C.c_uint32), ("first_sub", C.c_uint32)]
 
 
 def library_path():
@@ -57,6 +57,7 @@ def load_library():
     L.dk_launch_count.argtypes = [vp]
     L.dk_playout.argtypes = [vp, i32, u32, sz, vp, C.POINTER(DkRng), vp, vp, vp]
     L.dk_playout_host.argtypes = [vp, i32, u32, sz, vp, C.POINTER(DkRng), vp, vp]
+    L.dk_playout_host_compact.argtypes = [vp, i32, u32, sz, vp, C.POINTER(DkRng), vp, vp]
     L.dk_playout_trace.argtypes = [vp, i32, sz, C.POINTER(DkRng), vp, vp, vp, vp]
     for name, args in (
         ("dk_new_games", [vp, i32, sz, C.POINTER(DkRng), vp, vp]),
@@ -116,8 +117,8 @@ class DokoCuda:
             raise DokoCudaError(f"{what}: {STATUS.get(st, st)}: {self.L.dk_last_error(self.ctx).decode()}")
 
     @staticmethod
-    def rng(seed, first_id=0, epoch=0):
-        return DkRng(int(seed) & 0xFFFFFFFFFFFFFFFF, int(first_id), int(epoch), 0)
+    def rng(seed, first_id=0, epoch=0, first_sub=0):
+        return DkRng(int(seed) & 0xFFFFFFFFFFFFFFFF, int(first_id), int(epoch), int(first_sub))
 
     @staticmethod
     def _stream():
@@ -160,6 +161,16 @@ class DokoCuda:
             steps_out = np.empty((n,), dtype=np.uint32)
         self._check(self.L.dk_playout_host(self.ctx, engine, flags, n, _ptr(states), C.byref(rng), _ptr(points_out), _ptr(steps_out)),
                     "dk_playout_host")
+        return points_out, steps_out
+
+    def playout_host_compact(self, engine, n, rng, states=None, flags=0, points_out=None, steps_out=None):
+        """dk_playout_host_compact: int8 [n,4] points + uint8 [n] steps in host buffers (numpy or pinned torch tensors)."""
+        if points_out is None:
+            points_out = np.empty((n, 4), dtype=np.int8)
+        if steps_out is None:
+            steps_out = np.empty((n,), dtype=np.uint8)
+        self._check(self.L.dk_playout_host_compact(self.ctx, engine, flags, n, _ptr(states), C.byref(rng), _ptr(points_out), _ptr(steps_out)),
+                    "dk_playout_host_compact")
         return points_out, steps_out
 
     # ---- state records ---------------------------------------------------------------------------------------------------

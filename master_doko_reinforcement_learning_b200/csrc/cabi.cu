@@ -9,6 +9,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <vector>
 
 #include "../../include/doko_cuda.h"
 #include "kernels.cuh"
@@ -23,6 +24,8 @@ struct dk_ctx {
     // scratch for the *_host entry points
     void* d_scratch = nullptr;
     size_t d_scratch_bytes = 0;
+    cudaStream_t copy_stream = nullptr;
+    std::vector<cudaEvent_t> events;
     // NCCL (loaded lazily)
     void* nccl_lib = nullptr;
     void* nccl_comm = nullptr;
@@ -46,7 +49,7 @@ cudaStream_t pick_stream(dk_ctx* ctx, dk_stream s) { return s ? (cudaStream_t)s 
 
 dk::RngParams to_params(const dk_rng* r) {
     dk::RngParams p;
-    p.seed_lo = (uint32_t)r->seed; p.seed_hi = (uint32_t)(r->seed >> 32); p.first_id = r->first_id; p.epoch = r->epoch;
+    p.seed_lo = (uint32_t)r->seed; p.seed_hi = (uint32_t)(r->seed >> 32); p.first_id = r->first_id; p.epoch = r->epoch; p.first_sub = r->first_sub;
     return p;
 }
 
@@ -96,6 +99,8 @@ dk_status dk_destroy(dk_ctx* ctx) {
     if (!ctx) return DK_ERR_INVALID_ARGUMENT;
     cudaSetDevice(ctx->device);
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);
+    for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return DK_OK;
@@ -121,32 +126,35 @@ dk_status dk_synchronize(dk_ctx* ctx, dk_stream stream) {
 
 uint64_t dk_launch_count(const dk_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+static dk_status playout_launch(dk_ctx* ctx, int engine, uint32_t flags, size_t n, const dk_state* states, const dk::RngParams& rp,
+                                void* points_out, void* steps_out, bool compact, cudaStream_t s) {
+    const bool with_ann = (flags & DK_PLAYOUT_WITH_ANNOUNCEMENTS) != 0;
+    if (states == nullptr) {
+        unsigned grid = (unsigned)((n + dk::PLAYOUT_THREADS - 1) / dk::PLAYOUT_THREADS);
+        if (engine == DK_FDO) {
+            if (with_ann) dk::fdo_playout_fresh_kernel<true><<<grid, dk::PLAYOUT_THREADS, 0, s>>>(rp, (uint64_t)n, points_out, steps_out, compact);
+            else dk::fdo_playout_fresh_kernel<false><<<grid, dk::PLAYOUT_THREADS, 0, s>>>(rp, (uint64_t)n, points_out, steps_out, compact);
+            return check_launch(ctx, "fdo_playout_fresh_kernel");
+        }
+        dk::doko_playout_fresh_kernel<false><<<grid, dk::PLAYOUT_THREADS, 0, s>>>(rp, (uint64_t)n, points_out, steps_out, compact, nullptr, nullptr);
+        return check_launch(ctx, "doko_playout_fresh_kernel");
+    }
+    unsigned grid = (unsigned)((n + dk::STATE_THREADS - 1) / dk::STATE_THREADS);
+    if (engine == DK_FDO) {
+        if (with_ann) dk::playout_state_kernel<DK_FDO, true><<<grid, dk::STATE_THREADS, 0, s>>>(rp, (uint64_t)n, states, 1u, points_out, steps_out, compact);
+        else dk::playout_state_kernel<DK_FDO, false><<<grid, dk::STATE_THREADS, 0, s>>>(rp, (uint64_t)n, states, 1u, points_out, steps_out, compact);
+    } else {
+        dk::playout_state_kernel<DK_DOKO, false><<<grid, dk::STATE_THREADS, 0, s>>>(rp, (uint64_t)n, states, 1u, points_out, steps_out, compact);
+    }
+    return check_launch(ctx, "playout_state_kernel");
+}
+
 dk_status dk_playout(dk_ctx* ctx, int engine, uint32_t flags, size_t n, const dk_state* states, const dk_rng* rng,
                      int32_t* points_out, uint32_t* steps_out, dk_stream stream) {
     if (!ctx || !rng || (engine != DK_FDO && engine != DK_DOKO)) return DK_ERR_INVALID_ARGUMENT;
     if (n == 0) return DK_OK;
     DK_CUDA(ctx, cudaSetDevice(ctx->device));
-    cudaStream_t s = pick_stream(ctx, stream);
-    dk::RngParams rp = to_params(rng);
-    const bool with_ann = (flags & DK_PLAYOUT_WITH_ANNOUNCEMENTS) != 0;
-    if (states == nullptr) {
-        unsigned grid = (unsigned)((n + dk::PLAYOUT_THREADS - 1) / dk::PLAYOUT_THREADS);
-        if (engine == DK_FDO) {
-            if (with_ann) dk::fdo_playout_fresh_kernel<true><<<grid, dk::PLAYOUT_THREADS, 0, s>>>(rp, (uint64_t)n, (int4*)points_out, steps_out);
-            else dk::fdo_playout_fresh_kernel<false><<<grid, dk::PLAYOUT_THREADS, 0, s>>>(rp, (uint64_t)n, (int4*)points_out, steps_out);
-            return check_launch(ctx, "fdo_playout_fresh_kernel");
-        }
-        dk::doko_playout_fresh_kernel<false><<<grid, dk::PLAYOUT_THREADS, 0, s>>>(rp, (uint64_t)n, (int4*)points_out, steps_out, nullptr, nullptr);
-        return check_launch(ctx, "doko_playout_fresh_kernel");
-    }
-    unsigned grid = (unsigned)((n + dk::STATE_THREADS - 1) / dk::STATE_THREADS);
-    if (engine == DK_FDO) {
-        if (with_ann) dk::playout_state_kernel<DK_FDO, true><<<grid, dk::STATE_THREADS, 0, s>>>(rp, (uint64_t)n, states, 1u, (int4*)points_out, steps_out);
-        else dk::playout_state_kernel<DK_FDO, false><<<grid, dk::STATE_THREADS, 0, s>>>(rp, (uint64_t)n, states, 1u, (int4*)points_out, steps_out);
-    } else {
-        dk::playout_state_kernel<DK_DOKO, false><<<grid, dk::STATE_THREADS, 0, s>>>(rp, (uint64_t)n, states, 1u, (int4*)points_out, steps_out);
-    }
-    return check_launch(ctx, "playout_state_kernel");
+    return playout_launch(ctx, engine, flags, n, states, to_params(rng), points_out, steps_out, false, pick_stream(ctx, stream));
 }
 
 dk_status dk_playout_trace(dk_ctx* ctx, int engine, size_t n, const dk_rng* rng, int32_t* points_out, uint8_t* trace_out, uint32_t* aux_out,
@@ -156,7 +164,7 @@ dk_status dk_playout_trace(dk_ctx* ctx, int engine, size_t n, const dk_rng* rng,
     if (n == 0) return DK_OK;
     DK_CUDA(ctx, cudaSetDevice(ctx->device));
     unsigned grid = (unsigned)((n + dk::PLAYOUT_THREADS - 1) / dk::PLAYOUT_THREADS);
-    dk::doko_playout_fresh_kernel<true><<<grid, dk::PLAYOUT_THREADS, 0, pick_stream(ctx, stream)>>>(to_params(rng), (uint64_t)n, (int4*)points_out, nullptr,
+    dk::doko_playout_fresh_kernel<true><<<grid, dk::PLAYOUT_THREADS, 0, pick_stream(ctx, stream)>>>(to_params(rng), (uint64_t)n, points_out, nullptr, false,
                                                                                                     trace_out, (uint4*)aux_out);
     return check_launch(ctx, "doko_playout_fresh_kernel<trace>");
 }
@@ -319,25 +327,57 @@ dk_status dk_allreduce_root_stats(dk_ctx* ctx, size_t n_values, int64_t* values,
     return rc ? nccl_fail(ctx, "ncclAllReduce", rc) : DK_OK;
 }
 
-dk_status dk_playout_host(dk_ctx* ctx, int engine, uint32_t flags, size_t n, const dk_state* states_host, const dk_rng* rng,
-                          int32_t* points_out_host, uint32_t* steps_out_host) {
-    if (!ctx || !rng) return DK_ERR_INVALID_ARGUMENT;
+// Host-buffer playouts.  The batch is cut into chunks; chunk c's kernel runs on the compute stream while chunk c-1's results are
+// copied to the host on the copy stream, so the PCIe transfer overlaps the simulation (pinned host buffers make the copies truly
+// asynchronous; pageable ones still work).
+static dk_status playout_host_impl(dk_ctx* ctx, int engine, uint32_t flags, size_t n, const dk_state* states_host, const dk_rng* rng,
+                                   void* points_out_host, void* steps_out_host, bool compact) {
+    if (!ctx || !rng || (engine != DK_FDO && engine != DK_DOKO)) return DK_ERR_INVALID_ARGUMENT;
     if (n == 0) return DK_OK;
     DK_CUDA(ctx, cudaSetDevice(ctx->device));
-    size_t b_states = states_host ? n * sizeof(dk_state) : 0, b_pts = n * 16, b_steps = n * 4;
+    const size_t pb = compact ? 4 : 16, sb = compact ? 1 : 4;
+    size_t b_states = states_host ? n * sizeof(dk_state) : 0, b_pts = n * pb, b_steps = n * sb;
+    b_pts = (b_pts + 255) & ~(size_t)255;
     dk_status st = ensure_scratch(ctx, b_states + b_pts + b_steps);
     if (st != DK_OK) return st;
+    if (!ctx->copy_stream) DK_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     char* base = (char*)ctx->d_scratch;
     dk_state* d_states = states_host ? (dk_state*)base : nullptr;
-    int32_t* d_pts = (int32_t*)(base + b_states);
-    uint32_t* d_steps = (uint32_t*)(base + b_states + b_pts);
+    char* d_pts = base + b_states;
+    char* d_steps = base + b_states + b_pts;
     if (states_host) DK_CUDA(ctx, cudaMemcpyAsync(d_states, states_host, b_states, cudaMemcpyHostToDevice, ctx->stream));
-    st = dk_playout(ctx, engine, flags, n, d_states, rng, d_pts, d_steps, ctx->stream);
-    if (st != DK_OK) return st;
-    if (points_out_host) DK_CUDA(ctx, cudaMemcpyAsync(points_out_host, d_pts, b_pts, cudaMemcpyDeviceToHost, ctx->stream));
-    if (steps_out_host) DK_CUDA(ctx, cudaMemcpyAsync(steps_out_host, d_steps, b_steps, cudaMemcpyDeviceToHost, ctx->stream));
+    const size_t CH = (size_t)1 << 21;
+    const size_t n_chunks = (n + CH - 1) / CH;
+    if (ctx->events.size() < n_chunks) {
+        size_t old = ctx->events.size();
+        ctx->events.resize(n_chunks);
+        for (size_t e = old; e < n_chunks; ++e) DK_CUDA(ctx, cudaEventCreateWithFlags(&ctx->events[e], cudaEventDisableTiming));
+    }
+    dk::RngParams rp = to_params(rng);
+    for (size_t c = 0; c < n_chunks; ++c) {
+        size_t off = c * CH, cnt = n - off < CH ? n - off : CH;
+        dk::RngParams rc = rp;
+        rc.first_id = rp.first_id + off;
+        st = playout_launch(ctx, engine, flags, cnt, d_states ? d_states + off : nullptr, rc, d_pts + off * pb, d_steps + off * sb, compact, ctx->stream);
+        if (st != DK_OK) return st;
+        DK_CUDA(ctx, cudaEventRecord(ctx->events[c], ctx->stream));
+        DK_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->events[c], 0));
+        if (points_out_host) DK_CUDA(ctx, cudaMemcpyAsync((char*)points_out_host + off * pb, d_pts + off * pb, cnt * pb, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        if (steps_out_host) DK_CUDA(ctx, cudaMemcpyAsync((char*)steps_out_host + off * sb, d_steps + off * sb, cnt * sb, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    }
+    DK_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
     DK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return DK_OK;
+}
+
+dk_status dk_playout_host(dk_ctx* ctx, int engine, uint32_t flags, size_t n, const dk_state* states_host, const dk_rng* rng,
+                          int32_t* points_out_host, uint32_t* steps_out_host) {
+    return playout_host_impl(ctx, engine, flags, n, states_host, rng, points_out_host, steps_out_host, false);
+}
+
+dk_status dk_playout_host_compact(dk_ctx* ctx, int engine, uint32_t flags, size_t n, const dk_state* states_host, const dk_rng* rng,
+                                  int8_t* points_out_host, uint8_t* steps_out_host) {
+    return playout_host_impl(ctx, engine, flags, n, states_host, rng, points_out_host, steps_out_host, true);
 }
 
 }  // extern "C"

@@ -126,7 +126,7 @@ DK_HD uint32_t card_suit(uint32_t c) { return (c * 43u) >> 8; }           // c /
 DK_HD uint32_t card_eyes_by_rank(uint32_t rank) { return (0xB432A0u >> (4u * rank)) & 15u; }  // 0,10,2,3,4,11 (card_to_eyes.rs:8-40)
 
 // Trump masks per FdoGameType (rs-full-doko/src/card/card_color_masks.rs:7-246); plain colours are the
-// natural suits minus the trumps (equivalent to card_to_color.rs:11-258, checked by tests/test_rules_tables.py).
+// natural suits minus the trumps (equivalent to card_to_color.rs:11-258, checked by tests/test_oracle_rule_tables.py).
 DK_HD uint32_t trump_mask_for_game_type(uint32_t gt) {
     const uint32_t JACKS = (1u << 2) | (1u << 8) | (1u << 14) | (1u << 20);
     const uint32_t QUEENS = (1u << 3) | (1u << 9) | (1u << 15) | (1u << 21);
@@ -162,6 +162,26 @@ DK_HD uint32_t card_power(uint32_t c, uint32_t trump, uint32_t follow) {
     uint32_t tp = rank == 2u ? 4u + so : (rank == 3u ? 8u + so : (c == 7u ? 12u : plain));
     uint32_t cp = 1u + card_eyes_by_rank(rank);
     return (trump & bit) ? 16u + tp : ((follow & bit) ? cp : 0u);
+}
+
+// Per-card attribute word for the lock-step card loop (24 entries; staged in shared memory by the playout kernels: the lanes
+// of a warp index it with their own card, 24 words sit in 24 distinct banks, equal cards broadcast → conflict-free, and the
+// lookups run on the otherwise idle LSU pipe instead of the saturated ALU pipe):
+//   bits 0-3 eyes | 4-7 plain power (1 + eyes) | 8-12 trump power (16 + trump_to_rank order) | 13-14 suit
+DK_HD uint32_t card_lut_entry(uint32_t c) {
+    uint32_t suit = card_suit(c), rank = c - 6u * suit;
+    uint32_t so = suit ^ (suit >> 1);
+    uint32_t plain = (0x310020u >> (4u * rank)) & 15u;
+    uint32_t tp = rank == 2u ? 4u + so : (rank == 3u ? 8u + so : (c == 7u ? 12u : plain));
+    uint32_t eyes = card_eyes_by_rank(rank);
+    return eyes | ((1u + eyes) << 4) | ((16u + tp) << 8) | (suit << 13);
+}
+DK_HD uint32_t follow_mask_lut(uint32_t c, uint32_t entry, uint32_t trump) {
+    uint32_t suit_cards = 0x3Fu << (6u * (entry >> 13));
+    return ((trump >> c) & 1u) ? trump : (suit_cards & ~trump);
+}
+DK_HD uint32_t card_power_lut(uint32_t bit, uint32_t entry, uint32_t trump, uint32_t follow) {
+    return (trump & bit) ? ((entry >> 8) & 31u) : ((follow & bit) ? ((entry >> 4) & 15u) : 0u);
 }
 
 }  // namespace dk

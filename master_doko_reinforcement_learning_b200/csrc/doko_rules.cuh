@@ -58,17 +58,20 @@ struct DokoTrickAcc { uint32_t follow, best, bestk, teyes; };
 
 // Card step of frame seat K (rs-doko/src/action/allowed_actions.rs:153-192, state/state.rs:194-252).
 template <int K>
-DK_HD uint32_t doko_card_step(DokoLive& g, uint32_t& h, DokoTrickAcc& a, uint32_t word) {
+DK_HD uint32_t doko_card_step(DokoLive& g, uint32_t& h, DokoTrickAcc& a, uint32_t word, const uint32_t* __restrict__ lut) {
     uint32_t mask = h;
     if (K > 0) { uint32_t f = h & a.follow; mask = f ? f : h; }
     uint32_t idx = mulhi(word, popc(mask));
     uint32_t c = pick_msb_rank24(mask, idx);
     uint32_t bit = 1u << c;
-    if (g.dup & bit) g.dup ^= bit; else h ^= bit;
-    if (K == 0) a.follow = follow_mask(c, DOKO_TRUMP_MASK);
-    uint32_t pw = card_power(c, DOKO_TRUMP_MASK, a.follow);
+    uint32_t e = lut[c];
+    uint32_t dbl = g.dup & bit;
+    g.dup ^= dbl;
+    h ^= bit ^ dbl;
+    if (K == 0) a.follow = follow_mask_lut(c, e, DOKO_TRUMP_MASK);
+    uint32_t pw = card_power_lut(bit, e, DOKO_TRUMP_MASK, a.follow);
     if (K == 0 || pw > a.best) { a.best = pw; a.bestk = (uint32_t)K; }
-    a.teyes += card_eyes_by_rank(c - 6u * card_suit(c));
+    a.teyes += e & 15u;
     g.steps++;
     return c;
 }
@@ -110,7 +113,7 @@ struct DokoResume {
 
 // trace (optional, FRESH only): 52 action ids in play order.
 template <bool FRESH, bool TRACE>
-DK_HD void doko_play_to_end(DokoLive& g, const RngKey& key, const DokoResume* rs, uint8_t* trace) {
+DK_HD void doko_play_to_end(DokoLive& g, const RngKey& key, const DokoResume* rs, uint8_t* trace, const uint32_t* __restrict__ lut) {
     uint32_t n_res = FRESH ? 0u : rs->n_res;
     if (n_res < 4u) {
         U4 blk = rng_block(key, SITE_RESERVATION, 0);
@@ -132,10 +135,10 @@ DK_HD void doko_play_to_end(DokoLive& g, const RngKey& key, const DokoResume* rs
         bool first = !FRESH && t == t0;
         if (first) { k0 = rs->k0; if (k0 > 0u) a = rs->acc; }
         uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
-        if (!first || k0 <= 0u) c0 = doko_card_step<0>(g, g.h0, a, blk.x);
-        if (!first || k0 <= 1u) c1 = doko_card_step<1>(g, g.h1, a, blk.y);
-        if (!first || k0 <= 2u) c2 = doko_card_step<2>(g, g.h2, a, blk.z);
-        c3 = doko_card_step<3>(g, g.h3, a, blk.w);
+        if (!first || k0 <= 0u) c0 = doko_card_step<0>(g, g.h0, a, blk.x, lut);
+        if (!first || k0 <= 1u) c1 = doko_card_step<1>(g, g.h1, a, blk.y, lut);
+        if (!first || k0 <= 2u) c2 = doko_card_step<2>(g, g.h2, a, blk.z, lut);
+        c3 = doko_card_step<3>(g, g.h3, a, blk.w, lut);
         if (TRACE) { trace[4 + 4 * t] = (uint8_t)c0; trace[5 + 4 * t] = (uint8_t)c1; trace[6 + 4 * t] = (uint8_t)c2; trace[7 + 4 * t] = (uint8_t)c3; }
         doko_trick_done(g, a, t);
     }
@@ -147,7 +150,7 @@ DK_HD void doko_live_clear(DokoLive& g) {
 }
 
 template <bool TRACE, class Deck>
-DK_HD void doko_playout_fresh(const RngKey& key, Deck& deck, int32_t pts[4], uint32_t& steps, uint8_t* trace, uint32_t* aux) {
+DK_HD void doko_playout_fresh(const RngKey& key, Deck& deck, const uint32_t* __restrict__ lut, int32_t pts[4], uint32_t& steps, uint8_t* trace, uint32_t* aux) {
     DokoLive g;
     doko_live_clear(g);
     FdoLive dummy; dummy.base = 0;
@@ -155,7 +158,7 @@ DK_HD void doko_playout_fresh(const RngKey& key, Deck& deck, int32_t pts[4], uin
     fdo_deal(dummy, key, deck, ah, g.dup, start);        // same deal contract as the full engine
     g.h0 = ah[0]; g.h1 = ah[1]; g.h2 = ah[2]; g.h3 = ah[3];
     doko_rotate(g, start);
-    doko_play_to_end<true, TRACE>(g, key, nullptr, trace);
+    doko_play_to_end<true, TRACE>(g, key, nullptr, trace, lut);
     doko_final_points(g, pts);
     steps = g.steps;
     if (TRACE && aux) { aux[0] = g.wedding ? 1u : 0u; aux[1] = g.re_mask; aux[2] = g.eyes; aux[3] = g.ntricks; }

@@ -219,6 +219,10 @@ DK_HD uint32_t fdo_pick_reservation(uint32_t h, uint32_t dup, uint32_t word) {
 //   turns   consecutive "no" so far (auto-skipped seats count, announcement.rs:156-165)
 //   starts  2 bits per trick: absolute seat that leads trick t
 // Every decision that actually reaches a seat is one play_action ("game step") and consumes one word of SITE_ANNOUNCEMENT.
+// Announcement decisions are two-way draws ({NoAnnouncement, call}; MSB-rank 1 = the call), so the parity contract gives them ONE
+// BIT each: decision k of the call is bit (k & 31) of word (k >> 5) of the SITE_ANNOUNCEMENT stream.  Block 0 (128 decisions; the
+// longest game seen in 2x10^5 has 47) is computed in lock-step by all lanes before the data-dependent replay loop, so the loop
+// contains no Philox code; later blocks are fetched on demand.
 template <bool WITH_ANN>
 DK_HD void fdo_replay_announcements(FdoLive& g, const RngKey& key, uint32_t starts, uint32_t ci, uint32_t p, uint32_t turns) {
     const bool wedding = g.team_tag == TEAM_WEDDING_SOLVED;       // (an unsolved wedding cannot survive trick 2)
@@ -229,49 +233,62 @@ DK_HD void fdo_replay_announcements(FdoLive& g, const RngKey& key, uint32_t star
         p = (((starts >> (2u * (ci >> 2))) & 3u) + (ci & 3u)) & 3u;
         turns = 0;
     }
+    if (ci >= 48u) return;
     const uint32_t re = g.re_mask & 15u;
-    while (ci < 48u) {
-        uint32_t t = ci >> 2, k = ci & 3u;
-        uint32_t cmax = 12u - t;
-        uint32_t thr_re = fdo_min_cards_to_call(g.re_low, g.ko_low, w), thr_ko = fdo_min_cards_to_call(g.ko_low, g.re_low, w);
-        if (cmax < (thr_re < thr_ko ? thr_re : thr_ko)) break;     // monotone: nobody can ever call again
-        uint32_t base = (starts >> (2u * t)) & 3u;
-        uint32_t played = (((1u << k) - 1u) << base); played = (played | (played >> 4)) & 15u;   // seats that already played in trick t
+    uint32_t re_low = g.re_low, ko_low = g.ko_low, steps = 0, ord = g.ann_count;
+    uint32_t thr_re = fdo_min_cards_to_call(re_low, ko_low, w), thr_ko = fdo_min_cards_to_call(ko_low, re_low, w);
+    U4 bits; bits.x = bits.y = bits.z = bits.w = 0;
+    uint32_t bits_blk = 0;
+    if (WITH_ANN) bits = rng_block(key, SITE_ANNOUNCEMENT, 0);
+    // per-position values (recomputed when ci advances)
+    uint32_t cmax = 12u - (ci >> 2);
+    uint32_t base = (starts >> (2u * (ci >> 2))) & 3u;
+    uint32_t played = ((1u << (ci & 3u)) - 1u) << base; played = (played | (played >> 4)) & 15u;   // seats that already played in this trick
+    while (cmax >= (thr_re < thr_ko ? thr_re : thr_ko)) {         // else: monotone, nobody can ever call again
         // eligibility by absolute seat: cards on hand >= the team's threshold
         uint32_t e_re = cmax >= thr_re ? (cmax - 1u >= thr_re ? 15u : (~played & 15u)) : 0u;
         uint32_t e_ko = cmax >= thr_ko ? (cmax - 1u >= thr_ko ? 15u : (~played & 15u)) : 0u;
         uint32_t elig = (e_re & re) | (e_ko & ~re & 15u);
         uint32_t rot = ((elig | (elig << 4)) >> p) & 15u;
-        uint32_t d = rot ? ffs0(rot) : 4u;                        // seats skipped before the next eligible one
+        uint32_t d = rot ? ffs0(rot) : 4u;                        // seats auto-skipped before the next eligible one
         if (turns + d >= 4u) {                                    // RoundIsOver → card ci is played; next round
             ci++;
-            p = (((starts >> (2u * (ci >> 2))) & 3u) + (ci & 3u)) & 3u;
+            if (ci >= 48u) break;
+            cmax = 12u - (ci >> 2);
+            base = (starts >> (2u * (ci >> 2))) & 3u;
+            played = ((1u << (ci & 3u)) - 1u) << base; played = (played | (played >> 4)) & 15u;
+            p = (base + (ci & 3u)) & 3u;
             turns = 0;
             continue;
         }
         p = (p + d) & 3u; turns += d;
         uint32_t is_re = (re >> p) & 1u;
         uint32_t c = cmax - ((played >> p) & 1u);
-        uint32_t m = is_re ? g.re_low : g.ko_low, e = is_re ? g.ko_low : g.re_low;
-        uint32_t call = fdo_allowed_call(c, m, e, w);
-        g.steps++;
-        uint32_t ord = g.ann_count++;
+        uint32_t m = is_re ? re_low : ko_low;
+        uint32_t ml = m == 6u ? 0u : m;
+        uint32_t call = (ml < 5u && c + ml + w >= 11u) ? ml + 1u : 1u;   // the seat is eligible: next level, else the counter (→ Re/Kontra)
+        steps++;
         bool says = false;
         if (WITH_ANN) {                                           // allowed = {call, NoAnnouncement}: MSB rank 0 = NoAnnouncement
-            if ((ord >> 2) != g.ann_blk_id) { g.ann_blk_id = ord >> 2; g.ann_blk = rng_block(key, SITE_ANNOUNCEMENT, ord >> 2); }
-            says = mulhi(u4_word(g.ann_blk, ord & 3u), 2u) == 1u;
+            if ((ord >> 7) != bits_blk) { bits_blk = ord >> 7; bits = rng_block(key, SITE_ANNOUNCEMENT, bits_blk); }
+            says = (u4_word(bits, (ord >> 5) & 3u) >> (ord & 31u)) & 1u;
         }
-        if (says) { if (is_re) g.re_low = call; else g.ko_low = call; turns = 0; }   // announcement.rs:203-210
-        else turns++;
+        ord++;
+        if (says) {                                               // announcement.rs:203-210
+            if (is_re) re_low = call; else ko_low = call;
+            turns = 0;
+            thr_re = fdo_min_cards_to_call(re_low, ko_low, w); thr_ko = fdo_min_cards_to_call(ko_low, re_low, w);
+        } else turns++;
         p = (p + 1u) & 3u;
     }
+    g.re_low = re_low; g.ko_low = ko_low; g.steps += steps; g.ann_count = ord;
 }
 
 struct TrickAcc { uint32_t follow, best, bestk, bestc, teyes, foxm; };
 
 // Card step of frame seat K (compile-time) with hand register `h` (action/allowed_actions.rs:97-140, state.rs:274-357).
 template <int K>
-DK_HD void fdo_card_step(FdoLive& g, uint32_t& h, TrickAcc& a, uint32_t word, bool last_trick) {
+DK_HD void fdo_card_step(FdoLive& g, uint32_t& h, TrickAcc& a, uint32_t word, bool last_trick, const uint32_t* __restrict__ lut) {
     uint32_t mask = h;
     if (K > 0 && !last_trick) {                           // state.rs:360-372: no colour is enforced in the 12th trick
         uint32_t f = h & a.follow;
@@ -281,12 +298,14 @@ DK_HD void fdo_card_step(FdoLive& g, uint32_t& h, TrickAcc& a, uint32_t word, bo
     uint32_t idx = mulhi(word, n);
     uint32_t c = pick_msb_rank24(mask, idx);
     uint32_t bit = 1u << c;
-    if (g.dup & bit) g.dup ^= bit; else h ^= bit;         // hand.remove: a doubled card stays in the hand once
-    if (K == 0) a.follow = follow_mask(c, g.trump);
-    uint32_t pw = card_power(c, g.trump, a.follow);
+    uint32_t e = lut[c];
+    uint32_t dbl = g.dup & bit;                           // hand.remove: a doubled card stays in the hand once
+    g.dup ^= dbl;
+    h ^= bit ^ dbl;
+    if (K == 0) a.follow = follow_mask_lut(c, e, g.trump);
+    uint32_t pw = card_power_lut(bit, e, g.trump, a.follow);
     if (K == 0 || pw > a.best) { a.best = pw; a.bestk = (uint32_t)K; a.bestc = c; }   // strict: first of equals wins
-    uint32_t suit = card_suit(c);
-    a.teyes += card_eyes_by_rank(c - 6u * suit);
+    a.teyes += e & 15u;
     if (c == CARD_DA) a.foxm |= 1u << K;
     g.steps++;
 }
@@ -347,7 +366,7 @@ struct FdoResume {
 
 // Plays the game to the end.  FRESH: hands/base already set by the deal, nothing played yet.
 template <bool WITH_ANN, bool FRESH>
-DK_HD void fdo_play_to_end(FdoLive& g, const RngKey& key, const FdoResume* rs) {
+DK_HD void fdo_play_to_end(FdoLive& g, const RngKey& key, const FdoResume* rs, const uint32_t* __restrict__ lut) {
     uint32_t n_res = FRESH ? 0u : rs->n_res;
     if (n_res < 4u) {
         U4 blk = rng_block(key, SITE_RESERVATION, 0);
@@ -371,7 +390,7 @@ DK_HD void fdo_play_to_end(FdoLive& g, const RngKey& key, const FdoResume* rs) {
         if (first) { k0 = rs->k0; if (k0 > 0u) a = rs->acc; }
         bool last = t == 11u;
 #define DK_FDO_POS(K, HREG, WORD)                                                                      \
-        if (!first || k0 <= (uint32_t)(K)) fdo_card_step<K>(g, HREG, a, WORD, last);
+        if (!first || k0 <= (uint32_t)(K)) fdo_card_step<K>(g, HREG, a, WORD, last, lut);
         DK_FDO_POS(0, g.h0, blk.x)
         DK_FDO_POS(1, g.h1, blk.y)
         DK_FDO_POS(2, g.h2, blk.z)
@@ -386,7 +405,7 @@ DK_HD void fdo_play_to_end(FdoLive& g, const RngKey& key, const FdoResume* rs) {
 
 // Fresh game: deal + reservations + 12 tricks + scoring.
 template <bool WITH_ANN, class Deck>
-DK_HD void fdo_playout_fresh(const RngKey& key, Deck& deck, int32_t pts[4], uint32_t& steps) {
+DK_HD void fdo_playout_fresh(const RngKey& key, Deck& deck, const uint32_t* __restrict__ lut, int32_t pts[4], uint32_t& steps) {
     FdoLive g;
     fdo_live_clear(g);
     uint32_t ah[4], start;
@@ -394,7 +413,7 @@ DK_HD void fdo_playout_fresh(const RngKey& key, Deck& deck, int32_t pts[4], uint
     g.h0 = ah[0]; g.h1 = ah[1]; g.h2 = ah[2]; g.h3 = ah[3];
     g.base = 0;
     fdo_rotate(g, start);
-    fdo_play_to_end<WITH_ANN, true>(g, key, nullptr);
+    fdo_play_to_end<WITH_ANN, true>(g, key, nullptr, lut);
     fdo_final_points(g, pts);
     steps = g.steps;
 }

@@ -18,6 +18,7 @@ struct RngParams {
     uint32_t seed_lo, seed_hi;
     uint64_t first_id;
     uint32_t epoch;
+    uint32_t first_sub;
 };
 
 // Per-thread 12-word scratch in shared memory, word-interleaved across the block so that every access of a
@@ -27,6 +28,12 @@ struct SharedDeck {
     __device__ __forceinline__ uint32_t get(uint32_t w) const { return base[w * PLAYOUT_THREADS]; }
     __device__ __forceinline__ void set(uint32_t w, uint32_t v) { base[w * PLAYOUT_THREADS] = v; }
 };
+
+// Stage the 24-entry card attribute table in shared memory (first 24 threads), then sync.
+__device__ __forceinline__ void stage_card_lut(uint32_t* lut) {
+    if (threadIdx.x < 24) lut[threadIdx.x] = card_lut_entry(threadIdx.x);
+    __syncthreads();
+}
 
 __device__ __forceinline__ RngKey make_key(const RngParams& rp, uint64_t index, uint32_t unit_hi_override, bool use_override) {
     uint64_t unit = rp.first_id + index;
@@ -38,12 +45,26 @@ __device__ __forceinline__ RngKey make_key(const RngParams& rp, uint64_t index, 
     return k;
 }
 
+// Playout results: int32[4] points + uint32 steps, or the compact host-transfer form int8[4] + uint8 (lossless: |points| < 128,
+// steps < 256) selected at run time (uniform branch).
+__device__ __forceinline__ void store_result(void* __restrict__ points, void* __restrict__ steps, uint64_t i, const int32_t p[4], uint32_t s, bool compact) {
+    if (compact) {
+        if (points) reinterpret_cast<char4*>(points)[i] = make_char4((signed char)p[0], (signed char)p[1], (signed char)p[2], (signed char)p[3]);
+        if (steps) reinterpret_cast<uint8_t*>(steps)[i] = (uint8_t)s;
+    } else {
+        if (points) reinterpret_cast<int4*>(points)[i] = make_int4(p[0], p[1], p[2], p[3]);
+        if (steps) reinterpret_cast<uint32_t*>(steps)[i] = s;
+    }
+}
+
 // K2: fresh full-rules playouts.  Replaces FdoState::new_game + the random_action loop
 // (rs-full-doko/src/state/state.rs:169-178,378-431).  HBM traffic: 0 B in, 16 B points + 4 B steps out per game.
 template <bool WITH_ANN>
 __global__ void __launch_bounds__(PLAYOUT_THREADS)
-fdo_playout_fresh_kernel(RngParams rp, uint64_t n, int4* __restrict__ points, uint32_t* __restrict__ steps) {
+fdo_playout_fresh_kernel(RngParams rp, uint64_t n, void* __restrict__ points, void* __restrict__ steps, bool compact) {
     __shared__ uint32_t smem[12 * PLAYOUT_THREADS];
+    __shared__ uint32_t lut[24];
+    stage_card_lut(lut);
     uint64_t i = (uint64_t)blockIdx.x * PLAYOUT_THREADS + threadIdx.x;
     // Out-of-range lanes play game n-1 again (keeps the warp converged); they just do not store.
     uint64_t gi = i < n ? i : n - 1;
@@ -52,11 +73,8 @@ fdo_playout_fresh_kernel(RngParams rp, uint64_t n, int4* __restrict__ points, ui
     RngKey key = make_key(rp, gi, 0, false);
     int32_t p[4];
     uint32_t s;
-    fdo_playout_fresh<WITH_ANN>(key, deck, p, s);
-    if (i < n) {
-        if (points) points[i] = make_int4(p[0], p[1], p[2], p[3]);
-        if (steps) steps[i] = s;
-    }
+    fdo_playout_fresh<WITH_ANN>(key, deck, lut, p, s);
+    if (i < n) store_result(points, steps, i, p, s, compact);
 }
 
 
@@ -64,9 +82,11 @@ fdo_playout_fresh_kernel(RngParams rp, uint64_t n, int4* __restrict__ points, ui
 // TRACE additionally writes the 52 action ids and (wedding flag, re mask, packed eyes, packed tricks) per game.
 template <bool TRACE>
 __global__ void __launch_bounds__(PLAYOUT_THREADS)
-doko_playout_fresh_kernel(RngParams rp, uint64_t n, int4* __restrict__ points, uint32_t* __restrict__ steps,
+doko_playout_fresh_kernel(RngParams rp, uint64_t n, void* __restrict__ points, void* __restrict__ steps, bool compact,
                           uint8_t* __restrict__ trace, uint4* __restrict__ aux) {
     __shared__ uint32_t smem[12 * PLAYOUT_THREADS];
+    __shared__ uint32_t lut[24];
+    stage_card_lut(lut);
     uint64_t i = (uint64_t)blockIdx.x * PLAYOUT_THREADS + threadIdx.x;
     uint64_t gi = i < n ? i : n - 1;
     SharedDeck deck;
@@ -75,10 +95,9 @@ doko_playout_fresh_kernel(RngParams rp, uint64_t n, int4* __restrict__ points, u
     int32_t p[4];
     uint32_t s, ax[4];
     uint8_t tr[52];
-    doko_playout_fresh<TRACE>(key, deck, p, s, tr, ax);
+    doko_playout_fresh<TRACE>(key, deck, lut, p, s, tr, ax);
     if (i < n) {
-        if (points) points[i] = make_int4(p[0], p[1], p[2], p[3]);
-        if (steps) steps[i] = s;
+        store_result(points, steps, i, p, s, compact);
         if (TRACE) {
             if (trace) for (int k = 0; k < 52; ++k) trace[i * 52 + k] = tr[k];
             if (aux) aux[i] = make_uint4(ax[0], ax[1], ax[2], ax[3]);
@@ -239,8 +258,10 @@ fdo_step_encode_kernel(RngParams rp, uint64_t n, dk_state* __restrict__ states, 
 // with-announcement loop.  unit = first_id + (i / per_unit), unit_hi = i % per_unit when per_unit > 1 (leaf rollouts).
 template <int ENGINE, bool WITH_ANN>
 __global__ void __launch_bounds__(STATE_THREADS)
-playout_state_kernel(RngParams rp, uint64_t n, const dk_state* __restrict__ states, uint32_t per_unit, int4* __restrict__ points,
-                     uint32_t* __restrict__ steps) {
+playout_state_kernel(RngParams rp, uint64_t n, const dk_state* __restrict__ states, uint32_t per_unit, void* __restrict__ points,
+                     void* __restrict__ steps, bool compact) {
+    __shared__ uint32_t lut[24];
+    stage_card_lut(lut);
     uint64_t i = (uint64_t)blockIdx.x * STATE_THREADS + threadIdx.x;
     if (i >= n) return;
     uint64_t unit = per_unit > 1u ? i / per_unit : i;
@@ -251,15 +272,14 @@ playout_state_kernel(RngParams rp, uint64_t n, const dk_state* __restrict__ stat
     uint32_t st = 0;
     if (ENGINE == DK_FDO) {
         FdoLive g; FdoResume rs;
-        if (fdo_state_to_live(s, g, rs)) { fdo_play_to_end<WITH_ANN, false>(g, key, &rs); fdo_final_points(g, p); st = g.steps; }
+        if (fdo_state_to_live(s, g, rs)) { fdo_play_to_end<WITH_ANN, false>(g, key, &rs, lut); fdo_final_points(g, p); st = g.steps; }
         else { p[0] = s.points[0]; p[1] = s.points[1]; p[2] = s.points[2]; p[3] = s.points[3]; }
     } else {
         DokoLive g; DokoResume rs;
-        if (doko_state_to_live(s, g, rs)) { doko_play_to_end<false, false>(g, key, &rs, nullptr); doko_final_points(g, p); st = g.steps; }
+        if (doko_state_to_live(s, g, rs)) { doko_play_to_end<false, false>(g, key, &rs, nullptr, lut); doko_final_points(g, p); st = g.steps; }
         else { p[0] = s.points[0]; p[1] = s.points[1]; p[2] = s.points[2]; p[3] = s.points[3]; }
     }
-    if (points) points[i] = make_int4(p[0], p[1], p[2], p[3]);
-    if (steps) steps[i] = st;
+    store_result(points, steps, i, p, st, compact);
 }
 
 
@@ -280,7 +300,7 @@ fdo_determinize_kernel(RngParams rp, uint64_t n_info, uint32_t samples, const dk
     }
     __syncthreads();
     for (uint32_t smp = threadIdx.x; smp < samples; smp += MATCH_THREADS) {
-        RngKey key = make_key(rp, i, smp, true);
+        RngKey key = make_key(rp, i, rp.first_sub + smp, true);
         uint64_t h[4];
         uint8_t r[4];
         uint32_t st = prep.valid ? fdo_match_sample(prep, key, h, r) : 2u;
@@ -304,6 +324,8 @@ fdo_leaf_rollouts_kernel(RngParams rp, uint64_t n_leaves, uint32_t rollouts, int
     __shared__ MatchPrep prep;
     __shared__ __align__(16) dk_state leaf;
     __shared__ int red[4];
+    __shared__ uint32_t lut[24];
+    if (threadIdx.x < 24) lut[threadIdx.x] = card_lut_entry(threadIdx.x);
     uint64_t i = blockIdx.x;
     if (i >= n_leaves) return;
     if (threadIdx.x < 8) reinterpret_cast<uint4*>(&leaf)[threadIdx.x] = __ldg(reinterpret_cast<const uint4*>(states + i) + threadIdx.x);
@@ -313,7 +335,7 @@ fdo_leaf_rollouts_kernel(RngParams rp, uint64_t n_leaves, uint32_t rollouts, int
     __syncthreads();
     int acc[4] = {0, 0, 0, 0};
     for (uint32_t r = threadIdx.x; r < rollouts; r += MATCH_THREADS) {
-        RngKey key = make_key(rp, i, r, true);
+        RngKey key = make_key(rp, i, rp.first_sub + r, true);
         alignas(16) dk_state s = leaf;
         uint32_t status = 0;
         if (determinize && prep.valid) {
@@ -325,7 +347,7 @@ fdo_leaf_rollouts_kernel(RngParams rp, uint64_t n_leaves, uint32_t rollouts, int
         if (status == 0u) {
             FdoLive g; FdoResume rs;
             int32_t p[4];
-            if (fdo_state_to_live(s, g, rs)) { fdo_play_to_end<false, false>(g, key, &rs); fdo_final_points(g, p); }
+            if (fdo_state_to_live(s, g, rs)) { fdo_play_to_end<false, false>(g, key, &rs, lut); fdo_final_points(g, p); }
             else { p[0] = s.points[0]; p[1] = s.points[1]; p[2] = s.points[2]; p[3] = s.points[3]; }
             acc[0] += p[0]; acc[1] += p[1]; acc[2] += p[2]; acc[3] += p[3];
         }

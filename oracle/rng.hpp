@@ -19,8 +19,8 @@
 //  * PhiloxStream — the parity stream shared with the CUDA kernels.  Philox4x32-10, counter =
 //    (unit_lo, unit_hi, site<<16 | block, epoch), key = 64-bit seed.  Every reference RNG call
 //    site is a "site"; its k-th use inside one unit (game / sample / rollout) takes word k of
-//    that site's stream and maps it with idx = (uint64(w) * n) >> 32.  See DESIGN.md "Philox
-//    parity contract".
+//    that site's stream and maps it with idx = (uint64(w) * n) >> 32 (announcement decisions, which
+//    are two-way, take one bit each).  See DESIGN.md "Philox parity contract".
 #pragma once
 #include <cstdint>
 #include <cstring>
@@ -108,7 +108,16 @@ struct PhiloxStream final : Rng {
     uint32_t word(Site site) {
         return philox_word(seed, unit_lo, unit_hi, epoch, site, ordinal[site]++);
     }
-    uint32_t below(Site site, uint32_t n) override { return mul_shift(word(site), n); }
+    uint32_t below(Site site, uint32_t n) override {
+        if (site == SITE_ANNOUNCEMENT && n <= 2) {
+            // Announcement decisions are draws over {NoAnnouncement, call} (n = 2) or {NoAnnouncement} (n = 1): they take ONE BIT
+            // each — decision k is bit (k & 31) of word (k >> 5) of the site's stream — instead of a whole word.
+            uint32_t k = ordinal[site]++;
+            uint32_t w = philox_word(seed, unit_lo, unit_hi, epoch, site, k >> 5);
+            return n == 2 ? ((w >> (k & 31)) & 1u) : 0u;
+        }
+        return mul_shift(word(site), n);
+    }
     void set_ordinal(Site site, uint32_t o) override { ordinal[site] = o; }
     uint32_t start_player() override { return below(SITE_DEAL, 4); }
     // Durstenfeld, descending: for i in 47..1: j = draw(i+1); swap(i, j).

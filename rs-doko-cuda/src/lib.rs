@@ -31,7 +31,7 @@ pub struct dk_rng {
     pub seed: u64,
     pub first_id: u64,
     pub epoch: u32,
-    pub reserved: u32,
+    pub first_sub: u32,
 }
 
 pub const DK_DOKO: c_int = 0;
@@ -84,7 +84,7 @@ impl DokoCuda {
     /// The batched replacement of `McFullDokoEnvState::random_rollout` for `n` fresh games
     /// (rs-doko-mcts/src/env/envs/env_state_full_doko.rs:198-220): rewards = player_points as f64.
     pub fn random_playouts(&self, n: usize, seed: u64, first_id: u64, with_announcements: bool) -> Result<Vec<[f64; 4]>, DokoError> {
-        let rng = dk_rng { seed, first_id, epoch: 0, reserved: 0 };
+        let rng = dk_rng { seed, first_id, epoch: 0, first_sub: 0 };
         let mut pts = vec![0i32; n * 4];
         let flags = if with_announcements { DK_PLAYOUT_WITH_ANNOUNCEMENTS } else { 0 };
         self.check(unsafe { dk_playout_host(self.ctx, DK_FDO, flags, n, std::ptr::null(), &rng, pts.as_mut_ptr(), std::ptr::null_mut()) })?;

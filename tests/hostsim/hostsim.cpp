@@ -22,6 +22,12 @@ struct LocalDeck {
     uint32_t get(uint32_t i) const { return w[i]; }
     void set(uint32_t i, uint32_t v) { w[i] = v; }
 };
+const uint32_t* card_lut() {
+    static uint32_t lut[24];
+    static bool init = false;
+    if (!init) { for (uint32_t c = 0; c < 24; ++c) lut[c] = dk::card_lut_entry(c); init = true; }
+    return lut;
+}
 dk::RngKey make_key(uint64_t seed, uint64_t unit, uint32_t epoch) {
     dk::RngKey k; k.seed_lo = (uint32_t)seed; k.seed_hi = (uint32_t)(seed >> 32); k.unit_lo = (uint32_t)unit; k.unit_hi = (uint32_t)(unit >> 32); k.epoch = epoch;
     return k;
@@ -33,7 +39,7 @@ SIM_API void sim_fdo_playout_fresh(uint64_t seed, uint32_t epoch, uint64_t first
         LocalDeck deck;
         dk::RngKey key = make_key(seed, first_id + i, epoch);
         int32_t p[4]; uint32_t s;
-        if (with_ann) dk::fdo_playout_fresh<true>(key, deck, p, s); else dk::fdo_playout_fresh<false>(key, deck, p, s);
+        if (with_ann) dk::fdo_playout_fresh<true>(key, deck, card_lut(), p, s); else dk::fdo_playout_fresh<false>(key, deck, card_lut(), p, s);
         for (int q = 0; q < 4; ++q) points[i * 4 + q] = p[q];
         steps[i] = s;
     }
@@ -43,7 +49,7 @@ SIM_API void sim_doko_playout_fresh(uint64_t seed, uint32_t epoch, uint64_t firs
         LocalDeck deck;
         dk::RngKey key = make_key(seed, first_id + i, epoch);
         int32_t p[4]; uint32_t s; uint8_t tr[52]; uint32_t ax[4];
-        dk::doko_playout_fresh<true>(key, deck, p, s, tr, ax);
+        dk::doko_playout_fresh<true>(key, deck, card_lut(), p, s, tr, ax);
         for (int q = 0; q < 4; ++q) points[i * 4 + q] = p[q];
         steps[i] = s;
         if (trace) std::memcpy(trace + i * 52, tr, 52);
@@ -77,12 +83,12 @@ SIM_API int sim_playout_from_state(int engine, const dk_state* s, uint64_t seed,
     if (engine == DK_FDO) {
         dk::FdoLive g; dk::FdoResume rs;
         if (!dk::fdo_state_to_live(*s, g, rs)) { for (int p = 0; p < 4; ++p) points[p] = s->points[p]; *steps = 0; return 0; }
-        if (with_ann) dk::fdo_play_to_end<true, false>(g, key, &rs); else dk::fdo_play_to_end<false, false>(g, key, &rs);
+        if (with_ann) dk::fdo_play_to_end<true, false>(g, key, &rs, card_lut()); else dk::fdo_play_to_end<false, false>(g, key, &rs, card_lut());
         dk::fdo_final_points(g, points); *steps = g.steps;
     } else {
         dk::DokoLive g; dk::DokoResume rs;
         if (!dk::doko_state_to_live(*s, g, rs)) { for (int p = 0; p < 4; ++p) points[p] = s->points[p]; *steps = 0; return 0; }
-        dk::doko_play_to_end<false, false>(g, key, &rs, nullptr);
+        dk::doko_play_to_end<false, false>(g, key, &rs, nullptr, card_lut());
         dk::doko_final_points(g, points); *steps = g.steps;
     }
     return 1;
@@ -109,7 +115,7 @@ SIM_API uint32_t sim_fdo_leaf_rollout(const dk_state* s, uint64_t seed, uint64_t
     if (status) return status;
     dk::FdoLive g; dk::FdoResume rs;
     if (!dk::fdo_state_to_live(st, g, rs)) { for (int p = 0; p < 4; ++p) points[p] = st.points[p]; return 0; }
-    dk::fdo_play_to_end<false, false>(g, key, &rs);
+    dk::fdo_play_to_end<false, false>(g, key, &rs, card_lut());
     dk::fdo_final_points(g, points); *steps = g.steps;
     return 0;
 }

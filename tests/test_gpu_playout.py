@@ -74,3 +74,36 @@ def test_fdo_full_size_properties(dk):
     pts2, steps2 = dk.playout(pkg.DK_FDO, half, dk.rng(SEED, half, 2), flags=1)
     torch.cuda.synchronize()
     assert torch.equal(pts[half:], pts2) and torch.equal(steps[half:], steps2)
+
+
+def test_fdo_host_compact_and_chunked_paths(dk, orc):
+    """dk_playout_host / _compact cut the batch into 2^21-game chunks: results must equal the single-launch device path."""
+    import torch
+
+    import master_doko_reinforcement_learning_b200 as pkg
+
+    n = (1 << 22) + 12345
+    rng = dk.rng(SEED, 1 << 33, 8)
+    pts_d, steps_d = dk.playout(pkg.DK_FDO, n, rng, flags=1)
+    torch.cuda.synchronize()
+    pts_h, steps_h = dk.playout_host(pkg.DK_FDO, n, rng, flags=1)
+    pts_c, steps_c = dk.playout_host_compact(pkg.DK_FDO, n, rng, flags=1)
+    pd, sd = pts_d.cpu().numpy(), steps_d.cpu().numpy()
+    assert np.array_equal(pd, pts_h) and np.array_equal(sd.astype(np.uint32), steps_h)
+    assert np.array_equal(pd, pts_c.astype(np.int32)) and np.array_equal(sd, steps_c.astype(np.int32))
+    assert int(np.abs(pd).max()) < 128 and int(sd.max()) < 256
+
+
+def test_host_playout_from_host_states(dk, orc):
+    import master_doko_reinforcement_learning_b200 as pkg
+    from oracle_lib import DK_STATE_DTYPE, Fdo
+
+    objs = [Fdo.new_game_philox(orc, SEED, i, 0) for i in range(64)]
+    for i, o in enumerate(objs):
+        for k in range(3 * i):
+            o.random_step(SEED, i, 0, True, k)
+    recs = np.array([o.export() for o in objs], dtype=DK_STATE_DTYPE)
+    pts, steps = dk.playout_host(pkg.DK_FDO, len(objs), dk.rng(SEED, 40, 2), states=recs, flags=0)
+    for i, o in enumerate(objs):
+        rp, rs = o.rollout(SEED, 40 + i, 0, 2, False)
+        assert list(pts[i]) == rp and int(steps[i]) == rs
