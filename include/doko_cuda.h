@@ -220,7 +220,9 @@ DK_API dk_status dk_playout_host_compact(dk_ctx* ctx, int engine, uint32_t flags
                                          const dk_rng* rng, int8_t* points_out_host /*[host] n*4*/, uint8_t* steps_out_host /*[host] n*/);
 
 /* ---- determinization ---------------------------------------------------------------------------------
- * replaces card_matching (rs-full-doko/src/matching/card_matching.rs:241-467) as called by CAPSampling::sample
+ * DK_DOKO replaces sample_assignment_full (rs-doko-assignment/src/assignment.rs:458-581): hands only; reservations_out repeats
+ *          the real reservations (DoReservation codes by absolute seat).
+ * DK_FDO replaces card_matching (rs-full-doko/src/matching/card_matching.rs:241-467) as called by CAPSampling::sample
  *          (rs-doko-py-bridge/src/compare_impi/compare_impi.rs:64-83); observer = seat to move.
  * For info-state i and sample s (unit = first_id + i, unit_hi = s):
  *   hands_out[(i*S+s)*4 + seat], reservations_out[(i*S+s)*4 + seat] (DK_RES_* by ABSOLUTE seat, DK_RES_NONE if the

@@ -1,0 +1,132 @@
+// assignment.cuh — hidden-hand sampler of the simplified engine (rs-doko-assignment/src/assignment.rs:13-581) as a
+// thread-per-sample program on count planes instead of Vecs.
+//
+// The reference keeps ordered Vec<DoCard> multisets and uses position()/remove(); what the ORDER influences is (a) which
+// single-owner card is found first (ascending card id, the hand_to_vec order of `remaining`) and (b) which element a random
+// index denotes (remaining cards in ascending id with doubles adjacent; eligible seats ascending).  Both are reproduced on
+// two 24-bit planes per multiset (a = count >= 1, b = count == 2).
+#pragma once
+#include "matching.cuh"
+
+namespace dk {
+
+struct AssignPrep {
+    Hand2 remaining;
+    Hand2 allowed[4];      // by ABSOLUTE seat (the observer's list is empty)
+    uint32_t len[4];
+    uint32_t observer;
+    uint32_t obs_a, obs_b;
+    uint32_t valid;
+};
+
+DK_HD uint32_t h2_count(const Hand2& h) { return popc(h.a) + popc(h.b); }
+
+// calc_remaining_cards (:13-41) + player_allowed_to_have (:78-282)
+DK_HD void doko_assign_prepare(const dk_state& s, AssignPrep& m) {
+    const uint32_t obs = st_phase(s) == DK_PHASE_FINISHED ? 0u : st_cur(s);
+    m.valid = 1; m.observer = obs;
+    const uint32_t own_a = hand_any24(s.hands[obs]), own_b = hand_both24(s.hands[obs]);
+    m.obs_a = own_a; m.obs_b = own_b;
+    // counts of played cards
+    uint32_t p1 = 0, p2 = 0;
+    const uint32_t ci = s.card_index;
+    for (uint32_t j = 0; j < ci; ++j) { uint32_t bit = 1u << s.cards[j]; p2 |= p1 & bit; p1 |= bit; }
+    // remaining = 2 - played - own per card type
+    uint32_t gone1 = p1 | own_a, gone2 = p2 | own_b | (p1 & own_a);     // at least one / both copies accounted for
+    m.remaining.a = ~gone2 & 0xFFFFFFu;                                  // count >= 1
+    m.remaining.b = ~gone1 & 0xFFFFFFu;                                  // count == 2
+    uint32_t drop[4] = {0, 0, 0, 0};
+    for (uint32_t j = 0; j < ci; ++j) {                                  // seats that did not follow lose the led colour (:226-246)
+        uint32_t f = follow_mask(s.cards[j & ~3u], DOKO_TRUMP_MASK);
+        if (!((f >> s.cards[j]) & 1u)) drop[(st_trick_start(s, j >> 2) + (j & 3u)) & 3u] |= f;
+    }
+    const uint32_t tag = st_team_tag(s);
+    if (tag == TEAM_WEDDING_UNSOLVED || tag == TEAM_WEDDING_SOLVED)      // wedding announced: nobody else holds a ♣Q (:252-268)
+        for (uint32_t p = 0; p < 4u; ++p) if (p != st_wed_seat(s)) drop[p] |= 1u << CARD_CQ;
+    for (uint32_t p = 0; p < 4u; ++p) {
+        m.len[p] = popcll(s.hands[p]);
+        m.allowed[p].a = p == obs ? 0u : (m.remaining.a & ~drop[p]);
+        m.allowed[p].b = p == obs ? 0u : (m.remaining.b & ~drop[p]);
+    }
+}
+
+struct AssignState { Hand2 remaining, allowed[4], hand[4]; uint32_t len[4]; };
+
+// distribute_card (:284-316)
+DK_HD void doko_assign_distribute(AssignState& a, uint32_t player, uint32_t c) {
+    const uint32_t bit = 1u << c;
+#pragma unroll
+    for (uint32_t i = 0; i < 4u; ++i) {
+        if (i == player) { h2_add(a.hand[i], bit); a.len[i] -= 1u; }
+        if (a.allowed[i].a & bit) h2_remove_one(a.allowed[i], bit);
+    }
+    h2_remove_one(a.remaining, bit);
+#pragma unroll
+    for (uint32_t i = 0; i < 4u; ++i)
+        if (a.len[i] == 0u) { a.allowed[i].a &= ~a.remaining.a; a.allowed[i].b &= ~a.remaining.a; }
+}
+DK_HD uint32_t doko_assign_eligible(const AssignState& a, uint32_t bit) {
+    uint32_t m = 0;
+#pragma unroll
+    for (uint32_t i = 0; i < 4u; ++i) if ((a.allowed[i].a & bit) && a.len[i] > 0u) m |= 1u << i;
+    return m;
+}
+// k-th element (0-based) of a multiset listed in ascending card id with doubles adjacent.
+DK_HD uint32_t h2_select_adjacent(const Hand2& h, uint32_t k) {
+    uint32_t lo = 0, hi = 24;                           // invariant: answer in [lo, hi)
+#pragma unroll
+    for (int it = 0; it < 5; ++it) {
+        uint32_t mid = (lo + hi) >> 1;
+        uint32_t below = (1u << mid) - 1u;
+        uint32_t cnt = popc(h.a & below) + popc(h.b & below);   // elements with card id < mid
+        if (k >= cnt) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+// sample_assignment (:493-581).  Returns 0 ok, 1 dead end.
+DK_HD uint32_t doko_assign_sample(const AssignPrep& p, const RngKey& key, uint64_t hands_out[4]) {
+    AssignState a;
+    a.remaining = p.remaining;
+#pragma unroll
+    for (uint32_t i = 0; i < 4u; ++i) { a.allowed[i] = p.allowed[i]; a.len[i] = p.len[i]; a.hand[i].a = 0; a.hand[i].b = 0; }
+    U4 blk; blk.x = blk.y = blk.z = blk.w = 0;
+    uint32_t blk_id = 0xFFFFFFFFu, ord = 0, status = 0;
+    for (;;) {
+        // distribute_single_cards (:336-377): first remaining card (ascending id) with exactly one eligible seat
+        bool did = false;
+        uint32_t bits = a.remaining.a;
+        while (bits) {
+            uint32_t c = ffs0(bits); bits &= bits - 1u;
+            uint32_t e = doko_assign_eligible(a, 1u << c);
+            if (e && !(e & (e - 1u))) { doko_assign_distribute(a, ffs0(e), c); did = true; break; }
+        }
+        if (did) continue;
+        // distribute_exactly_as_per_hand (:379-417)
+#pragma unroll
+        for (uint32_t i = 0; i < 4u; ++i) {
+            if (!did && a.len[i] > 0u && a.len[i] == h2_count(a.allowed[i])) {
+                uint32_t sa = a.allowed[i].a, sb = a.allowed[i].b;
+                while (sa) { uint32_t c = ffs0(sa); sa &= sa - 1u; doko_assign_distribute(a, i, c); if ((sb >> c) & 1u) doko_assign_distribute(a, i, c); }
+                did = true;
+            }
+        }
+        if (did) continue;
+        // distribute_single_card_randomly (:419-456)
+        uint32_t n = h2_count(a.remaining);
+        if (n == 0u) break;
+        uint32_t w0, w1;
+        { uint32_t o = ord++; if ((o >> 2) != blk_id) { blk_id = o >> 2; blk = rng_block(key, SITE_ASSIGN, blk_id); } w0 = u4_word(blk, o & 3u); }
+        uint32_t c = h2_select_adjacent(a.remaining, mulhi(w0, n));
+        uint32_t e = doko_assign_eligible(a, 1u << c);
+        if (e == 0u) { status = 1u; break; }            // `.choose(rng).unwrap()` on an empty list would panic
+        { uint32_t o = ord++; if ((o >> 2) != blk_id) { blk_id = o >> 2; blk = rng_block(key, SITE_ASSIGN, blk_id); } w1 = u4_word(blk, o & 3u); }
+        uint32_t seat = select_lsb(e, mulhi(w1, popc(e)));
+        doko_assign_distribute(a, seat, c);
+    }
+#pragma unroll
+    for (uint32_t i = 0; i < 4u; ++i) hands_out[i] = (uint64_t)a.hand[i].a | ((uint64_t)a.hand[i].b << 24);
+    hands_out[p.observer] = (uint64_t)p.obs_a | ((uint64_t)p.obs_b << 24);     // hand_from_vec(hand_to_vec(own)): canonical copy order
+    return status;
+}
+
+}  // namespace dk

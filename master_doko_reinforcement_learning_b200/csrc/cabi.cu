@@ -243,10 +243,15 @@ dk_status dk_step_random_encode(dk_ctx* ctx, size_t n, dk_state* states, const d
 dk_status dk_determinize(dk_ctx* ctx, int engine, size_t n_info, size_t samples_per_info, const dk_state* states, const dk_rng* rng,
                          uint64_t* hands_out, uint8_t* reservations_out, uint8_t* status_out, dk_stream stream) {
     if (!ctx || !states || !rng) return DK_ERR_INVALID_ARGUMENT;
-    if (engine != DK_FDO) return fail(ctx, DK_ERR_UNSUPPORTED, "dk_determinize: DK_DOKO (rs-doko-assignment) is not built yet");
+    if (engine != DK_FDO && engine != DK_DOKO) return DK_ERR_INVALID_ARGUMENT;
     if (n_info == 0 || samples_per_info == 0) return DK_OK;
     if (samples_per_info > 0xFFFFFFFFull || n_info > 0x7FFFFFFFull) return DK_ERR_INVALID_ARGUMENT;
     DK_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (engine == DK_DOKO) {
+        dk::doko_assign_kernel<<<(unsigned)n_info, dk::MATCH_THREADS, 0, pick_stream(ctx, stream)>>>(to_params(rng), (uint64_t)n_info, (uint32_t)samples_per_info,
+                                                                                               states, hands_out, reservations_out, status_out);
+        return check_launch(ctx, "doko_assign_kernel");
+    }
     dk::fdo_determinize_kernel<<<(unsigned)n_info, dk::MATCH_THREADS, 0, pick_stream(ctx, stream)>>>(to_params(rng), (uint64_t)n_info, (uint32_t)samples_per_info,
                                                                                                    states, hands_out, reservations_out, status_out);
     return check_launch(ctx, "fdo_determinize_kernel");

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "assignment.cuh"
 #include "dk_common.cuh"
 #include "doko_rules.cuh"
 #include "encode.cuh"
@@ -312,6 +313,39 @@ fdo_determinize_kernel(RngParams rp, uint64_t n_info, uint32_t samples, const dk
             dst[1] = make_ulonglong2(h[2], h[3]);
         }
         if (res_out) reinterpret_cast<uint32_t*>(res_out)[o] = (uint32_t)r[0] | ((uint32_t)r[1] << 8) | ((uint32_t)r[2] << 16) | ((uint32_t)r[3] << 24);
+        if (status_out) status_out[o] = (uint8_t)st;
+    }
+}
+
+// K3 (rs-doko): sample_assignment (rs-doko-assignment/src/assignment.rs:493-581).  Same block = info-state / thread = sample shape.
+// reservations_out repeats the real reservations by absolute seat (the reference only replaces the hands).
+__global__ void __launch_bounds__(MATCH_THREADS)
+doko_assign_kernel(RngParams rp, uint64_t n_info, uint32_t samples, const dk_state* __restrict__ states, uint64_t* __restrict__ hands_out,
+                   uint8_t* __restrict__ res_out, uint8_t* __restrict__ status_out) {
+    __shared__ AssignPrep prep;
+    __shared__ uint32_t res_word;
+    uint64_t i = blockIdx.x;
+    if (i >= n_info) return;
+    if (threadIdx.x == 0) {
+        alignas(16) dk_state s;
+        load_state(states + i, s);
+        doko_assign_prepare(s, prep);
+        uint32_t r = 0xFFFFFFFFu, start = st_game_start(s);
+        for (uint32_t k = 0; k < s.n_reservations; ++k) { uint32_t seat = (start + k) & 3u; r = (r & ~(0xFFu << (8u * seat))) | ((uint32_t)s.reservations[k] << (8u * seat)); }
+        res_word = r;
+    }
+    __syncthreads();
+    for (uint32_t smp = threadIdx.x; smp < samples; smp += MATCH_THREADS) {
+        RngKey key = make_key(rp, i, rp.first_sub + smp, true);
+        uint64_t h[4];
+        uint32_t st = doko_assign_sample(prep, key, h);
+        uint64_t o = i * samples + smp;
+        if (hands_out) {
+            ulonglong2* dst = reinterpret_cast<ulonglong2*>(hands_out + 4 * o);
+            dst[0] = make_ulonglong2(h[0], h[1]);
+            dst[1] = make_ulonglong2(h[2], h[3]);
+        }
+        if (res_out) reinterpret_cast<uint32_t*>(res_out)[o] = res_word;
         if (status_out) status_out[o] = (uint8_t)st;
     }
 }

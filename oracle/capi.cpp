@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "../include/doko_cuda.h"
+#include "assignment.hpp"
 #include "bitflag.hpp"
 #include "doko.hpp"
 #include "encode.hpp"
@@ -437,6 +438,15 @@ ORC_API void orc_fdo_random_rollout_philox(const void* h, uint64_t seed, uint64_
     if (steps) *steps = s.n_play_actions - before;
 }
 
+// rs-doko-assignment sample_assignment_full on `h` with Philox unit (unit, sample): returns status; hands[4]
+ORC_API int orc_doko_sample_assignment_philox(const void* h, uint64_t seed, uint64_t unit, uint32_t sample, uint32_t epoch, uint64_t hands[4]) {
+    PhiloxStream r(seed, (uint32_t)unit, sample, epoch);
+    int status = 1;
+    guarded([&] { status = doko::sample_assignment_full(*(const doko::State*)h, r, hands); });
+    return status;
+}
+// are_hands_consistent is not restated; the samples are checked with the properties below instead (tests).
+
 // One leaf rollout: [card_matching → clone_with_different_hands_and_reservations →] random_rollout, all on the Philox unit (unit, rollout).
 // Returns the determinization status (0 ok).
 ORC_API int orc_fdo_leaf_rollout_philox(const void* h, uint64_t seed, uint64_t unit, uint32_t rollout, uint32_t epoch, int determinize,
@@ -530,3 +540,21 @@ ORC_API double orc_playout_philox(int engine, int with_announcements, uint64_t s
     return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 ORC_API int orc_hardware_threads() { return (int)std::thread::hardware_concurrency(); }
+
+// ---- raw FdoAnnouncements object for the protocol step tests (announcement.rs:228-573) ---------------------------------------
+ORC_API void* orc_ann_new() { return new fdo::Announcements(); }
+ORC_API void orc_ann_free(void* a) { delete (fdo::Announcements*)a; }
+// op 0 = start_round(card_index, player, ...), op 1 = play_announcement(player, ann bit, card_index, ...)
+// out = [result kind (0 NextPlayerIs, 1 RoundIsOver), result player, n calls, starting_player, turns, re_lowest bit, contra_lowest bit, allowed set,
+//        call[k] = player | card_index<<8 | ann<<16 ...]
+ORC_API int orc_ann_step(void* a, int op, int player, int ann, int card_index, const uint32_t lens[4], int tag, int wedding_player, int solved_idx,
+                         uint32_t re_players, int32_t* out) {
+    fdo::Announcements& A = *(fdo::Announcements*)a;
+    fdo::TeamState ts; ts.tag = tag; ts.wedding_player = wedding_player; ts.solved_trick_index = solved_idx; ts.re_players = re_players;
+    return guarded([&] {
+        fdo::ProgressResult r = op == 0 ? A.start_round(card_index, player, lens, ts) : A.play_announcement(player, ann, card_index, lens, ts);
+        out[0] = r.kind == fdo::ROUND_IS_OVER; out[1] = r.player; out[2] = A.n; out[3] = A.starting_player; out[4] = A.turns_without;
+        out[5] = A.re_lowest; out[6] = A.contra_lowest; out[7] = (int)A.current_allowed;
+        for (int k = 0; k < A.n; ++k) out[8 + k] = A.occ[k].player | (A.occ[k].card_index << 8) | (A.occ[k].announcement << 16);
+    });
+}

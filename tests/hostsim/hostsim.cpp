@@ -13,6 +13,7 @@
 #include "../../master_doko_reinforcement_learning_b200/csrc/state_ops.cuh"
 #include "../../master_doko_reinforcement_learning_b200/csrc/encode.cuh"
 #include "../../master_doko_reinforcement_learning_b200/csrc/matching.cuh"
+#include "../../master_doko_reinforcement_learning_b200/csrc/assignment.cuh"
 
 #define SIM_API extern "C" __attribute__((visibility("default")))
 
@@ -118,4 +119,10 @@ SIM_API uint32_t sim_fdo_leaf_rollout(const dk_state* s, uint64_t seed, uint64_t
     dk::fdo_play_to_end<false, false>(g, key, &rs, card_lut());
     dk::fdo_final_points(g, points); *steps = g.steps;
     return 0;
+}
+
+SIM_API uint32_t sim_doko_assign(const dk_state* s, uint64_t seed, uint64_t unit, uint32_t sample, uint32_t epoch, uint64_t hands[4]) {
+    dk::AssignPrep prep; dk::doko_assign_prepare(*s, prep);
+    dk::RngKey key = make_key(seed, unit, epoch); key.unit_hi = sample;
+    return dk::doko_assign_sample(prep, key, hands);
 }

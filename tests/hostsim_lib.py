@@ -28,6 +28,8 @@ def load():
         L.sim_doko_playout_fresh.argtypes = [u64, u32, u64, u64, vp, vp, vp, vp]
         L.sim_fdo_determinize.restype = u32
         L.sim_fdo_determinize.argtypes = [vp, u64, u64, u32, u32, vp, vp]
+        L.sim_doko_assign.restype = u32
+        L.sim_doko_assign.argtypes = [vp, u64, u64, u32, u32, vp]
         L.sim_fdo_leaf_rollout.restype = u32
         L.sim_fdo_leaf_rollout.argtypes = [vp, u64, u64, u32, u32, i32, vp, vp]
         L.sim_fdo_score.restype = i32

@@ -106,6 +106,7 @@ def load():
     L.orc_doko_encode.argtypes = [vp, i32, vp]
     L.orc_fdo_random_step_philox.argtypes = [vp, u64, u64, u32, i32, u32]
     L.orc_fdo_step_site.argtypes = [vp, u64, u64, u32, i32, i32]
+    L.orc_doko_sample_assignment_philox.argtypes = [vp, u64, u64, u32, u32, vp]
     L.orc_fdo_leaf_rollout_philox.argtypes = [vp, u64, u64, u32, u32, i32, vp, vp]
     L.orc_doko_random_step_philox.argtypes = [vp, u64, u64, u32]
     L.orc_fdo_hand_plus.restype = u64
@@ -300,6 +301,11 @@ class Doko:
 
     def random_step(self, seed, unit, epoch=0):
         return self.L.orc_doko_random_step_philox(self.h, seed, unit, epoch)
+
+    def sample_assignment(self, seed, unit, sample, epoch=0):
+        hands = (C.c_uint64 * 4)()
+        st = self.L.orc_doko_sample_assignment_philox(self.h, seed, unit, sample, epoch, hands)
+        return st, [int(x) for x in hands]
 
 
 def playout_philox(L, engine, n, seed, first_id=0, epoch=0, with_announcements=True, n_threads=0, want_aux=False, trace_stride=0):

@@ -90,3 +90,34 @@ def test_leaf_rollouts_sum_matches_oracle(dk, orc, determinize):
             if st == 0:
                 exp += np.array(pts)
         assert np.array_equal(sums[i], exp), f"leaf {i}"
+
+
+def test_doko_assignment_matches_oracle(dk, orc):
+    """rs-doko-assignment on the GPU (config 3, simplified engine) == the Vec-based oracle restatement."""
+    import torch
+
+    from oracle_lib import Doko
+
+    prng = np.random.default_rng(17)
+    objs = []
+    for i in range(64):
+        o = Doko.new_game_philox(orc, SEED, 300 + i, 0)
+        target = 4 + (8, 16, 24, 32)[i % 4]
+        n = 0
+        while o.allowed() and n < target:
+            m = o.allowed()
+            legal = [a for a in range(26) if (m >> a) & 1]
+            a = int(prng.choice(legal))
+            if i % 2 == 0 and (m >> 25) & 1:
+                a = 25
+            o.play(a)
+            n += 1
+        objs.append(o)
+    S = 48
+    hands, res, status = dk.determinize(0, to_dev(objs), S, dk.rng(SEED, 5000, 6))
+    torch.cuda.synchronize()
+    hands, status = hands.cpu().numpy().astype(np.uint64), status.cpu().numpy()
+    for i, o in enumerate(objs):
+        for s in range(S):
+            st_o, h_o = o.sample_assignment(SEED, 5000 + i, s, 6)
+            assert (int(status[i, s]), [int(x) for x in hands[i, s]]) == (st_o, h_o), f"state {i} sample {s}"
