@@ -48,10 +48,14 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.gpu)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(self.gpu)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
+            # nvidia-smi's start-up takes driver locks that stall kernel launches for ~0.2 s: wait until it is in its sampling loop
+            t0 = time.time()
+            while len(self.lines) < 2 and time.time() - t0 < 5.0:
+                time.sleep(0.05)
         except Exception:
             self.proc = None
 

@@ -55,6 +55,14 @@ DK_HD uint32_t ffs0ll(uint64_t x) {
 #endif
 }
 
+DK_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) {  // low 32 bits of (hi:lo) >> sh, sh < 32
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(lo, hi, sh);
+#else
+    return (uint32_t)((((uint64_t)hi << 32) | lo) >> sh);
+#endif
+}
+
 // ---- Philox4x32-10 ----------------------------------------------------------------------------------
 // Parity stream shared with the oracle (DESIGN.md "Philox parity contract"):
 //   counter = (unit_lo, unit_hi, site<<16 | block, epoch), key = (seed_lo, seed_hi);

@@ -223,6 +223,28 @@ DK_HD uint32_t fdo_pick_reservation(uint32_t h, uint32_t dup, uint32_t word) {
 // BIT each: decision k of the call is bit (k & 31) of word (k >> 5) of the SITE_ANNOUNCEMENT stream.  Block 0 (128 decisions; the
 // longest game seen in 2x10^5 has 47) is computed in lock-step by all lanes before the data-dependent replay loop, so the loop
 // contains no Philox code; later blocks are fetched on demand.
+struct AnnStream { U4 w; uint32_t blk; };
+// `m` (<= 4) consecutive decision bits starting at decision `ord` (bit k of the stream = bit (k & 31) of word (k >> 5)).
+DK_HD uint32_t fdo_ann_bits(AnnStream& st, const RngKey& key, uint32_t ord, uint32_t m) {
+    if (((ord + 3u) >> 7) == (ord >> 7)) {                        // the window lies in one 128-bit block (always, in practice)
+        if ((ord >> 7) != st.blk) { st.blk = ord >> 7; st.w = rng_block(key, SITE_ANNOUNCEMENT, st.blk); }
+        uint32_t wi = (ord >> 5) & 3u;
+        uint32_t lo = u4_word(st.w, wi), hi = u4_word(st.w, (wi + 1u) & 3u);   // hi is only used when the window stays inside the block
+        return funnel_r(lo, hi, ord & 31u) & ((1u << m) - 1u);
+    }
+    uint32_t r = 0;                                               // window straddles two blocks: bit by bit
+    for (uint32_t i = 0; i < m; ++i) {
+        uint32_t k = ord + i;
+        if ((k >> 7) != st.blk) { st.blk = k >> 7; st.w = rng_block(key, SITE_ANNOUNCEMENT, st.blk); }
+        r |= ((u4_word(st.w, (k >> 5) & 3u) >> (k & 31u)) & 1u) << i;
+    }
+    return r;
+}
+
+// The loop advances by SEGMENTS: from (seat p, `turns` consecutive no's) the next 4 - turns seats are visited unless somebody
+// calls; the eligible ones among them each consume one decision bit.  All-zero bits → the round is over (advance to the next
+// card); otherwise the first set bit is a call, which changes the levels and restarts the count.  Iterations per lane =
+// #calls + #rounds (about 16) instead of #asks + #rounds (about 26), and there is no Philox code inside the loop.
 template <bool WITH_ANN>
 DK_HD void fdo_replay_announcements(FdoLive& g, const RngKey& key, uint32_t starts, uint32_t ci, uint32_t p, uint32_t turns) {
     const bool wedding = g.team_tag == TEAM_WEDDING_SOLVED;       // (an unsolved wedding cannot survive trick 2)
@@ -235,11 +257,10 @@ DK_HD void fdo_replay_announcements(FdoLive& g, const RngKey& key, uint32_t star
     }
     if (ci >= 48u) return;
     const uint32_t re = g.re_mask & 15u;
-    uint32_t re_low = g.re_low, ko_low = g.ko_low, steps = 0, ord = g.ann_count;
+    uint32_t re_low = g.re_low, ko_low = g.ko_low, ord = g.ann_count;
     uint32_t thr_re = fdo_min_cards_to_call(re_low, ko_low, w), thr_ko = fdo_min_cards_to_call(ko_low, re_low, w);
-    U4 bits; bits.x = bits.y = bits.z = bits.w = 0;
-    uint32_t bits_blk = 0;
-    if (WITH_ANN) bits = rng_block(key, SITE_ANNOUNCEMENT, 0);
+    AnnStream st; st.blk = 0; st.w.x = st.w.y = st.w.z = st.w.w = 0;
+    if (WITH_ANN) st.w = rng_block(key, SITE_ANNOUNCEMENT, 0);     // lock-step: every lane fetches block 0 before the loop
     // per-position values (recomputed when ci advances)
     uint32_t cmax = 12u - (ci >> 2);
     uint32_t base = (starts >> (2u * (ci >> 2))) & 3u;
@@ -249,9 +270,12 @@ DK_HD void fdo_replay_announcements(FdoLive& g, const RngKey& key, uint32_t star
         uint32_t e_re = cmax >= thr_re ? (cmax - 1u >= thr_re ? 15u : (~played & 15u)) : 0u;
         uint32_t e_ko = cmax >= thr_ko ? (cmax - 1u >= thr_ko ? 15u : (~played & 15u)) : 0u;
         uint32_t elig = (e_re & re) | (e_ko & ~re & 15u);
-        uint32_t rot = ((elig | (elig << 4)) >> p) & 15u;
-        uint32_t d = rot ? ffs0(rot) : 4u;                        // seats auto-skipped before the next eligible one
-        if (turns + d >= 4u) {                                    // RoundIsOver → card ci is played; next round
+        uint32_t rot = ((elig | (elig << 4)) >> p) & 15u;         // bit d: seat p + d is eligible
+        uint32_t win = rot & ((1u << (4u - turns)) - 1u);         // the seats visited before the count reaches 4
+        uint32_t m = popc(win);
+        uint32_t hit = (WITH_ANN && m) ? fdo_ann_bits(st, key, ord, m) : 0u;
+        if (hit == 0u) {                                          // everybody passes: RoundIsOver → card ci is played; next round
+            ord += m;
             ci++;
             if (ci >= 48u) break;
             cmax = 12u - (ci >> 2);
@@ -261,27 +285,21 @@ DK_HD void fdo_replay_announcements(FdoLive& g, const RngKey& key, uint32_t star
             turns = 0;
             continue;
         }
-        p = (p + d) & 3u; turns += d;
+        uint32_t j = ffs0(hit);                                   // j eligible seats pass, the (j+1)-th calls
+        ord += j + 1u;
+        uint32_t d = select_lsb(win, j);                          // its distance from p
+        p = (p + d) & 3u;
         uint32_t is_re = (re >> p) & 1u;
         uint32_t c = cmax - ((played >> p) & 1u);
-        uint32_t m = is_re ? re_low : ko_low;
-        uint32_t ml = m == 6u ? 0u : m;
-        uint32_t call = (ml < 5u && c + ml + w >= 11u) ? ml + 1u : 1u;   // the seat is eligible: next level, else the counter (→ Re/Kontra)
-        steps++;
-        bool says = false;
-        if (WITH_ANN) {                                           // allowed = {call, NoAnnouncement}: MSB rank 0 = NoAnnouncement
-            if ((ord >> 7) != bits_blk) { bits_blk = ord >> 7; bits = rng_block(key, SITE_ANNOUNCEMENT, bits_blk); }
-            says = (u4_word(bits, (ord >> 5) & 3u) >> (ord & 31u)) & 1u;
-        }
-        ord++;
-        if (says) {                                               // announcement.rs:203-210
-            if (is_re) re_low = call; else ko_low = call;
-            turns = 0;
-            thr_re = fdo_min_cards_to_call(re_low, ko_low, w); thr_ko = fdo_min_cards_to_call(ko_low, re_low, w);
-        } else turns++;
+        uint32_t ml = is_re ? re_low : ko_low;
+        ml = ml == 6u ? 0u : ml;
+        uint32_t call = (ml < 5u && c + ml + w >= 11u) ? ml + 1u : 1u;   // next level, else the counter (recorded as Re/Kontra)
+        if (is_re) re_low = call; else ko_low = call;             // announcement.rs:203-210
+        thr_re = fdo_min_cards_to_call(re_low, ko_low, w); thr_ko = fdo_min_cards_to_call(ko_low, re_low, w);
+        turns = 0;
         p = (p + 1u) & 3u;
     }
-    g.re_low = re_low; g.ko_low = ko_low; g.steps += steps; g.ann_count = ord;
+    g.re_low = re_low; g.ko_low = ko_low; g.steps += ord - g.ann_count; g.ann_count = ord;
 }
 
 struct TrickAcc { uint32_t follow, best, bestk, bestc, teyes, foxm; };

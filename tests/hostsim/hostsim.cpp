@@ -126,3 +126,9 @@ SIM_API uint32_t sim_doko_assign(const dk_state* s, uint64_t seed, uint64_t unit
     dk::RngKey key = make_key(seed, unit, epoch); key.unit_hi = sample;
     return dk::doko_assign_sample(prep, key, hands);
 }
+
+SIM_API uint32_t sim_fdo_ann_bits(uint64_t seed, uint64_t unit, uint32_t epoch, uint32_t ord, uint32_t m) {
+    dk::RngKey key = make_key(seed, unit, epoch);
+    dk::AnnStream st; st.blk = 0; st.w = dk::rng_block(key, dk::SITE_ANNOUNCEMENT, 0);
+    return dk::fdo_ann_bits(st, key, ord, m);
+}

@@ -41,3 +41,17 @@ def test_smallrng_stale_vectors_are_documented(orc):
     # ... while the SAME shuffle reproduces the rs-full-doko vector (hand.rs:559-585), because both crates share the deal code path
     assert [int(h) for h in hands] == [0b0000000010000000000000110100100110000110110001, 0b0001000000100001000000000001010101100001100101,
                                        0b1000000000000000001000011110110000000000011110, 0b0000001000011000000000100010001001011110000010]
+
+
+def test_announcement_bit_stream_window(orc):
+    """Device window extraction (incl. windows that straddle a 128-decision Philox block, which real games never reach) ==
+    bit k of the stream = bit (k & 31) of word (k >> 5)."""
+    sim = hostsim_lib.load()
+    sim.sim_fdo_ann_bits.restype = C.c_uint32
+    sim.sim_fdo_ann_bits.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32]
+    seed, unit, epoch = 0xABCDEF0123, 4242, 3
+    bit = lambda k: (orc.orc_philox_word(seed, unit, 0, epoch, 2, k >> 5) >> (k & 31)) & 1
+    for ord_ in list(range(0, 140)) + [250, 253, 254, 255, 256, 381, 383]:
+        for m in (1, 2, 3, 4):
+            exp = sum(bit(ord_ + i) << i for i in range(m))
+            assert sim.sim_fdo_ann_bits(seed, unit, epoch, ord_, m) == exp, (ord_, m)
