@@ -558,3 +558,19 @@ ORC_API int orc_ann_step(void* a, int op, int player, int ann, int card_index, c
         for (int k = 0; k < A.n; ++k) out[8 + k] = A.occ[k].player | (A.occ[k].card_index << 8) | (A.occ[k].announcement << 16);
     });
 }
+
+// sample_assignment on raw inputs (the form of the reference's own tests, assignment.rs:908-1186):
+// tricks[t*5 + {0..3 cards (-1 = none), 4 start}] for t < n_tricks.
+ORC_API int orc_doko_sample_assignment_raw(int marriage, int n_tricks, const int32_t* tricks, uint64_t own_hand, const uint32_t lens[4], int observer,
+                                           uint64_t seed, uint64_t unit, uint32_t sample, uint32_t epoch, uint64_t hands[4]) {
+    doko::Trick ts[12];
+    for (int t = 0; t < n_tricks; ++t) {
+        ts[t].present = true; ts[t].start_player = (int8_t)tricks[t * 5 + 4];
+        for (int k = 0; k < 4; ++k) if (tricks[t * 5 + k] >= 0) ts[t].play_card(tricks[t * 5 + k]);
+    }
+    size_t l[4] = {lens[0], lens[1], lens[2], lens[3]};
+    PhiloxStream r(seed, (uint32_t)unit, sample, epoch);
+    int status = 1;
+    guarded([&] { status = doko::sample_assignment(marriage, ts, own_hand, l, observer, r, hands); });
+    return status;
+}

@@ -121,3 +121,19 @@ def test_doko_assignment_matches_oracle(dk, orc):
         for s in range(S):
             st_o, h_o = o.sample_assignment(SEED, 5000 + i, s, 6)
             assert (int(status[i, s]), [int(x) for x in hands[i, s]]) == (st_o, h_o), f"state {i} sample {s}"
+
+
+def test_doko_assignment_support_sets_on_gpu(dk):
+    """The reference's own rs-doko-assignment tests on the kernel: 1000 samples → exactly the enumerated 9 / 12 assignments."""
+    import torch
+
+    from assignment_cases import CASES, canonical, case_record, expected_set
+
+    for case in CASES:
+        rec = case_record(case)
+        st = torch.from_numpy(np.frombuffer(rec.tobytes(), dtype=np.uint8).reshape(1, 128).copy()).cuda()
+        hands, _, status = dk.determinize(0, st, 1000, dk.rng(42, 0, 0))
+        torch.cuda.synchronize()
+        assert int(status.max()) == 0
+        seen = {canonical([int(x) for x in h]) for h in hands[0].cpu().numpy().astype(np.uint64)}
+        assert len(seen) == case["n_unique"] and expected_set(case) <= seen
