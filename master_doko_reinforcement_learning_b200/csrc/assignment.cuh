@@ -92,13 +92,17 @@ DK_HD uint32_t doko_assign_sample(const AssignPrep& p, const RngKey& key, uint64
     U4 blk; blk.x = blk.y = blk.z = blk.w = 0;
     uint32_t blk_id = 0xFFFFFFFFu, ord = 0, status = 0;
     for (;;) {
-        // distribute_single_cards (:336-377): first remaining card (ascending id) with exactly one eligible seat
+        // distribute_single_cards (:336-377): first remaining card (ascending id) with exactly one eligible seat — bit-parallel:
+        // "exactly one of four" = odd parity minus the triples
         bool did = false;
-        uint32_t bits = a.remaining.a;
-        while (bits) {
-            uint32_t c = ffs0(bits); bits &= bits - 1u;
-            uint32_t e = doko_assign_eligible(a, 1u << c);
-            if (e && !(e & (e - 1u))) { doko_assign_distribute(a, ffs0(e), c); did = true; break; }
+        {
+            uint32_t e0 = a.len[0] ? a.allowed[0].a : 0u, e1 = a.len[1] ? a.allowed[1].a : 0u, e2 = a.len[2] ? a.allowed[2].a : 0u, e3 = a.len[3] ? a.allowed[3].a : 0u;
+            uint32_t one = (e0 ^ e1 ^ e2 ^ e3) & ~((e0 & e1 & e2) | (e0 & e1 & e3) | (e0 & e2 & e3) | (e1 & e2 & e3)) & a.remaining.a;
+            if (one) {
+                uint32_t c = ffs0(one), bit = 1u << c;
+                doko_assign_distribute(a, (e0 & bit) ? 0u : ((e1 & bit) ? 1u : ((e2 & bit) ? 2u : 3u)), c);
+                did = true;
+            }
         }
         if (did) continue;
         // distribute_exactly_as_per_hand (:379-417)

@@ -110,16 +110,25 @@ DK_HD void fdo_match_assign(MatchState& m, uint32_t j, uint32_t c) {
     if (c == CARD_CQ) m.must_q &= ~(1u << j);
 }
 // rule 1 (:78-113): walk a SNAPSHOT of the available cards (copy-A bits ascending, then copy-B bits) and hand every card that
-// exactly one hidden seat can hold to that seat.
+// exactly one hidden seat can hold to that seat.  The seats' possible sets only change when a card is assigned, so between two
+// assignments the "exactly one owner" mask is constant: instead of visiting every card, jump to the next snapshot card whose bit is
+// set in that mask (bit-parallel, exact).
+DK_HD uint32_t fdo_match_single_owner_mask(const MatchState& m) {
+    uint32_t p0 = m.possible[0].a, p1 = m.possible[1].a, p2 = m.possible[2].a;
+    return (p0 ^ p1 ^ p2) & ~(p0 & p1 & p2);                  // odd parity minus "all three" = exactly one
+}
 DK_HD void fdo_match_rule1(MatchState& m) {
     uint32_t snap[2] = {m.avail.a, m.avail.b};
+#pragma unroll
     for (uint32_t plane = 0; plane < 2u; ++plane) {
-        uint32_t bits = snap[plane];
-        while (bits) {
-            uint32_t c = ffs0(bits), bit = 1u << c;
-            bits &= bits - 1u;
-            uint32_t h0 = (m.possible[0].a & bit) ? 1u : 0u, h1 = (m.possible[1].a & bit) ? 1u : 0u, h2 = (m.possible[2].a & bit) ? 1u : 0u;
-            if (h0 + h1 + h2 == 1u) fdo_match_assign(m, h0 ? 0u : (h1 ? 1u : 2u), c);
+        uint32_t todo = snap[plane];
+        for (;;) {
+            uint32_t cand = todo & fdo_match_single_owner_mask(m);
+            if (cand == 0u) break;
+            uint32_t c = ffs0(cand), bit = 1u << c;
+            todo &= ~(bit | (bit - 1u));                          // everything up to and including c has been visited
+            uint32_t j = (m.possible[0].a & bit) ? 0u : ((m.possible[1].a & bit) ? 1u : 2u);
+            fdo_match_assign(m, j, c);
         }
     }
 }
