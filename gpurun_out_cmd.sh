@@ -1,4 +1,4 @@
 set -x
 mkdir -p gpurun_out
-python -m pytest tests -x -q -m gpu 2>&1 | tail -6
-python profiles/bench_kernels.py > gpurun_out/kernels3.json 2> gpurun_out/kernels3.err; tail -2 gpurun_out/kernels3.err; cat gpurun_out/kernels3.json
+python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; tail -3 gpurun_out/pytest_gpu.log
+python profiles/bench_kernels.py > gpurun_out/kernels_v4.json 2> gpurun_out/kernels_v4.err; tail -c 1500 gpurun_out/kernels_v4.json

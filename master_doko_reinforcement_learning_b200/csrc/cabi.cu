@@ -224,7 +224,7 @@ dk_status dk_encode(dk_ctx* ctx, int layout, size_t n, const dk_state* states, i
     DK_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t s = pick_stream(ctx, stream);
     unsigned grid = (unsigned)((n + dk::ENC_THREADS - 1) / dk::ENC_THREADS);
-    if (layout == DK_LAYOUT_FDO_PI311) dk::encode_kernel<DK_LAYOUT_FDO_PI311><<<grid, dk::ENC_THREADS, 0, s>>>((uint64_t)n, states, out, row_stride);
+    if (layout == DK_LAYOUT_FDO_PI311) dk::encode_pi_kernel<<<grid, dk::ENC_THREADS, 0, s>>>((uint64_t)n, states, out, row_stride);
     else if (layout == DK_LAYOUT_DO114) dk::encode_kernel<DK_LAYOUT_DO114><<<grid, dk::ENC_THREADS, 0, s>>>((uint64_t)n, states, out, row_stride);
     else dk::encode_kernel<DK_LAYOUT_DO110><<<grid, dk::ENC_THREADS, 0, s>>>((uint64_t)n, states, out, row_stride);
     return check_launch(ctx, "encode_kernel");

@@ -27,13 +27,14 @@ DK_HD uint32_t fdo_card_token(uint32_t c) {
 
 // encode_state_pi (rs-doko-networks/src/full_doko/var1/encode_pi.rs:27-216) with obs = observation_for_current_player():
 // 62 slots x 5 channels (token, position, player, sub-position, team) + phase = 311 values.
-// out(i, v) receives value v for row element i (0..310).
+// The sink receives out.slot(n, token, position, player, sub-position, team) for the 62 slots and out.phase(v); row element
+// indices are n, 62+n, 124+n, 186+n, 248+n and 310.
 template <class Out>
 DK_HD void fdo_encode_pi(const dk_state& s, Out& out) {
     const uint32_t cur = st_phase(s) == DK_PHASE_FINISHED ? 0u : st_cur(s);   // current_player.unwrap_or(BOTTOM) (:31-33)
     uint32_t n = 0;
     auto push = [&](uint32_t tok, uint32_t pos, uint32_t ply, uint32_t sub, uint32_t team) {
-        out(n, tok); out(62u + n, pos); out(124u + n, ply); out(186u + n, sub); out(248u + n, team);
+        out.slot(n, tok, pos, ply, sub, team);
         n++;
     };
     const uint32_t start = st_game_start(s);
@@ -65,7 +66,7 @@ DK_HD void fdo_encode_pi(const dk_state& s, Out& out) {
         sub++;
     }
     for (uint32_t a = n_calls; a < 10u; ++a) push(37u, 0u, 0u, 0u, 0u);         // (:167-179)
-    out(310u, st_phase(s));                                                   // encode_phase (var1/phase.rs:9-18)
+    out.phase(st_phase(s));                                                   // encode_phase (var1/phase.rs:9-18)
 }
 
 // encode_state / encode_state_with_reservations (rs-doko-embeddings/src/encode_state.rs:84-317): 110 / 114 values.

@@ -189,7 +189,7 @@ terminal_kernel(uint64_t n, const dk_state* __restrict__ states, uint8_t* __rest
 // Token values are staged as bytes in shared memory (one padded row per game, odd word pitch → conflict-free when the 32
 // lanes of a warp write the same column), then every warp widens whole rows to i64 with 256-byte-contiguous stores.
 constexpr int ENC_THREADS = 128;
-constexpr int ENC_ROW = 316;   // bytes; 79 words (odd)
+constexpr int ENC_ROW = 116;   // bytes; 29 words (odd) — rs-doko layouts (110 / 114 values)
 struct SmemRowOut {
     uint8_t* row;
     __device__ __forceinline__ void operator()(uint32_t i, uint32_t v) const { row[i] = (uint8_t)v; }
@@ -204,6 +204,52 @@ __device__ __forceinline__ void write_rows(const uint8_t* __restrict__ tok, int 
         for (int i = lane; i < len; i += 32) dst[i] = (int64_t)src[i];
     }
 }
+// encode_state_pi staging: one packed word per slot (token 6 b | position 6 b | player 3 b | sub-position 4 b | team 2 b) plus the phase;
+// 63 words per game (odd pitch → conflict-free), then each warp expands whole rows channel by channel: every store instruction writes
+// 32 (resp. 30) consecutive i64 = 256 contiguous bytes.
+constexpr int PI_ROW = 63;
+struct SmemSlotOut {
+    uint32_t* row;
+    __device__ __forceinline__ void slot(uint32_t n, uint32_t tok, uint32_t pos, uint32_t ply, uint32_t sub, uint32_t team) const {
+        row[n] = tok | (pos << 6) | (ply << 12) | (sub << 15) | (team << 19);
+    }
+    __device__ __forceinline__ void phase(uint32_t v) const { row[62] = v; }
+};
+__device__ __forceinline__ void write_rows_pi(const uint32_t* __restrict__ tok, uint64_t first, uint64_t n, int64_t* __restrict__ out, size_t row_stride) {
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int r = warp; r < ENC_THREADS; r += ENC_THREADS / 32) {
+        uint64_t g = first + r;
+        if (g >= n) break;
+        const uint32_t* src = tok + r * PI_ROW;
+        int64_t* dst = out + g * row_stride;
+        uint32_t w0 = src[lane], w1 = lane < 30 ? src[32 + lane] : 0u;
+#define DK_PI_CH(CH, SH, MASK)                                                    \
+        dst[(CH) * 62 + lane] = (int64_t)((w0 >> (SH)) & (MASK));                     \
+        if (lane < 30) dst[(CH) * 62 + 32 + lane] = (int64_t)((w1 >> (SH)) & (MASK));
+        DK_PI_CH(0, 0, 63u)
+        DK_PI_CH(1, 6, 63u)
+        DK_PI_CH(2, 12, 7u)
+        DK_PI_CH(3, 15, 15u)
+        DK_PI_CH(4, 19, 3u)
+#undef DK_PI_CH
+        if (lane == 0) dst[310] = (int64_t)src[62];
+    }
+}
+__global__ void __launch_bounds__(ENC_THREADS)
+encode_pi_kernel(uint64_t n, const dk_state* __restrict__ states, int64_t* __restrict__ out, size_t row_stride) {
+    __shared__ uint32_t tok[ENC_THREADS * PI_ROW];
+    uint64_t first = (uint64_t)blockIdx.x * ENC_THREADS;
+    uint64_t i = first + threadIdx.x;
+    if (i < n) {
+        alignas(16) dk_state s;
+        load_state(states + i, s);
+        SmemSlotOut o{tok + threadIdx.x * PI_ROW};
+        fdo_encode_pi(s, o);
+    }
+    __syncthreads();
+    write_rows_pi(tok, first, n, out, row_stride);
+}
+
 template <int LAYOUT>
 __global__ void __launch_bounds__(ENC_THREADS)
 encode_kernel(uint64_t n, const dk_state* __restrict__ states, int64_t* __restrict__ out, size_t row_stride) {
@@ -214,10 +260,10 @@ encode_kernel(uint64_t n, const dk_state* __restrict__ states, int64_t* __restri
         alignas(16) dk_state s;
         load_state(states + i, s);
         SmemRowOut o{tok + threadIdx.x * ENC_ROW};
-        if (LAYOUT == DK_LAYOUT_FDO_PI311) fdo_encode_pi(s, o); else doko_encode(s, LAYOUT == DK_LAYOUT_DO114, o);
+        doko_encode(s, LAYOUT == DK_LAYOUT_DO114, o);
     }
     __syncthreads();
-    write_rows(tok, LAYOUT == DK_LAYOUT_FDO_PI311 ? 311 : (LAYOUT == DK_LAYOUT_DO114 ? 114 : 110), first, n, out, row_stride);
+    write_rows(tok, LAYOUT == DK_LAYOUT_DO114 ? 114 : 110, first, n, out, row_stride);
 }
 
 // The reference's random pick on a 39-bit mask: index from the most significant set bit (bit_flag.rs:86-94,104-171).
@@ -232,7 +278,7 @@ __device__ __forceinline__ uint32_t pick_msb_rank64(uint64_t mask, uint32_t idx)
 __global__ void __launch_bounds__(ENC_THREADS)
 fdo_step_encode_kernel(RngParams rp, uint64_t n, dk_state* __restrict__ states, uint32_t flags, int64_t* __restrict__ obs, size_t row_stride,
                        uint8_t* __restrict__ action_out) {
-    __shared__ __align__(16) uint8_t tok[ENC_THREADS * ENC_ROW];
+    __shared__ uint32_t tok[ENC_THREADS * PI_ROW];
     uint64_t first = (uint64_t)blockIdx.x * ENC_THREADS;
     uint64_t i = first + threadIdx.x;
     if (i < n) {
@@ -249,10 +295,10 @@ fdo_step_encode_kernel(RngParams rp, uint64_t n, dk_state* __restrict__ states, 
             store_state(states + i, s);
         }
         if (action_out) action_out[i] = (uint8_t)a;
-        if (obs) { SmemRowOut o{tok + threadIdx.x * ENC_ROW}; fdo_encode_pi(s, o); }
+        if (obs) { SmemSlotOut o{tok + threadIdx.x * PI_ROW}; fdo_encode_pi(s, o); }
     }
     __syncthreads();
-    if (obs) write_rows(tok, 311, first, n, obs, row_stride);
+    if (obs) write_rows_pi(tok, first, n, obs, row_stride);
 }
 
 // K2/K4 from stored states: McEnvState::random_rollout (rs-doko-mcts/src/env/envs/env_state_full_doko.rs:198-220) and the

@@ -73,7 +73,14 @@ SIM_API uint64_t sim_legal_mask(int engine, const dk_state* s) { return engine =
 SIM_API uint32_t sim_apply(int engine, dk_state* s, uint32_t action, uint32_t flags) {
     return engine == DK_FDO ? dk::fdo_state_apply_az(*s, action, (flags & DK_APPLY_SKIP_SINGLE) != 0) : dk::doko_state_apply(*s, action);
 }
-namespace { struct RowOut { int64_t* row; void operator()(uint32_t i, uint32_t v) { row[i] = (int64_t)v; } }; }
+namespace { struct RowOut {
+    int64_t* row;
+    void operator()(uint32_t i, uint32_t v) { row[i] = (int64_t)v; }
+    void slot(uint32_t n, uint32_t tok, uint32_t pos, uint32_t ply, uint32_t sub, uint32_t team) {
+        row[n] = tok; row[62 + n] = pos; row[124 + n] = ply; row[186 + n] = sub; row[248 + n] = team;
+    }
+    void phase(uint32_t v) { row[310] = v; }
+}; }
 SIM_API void sim_encode(int layout, const dk_state* s, int64_t* out) {
     RowOut o{out};
     if (layout == DK_LAYOUT_FDO_PI311) dk::fdo_encode_pi(*s, o); else dk::doko_encode(*s, layout == DK_LAYOUT_DO114, o);

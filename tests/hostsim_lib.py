@@ -15,7 +15,9 @@ def load():
     global _lib
     if _lib is None:
         subprocess.check_call(["make", "-s", "-C", DIR])
-        L = C.CDLL(LIB)
+        # DK_HOSTSIM_LIB: swap in an instrumented build (make -C tests/hostsim asan; run with LD_PRELOAD=libasan) — the
+        # bounds/UB check of the per-thread kernel logic on this pool, where compute-sanitizer is not available.
+        L = C.CDLL(os.environ.get("DK_HOSTSIM_LIB", LIB))
         vp, u64, u32, i32 = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int
         L.sim_legal_mask.restype = u64
         L.sim_legal_mask.argtypes = [i32, vp]
