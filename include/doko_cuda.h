@@ -237,6 +237,51 @@ DK_API dk_status dk_leaf_rollouts(dk_ctx* ctx, size_t n_leaves, size_t rollouts_
                            const dk_state* states /*[dev]*/, const dk_rng* rng, int64_t* point_sum_out /*[dev] n_leaves*4*/,
                            dk_stream stream);
 
+/* ---- PIMC move decision ------------------------------------------------------------------
+ * DefaultImpiPolicy::execute (rs-doko-py-bridge/src/compare_impi/compare_impi.rs:212-372): num_samples determinizations of the
+ * info-state (CAPSampling = card_matching, :64-83), a per-sample policy that returns visit counts per action, and a PolicyFusionFn.
+ *
+ * dk_pimc_evaluate fills the per-sample policy slot (EvFullDokoPolicy::evaluate, rs-doko-evaluator/src/full_doko/policy/policy.rs:22-29)
+ * with a flat Monte-Carlo search (new design; the reference plugs a UCT search in there): for root i, determinization d
+ * (stream (first_id + i, first_sub + d) — exactly dk_determinize's sample) and rollout r, EVERY legal action a of the seat to move is
+ * played on the determinized state and followed by a _no_announcement random_rollout on the stream
+ * (first_id + i, (first_sub + d) * n_rollouts + r), the same for all actions (common random numbers);
+ *   value_sum_out[(i*n_det + d)*39 + a] = sum over r of player_points[mover]   (exact integer),
+ *   visits_out   [(i*n_det + d)*39 + a] = number of rollouts r in which a had the strictly greatest value (first in action order
+ *                                         among equals) — each successful row sums to n_rollouts, like the visit counts of a search,
+ *   status_out   [i*n_det + d] != 0 for a determinization dead end (a failed sample: ForwardPredResult::NotConsistent; row = 0).
+ * A finished root yields zero rows with status 0. */
+#define DK_N_ACTIONS 39u    /* FdoAction::COUNT (rs-full-doko/src/action/action.rs:13-54) */
+#define DK_ACTION_NONE 0xFFu
+DK_API dk_status dk_pimc_evaluate(dk_ctx* ctx, size_t n_roots, size_t n_det, size_t n_rollouts, const dk_state* states /*[dev]*/,
+                                  const dk_rng* rng, uint32_t* visits_out /*[dev] or NULL*/, int64_t* value_sum_out /*[dev] or NULL*/,
+                                  uint8_t* status_out /*[dev] or NULL*/, dk_stream stream);
+
+/* PolicyFusionFn::fuse (policy_fusion.rs:9-16) per root: rows = the samples of one root, visits[(i*n_rows + s)*39 + a]; rows with
+ * status != 0 (status may be NULL) are failed samples and are left out, as execute does (compare_impi.rs:318-330).
+ *   DK_FUSE_MAX_N    PolicyFusionMaxN (:23-73): rank the allowed actions per row by visits (stable, descending), sum the ranks,
+ *                    smallest sum wins, first index among equals.
+ *   DK_FUSE_AVERAGE  PolicyFusionAverageStrategy (:79-123): sum of visits/total per row in f32, largest wins, LAST index among equals;
+ *                    `allowed` is ignored, as in the reference.
+ * action_out[i] = DK_ACTION_NONE when no sample of root i succeeded (the caller then falls back to a random non-announcement action,
+ * compare_impi.rs:357-368); n_success_out[i] (nullable) = number of rows fused. */
+#define DK_FUSE_MAX_N 0
+#define DK_FUSE_AVERAGE 1
+DK_API dk_status dk_fuse(dk_ctx* ctx, int strategy, size_t n_roots, size_t n_rows, const uint32_t* visits /*[dev]*/,
+                         const uint8_t* status /*[dev] or NULL*/, const uint64_t* allowed /*[dev] n_roots, bit a = action a*/,
+                         uint8_t* action_out /*[dev]*/, uint32_t* n_success_out /*[dev] or NULL*/, dk_stream stream);
+
+/* Sharded decision: every rank evaluates its own determinizations of every root, reduces them to DK_ROOT_STATS int64 per root
+ *   [0,39) MaxN rank sums of the allowed actions | [39,78) visit sums | [78] successful samples | [79] 0
+ * (accumulate != 0 adds to `stats` instead of overwriting), the ranks sum them with dk_allreduce_root_stats, and dk_pimc_pick decides.
+ * MaxN from the statistics is identical to dk_fuse over the union of the rows; Average is the arg-max of the summed visits (last among
+ * equals), which is PolicyFusionAverageStrategy in exact arithmetic when every row has the same total. */
+#define DK_ROOT_STATS 80u
+DK_API dk_status dk_pimc_root_stats(dk_ctx* ctx, size_t n_roots, size_t n_rows, const uint32_t* visits /*[dev]*/, const uint8_t* status /*[dev] or NULL*/,
+                                    const uint64_t* allowed /*[dev]*/, int64_t* stats /*[dev] n_roots*DK_ROOT_STATS*/, int accumulate, dk_stream stream);
+DK_API dk_status dk_pimc_pick(dk_ctx* ctx, int strategy, size_t n_roots, const int64_t* stats /*[dev]*/, const uint64_t* allowed /*[dev]*/,
+                              uint8_t* action_out /*[dev]*/, dk_stream stream);
+
 /* ---- multi-GPU root statistics (the only exchange step) --------------------------------------
  * replaces the per-determinization fuse of PolicyFusion* (rs-doko-py-bridge/src/compare_impi/policy_fusion.rs:18-123):
  * integer sums over ranks, order-independent and bit-reproducible.  NCCL is loaded lazily (dlopen). */

@@ -9,6 +9,10 @@ from . import _build
 DK_DOKO, DK_FDO = 0, 1
 DK_PLAYOUT_WITH_ANNOUNCEMENTS = 1
 DK_APPLY_SKIP_SINGLE = 1
+N_ACTIONS = 39          # FdoAction::COUNT
+ACTION_NONE = 0xFF
+FUSE_MAX_N, FUSE_AVERAGE = 0, 1
+ROOT_STATS = 80
 DK_LAYOUT_DO110, DK_LAYOUT_DO114, DK_LAYOUT_FDO_PI311 = 0, 1, 2
 OBS_LEN = {DK_LAYOUT_DO110: 110, DK_LAYOUT_DO114: 114, DK_LAYOUT_FDO_PI311: 311}
 STATUS = {0: "DK_OK", 1: "DK_ERR_INVALID_ARGUMENT", 2: "DK_ERR_CUDA", 3: "DK_ERR_NO_DEVICE", 4: "DK_ERR_NCCL", 5: "DK_ERR_UNSUPPORTED"}
@@ -69,6 +73,10 @@ def load_library():
         ("dk_step_random_encode", [vp, sz, vp, C.POINTER(DkRng), u32, vp, sz, vp, vp]),
         ("dk_determinize", [vp, i32, sz, sz, vp, C.POINTER(DkRng), vp, vp, vp, vp]),
         ("dk_leaf_rollouts", [vp, sz, sz, i32, vp, C.POINTER(DkRng), vp, vp]),
+        ("dk_pimc_evaluate", [vp, sz, sz, sz, vp, C.POINTER(DkRng), vp, vp, vp, vp]),
+        ("dk_fuse", [vp, i32, sz, sz, vp, vp, vp, vp, vp, vp]),
+        ("dk_pimc_root_stats", [vp, sz, sz, vp, vp, vp, vp, i32, vp]),
+        ("dk_pimc_pick", [vp, i32, sz, vp, vp, vp, vp]),
         ("dk_comm_unique_id", [vp, vp]),
         ("dk_comm_init", [vp, i32, i32, vp]),
         ("dk_comm_destroy", [vp]),
@@ -278,6 +286,50 @@ class DokoCuda:
         self._check(self.L.dk_leaf_rollouts(self.ctx, n, rollouts_per_leaf, int(determinize), _ptr(states), C.byref(rng), _ptr(out),
                                             stream if stream is not None else self._stream()), "dk_leaf_rollouts")
         return out
+
+    # ---- PIMC move decision ------------------------------------------------------------------------------
+    def pimc_evaluate(self, states, n_det, n_rollouts, rng, want_values=True, stream=None):
+        """Flat Monte-Carlo PIMC: (visits uint32→int32 view [n,n_det,39], value_sum int64 [n,n_det,39] or None, status uint8 [n,n_det])."""
+        import torch
+
+        n = states.shape[0]
+        visits = torch.empty((n, n_det, N_ACTIONS), dtype=torch.int32, device=self._dev())
+        values = torch.empty((n, n_det, N_ACTIONS), dtype=torch.int64, device=self._dev()) if want_values else None
+        status = torch.empty((n, n_det), dtype=torch.uint8, device=self._dev())
+        self._check(self.L.dk_pimc_evaluate(self.ctx, n, n_det, n_rollouts, _ptr(states), C.byref(rng), _ptr(visits),
+                                            _ptr(values) if want_values else None, _ptr(status),
+                                            stream if stream is not None else self._stream()), "dk_pimc_evaluate")
+        return visits, values, status
+
+    def fuse(self, strategy, visits, allowed, status=None, stream=None):
+        """PolicyFusionMaxN (FUSE_MAX_N) / PolicyFusionAverageStrategy (FUSE_AVERAGE) per root: (action uint8 [n], n_success int32 [n])."""
+        import torch
+
+        n, rows = visits.shape[0], visits.shape[1]
+        action = torch.empty((n,), dtype=torch.uint8, device=self._dev())
+        n_ok = torch.empty((n,), dtype=torch.int32, device=self._dev())
+        self._check(self.L.dk_fuse(self.ctx, strategy, n, rows, _ptr(visits), _ptr(status) if status is not None else None, _ptr(allowed),
+                                   _ptr(action), _ptr(n_ok), stream if stream is not None else self._stream()), "dk_fuse")
+        return action, n_ok
+
+    def pimc_root_stats(self, visits, allowed, status=None, out=None, accumulate=False, stream=None):
+        """Additive int64 root statistics [n, ROOT_STATS] of this rank's determinizations (MaxN rank sums | visit sums | successes)."""
+        import torch
+
+        n, rows = visits.shape[0], visits.shape[1]
+        out = torch.zeros((n, ROOT_STATS), dtype=torch.int64, device=self._dev()) if out is None else out
+        self._check(self.L.dk_pimc_root_stats(self.ctx, n, rows, _ptr(visits), _ptr(status) if status is not None else None, _ptr(allowed),
+                                              _ptr(out), int(accumulate), stream if stream is not None else self._stream()), "dk_pimc_root_stats")
+        return out
+
+    def pimc_pick(self, strategy, stats, allowed, stream=None):
+        import torch
+
+        n = stats.shape[0]
+        action = torch.empty((n,), dtype=torch.uint8, device=self._dev())
+        self._check(self.L.dk_pimc_pick(self.ctx, strategy, n, _ptr(stats), _ptr(allowed), _ptr(action),
+                                        stream if stream is not None else self._stream()), "dk_pimc_pick")
+        return action
 
     # ---- multi-GPU root statistics ----------------------------------------------------------------------------------------
     def comm_init(self, group=None):

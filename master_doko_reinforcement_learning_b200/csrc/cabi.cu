@@ -268,6 +268,59 @@ dk_status dk_leaf_rollouts(dk_ctx* ctx, size_t n_leaves, size_t rollouts_per_lea
     return check_launch(ctx, "fdo_leaf_rollouts_kernel");
 }
 
+// ---- PIMC move decision ----------------------------------------------------------------------------------
+dk_status dk_pimc_evaluate(dk_ctx* ctx, size_t n_roots, size_t n_det, size_t n_rollouts, const dk_state* states, const dk_rng* rng,
+                           uint32_t* visits_out, int64_t* value_sum_out, uint8_t* status_out, dk_stream stream) {
+    if (!ctx || !states || !rng || (!visits_out && !value_sum_out)) return DK_ERR_INVALID_ARGUMENT;
+    if (n_roots == 0 || n_det == 0) return DK_OK;
+    // unit_hi of rollout (d, r) is (first_sub + d) * n_rollouts + r: keep it inside 32 bits; int32 block sums: |points| < 128
+    if (n_rollouts == 0 || n_rollouts > 0x1000000ull || n_det > 0xFFFFFFFFull ||
+        ((uint64_t)rng->first_sub + n_det) * n_rollouts > 0xFFFFFFFFull) return DK_ERR_INVALID_ARGUMENT;
+    uint32_t dpb = (uint32_t)(dk::PIMC_THREADS / n_rollouts);
+    if (dpb < 1u) dpb = 1u;
+    if (dpb > (uint32_t)dk::PIMC_MAX_DPB) dpb = dk::PIMC_MAX_DPB;
+    if (dpb > n_det) dpb = (uint32_t)n_det;
+    uint64_t blocks_per_root = (n_det + dpb - 1) / dpb;
+    if (n_roots * blocks_per_root > 0x7FFFFFFFull) return DK_ERR_INVALID_ARGUMENT;
+    DK_CUDA(ctx, cudaSetDevice(ctx->device));
+    dk::fdo_pimc_kernel<<<(unsigned)(n_roots * blocks_per_root), dk::PIMC_THREADS, 0, pick_stream(ctx, stream)>>>(
+        to_params(rng), (uint64_t)n_roots, (uint32_t)n_det, (uint32_t)n_rollouts, dpb, (uint32_t)blocks_per_root, states, visits_out,
+        (long long*)value_sum_out, status_out);
+    return check_launch(ctx, "fdo_pimc_kernel");
+}
+
+dk_status dk_fuse(dk_ctx* ctx, int strategy, size_t n_roots, size_t n_rows, const uint32_t* visits, const uint8_t* status, const uint64_t* allowed,
+                  uint8_t* action_out, uint32_t* n_success_out, dk_stream stream) {
+    if (!ctx || !visits || !allowed || !action_out || (strategy != DK_FUSE_MAX_N && strategy != DK_FUSE_AVERAGE) || n_rows > 0xFFFFFFFFull)
+        return DK_ERR_INVALID_ARGUMENT;
+    if (n_roots == 0) return DK_OK;
+    DK_CUDA(ctx, cudaSetDevice(ctx->device));
+    unsigned grid = (unsigned)((n_roots + dk::STATE_THREADS - 1) / dk::STATE_THREADS);
+    dk::fuse_kernel<<<grid, dk::STATE_THREADS, 0, pick_stream(ctx, stream)>>>((uint32_t)strategy, (uint64_t)n_roots, (uint32_t)n_rows, visits, status, allowed,
+                                                                             action_out, n_success_out);
+    return check_launch(ctx, "fuse_kernel");
+}
+
+dk_status dk_pimc_root_stats(dk_ctx* ctx, size_t n_roots, size_t n_rows, const uint32_t* visits, const uint8_t* status, const uint64_t* allowed,
+                             int64_t* stats, int accumulate, dk_stream stream) {
+    if (!ctx || !visits || !allowed || !stats || n_rows > 0xFFFFFFFFull) return DK_ERR_INVALID_ARGUMENT;
+    if (n_roots == 0) return DK_OK;
+    DK_CUDA(ctx, cudaSetDevice(ctx->device));
+    unsigned grid = (unsigned)((n_roots + dk::STATE_THREADS - 1) / dk::STATE_THREADS);
+    dk::root_stats_kernel<<<grid, dk::STATE_THREADS, 0, pick_stream(ctx, stream)>>>((uint64_t)n_roots, (uint32_t)n_rows, visits, status, allowed,
+                                                                                   (long long*)stats, accumulate);
+    return check_launch(ctx, "root_stats_kernel");
+}
+
+dk_status dk_pimc_pick(dk_ctx* ctx, int strategy, size_t n_roots, const int64_t* stats, const uint64_t* allowed, uint8_t* action_out, dk_stream stream) {
+    if (!ctx || !stats || !allowed || !action_out || (strategy != DK_FUSE_MAX_N && strategy != DK_FUSE_AVERAGE)) return DK_ERR_INVALID_ARGUMENT;
+    if (n_roots == 0) return DK_OK;
+    DK_CUDA(ctx, cudaSetDevice(ctx->device));
+    unsigned grid = (unsigned)((n_roots + dk::STATE_THREADS - 1) / dk::STATE_THREADS);
+    dk::root_pick_kernel<<<grid, dk::STATE_THREADS, 0, pick_stream(ctx, stream)>>>((uint32_t)strategy, (uint64_t)n_roots, (const long long*)stats, allowed, action_out);
+    return check_launch(ctx, "root_pick_kernel");
+}
+
 // ---- NCCL (dlopen; the only exchange step of the path) ---------------------------------------------------------------------
 namespace {
 struct NcclApi {

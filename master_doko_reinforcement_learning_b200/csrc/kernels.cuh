@@ -9,6 +9,7 @@
 #include "encode.cuh"
 #include "fdo_rules.cuh"
 #include "matching.cuh"
+#include "pimc.cuh"
 #include "state_ops.cuh"
 
 namespace dk {
@@ -441,6 +442,120 @@ fdo_leaf_rollouts_kernel(RngParams rp, uint64_t n_leaves, uint32_t rollouts, int
     }
     __syncthreads();
     if (threadIdx.x < 4) point_sum[4 * i + threadIdx.x] = (long long)red[threadIdx.x];
+}
+
+// N2: flat Monte-Carlo PIMC evaluator (the per-sample policy slot of DefaultImpiPolicy::execute,
+// rs-doko-py-bridge/src/compare_impi/compare_impi.rs:223-262, filled with "every legal action × R rollouts" instead of a UCT search).
+// One block = one root × PIMC_DPB determinizations: thread 0 builds the constraint tables once, thread j samples determinization j
+// (stream (root, d) — the dk_determinize stream), then the block's threads take the (d, r) pairs; each plays EVERY legal action of
+// the seat to move followed by a _no_announcement rollout on the stream (root, d·R + r) shared by all actions (common random
+// numbers), adds points[mover] to value_sum[d][a] and one visit to the best action (first among equals).  The action loop is
+// uniform across the block (the legal set of the mover does not depend on the hidden hands), so lanes stay in lock-step per action.
+constexpr int PIMC_THREADS = 128;
+constexpr int PIMC_MAX_DPB = 32;
+__global__ void __launch_bounds__(PIMC_THREADS)
+fdo_pimc_kernel(RngParams rp, uint64_t n_roots, uint32_t n_det, uint32_t n_rollouts, uint32_t dpb, uint32_t blocks_per_root,
+                const dk_state* __restrict__ states, uint32_t* __restrict__ visits_out, long long* __restrict__ value_out,
+                uint8_t* __restrict__ status_out) {
+    __shared__ MatchPrep prep;
+    __shared__ __align__(16) dk_state det_state[PIMC_MAX_DPB];
+    __shared__ int vsum[PIMC_MAX_DPB][N_ACTIONS];
+    __shared__ uint32_t wins[PIMC_MAX_DPB][N_ACTIONS];
+    __shared__ uint8_t det_status[PIMC_MAX_DPB];
+    __shared__ uint32_t lut[24];
+    const uint64_t root = blockIdx.x / blocks_per_root;
+    const uint32_t d0 = (uint32_t)(blockIdx.x % blocks_per_root) * dpb;
+    const uint32_t nd = min(dpb, n_det - d0);
+    if (threadIdx.x < 24) lut[threadIdx.x] = card_lut_entry(threadIdx.x);
+    if (threadIdx.x < 8) reinterpret_cast<uint4*>(&det_state[0])[threadIdx.x] = __ldg(reinterpret_cast<const uint4*>(states + root) + threadIdx.x);
+    for (uint32_t k = threadIdx.x; k < nd * N_ACTIONS; k += PIMC_THREADS) { (&vsum[0][0])[k] = 0; (&wins[0][0])[k] = 0u; }
+    __syncthreads();
+    if (threadIdx.x == 0) fdo_match_prepare(det_state[0], prep);
+    __syncthreads();
+    const bool finished = !prep.valid;   // finished root: no legal action, rows stay zero
+    alignas(16) dk_state rootst = det_state[0];
+    __syncthreads();
+    if (threadIdx.x < nd) {
+        uint32_t st = 0;
+        alignas(16) dk_state s = rootst;
+        if (!finished) {
+            RngKey key = make_key(rp, root, rp.first_sub + d0 + threadIdx.x, true);
+            uint64_t h[4];
+            uint8_t res[4];
+            st = fdo_match_sample(prep, key, h, res);
+            if (st == 0u) fdo_state_with_hands_and_reservations(s, h, res);
+        }
+        det_state[threadIdx.x] = s;
+        det_status[threadIdx.x] = (uint8_t)st;
+    }
+    __syncthreads();
+    const uint32_t mover = st_cur(rootst);
+    const uint32_t n_items = nd * n_rollouts;
+    for (uint32_t base = 0; base < n_items; base += PIMC_THREADS) {
+        const uint32_t item = base + threadIdx.x;
+        const bool on = item < n_items;
+        const uint32_t dl = on ? item / n_rollouts : 0u, r = on ? item - dl * n_rollouts : 0u;
+        const bool live = on && !finished && det_status[dl] == 0u;
+        const unsigned active = __ballot_sync(0xFFFFFFFFu, live);
+        if (!live) continue;
+        const unsigned peers = __match_any_sync(active, dl);
+        const bool leader = (uint32_t)(__ffs((int)peers) - 1) == (threadIdx.x & 31u);
+        const RngKey key = make_key(rp, root, (rp.first_sub + d0 + dl) * n_rollouts + r, true);
+        int best_v = 0;
+        uint32_t best_a = ACTION_NONE;
+        // legal set of the determinized state: the mover's own hand and the public state do not depend on the sample, so this is the
+        // root's legal set and the loop is uniform across the block; peers (same dl) share it exactly in any case
+        for (uint64_t m = fdo_state_legal_mask(det_state[dl]); m; m &= m - 1ull) {
+            const uint32_t a = ffs0ll(m);
+            alignas(16) dk_state s = det_state[dl];
+            fdo_state_apply(s, a);
+            int32_t p[4];
+            FdoLive g; FdoResume rs;
+            if (fdo_state_to_live(s, g, rs)) { fdo_play_to_end<false, false>(g, key, &rs, lut); fdo_final_points(g, p); }
+            else { p[0] = s.points[0]; p[1] = s.points[1]; p[2] = s.points[2]; p[3] = s.points[3]; }
+            const int v = (mover & 2u) ? ((mover & 1u) ? p[3] : p[2]) : ((mover & 1u) ? p[1] : p[0]);
+            const int tot = __reduce_add_sync(peers, v);
+            if (leader) atomicAdd(&vsum[dl][a], tot);
+            if (best_a == ACTION_NONE || v > best_v) { best_a = a; best_v = v; }
+        }
+        if (best_a != ACTION_NONE) atomicAdd(&wins[dl][best_a], 1u);
+    }
+    __syncthreads();
+    const uint64_t row0 = root * n_det + d0;
+    for (uint32_t k = threadIdx.x; k < nd * N_ACTIONS; k += PIMC_THREADS) {
+        if (visits_out) visits_out[row0 * N_ACTIONS + k] = (&wins[0][0])[k];
+        if (value_out) value_out[row0 * N_ACTIONS + k] = (long long)(&vsum[0][0])[k];
+    }
+    if (status_out && threadIdx.x < nd) status_out[row0 + threadIdx.x] = det_status[threadIdx.x];
+}
+
+// Fuse per root (thread per root; the rows of one root are contiguous).
+__global__ void __launch_bounds__(STATE_THREADS)
+fuse_kernel(uint32_t strategy, uint64_t n_roots, uint32_t n_det, const uint32_t* __restrict__ visits, const uint8_t* __restrict__ status,
+            const uint64_t* __restrict__ allowed, uint8_t* __restrict__ action_out, uint32_t* __restrict__ n_ok_out) {
+    uint64_t i = (uint64_t)blockIdx.x * STATE_THREADS + threadIdx.x;
+    if (i >= n_roots) return;
+    const uint32_t* v = visits + i * n_det * N_ACTIONS;
+    const uint8_t* st = status ? status + i * n_det : nullptr;
+    uint32_t n_ok = 0;
+    uint32_t a = strategy == 0u ? fuse_max_n(v, st, n_det, allowed[i], &n_ok) : fuse_average(v, st, n_det, &n_ok);
+    action_out[i] = (uint8_t)(n_ok == 0u ? ACTION_NONE : a);
+    if (n_ok_out) n_ok_out[i] = n_ok;
+}
+__global__ void __launch_bounds__(STATE_THREADS)
+root_stats_kernel(uint64_t n_roots, uint32_t n_det, const uint32_t* __restrict__ visits, const uint8_t* __restrict__ status,
+                  const uint64_t* __restrict__ allowed, long long* __restrict__ stats, int accumulate) {
+    uint64_t i = (uint64_t)blockIdx.x * STATE_THREADS + threadIdx.x;
+    if (i >= n_roots) return;
+    long long* out = stats + i * ROOT_STATS;
+    if (!accumulate) for (uint32_t k = 0; k < ROOT_STATS; ++k) out[k] = 0;
+    root_stats_accumulate(visits + i * n_det * N_ACTIONS, status ? status + i * n_det : nullptr, n_det, allowed[i], out);
+}
+__global__ void __launch_bounds__(STATE_THREADS)
+root_pick_kernel(uint32_t strategy, uint64_t n_roots, const long long* __restrict__ stats, const uint64_t* __restrict__ allowed, uint8_t* __restrict__ action_out) {
+    uint64_t i = (uint64_t)blockIdx.x * STATE_THREADS + threadIdx.x;
+    if (i >= n_roots) return;
+    action_out[i] = (uint8_t)root_stats_pick(strategy, stats + i * ROOT_STATS, allowed[i]);
 }
 
 }  // namespace dk

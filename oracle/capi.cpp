@@ -16,6 +16,7 @@
 #include "encode.hpp"
 #include "fdo.hpp"
 #include "matching.hpp"
+#include "pimc.hpp"
 #include "rng.hpp"
 
 using namespace oracle;
@@ -572,5 +573,15 @@ ORC_API int orc_doko_sample_assignment_raw(int marriage, int n_tricks, const int
     PhiloxStream r(seed, (uint32_t)unit, sample, epoch);
     int status = 1;
     guarded([&] { status = doko::sample_assignment(marriage, ts, own_hand, l, observer, r, hands); });
+    return status;
+}
+
+// ---- PIMC move decision ----------------------------------------------------------------------
+ORC_API int orc_fuse_max_n(const uint32_t* visits, uint64_t n_rows, uint64_t allowed) { return pimc::fuse_max_n(visits, (size_t)n_rows, allowed); }
+ORC_API int orc_fuse_average(const uint32_t* visits, uint64_t n_rows) { return pimc::fuse_average(visits, (size_t)n_rows); }
+ORC_API int orc_fdo_flat_mc_philox(const void* h, uint64_t seed, uint64_t unit, uint32_t det, uint32_t n_rollouts, uint32_t epoch,
+                                   uint32_t visits[39], int64_t value_sum[39]) {
+    int status = 1;
+    guarded([&] { status = pimc::flat_mc(*(const fdo::State*)h, seed, unit, det, n_rollouts, epoch, visits, value_sum); });
     return status;
 }

@@ -99,6 +99,19 @@ def main():
     for det in (True, False):
         t = timed(lambda: dk.leaf_rollouts(leaves, R, dk.rng(SEED, 0, 11), determinize=det, out=sums), iters=3)
         out[f"K4_leaf_rollouts_1024x1024_det{int(det)}"] = {"sec": t, "rollouts_per_s": n_leaves * R / t}
+    # N2 PIMC decision: 1024 roots x 64 determinizations x 32 rollouts x (legal actions), evaluate + fuse
+    n_roots, n_det, R2 = int(1024 * a.scale), 64, 32
+    roots = sub[:n_roots]
+    allowed = dk.legal_mask(pkg.DK_FDO, roots)
+    n_legal = float(sum(bin(int(m) & ((1 << 39) - 1)).count("1") for m in allowed.cpu().tolist())) / n_roots
+
+    def n2():
+        v, _, st = dk.pimc_evaluate(roots, n_det, R2, dk.rng(SEED, 0, 12), want_values=False)
+        dk.fuse(pkg.FUSE_MAX_N, v, allowed, st)
+
+    t = timed(n2, iters=3)
+    out["N2_pimc_decision_1024x64x32"] = {"sec": t, "decisions_per_s": n_roots / t, "mean_legal_actions": n_legal,
+                                          "rollouts_per_s": n_roots * n_det * R2 * n_legal / t}
     out["launches"] = dk.launch_count()
     print(json.dumps(out))
 

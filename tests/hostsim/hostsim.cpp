@@ -14,6 +14,7 @@
 #include "../../master_doko_reinforcement_learning_b200/csrc/encode.cuh"
 #include "../../master_doko_reinforcement_learning_b200/csrc/matching.cuh"
 #include "../../master_doko_reinforcement_learning_b200/csrc/assignment.cuh"
+#include "../../master_doko_reinforcement_learning_b200/csrc/pimc.cuh"
 
 #define SIM_API extern "C" __attribute__((visibility("default")))
 
@@ -138,4 +139,44 @@ SIM_API uint32_t sim_fdo_ann_bits(uint64_t seed, uint64_t unit, uint32_t epoch, 
     dk::RngKey key = make_key(seed, unit, epoch);
     dk::AnnStream st; st.blk = 0; st.w = dk::rng_block(key, dk::SITE_ANNOUNCEMENT, 0);
     return dk::fdo_ann_bits(st, key, ord, m);
+}
+
+// ---- PIMC (pimc.cuh + the per-thread body of fdo_pimc_kernel, run sequentially) -------------------------------------------------------
+SIM_API uint32_t sim_fuse(int strategy, const uint32_t* visits, const uint8_t* status, uint32_t n_rows, uint64_t allowed, uint32_t* n_ok) {
+    return strategy == 0 ? dk::fuse_max_n(visits, status, n_rows, allowed, n_ok) : dk::fuse_average(visits, status, n_rows, n_ok);
+}
+SIM_API void sim_root_stats(const uint32_t* visits, const uint8_t* status, uint32_t n_rows, uint64_t allowed, long long* stats) {
+    dk::root_stats_accumulate(visits, status, n_rows, allowed, stats);
+}
+SIM_API uint32_t sim_root_pick(uint32_t strategy, const long long* stats, uint64_t allowed) { return dk::root_stats_pick(strategy, stats, allowed); }
+SIM_API uint32_t sim_fdo_flat_mc(const dk_state* root, uint64_t seed, uint64_t unit, uint32_t det, uint32_t n_rollouts, uint32_t epoch,
+                                 uint32_t visits[39], int64_t value_sum[39]) {
+    for (int a = 0; a < 39; ++a) { visits[a] = 0; value_sum[a] = 0; }
+    dk::MatchPrep prep; dk::fdo_match_prepare(*root, prep);
+    if (!prep.valid) return 0;
+    dk::RngKey key = make_key(seed, unit, epoch); key.unit_hi = det;
+    uint64_t hands[4]; uint8_t res[4];
+    uint32_t status = dk::fdo_match_sample(prep, key, hands, res);
+    if (status) return status;
+    dk_state ds = *root;
+    dk::fdo_state_with_hands_and_reservations(ds, hands, res);
+    const uint32_t mover = dk::st_cur(*root);
+    for (uint32_t r = 0; r < n_rollouts; ++r) {
+        key.unit_hi = det * n_rollouts + r;
+        int best_v = 0; uint32_t best_a = dk::ACTION_NONE;
+        for (uint64_t m = dk::fdo_state_legal_mask(ds); m; m &= m - 1ull) {
+            uint32_t a = dk::ffs0ll(m);
+            dk_state st = ds;
+            dk::fdo_state_apply(st, a);
+            int32_t p[4];
+            dk::FdoLive g; dk::FdoResume rs;
+            if (dk::fdo_state_to_live(st, g, rs)) { dk::fdo_play_to_end<false, false>(g, key, &rs, card_lut()); dk::fdo_final_points(g, p); }
+            else for (int q = 0; q < 4; ++q) p[q] = st.points[q];
+            int v = p[mover];
+            value_sum[a] += v;
+            if (best_a == dk::ACTION_NONE || v > best_v) { best_a = a; best_v = v; }
+        }
+        if (best_a != dk::ACTION_NONE) visits[best_a] += 1;
+    }
+    return 0;
 }

@@ -34,6 +34,13 @@ def load():
         L.sim_doko_assign.argtypes = [vp, u64, u64, u32, u32, vp]
         L.sim_fdo_leaf_rollout.restype = u32
         L.sim_fdo_leaf_rollout.argtypes = [vp, u64, u64, u32, u32, i32, vp, vp]
+        L.sim_fuse.restype = u32
+        L.sim_fuse.argtypes = [i32, vp, vp, u32, u64, vp]
+        L.sim_root_stats.argtypes = [vp, vp, u32, u64, vp]
+        L.sim_root_pick.restype = u32
+        L.sim_root_pick.argtypes = [u32, vp, u64]
+        L.sim_fdo_flat_mc.restype = u32
+        L.sim_fdo_flat_mc.argtypes = [vp, u64, u64, u32, u32, u32, vp, vp]
         L.sim_fdo_score.restype = i32
         L.sim_fdo_score.argtypes = [u32, u32, u32, u32, u32, i32, vp]
         for n in ("sim_fdo_allowed_call", "sim_select_lsb24", "sim_select_lsb", "sim_card_power", "sim_trump_mask", "sim_follow_mask"):

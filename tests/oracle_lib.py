@@ -135,6 +135,9 @@ def load():
     L.orc_smallrng_distribute_cards.argtypes = [u64, i32, vp]
     L.orc_smallrng_bitflag_picks.argtypes = [u64, u64, i32, i32, vp]
     L.orc_smallrng_ranges.argtypes = [u64, i32, vp, vp]
+    L.orc_fuse_max_n.argtypes = [vp, u64, u64]
+    L.orc_fuse_average.argtypes = [vp, u64]
+    L.orc_fdo_flat_mc_philox.argtypes = [vp, u64, u64, u32, u32, u32, vp, vp]
     _lib = L
     return L
 
@@ -239,6 +242,13 @@ class Fdo:
         st = self.L.orc_fdo_leaf_rollout_philox(self.h, seed, unit, rollout, epoch, int(determinize), pts, C.byref(steps))
         return st, list(pts), steps.value
 
+    def flat_mc(self, seed, unit, det, n_rollouts, epoch=0):
+        """(status, visits[39], value_sum[39]) of oracle/pimc.hpp flat_mc."""
+        visits = np.zeros(39, dtype=np.uint32)
+        values = np.zeros(39, dtype=np.int64)
+        st = self.L.orc_fdo_flat_mc_philox(self.h, seed, unit, det, n_rollouts, epoch, visits.ctypes.data_as(C.c_void_p), values.ctypes.data_as(C.c_void_p))
+        return st, visits, values
+
     def rollout(self, seed, unit, rollout, epoch=0, with_announcements=False):
         pts = (C.c_int32 * 4)()
         steps = C.c_uint32()
@@ -319,3 +329,11 @@ def playout_philox(L, engine, n, seed, first_id=0, epoch=0, with_announcements=T
                                aux.ctypes.data_as(C.c_void_p) if want_aux else None,
                                trace.ctypes.data_as(C.c_void_p) if trace_stride else None, trace_stride)
     return dict(points=points, steps=steps, aux=aux, trace=trace, seconds=sec)
+
+
+def fuse(L, strategy, visits, allowed_mask=0):
+    """PolicyFusionMaxN (strategy 0) / PolicyFusionAverageStrategy (1) over rows [n][39] of successful samples (oracle/pimc.hpp)."""
+    v = np.ascontiguousarray(visits, dtype=np.uint32).reshape(-1, 39)
+    if strategy == 0:
+        return L.orc_fuse_max_n(v.ctypes.data_as(C.c_void_p), v.shape[0], allowed_mask)
+    return L.orc_fuse_average(v.ctypes.data_as(C.c_void_p), v.shape[0])
