@@ -282,6 +282,52 @@ DK_API dk_status dk_pimc_root_stats(dk_ctx* ctx, size_t n_roots, size_t n_rows, 
 DK_API dk_status dk_pimc_pick(dk_ctx* ctx, int strategy, size_t n_roots, const int64_t* stats /*[dev]*/, const uint64_t* allowed /*[dev]*/,
                               uint8_t* action_out /*[dev]*/, dk_stream stream);
 
+/* ---- AlphaZero self-play driver -----------------------------------------------------------
+ * self_play with ValueTarget::Default (rs-doko-alpha-zero/src/alpha_zero/train/self_play.rs:19-207) over FdoAzEnvState
+ * (rs-doko-alpha-zero/src/env/envs/full_doko/full_doko.rs:43-172), for a batch of games in lock-step.  The experience buffers are
+ * caller-owned device memory and take the place of states_buffer / policy_targets_buffer / value_targets_buffer (self_play.rs:51-53);
+ * observations are encoded straight into their row, where the network batcher reads them (no Vec<i64>, no host round trip).
+ * Row numbers are deterministic: turn-major, game order inside a turn.
+ *
+ * One turn:   dk_sp_begin_turn  → per game: is_terminal, allowed_actions_by_action_index(false, az_epoch), forced move
+ *                                 (number_of_allowed_actions(az_epoch) == 1, :76) with the keep draw `gen::<f32>() < keep_prob` (:88;
+ *                                 Philox SITE_KEEP word 0 of unit first_id + game, epoch rng->epoch), row assignment,
+ *                                 encode_into_memory into the row, current_player, one-hot policy target of forced moves
+ *             [search]          → the caller fills policy[n][39] (visits / visit_sum, :118-137) and action[n] for the games whose flags
+ *                                 have neither DK_SP_DONE nor DK_SP_FORCED; dk_sp_turn_view exposes allowed / flags / rows (device
+ *                                 pointers owned by the driver, valid until the next begin_turn).  dk_sp_uniform_search is the stand-in
+ *                                 used by tests and benches: one draw over the allowed set (SITE_STEP word 0), uniform policy target.
+ *             dk_sp_end_turn    → policy target into the row, take_action_by_action_index(action, false, az_epoch) (:101,:188);
+ *                                 err_out[i] != 0 for an action outside the allowed set (state unchanged; the reference would panic).
+ * After the last turn dk_sp_finalize writes every row's value target: the final rewards (player_points / 8 as f32) rotated to the
+ * row's mover (RotArr::new_from_0(cp, rewards).extract(), :195-205). */
+typedef struct dk_selfplay dk_selfplay;
+typedef struct dk_sp_buffers {
+    int64_t* states;   /* [dev] capacity * 311 */
+    float* policy;     /* [dev] capacity * 39  */
+    float* value;      /* [dev] capacity * 4   */
+    uint8_t* player;   /* [dev] capacity       current_player of the row (current_player_vec, self_play.rs:58) */
+    uint32_t* game;    /* [dev] capacity       game index of the row */
+    size_t capacity;   /* rows; further rows are dropped (flag DK_SP_DROPPED) and counted */
+} dk_sp_buffers;
+#define DK_SP_DONE 1u
+#define DK_SP_FORCED 2u
+#define DK_SP_KEPT 4u
+#define DK_SP_DROPPED 8u
+#define DK_SP_SEARCH_FORCED 1u /* dk_sp_begin_turn flag: no forced-move shortcut (ValueTarget::Greedy / Avg search every turn, :76) */
+DK_API dk_status dk_sp_create(dk_ctx* ctx, size_t max_games, const dk_sp_buffers* bufs, dk_selfplay** out);
+DK_API dk_status dk_sp_destroy(dk_selfplay* sp);
+DK_API dk_status dk_sp_reset(dk_selfplay* sp, dk_stream stream);
+DK_API dk_status dk_sp_begin_turn(dk_selfplay* sp, size_t n, const dk_state* states /*[dev]*/, uint64_t az_epoch, float keep_prob, uint32_t flags,
+                                  const dk_rng* rng, dk_stream stream);
+DK_API dk_status dk_sp_turn_view(dk_selfplay* sp, const uint64_t** allowed /*[dev] n*/, const uint8_t** flags /*[dev] n*/, const int64_t** rows /*[dev] n, -1 = none*/);
+DK_API dk_status dk_sp_uniform_search(dk_selfplay* sp, const dk_rng* rng, float* policy_out /*[dev] n*39*/, uint8_t* action_out /*[dev] n*/, dk_stream stream);
+DK_API dk_status dk_sp_end_turn(dk_selfplay* sp, dk_state* states /*[dev] in/out*/, const float* policy /*[dev] n*39*/, const uint8_t* action /*[dev] n*/,
+                                uint8_t* err_out /*[dev] n or NULL*/, dk_stream stream);
+DK_API dk_status dk_sp_finalize(dk_selfplay* sp, const dk_state* states /*[dev]*/, dk_stream stream);
+/* Synchronises the stream: rows recorded so far, rows dropped for lack of capacity, rows whose game was unfinished at the last finalize. */
+DK_API dk_status dk_sp_counts(dk_selfplay* sp, uint64_t* rows, uint64_t* dropped, uint64_t* unfinished, dk_stream stream);
+
 /* ---- multi-GPU root statistics (the only exchange step) --------------------------------------
  * replaces the per-determinization fuse of PolicyFusion* (rs-doko-py-bridge/src/compare_impi/policy_fusion.rs:18-123):
  * integer sums over ranks, order-independent and bit-reproducible.  NCCL is loaded lazily (dlopen). */

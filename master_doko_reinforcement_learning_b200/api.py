@@ -77,6 +77,15 @@ def load_library():
         ("dk_fuse", [vp, i32, sz, sz, vp, vp, vp, vp, vp, vp]),
         ("dk_pimc_root_stats", [vp, sz, sz, vp, vp, vp, vp, i32, vp]),
         ("dk_pimc_pick", [vp, i32, sz, vp, vp, vp, vp]),
+        ("dk_sp_create", [vp, sz, vp, C.POINTER(vp)]),
+        ("dk_sp_destroy", [vp]),
+        ("dk_sp_reset", [vp, vp]),
+        ("dk_sp_begin_turn", [vp, sz, vp, u64, C.c_float, u32, C.POINTER(DkRng), vp]),
+        ("dk_sp_turn_view", [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),
+        ("dk_sp_uniform_search", [vp, C.POINTER(DkRng), vp, vp, vp]),
+        ("dk_sp_end_turn", [vp, vp, vp, vp, vp, vp]),
+        ("dk_sp_finalize", [vp, vp, vp]),
+        ("dk_sp_counts", [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64), vp]),
         ("dk_comm_unique_id", [vp, vp]),
         ("dk_comm_init", [vp, i32, i32, vp]),
         ("dk_comm_destroy", [vp]),
@@ -331,6 +340,10 @@ class DokoCuda:
                                         stream if stream is not None else self._stream()), "dk_pimc_pick")
         return action
 
+    def self_play(self, max_games, capacity):
+        """Lock-step AlphaZero self-play driver with its experience buffers."""
+        return SelfPlay(self, max_games, capacity)
+
     # ---- multi-GPU root statistics ----------------------------------------------------------------------------------------
     def comm_init(self, group=None):
         """Create the library's NCCL communicator over the ranks of a torch.distributed group (torch is only the rendezvous)."""
@@ -354,3 +367,98 @@ class DokoCuda:
         self._check(self.L.dk_allreduce_root_stats(self.ctx, values.numel(), _ptr(values), stream if stream is not None else self._stream()),
                     "dk_allreduce_root_stats")
         return values
+
+
+class DkSpBuffers(C.Structure):
+    _fields_ = [("states", C.c_void_p), ("policy", C.c_void_p), ("value", C.c_void_p), ("player", C.c_void_p), ("game", C.c_void_p),
+                ("capacity", C.c_size_t)]
+
+
+SP_DONE, SP_FORCED, SP_KEPT, SP_DROPPED = 1, 2, 4, 8
+SP_SEARCH_FORCED = 1
+
+
+class SelfPlay:
+    """Host mirror of `self_play` (rs-doko-alpha-zero/src/alpha_zero/train/self_play.rs:19-207) for a batch of games in lock-step.
+
+    The experience buffers (states int64 [capacity,311], policy float32 [capacity,39], value float32 [capacity,4], player uint8,
+    game int32) are torch cuda tensors owned by this object; rows [0, rows()) are valid."""
+
+    def __init__(self, dk, max_games, capacity):
+        import torch
+
+        self.dk, self.max_games, self.capacity = dk, int(max_games), int(capacity)
+        dev = dk._dev()
+        self.states = torch.empty((capacity, OBS_LEN[DK_LAYOUT_FDO_PI311]), dtype=torch.int64, device=dev)
+        self.policy = torch.empty((capacity, N_ACTIONS), dtype=torch.float32, device=dev)
+        self.value = torch.zeros((capacity, 4), dtype=torch.float32, device=dev)
+        self.player = torch.empty((capacity,), dtype=torch.uint8, device=dev)
+        self.game = torch.empty((capacity,), dtype=torch.int32, device=dev)
+        self.search_policy = torch.zeros((max_games, N_ACTIONS), dtype=torch.float32, device=dev)
+        self.search_action = torch.zeros((max_games,), dtype=torch.uint8, device=dev)
+        self.err = torch.zeros((max_games,), dtype=torch.uint8, device=dev)
+        bufs = DkSpBuffers(_ptr(self.states), _ptr(self.policy), _ptr(self.value), _ptr(self.player), _ptr(self.game), capacity)
+        self.h = C.c_void_p()
+        dk._check(dk.L.dk_sp_create(dk.ctx, max_games, C.byref(bufs), C.byref(self.h)), "dk_sp_create")
+        self.n = 0
+
+    def close(self):
+        if self.h:
+            self.dk.L.dk_sp_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reset(self):
+        self.dk._check(self.dk.L.dk_sp_reset(self.h, self.dk._stream()), "dk_sp_reset")
+
+    def begin_turn(self, states, az_epoch, keep_prob, rng, flags=0):
+        self.n = states.shape[0]
+        self.dk._check(self.dk.L.dk_sp_begin_turn(self.h, self.n, _ptr(states), az_epoch, keep_prob, flags, C.byref(rng), self.dk._stream()),
+                       "dk_sp_begin_turn")
+
+    def turn_view(self):
+        """(allowed int64 [n], flags uint8 [n], rows int64 [n]) — views of the driver's device arrays, valid until the next begin_turn."""
+        import torch
+
+        a, f, r = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self.dk._check(self.dk.L.dk_sp_turn_view(self.h, C.byref(a), C.byref(f), C.byref(r)), "dk_sp_turn_view")
+        return (_wrap_device(a.value, (self.n,), torch.int64, self.dk._dev()), _wrap_device(f.value, (self.n,), torch.uint8, self.dk._dev()),
+                _wrap_device(r.value, (self.n,), torch.int64, self.dk._dev()))
+
+    def uniform_search(self, rng):
+        self.dk._check(self.dk.L.dk_sp_uniform_search(self.h, C.byref(rng), _ptr(self.search_policy), _ptr(self.search_action), self.dk._stream()),
+                       "dk_sp_uniform_search")
+        return self.search_policy, self.search_action
+
+    def end_turn(self, states, policy=None, action=None):
+        policy = self.search_policy if policy is None else policy
+        action = self.search_action if action is None else action
+        self.dk._check(self.dk.L.dk_sp_end_turn(self.h, _ptr(states), _ptr(policy), _ptr(action), _ptr(self.err), self.dk._stream()), "dk_sp_end_turn")
+        return self.err
+
+    def finalize(self, states):
+        self.dk._check(self.dk.L.dk_sp_finalize(self.h, _ptr(states), self.dk._stream()), "dk_sp_finalize")
+
+    def counts(self):
+        r, d, u = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self.dk._check(self.dk.L.dk_sp_counts(self.h, C.byref(r), C.byref(d), C.byref(u), self.dk._stream()), "dk_sp_counts")
+        return r.value, d.value, u.value
+
+
+def _wrap_device(ptr, shape, dtype, device):
+    """torch view of device memory owned by the library (no copy), via the CUDA array interface."""
+    import torch
+
+    typestr = {torch.int64: "<i8", torch.uint8: "|u1", torch.int32: "<i4", torch.float32: "<f4"}[dtype]
+
+    class _Holder:
+        pass
+
+    h = _Holder()
+    h.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2, "strides": None}
+    return torch.as_tensor(h, device=device)

@@ -13,6 +13,7 @@
 
 #include "../../include/doko_cuda.h"
 #include "kernels.cuh"
+#include "selfplay_kernels.cuh"
 
 struct dk_ctx {
     int device = 0;
@@ -319,6 +320,123 @@ dk_status dk_pimc_pick(dk_ctx* ctx, int strategy, size_t n_roots, const int64_t*
     unsigned grid = (unsigned)((n_roots + dk::STATE_THREADS - 1) / dk::STATE_THREADS);
     dk::root_pick_kernel<<<grid, dk::STATE_THREADS, 0, pick_stream(ctx, stream)>>>((uint32_t)strategy, (uint64_t)n_roots, (const long long*)stats, allowed, action_out);
     return check_launch(ctx, "root_pick_kernel");
+}
+
+// ---- AlphaZero self-play driver ----------------------------------------------------------------------------
+struct dk_selfplay {
+    dk_ctx* ctx = nullptr;
+    size_t max_games = 0;
+    dk::SpBuffers buf{};
+    uint64_t* allowed = nullptr;               // [max_games]
+    long long* rows = nullptr;                 // [max_games]
+    uint8_t* flags = nullptr;                  // [max_games]
+    uint32_t* block_counts = nullptr;          // [n_blocks]
+    unsigned long long* block_offsets = nullptr;
+    unsigned long long* counters = nullptr;    // count, dropped, unfinished
+    size_t turn_n = 0;
+};
+
+dk_status dk_sp_create(dk_ctx* ctx, size_t max_games, const dk_sp_buffers* bufs, dk_selfplay** out) {
+    if (!ctx || !out || !bufs || max_games == 0 || max_games > 0x7FFFFFFFull * dk::SP_THREADS / 2) return DK_ERR_INVALID_ARGUMENT;
+    if (!bufs->states || !bufs->policy || !bufs->value || !bufs->player || !bufs->game) return DK_ERR_INVALID_ARGUMENT;
+    DK_CUDA(ctx, cudaSetDevice(ctx->device));
+    dk_selfplay* sp = new dk_selfplay();
+    sp->ctx = ctx; sp->max_games = max_games;
+    sp->buf.states = (long long*)bufs->states; sp->buf.policy = bufs->policy; sp->buf.value = bufs->value;
+    sp->buf.player = bufs->player; sp->buf.game = bufs->game; sp->buf.capacity = bufs->capacity;
+    size_t nb = (max_games + dk::SP_THREADS - 1) / dk::SP_THREADS;
+    cudaError_t e = cudaMalloc(&sp->allowed, max_games * sizeof(uint64_t));
+    if (e == cudaSuccess) e = cudaMalloc(&sp->rows, max_games * sizeof(long long));
+    if (e == cudaSuccess) e = cudaMalloc(&sp->flags, max_games);
+    if (e == cudaSuccess) e = cudaMalloc(&sp->block_counts, nb * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&sp->block_offsets, nb * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc(&sp->counters, 3 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemset(sp->counters, 0, 3 * sizeof(unsigned long long));
+    if (e != cudaSuccess) { dk_sp_destroy(sp); return fail(ctx, DK_ERR_CUDA, std::string("dk_sp_create: ") + cudaGetErrorString(e)); }
+    *out = sp;
+    return DK_OK;
+}
+dk_status dk_sp_destroy(dk_selfplay* sp) {
+    if (!sp) return DK_OK;
+    cudaSetDevice(sp->ctx->device);
+    cudaFree(sp->allowed); cudaFree(sp->rows); cudaFree(sp->flags); cudaFree(sp->block_counts); cudaFree(sp->block_offsets); cudaFree(sp->counters);
+    delete sp;
+    return DK_OK;
+}
+dk_status dk_sp_reset(dk_selfplay* sp, dk_stream stream) {
+    if (!sp) return DK_ERR_INVALID_ARGUMENT;
+    dk_ctx* ctx = sp->ctx;
+    DK_CUDA(ctx, cudaSetDevice(ctx->device));
+    DK_CUDA(ctx, cudaMemsetAsync(sp->counters, 0, 3 * sizeof(unsigned long long), pick_stream(ctx, stream)));
+    return DK_OK;
+}
+dk_status dk_sp_begin_turn(dk_selfplay* sp, size_t n, const dk_state* states, uint64_t az_epoch, float keep_prob, uint32_t flags, const dk_rng* rng,
+                           dk_stream stream) {
+    if (!sp || !states || !rng || n > sp->max_games) return DK_ERR_INVALID_ARGUMENT;
+    dk_ctx* ctx = sp->ctx;
+    sp->turn_n = n;
+    if (n == 0) return DK_OK;
+    DK_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = pick_stream(ctx, stream);
+    unsigned nb = (unsigned)((n + dk::SP_THREADS - 1) / dk::SP_THREADS);
+    dk::sp_plan_kernel<<<nb, dk::SP_THREADS, 0, s>>>(to_params(rng), (uint64_t)n, states, az_epoch, keep_prob, (flags & DK_SP_SEARCH_FORCED) ? 1u : 0u,
+                                                     sp->allowed, sp->flags, sp->block_counts);
+    dk_status st = check_launch(ctx, "sp_plan_kernel");
+    if (st != DK_OK) return st;
+    dk::sp_scan_kernel<<<1, 1024, 0, s>>>(nb, sp->block_counts, sp->block_offsets, sp->counters, sp->counters + 1, sp->buf.capacity);
+    st = check_launch(ctx, "sp_scan_kernel");
+    if (st != DK_OK) return st;
+    dk::sp_encode_kernel<<<nb, dk::SP_THREADS, 0, s>>>((uint64_t)n, states, sp->allowed, sp->flags, sp->block_offsets, sp->buf, sp->rows);
+    return check_launch(ctx, "sp_encode_kernel");
+}
+dk_status dk_sp_turn_view(dk_selfplay* sp, const uint64_t** allowed, const uint8_t** flags, const int64_t** rows) {
+    if (!sp) return DK_ERR_INVALID_ARGUMENT;
+    if (allowed) *allowed = sp->allowed;
+    if (flags) *flags = sp->flags;
+    if (rows) *rows = (const int64_t*)sp->rows;
+    return DK_OK;
+}
+dk_status dk_sp_uniform_search(dk_selfplay* sp, const dk_rng* rng, float* policy_out, uint8_t* action_out, dk_stream stream) {
+    if (!sp || !rng || !policy_out || !action_out) return DK_ERR_INVALID_ARGUMENT;
+    dk_ctx* ctx = sp->ctx;
+    size_t n = sp->turn_n;
+    if (n == 0) return DK_OK;
+    DK_CUDA(ctx, cudaSetDevice(ctx->device));
+    unsigned grid = (unsigned)((n + dk::STATE_THREADS - 1) / dk::STATE_THREADS);
+    dk::sp_uniform_search_kernel<<<grid, dk::STATE_THREADS, 0, pick_stream(ctx, stream)>>>(to_params(rng), (uint64_t)n, sp->allowed, sp->flags, policy_out, action_out);
+    return check_launch(ctx, "sp_uniform_search_kernel");
+}
+dk_status dk_sp_end_turn(dk_selfplay* sp, dk_state* states, const float* policy, const uint8_t* action, uint8_t* err_out, dk_stream stream) {
+    if (!sp || !states || !policy || !action) return DK_ERR_INVALID_ARGUMENT;
+    dk_ctx* ctx = sp->ctx;
+    size_t n = sp->turn_n;
+    if (n == 0) return DK_OK;
+    DK_CUDA(ctx, cudaSetDevice(ctx->device));
+    unsigned grid = (unsigned)((n + dk::STATE_THREADS - 1) / dk::STATE_THREADS);
+    dk::sp_apply_kernel<<<grid, dk::STATE_THREADS, 0, pick_stream(ctx, stream)>>>((uint64_t)n, states, sp->allowed, sp->flags, sp->rows, policy, action, sp->buf, err_out);
+    return check_launch(ctx, "sp_apply_kernel");
+}
+dk_status dk_sp_finalize(dk_selfplay* sp, const dk_state* states, dk_stream stream) {
+    if (!sp || !states) return DK_ERR_INVALID_ARGUMENT;
+    dk_ctx* ctx = sp->ctx;
+    DK_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = pick_stream(ctx, stream);
+    DK_CUDA(ctx, cudaMemsetAsync(sp->counters + 2, 0, sizeof(unsigned long long), s));
+    dk::sp_finalize_kernel<<<ctx->sm_count * 8, dk::STATE_THREADS, 0, s>>>(sp->counters, states, sp->buf, sp->counters + 2);
+    return check_launch(ctx, "sp_finalize_kernel");
+}
+dk_status dk_sp_counts(dk_selfplay* sp, uint64_t* rows, uint64_t* dropped, uint64_t* unfinished, dk_stream stream) {
+    if (!sp) return DK_ERR_INVALID_ARGUMENT;
+    dk_ctx* ctx = sp->ctx;
+    DK_CUDA(ctx, cudaSetDevice(ctx->device));
+    unsigned long long h[3];
+    cudaStream_t s = pick_stream(ctx, stream);
+    DK_CUDA(ctx, cudaMemcpyAsync(h, sp->counters, sizeof h, cudaMemcpyDeviceToHost, s));
+    DK_CUDA(ctx, cudaStreamSynchronize(s));
+    if (rows) *rows = h[0];
+    if (dropped) *dropped = h[1];
+    if (unfinished) *unfinished = h[2];
+    return DK_OK;
 }
 
 // ---- NCCL (dlopen; the only exchange step of the path) ---------------------------------------------------------------------

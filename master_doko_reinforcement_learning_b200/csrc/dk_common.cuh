@@ -67,10 +67,10 @@ DK_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) {  // low 32 bits
 // Parity stream shared with the oracle (DESIGN.md "Philox parity contract"):
 //   counter = (unit_lo, unit_hi, site<<16 | block, epoch), key = (seed_lo, seed_hi);
 //   decision k of call-site class `site` inside one unit uses word (k & 3) of block (k >> 2),
-//   mapped onto n choices by idx = mulhi(word, n).
+//   mapped onto n choices by idx = mulhi(word, n); announcement decisions take one BIT each (fdo_rules.cuh AnnStream).
 enum Site : uint32_t {
     SITE_DEAL = 0, SITE_RESERVATION = 1, SITE_ANNOUNCEMENT = 2, SITE_CARD = 3,
-    SITE_MATCH_CARD = 4, SITE_MATCH_RESERVATION = 5, SITE_ASSIGN = 6, SITE_STEP = 7
+    SITE_MATCH_CARD = 4, SITE_MATCH_RESERVATION = 5, SITE_ASSIGN = 6, SITE_STEP = 7, SITE_KEEP = 8
 };
 
 struct U4 { uint32_t x, y, z, w; };

@@ -1,0 +1,208 @@
+// selfplay_kernels.cuh — kernels of the lock-step self-play driver (see selfplay.cuh).
+#pragma once
+#include "kernels.cuh"
+#include "selfplay.cuh"
+
+namespace dk {
+
+struct SpBuffers {
+    long long* states;    // [capacity][311]
+    float* policy;        // [capacity][39]
+    float* value;         // [capacity][4]
+    uint8_t* player;      // [capacity]
+    uint32_t* game;       // [capacity]
+    unsigned long long capacity;
+};
+
+constexpr int SP_THREADS = ENC_THREADS;   // plan / encode / apply use the same game → block mapping
+
+__global__ void __launch_bounds__(SP_THREADS)
+sp_plan_kernel(RngParams rp, uint64_t n, const dk_state* __restrict__ states, uint64_t az_epoch, float keep_prob, uint32_t search_forced,
+               uint64_t* __restrict__ allowed_out, uint8_t* __restrict__ flags_out, uint32_t* __restrict__ block_counts) {
+    uint64_t i = (uint64_t)blockIdx.x * SP_THREADS + threadIdx.x;
+    uint32_t flags = SP_DONE;
+    uint64_t allowed = 0;
+    if (i < n) {
+        alignas(16) dk_state s;
+        load_state(states + i, s);
+        if (st_phase(s) != DK_PHASE_FINISHED) {
+            allowed = sp_az_allowed(s, az_epoch);
+            flags = 0;
+            if (popcll(allowed) == 1u && !search_forced) {
+                flags = SP_FORCED;
+                RngKey key = make_key(rp, i, 0, false);
+                U4 blk = rng_block(key, SITE_KEEP, 0);
+                if (sp_keep_draw(blk.x) < keep_prob) flags |= SP_KEPT;
+            } else flags = SP_KEPT;
+        }
+        allowed_out[i] = allowed;
+        flags_out[i] = (uint8_t)flags;
+    }
+    int c = __syncthreads_count((flags & SP_KEPT) != 0u);
+    if (threadIdx.x == 0) block_counts[blockIdx.x] = (uint32_t)c;
+}
+
+// Single block: block_offsets[b] = rows already recorded + sum of counts of the blocks before b; *count advances (saturating at the
+// capacity — rows beyond it are dropped by sp_encode and counted in *dropped).
+__global__ void __launch_bounds__(1024)
+sp_scan_kernel(uint32_t n_blocks, const uint32_t* __restrict__ block_counts, unsigned long long* __restrict__ block_offsets,
+               unsigned long long* __restrict__ count, unsigned long long* __restrict__ dropped, unsigned long long capacity) {
+    __shared__ unsigned long long warp_sum[32];
+    __shared__ unsigned long long carry;
+    if (threadIdx.x == 0) carry = *count;
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    for (uint32_t base = 0; base < n_blocks; base += 1024u) {
+        uint32_t b = base + threadIdx.x;
+        unsigned long long v = b < n_blocks ? block_counts[b] : 0ull, x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, x, o); if ((int)lane >= o) x += y; }
+        if (lane == 31u) warp_sum[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned long long w = warp_sum[lane], z = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, z, o); if ((int)lane >= o) z += y; }
+            warp_sum[lane] = z - w;                                  // exclusive prefix of the warp totals
+        }
+        __syncthreads();
+        unsigned long long excl = carry + warp_sum[warp] + (x - v);
+        if (b < n_blocks) block_offsets[b] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023u) carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        unsigned long long total = carry;                              // rows before this turn (<= capacity) + rows kept in it
+        if (total > capacity) { *dropped += total - capacity; total = capacity; }
+        *count = total;
+    }
+}
+
+__global__ void __launch_bounds__(SP_THREADS)
+sp_encode_kernel(uint64_t n, const dk_state* __restrict__ states, const uint64_t* __restrict__ allowed, uint8_t* __restrict__ flags_io,
+                 const unsigned long long* __restrict__ block_offsets, SpBuffers buf, long long* __restrict__ row_out) {
+    __shared__ uint32_t tok[SP_THREADS * PI_ROW];
+    __shared__ long long row_of[SP_THREADS];
+    __shared__ uint32_t warp_count[SP_THREADS / 32];
+    const uint64_t first = (uint64_t)blockIdx.x * SP_THREADS;
+    const uint64_t i = first + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint32_t flags = i < n ? flags_io[i] : SP_DONE;
+    const bool kept = (flags & SP_KEPT) != 0u;
+    const unsigned ballot = __ballot_sync(0xFFFFFFFFu, kept);
+    if (lane == 0) warp_count[warp] = popc(ballot);
+    __syncthreads();
+    uint32_t before = popc(ballot & ((1u << lane) - 1u));
+    for (uint32_t w = 0; w < warp; ++w) before += warp_count[w];
+    long long row = -1;
+    if (kept) {
+        unsigned long long r = block_offsets[blockIdx.x] + before;
+        if (r < buf.capacity) row = (long long)r;
+        else { flags = (flags & ~SP_KEPT) | SP_DROPPED; flags_io[i] = (uint8_t)flags; }
+    }
+    row_of[threadIdx.x] = row;
+    if (i < n && row_out) row_out[i] = row;
+    if (row >= 0) {
+        alignas(16) dk_state s;
+        load_state(states + i, s);
+        SmemSlotOut o{tok + threadIdx.x * PI_ROW};
+        fdo_encode_pi(s, o);
+        buf.player[row] = (uint8_t)(st_phase(s) == DK_PHASE_FINISHED ? 0u : st_cur(s));
+        buf.game[row] = (uint32_t)i;
+        if (flags & SP_FORCED) {                                      // one-hot policy target of a forced move (self_play.rs:85-86)
+            const uint32_t a = ffs0ll(allowed[i]);
+            float* p = buf.policy + (size_t)row * N_ACTIONS;
+            for (uint32_t k = 0; k < N_ACTIONS; ++k) p[k] = k == a ? 1.0f : 0.0f;
+        }
+    }
+    __syncthreads();
+    // expand the staged rows: one warp per row, rows of one block are consecutive in the buffer
+    for (int r = warp; r < SP_THREADS; r += SP_THREADS / 32) {
+        const long long dst_row = row_of[r];
+        if (dst_row < 0) continue;
+        const uint32_t* src = tok + r * PI_ROW;
+        long long* dst = buf.states + (size_t)dst_row * 311u;
+        uint32_t w0 = src[lane], w1 = lane < 30 ? src[32 + lane] : 0u;
+#define DK_SP_CH(CH, SH, MASK)                                                    \
+        dst[(CH) * 62 + lane] = (long long)((w0 >> (SH)) & (MASK));                   \
+        if (lane < 30) dst[(CH) * 62 + 32 + lane] = (long long)((w1 >> (SH)) & (MASK));
+        DK_SP_CH(0, 0, 63u)
+        DK_SP_CH(1, 6, 63u)
+        DK_SP_CH(2, 12, 7u)
+        DK_SP_CH(3, 15, 15u)
+        DK_SP_CH(4, 19, 3u)
+#undef DK_SP_CH
+        if (lane == 0) dst[310] = (long long)src[62];
+    }
+}
+
+// Stand-in for the search slot (tests / benches): one draw over the allowed set (MSB-first rank pick like FdoAllowedActions::random,
+// SITE_STEP word 0) and the uniform distribution as policy target, for every game that is neither finished nor forced.
+__global__ void __launch_bounds__(STATE_THREADS)
+sp_uniform_search_kernel(RngParams rp, uint64_t n, const uint64_t* __restrict__ allowed, const uint8_t* __restrict__ flags,
+                         float* __restrict__ policy, uint8_t* __restrict__ action) {
+    uint64_t i = (uint64_t)blockIdx.x * STATE_THREADS + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t f = flags[i];
+    if (f & (SP_DONE | SP_FORCED)) { action[i] = (uint8_t)ACTION_NONE; return; }
+    const uint64_t m = allowed[i];
+    const uint32_t cnt = popcll(m);
+    RngKey key = make_key(rp, i, 0, false);
+    U4 blk = rng_block(key, SITE_STEP, 0);
+    action[i] = (uint8_t)pick_msb_rank64(m, mulhi(blk.x, cnt));
+    const float u = f32_div(1.0f, (float)cnt);
+    float* p = policy + i * N_ACTIONS;
+    for (uint32_t k = 0; k < N_ACTIONS; ++k) p[k] = ((m >> k) & 1ull) ? u : 0.0f;
+}
+
+__global__ void __launch_bounds__(STATE_THREADS)
+sp_apply_kernel(uint64_t n, dk_state* __restrict__ states, const uint64_t* __restrict__ allowed, const uint8_t* __restrict__ flags,
+                const long long* __restrict__ rows, const float* __restrict__ policy, const uint8_t* __restrict__ action, SpBuffers buf,
+                uint8_t* __restrict__ err_out) {
+    uint64_t i = (uint64_t)blockIdx.x * STATE_THREADS + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t f = flags[i];
+    uint32_t err = 0;
+    if (!(f & SP_DONE)) {
+        const uint64_t m = allowed[i];
+        const uint32_t a = (f & SP_FORCED) ? ffs0ll(m) : action[i];
+        if (a >= N_ACTIONS || !((m >> a) & 1ull)) err = 1;             // the reference would panic in play_action
+        else {
+            const long long row = rows[i];
+            if (row >= 0 && !(f & SP_FORCED)) {
+                const float* src = policy + i * N_ACTIONS;
+                float* dst = buf.policy + (size_t)row * N_ACTIONS;
+                for (uint32_t k = 0; k < N_ACTIONS; ++k) dst[k] = src[k];
+            }
+            alignas(16) dk_state s;
+            load_state(states + i, s);
+            fdo_state_apply(s, a);
+            store_state(states + i, s);
+        }
+    }
+    if (err_out) err_out[i] = (uint8_t)err;
+}
+
+// Value targets of rows [0, count): rewards of the row's (finished) game rotated to the row's mover.  Rows of unfinished games
+// are left untouched and reported through *unfinished.
+__global__ void __launch_bounds__(STATE_THREADS)
+sp_finalize_kernel(const unsigned long long* __restrict__ count, const dk_state* __restrict__ states, SpBuffers buf,
+                   unsigned long long* __restrict__ unfinished) {
+    const unsigned long long total = *count;
+    for (unsigned long long r = (unsigned long long)blockIdx.x * STATE_THREADS + threadIdx.x; r < total; r += (unsigned long long)gridDim.x * STATE_THREADS) {
+        const dk_state* s = states + buf.game[r];
+        const uint32_t meta = __ldg(&s->meta);
+        if ((meta & 3u) != DK_PHASE_FINISHED) { atomicAdd(unfinished, 1ull); continue; }
+        const uint32_t packed = __ldg(reinterpret_cast<const uint32_t*>(s->points));
+        const uint32_t player = buf.player[r];
+        float4 v;
+        v.x = (float)(int8_t)(packed >> (8u * ((player + 0u) & 3u))) / 8.0f;
+        v.y = (float)(int8_t)(packed >> (8u * ((player + 1u) & 3u))) / 8.0f;
+        v.z = (float)(int8_t)(packed >> (8u * ((player + 2u) & 3u))) / 8.0f;
+        v.w = (float)(int8_t)(packed >> (8u * ((player + 3u) & 3u))) / 8.0f;
+        reinterpret_cast<float4*>(buf.value)[r] = v;
+    }
+}
+
+}  // namespace dk

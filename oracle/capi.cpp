@@ -18,6 +18,7 @@
 #include "matching.hpp"
 #include "pimc.hpp"
 #include "rng.hpp"
+#include "selfplay.hpp"
 
 using namespace oracle;
 
@@ -585,3 +586,35 @@ ORC_API int orc_fdo_flat_mc_philox(const void* h, uint64_t seed, uint64_t unit, 
     guarded([&] { status = pimc::flat_mc(*(const fdo::State*)h, seed, unit, det, n_rollouts, epoch, visits, value_sum); });
     return status;
 }
+
+// ---- AlphaZero self-play driver ----------------------------------------------------------------
+// One game `unit` dealt from the Philox stream (epoch first_epoch), played by self_play with the uniform stand-in search.
+// Returns the number of rows (<= max_rows are written); *turns_out = number of turns.
+ORC_API int orc_selfplay_uniform(uint64_t seed, uint64_t unit, uint64_t az_epoch, float keep_prob, uint32_t first_epoch, int max_rows,
+                                 int64_t* states_out, float* policy_out, float* value_out, uint8_t* player_out, uint16_t* turn_out,
+                                 uint8_t* forced_out, uint32_t* turns_out, int32_t points_out[4]) {
+    PhiloxStream deal(seed, (uint32_t)unit, (uint32_t)(unit >> 32), first_epoch);
+    fdo::State s = fdo::State::new_game(deal);
+    std::vector<selfplay::Row> rows;
+    uint32_t turns = 0;
+    int rc = guarded([&] {
+        turns = selfplay::self_play(s, (size_t)az_epoch, keep_prob, seed, unit, first_epoch,
+            [&](const fdo::State& st, uint64_t allowed, uint32_t turn, float* policy) {
+                return selfplay::uniform_search(seed, unit, first_epoch, st, allowed, turn, policy); }, rows);
+    });
+    if (rc) return -1;
+    if (turns_out) *turns_out = turns;
+    for (size_t i = 0; i < rows.size() && (int)i < max_rows; ++i) {
+        std::memcpy(states_out + i * 311, rows[i].state, sizeof rows[i].state);
+        std::memcpy(policy_out + i * 39, rows[i].policy, sizeof rows[i].policy);
+        std::memcpy(value_out + i * 4, rows[i].value, sizeof rows[i].value);
+        player_out[i] = rows[i].player; turn_out[i] = rows[i].turn; forced_out[i] = rows[i].forced;
+    }
+    if (points_out) {
+        // replay to the end to report the final points (value targets already carry them rotated)
+        for (int p = 0; p < 4; ++p) points_out[p] = 0;
+        if (!rows.empty()) for (int j = 0; j < 4; ++j) points_out[(rows[0].player + j) % 4] = (int32_t)(rows[0].value[j] * 8.0f);
+    }
+    return (int)rows.size();
+}
+ORC_API uint64_t orc_fdo_az_allowed(const void* h, int is_secondary, uint64_t epoch) { return selfplay::az_allowed(*(const fdo::State*)h, is_secondary != 0, (size_t)epoch); }

@@ -42,7 +42,8 @@ enum Site : uint32_t {
     SITE_MATCH_RESERVATION = 5, // hidden reservation `.choose(rng)` (card_matching.rs:450); word = seat index
     SITE_ASSIGN = 6,       // rs-doko-assignment random card / random player (assignment.rs:419-445)
     SITE_STEP = 7,         // lock-step env step (config 5): one decision per call, word 0
-    SITE_COUNT = 8,
+    SITE_KEEP = 8,         // self_play's `rng.gen::<f32>() < probability_of_keeping_experience` (self_play.rs:88); word 0 of the turn's epoch
+    SITE_COUNT = 9,
 };
 
 // Abstract source.  `below(site, n)` returns a value in [0, n).

@@ -112,6 +112,34 @@ def main():
     t = timed(n2, iters=3)
     out["N2_pimc_decision_1024x64x32"] = {"sec": t, "decisions_per_s": n_roots / t, "mean_legal_actions": n_legal,
                                           "rollouts_per_s": n_roots * n_det * R2 * n_legal / t}
+    # N1 self-play driver: 2^20 games in lock-step, one full turn = plan + scan + encode-into-row + stand-in search + apply
+    n_sp = int((1 << 20) * a.scale)
+    sp_states = dk.new_games(pkg.DK_FDO, n_sp, dk.rng(SEED, 0, 0))
+    sp = dk.self_play(n_sp, n_sp * 4)
+    for t in range(12):                                   # into the card phase, where most turns are searched (not forced)
+        sp.reset()
+        sp.begin_turn(sp_states, 0, 1.0, dk.rng(SEED, 0, t))
+        sp.uniform_search(dk.rng(SEED, 0, t))
+        sp.end_turn(sp_states)
+    snapshot = sp_states.clone()
+
+    def n1():
+        sp_states.copy_(snapshot)
+        sp.reset()
+        sp.begin_turn(sp_states, 0, 1.0, dk.rng(SEED, 0, 12))
+        sp.uniform_search(dk.rng(SEED, 0, 12))
+        sp.end_turn(sp_states)
+
+    def n1_copy_only():
+        sp_states.copy_(snapshot)
+
+    t_all, t_copy = timed(n1, iters=5), timed(n1_copy_only, iters=5)
+    t = t_all - t_copy
+    rows, dropped, _ = sp.counts()
+    # bytes per game-turn: plan 128 r + 9 w; encode 128 r + 2488 w + 5 w (+156 w forced); search 9 r + 157 w; apply 128 r + 128 w + 9 r + 156 r + 156 w
+    bytes_turn = 128 + 9 + 128 + 2488 + 5 + 9 + 157 + 128 + 128 + 9 + 156 + 156
+    out["N1_selfplay_turn_2p20"] = {"sec": t, "game_turns_per_s": n_sp / t, "rows": rows, "dropped": dropped, "bytes_per_game_turn": bytes_turn,
+                                    "algorithmic_GBps": n_sp * bytes_turn / t / 1e9, "hbm_frac_of_measured": n_sp * bytes_turn / t / 1e9 / hbm}
     out["launches"] = dk.launch_count()
     print(json.dumps(out))
 

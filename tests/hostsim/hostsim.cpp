@@ -15,6 +15,7 @@
 #include "../../master_doko_reinforcement_learning_b200/csrc/matching.cuh"
 #include "../../master_doko_reinforcement_learning_b200/csrc/assignment.cuh"
 #include "../../master_doko_reinforcement_learning_b200/csrc/pimc.cuh"
+#include "../../master_doko_reinforcement_learning_b200/csrc/selfplay.cuh"
 
 #define SIM_API extern "C" __attribute__((visibility("default")))
 
@@ -180,3 +181,8 @@ SIM_API uint32_t sim_fdo_flat_mc(const dk_state* root, uint64_t seed, uint64_t u
     }
     return 0;
 }
+
+// ---- self-play driver helpers (selfplay.cuh) ---------------------------------------------------------------------------------------
+SIM_API uint64_t sim_sp_az_allowed(const dk_state* s, uint64_t az_epoch) { return dk::sp_az_allowed(*s, az_epoch); }
+SIM_API float sim_sp_keep_draw(uint32_t word) { return dk::sp_keep_draw(word); }
+SIM_API float sim_sp_value_target(const dk_state* s, uint32_t player, uint32_t k) { return dk::sp_value_target(*s, player, k); }

@@ -34,6 +34,12 @@ def load():
         L.sim_doko_assign.argtypes = [vp, u64, u64, u32, u32, vp]
         L.sim_fdo_leaf_rollout.restype = u32
         L.sim_fdo_leaf_rollout.argtypes = [vp, u64, u64, u32, u32, i32, vp, vp]
+        L.sim_sp_az_allowed.restype = u64
+        L.sim_sp_az_allowed.argtypes = [vp, u64]
+        L.sim_sp_keep_draw.restype = C.c_float
+        L.sim_sp_keep_draw.argtypes = [u32]
+        L.sim_sp_value_target.restype = C.c_float
+        L.sim_sp_value_target.argtypes = [vp, u32, u32]
         L.sim_fuse.restype = u32
         L.sim_fuse.argtypes = [i32, vp, vp, u32, u64, vp]
         L.sim_root_stats.argtypes = [vp, vp, u32, u64, vp]

@@ -135,6 +135,9 @@ def load():
     L.orc_smallrng_distribute_cards.argtypes = [u64, i32, vp]
     L.orc_smallrng_bitflag_picks.argtypes = [u64, u64, i32, i32, vp]
     L.orc_smallrng_ranges.argtypes = [u64, i32, vp, vp]
+    L.orc_selfplay_uniform.argtypes = [u64, u64, u64, C.c_float, u32, i32, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.orc_fdo_az_allowed.restype = u64
+    L.orc_fdo_az_allowed.argtypes = [vp, i32, u64]
     L.orc_fuse_max_n.argtypes = [vp, u64, u64]
     L.orc_fuse_average.argtypes = [vp, u64]
     L.orc_fdo_flat_mc_philox.argtypes = [vp, u64, u64, u32, u32, u32, vp, vp]
@@ -337,3 +340,22 @@ def fuse(L, strategy, visits, allowed_mask=0):
     if strategy == 0:
         return L.orc_fuse_max_n(v.ctypes.data_as(C.c_void_p), v.shape[0], allowed_mask)
     return L.orc_fuse_average(v.ctypes.data_as(C.c_void_p), v.shape[0])
+
+
+def selfplay_uniform(L, seed, unit, az_epoch, keep_prob, first_epoch=0, max_rows=250):
+    """oracle/selfplay.hpp self_play of one Philox-dealt game with the uniform stand-in search.
+    Returns dict(states [r,311] i64, policy [r,39] f32, value [r,4] f32, player, turn, forced, turns, points)."""
+    st = np.zeros((max_rows, 311), dtype=np.int64)
+    po = np.zeros((max_rows, 39), dtype=np.float32)
+    va = np.zeros((max_rows, 4), dtype=np.float32)
+    pl = np.zeros(max_rows, dtype=np.uint8)
+    tu = np.zeros(max_rows, dtype=np.uint16)
+    fo = np.zeros(max_rows, dtype=np.uint8)
+    turns = C.c_uint32()
+    pts = (C.c_int32 * 4)()
+    vp = C.c_void_p
+    n = L.orc_selfplay_uniform(seed, unit, az_epoch, keep_prob, first_epoch, max_rows, st.ctypes.data_as(vp), po.ctypes.data_as(vp), va.ctypes.data_as(vp),
+                               pl.ctypes.data_as(vp), tu.ctypes.data_as(vp), fo.ctypes.data_as(vp), C.byref(turns), pts)
+    assert 0 <= n <= max_rows, L.orc_last_error()
+    return {"states": st[:n], "policy": po[:n], "value": va[:n], "player": pl[:n], "turn": tu[:n], "forced": fo[:n], "turns": turns.value,
+            "points": list(pts)}
