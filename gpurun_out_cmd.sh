@@ -1,3 +1,3 @@
 set -x
 mkdir -p gpurun_out
-python -m pytest tests/test_gpu_selfplay.py -m gpu -x -q > gpurun_out/pytest_sp.log 2>&1; tail -30 gpurun_out/pytest_sp.log
+python profiles/bench_kernels.py > gpurun_out/kernels_v6.json 2> gpurun_out/kernels_v6.err; tail -c 900 gpurun_out/kernels_v6.json; tail -3 gpurun_out/kernels_v6.err
