@@ -113,10 +113,63 @@ class EnvBatch {
         ctx_.check(dk_determinize(ctx_.get(), engine_, len(), samples, states(), &rng, hands_out_dev, reservations_out_dev, status_out_dev, stream), "dk_determinize");
     }
 
+    // DefaultImpiPolicy::execute up to the fuse (compare_impi.rs:212-345): S determinizations x flat Monte-Carlo per-sample policy;
+    // visits_out [n][S][39], status_out [n][S]
+    void pimc_evaluate(const dk_rng& rng, size_t n_det, size_t n_rollouts, uint32_t* visits_out_dev, int64_t* value_sum_out_dev, uint8_t* status_out_dev,
+                       dk_stream stream = nullptr) const {
+        ctx_.check(dk_pimc_evaluate(ctx_.get(), len(), n_det, n_rollouts, states(), &rng, visits_out_dev, value_sum_out_dev, status_out_dev, stream), "dk_pimc_evaluate");
+    }
+
    private:
     Context& ctx_;
     int engine_;
     DeviceBuffer<dk_state> states_;
+};
+
+// PolicyFusionFn::fuse (policy_fusion.rs:9-16) for a batch of roots; strategy = DK_FUSE_MAX_N (PolicyFusionMaxN) or DK_FUSE_AVERAGE
+// (PolicyFusionAverageStrategy).  action_out[i] == DK_ACTION_NONE when no sample of root i succeeded.
+inline void fuse(Context& ctx, int strategy, size_t n_roots, size_t n_rows, const uint32_t* visits_dev, const uint8_t* status_dev, const uint64_t* allowed_dev,
+                 uint8_t* action_out_dev, uint32_t* n_success_out_dev = nullptr, dk_stream stream = nullptr) {
+    ctx.check(dk_fuse(ctx.get(), strategy, n_roots, n_rows, visits_dev, status_dev, allowed_dev, action_out_dev, n_success_out_dev, stream), "dk_fuse");
+}
+
+// self_play (rs-doko-alpha-zero/src/alpha_zero/train/self_play.rs:19-207) for an EnvBatch in lock-step.  The experience buffers
+// take the place of states_buffer / policy_targets_buffer / value_targets_buffer and stay in device memory.
+class SelfPlay {
+   public:
+    SelfPlay(Context& ctx, size_t max_games, size_t capacity)
+        : ctx_(ctx), states_(capacity * 311), policy_(capacity * DK_N_ACTIONS), value_(capacity * 4), player_(capacity), game_(capacity) {
+        dk_sp_buffers b{states_.data(), policy_.data(), value_.data(), player_.data(), game_.data(), capacity};
+        ctx_.check(dk_sp_create(ctx_.get(), max_games, &b, &sp_), "dk_sp_create");
+    }
+    ~SelfPlay() { dk_sp_destroy(sp_); }
+    SelfPlay(const SelfPlay&) = delete;
+    SelfPlay& operator=(const SelfPlay&) = delete;
+
+    void reset(dk_stream stream = nullptr) { ctx_.check(dk_sp_reset(sp_, stream), "dk_sp_reset"); }
+    // is_terminal / number_of_allowed_actions / encode_into_memory / current_player of every game; rows assigned
+    void begin_turn(const EnvBatch& env, uint64_t az_epoch, float probability_of_keeping_experience, const dk_rng& rng, uint32_t flags = 0, dk_stream stream = nullptr) {
+        ctx_.check(dk_sp_begin_turn(sp_, env.len(), env.states(), az_epoch, probability_of_keeping_experience, flags, &rng, stream), "dk_sp_begin_turn");
+    }
+    void turn_view(const uint64_t** allowed, const uint8_t** flags, const int64_t** rows) { ctx_.check(dk_sp_turn_view(sp_, allowed, flags, rows), "dk_sp_turn_view"); }
+    // policy target + take_action_by_action_index(action, false, epoch)
+    void end_turn(EnvBatch& env, const float* policy_dev, const uint8_t* action_dev, uint8_t* err_out_dev = nullptr, dk_stream stream = nullptr) {
+        ctx_.check(dk_sp_end_turn(sp_, env.states(), policy_dev, action_dev, err_out_dev, stream), "dk_sp_end_turn");
+    }
+    void finalize(const EnvBatch& env, dk_stream stream = nullptr) { ctx_.check(dk_sp_finalize(sp_, env.states(), stream), "dk_sp_finalize"); }
+    uint64_t rows(dk_stream stream = nullptr) { uint64_t r = 0; ctx_.check(dk_sp_counts(sp_, &r, nullptr, nullptr, stream), "dk_sp_counts"); return r; }
+    const DeviceBuffer<int64_t>& states_buffer() const { return states_; }
+    const DeviceBuffer<float>& policy_targets_buffer() const { return policy_; }
+    const DeviceBuffer<float>& value_targets_buffer() const { return value_; }
+    dk_selfplay* get() const { return sp_; }
+
+   private:
+    Context& ctx_;
+    DeviceBuffer<int64_t> states_;
+    DeviceBuffer<float> policy_, value_;
+    DeviceBuffer<uint8_t> player_;
+    DeviceBuffer<uint32_t> game_;
+    dk_selfplay* sp_ = nullptr;
 };
 
 }  // namespace doko
