@@ -1,3 +1,3 @@
 set -x
 mkdir -p gpurun_out
-python profiles/bench_kernels.py > gpurun_out/kernels_v6.json 2> gpurun_out/kernels_v6.err; tail -c 900 gpurun_out/kernels_v6.json; tail -3 gpurun_out/kernels_v6.err
+python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; tail -15 gpurun_out/pytest_gpu.log

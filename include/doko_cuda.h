@@ -237,6 +237,16 @@ DK_API dk_status dk_leaf_rollouts(dk_ctx* ctx, size_t n_leaves, size_t rollouts_
                            const dk_state* states /*[dev]*/, const dk_rng* rng, int64_t* point_sum_out /*[dev] n_leaves*4*/,
                            dk_stream stream);
 
+/* encode_state_ipi (rs-doko-networks/src/full_doko/var1/encode_ipi.rs:48-306): the imperfect-information 311-token
+ * layout of the autoregressive hand predictor, observer = seat to move.  Per game: assumed_hands[i*4 + seat] = cards guessed so far for
+ * that seat (48-bit board; the observer's entry is ignored), assumed_reservations[i*4 + seat] = guessed DK_RES_* or DK_RES_NONE
+ * (used only where the visible reservation is NotRevealed), next_player[i] = seat the next card is guessed for.  Same row layout as
+ * DK_LAYOUT_FDO_PI311 (5 channels x 62 slots + 1).  err_out[i] != 0 (nullable) where the reference would panic: a guessed hand larger
+ * than the real one (`hand.len() - assumed.len()`, :158) — the row is then truncated / zero-padded. */
+DK_API dk_status dk_encode_ipi(dk_ctx* ctx, size_t n, const dk_state* states /*[dev]*/, const uint64_t* assumed_hands /*[dev] n*4*/,
+                               const uint8_t* assumed_reservations /*[dev] n*4*/, const uint8_t* next_player /*[dev] n*/,
+                               int64_t* out /*[dev] n*row_stride*/, size_t row_stride, uint8_t* err_out /*[dev] n or NULL*/, dk_stream stream);
+
 /* ---- PIMC move decision ------------------------------------------------------------------
  * DefaultImpiPolicy::execute (rs-doko-py-bridge/src/compare_impi/compare_impi.rs:212-372): num_samples determinizations of the
  * info-state (CAPSampling = card_matching, :64-83), a per-sample policy that returns visit counts per action, and a PolicyFusionFn.

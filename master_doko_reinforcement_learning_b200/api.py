@@ -73,6 +73,7 @@ def load_library():
         ("dk_step_random_encode", [vp, sz, vp, C.POINTER(DkRng), u32, vp, sz, vp, vp]),
         ("dk_determinize", [vp, i32, sz, sz, vp, C.POINTER(DkRng), vp, vp, vp, vp]),
         ("dk_leaf_rollouts", [vp, sz, sz, i32, vp, C.POINTER(DkRng), vp, vp]),
+        ("dk_encode_ipi", [vp, sz, vp, vp, vp, vp, vp, sz, vp, vp]),
         ("dk_pimc_evaluate", [vp, sz, sz, sz, vp, C.POINTER(DkRng), vp, vp, vp, vp]),
         ("dk_fuse", [vp, i32, sz, sz, vp, vp, vp, vp, vp, vp]),
         ("dk_pimc_root_stats", [vp, sz, sz, vp, vp, vp, vp, i32, vp]),
@@ -295,6 +296,19 @@ class DokoCuda:
         self._check(self.L.dk_leaf_rollouts(self.ctx, n, rollouts_per_leaf, int(determinize), _ptr(states), C.byref(rng), _ptr(out),
                                             stream if stream is not None else self._stream()), "dk_leaf_rollouts")
         return out
+
+    def encode_ipi(self, states, assumed_hands, assumed_reservations, next_player, out=None, row_stride=None, stream=None):
+        """encode_state_ipi rows (int64 [n,row_stride]) + err flags (uint8 [n]).  assumed_hands int64 [n,4], assumed_reservations uint8 [n,4],
+        next_player uint8 [n] — cuda tensors."""
+        import torch
+
+        n = states.shape[0]
+        row_stride = row_stride or 311
+        out = torch.empty((n, row_stride), dtype=torch.int64, device=self._dev()) if out is None else out
+        err = torch.empty((n,), dtype=torch.uint8, device=self._dev())
+        self._check(self.L.dk_encode_ipi(self.ctx, n, _ptr(states), _ptr(assumed_hands), _ptr(assumed_reservations), _ptr(next_player), _ptr(out),
+                                         row_stride, _ptr(err), stream if stream is not None else self._stream()), "dk_encode_ipi")
+        return out, err
 
     # ---- PIMC move decision (SURVEY.md §8f N2) ------------------------------------------------------------------------------
     def pimc_evaluate(self, states, n_det, n_rollouts, rng, want_values=True, stream=None):

@@ -269,6 +269,17 @@ dk_status dk_leaf_rollouts(dk_ctx* ctx, size_t n_leaves, size_t rollouts_per_lea
     return check_launch(ctx, "fdo_leaf_rollouts_kernel");
 }
 
+dk_status dk_encode_ipi(dk_ctx* ctx, size_t n, const dk_state* states, const uint64_t* assumed_hands, const uint8_t* assumed_reservations,
+                        const uint8_t* next_player, int64_t* out, size_t row_stride, uint8_t* err_out, dk_stream stream) {
+    if (!ctx || !states || !assumed_hands || !assumed_reservations || !next_player || !out || row_stride < 311) return DK_ERR_INVALID_ARGUMENT;
+    if (n == 0) return DK_OK;
+    DK_CUDA(ctx, cudaSetDevice(ctx->device));
+    unsigned grid = (unsigned)((n + dk::ENC_THREADS - 1) / dk::ENC_THREADS);
+    dk::encode_ipi_kernel<<<grid, dk::ENC_THREADS, 0, pick_stream(ctx, stream)>>>((uint64_t)n, states, assumed_hands, assumed_reservations, next_player, out,
+                                                                                 row_stride, err_out);
+    return check_launch(ctx, "encode_ipi_kernel");
+}
+
 // ---- PIMC move decision ----------------------------------------------------------------------------------
 dk_status dk_pimc_evaluate(dk_ctx* ctx, size_t n_roots, size_t n_det, size_t n_rollouts, const dk_state* states, const dk_rng* rng,
                            uint32_t* visits_out, int64_t* value_sum_out, uint8_t* status_out, dk_stream stream) {

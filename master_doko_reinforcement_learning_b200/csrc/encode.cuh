@@ -69,6 +69,73 @@ DK_HD void fdo_encode_pi(const dk_state& s, Out& out) {
     out.phase(st_phase(s));                                                   // encode_phase (var1/phase.rs:9-18)
 }
 
+// encode_state_ipi (rs-doko-networks/src/full_doko/var1/encode_ipi.rs:48-306) with obs = observation_for_current_player(): the
+// imperfect-information layout of the autoregressive hand predictor.  Slots: the four VISIBLE reservations in play order (a
+// NotRevealed one replaced by the guess, :68-79), played cards, the observer's own hand, then for the other seats from the observer
+// on: the cards guessed so far followed by one "unknown" slot per card still missing (:132-174), 10 call slots; the last value is
+// the seat the next card is guessed for, relative to the observer (:232).  assumed hands are bitboards by ABSOLUTE seat (the
+// observer's entry is ignored), assumed reservations DK_RES_* by absolute seat or DK_RES_NONE.
+// Returns 0, or 1 when the reference would panic (a guessed hand larger than the real one ⇒ `hand.len() - assumed.len()` underflows,
+// or the slot count is not 62); the row is then zero-padded / truncated.
+template <class Out>
+DK_HD uint32_t fdo_encode_ipi(const dk_state& s, const uint64_t assumed[4], const uint8_t assumed_res[4], uint32_t next_player, Out& out) {
+    const uint32_t cur = st_phase(s) == DK_PHASE_FINISHED ? 0u : st_cur(s);
+    uint32_t n = 0, err = 0;
+    auto push = [&](uint32_t tok, uint32_t pos, uint32_t ply, uint32_t sub, uint32_t team) {
+        if (n < 62u) out.slot(n, tok, pos, ply, sub, team); else err = 1u;
+        n++;
+    };
+    const uint32_t start = st_game_start(s), nres = s.n_reservations;
+    const bool completed = nres == 4u;
+    bool solo_seen = false;
+    for (uint32_t i = 0; i < 4u; ++i) {                                       // get_visible_reservations(observer) (visible_reservations_logic.rs:7-70)
+        const uint32_t seat = (start + i) & 3u;
+        uint32_t tok = 35u;                                                   // NoneYet
+        if (i < nres) {
+            const uint32_t code = s.reservations[i];
+            if (code == 0u) tok = 25u;
+            else if (code == 1u) tok = (completed || seat == cur) ? 26u : 34u;
+            else if (completed && !solo_seen) { tok = 25u + code; solo_seen = true; }
+            else tok = 34u;                                                   // NotRevealed
+            if (tok == 34u && assumed_res[seat] != 0xFFu) tok = 25u + assumed_res[seat];
+        }
+        push(tok, i + 1u, ((seat - cur) & 3u) + 1u, 0u, 0u);
+    }
+    const uint32_t ci = s.card_index;
+    for (uint32_t j = 0; j < ci; ++j) {                                       // played cards (:93-110)
+        uint32_t seat = (st_trick_start(s, j >> 2) + (j & 3u)) & 3u;
+        push(fdo_card_token(s.cards[j]), j + 5u, ((seat - cur) & 3u) + 1u, 0u, 0u);
+    }
+    for (uint32_t i = 0; i < 4u; ++i) {
+        const uint32_t seat = (cur + i) & 3u;
+        const uint64_t real = s.hands[seat], h = i == 0u ? real : assumed[seat];
+        for (uint64_t b = h; b; b &= b - 1ull) {
+            uint32_t pos = ffs0ll(b);
+            uint32_t c = pos < 24u ? pos : pos - 24u;
+            uint32_t second = (pos >= 24u && ((h >> c) & 1ull)) ? 1u : 0u;
+            push(fdo_card_token(c), 53u + i, 0u, 11u + second, 0u);
+        }
+        if (i > 0u) {
+            const uint32_t have = popcll(real), guessed = popcll(h);
+            if (guessed > have) err = 1u;
+            for (uint32_t k = guessed; k < have; ++k) push(0u, 53u + i, 0u, 0u, 0u);   // still unknown (:160-173)
+        }
+    }
+    const uint32_t n_calls = st_n_calls(s), re = st_re_mask(s);
+    uint32_t sub = 0, last = 0xFFFFFFFFu;
+    for (uint32_t a = 0; a < n_calls && a < 10u; ++a) {                       // calls (:191-215)
+        uint32_t v = s.announcements[a], cidx = v & 63u, seat = (v >> 6) & 3u, lvl = (v >> 8) & 7u;
+        if (cidx != last) { last = cidx; sub = 0; }
+        push(lvl == 6u ? 38u : 37u + lvl, cidx + 1u, ((seat - cur) & 3u) + 1u, sub + 1u, ((re >> seat) & 1u) ? 1u : 2u);
+        sub++;
+    }
+    for (uint32_t a = n_calls; a < 10u; ++a) push(37u, 0u, 0u, 0u, 0u);
+    if (n != 62u) err = 1u;
+    for (; n < 62u; ++n) out.slot(n, 0u, 0u, 0u, 0u, 0u);
+    out.phase(((next_player - cur) & 3u) + 1u);
+    return err;
+}
+
 // encode_state / encode_state_with_reservations (rs-doko-embeddings/src/encode_state.rs:84-317): 110 / 114 values.
 template <class Out>
 DK_HD void doko_encode(const dk_state& s, bool with_reservations, Out& out) {

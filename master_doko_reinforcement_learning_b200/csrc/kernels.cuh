@@ -251,6 +251,29 @@ encode_pi_kernel(uint64_t n, const dk_state* __restrict__ states, int64_t* __res
     write_rows_pi(tok, first, n, out, row_stride);
 }
 
+// encode_state_ipi for a batch: per game the guessed hands (u64[4] by absolute seat), guessed reservations (u8[4]) and the seat to guess for.
+__global__ void __launch_bounds__(ENC_THREADS)
+encode_ipi_kernel(uint64_t n, const dk_state* __restrict__ states, const uint64_t* __restrict__ assumed_hands, const uint8_t* __restrict__ assumed_res,
+                  const uint8_t* __restrict__ next_player, int64_t* __restrict__ out, size_t row_stride, uint8_t* __restrict__ err_out) {
+    __shared__ uint32_t tok[ENC_THREADS * PI_ROW];
+    uint64_t first = (uint64_t)blockIdx.x * ENC_THREADS;
+    uint64_t i = first + threadIdx.x;
+    if (i < n) {
+        alignas(16) dk_state s;
+        load_state(states + i, s);
+        const ulonglong2* hp = reinterpret_cast<const ulonglong2*>(assumed_hands + 4 * i);
+        ulonglong2 h01 = __ldg(hp), h23 = __ldg(hp + 1);
+        uint64_t ah[4] = {h01.x, h01.y, h23.x, h23.y};
+        uint32_t packed = __ldg(reinterpret_cast<const uint32_t*>(assumed_res) + i);
+        uint8_t ar[4] = {(uint8_t)packed, (uint8_t)(packed >> 8), (uint8_t)(packed >> 16), (uint8_t)(packed >> 24)};
+        SmemSlotOut o{tok + threadIdx.x * PI_ROW};
+        uint32_t err = fdo_encode_ipi(s, ah, ar, next_player[i] & 3u, o);
+        if (err_out) err_out[i] = (uint8_t)err;
+    }
+    __syncthreads();
+    write_rows_pi(tok, first, n, out, row_stride);
+}
+
 template <int LAYOUT>
 __global__ void __launch_bounds__(ENC_THREADS)
 encode_kernel(uint64_t n, const dk_state* __restrict__ states, int64_t* __restrict__ out, size_t row_stride) {

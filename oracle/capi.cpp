@@ -618,3 +618,10 @@ ORC_API int orc_selfplay_uniform(uint64_t seed, uint64_t unit, uint64_t az_epoch
     return (int)rows.size();
 }
 ORC_API uint64_t orc_fdo_az_allowed(const void* h, int is_secondary, uint64_t epoch) { return selfplay::az_allowed(*(const fdo::State*)h, is_secondary != 0, (size_t)epoch); }
+
+// encode_state_ipi: assumed hands (bitboards by absolute seat), assumed reservations (DK_RES_* / DK_RES_NONE)
+ORC_API int orc_fdo_encode_ipi(const void* h, const uint64_t assumed_hands[4], const uint8_t assumed_res[4], int next_player, int64_t out[311]) {
+    fdo::Hand ah[4]; int ar[4];
+    for (int p = 0; p < 4; ++p) { ah[p].bits = assumed_hands[p]; ar[p] = assumed_res[p] == DK_RES_NONE ? (int)fdo::R_NONE : (int)assumed_res[p]; }
+    return guarded([&] { fdo::encode_state_ipi(*(const fdo::State*)h, ah, ar, next_player, out); });
+}

@@ -169,5 +169,93 @@ inline void encode_state_pi(const State& s, int64_t out[311]) {
     out[310] = encode_phase(s.current_phase);
 }
 
+
+// encode_reservation_or_card_or_reservation (var2/encode_reservation_or_card_or_none.rs:48-68): FdoVisibleReservation → token
+inline int64_t encode_visible_reservation_token(int vr) {
+    switch (vr) {
+        case VR_HEALTHY: return 25; case VR_WEDDING: return 26; case VR_DIAMONDS_SOLO: return 27; case VR_HEARTS_SOLO: return 28;
+        case VR_SPADES_SOLO: return 29; case VR_CLUBS_SOLO: return 30; case VR_QUEENS_SOLO: return 31; case VR_JACKS_SOLO: return 32;
+        case VR_TRUMPLESS_SOLO: return 33; case VR_NOT_REVEALED: return 34; case VR_NONE_YET: return 35;
+    }
+    throw std::runtime_error("bad visible reservation");
+}
+// reservation_to_visible_reservation (var1/encode_ipi.rs:29-46)
+inline int reservation_to_visible(int r) {
+    switch (r) {
+        case R_NONE: return VR_NONE_YET; case R_HEALTHY: return VR_HEALTHY; case R_WEDDING: return VR_WEDDING;
+        case R_DIAMONDS_SOLO: return VR_DIAMONDS_SOLO; case R_HEARTS_SOLO: return VR_HEARTS_SOLO; case R_SPADES_SOLO: return VR_SPADES_SOLO;
+        case R_CLUBS_SOLO: return VR_CLUBS_SOLO; case R_QUEENS_SOLO: return VR_QUEENS_SOLO; case R_JACKS_SOLO: return VR_JACKS_SOLO;
+        case R_TRUMPLESS_SOLO: return VR_TRUMPLESS_SOLO;
+    }
+    throw std::runtime_error("bad reservation");
+}
+
+// encode_state_ipi (var1/encode_ipi.rs:48-306) with obs = state.observation_for_current_player(): the imperfect-information layout of
+// the autoregressive hand predictor.  assumed_hands / assumed_reservations are indexed by ABSOLUTE seat (PlayerZeroOrientedArr);
+// assumed_reservations[p] = R_NONE for "no guess yet".
+inline void encode_state_ipi(const State& s, const Hand assumed_hands[4], const int assumed_reservations[4], int next_player_to_chose_card_for,
+                             int64_t out[311]) {
+    const int current_player = s.current_player < 0 ? 0 : s.current_player;                      // :56-58
+    int64_t tok[62], pos[62], ply[62], sub[62], team[62];
+    int n = 0, index = 0;
+    auto push = [&](int64_t p, int64_t t, int64_t pl, int64_t su, int64_t te) {
+        if (n >= 62) throw std::runtime_error("encode_state_ipi: more than 62 slots");
+        pos[n] = p; tok[n] = t; ply[n] = pl; sub[n] = su; team[n] = te; n++;
+    };
+    int visible[4];
+    get_visible_reservations(s.reservations_round, current_player, visible);
+    for (int i = 0; i < 4; ++i) {                                                                // visible reservations in PLAY order (:68-91)
+        int player = player_next(s.reservations_round.starting_player, i);
+        int v = visible[player];
+        if (v == VR_NOT_REVEALED && assumed_reservations[player] != R_NONE) v = reservation_to_visible(assumed_reservations[player]);
+        push(encode_position_or_unknown_int(index), encode_visible_reservation_token(v), encode_player_or_none(player, current_player), 0, 0);
+        index += 1;
+    }
+    for (int t = 0; t < s.n_tricks; ++t)                                                         // played cards (:93-110)
+        for (int k = 0; k < s.tricks[t].len; ++k) {
+            push(encode_position_or_unknown_int(index), encode_card_token(s.tricks[t].cards[k]),
+                 encode_player_or_none(s.tricks[t].player_at(k), current_player), 0, 0);
+            index += 1;
+        }
+    {                                                                                            // the observer's own hand (:113-130)
+        Hand already;
+        int cards[48]; int m = s.hands[current_player].iter(cards);
+        for (int j = 0; j < m; ++j) {
+            push(encode_position_or_unknown_hand(current_player, current_player), encode_card_token(cards[j]), 0,
+                 encode_subposition_card(already.contains(cards[j]) ? 1 : 0), 0);
+            already.add(cards[j]);
+        }
+    }
+    for (int i = 1; i < 4; ++i) {                                                                // the other seats from the observer on (:132-174)
+        int player = player_next(current_player, i);
+        Hand already;
+        int cards[48]; int m = assumed_hands[player].iter(cards);
+        for (int j = 0; j < m; ++j) {
+            push(encode_position_or_unknown_hand(player, current_player), encode_card_token(cards[j]), 0,
+                 encode_subposition_card(already.contains(cards[j]) ? 1 : 0), 0);
+            already.add(cards[j]);
+        }
+        if (s.hands[player].len() < assumed_hands[player].len()) throw std::runtime_error("hand.len() - assumed.len() underflows");   // :158
+        uint32_t diff = s.hands[player].len() - assumed_hands[player].len();
+        for (uint32_t j = 0; j < diff; ++j)                                                      // still unknown cards
+            push(encode_position_or_unknown_hand(player, current_player), encode_card_token(CARD_NONE), 0, 0, 0);
+    }
+    int subposition_index = 0; int64_t last_position = -1;                                       // announcements (:191-215), as in encode_state_pi
+    for (int a = 0; a < s.announcements.n; ++a) {
+        const AnnouncementOccurrence& o = s.announcements.occ[a];
+        if ((int64_t)o.card_index != last_position) { last_position = o.card_index; subposition_index = 0; }
+        if (!s.team_state.has_re_players()) throw std::runtime_error("not possible");
+        int tm = ((s.team_state.re_players >> o.player) & 1) ? 0 : 1;
+        push(encode_position_or_unknown_int(o.card_index), encode_pi_announcement(o.announcement),
+             encode_player_or_none(o.player, current_player), encode_subposition_pos(subposition_index), encode_announcement_team(tm));
+        subposition_index += 1;
+    }
+    if (s.announcements.n > 10) throw std::runtime_error("10 - announcements.len() underflows");      // :217
+    for (int i = 0; i < 10 - s.announcements.n; ++i) push(0, encode_pi_announcement(A_NONE), 0, 0, 0);
+    if (n != 62) throw std::runtime_error("encode_state_ipi: slot count != 62");                        // try_into().unwrap() (:238-242)
+    for (int i = 0; i < 62; ++i) { out[i] = tok[i]; out[62 + i] = pos[i]; out[124 + i] = ply[i]; out[186 + i] = sub[i]; out[248 + i] = team[i]; }
+    out[310] = encode_player_or_none(next_player_to_chose_card_for, current_player);                   // :232, :298-305
+}
+
 }  // namespace fdo
 }  // namespace oracle

@@ -55,10 +55,8 @@ def evaluate(expr):
     raise ValueError(expr)
 
 
-def main():
-    src = open(REF, encoding="utf-8").read()
-    body = src[src.index("fn test_encode_state()"):]
-    lit = body[:body.index("let result = encode_state_pi(")]
+def parse_state(lit):
+    """The FdoState struct literal of a hand-built reference test → plain dict."""
     m = re.search(r"reservations: PlayerOrientedVec::from_full\(FdoPlayer::(\w+), vec!\[(.*?)\]\)", lit, re.S)
     start = PL[m.group(1)]
     reservations = [RES.index(x) for x in re.findall(r"FdoReservation::(\w+)", m.group(2))]
@@ -82,6 +80,13 @@ def main():
         "num_tricks": [int(x) for x in re.search(r"player_num_tricks: PlayerZeroOrientedArr::from_full\(\[(.*?)\]\)", lit).group(1).split(",")],
         "re_players": [PL[p] for p in re.findall(r"FdoPlayer::(\w+)", re.search(r"re_players: FdoPlayerSet::from_vec\(vec!\[(.*?)\]\)", lit).group(1))],
     }
+    return state
+
+
+def main():
+    src = open(REF, encoding="utf-8").read()
+    body = src[src.index("fn test_encode_state()"):]
+    state = parse_state(body[:body.index("let result = encode_state_pi(")])
     expected = [evaluate(x.strip()) for x in re.findall(r"assert_eq_inc!\(result\[i\.\.i\+1\], (.*)\);", body)]
     assert len(expected) == 311, len(expected)
     json.dump({"source": "rs-doko-networks/src/full_doko/var1/encode_pi.rs:237-793", "state": state, "expected": expected}, open(OUT, "w"))

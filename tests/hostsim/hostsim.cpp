@@ -186,3 +186,8 @@ SIM_API uint32_t sim_fdo_flat_mc(const dk_state* root, uint64_t seed, uint64_t u
 SIM_API uint64_t sim_sp_az_allowed(const dk_state* s, uint64_t az_epoch) { return dk::sp_az_allowed(*s, az_epoch); }
 SIM_API float sim_sp_keep_draw(uint32_t word) { return dk::sp_keep_draw(word); }
 SIM_API float sim_sp_value_target(const dk_state* s, uint32_t player, uint32_t k) { return dk::sp_value_target(*s, player, k); }
+
+SIM_API uint32_t sim_encode_ipi(const dk_state* s, const uint64_t assumed[4], const uint8_t assumed_res[4], uint32_t next_player, int64_t* out) {
+    RowOut o{out};
+    return dk::fdo_encode_ipi(*s, assumed, assumed_res, next_player, o);
+}

@@ -40,6 +40,8 @@ def load():
         L.sim_sp_keep_draw.argtypes = [u32]
         L.sim_sp_value_target.restype = C.c_float
         L.sim_sp_value_target.argtypes = [vp, u32, u32]
+        L.sim_encode_ipi.restype = u32
+        L.sim_encode_ipi.argtypes = [vp, vp, vp, u32, vp]
         L.sim_fuse.restype = u32
         L.sim_fuse.argtypes = [i32, vp, vp, u32, u64, vp]
         L.sim_root_stats.argtypes = [vp, vp, u32, u64, vp]

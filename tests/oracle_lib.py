@@ -138,6 +138,7 @@ def load():
     L.orc_selfplay_uniform.argtypes = [u64, u64, u64, C.c_float, u32, i32, vp, vp, vp, vp, vp, vp, vp, vp]
     L.orc_fdo_az_allowed.restype = u64
     L.orc_fdo_az_allowed.argtypes = [vp, i32, u64]
+    L.orc_fdo_encode_ipi.argtypes = [vp, vp, vp, i32, vp]
     L.orc_fuse_max_n.argtypes = [vp, u64, u64]
     L.orc_fuse_average.argtypes = [vp, u64]
     L.orc_fdo_flat_mc_philox.argtypes = [vp, u64, u64, u32, u32, u32, vp, vp]
@@ -218,6 +219,13 @@ class Fdo:
         if self.L.orc_fdo_encode_pi(self.h, o):
             raise RuntimeError(self.L.orc_last_error().decode())
         return np.array(o, dtype=np.int64)
+
+    def encode_ipi(self, assumed_hands, assumed_res, next_player):
+        out = (C.c_int64 * 311)()
+        rc = self.L.orc_fdo_encode_ipi(self.h, (C.c_uint64 * 4)(*assumed_hands), (C.c_uint8 * 4)(*assumed_res), next_player, out)
+        if rc:
+            raise RuntimeError(self.L.orc_last_error().decode())
+        return np.array(out, dtype=np.int64)
 
     def export(self):
         rec = np.zeros(1, dtype=DK_STATE_DTYPE)

@@ -18,8 +18,8 @@ from oracle_lib import DK_STATE_DTYPE, Doko, Fdo, card_id, hand_from_cards
 G = os.path.join(os.path.dirname(__file__), "golden")
 
 
-def pi_record():
-    v = json.load(open(os.path.join(G, "encode_pi_vector.json")))
+def pi_record(path=None):
+    v = json.load(open(path or os.path.join(G, "encode_pi_vector.json")))
     st = v["state"]
     rec = np.zeros(1, dtype=DK_STATE_DTYPE)
     r = rec[0]
