@@ -338,6 +338,36 @@ DK_API dk_status dk_sp_finalize(dk_selfplay* sp, const dk_state* states /*[dev]*
 /* Synchronises the stream: rows recorded so far, rows dropped for lack of capacity, rows whose game was unfinished at the last finalize. */
 DK_API dk_status dk_sp_counts(dk_selfplay* sp, uint64_t* rows, uint64_t* dropped, uint64_t* unfinished, dk_stream stream);
 
+/* The reference's on-disk experience record for rows of the experience buffers: DBRecord {state, value, policy} through
+ * bincode::serialize (rs-doko-alpha-zero/src/alpha_zero/net/experience_replay_buffer3.rs:11-20,94-121; bincode 1.3.3, heapless 0.8.0):
+ *   u64 311 | 311 x i64 | u64 4 | 4 x f32 | u64 39 | 39 x f32, little endian, DK_REPLAY_RECORD_BYTES each, back to back in `out`
+ * (4-byte aligned).  One D2H copy of `out` then holds exactly the values `append_slice` inserts into sled (the random u64 keys and the
+ * store itself stay on the host side). */
+#define DK_REPLAY_RECORD_BYTES 2684u
+DK_API dk_status dk_pack_replay_records(dk_ctx* ctx, size_t n_rows, const int64_t* states /*[dev] n_rows*311*/, const float* value /*[dev] n_rows*4*/,
+                                        const float* policy /*[dev] n_rows*39*/, uint8_t* out /*[dev] n_rows*DK_REPLAY_RECORD_BYTES*/, dk_stream stream);
+
+/* ---- UCT search ----------------------------------------------------------------------------
+ * CachedMCTS::monte_carlo_tree_search (rs-doko-mcts/src/mcts/mcts.rs:160-232, node.rs:138-278) over McFullDokoEnvState
+ * (rs-doko-mcts/src/env/envs/env_state_full_doko.rs:62-220) as EvFullDokoMCTSPolicy runs it (rs-doko-evaluator/src/full_doko/policy/
+ * mcts_policy.rs:76-118): min-max-normalised Q + c*sqrt(ln N / n) selection, expand_single with a random unexpanded action, a
+ * _no_announcement random_rollout from the new node, backpropagation of result[parent.current_player].
+ * One tree per (root i, d), d < trees_per_root; determinize != 0 first replaces root i by its determinization first_sub + d (the
+ * dk_determinize sample) — trees_per_root is then DefaultImpiPolicy's num_samples and visits_out feeds dk_fuse directly; with
+ * determinize == 0 the given states are searched as they are (perfect information, mcts_pi_policy).  Iteration `it` of a tree uses
+ * the Philox unit (first_id + i, (first_sub + d) * iterations + it): expansion pick = word 0 of site 9, rollout draws at their
+ * state-derived ordinals.  Selection is bit-identical to the f64 arithmetic of the reference (ln from the host libm).
+ *   visits_out[t*39 + a], values_out[t*39 + a] = win_score / visits as f32 (0 for actions without a child), t = i*trees_per_root + d
+ *   action_out[t] = move with the most visits (last among equals in child order), DK_ACTION_NONE if the root has no child
+ *   status_out[t] != 0: determinization dead end (row = 0).
+ * workspace: caller-owned device memory, 16-byte aligned, >= dk_uct_workspace_bytes(n_roots * trees_per_root, iterations)
+ * (208 bytes per node, iterations + 1 nodes per tree). */
+DK_API size_t dk_uct_workspace_bytes(size_t n_trees, size_t iterations);
+DK_API dk_status dk_uct_search(dk_ctx* ctx, size_t n_roots, size_t trees_per_root, int determinize, size_t iterations, float uct_exploration_constant,
+                               const dk_state* states /*[dev]*/, const dk_rng* rng, void* workspace /*[dev]*/, size_t workspace_bytes,
+                               uint32_t* visits_out /*[dev] or NULL*/, float* values_out /*[dev] or NULL*/, uint8_t* action_out /*[dev] or NULL*/,
+                               uint8_t* status_out /*[dev] or NULL*/, dk_stream stream);
+
 /* ---- multi-GPU root statistics (the only exchange step) --------------------------------------
  * replaces the per-determinization fuse of PolicyFusion* (rs-doko-py-bridge/src/compare_impi/policy_fusion.rs:18-123):
  * integer sums over ranks, order-independent and bit-reproducible.  NCCL is loaded lazily (dlopen). */

@@ -13,6 +13,7 @@ N_ACTIONS = 39          # FdoAction::COUNT
 ACTION_NONE = 0xFF
 FUSE_MAX_N, FUSE_AVERAGE = 0, 1
 ROOT_STATS = 80
+REPLAY_RECORD_BYTES = 2684
 DK_LAYOUT_DO110, DK_LAYOUT_DO114, DK_LAYOUT_FDO_PI311 = 0, 1, 2
 OBS_LEN = {DK_LAYOUT_DO110: 110, DK_LAYOUT_DO114: 114, DK_LAYOUT_FDO_PI311: 311}
 STATUS = {0: "DK_OK", 1: "DK_ERR_INVALID_ARGUMENT", 2: "DK_ERR_CUDA", 3: "DK_ERR_NO_DEVICE", 4: "DK_ERR_NCCL", 5: "DK_ERR_UNSUPPORTED"}
@@ -57,6 +58,8 @@ def load_library():
     L.dk_destroy.argtypes = [vp]
     L.dk_device_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(sz)]
     L.dk_synchronize.argtypes = [vp, vp]
+    L.dk_uct_workspace_bytes.restype = sz
+    L.dk_uct_workspace_bytes.argtypes = [sz, sz]
     L.dk_launch_count.restype = u64
     L.dk_launch_count.argtypes = [vp]
     L.dk_playout.argtypes = [vp, i32, u32, sz, vp, C.POINTER(DkRng), vp, vp, vp]
@@ -87,6 +90,8 @@ def load_library():
         ("dk_sp_end_turn", [vp, vp, vp, vp, vp, vp]),
         ("dk_sp_finalize", [vp, vp, vp]),
         ("dk_sp_counts", [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64), vp]),
+        ("dk_uct_search", [vp, sz, sz, i32, sz, C.c_float, vp, C.POINTER(DkRng), vp, sz, vp, vp, vp, vp, vp]),
+        ("dk_pack_replay_records", [vp, sz, vp, vp, vp, vp, vp]),
         ("dk_comm_unique_id", [vp, vp]),
         ("dk_comm_init", [vp, i32, i32, vp]),
         ("dk_comm_destroy", [vp]),
@@ -353,6 +358,33 @@ class DokoCuda:
         self._check(self.L.dk_pimc_pick(self.ctx, strategy, n, _ptr(stats), _ptr(allowed), _ptr(action),
                                         stream if stream is not None else self._stream()), "dk_pimc_pick")
         return action
+
+    def uct_search(self, states, iterations, uct_c, rng, trees_per_root=1, determinize=False, workspace=None, stream=None):
+        """One UCT tree per (state, d): (visits int32 [n,T,39], values float32 [n,T,39], action uint8 [n,T], status uint8 [n,T])."""
+        import torch
+
+        n = states.shape[0]
+        need = self.L.dk_uct_workspace_bytes(n * trees_per_root, iterations)
+        if workspace is None or workspace.numel() * workspace.element_size() < need:
+            workspace = torch.empty(((need + 15) // 16 * 2,), dtype=torch.int64, device=self._dev())
+        visits = torch.empty((n, trees_per_root, N_ACTIONS), dtype=torch.int32, device=self._dev())
+        values = torch.empty((n, trees_per_root, N_ACTIONS), dtype=torch.float32, device=self._dev())
+        action = torch.empty((n, trees_per_root), dtype=torch.uint8, device=self._dev())
+        status = torch.empty((n, trees_per_root), dtype=torch.uint8, device=self._dev())
+        self._check(self.L.dk_uct_search(self.ctx, n, trees_per_root, int(determinize), iterations, uct_c, _ptr(states), C.byref(rng), _ptr(workspace),
+                                         workspace.numel() * workspace.element_size(), _ptr(visits), _ptr(values), _ptr(action), _ptr(status),
+                                         stream if stream is not None else self._stream()), "dk_uct_search")
+        return visits, values, action, status
+
+    def pack_replay_records(self, states, value, policy, out=None, stream=None):
+        """bincode DBRecord bytes (uint8 [n, 2684]) of experience rows — the values the reference's replay buffer stores."""
+        import torch
+
+        n = states.shape[0]
+        out = torch.empty((n, REPLAY_RECORD_BYTES), dtype=torch.uint8, device=self._dev()) if out is None else out
+        self._check(self.L.dk_pack_replay_records(self.ctx, n, _ptr(states), _ptr(value), _ptr(policy), _ptr(out),
+                                                  stream if stream is not None else self._stream()), "dk_pack_replay_records")
+        return out
 
     def self_play(self, max_games, capacity):
         """Lock-step AlphaZero self-play driver with its experience buffers."""

@@ -28,6 +28,9 @@ struct dk_ctx {
     cudaStream_t copy_stream = nullptr;
     std::vector<cudaEvent_t> events;
     // NCCL (loaded lazily)
+    // ln(N) table of the UCT search (host libm values, see uct.cuh)
+    double* d_ln_table = nullptr;
+    size_t ln_table_len = 0;
     void* nccl_lib = nullptr;
     void* nccl_comm = nullptr;
     int nccl_ranks = 0, nccl_rank = 0;
@@ -448,6 +451,50 @@ dk_status dk_sp_counts(dk_selfplay* sp, uint64_t* rows, uint64_t* dropped, uint6
     if (dropped) *dropped = h[1];
     if (unfinished) *unfinished = h[2];
     return DK_OK;
+}
+
+dk_status dk_pack_replay_records(dk_ctx* ctx, size_t n_rows, const int64_t* states, const float* value, const float* policy, uint8_t* out, dk_stream stream) {
+    if (!ctx || !states || !value || !policy || !out || ((uintptr_t)out & 3u)) return DK_ERR_INVALID_ARGUMENT;
+    if (n_rows == 0) return DK_OK;
+    DK_CUDA(ctx, cudaSetDevice(ctx->device));
+    unsigned long long total = (unsigned long long)n_rows * dk::REPLAY_WORDS;
+    unsigned long long want = (total + 255ull) / 256ull, cap = (unsigned long long)ctx->sm_count * 32ull;
+    unsigned grid = (unsigned)(want < cap ? want : cap);
+    dk::pack_replay_records_kernel<<<grid, 256, 0, pick_stream(ctx, stream)>>>((unsigned long long)n_rows, (const long long*)states, value, policy, (uint32_t*)out);
+    return check_launch(ctx, "pack_replay_records_kernel");
+}
+
+// ---- UCT search -------------------------------------------------------------------------------------------
+size_t dk_uct_workspace_bytes(size_t n_trees, size_t iterations) { return n_trees * (iterations + 1) * sizeof(dk::UctNode); }
+
+dk_status dk_uct_search(dk_ctx* ctx, size_t n_roots, size_t trees_per_root, int determinize, size_t iterations, float uct_exploration_constant,
+                        const dk_state* states, const dk_rng* rng, void* workspace, size_t workspace_bytes, uint32_t* visits_out, float* values_out,
+                        uint8_t* action_out, uint8_t* status_out, dk_stream stream) {
+    if (!ctx || !states || !rng || !workspace || trees_per_root == 0 || ((uintptr_t)workspace & 15u)) return DK_ERR_INVALID_ARGUMENT;
+    if (n_roots == 0) return DK_OK;
+    const size_t n_trees = n_roots * trees_per_root;
+    if (iterations == 0 || iterations > 0x7FFFFFFFull || n_trees > 0x7FFFFFFFull * dk::UCT_THREADS / 2 ||
+        ((uint64_t)rng->first_sub + trees_per_root) * iterations > 0xFFFFFFFFull || workspace_bytes < dk_uct_workspace_bytes(n_trees, iterations))
+        return DK_ERR_INVALID_ARGUMENT;
+    DK_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = pick_stream(ctx, stream);
+    if (ctx->ln_table_len < iterations + 1) {
+        // ln via the HOST libm (what Rust's f64::ln calls), so that selection is bit-identical to the CPU reference path
+        std::vector<double> t(iterations + 1);
+        t[0] = 0.0;
+        for (size_t n = 1; n <= iterations; ++n) t[n] = std::log((double)n);
+        DK_CUDA(ctx, cudaStreamSynchronize(s));
+        if (ctx->d_ln_table) cudaFree(ctx->d_ln_table);
+        ctx->d_ln_table = nullptr; ctx->ln_table_len = 0;
+        DK_CUDA(ctx, cudaMalloc(&ctx->d_ln_table, t.size() * sizeof(double)));
+        DK_CUDA(ctx, cudaMemcpy(ctx->d_ln_table, t.data(), t.size() * sizeof(double), cudaMemcpyHostToDevice));
+        ctx->ln_table_len = t.size();
+    }
+    unsigned grid = (unsigned)((n_trees + dk::UCT_THREADS - 1) / dk::UCT_THREADS);
+    dk::fdo_uct_kernel<<<grid, dk::UCT_THREADS, 0, s>>>(to_params(rng), (uint64_t)n_trees, (uint32_t)trees_per_root, (uint32_t)iterations,
+                                                        (double)uct_exploration_constant, ctx->d_ln_table, determinize, states, (dk::UctNode*)workspace,
+                                                        visits_out, values_out, action_out, status_out);
+    return check_launch(ctx, "fdo_uct_kernel");
 }
 
 // ---- NCCL (dlopen; the only exchange step of the path) ---------------------------------------------------------------------

@@ -70,7 +70,7 @@ DK_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) {  // low 32 bits
 //   mapped onto n choices by idx = mulhi(word, n); announcement decisions take one BIT each (fdo_rules.cuh AnnStream).
 enum Site : uint32_t {
     SITE_DEAL = 0, SITE_RESERVATION = 1, SITE_ANNOUNCEMENT = 2, SITE_CARD = 3,
-    SITE_MATCH_CARD = 4, SITE_MATCH_RESERVATION = 5, SITE_ASSIGN = 6, SITE_STEP = 7, SITE_KEEP = 8
+    SITE_MATCH_CARD = 4, SITE_MATCH_RESERVATION = 5, SITE_ASSIGN = 6, SITE_STEP = 7, SITE_KEEP = 8, SITE_EXPAND = 9
 };
 
 struct U4 { uint32_t x, y, z, w; };
@@ -127,6 +127,13 @@ DK_HD uint32_t select_lsb24(uint32_t x, uint32_t k) {
 }
 // The reference's random pick: index idx counted from the MOST significant set bit.
 DK_HD uint32_t pick_msb_rank24(uint32_t mask, uint32_t idx) { return select_lsb24(mask, popc(mask) - 1u - idx); }
+
+// The reference's random pick on a 39-bit action mask: index from the most significant set bit (bit_flag.rs:86-94,104-171).
+DK_HD uint32_t pick_msb_rank64(uint64_t mask, uint32_t idx) {
+    uint32_t lo = (uint32_t)mask, hi = (uint32_t)(mask >> 32);
+    uint32_t k = popc(lo) + popc(hi) - 1u - idx, cl = popc(lo);
+    return k < cl ? select_lsb(lo, k) : 32u + select_lsb(hi, k - cl);
+}
 
 // ---- card arithmetic ------------------------------------------------------------------------------------
 // card id c = suit*6 + rank; suits ♦0 ♥1 ♣2 ♠3; ranks 9,10,J,Q,K,A = 0..5 (rs-full-doko/src/card/cards.rs:7-36)

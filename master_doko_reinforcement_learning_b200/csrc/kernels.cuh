@@ -290,12 +290,6 @@ encode_kernel(uint64_t n, const dk_state* __restrict__ states, int64_t* __restri
     write_rows(tok, LAYOUT == DK_LAYOUT_DO114 ? 114 : 110, first, n, out, row_stride);
 }
 
-// The reference's random pick on a 39-bit mask: index from the most significant set bit (bit_flag.rs:86-94,104-171).
-__device__ __forceinline__ uint32_t pick_msb_rank64(uint64_t mask, uint32_t idx) {
-    uint32_t lo = (uint32_t)mask, hi = (uint32_t)(mask >> 32);
-    uint32_t k = popc(lo) + popc(hi) - 1u - idx, cl = popc(lo);
-    return k < cl ? select_lsb(lo, k) : 32u + select_lsb(hi, k - cl);
-}
 // K5: one lock-step self-play env step + observation: legal mask → one draw (SITE_STEP word 0, unit = game id,
 // epoch = caller's step counter) → play_action [→ skip forced moves] → encode_state_pi of the new state.
 // Algorithmic HBM bytes per game: 128 read + 128 written + 2488 written.

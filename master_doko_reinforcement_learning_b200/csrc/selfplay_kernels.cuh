@@ -2,6 +2,7 @@
 #pragma once
 #include "kernels.cuh"
 #include "selfplay.cuh"
+#include "uct.cuh"
 
 namespace dk {
 
@@ -203,6 +204,73 @@ sp_finalize_kernel(const unsigned long long* __restrict__ count, const dk_state*
         v.w = (float)(int8_t)(packed >> (8u * ((player + 3u) & 3u))) / 8.0f;
         reinterpret_cast<float4*>(buf.value)[r] = v;
     }
+}
+
+// The reference's on-disk experience record (DBRecord through bincode 1.3.3, experience_replay_buffer3.rs:11-20,94-121):
+//   u64 311 | 311 x i64 | u64 4 | 4 x f32 | u64 39 | 39 x f32 = 2684 bytes = 671 little-endian 32-bit words, records back to back.
+// Pure byte shuffling: one thread per output word, consecutive threads write consecutive words.
+constexpr uint32_t REPLAY_WORDS = 671u;
+__global__ void __launch_bounds__(256)
+pack_replay_records_kernel(unsigned long long n_rows, const long long* __restrict__ states, const float* __restrict__ value,
+                           const float* __restrict__ policy, uint32_t* __restrict__ out) {
+    const unsigned long long total = n_rows * REPLAY_WORDS;
+    for (unsigned long long g = (unsigned long long)blockIdx.x * 256u + threadIdx.x; g < total; g += (unsigned long long)gridDim.x * 256u) {
+        const unsigned long long r = g / REPLAY_WORDS;
+        const uint32_t w = (uint32_t)(g - r * REPLAY_WORDS);
+        uint32_t v;
+        if (w < 2u) v = w == 0u ? 311u : 0u;
+        else if (w < 624u) {
+            const uint32_t e = (w - 2u) >> 1;
+            const unsigned long long x = (unsigned long long)__ldg(states + r * 311u + e);
+            v = (w & 1u) ? (uint32_t)(x >> 32) : (uint32_t)x;           // w - 2 even ⇔ w even ⇒ low half
+        } else if (w < 626u) v = w == 624u ? 4u : 0u;
+        else if (w < 630u) v = __float_as_uint(__ldg(value + r * 4u + (w - 626u)));
+        else if (w < 632u) v = w == 630u ? 39u : 0u;
+        else v = __float_as_uint(__ldg(policy + r * 39u + (w - 632u)));
+        out[g] = v;
+    }
+}
+
+// N3: one UCT tree per thread.  Tree t = root (t / trees_per_root), sub-index d = t % trees_per_root; with `determinize` the root state
+// is first replaced by determinization (first_sub + d) of the info-state (the dk_determinize stream).  Iteration `it` runs on the
+// Philox unit (first_id + root, (first_sub + d) * iterations + it).
+constexpr int UCT_THREADS = 64;
+__global__ void __launch_bounds__(UCT_THREADS)
+fdo_uct_kernel(RngParams rp, uint64_t n_trees, uint32_t trees_per_root, uint32_t iterations, double c, const double* __restrict__ ln_table, int determinize,
+               const dk_state* __restrict__ states, UctNode* __restrict__ pool_base, uint32_t* __restrict__ visits_out, float* __restrict__ values_out,
+               uint8_t* __restrict__ action_out, uint8_t* __restrict__ status_out) {
+    __shared__ uint32_t lut[24];
+    stage_card_lut(lut);
+    const uint64_t t = (uint64_t)blockIdx.x * UCT_THREADS + threadIdx.x;
+    if (t >= n_trees) return;
+    const uint64_t root = t / trees_per_root;
+    const uint32_t sub = rp.first_sub + (uint32_t)(t - root * trees_per_root);
+    UctNode* pool = pool_base + t * ((uint64_t)iterations + 1ull);
+    alignas(16) dk_state s;
+    load_state(states + root, s);
+    uint32_t status = 0;
+    if (determinize && st_phase(s) != DK_PHASE_FINISHED) {
+        MatchPrep prep;
+        fdo_match_prepare(s, prep);
+        uint64_t h[4];
+        uint8_t res[4];
+        status = fdo_match_sample(prep, make_key(rp, root, sub, true), h, res);
+        if (status == 0u) fdo_state_with_hands_and_reservations(s, h, res);
+    }
+    uint32_t best = 0xFFu;
+    if (visits_out) for (uint32_t a = 0; a < N_ACTIONS; ++a) visits_out[t * N_ACTIONS + a] = 0u;
+    if (values_out) for (uint32_t a = 0; a < N_ACTIONS; ++a) values_out[t * N_ACTIONS + a] = 0.0f;
+    if (status == 0u) {
+        uct_init_node(pool[0], s, UCT_NONE, 63u, true);
+        uint32_t n_nodes = 1;
+        for (uint32_t it = 0; it < iterations; ++it) {
+            RngKey key = make_key(rp, root, sub * iterations + it, true);
+            if (uct_iteration(pool, n_nodes, key, c, ln_table, lut)) { status = 3u; break; }
+        }
+        best = uct_moves(pool, visits_out ? visits_out + t * N_ACTIONS : (uint32_t*)nullptr, values_out ? values_out + t * N_ACTIONS : (float*)nullptr);
+    }
+    if (action_out) action_out[t] = (uint8_t)best;
+    if (status_out) status_out[t] = (uint8_t)status;
 }
 
 }  // namespace dk

@@ -16,7 +16,9 @@
 #include "encode.hpp"
 #include "fdo.hpp"
 #include "matching.hpp"
+#include "mcts.hpp"
 #include "pimc.hpp"
+#include "replay.hpp"
 #include "rng.hpp"
 #include "selfplay.hpp"
 
@@ -625,3 +627,34 @@ ORC_API int orc_fdo_encode_ipi(const void* h, const uint64_t assumed_hands[4], c
     for (int p = 0; p < 4; ++p) { ah[p].bits = assumed_hands[p]; ar[p] = assumed_res[p] == DK_RES_NONE ? (int)fdo::R_NONE : (int)assumed_res[p]; }
     return guarded([&] { fdo::encode_state_ipi(*(const fdo::State*)h, ah, ar, next_player, out); });
 }
+
+// bincode DBRecord bytes (oracle/replay.hpp) for n rows
+ORC_API void orc_replay_records(uint64_t n, const int64_t* states, const float* value, const float* policy, uint8_t* out) {
+    for (uint64_t r = 0; r < n; ++r) replay::serialize_record(states + r * 311, value + r * 4, policy + r * 39, out + r * replay::RECORD_BYTES);
+}
+
+// ---- UCT search --------------------------------------------------------------------------------------
+// Tree (unit, sub) over `h` [after card_matching determinization `sub` when determinize != 0].  Returns the determinization status
+// (0 ok); *action_out = move with the most visits (-1 when the root has no children).
+ORC_API int orc_fdo_uct_search_philox(const void* h, uint64_t seed, uint64_t unit, uint32_t sub, uint32_t epoch, int determinize, uint32_t iterations,
+                                      float uct_c, uint32_t visits[39], float values[39], int32_t* action_out) {
+    fdo::State s = *(const fdo::State*)h;
+    int status = 0;
+    for (int a = 0; a < 39; ++a) { visits[a] = 0; values[a] = 0.0f; }
+    if (action_out) *action_out = -1;
+    int rc = guarded([&] {
+        if (determinize && s.current_phase != fdo::PH_FINISHED) {
+            PhiloxStream rm(seed, (uint32_t)unit, sub, epoch);
+            fdo::Hand oh[4]; int ores[4];
+            status = fdo::card_matching(s, rm, oh, ores);
+            if (status == 0) s = fdo::with_hands_and_reservations(s, oh, ores);
+        }
+        if (status == 0) {
+            std::vector<mcts::Move> moves = mcts::search(s, (double)uct_c, iterations, seed, unit, sub, epoch);
+            int best = mcts::moves_to_arrays(moves, visits, values);
+            if (action_out) *action_out = best;
+        }
+    });
+    return rc ? -1 : status;
+}
+ORC_API uint64_t orc_fdo_mc_allowed(const void* h, int first_expansion) { return mcts::allowed_actions(*(const fdo::State*)h, first_expansion != 0); }

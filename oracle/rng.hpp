@@ -43,7 +43,8 @@ enum Site : uint32_t {
     SITE_ASSIGN = 6,       // rs-doko-assignment random card / random player (assignment.rs:419-445)
     SITE_STEP = 7,         // lock-step env step (config 5): one decision per call, word 0
     SITE_KEEP = 8,         // self_play's `rng.gen::<f32>() < probability_of_keeping_experience` (self_play.rs:88); word 0 of the turn's epoch
-    SITE_COUNT = 9,
+    SITE_EXPAND = 9,       // MCTS expand_single's `unexpanded_actions.random(rng)` (rs-doko-mcts/src/mcts/mcts.rs:78-80); word 0 of the iteration's unit
+    SITE_COUNT = 10,
 };
 
 // Abstract source.  `below(site, n)` returns a value in [0, n).

@@ -112,6 +112,16 @@ def main():
     t = timed(n2, iters=3)
     out["N2_pimc_decision_1024x64x32"] = {"sec": t, "decisions_per_s": n_roots / t, "mean_legal_actions": n_legal,
                                           "rollouts_per_s": n_roots * n_det * R2 * n_legal / t}
+    # N3 UCT search: 2048 roots x 8 determinized trees x 256 iterations (mcts_cap_* per-sample search)
+    n_uct, T, iters_uct = int(2048 * a.scale), 8, 256
+    uct_roots = sub[:n_uct]
+    need = dk.L.dk_uct_workspace_bytes(n_uct * T, iters_uct)
+    ws = torch.empty((need // 8 + 2,), dtype=torch.int64, device="cuda")
+    t = timed(lambda: dk.uct_search(uct_roots, iters_uct, 1.4, dk.rng(SEED, 0, 13), trees_per_root=T, determinize=True, workspace=ws), iters=3)
+    out["N3_uct_search_2048x8x256"] = {"sec": t, "trees": n_uct * T, "iterations_per_s": n_uct * T * iters_uct / t, "decisions_per_s": n_uct / t,
+                                       "workspace_GB": need / 1e9}
+    del ws
+
     # N1 self-play driver: 2^20 games in lock-step, one full turn = plan + scan + encode-into-row + stand-in search + apply
     n_sp = int((1 << 20) * a.scale)
     sp_states = dk.new_games(pkg.DK_FDO, n_sp, dk.rng(SEED, 0, 0))

@@ -16,6 +16,9 @@
 #include "../../master_doko_reinforcement_learning_b200/csrc/assignment.cuh"
 #include "../../master_doko_reinforcement_learning_b200/csrc/pimc.cuh"
 #include "../../master_doko_reinforcement_learning_b200/csrc/selfplay.cuh"
+#include "../../master_doko_reinforcement_learning_b200/csrc/uct.cuh"
+#include <cmath>
+#include <vector>
 
 #define SIM_API extern "C" __attribute__((visibility("default")))
 
@@ -191,3 +194,33 @@ SIM_API uint32_t sim_encode_ipi(const dk_state* s, const uint64_t assumed[4], co
     RowOut o{out};
     return dk::fdo_encode_ipi(*s, assumed, assumed_res, next_player, o);
 }
+
+// ---- UCT search (uct.cuh; the per-thread body of fdo_uct_kernel) -------------------------------------------------------------------
+SIM_API uint32_t sim_fdo_uct_search(const dk_state* root, uint64_t seed, uint64_t unit, uint32_t sub, uint32_t epoch, int determinize, uint32_t iterations,
+                                    float uct_c, uint32_t visits[39], float values[39], int32_t* action_out) {
+    for (int a = 0; a < 39; ++a) { visits[a] = 0; values[a] = 0.0f; }
+    *action_out = -1;
+    dk_state s = *root;
+    dk::RngKey key = make_key(seed, unit, epoch);
+    if (determinize && dk::st_phase(s) != DK_PHASE_FINISHED) {
+        dk::MatchPrep prep; dk::fdo_match_prepare(s, prep);
+        key.unit_hi = sub;
+        uint64_t hands[4]; uint8_t res[4];
+        uint32_t status = dk::fdo_match_sample(prep, key, hands, res);
+        if (status) return status;
+        dk::fdo_state_with_hands_and_reservations(s, hands, res);
+    }
+    std::vector<double> ln_table(iterations + 1, 0.0);
+    for (uint32_t n = 1; n <= iterations; ++n) ln_table[n] = std::log((double)n);
+    std::vector<dk::UctNode> pool(iterations + 1);
+    dk::uct_init_node(pool[0], s, dk::UCT_NONE, 63u, true);
+    uint32_t n_nodes = 1;
+    for (uint32_t it = 0; it < iterations; ++it) {
+        key.unit_hi = sub * iterations + it;
+        if (dk::uct_iteration(pool.data(), n_nodes, key, (double)uct_c, ln_table.data(), card_lut())) return 3;
+    }
+    uint32_t best = dk::uct_moves(pool.data(), visits, values);
+    *action_out = best == 0xFFu ? -1 : (int32_t)best;
+    return 0;
+}
+SIM_API uint64_t sim_uct_allowed(const dk_state* s, int first) { return dk::uct_allowed(*s, first != 0); }

@@ -42,6 +42,10 @@ def load():
         L.sim_sp_value_target.argtypes = [vp, u32, u32]
         L.sim_encode_ipi.restype = u32
         L.sim_encode_ipi.argtypes = [vp, vp, vp, u32, vp]
+        L.sim_fdo_uct_search.restype = u32
+        L.sim_fdo_uct_search.argtypes = [vp, u64, u64, u32, u32, i32, u32, C.c_float, vp, vp, vp]
+        L.sim_uct_allowed.restype = u64
+        L.sim_uct_allowed.argtypes = [vp, i32]
         L.sim_fuse.restype = u32
         L.sim_fuse.argtypes = [i32, vp, vp, u32, u64, vp]
         L.sim_root_stats.argtypes = [vp, vp, u32, u64, vp]

@@ -139,6 +139,10 @@ def load():
     L.orc_fdo_az_allowed.restype = u64
     L.orc_fdo_az_allowed.argtypes = [vp, i32, u64]
     L.orc_fdo_encode_ipi.argtypes = [vp, vp, vp, i32, vp]
+    L.orc_replay_records.argtypes = [u64, vp, vp, vp, vp]
+    L.orc_fdo_uct_search_philox.argtypes = [vp, u64, u64, u32, u32, i32, u32, C.c_float, vp, vp, vp]
+    L.orc_fdo_mc_allowed.restype = u64
+    L.orc_fdo_mc_allowed.argtypes = [vp, i32]
     L.orc_fuse_max_n.argtypes = [vp, u64, u64]
     L.orc_fuse_average.argtypes = [vp, u64]
     L.orc_fdo_flat_mc_philox.argtypes = [vp, u64, u64, u32, u32, u32, vp, vp]
@@ -252,6 +256,18 @@ class Fdo:
         steps = C.c_uint32()
         st = self.L.orc_fdo_leaf_rollout_philox(self.h, seed, unit, rollout, epoch, int(determinize), pts, C.byref(steps))
         return st, list(pts), steps.value
+
+    def uct_search(self, seed, unit, sub, iterations, uct_c, epoch=0, determinize=False):
+        """(status, visits[39] u32, values[39] f32, action) of oracle/mcts.hpp search."""
+        visits = np.zeros(39, dtype=np.uint32)
+        values = np.zeros(39, dtype=np.float32)
+        action = C.c_int32()
+        vp = C.c_void_p
+        st = self.L.orc_fdo_uct_search_philox(self.h, seed, unit, sub, epoch, int(determinize), iterations, uct_c, visits.ctypes.data_as(vp),
+                                              values.ctypes.data_as(vp), C.byref(action))
+        if st < 0:
+            raise RuntimeError(self.L.orc_last_error().decode())
+        return st, visits, values, action.value
 
     def flat_mc(self, seed, unit, det, n_rollouts, epoch=0):
         """(status, visits[39], value_sum[39]) of oracle/pimc.hpp flat_mc."""
@@ -367,3 +383,14 @@ def selfplay_uniform(L, seed, unit, az_epoch, keep_prob, first_epoch=0, max_rows
     assert 0 <= n <= max_rows, L.orc_last_error()
     return {"states": st[:n], "policy": po[:n], "value": va[:n], "player": pl[:n], "turn": tu[:n], "forced": fo[:n], "turns": turns.value,
             "points": list(pts)}
+
+
+def replay_records(L, states, value, policy):
+    """bincode DBRecord bytes [n, 2684] (oracle/replay.hpp)."""
+    st = np.ascontiguousarray(states, dtype=np.int64)
+    va = np.ascontiguousarray(value, dtype=np.float32)
+    po = np.ascontiguousarray(policy, dtype=np.float32)
+    out = np.zeros((st.shape[0], 2684), dtype=np.uint8)
+    vp = C.c_void_p
+    L.orc_replay_records(st.shape[0], st.ctypes.data_as(vp), va.ctypes.data_as(vp), po.ctypes.data_as(vp), out.ctypes.data_as(vp))
+    return out
