@@ -128,6 +128,26 @@ DK_HD uint32_t select_lsb24(uint32_t x, uint32_t k) {
 // The reference's random pick: index idx counted from the MOST significant set bit.
 DK_HD uint32_t pick_msb_rank24(uint32_t mask, uint32_t idx) { return select_lsb24(mask, popc(mask) - 1u - idx); }
 
+// Rank select with a 64-entry table for the last level (the lock-step card loop's version: two popc levels 12 / 6, then one
+// shared-memory lookup on the idle LSU pipe instead of three more compare/select levels on the saturated ALU pipe).
+// Table word b (b = 6-bit mask): bits 3j..3j+2 = position of the j-th set bit of b counted from the LSB.
+DK_HD uint32_t rank_lut6_entry(uint32_t b) {
+    uint32_t e = 0, j = 0;
+    for (uint32_t pos = 0; pos < 6u; ++pos) if ((b >> pos) & 1u) { e |= pos << (3u * j); j++; }
+    return e;
+}
+constexpr uint32_t CARD_LUT_WORDS = 96u;     // [0,24) card attributes (card_lut_entry) | [32,96) rank_lut6_entry
+constexpr uint32_t RANK_LUT_BASE = 32u;
+DK_HD uint32_t select_lsb24_lut(uint32_t x, uint32_t k, const uint32_t* __restrict__ lut) {
+    uint32_t pos = 0, c;
+    c = popc(x & 0xFFFu); if (k >= c) { k -= c; x >>= 12; pos = 12u; }
+    c = popc(x & 0x3Fu);  if (k >= c) { k -= c; x >>= 6;  pos += 6u; }
+    return pos + ((lut[RANK_LUT_BASE + (x & 63u)] >> (3u * k)) & 7u);
+}
+DK_HD uint32_t pick_msb_rank24_lut(uint32_t mask, uint32_t idx, const uint32_t* __restrict__ lut) {
+    return select_lsb24_lut(mask, popc(mask) - 1u - idx, lut);
+}
+
 // The reference's random pick on a 39-bit action mask: index from the most significant set bit (bit_flag.rs:86-94,104-171).
 DK_HD uint32_t pick_msb_rank64(uint64_t mask, uint32_t idx) {
     uint32_t lo = (uint32_t)mask, hi = (uint32_t)(mask >> 32);

@@ -62,7 +62,7 @@ DK_HD uint32_t doko_card_step(DokoLive& g, uint32_t& h, DokoTrickAcc& a, uint32_
     uint32_t mask = h;
     if (K > 0) { uint32_t f = h & a.follow; mask = f ? f : h; }
     uint32_t idx = mulhi(word, popc(mask));
-    uint32_t c = pick_msb_rank24(mask, idx);
+    uint32_t c = pick_msb_rank24_lut(mask, idx, lut);
     uint32_t bit = 1u << c;
     uint32_t e = lut[c];
     uint32_t dbl = g.dup & bit;

@@ -93,7 +93,7 @@ struct FdoLive {
     uint32_t eyes;            // 8 bits per absolute seat
     uint32_t ntricks;         // 4 bits per absolute seat
     uint32_t dkc;             // 4 bits per absolute seat: tricks with >= 40 eyes (Doppelkopf)
-    uint32_t foxes;           // up to two 5-bit records (1, seat that played ♦A : 2, seat that won it : 2)
+    uint32_t foxes;           // up to two 8-bit records (fdo_fox_record)
     uint32_t trump;           // trump mask of the game type
     uint32_t gt;              // FdoGameType
     uint32_t team_tag, re_mask, wed_seat, solved_idx;
@@ -314,7 +314,7 @@ DK_HD void fdo_card_step(FdoLive& g, uint32_t& h, TrickAcc& a, uint32_t word, bo
     }
     uint32_t n = popc(mask);
     uint32_t idx = mulhi(word, n);
-    uint32_t c = pick_msb_rank24(mask, idx);
+    uint32_t c = pick_msb_rank24_lut(mask, idx, lut);
     uint32_t bit = 1u << c;
     uint32_t e = lut[c];
     uint32_t dbl = g.dup & bit;                           // hand.remove: a doubled card stays in the hand once
@@ -328,15 +328,20 @@ DK_HD void fdo_card_step(FdoLive& g, uint32_t& h, TrickAcc& a, uint32_t word, bo
     g.steps++;
 }
 
+// ♦A log: one 8-bit record per trick that contained a ♦A (at most two): absolute seats that played one (4 bits) << 2 | winner seat.
+// foxm is frame-relative (bit k = k-th card of the trick), lead = absolute seat of the trick's first card.
+DK_HD uint32_t fdo_fox_record(uint32_t foxes, uint32_t foxm, uint32_t lead, uint32_t winner) {
+    uint32_t abs_mask = ((foxm << lead) | (foxm >> (4u - lead))) & 15u;
+    return foxm ? ((foxes << 8) | (abs_mask << 2) | winner) : foxes;
+}
+
 // Book-keeping when a trick is complete (state.rs:293-352, team/team_logic.rs:59-112, additional_points/*.rs).
 DK_HD void fdo_trick_done(FdoLive& g, const TrickAcc& a, uint32_t t) {
     uint32_t w = (g.base + a.bestk) & 3u;
     g.eyes += a.teyes << (8u * w);
     g.ntricks += 1u << (4u * w);
     if (a.teyes >= 40u) g.dkc += 1u << (4u * w);
-#pragma unroll
-    for (uint32_t k = 0; k < 4; ++k)
-        if ((a.foxm >> k) & 1u) g.foxes = (g.foxes << 5) | 16u | (((g.base + k) & 3u) << 2) | w;
+    g.foxes = fdo_fox_record(g.foxes, a.foxm, g.base, w);
     if (g.team_tag == TEAM_WEDDING_UNSOLVED) {
         if (w != g.wed_seat) { g.team_tag = TEAM_WEDDING_SOLVED; g.solved_idx = t; g.re_mask = (1u << g.wed_seat) | (1u << w); }
         else if (t == 2u) { g.team_tag = TEAM_WEDDING_SOLVED; g.solved_idx = 2u; g.re_mask = 1u << g.wed_seat; }
@@ -357,12 +362,11 @@ DK_HD void fdo_final_points(const FdoLive& g, int32_t pts[4]) {
         if (re) { re_eyes += e; re_tricks += n; extras += (int32_t)d; } else { extras -= (int32_t)d; }
     }
 #pragma unroll
-    for (uint32_t f = 0; f < 2; ++f) {
-        uint32_t rec = (g.foxes >> (5u * f)) & 31u;
-        if (rec & 16u) {
-            bool played_re = (g.re_mask >> ((rec >> 2) & 3u)) & 1u, won_re = (g.re_mask >> (rec & 3u)) & 1u;
-            if (played_re != won_re) extras += won_re ? 1 : -1;
-        }
+    for (uint32_t f = 0; f < 2; ++f) {                                // caught foxes: ♦A played by the other team than the trick's winner
+        uint32_t rec = (g.foxes >> (8u * f)) & 255u, players = rec >> 2;
+        bool won_re = (g.re_mask >> (rec & 3u)) & 1u;
+        int32_t caught = (int32_t)popc(players & (won_re ? ~g.re_mask : g.re_mask) & 15u);
+        extras += won_re ? caught : -caught;
     }
     if (g.karl) extras += ((g.re_mask >> g.last_winner) & 1u) ? 1 : -1;
     int32_t ko;

@@ -32,8 +32,12 @@ struct SharedDeck {
 };
 
 // Stage the 24-entry card attribute table in shared memory (first 24 threads), then sync.
-__device__ __forceinline__ void stage_card_lut(uint32_t* lut) {
+__device__ __forceinline__ void fill_card_lut(uint32_t* lut) {       // needs blockDim.x >= 64; caller syncs
     if (threadIdx.x < 24) lut[threadIdx.x] = card_lut_entry(threadIdx.x);
+    if (threadIdx.x < 64) lut[RANK_LUT_BASE + threadIdx.x] = rank_lut6_entry(threadIdx.x);
+}
+__device__ __forceinline__ void stage_card_lut(uint32_t* lut) {
+    fill_card_lut(lut);
     __syncthreads();
 }
 
@@ -65,7 +69,7 @@ template <bool WITH_ANN>
 __global__ void __launch_bounds__(PLAYOUT_THREADS)
 fdo_playout_fresh_kernel(RngParams rp, uint64_t n, void* __restrict__ points, void* __restrict__ steps, bool compact) {
     __shared__ uint32_t smem[12 * PLAYOUT_THREADS];
-    __shared__ uint32_t lut[24];
+    __shared__ uint32_t lut[CARD_LUT_WORDS];
     stage_card_lut(lut);
     uint64_t i = (uint64_t)blockIdx.x * PLAYOUT_THREADS + threadIdx.x;
     // Out-of-range lanes play game n-1 again (keeps the warp converged); they just do not store.
@@ -87,7 +91,7 @@ __global__ void __launch_bounds__(PLAYOUT_THREADS)
 doko_playout_fresh_kernel(RngParams rp, uint64_t n, void* __restrict__ points, void* __restrict__ steps, bool compact,
                           uint8_t* __restrict__ trace, uint4* __restrict__ aux) {
     __shared__ uint32_t smem[12 * PLAYOUT_THREADS];
-    __shared__ uint32_t lut[24];
+    __shared__ uint32_t lut[CARD_LUT_WORDS];
     stage_card_lut(lut);
     uint64_t i = (uint64_t)blockIdx.x * PLAYOUT_THREADS + threadIdx.x;
     uint64_t gi = i < n ? i : n - 1;
@@ -123,6 +127,46 @@ __device__ __forceinline__ void store_state(dk_state* __restrict__ dst, const dk
 
 constexpr int STATE_THREADS = 128;
 
+// Block-cooperative state I/O: the BLOCK records of a block are contiguous in HBM (BLOCK x 128 B), so the block moves them with
+// fully coalesced 16-byte accesses (a warp instruction covers 512 contiguous bytes instead of 32 separate 128-byte lines) and
+// every thread then picks its own record out of shared memory.  16-byte chunk j of record t sits at t*8 + (j ^ (t & 7)): both the
+// cooperative phase and the per-thread phase are bank-conflict free.  All threads of the block must call load / store.
+template <int BLOCK>
+struct StateStage {
+    static __device__ __forceinline__ void load(const dk_state* __restrict__ states, uint64_t first, uint64_t n, uint4* sm) {
+        const uint4* g = reinterpret_cast<const uint4*>(states + first);
+        const uint32_t avail = (uint32_t)min((uint64_t)BLOCK, n - first) * 8u;
+#pragma unroll
+        for (uint32_t k = 0; k < 8u; ++k) {
+            const uint32_t e = k * BLOCK + threadIdx.x;
+            if (e < avail) { const uint32_t t = e >> 3, j = e & 7u; sm[t * 8u + (j ^ (t & 7u))] = __ldg(g + e); }
+        }
+        __syncthreads();
+    }
+    static __device__ __forceinline__ void get(const uint4* sm, dk_state& s) {
+        uint4* d4 = reinterpret_cast<uint4*>(&s);
+        const uint32_t t = threadIdx.x;
+#pragma unroll
+        for (uint32_t j = 0; j < 8u; ++j) d4[j] = sm[t * 8u + (j ^ (t & 7u))];
+    }
+    static __device__ __forceinline__ void put(uint4* sm, const dk_state& s) {
+        const uint4* s4 = reinterpret_cast<const uint4*>(&s);
+        const uint32_t t = threadIdx.x;
+#pragma unroll
+        for (uint32_t j = 0; j < 8u; ++j) sm[t * 8u + (j ^ (t & 7u))] = s4[j];
+    }
+    static __device__ __forceinline__ void store(dk_state* __restrict__ states, uint64_t first, uint64_t n, const uint4* sm) {
+        __syncthreads();
+        uint4* g = reinterpret_cast<uint4*>(states + first);
+        const uint32_t avail = (uint32_t)min((uint64_t)BLOCK, n - first) * 8u;
+#pragma unroll
+        for (uint32_t k = 0; k < 8u; ++k) {
+            const uint32_t e = k * BLOCK + threadIdx.x;
+            if (e < avail) { const uint32_t t = e >> 3, j = e & 7u; g[e] = sm[t * 8u + (j ^ (t & 7u))]; }
+        }
+    }
+};
+
 // dk_new_games: FdoState::new_game / DoState::new_game (deal from the stream) → records.
 __global__ void __launch_bounds__(PLAYOUT_THREADS)
 new_games_kernel(RngParams rp, uint64_t n, dk_state* __restrict__ out) {
@@ -156,22 +200,28 @@ from_deals_kernel(uint64_t n, const uint64_t* __restrict__ hands, const uint8_t*
 template <int ENGINE>
 __global__ void __launch_bounds__(STATE_THREADS)
 legal_mask_kernel(uint64_t n, const dk_state* __restrict__ states, uint64_t* __restrict__ mask_out) {
-    uint64_t i = (uint64_t)blockIdx.x * STATE_THREADS + threadIdx.x;
+    __shared__ uint4 stage[STATE_THREADS * 8];
+    const uint64_t first = (uint64_t)blockIdx.x * STATE_THREADS, i = first + threadIdx.x;
+    StateStage<STATE_THREADS>::load(states, first, n, stage);
     if (i >= n) return;
     alignas(16) dk_state s;
-    load_state(states + i, s);
+    StateStage<STATE_THREADS>::get(stage, s);
     mask_out[i] = ENGINE == DK_FDO ? fdo_state_legal_mask(s) : doko_state_legal_mask(s);
 }
 template <int ENGINE>
 __global__ void __launch_bounds__(STATE_THREADS)
 apply_kernel(uint64_t n, dk_state* __restrict__ states, const uint8_t* __restrict__ action, uint32_t flags, uint8_t* __restrict__ err_out) {
-    uint64_t i = (uint64_t)blockIdx.x * STATE_THREADS + threadIdx.x;
-    if (i >= n) return;
-    alignas(16) dk_state s;
-    load_state(states + i, s);
-    uint32_t err = ENGINE == DK_FDO ? fdo_state_apply_az(s, action[i], (flags & DK_APPLY_SKIP_SINGLE) != 0) : doko_state_apply(s, action[i]);
-    if (!err) store_state(states + i, s);
-    if (err_out) err_out[i] = (uint8_t)err;
+    __shared__ uint4 stage[STATE_THREADS * 8];
+    const uint64_t first = (uint64_t)blockIdx.x * STATE_THREADS, i = first + threadIdx.x;
+    StateStage<STATE_THREADS>::load(states, first, n, stage);
+    if (i < n) {
+        alignas(16) dk_state s;
+        StateStage<STATE_THREADS>::get(stage, s);
+        uint32_t err = ENGINE == DK_FDO ? fdo_state_apply_az(s, action[i], (flags & DK_APPLY_SKIP_SINGLE) != 0) : doko_state_apply(s, action[i]);
+        if (!err) StateStage<STATE_THREADS>::put(stage, s);              // an illegal action leaves the record as it was
+        if (err_out) err_out[i] = (uint8_t)err;
+    }
+    StateStage<STATE_THREADS>::store(states, first, n, stage);
 }
 __global__ void __launch_bounds__(STATE_THREADS)
 terminal_kernel(uint64_t n, const dk_state* __restrict__ states, uint8_t* __restrict__ done_out, int4* __restrict__ points_out) {
@@ -325,7 +375,7 @@ template <int ENGINE, bool WITH_ANN>
 __global__ void __launch_bounds__(STATE_THREADS)
 playout_state_kernel(RngParams rp, uint64_t n, const dk_state* __restrict__ states, uint32_t per_unit, void* __restrict__ points,
                      void* __restrict__ steps, bool compact) {
-    __shared__ uint32_t lut[24];
+    __shared__ uint32_t lut[CARD_LUT_WORDS];
     stage_card_lut(lut);
     uint64_t i = (uint64_t)blockIdx.x * STATE_THREADS + threadIdx.x;
     if (i >= n) return;
@@ -422,8 +472,8 @@ fdo_leaf_rollouts_kernel(RngParams rp, uint64_t n_leaves, uint32_t rollouts, int
     __shared__ MatchPrep prep;
     __shared__ __align__(16) dk_state leaf;
     __shared__ int red[4];
-    __shared__ uint32_t lut[24];
-    if (threadIdx.x < 24) lut[threadIdx.x] = card_lut_entry(threadIdx.x);
+    __shared__ uint32_t lut[CARD_LUT_WORDS];
+    fill_card_lut(lut);
     uint64_t i = blockIdx.x;
     if (i >= n_leaves) return;
     if (threadIdx.x < 8) reinterpret_cast<uint4*>(&leaf)[threadIdx.x] = __ldg(reinterpret_cast<const uint4*>(states + i) + threadIdx.x);
@@ -479,11 +529,11 @@ fdo_pimc_kernel(RngParams rp, uint64_t n_roots, uint32_t n_det, uint32_t n_rollo
     __shared__ int vsum[PIMC_MAX_DPB][N_ACTIONS];
     __shared__ uint32_t wins[PIMC_MAX_DPB][N_ACTIONS];
     __shared__ uint8_t det_status[PIMC_MAX_DPB];
-    __shared__ uint32_t lut[24];
+    __shared__ uint32_t lut[CARD_LUT_WORDS];
     const uint64_t root = blockIdx.x / blocks_per_root;
     const uint32_t d0 = (uint32_t)(blockIdx.x % blocks_per_root) * dpb;
     const uint32_t nd = min(dpb, n_det - d0);
-    if (threadIdx.x < 24) lut[threadIdx.x] = card_lut_entry(threadIdx.x);
+    fill_card_lut(lut);
     if (threadIdx.x < 8) reinterpret_cast<uint4*>(&det_state[0])[threadIdx.x] = __ldg(reinterpret_cast<const uint4*>(states + root) + threadIdx.x);
     for (uint32_t k = threadIdx.x; k < nd * N_ACTIONS; k += PIMC_THREADS) { (&vsum[0][0])[k] = 0; (&wins[0][0])[k] = 0u; }
     __syncthreads();

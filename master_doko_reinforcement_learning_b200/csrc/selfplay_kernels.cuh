@@ -20,12 +20,14 @@ constexpr int SP_THREADS = ENC_THREADS;   // plan / encode / apply use the same 
 __global__ void __launch_bounds__(SP_THREADS)
 sp_plan_kernel(RngParams rp, uint64_t n, const dk_state* __restrict__ states, uint64_t az_epoch, float keep_prob, uint32_t search_forced,
                uint64_t* __restrict__ allowed_out, uint8_t* __restrict__ flags_out, uint32_t* __restrict__ block_counts) {
-    uint64_t i = (uint64_t)blockIdx.x * SP_THREADS + threadIdx.x;
+    __shared__ uint4 stage[SP_THREADS * 8];
+    const uint64_t first = (uint64_t)blockIdx.x * SP_THREADS, i = first + threadIdx.x;
+    StateStage<SP_THREADS>::load(states, first, n, stage);
     uint32_t flags = SP_DONE;
     uint64_t allowed = 0;
     if (i < n) {
         alignas(16) dk_state s;
-        load_state(states + i, s);
+        StateStage<SP_THREADS>::get(stage, s);
         if (st_phase(s) != DK_PHASE_FINISHED) {
             allowed = sp_az_allowed(s, az_epoch);
             flags = 0;
@@ -143,46 +145,74 @@ sp_encode_kernel(uint64_t n, const dk_state* __restrict__ states, const uint64_t
 __global__ void __launch_bounds__(STATE_THREADS)
 sp_uniform_search_kernel(RngParams rp, uint64_t n, const uint64_t* __restrict__ allowed, const uint8_t* __restrict__ flags,
                          float* __restrict__ policy, uint8_t* __restrict__ action) {
-    uint64_t i = (uint64_t)blockIdx.x * STATE_THREADS + threadIdx.x;
-    if (i >= n) return;
-    const uint32_t f = flags[i];
-    if (f & (SP_DONE | SP_FORCED)) { action[i] = (uint8_t)ACTION_NONE; return; }
-    const uint64_t m = allowed[i];
-    const uint32_t cnt = popcll(m);
-    RngKey key = make_key(rp, i, 0, false);
-    U4 blk = rng_block(key, SITE_STEP, 0);
-    action[i] = (uint8_t)pick_msb_rank64(m, mulhi(blk.x, cnt));
-    const float u = f32_div(1.0f, (float)cnt);
-    float* p = policy + i * N_ACTIONS;
-    for (uint32_t k = 0; k < N_ACTIONS; ++k) p[k] = ((m >> k) & 1ull) ? u : 0.0f;
+    __shared__ uint64_t mask_s[STATE_THREADS];
+    __shared__ float prob_s[STATE_THREADS];
+    const uint64_t first = (uint64_t)blockIdx.x * STATE_THREADS;
+    const uint64_t i = first + threadIdx.x;
+    uint64_t m = 0;
+    float u = 0.0f;
+    if (i < n) {
+        const uint32_t f = flags[i];
+        if (f & (SP_DONE | SP_FORCED)) action[i] = (uint8_t)ACTION_NONE;
+        else {
+            m = allowed[i];
+            const uint32_t cnt = popcll(m);
+            RngKey key = make_key(rp, i, 0, false);
+            U4 blk = rng_block(key, SITE_STEP, 0);
+            action[i] = (uint8_t)pick_msb_rank64(m, mulhi(blk.x, cnt));
+            u = f32_div(1.0f, (float)cnt);
+        }
+    }
+    mask_s[threadIdx.x] = m;
+    prob_s[threadIdx.x] = u;
+    __syncthreads();
+    // the block's 128 x 39 policy values are contiguous: consecutive threads write consecutive floats (rows of finished / forced games stay untouched)
+    const uint32_t games = (uint32_t)min((uint64_t)STATE_THREADS, n - first);
+    float* dst = policy + first * N_ACTIONS;
+    for (uint32_t e = threadIdx.x; e < games * N_ACTIONS; e += STATE_THREADS) {
+        const uint32_t g = e / N_ACTIONS, a = e - g * N_ACTIONS;
+        const uint64_t mg = mask_s[g];
+        if (mg) dst[e] = ((mg >> a) & 1ull) ? prob_s[g] : 0.0f;
+    }
 }
 
 __global__ void __launch_bounds__(STATE_THREADS)
 sp_apply_kernel(uint64_t n, dk_state* __restrict__ states, const uint64_t* __restrict__ allowed, const uint8_t* __restrict__ flags,
                 const long long* __restrict__ rows, const float* __restrict__ policy, const uint8_t* __restrict__ action, SpBuffers buf,
                 uint8_t* __restrict__ err_out) {
-    uint64_t i = (uint64_t)blockIdx.x * STATE_THREADS + threadIdx.x;
-    if (i >= n) return;
-    const uint32_t f = flags[i];
-    uint32_t err = 0;
-    if (!(f & SP_DONE)) {
-        const uint64_t m = allowed[i];
-        const uint32_t a = (f & SP_FORCED) ? ffs0ll(m) : action[i];
-        if (a >= N_ACTIONS || !((m >> a) & 1ull)) err = 1;             // the reference would panic in play_action
-        else {
-            const long long row = rows[i];
-            if (row >= 0 && !(f & SP_FORCED)) {
-                const float* src = policy + i * N_ACTIONS;
-                float* dst = buf.policy + (size_t)row * N_ACTIONS;
-                for (uint32_t k = 0; k < N_ACTIONS; ++k) dst[k] = src[k];
+    __shared__ long long row_s[STATE_THREADS];
+    __shared__ uint4 stage[STATE_THREADS * 8];
+    const uint64_t first = (uint64_t)blockIdx.x * STATE_THREADS;
+    const uint64_t i = first + threadIdx.x;
+    StateStage<STATE_THREADS>::load(states, first, n, stage);
+    long long copy_row = -1;
+    if (i < n) {
+        const uint32_t f = flags[i];
+        uint32_t err = 0;
+        if (!(f & SP_DONE)) {
+            const uint64_t m = allowed[i];
+            const uint32_t a = (f & SP_FORCED) ? ffs0ll(m) : action[i];
+            if (a >= N_ACTIONS || !((m >> a) & 1ull)) err = 1;             // the reference would panic in play_action
+            else {
+                if (!(f & SP_FORCED)) copy_row = rows[i];
+                alignas(16) dk_state s;
+                StateStage<STATE_THREADS>::get(stage, s);
+                fdo_state_apply(s, a);
+                StateStage<STATE_THREADS>::put(stage, s);
             }
-            alignas(16) dk_state s;
-            load_state(states + i, s);
-            fdo_state_apply(s, a);
-            store_state(states + i, s);
         }
+        if (err_out) err_out[i] = (uint8_t)err;
     }
-    if (err_out) err_out[i] = (uint8_t)err;
+    row_s[threadIdx.x] = copy_row;
+    StateStage<STATE_THREADS>::store(states, first, n, stage);       // (syncs first: row_s is visible afterwards as well)
+    // policy targets of the searched games → their rows (rows of one block are consecutive): coalesced reads and writes
+    const uint32_t games = (uint32_t)min((uint64_t)STATE_THREADS, n - first);
+    const float* src = policy + first * N_ACTIONS;
+    for (uint32_t e = threadIdx.x; e < games * N_ACTIONS; e += STATE_THREADS) {
+        const uint32_t g = e / N_ACTIONS, a = e - g * N_ACTIONS;
+        const long long row = row_s[g];
+        if (row >= 0) buf.policy[(size_t)row * N_ACTIONS + a] = src[e];
+    }
 }
 
 // Value targets of rows [0, count): rewards of the row's (finished) game rotated to the row's mover.  Rows of unfinished games
@@ -235,11 +265,11 @@ pack_replay_records_kernel(unsigned long long n_rows, const long long* __restric
 // is first replaced by determinization (first_sub + d) of the info-state (the dk_determinize stream).  Iteration `it` runs on the
 // Philox unit (first_id + root, (first_sub + d) * iterations + it).
 constexpr int UCT_THREADS = 64;
-__global__ void __launch_bounds__(UCT_THREADS)
+__global__ void __launch_bounds__(UCT_THREADS, 16)
 fdo_uct_kernel(RngParams rp, uint64_t n_trees, uint32_t trees_per_root, uint32_t iterations, double c, const double* __restrict__ ln_table, int determinize,
                const dk_state* __restrict__ states, UctNode* __restrict__ pool_base, uint32_t* __restrict__ visits_out, float* __restrict__ values_out,
                uint8_t* __restrict__ action_out, uint8_t* __restrict__ status_out) {
-    __shared__ uint32_t lut[24];
+    __shared__ uint32_t lut[CARD_LUT_WORDS];
     stage_card_lut(lut);
     const uint64_t t = (uint64_t)blockIdx.x * UCT_THREADS + threadIdx.x;
     if (t >= n_trees) return;

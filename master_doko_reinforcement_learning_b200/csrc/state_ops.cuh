@@ -275,8 +275,7 @@ DK_HD bool fdo_state_to_live(const dk_state& s, FdoLive& g, FdoResume& rs) {
             uint32_t e, fm, w = st_trick_start(s, t + 1u);
             (void)fdo_state_trick_winner(s, t, g.trump, nullptr, &e, &fm);
             if (e >= 40u) g.dkc += 1u << (4u * w);
-            for (uint32_t k = 0; k < 4u; ++k)
-                if ((fm >> k) & 1u) g.foxes = (g.foxes << 5) | 16u | (((st_trick_start(s, t) + k) & 3u) << 2) | w;
+            g.foxes = fdo_fox_record(g.foxes, fm, st_trick_start(s, t), w);
             rs.starts |= st_trick_start(s, t) << (2u * t);
             g.last_winner = w;
         }

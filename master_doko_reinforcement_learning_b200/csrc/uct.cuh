@@ -85,30 +85,43 @@ DK_HD void uct_init_node(UctNode& n, const dk_state& s, uint32_t parent, uint32_
 }
 DK_HD double uct_q(const UctNode& c) { return c.visits > 0u ? dk_ddiv((double)c.win, (double)c.visits) : 0.0; }
 
-// find_best_child (node.rs:258-278) with uct (:238-256) and min_max_normalized_q (:202-236) of every child.
+// find_best_child (node.rs:258-278) with uct (:238-256) and min_max_normalized_q (:202-236) of every child.  The children's
+// (visits, win) pairs are fetched first, all loads in flight together (one memory round trip per tree level instead of one per child).
 DK_HD uint32_t uct_find_best_child(const UctNode* __restrict__ pool, uint32_t self, double c, const double* __restrict__ ln_table) {
     const UctNode& p = pool[self];
     const uint32_t nch = uct_n_children(p);
+    uint32_t idx[UCT_MAX_CHILDREN], vis[UCT_MAX_CHILDREN];
+    long long win[UCT_MAX_CHILDREN];
+#pragma unroll
+    for (uint32_t k = 0; k < UCT_MAX_CHILDREN; ++k) idx[k] = k < nch ? p.child[k] : self;
+#pragma unroll
+    for (uint32_t k = 0; k < UCT_MAX_CHILDREN; ++k) { vis[k] = pool[idx[k]].visits; win[k] = pool[idx[k]].win; }
     double min_q = dk_inf(), max_q = -dk_inf();
-    for (uint32_t k = 0; k < nch; ++k) {
-        double q = uct_q(pool[p.child[k]]);
-        if (q < min_q) min_q = q;
-        if (q > max_q) max_q = q;
+#pragma unroll
+    for (uint32_t k = 0; k < UCT_MAX_CHILDREN; ++k) {
+        if (k < nch) {
+            double q = vis[k] > 0u ? dk_ddiv((double)win[k], (double)vis[k]) : 0.0;
+            if (q < min_q) min_q = q;
+            if (q > max_q) max_q = q;
+        }
     }
     const double span = dk_dadd(max_q, -min_q);
     const bool flat = fabs(span) < 2.220446049250313e-16;            // f64::EPSILON
     const double ln_n = ln_table[p.visits];
     double best_uct = -dk_inf();
     uint32_t best = UCT_NONE;
-    for (uint32_t k = 0; k < nch; ++k) {
-        const UctNode& ch = pool[p.child[k]];
-        double u;
-        if (ch.visits == 0u) u = dk_inf();
-        else {
-            double norm_q = flat ? 1.0 : dk_dadd(dk_ddiv(dk_dmul(2.0, dk_dadd(uct_q(ch), -min_q)), span), -1.0);
-            u = dk_dadd(norm_q, dk_dmul(c, dk_dsqrt(dk_ddiv(ln_n, (double)ch.visits))));
+#pragma unroll
+    for (uint32_t k = 0; k < UCT_MAX_CHILDREN; ++k) {
+        if (k < nch) {
+            double u;
+            if (vis[k] == 0u) u = dk_inf();
+            else {
+                double q = dk_ddiv((double)win[k], (double)vis[k]);
+                double norm_q = flat ? 1.0 : dk_dadd(dk_ddiv(dk_dmul(2.0, dk_dadd(q, -min_q)), span), -1.0);
+                u = dk_dadd(norm_q, dk_dmul(c, dk_dsqrt(dk_ddiv(ln_n, (double)vis[k]))));
+            }
+            if (u > best_uct) { best_uct = u; best = idx[k]; }
         }
-        if (u > best_uct) { best_uct = u; best = p.child[k]; }
     }
     return best;
 }
@@ -126,21 +139,20 @@ DK_HD uint32_t uct_iteration(UctNode* __restrict__ pool, uint32_t& n_nodes, cons
     }
     uint32_t explore = node;
     const uint64_t unexpanded = pool[node].info & UCT_ACTION_MASK;
+    alignas(16) dk_state s = pool[node].state;
     if (unexpanded != 0ull) {                                                    // expand_single (:65-104)
         const uint32_t nch = uct_n_children(pool[node]);
         if (nch >= UCT_MAX_CHILDREN) return 1u;
         U4 blk = rng_block(key, SITE_EXPAND, 0);
         const uint32_t a = pick_msb_rank64(unexpanded, mulhi(blk.x, popcll(unexpanded)));
-        alignas(16) dk_state s = pool[node].state;
         fdo_state_apply(s, a);                                                   // by_action
         explore = n_nodes++;
         uct_init_node(pool[explore], s, node, a, false);
         pool[node].child[nch] = explore;
         pool[node].info = (pool[node].info & ~(1ull << a) & ~(15ull << 56)) | ((uint64_t)(nch + 1u) << 56);
     }
-    int32_t p[4];                                                                // random_rollout (env_state_full_doko.rs:198-220)
+    int32_t p[4];                                                                // random_rollout (env_state_full_doko.rs:198-220) from `s`
     {
-        alignas(16) dk_state s = pool[explore].state;
         FdoLive g; FdoResume rs;
         if (fdo_state_to_live(s, g, rs)) { fdo_play_to_end<false, false>(g, key, &rs, lut); fdo_final_points(g, p); }
         else { p[0] = s.points[0]; p[1] = s.points[1]; p[2] = s.points[2]; p[3] = s.points[3]; }

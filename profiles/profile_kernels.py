@@ -35,6 +35,23 @@ def main():
         sub = states[:1024].clone()
         for k in range(3):
             dk.leaf_rollouts(sub, 1024, dk.rng(SEED, 0, 11), determinize=True)
+    elif a.which == "uct":
+        sub = states[:2048].clone()
+        need = dk.L.dk_uct_workspace_bytes(2048 * 64, 256)
+        ws = torch.empty((need // 8 + 2,), dtype=torch.int64, device="cuda")
+        for k in range(2):
+            dk.uct_search(sub, 256, 1.4, dk.rng(SEED, 0, 13), trees_per_root=64, determinize=True, workspace=ws)
+    elif a.which == "pimc":
+        sub = states[:1024].clone()
+        for k in range(3):
+            dk.pimc_evaluate(sub, 64, 32, dk.rng(SEED, 0, 12), want_values=False)
+    elif a.which == "sp":
+        sp = dk.self_play(n, n * 3)
+        for k in range(3):
+            sp.reset()
+            sp.begin_turn(states, 0, 1.0, dk.rng(SEED, 0, 200 + k))
+            sp.uniform_search(dk.rng(SEED, 0, 200 + k))
+            sp.end_turn(states)
     torch.cuda.synchronize()
     print("done", a.which)
 

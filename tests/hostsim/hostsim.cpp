@@ -29,9 +29,9 @@ struct LocalDeck {
     void set(uint32_t i, uint32_t v) { w[i] = v; }
 };
 const uint32_t* card_lut() {
-    static uint32_t lut[24];
+    static uint32_t lut[dk::CARD_LUT_WORDS];
     static bool init = false;
-    if (!init) { for (uint32_t c = 0; c < 24; ++c) lut[c] = dk::card_lut_entry(c); init = true; }
+    if (!init) { for (uint32_t c = 0; c < 24; ++c) lut[c] = dk::card_lut_entry(c); for (uint32_t b = 0; b < 64; ++b) lut[dk::RANK_LUT_BASE + b] = dk::rank_lut6_entry(b); init = true; }
     return lut;
 }
 dk::RngKey make_key(uint64_t seed, uint64_t unit, uint32_t epoch) {
