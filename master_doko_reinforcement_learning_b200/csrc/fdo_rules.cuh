@@ -38,10 +38,10 @@ DK_HD uint32_t fdo_allowed_call(uint32_t c, uint32_t m, uint32_t e, uint32_t w) 
 }
 // Smallest hand size with which some seat of a team (own lowest m, enemy lowest e) could still call.
 DK_HD uint32_t fdo_min_cards_to_call(uint32_t m, uint32_t e, uint32_t w) {
-    uint32_t ml = m == 6u ? 0u : m;
-    uint32_t a = ml < 5u ? 11u - ml - w : 99u;
-    uint32_t b = (e >= 1u && e <= 5u && m == 0u) ? 11u - e - w : 99u;
-    return a < b ? a : b;
+    // = min(regular: m' < 5 ? 11 - m' - w : none, counter: (1 <= e <= 5 && m == 0) ? 11 - e - w : none) with m' = (m == 6 ? 0 : m):
+    // the team has called nothing (m == 0): 11 - w, lowered by the enemy's regular level; otherwise 11 - w - m', none (99) at Black.
+    uint32_t sub = m == 0u ? (e - 1u < 5u ? e : 0u) : ((0x0F43210u >> (4u * m)) & 15u);
+    return sub == 15u ? 99u : 11u - w - sub;
 }
 
 // ---- scoring ----------------------------------------------------------------------------------------------------
@@ -122,8 +122,8 @@ DK_HD void fdo_live_clear(FdoLive& g) {
 
 // Deal: start seat = draw(4) from word 0 of SITE_DEAL, then a Durstenfeld shuffle (i = 47..1, j = draw(i+1), swap) of
 // [c0,c0,c1,c1,...] using words 1..47; seat p receives positions 12p..12p+11 (add: copy A first, then copy B)
-// (rs-full-doko/src/state/state.rs:169-178, hand/hand.rs:116-188).  `Deck` provides 12 words of per-thread scratch
-// (shared memory on the device).  Position i is final after step i, so its card goes straight into seat i/12's hand.
+// (rs-full-doko/src/state/state.rs:169-178, hand/hand.rs:116-188).  `Deck` provides 48 bytes of per-thread scratch, set up
+// a word at a time and then byte-addressed (shared memory on the device, word-interleaved across the block: conflict-free).  Position i is final after step i, so its card goes straight into seat i/12's hand.
 template <class Deck>
 DK_HD void fdo_deal(FdoLive& g, const RngKey& key, Deck& deck, uint32_t abs_hand[4], uint32_t& dup, uint32_t& start) {
 #pragma unroll
@@ -141,13 +141,9 @@ DK_HD void fdo_deal(FdoLive& g, const RngKey& key, Deck& deck, uint32_t abs_hand
             if (ord == 0u) { start = mulhi(ws[q], 4u); continue; }
             uint32_t i = 48u - ord;                       // 47 .. 1
             uint32_t j = mulhi(ws[q], i + 1u);
-            uint32_t wi = i >> 2, si = (i & 3u) * 8u;
-            uint32_t wj = j >> 2, sj = (j & 3u) * 8u;
-            uint32_t vi = deck.get(wi);
-            uint32_t vj = deck.get(wj);
-            uint32_t ci = (vi >> si) & 0xFFu;             // card currently at position i
-            uint32_t cj = (vj >> sj) & 0xFFu;             // card that ends up at position i
-            deck.set(wj, (vj & ~(0xFFu << sj)) | (ci << sj));
+            uint32_t ci = deck.get8(i);                   // card currently at position i (byte access: no shift / mask arithmetic)
+            uint32_t cj = deck.get8(j);                   // card that ends up at position i
+            deck.set8(j, ci);
             uint32_t bit = 1u << cj;
             uint32_t seat = i / 12u;
             d |= h[seat] & bit;
@@ -155,7 +151,7 @@ DK_HD void fdo_deal(FdoLive& g, const RngKey& key, Deck& deck, uint32_t abs_hand
         }
     }
     {   // position 0
-        uint32_t c0 = deck.get(0) & 0xFFu;
+        uint32_t c0 = deck.get8(0);
         uint32_t bit = 1u << c0;
         d |= h[0] & bit;
         h[0] |= bit;
@@ -287,7 +283,11 @@ DK_HD void fdo_replay_announcements(FdoLive& g, const RngKey& key, uint32_t star
         }
         uint32_t j = ffs0(hit);                                   // j eligible seats pass, the (j+1)-th calls
         ord += j + 1u;
-        uint32_t d = select_lsb(win, j);                          // its distance from p
+        uint32_t wj = win;                                        // distance of the (j+1)-th eligible seat from p: win has <= 4 bits,
+        if (j > 0u) wj &= wj - 1u;                                //   so clearing the lowest set bit j times beats a generic rank select
+        if (j > 1u) wj &= wj - 1u;
+        if (j > 2u) wj &= wj - 1u;
+        uint32_t d = ffs0(wj);
         p = (p + d) & 3u;
         uint32_t is_re = (re >> p) & 1u;
         uint32_t c = cmax - ((played >> p) & 1u);

@@ -29,6 +29,9 @@ struct SharedDeck {
     uint32_t* base;  // &smem[threadIdx.x]
     __device__ __forceinline__ uint32_t get(uint32_t w) const { return base[w * PLAYOUT_THREADS]; }
     __device__ __forceinline__ void set(uint32_t w, uint32_t v) { base[w * PLAYOUT_THREADS] = v; }
+    // byte j of the thread's 48: byte (j & 3) of word (j >> 2); every lane stays in its own bank for any j
+    __device__ __forceinline__ uint32_t get8(uint32_t j) const { return reinterpret_cast<const uint8_t*>(base)[(j >> 2) * (PLAYOUT_THREADS * 4) + (j & 3u)]; }
+    __device__ __forceinline__ void set8(uint32_t j, uint32_t v) { reinterpret_cast<uint8_t*>(base)[(j >> 2) * (PLAYOUT_THREADS * 4) + (j & 3u)] = (uint8_t)v; }
 };
 
 // Stage the 24-entry card attribute table in shared memory (first 24 threads), then sync.

@@ -27,6 +27,8 @@ struct LocalDeck {
     uint32_t w[12];
     uint32_t get(uint32_t i) const { return w[i]; }
     void set(uint32_t i, uint32_t v) { w[i] = v; }
+    uint32_t get8(uint32_t j) const { return (w[j >> 2] >> (8u * (j & 3u))) & 0xFFu; }
+    void set8(uint32_t j, uint32_t v) { w[j >> 2] = (w[j >> 2] & ~(0xFFu << (8u * (j & 3u)))) | ((v & 0xFFu) << (8u * (j & 3u))); }
 };
 const uint32_t* card_lut() {
     static uint32_t lut[dk::CARD_LUT_WORDS];
@@ -224,3 +226,4 @@ SIM_API uint32_t sim_fdo_uct_search(const dk_state* root, uint64_t seed, uint64_
     return 0;
 }
 SIM_API uint64_t sim_uct_allowed(const dk_state* s, int first) { return dk::uct_allowed(*s, first != 0); }
+SIM_API uint32_t sim_fdo_min_cards_to_call(uint32_t m, uint32_t e, uint32_t w) { return dk::fdo_min_cards_to_call(m, e, w); }

@@ -112,6 +112,20 @@ def test_device_allowed_call_matches_oracle_exhaustively(orc):
                     assert sim.sim_fdo_allowed_call(c, m, e, w) == act[exp], (c, m, e, w)
 
 
+def test_device_min_cards_to_call_is_the_threshold_of_allowed_call():
+    """fdo_min_cards_to_call(m, e, w) = the smallest hand size for which fdo_allowed_call is non-empty (99 = never), exhaustively."""
+    sim = hostsim_lib.load()
+    for m in range(7):
+        for e in range(7):
+            for w in (0, 1, 2):
+                ok = [c for c in range(0, 13) if sim.sim_fdo_allowed_call(c, m, e, w) != 0]
+                thr = sim.sim_fdo_min_cards_to_call(m, e, w)
+                if ok:
+                    assert thr == min(ok) and ok == list(range(min(ok), 13)), (m, e, w, thr, ok)
+                else:
+                    assert thr > 12, (m, e, w, thr)
+
+
 def test_device_score_matches_oracle_exhaustively(orc):
     """Closed-form scoring (fdo_score) vs the literal stats.rs restatement over all calls x eyes x trick extremes x team sizes."""
     sim = hostsim_lib.load()
