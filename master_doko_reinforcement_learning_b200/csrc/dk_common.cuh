@@ -136,7 +136,8 @@ DK_HD uint32_t rank_lut6_entry(uint32_t b) {
     for (uint32_t pos = 0; pos < 6u; ++pos) if ((b >> pos) & 1u) { e |= pos << (3u * j); j++; }
     return e;
 }
-constexpr uint32_t CARD_LUT_WORDS = 96u;     // [0,24) card attributes (card_lut_entry) | [32,96) rank_lut6_entry
+constexpr uint32_t CARD_LUT_WORDS = 96u;     // [0,24) card attributes (card_lut_entry) | [24,31) fdo_thr_lut_word | [32,96) rank_lut6_entry
+constexpr uint32_t THR_LUT_BASE = 24u;
 constexpr uint32_t RANK_LUT_BASE = 32u;
 DK_HD uint32_t select_lsb24_lut(uint32_t x, uint32_t k, const uint32_t* __restrict__ lut) {
     uint32_t pos = 0, c;

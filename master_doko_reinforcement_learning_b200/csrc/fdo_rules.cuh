@@ -44,6 +44,21 @@ DK_HD uint32_t fdo_min_cards_to_call(uint32_t m, uint32_t e, uint32_t w) {
     return sub == 15u ? 99u : 11u - w - sub;
 }
 
+// The same through the shared-memory table (words THR_LUT_BASE + m, nibble e = the amount the base threshold 11 - w is lowered by,
+// 15 = the team can never call again): one lookup on the LSU pipe in the replay loop instead of a select chain on the ALU pipe.
+DK_HD uint32_t fdo_thr_lut_word(uint32_t m) {
+    uint32_t word = 0;
+    for (uint32_t e = 0; e < 8u; ++e) {
+        uint32_t sub = m == 0u ? ((e >= 1u && e <= 5u) ? e : 0u) : (m < 5u ? m : (m == 5u ? 15u : 0u));
+        word |= sub << (4u * e);
+    }
+    return word;
+}
+DK_HD uint32_t fdo_min_cards_to_call_lut(uint32_t m, uint32_t e, uint32_t w, const uint32_t* __restrict__ lut) {
+    uint32_t sub = (lut[THR_LUT_BASE + m] >> (4u * e)) & 15u;
+    return sub == 15u ? 99u : 11u - w - sub;
+}
+
 // ---- scoring ----------------------------------------------------------------------------------------------------
 // Closed form of FdoEndOfGameStats::calculate (stats/stats.rs:46-240) and its callees re_won (win_conditions/re_won.rs),
 // kontra_won, FdoBasicWinningPointsDetails::calculate (basic_points/basic_winning_points.rs:48-284),
@@ -102,8 +117,6 @@ struct FdoLive {
     uint32_t last_winner;     // absolute seat that won the last completed trick
     uint32_t steps;           // play_action calls so far
     uint32_t ann_count;       // announcement decisions so far in this call (ordinal of SITE_ANNOUNCEMENT)
-    U4 ann_blk;               // cached Philox block of the announcement stream
-    uint32_t ann_blk_id;
 };
 
 DK_HD void fdo_rotate(FdoLive& g, uint32_t r) {  // new frame index i = old index (i + r) & 3
@@ -117,7 +130,7 @@ DK_HD void fdo_rotate(FdoLive& g, uint32_t r) {  // new frame index i = old inde
 DK_HD void fdo_live_clear(FdoLive& g) {
     g.h0 = g.h1 = g.h2 = g.h3 = g.dup = 0; g.base = 0; g.eyes = g.ntricks = g.dkc = g.foxes = 0; g.trump = 0; g.gt = 15;
     g.team_tag = TEAM_IN_RESERVATIONS; g.re_mask = 0; g.wed_seat = 0; g.solved_idx = 0; g.re_low = g.ko_low = 0; g.karl = 0;
-    g.last_winner = 0; g.steps = 0; g.ann_count = 0; g.ann_blk_id = 0xFFFFFFFFu; g.ann_blk.x = g.ann_blk.y = g.ann_blk.z = g.ann_blk.w = 0;
+    g.last_winner = 0; g.steps = 0; g.ann_count = 0;
 }
 
 // Deal: start seat = draw(4) from word 0 of SITE_DEAL, then a Durstenfeld shuffle (i = 47..1, j = draw(i+1), swap) of
@@ -219,22 +232,38 @@ DK_HD uint32_t fdo_pick_reservation(uint32_t h, uint32_t dup, uint32_t word) {
 // BIT each: decision k of the call is bit (k & 31) of word (k >> 5) of the SITE_ANNOUNCEMENT stream.  Block 0 (128 decisions; the
 // longest game seen in 2x10^5 has 47) is computed in lock-step by all lanes before the data-dependent replay loop, so the loop
 // contains no Philox code; later blocks are fetched on demand.
-struct AnnStream { U4 w; uint32_t blk; };
-// `m` (<= 4) consecutive decision bits starting at decision `ord` (bit k of the stream = bit (k & 31) of word (k >> 5)).
-DK_HD uint32_t fdo_ann_bits(AnnStream& st, const RngKey& key, uint32_t ord, uint32_t m) {
-    if (((ord + 3u) >> 7) == (ord >> 7)) {                        // the window lies in one 128-bit block (always, in practice)
-        if ((ord >> 7) != st.blk) { st.blk = ord >> 7; st.w = rng_block(key, SITE_ANNOUNCEMENT, st.blk); }
-        uint32_t wi = (ord >> 5) & 3u;
-        uint32_t lo = u4_word(st.w, wi), hi = u4_word(st.w, (wi + 1u) & 3u);   // hi is only used when the window stays inside the block
-        return funnel_r(lo, hi, ord & 31u) & ((1u << m) - 1u);
+// The replay loop reads the stream through a 64-bit shift buffer: peek = one AND, consume = one 64-bit shift; a 32-bit word is
+// appended (rare branch, about once per 28 decisions) whenever fewer than 4 bits are left.
+struct AnnBits {
+    uint64_t buf;      // decisions [ord, ord + avail) of the stream, LSB first
+    uint32_t avail;    // valid bits in buf (>= 4 between calls)
+    uint32_t next;     // index of the next 32-bit word to append (word k = decisions 32k .. 32k+31 = word k & 3 of block k >> 2)
+    U4 w;              // cached Philox block
+    uint32_t blk;
+};
+DK_HD void fdo_ann_refill(AnnBits& st, const RngKey& key) {
+    while (st.avail <= 32u) {
+        if ((st.next >> 2) != st.blk) { st.blk = st.next >> 2; st.w = rng_block(key, SITE_ANNOUNCEMENT, st.blk); }
+        st.buf |= (uint64_t)u4_word(st.w, st.next & 3u) << st.avail;
+        st.avail += 32u;
+        st.next++;
     }
-    uint32_t r = 0;                                               // window straddles two blocks: bit by bit
-    for (uint32_t i = 0; i < m; ++i) {
-        uint32_t k = ord + i;
-        if ((k >> 7) != st.blk) { st.blk = k >> 7; st.w = rng_block(key, SITE_ANNOUNCEMENT, st.blk); }
-        r |= ((u4_word(st.w, (k >> 5) & 3u) >> (k & 31u)) & 1u) << i;
-    }
-    return r;
+}
+// Position the buffer at decision `ord`; computes the Philox block that holds it (in lock-step, before the data-dependent loop).
+DK_HD void fdo_ann_open(AnnBits& st, const RngKey& key, uint32_t ord) {
+    st.blk = ord >> 7;
+    st.w = rng_block(key, SITE_ANNOUNCEMENT, st.blk);
+    const uint32_t wi = ord >> 5;
+    st.buf = (uint64_t)(u4_word(st.w, wi & 3u) >> (ord & 31u));
+    st.avail = 32u - (ord & 31u);
+    st.next = wi + 1u;
+    fdo_ann_refill(st, key);
+}
+DK_HD uint32_t fdo_ann_peek(const AnnBits& st, uint32_t m) { return (uint32_t)st.buf & ((1u << m) - 1u); }   // m <= 4 decisions
+DK_HD void fdo_ann_consume(AnnBits& st, const RngKey& key, uint32_t n) {
+    st.buf >>= n;
+    st.avail -= n;
+    if (st.avail < 4u) fdo_ann_refill(st, key);
 }
 
 // The loop advances by SEGMENTS: from (seat p, `turns` consecutive no's) the next 4 - turns seats are visited unless somebody
@@ -242,7 +271,7 @@ DK_HD uint32_t fdo_ann_bits(AnnStream& st, const RngKey& key, uint32_t ord, uint
 // card); otherwise the first set bit is a call, which changes the levels and restarts the count.  Iterations per lane =
 // #calls + #rounds (about 16) instead of #asks + #rounds (about 26), and there is no Philox code inside the loop.
 template <bool WITH_ANN>
-DK_HD void fdo_replay_announcements(FdoLive& g, const RngKey& key, uint32_t starts, uint32_t ci, uint32_t p, uint32_t turns) {
+DK_HD void fdo_replay_announcements(FdoLive& g, const RngKey& key, uint32_t starts, uint32_t ci, uint32_t p, uint32_t turns, const uint32_t* __restrict__ lut) {
     const bool wedding = g.team_tag == TEAM_WEDDING_SOLVED;       // (an unsolved wedding cannot survive trick 2)
     const uint32_t w = wedding ? g.solved_idx : 0u;
     const uint32_t first_ci = wedding ? 4u * (g.solved_idx + 1u) : 0u;   // no calls while the wedding is unsolved
@@ -254,9 +283,9 @@ DK_HD void fdo_replay_announcements(FdoLive& g, const RngKey& key, uint32_t star
     if (ci >= 48u) return;
     const uint32_t re = g.re_mask & 15u;
     uint32_t re_low = g.re_low, ko_low = g.ko_low, ord = g.ann_count;
-    uint32_t thr_re = fdo_min_cards_to_call(re_low, ko_low, w), thr_ko = fdo_min_cards_to_call(ko_low, re_low, w);
-    AnnStream st; st.blk = 0; st.w.x = st.w.y = st.w.z = st.w.w = 0;
-    if (WITH_ANN) st.w = rng_block(key, SITE_ANNOUNCEMENT, 0);     // lock-step: every lane fetches block 0 before the loop
+    uint32_t thr_re = fdo_min_cards_to_call_lut(re_low, ko_low, w, lut), thr_ko = fdo_min_cards_to_call_lut(ko_low, re_low, w, lut);
+    AnnBits st; st.buf = 0; st.avail = 0; st.next = 0; st.blk = 0; st.w.x = st.w.y = st.w.z = st.w.w = 0;
+    if (WITH_ANN) fdo_ann_open(st, key, ord);                      // lock-step: every lane fetches its block (block 0 for a fresh game) before the loop
     // per-position values (recomputed when ci advances)
     uint32_t cmax = 12u - (ci >> 2);
     uint32_t base = (starts >> (2u * (ci >> 2))) & 3u;
@@ -269,9 +298,10 @@ DK_HD void fdo_replay_announcements(FdoLive& g, const RngKey& key, uint32_t star
         uint32_t rot = ((elig | (elig << 4)) >> p) & 15u;         // bit d: seat p + d is eligible
         uint32_t win = rot & ((1u << (4u - turns)) - 1u);         // the seats visited before the count reaches 4
         uint32_t m = popc(win);
-        uint32_t hit = (WITH_ANN && m) ? fdo_ann_bits(st, key, ord, m) : 0u;
+        uint32_t hit = (WITH_ANN && m) ? fdo_ann_peek(st, m) : 0u;
         if (hit == 0u) {                                          // everybody passes: RoundIsOver → card ci is played; next round
             ord += m;
+            if (WITH_ANN) fdo_ann_consume(st, key, m);
             ci++;
             if (ci >= 48u) break;
             cmax = 12u - (ci >> 2);
@@ -283,6 +313,7 @@ DK_HD void fdo_replay_announcements(FdoLive& g, const RngKey& key, uint32_t star
         }
         uint32_t j = ffs0(hit);                                   // j eligible seats pass, the (j+1)-th calls
         ord += j + 1u;
+        fdo_ann_consume(st, key, j + 1u);
         uint32_t wj = win;                                        // distance of the (j+1)-th eligible seat from p: win has <= 4 bits,
         if (j > 0u) wj &= wj - 1u;                                //   so clearing the lowest set bit j times beats a generic rank select
         if (j > 1u) wj &= wj - 1u;
@@ -295,7 +326,7 @@ DK_HD void fdo_replay_announcements(FdoLive& g, const RngKey& key, uint32_t star
         ml = ml == 6u ? 0u : ml;
         uint32_t call = (ml < 5u && c + ml + w >= 11u) ? ml + 1u : 1u;   // next level, else the counter (recorded as Re/Kontra)
         if (is_re) re_low = call; else ko_low = call;             // announcement.rs:203-210
-        thr_re = fdo_min_cards_to_call(re_low, ko_low, w); thr_ko = fdo_min_cards_to_call(ko_low, re_low, w);
+        thr_re = fdo_min_cards_to_call_lut(re_low, ko_low, w, lut); thr_ko = fdo_min_cards_to_call_lut(ko_low, re_low, w, lut);
         turns = 0;
         p = (p + 1u) & 3u;
     }
@@ -421,8 +452,8 @@ DK_HD void fdo_play_to_end(FdoLive& g, const RngKey& key, const FdoResume* rs, c
         fdo_trick_done(g, a, t);
     }
     // announcement rounds (see fdo_replay_announcements): fresh games start with the round before card 0
-    if (FRESH) fdo_replay_announcements<WITH_ANN>(g, key, starts, 0u, starts & 3u, 0u);
-    else fdo_replay_announcements<WITH_ANN>(g, key, starts, rs->ann_ci, rs->ann_p, rs->ann_turns);
+    if (FRESH) fdo_replay_announcements<WITH_ANN>(g, key, starts, 0u, starts & 3u, 0u, lut);
+    else fdo_replay_announcements<WITH_ANN>(g, key, starts, rs->ann_ci, rs->ann_p, rs->ann_turns, lut);
 }
 
 // Fresh game: deal + reservations + 12 tricks + scoring.

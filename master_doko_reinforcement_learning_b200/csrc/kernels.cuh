@@ -37,6 +37,7 @@ struct SharedDeck {
 // Stage the 24-entry card attribute table in shared memory (first 24 threads), then sync.
 __device__ __forceinline__ void fill_card_lut(uint32_t* lut) {       // needs blockDim.x >= 64; caller syncs
     if (threadIdx.x < 24) lut[threadIdx.x] = card_lut_entry(threadIdx.x);
+    else if (threadIdx.x < 31) lut[threadIdx.x] = fdo_thr_lut_word(threadIdx.x - THR_LUT_BASE);
     if (threadIdx.x < 64) lut[RANK_LUT_BASE + threadIdx.x] = rank_lut6_entry(threadIdx.x);
 }
 __device__ __forceinline__ void stage_card_lut(uint32_t* lut) {

@@ -33,7 +33,7 @@ struct LocalDeck {
 const uint32_t* card_lut() {
     static uint32_t lut[dk::CARD_LUT_WORDS];
     static bool init = false;
-    if (!init) { for (uint32_t c = 0; c < 24; ++c) lut[c] = dk::card_lut_entry(c); for (uint32_t b = 0; b < 64; ++b) lut[dk::RANK_LUT_BASE + b] = dk::rank_lut6_entry(b); init = true; }
+    if (!init) { for (uint32_t c = 0; c < 24; ++c) lut[c] = dk::card_lut_entry(c); for (uint32_t b = 0; b < 64; ++b) lut[dk::RANK_LUT_BASE + b] = dk::rank_lut6_entry(b); for (uint32_t m = 0; m < 7; ++m) lut[dk::THR_LUT_BASE + m] = dk::fdo_thr_lut_word(m); init = true; }
     return lut;
 }
 dk::RngKey make_key(uint64_t seed, uint64_t unit, uint32_t epoch) {
@@ -143,8 +143,12 @@ SIM_API uint32_t sim_doko_assign(const dk_state* s, uint64_t seed, uint64_t unit
 
 SIM_API uint32_t sim_fdo_ann_bits(uint64_t seed, uint64_t unit, uint32_t epoch, uint32_t ord, uint32_t m) {
     dk::RngKey key = make_key(seed, unit, epoch);
-    dk::AnnStream st; st.blk = 0; st.w = dk::rng_block(key, dk::SITE_ANNOUNCEMENT, 0);
-    return dk::fdo_ann_bits(st, key, ord, m);
+    // walk the stream in steps of 3 from the start so that consume / refill are exercised, then peek at `ord`
+    dk::AnnBits st; dk::fdo_ann_open(st, key, ord % 3u);
+    for (uint32_t k = ord % 3u; k < ord; k += 3u) dk::fdo_ann_consume(st, key, 3u);
+    uint32_t walked = dk::fdo_ann_peek(st, m);
+    dk::AnnBits direct; dk::fdo_ann_open(direct, key, ord);
+    return walked == dk::fdo_ann_peek(direct, m) ? walked : 0xFFFFFFFFu;
 }
 
 // ---- PIMC (pimc.cuh + the per-thread body of fdo_pimc_kernel, run sequentially) -------------------------------------------------------
@@ -226,4 +230,7 @@ SIM_API uint32_t sim_fdo_uct_search(const dk_state* root, uint64_t seed, uint64_
     return 0;
 }
 SIM_API uint64_t sim_uct_allowed(const dk_state* s, int first) { return dk::uct_allowed(*s, first != 0); }
-SIM_API uint32_t sim_fdo_min_cards_to_call(uint32_t m, uint32_t e, uint32_t w) { return dk::fdo_min_cards_to_call(m, e, w); }
+SIM_API uint32_t sim_fdo_min_cards_to_call(uint32_t m, uint32_t e, uint32_t w) {
+    uint32_t a = dk::fdo_min_cards_to_call(m, e, w), b = dk::fdo_min_cards_to_call_lut(m, e, w, card_lut());
+    return a == b ? a : 0xFFFFFFFFu;     // closed form and table form must agree
+}
