@@ -1,7 +1,7 @@
 set -x
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; tail -3 gpurun_out/pytest_gpu.log
-timeout 600 python profiles/bench_kernels.py > gpurun_out/kernels_v11.json 2> gpurun_out/kernels_v11.err; head -c 600 gpurun_out/kernels_v11.json; tail -3 gpurun_out/kernels_v11.err
-python profiles/profile_playout.py > gpurun_out/plain_playout.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:fdo_playout_fresh -s 2 -c 1 -o gpurun_out/prof_fdo_playout_v6 python profiles/profile_playout.py > gpurun_out/ncu_playout.log 2>&1
-tail -2 gpurun_out/ncu_playout.log
+python bench.py > gpurun_out/bench_v6.json 2> gpurun_out/bench_v6.err; tail -c 3000 gpurun_out/bench_v6.json; tail -3 gpurun_out/bench_v6.err
+python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_v6_ref.json 2> gpurun_out/bench_v6_ref.err; tail -c 1200 gpurun_out/bench_v6_ref.json
+python bench.py --steps 2 --warmup 1 > gpurun_out/b.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_v6.csv python bench.py --steps 2 --warmup 1 > gpurun_out/ncu_bench.log 2>&1
+tail -2 gpurun_out/ncu_bench.log | cut -c1-300
