@@ -120,6 +120,21 @@ class EnvBatch {
         ctx_.check(dk_pimc_evaluate(ctx_.get(), len(), n_det, n_rollouts, states(), &rng, visits_out_dev, value_sum_out_dev, status_out_dev, stream), "dk_pimc_evaluate");
     }
 
+    // EvFullDokoMCTSPolicy::evaluate for every game (mcts_policy.rs:76-118): one UCT tree per (game, d); determinize = CAPSampling first.
+    // workspace: dk_uct_workspace_bytes(len() * trees_per_game, iterations) bytes of device memory.
+    void monte_carlo_tree_search(const dk_rng& rng, size_t trees_per_game, bool determinize, size_t iterations, float uct_exploration_constant, void* workspace_dev,
+                                 size_t workspace_bytes, uint32_t* visits_out_dev, float* values_out_dev, uint8_t* action_out_dev, uint8_t* status_out_dev,
+                                 dk_stream stream = nullptr) const {
+        ctx_.check(dk_uct_search(ctx_.get(), len(), trees_per_game, determinize ? 1 : 0, iterations, uct_exploration_constant, states(), &rng, workspace_dev,
+                                 workspace_bytes, visits_out_dev, values_out_dev, action_out_dev, status_out_dev, stream), "dk_uct_search");
+    }
+    // encode_state_ipi for the whole batch (guessed hands / reservations by absolute seat, seat to guess for)
+    void encode_ipi(const uint64_t* assumed_hands_dev, const uint8_t* assumed_reservations_dev, const uint8_t* next_player_dev, int64_t* out_dev, size_t row_stride,
+                    uint8_t* err_out_dev = nullptr, dk_stream stream = nullptr) const {
+        ctx_.check(dk_encode_ipi(ctx_.get(), len(), states(), assumed_hands_dev, assumed_reservations_dev, next_player_dev, out_dev, row_stride, err_out_dev, stream),
+                   "dk_encode_ipi");
+    }
+
    private:
     Context& ctx_;
     int engine_;
