@@ -1,7 +1,4 @@
 set -x
 mkdir -p gpurun_out
-python bench.py > gpurun_out/bench_v6.json 2> gpurun_out/bench_v6.err; tail -c 3000 gpurun_out/bench_v6.json; tail -3 gpurun_out/bench_v6.err
-python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_v6_ref.json 2> gpurun_out/bench_v6_ref.err; tail -c 1200 gpurun_out/bench_v6_ref.json
-python bench.py --steps 2 --warmup 1 > gpurun_out/b.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_v6.csv python bench.py --steps 2 --warmup 1 > gpurun_out/ncu_bench.log 2>&1
-tail -2 gpurun_out/ncu_bench.log | cut -c1-300
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/multigpu_check.py > gpurun_out/multigpu_check_v2.txt 2>&1; tail -3 gpurun_out/multigpu_check_v2.txt
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 5 --warmup 3 > gpurun_out/bench_v6_2gpu.json 2> gpurun_out/bench_v6_2gpu.err; tail -c 900 gpurun_out/bench_v6_2gpu.json

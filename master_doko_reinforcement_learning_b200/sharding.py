@@ -26,3 +26,31 @@ def leaf_rollout_root_stats(dk, states, rollouts_per_leaf, rng_seed, first_id=0,
     if world > 1:
         dk.allreduce_root_stats(sums)
     return sums
+
+
+def pimc_decide(dk, states, n_det, strategy, rng_seed, first_id=0, epoch=0, n_rollouts=None, uct_iterations=None, uct_c=1.4, group=None):
+    """Sharded PIMC move decision (DefaultImpiPolicy::execute, compare_impi.rs:212-372): every rank takes a contiguous share of the
+    determinizations of EVERY root (sample numbers first_sub .. first_sub+count-1), evaluates them with the flat Monte-Carlo policy
+    (`n_rollouts`) or the UCT search (`uct_iterations`), reduces them to integer root statistics, all-reduces those and picks.
+    All ranks return the same actions (uint8 [n], 0xFF = no successful sample)."""
+    import torch.distributed as dist
+
+    world, rank = (dist.get_world_size(group), dist.get_rank(group)) if dist.is_available() and dist.is_initialized() else (1, 0)
+    first_sub, count = shard_range(n_det, rank, world)
+    allowed = dk.legal_mask(1, states)
+    stats = None
+    if count > 0:
+        rng = dk.rng(rng_seed, first_id, epoch, first_sub)
+        if uct_iterations is not None:
+            visits, _, _, status = dk.uct_search(states, uct_iterations, uct_c, rng, trees_per_root=count, determinize=True)
+        else:
+            visits, _, status = dk.pimc_evaluate(states, count, n_rollouts, rng, want_values=False)
+        stats = dk.pimc_root_stats(visits, allowed, status)
+    else:
+        import torch
+
+        from .api import ROOT_STATS
+        stats = torch.zeros((states.shape[0], ROOT_STATS), dtype=torch.int64, device=states.device)
+    if world > 1:
+        dk.allreduce_root_stats(stats)
+    return dk.pimc_pick(strategy, stats, allowed), stats

@@ -1,6 +1,7 @@
 #!/usr/bin/env python3
 """torchrun --nproc-per-node N tests/multigpu_check.py — on-GPU multi-rank check (run with `gpurun --gpus N`):
-sharded leaf rollouts + dk_allreduce_root_stats equal the single-GPU result, on every rank."""
+sharded leaf rollouts + dk_allreduce_root_stats equal the single-GPU result, and the sharded PIMC decisions (flat Monte-Carlo and UCT per
+determinization → root statistics → all-reduce → pick) equal the single-GPU fuse, on every rank."""
 import os
 import sys
 
@@ -13,7 +14,7 @@ def main():
     import torch.distributed as dist
 
     import master_doko_reinforcement_learning_b200 as pkg
-    from master_doko_reinforcement_learning_b200.sharding import leaf_rollout_root_stats
+    from master_doko_reinforcement_learning_b200.sharding import leaf_rollout_root_stats, pimc_decide
 
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -36,6 +37,16 @@ def main():
     full = dk.leaf_rollouts(states, R, dk.rng(seed, 0, 7), determinize=True)      # all rollouts on this GPU
     torch.cuda.synchronize()
     ok = torch.equal(sums, full)
+    # sharded PIMC decisions (flat MC and UCT per determinization) == the single-GPU fuse over all determinizations
+    roots, n_det = states[:256], 16
+    allowed = dk.legal_mask(pkg.DK_FDO, roots)
+    for strategy in (pkg.FUSE_MAX_N, pkg.FUSE_AVERAGE):
+        act, _ = pimc_decide(dk, roots, n_det, strategy, seed, first_id=0, epoch=8, n_rollouts=32)
+        v, _, st = dk.pimc_evaluate(roots, n_det, 32, dk.rng(seed, 0, 8), want_values=False)
+        ok = ok and torch.equal(act, dk.fuse(strategy, v, allowed, st)[0])
+    act, _ = pimc_decide(dk, roots, n_det, pkg.FUSE_MAX_N, seed, first_id=0, epoch=9, uct_iterations=64)
+    v, _, _, st = dk.uct_search(roots, 64, 1.4, dk.rng(seed, 0, 9), trees_per_root=n_det, determinize=True)
+    ok = ok and torch.equal(act, dk.fuse(pkg.FUSE_MAX_N, v, allowed, st)[0])
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:

@@ -71,3 +71,62 @@ def test_root_stats_sum_over_two_ranks_gloo():
     ret = mgr.dict()
     mp.spawn(_worker, args=(2, port, ret), nprocs=2, join=True)
     assert ret.get("ok") is True
+
+
+def _pimc_worker(rank, world, port, ret):
+    import torch
+    import torch.distributed as dist
+
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import hostsim_lib
+    import oracle_lib
+    from oracle_lib import Fdo
+
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    L, sim = oracle_lib.load(), hostsim_lib.load()
+    seed, n_roots, n_det, R = 7, 5, 9, 8
+    roots = []
+    for i in range(n_roots):
+        o = Fdo.new_game_philox(L, seed, i, 0)
+        for k in range(6 + 7 * i):
+            o.random_step(seed, i, 0, True, k)
+        roots.append(o)
+    first_sub, count = shard_range(n_det, rank, world)
+    stats = np.zeros((n_roots, 80), dtype=np.int64)
+    for i, o in enumerate(roots):
+        rows = np.zeros((count, 39), dtype=np.uint32)
+        status = np.zeros(count, dtype=np.uint8)
+        for d in range(count):
+            st, vis, _ = o.flat_mc(seed, 100 + i, first_sub + d, R, 2)
+            rows[d], status[d] = vis, st
+        if count:
+            sim.sim_root_stats(hostsim_lib.ptr(rows), hostsim_lib.ptr(status), count, o.allowed(), hostsim_lib.ptr(stats[i]))
+    t = torch.from_numpy(stats.copy())
+    dist.all_reduce(t)                                   # the exchange step: integer sum of [roots][80] statistics
+    total = t.numpy()
+    if rank == 0:
+        ok = True
+        for i, o in enumerate(roots):
+            rows = [o.flat_mc(seed, 100 + i, d, R, 2) for d in range(n_det)]
+            good = np.array([v for st, v, _ in rows if st == 0])
+            for strategy in (0, 1):                      # R = 8: every row total is a power of two, so Average agrees exactly as well
+                pick = sim.sim_root_pick(strategy, hostsim_lib.ptr(np.ascontiguousarray(total[i])), o.allowed())
+                ok = ok and pick == oracle_lib.fuse(L, strategy, good, o.allowed())
+        ret["ok"] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_pimc_decision_over_two_ranks_gloo():
+    """Each rank evaluates its share of the determinizations (oracle rows as a stand-in for the kernel), reduces them to the additive
+    root statistics, gloo all-reduces them, and the pick equals the PolicyFusion decision over all determinizations."""
+    import torch.multiprocessing as mp
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_pimc_worker, args=(2, port, ret), nprocs=2, join=True)
+    assert ret.get("ok") is True
