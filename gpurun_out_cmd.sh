@@ -1,4 +1,5 @@
 set -x
 mkdir -p gpurun_out
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/multigpu_check.py > gpurun_out/multigpu_check_v2.txt 2>&1; tail -3 gpurun_out/multigpu_check_v2.txt
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 5 --warmup 3 > gpurun_out/bench_v6_2gpu.json 2> gpurun_out/bench_v6_2gpu.err; tail -c 900 gpurun_out/bench_v6_2gpu.json
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; tail -3 gpurun_out/pytest_gpu.log
+timeout 900 python profiles/bench_uct.py > gpurun_out/uct_v4.json 2> gpurun_out/uct_v4.err; cat gpurun_out/uct_v4.json; tail -3 gpurun_out/uct_v4.err
+timeout 600 python profiles/bench_kernels.py > gpurun_out/kernels_v13.json 2> gpurun_out/kernels_v13.err; tail -c 900 gpurun_out/kernels_v13.json; tail -3 gpurun_out/kernels_v13.err

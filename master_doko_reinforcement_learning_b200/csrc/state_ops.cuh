@@ -272,8 +272,15 @@ DK_HD bool fdo_state_to_live(const dk_state& s, FdoLive& g, FdoResume& rs) {
         for (uint32_t p = 0; p < 4u; ++p) { g.eyes |= (uint32_t)s.eyes[p] << (8u * p); }
         g.ntricks = s.num_tricks;
         for (uint32_t t = 0; t < t0; ++t) {                                  // trackers of the completed tricks
-            uint32_t e, fm, w = st_trick_start(s, t + 1u);
-            (void)fdo_state_trick_winner(s, t, g.trump, nullptr, &e, &fm);
+            // the winner of trick t leads trick t + 1, so only the eyes and the ♦A positions have to be re-read from the cards
+            uint32_t e = 0, fm = 0, w = st_trick_start(s, t + 1u);
+            const uint32_t quad = reinterpret_cast<const uint32_t*>(s.cards)[t];     // the trick's four cards (cards[] sits at byte 32 of the record)
+#pragma unroll
+            for (uint32_t k = 0; k < 4u; ++k) {
+                const uint32_t c = (quad >> (8u * k)) & 255u;
+                e += card_eyes_by_rank(c - 6u * card_suit(c));
+                fm |= (c == CARD_DA ? 1u : 0u) << k;
+            }
             if (e >= 40u) g.dkc += 1u << (4u * w);
             g.foxes = fdo_fox_record(g.foxes, fm, st_trick_start(s, t), w);
             rs.starts |= st_trick_start(s, t) << (2u * t);

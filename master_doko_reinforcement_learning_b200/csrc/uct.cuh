@@ -83,11 +83,37 @@ DK_HD void uct_init_node(UctNode& n, const dk_state& s, uint32_t parent, uint32_
     const bool terminal = st_phase(s) == DK_PHASE_FINISHED;
     n.info = uct_allowed(s, root) | ((uint64_t)(terminal ? 0u : st_cur(s)) << 40) | ((uint64_t)(terminal ? 1u : 0u) << 42) | ((uint64_t)(last_action & 63u) << 48);
 }
-DK_HD double uct_q(const UctNode& c) { return c.visits > 0u ? dk_ddiv((double)c.win, (double)c.visits) : 0.0; }
 
-// find_best_child (node.rs:258-278) with uct (:238-256) and min_max_normalized_q (:202-236) of every child.  The children's
-// (visits, win) pairs are fetched first, all loads in flight together (one memory round trip per tree level instead of one per child).
-DK_HD uint32_t uct_find_best_child(const UctNode* __restrict__ pool, uint32_t self, double c, const double* __restrict__ ln_table) {
+DK_HD float dk_fdiv_fast(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return __fdividef(a, b);          // <= 2 ulp; the filter's error budget below allows far more
+#else
+    return a / b;
+#endif
+}
+
+// Exact UCT value of one child (node.rs:238-256 with min_max_normalized_q :202-236) from exact min / max Q of its siblings.
+DK_HD double uct_value_exact(long long win, uint32_t vis, double min_q, double span, bool flat, double ln_n, double c) {
+    if (vis == 0u) return dk_inf();
+    const double q = dk_ddiv((double)win, (double)vis);
+    const double norm_q = flat ? 1.0 : dk_dadd(dk_ddiv(dk_dmul(2.0, dk_dadd(q, -min_q)), span), -1.0);
+    return dk_dadd(norm_q, dk_dmul(c, dk_dsqrt(dk_ddiv(ln_n, (double)vis))));
+}
+
+// find_best_child (node.rs:258-278): the child with the strictly greatest f64 UCT value, first in child order among equals.
+//
+// The children's (visits, win) pairs are fetched first, all loads in flight together (one memory round trip per tree level).
+// The f64 divisions and square roots of the reference are software sequences of ~30 instructions each on the GPU, so the
+// decision is taken in two stages that TOGETHER are bit-identical to evaluating every child in f64:
+//   1. a cheap f32 evaluation u~ with a proven error bound |u~ - u| <= eps.  Only children with u~ >= max(u~) - 2 eps can be the
+//      exact arg-max (and all exact ties are among them).  Almost always exactly one child survives and is returned — no f64 at all.
+//      Bound: Q = win / visits with |Q| <= 128 has an absolute f32 error <= 5e-5, hence numerator and span of the normalisation
+//      <= 1.2e-4 each and the normalised Q <= 5e-4 / span~ + 1e-6; the exploration term has a relative error <= 5e-7 and a
+//      magnitude <= 4.64 c (N < 2^31).  eps = 1e-3 / span~ + 4e-5 c + 4e-5 leaves a factor >= 2 everywhere; the filter is skipped
+//      when span~ < 4e-3 or a child has no visits.
+//   2. the survivors are evaluated exactly.  The exact min / max Q come from the children that are minimal / maximal as RATIONALS
+//      (integer cross-multiplication; IEEE division is monotone, so the rounded extremes are the extremes of the rounded values).
+DK_HD uint32_t uct_find_best_child(const UctNode* __restrict__ pool, uint32_t self, double c, double ln_n, bool use_filter = true) {   // ln_n = ln(visits of `self`)
     const UctNode& p = pool[self];
     const uint32_t nch = uct_n_children(p);
     uint32_t idx[UCT_MAX_CHILDREN], vis[UCT_MAX_CHILDREN];
@@ -96,32 +122,67 @@ DK_HD uint32_t uct_find_best_child(const UctNode* __restrict__ pool, uint32_t se
     for (uint32_t k = 0; k < UCT_MAX_CHILDREN; ++k) idx[k] = k < nch ? p.child[k] : self;
 #pragma unroll
     for (uint32_t k = 0; k < UCT_MAX_CHILDREN; ++k) { vis[k] = pool[idx[k]].visits; win[k] = pool[idx[k]].win; }
-    double min_q = dk_inf(), max_q = -dk_inf();
+    uint32_t cand = (1u << nch) - 1u;
+    {   // stage 1: f32 filter
+        float qf[UCT_MAX_CHILDREN];
+        float minf = 3.0e38f, maxf = -3.0e38f;
+        bool any_unvisited = false;
 #pragma unroll
-    for (uint32_t k = 0; k < UCT_MAX_CHILDREN; ++k) {
-        if (k < nch) {
-            double q = vis[k] > 0u ? dk_ddiv((double)win[k], (double)vis[k]) : 0.0;
-            if (q < min_q) min_q = q;
-            if (q > max_q) max_q = q;
+        for (uint32_t k = 0; k < UCT_MAX_CHILDREN; ++k) {
+            const bool on = k < nch;
+            any_unvisited |= on && vis[k] == 0u;
+            const float qk = dk_fdiv_fast((float)win[k], (float)(vis[k] ? vis[k] : 1u));
+            qf[k] = qk;
+            if (on && qk < minf) minf = qk;
+            if (on && qk > maxf) maxf = qk;
+        }
+        const float spanf = maxf - minf;
+        if (use_filter && !any_unvisited && spanf >= 4.0e-3f && p.visits < (1u << 24)) {
+            const float cf = (float)c, lnf = (float)ln_n;
+            const float eps = dk_fdiv_fast(1.0e-3f, spanf) + 4.0e-5f * cf + 4.0e-5f;
+            const float scale = dk_fdiv_fast(2.0f, spanf);
+            float uf[UCT_MAX_CHILDREN];
+            float top = -3.0e38f;
+#pragma unroll
+            for (uint32_t k = 0; k < UCT_MAX_CHILDREN; ++k) {
+                const float u = (qf[k] - minf) * scale - 1.0f + cf * sqrtf(dk_fdiv_fast(lnf, (float)(vis[k] ? vis[k] : 1u)));
+                uf[k] = u;
+                if (k < nch && u > top) top = u;
+            }
+            const float thr = top - 2.0f * eps;
+            uint32_t m = 0;
+#pragma unroll
+            for (uint32_t k = 0; k < UCT_MAX_CHILDREN; ++k) m |= (k < nch && uf[k] >= thr) ? (1u << k) : 0u;
+            cand = m;
+            if ((m & (m - 1u)) == 0u) {                                   // a single survivor: it is the exact arg-max
+                uint32_t best = self;
+#pragma unroll
+                for (uint32_t k = 0; k < UCT_MAX_CHILDREN; ++k) if ((m >> k) & 1u) best = idx[k];
+                return best;
+            }
         }
     }
+    // stage 2: exact evaluation of the survivors.  Extremes of Q as rationals: win_a / vis_a < win_b / vis_b  <=>  win_a vis_b < win_b vis_a
+    // (unvisited children count as Q = 0 = 0 / 1).
+    long long lo_w = 0, hi_w = 0;
+    uint32_t lo_v = 0, hi_v = 0;
+#pragma unroll 1
+    for (uint32_t k = 0; k < nch; ++k) {
+        const long long w = vis[k] ? win[k] : 0;
+        const uint32_t v = vis[k] ? vis[k] : 1u;
+        if (lo_v == 0u || w * (long long)lo_v < lo_w * (long long)v) { lo_w = w; lo_v = v; }
+        if (hi_v == 0u || w * (long long)hi_v > hi_w * (long long)v) { hi_w = w; hi_v = v; }
+    }
+    const double min_q = dk_ddiv((double)lo_w, (double)lo_v), max_q = dk_ddiv((double)hi_w, (double)hi_v);
     const double span = dk_dadd(max_q, -min_q);
     const bool flat = fabs(span) < 2.220446049250313e-16;            // f64::EPSILON
-    const double ln_n = ln_table[p.visits];
     double best_uct = -dk_inf();
     uint32_t best = UCT_NONE;
-#pragma unroll
-    for (uint32_t k = 0; k < UCT_MAX_CHILDREN; ++k) {
-        if (k < nch) {
-            double u;
-            if (vis[k] == 0u) u = dk_inf();
-            else {
-                double q = dk_ddiv((double)win[k], (double)vis[k]);
-                double norm_q = flat ? 1.0 : dk_dadd(dk_ddiv(dk_dmul(2.0, dk_dadd(q, -min_q)), span), -1.0);
-                u = dk_dadd(norm_q, dk_dmul(c, dk_dsqrt(dk_ddiv(ln_n, (double)vis[k]))));
-            }
-            if (u > best_uct) { best_uct = u; best = idx[k]; }
-        }
+#pragma unroll 1
+    for (uint32_t k = 0; k < nch; ++k) {
+        if (!((cand >> k) & 1u)) continue;
+        const double u = uct_value_exact(win[k], vis[k], min_q, span, flat, ln_n, c);
+        if (u > best_uct) { best_uct = u; best = idx[k]; }
     }
     return best;
 }
@@ -135,7 +196,7 @@ DK_HD uint32_t uct_iteration(UctNode* __restrict__ pool, uint32_t& n_nodes, cons
     for (;;) {                                                                   // select_promising_node (:45-63)
         const UctNode& n = pool[node];
         if (uct_n_children(n) == 0u || (n.info & UCT_ACTION_MASK) != 0ull) break;
-        node = uct_find_best_child(pool, node, c, ln_table);
+        node = uct_find_best_child(pool, node, c, ln_table[n.visits]);
     }
     uint32_t explore = node;
     const uint64_t unexpanded = pool[node].info & UCT_ACTION_MASK;

@@ -234,3 +234,15 @@ SIM_API uint32_t sim_fdo_min_cards_to_call(uint32_t m, uint32_t e, uint32_t w) {
     uint32_t a = dk::fdo_min_cards_to_call(m, e, w), b = dk::fdo_min_cards_to_call_lut(m, e, w, card_lut());
     return a == b ? a : 0xFFFFFFFFu;     // closed form and table form must agree
 }
+
+// find_best_child on a synthetic family: child index chosen with the f32 filter (low byte) and by the all-f64 evaluation (next byte)
+SIM_API uint32_t sim_uct_select_check(uint32_t nch, const uint32_t* vis, const long long* win, uint32_t parent_visits, float uct_c) {
+    std::vector<dk::UctNode> pool(nch + 1);
+    std::memset(pool.data(), 0, pool.size() * sizeof(dk::UctNode));
+    pool[0].visits = parent_visits; pool[0].parent = dk::UCT_NONE; pool[0].info = (uint64_t)nch << 56;
+    for (uint32_t k = 0; k < nch; ++k) { pool[0].child[k] = k + 1; pool[k + 1].visits = vis[k]; pool[k + 1].win = win[k]; pool[k + 1].parent = 0; }
+    const double ln_n = std::log((double)parent_visits);
+    uint32_t a = dk::uct_find_best_child(pool.data(), 0, (double)uct_c, ln_n, true);
+    uint32_t b = dk::uct_find_best_child(pool.data(), 0, (double)uct_c, ln_n, false);
+    return (a & 255u) | ((b & 255u) << 8);
+}

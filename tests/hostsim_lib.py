@@ -44,6 +44,8 @@ def load():
         L.sim_encode_ipi.argtypes = [vp, vp, vp, u32, vp]
         L.sim_fdo_uct_search.restype = u32
         L.sim_fdo_uct_search.argtypes = [vp, u64, u64, u32, u32, i32, u32, C.c_float, vp, vp, vp]
+        L.sim_uct_select_check.restype = u32
+        L.sim_uct_select_check.argtypes = [u32, vp, vp, u32, C.c_float]
         L.sim_uct_allowed.restype = u64
         L.sim_uct_allowed.argtypes = [vp, i32]
         L.sim_fuse.restype = u32

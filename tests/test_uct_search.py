@@ -112,3 +112,46 @@ def test_search_prefers_the_winning_card(orc):
         if found >= 5:
             break
     assert found >= 3
+
+
+def test_two_stage_selection_equals_all_f64_selection():
+    """uct_find_best_child takes the decision with an f32 filter + exact evaluation of the survivors; it must pick the same child as
+    evaluating every child in f64 (what the reference does), in particular on exact ties and on near ties below the f32 resolution."""
+    sim = hostsim_lib.load()
+    prng = np.random.default_rng(12)
+    n_cases = 0
+    for trial in range(40000):
+        nch = int(prng.integers(1, 13))
+        kind = trial % 8
+        if kind == 0:                                    # random statistics
+            vis = prng.integers(1, 2000, size=nch)
+            win = np.array([int(prng.integers(-60, 61)) * int(v) + int(prng.integers(-v, v + 1)) for v in vis])
+        elif kind == 1:                                  # exact ties: equal fractions with different denominators
+            base_v = int(prng.integers(1, 50)); base_w = int(prng.integers(-30, 31)) * base_v
+            mult = prng.integers(1, 4, size=nch)
+            vis = base_v * mult; win = base_w * mult
+            j = int(prng.integers(0, nch)); win[j] += int(prng.integers(-3, 4))
+        elif kind == 2:                                  # near ties far below f32 resolution: huge visit counts, win differs by one
+            v = int(prng.integers(1 << 18, 1 << 22))
+            vis = np.full(nch, v); win = np.full(nch, int(prng.integers(-20, 21)) * v) + prng.integers(-2, 3, size=nch)
+        elif kind == 3:                                  # tiny span
+            v = int(prng.integers(1000, 100000))
+            vis = np.full(nch, v) + prng.integers(0, 3, size=nch); win = vis * int(prng.integers(-10, 11)) + prng.integers(0, 2, size=nch)
+        elif kind == 4:                                  # young nodes: one or two visits each, small integer results
+            vis = prng.integers(1, 3, size=nch); win = np.array([int(prng.integers(-12, 13)) for _ in range(nch)]) * vis
+        elif kind == 5:                                  # some unvisited children
+            vis = prng.integers(0, 3, size=nch); win = prng.integers(-10, 11, size=nch) * vis
+        elif kind == 6:                                  # Q equal, exploration decides: visit counts differ by one
+            v = int(prng.integers(10, 5000)); q = int(prng.integers(-40, 41))
+            vis = v + prng.integers(0, 2, size=nch); win = q * vis
+        else:                                            # extremes of the value range
+            vis = prng.integers(1, 1 << 20, size=nch); win = vis * prng.choice([-127, 127, 0, 126], size=nch)
+        vis = np.ascontiguousarray(vis, dtype=np.uint32); win = np.ascontiguousarray(win, dtype=np.int64)
+        parent = int(vis.sum()) + 1
+        if parent >= 1 << 23:
+            parent = int(vis.max()) + 1
+        c = float(prng.choice([0.0, 0.1, 0.5, 1.4, 2.0, 4.0, 25.0]))
+        r = sim.sim_uct_select_check(nch, hostsim_lib.ptr(vis), hostsim_lib.ptr(win), parent, c)
+        assert (r & 255) == (r >> 8), (trial, kind, nch, vis, win, parent, c, r & 255, r >> 8)
+        n_cases += 1
+    assert n_cases == 40000
