@@ -1,5 +1,5 @@
 set -x
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; tail -3 gpurun_out/pytest_gpu.log
-timeout 900 python profiles/bench_uct.py > gpurun_out/uct_v4.json 2> gpurun_out/uct_v4.err; cat gpurun_out/uct_v4.json; tail -3 gpurun_out/uct_v4.err
-timeout 600 python profiles/bench_kernels.py > gpurun_out/kernels_v13.json 2> gpurun_out/kernels_v13.err; tail -c 900 gpurun_out/kernels_v13.json; tail -3 gpurun_out/kernels_v13.err
+python profiles/profile_playout.py --n 16777216 --launches 3 > gpurun_out/plain_playout_2p24.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:fdo_playout_fresh -s 2 -c 1 -o gpurun_out/prof_fdo_playout_v6_2p24 python profiles/profile_playout.py --n 16777216 --launches 3 > gpurun_out/ncu_playout_2p24.log 2>&1
+tail -2 gpurun_out/ncu_playout_2p24.log; tail -1 gpurun_out/plain_playout_2p24.log
