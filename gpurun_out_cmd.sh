@@ -1,5 +1,5 @@
 set -x
 mkdir -p gpurun_out
-python profiles/profile_playout.py --n 16777216 --launches 3 > gpurun_out/plain_playout_2p24.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:fdo_playout_fresh -s 2 -c 1 -o gpurun_out/prof_fdo_playout_v6_2p24 python profiles/profile_playout.py --n 16777216 --launches 3 > gpurun_out/ncu_playout_2p24.log 2>&1
-tail -2 gpurun_out/ncu_playout_2p24.log; tail -1 gpurun_out/plain_playout_2p24.log
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; tail -3 gpurun_out/pytest_gpu.log
+python profiles/sanitize_smoke.py > gpurun_out/smoke.log 2>&1; tail -2 gpurun_out/smoke.log
+timeout 600 python profiles/bench_kernels.py > gpurun_out/kernels_v15.json 2> gpurun_out/kernels_v15.err; head -c 1300 gpurun_out/kernels_v15.json | tail -c 700; tail -3 gpurun_out/kernels_v15.err

@@ -658,3 +658,91 @@ ORC_API int orc_fdo_uct_search_philox(const void* h, uint64_t seed, uint64_t uni
     return rc ? -1 : status;
 }
 ORC_API uint64_t orc_fdo_mc_allowed(const void* h, int first_expansion) { return mcts::allowed_actions(*(const fdo::State*)h, first_expansion != 0); }
+
+// ---- CPU baselines of the other configs: the oracle timed on host threads, static partition of the unit ids ------------
+// kind: 3 = card_matching samples (config 3, rs-full-doko), 30 = sample_assignment (config 3, rs-doko), 5 = lock-step env step + encode_state_pi
+//       (config 5), 4 = determinized leaf rollouts (config 4), 6 = UCT iterations (N3), 7 = flat Monte-Carlo PIMC rollouts (N2).
+// Units are mid-game info-states made like BASELINE config 3 (games advanced by random steps to card_index 8/16/24/32 round-robin).
+// Returns wall seconds; *work_out = number of work items done (samples / step-encodes / rollouts / iterations).
+ORC_API double orc_cpu_baseline(int kind, uint64_t seed, uint64_t n_units, uint32_t per_unit, int n_threads, uint64_t* work_out) {
+    if (n_threads <= 0) n_threads = (int)std::thread::hardware_concurrency();
+    if (n_threads < 1) n_threads = 1;
+    std::vector<uint64_t> work((size_t)n_threads, 0);
+    auto make_fdo = [&](uint64_t unit) {
+        PhiloxStream r(seed, (uint32_t)unit, 0, 0);
+        fdo::State s = fdo::State::new_game(r);
+        const int target = 8 * (1 + (int)(unit & 3));
+        while (s.current_phase != fdo::PH_FINISHED && s.card_index < target) s.random_action_for_current_player(r);
+        return s;
+    };
+    auto make_doko = [&](uint64_t unit) {
+        PhiloxStream r(seed, (uint32_t)unit, 0, 0);
+        doko::State s = doko::State::new_game(r);
+        const int target = 8 * (1 + (int)(unit & 3)) + 4;
+        for (int k = 0; k < target; ++k) if (s.random_action_for_current_player(r)) break;
+        return s;
+    };
+    auto t0 = std::chrono::steady_clock::now();
+    std::vector<std::thread> th;
+    uint64_t per = (n_units + n_threads - 1) / n_threads;
+    for (int t = 0; t < n_threads; ++t) {
+        uint64_t lo = (uint64_t)t * per, hi = lo + per > n_units ? n_units : lo + per;
+        if (lo >= hi) break;
+        th.emplace_back([&, t, lo, hi] {
+            uint64_t done = 0;
+            volatile int64_t sink = 0;
+            for (uint64_t unit = lo; unit < hi; ++unit) {
+                try {
+                    if (kind == 30) {
+                        doko::State s = make_doko(unit);
+                        for (uint32_t k = 0; k < per_unit; ++k) {
+                            PhiloxStream r(seed, (uint32_t)unit, k, 1); uint64_t hands[4];
+                            sink += doko::sample_assignment_full(s, r, hands) + (int64_t)(hands[0] & 1); done++;
+                        }
+                        continue;
+                    }
+                    fdo::State s = make_fdo(unit);
+                    if (s.current_phase == fdo::PH_FINISHED) continue;
+                    if (kind == 3) {
+                        for (uint32_t k = 0; k < per_unit; ++k) {
+                            PhiloxStream r(seed, (uint32_t)unit, k, 1); fdo::Hand oh[4]; int ores[4];
+                            sink += fdo::card_matching(s, r, oh, ores) + (int64_t)(oh[0].bits & 1); done++;
+                        }
+                    } else if (kind == 4) {
+                        for (uint32_t k = 0; k < per_unit; ++k) {
+                            PhiloxStream r(seed, (uint32_t)unit, k, 1); fdo::Hand oh[4]; int ores[4];
+                            if (fdo::card_matching(s, r, oh, ores)) continue;
+                            fdo::State d = fdo::with_hands_and_reservations(s, oh, ores);
+                            r.set_ordinal(SITE_CARD, (uint32_t)d.card_index); r.set_ordinal(SITE_RESERVATION, (uint32_t)d.reservations_round.len);
+                            for (;;) { if (d.random_action_for_current_player_no_announcement(r)) break; }
+                            sink += d.end_of_game_stats.player_points[0]; done++;
+                        }
+                    } else if (kind == 5) {
+                        int64_t obs[311];
+                        for (uint32_t k = 0; k < per_unit && s.current_phase != fdo::PH_FINISHED; ++k) {
+                            PhiloxStream r(seed, (uint32_t)unit, 0, 100 + k);
+                            uint64_t allowed = s.allowed_actions();
+                            uint64_t bit = random_single(allowed, r, SITE_STEP);
+                            s.play_action(__builtin_ctzll(bit));
+                            fdo::encode_state_pi(s, obs); sink += obs[0]; done++;
+                        }
+                    } else if (kind == 6) {
+                        std::vector<mcts::Move> m = mcts::search(s, 1.4, per_unit, seed, unit, 0, 1);
+                        sink += (int64_t)m.size(); done += per_unit;
+                    } else if (kind == 7) {
+                        uint32_t visits[39]; int64_t values[39];
+                        if (pimc::flat_mc(s, seed, unit, 0, per_unit, 1, visits, values) == 0)
+                            done += (uint64_t)per_unit * (uint64_t)__builtin_popcountll(s.allowed_actions());
+                    }
+                } catch (const std::exception&) {}
+            }
+            work[(size_t)t] = done;
+        });
+    }
+    for (auto& x : th) x.join();
+    double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    uint64_t total = 0;
+    for (uint64_t w : work) total += w;
+    if (work_out) *work_out = total;
+    return sec;
+}

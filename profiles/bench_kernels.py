@@ -90,6 +90,20 @@ def main():
 
     t = timed(k3, iters=3)
     out["K3_determinize_4096x4096"] = {"sec": t, "samples_per_s": n_info * S / t, "dead_ends": int((status != 0).sum()), "out_GBps": n_info * S * 37 / t / 1e9}
+    # K3 (rs-doko): sample_assignment on simplified-engine info-states, 4096 states x 1024 samples
+    d_states = dk.new_games(pkg.DK_DOKO, n_info, dk.rng(SEED, 0, 0))
+    for k in range(20):                                       # 4 reservations + 16 cards: lowest legal action each turn
+        m = dk.legal_mask(pkg.DK_DOKO, d_states)
+        act = (torch.log2((m & -m).to(torch.float64)).to(torch.uint8))
+        dk.apply(pkg.DK_DOKO, d_states, act)
+    S2 = 1024
+
+    def k3d():
+        dk._check(dk.L.dk_determinize(dk.ctx, pkg.DK_DOKO, n_info, S2, pkg.api._ptr(d_states), __import__("ctypes").byref(dk.rng(SEED, 0, 9)), pkg.api._ptr(hands),
+                                      pkg.api._ptr(res), pkg.api._ptr(status), dk._stream()), "dk_determinize")
+
+    t = timed(k3d, iters=3)
+    out["K3_sample_assignment_4096x1024"] = {"sec": t, "samples_per_s": n_info * S2 / t, "dead_ends": int((status.view(-1)[: n_info * S2] != 0).sum())}
     del hands, res, status
 
     # K4 leaf rollouts: 1024 leaves x 1024 rollouts (per-GPU share of config 4)
