@@ -1,5 +1,4 @@
 set -x
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; tail -3 gpurun_out/pytest_gpu.log
-python profiles/sanitize_smoke.py > gpurun_out/smoke.log 2>&1; tail -2 gpurun_out/smoke.log
-timeout 600 python profiles/bench_kernels.py > gpurun_out/kernels_v15.json 2> gpurun_out/kernels_v15.err; head -c 1300 gpurun_out/kernels_v15.json | tail -c 700; tail -3 gpurun_out/kernels_v15.err
+for c in "" 100 75 66 50 40 25; do if [ -z "$c" ]; then python profiles/experiments/k5_carveout.py; else DK_ENC_CARVEOUT=$c python profiles/experiments/k5_carveout.py; fi; done > gpurun_out/carveout.txt 2>&1
+cat gpurun_out/carveout.txt
