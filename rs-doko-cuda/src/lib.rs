@@ -55,7 +55,54 @@ extern "C" {
                           hands_out: *mut u64, reservations_out: *mut u8, status_out: *mut u8, stream: *mut c_void) -> i32;
     pub fn dk_leaf_rollouts(ctx: *mut dk_ctx, n_leaves: usize, rollouts_per_leaf: usize, determinize: c_int, states: *const dk_state,
                             rng: *const dk_rng, point_sum_out: *mut i64, stream: *mut c_void) -> i32;
+    // PIMC move decision (DefaultImpiPolicy::execute, PolicyFusionFn::fuse)
+    pub fn dk_pimc_evaluate(ctx: *mut dk_ctx, n_roots: usize, n_det: usize, n_rollouts: usize, states: *const dk_state, rng: *const dk_rng,
+                            visits_out: *mut u32, value_sum_out: *mut i64, status_out: *mut u8, stream: *mut c_void) -> i32;
+    pub fn dk_fuse(ctx: *mut dk_ctx, strategy: c_int, n_roots: usize, n_rows: usize, visits: *const u32, status: *const u8, allowed: *const u64,
+                   action_out: *mut u8, n_success_out: *mut u32, stream: *mut c_void) -> i32;
+    pub fn dk_pimc_root_stats(ctx: *mut dk_ctx, n_roots: usize, n_rows: usize, visits: *const u32, status: *const u8, allowed: *const u64,
+                              stats: *mut i64, accumulate: c_int, stream: *mut c_void) -> i32;
+    pub fn dk_pimc_pick(ctx: *mut dk_ctx, strategy: c_int, n_roots: usize, stats: *const i64, allowed: *const u64, action_out: *mut u8,
+                        stream: *mut c_void) -> i32;
+    // CachedMCTS::monte_carlo_tree_search per (root, sample)
+    pub fn dk_uct_workspace_bytes(n_trees: usize, iterations: usize) -> usize;
+    pub fn dk_uct_search(ctx: *mut dk_ctx, n_roots: usize, trees_per_root: usize, determinize: c_int, iterations: usize, uct_exploration_constant: f32,
+                         states: *const dk_state, rng: *const dk_rng, workspace: *mut c_void, workspace_bytes: usize, visits_out: *mut u32,
+                         values_out: *mut f32, action_out: *mut u8, status_out: *mut u8, stream: *mut c_void) -> i32;
+    // encode_state_ipi, replay records
+    pub fn dk_encode_ipi(ctx: *mut dk_ctx, n: usize, states: *const dk_state, assumed_hands: *const u64, assumed_reservations: *const u8,
+                         next_player: *const u8, out: *mut i64, row_stride: usize, err_out: *mut u8, stream: *mut c_void) -> i32;
+    pub fn dk_pack_replay_records(ctx: *mut dk_ctx, n_rows: usize, states: *const i64, value: *const f32, policy: *const f32, out: *mut u8,
+                                  stream: *mut c_void) -> i32;
+    // lock-step self_play driver
+    pub fn dk_sp_create(ctx: *mut dk_ctx, max_games: usize, bufs: *const dk_sp_buffers, out: *mut *mut dk_selfplay) -> i32;
+    pub fn dk_sp_destroy(sp: *mut dk_selfplay) -> i32;
+    pub fn dk_sp_reset(sp: *mut dk_selfplay, stream: *mut c_void) -> i32;
+    pub fn dk_sp_begin_turn(sp: *mut dk_selfplay, n: usize, states: *const dk_state, az_epoch: u64, keep_prob: f32, flags: u32, rng: *const dk_rng,
+                            stream: *mut c_void) -> i32;
+    pub fn dk_sp_turn_view(sp: *mut dk_selfplay, allowed: *mut *const u64, flags: *mut *const u8, rows: *mut *const i64) -> i32;
+    pub fn dk_sp_end_turn(sp: *mut dk_selfplay, states: *mut dk_state, policy: *const f32, action: *const u8, err_out: *mut u8, stream: *mut c_void) -> i32;
+    pub fn dk_sp_finalize(sp: *mut dk_selfplay, states: *const dk_state, stream: *mut c_void) -> i32;
+    pub fn dk_sp_counts(sp: *mut dk_selfplay, rows: *mut u64, dropped: *mut u64, unfinished: *mut u64, stream: *mut c_void) -> i32;
 }
+
+#[repr(C)]
+pub struct dk_selfplay {
+    _private: [u8; 0],
+}
+/// include/doko_cuda.h: dk_sp_buffers — caller-owned device memory standing in for states_buffer / policy_targets_buffer / value_targets_buffer
+#[repr(C)]
+pub struct dk_sp_buffers {
+    pub states: *mut i64,
+    pub policy: *mut f32,
+    pub value: *mut f32,
+    pub player: *mut u8,
+    pub game: *mut u32,
+    pub capacity: usize,
+}
+pub const DK_FUSE_MAX_N: c_int = 0;
+pub const DK_FUSE_AVERAGE: c_int = 1;
+pub const DK_ACTION_NONE: u8 = 0xFF;
 
 pub struct DokoCuda {
     ctx: *mut dk_ctx,

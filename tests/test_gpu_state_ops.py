@@ -159,3 +159,35 @@ def test_doko_one_million_playouts_config1(dk, orc):
     ref = oracle_lib.playout_philox(orc, 0, n, SEED, 0, 1, True, 0)
     assert np.array_equal(pts.cpu().numpy(), ref["points"])
     assert int(steps.min()) == 52 and int(steps.max()) == 52
+
+
+def test_argument_errors_are_status_codes_not_crashes(dk):
+    """Error behaviour of the boundary: bad arguments come back as DK_ERR_INVALID_ARGUMENT (the reference would panic), n == 0 is a no-op."""
+    import ctypes as C
+
+    import torch
+
+    import master_doko_reinforcement_learning_b200.api as api
+
+    L, ctx = dk.L, dk.ctx
+    states = dk.new_games(1, 4, dk.rng(1, 0, 0))
+    rng = dk.rng(1, 0, 0)
+    out = torch.empty((4, 311), dtype=torch.int64, device="cuda")
+    mask = torch.empty((4,), dtype=torch.int64, device="cuda")
+    p = api._ptr
+    INVALID = 1
+    assert L.dk_legal_mask(ctx, 7, 4, p(states), p(mask), None) == INVALID                       # unknown engine
+    assert L.dk_legal_mask(ctx, 1, 4, None, p(mask), None) == INVALID                            # NULL states
+    assert L.dk_encode(ctx, 2, 4, p(states), p(out), 310, None) == INVALID                       # row_stride < row length
+    assert L.dk_encode(ctx, 9, 4, p(states), p(out), 311, None) == INVALID                       # unknown layout
+    assert L.dk_playout(ctx, 5, 0, 4, None, C.byref(rng), p(mask), None, None) == INVALID
+    assert L.dk_pimc_evaluate(ctx, 4, 2, 0, p(states), C.byref(rng), p(out), None, None, None) == INVALID       # zero rollouts
+    assert L.dk_fuse(ctx, 5, 4, 2, p(out), None, p(mask), p(mask), None, None) == INVALID        # unknown strategy
+    assert L.dk_uct_search(ctx, 4, 1, 0, 10, C.c_float(1.4), p(states), C.byref(rng), p(out), 16, None, None, None, None, None) == INVALID   # workspace too small
+    assert L.dk_encode(ctx, 2, 0, p(states), p(out), 311, None) == 0                             # empty batch
+    assert L.dk_legal_mask(ctx, 1, 0, p(states), p(mask), None) == 0
+    assert b"" is not None and L.dk_last_error(ctx) is not None
+    # the context is still healthy
+    m = dk.legal_mask(1, states)
+    torch.cuda.synchronize()
+    assert int((m != 0).sum()) == 4
