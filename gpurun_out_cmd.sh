@@ -1,4 +1,4 @@
 set -x
 mkdir -p gpurun_out
-for c in "" 100 75 66 50 40 25; do if [ -z "$c" ]; then python profiles/experiments/k5_carveout.py; else DK_ENC_CARVEOUT=$c python profiles/experiments/k5_carveout.py; fi; done > gpurun_out/carveout.txt 2>&1
-cat gpurun_out/carveout.txt
+timeout 900 python -m pytest tests/test_gpu_selfplay.py tests/test_replay_record.py tests/test_gpu_state_ops.py tests/test_gpu_full_size.py -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; tail -3 gpurun_out/pytest_gpu.log
+python profiles/experiments/n1_split.py > gpurun_out/n1_split2.txt 2>&1; tail -1 gpurun_out/n1_split2.txt

@@ -400,7 +400,8 @@ dk_status dk_sp_begin_turn(dk_selfplay* sp, size_t n, const dk_state* states, ui
     dk::sp_scan_kernel<<<1, 1024, 0, s>>>(nb, sp->block_counts, sp->block_offsets, sp->counters, sp->counters + 1, sp->buf.capacity);
     st = check_launch(ctx, "sp_scan_kernel");
     if (st != DK_OK) return st;
-    dk::sp_encode_kernel<<<nb, dk::SP_THREADS, 0, s>>>((uint64_t)n, states, sp->allowed, sp->flags, sp->block_offsets, sp->buf, sp->rows);
+    dk::sp_encode_kernel<<<nb, dk::SP_THREADS, 0, s>>>((uint64_t)n, states, sp->allowed, sp->flags, sp->block_offsets, sp->buf, sp->rows,
+                                                       !((uintptr_t)sp->buf.states & 31u));
     return check_launch(ctx, "sp_encode_kernel");
 }
 dk_status dk_sp_turn_view(dk_selfplay* sp, const uint64_t** allowed, const uint8_t** flags, const int64_t** rows) {

@@ -271,24 +271,26 @@ struct SmemSlotOut {
     }
     __device__ __forceinline__ void phase(uint32_t v) const { row[62] = v; }
 };
+// one staged row → one i64 row, channel by channel (the calling warp's 32 lanes)
+__device__ __forceinline__ void write_row_pi(const uint32_t* __restrict__ src, long long* __restrict__ dst, uint32_t lane) {
+    uint32_t w0 = src[lane], w1 = lane < 30 ? src[32 + lane] : 0u;
+#define DK_PI_CH(CH, SH, MASK)                                                    \
+    dst[(CH) * 62 + lane] = (long long)((w0 >> (SH)) & (MASK));                       \
+    if (lane < 30) dst[(CH) * 62 + 32 + lane] = (long long)((w1 >> (SH)) & (MASK));
+    DK_PI_CH(0, 0, 63u)
+    DK_PI_CH(1, 6, 63u)
+    DK_PI_CH(2, 12, 7u)
+    DK_PI_CH(3, 15, 15u)
+    DK_PI_CH(4, 19, 3u)
+#undef DK_PI_CH
+    if (lane == 0) dst[310] = (long long)src[62];
+}
 __device__ __forceinline__ void write_rows_pi(const uint32_t* __restrict__ tok, uint64_t first, uint64_t n, int64_t* __restrict__ out, size_t row_stride) {
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int r = warp; r < ENC_THREADS; r += ENC_THREADS / 32) {
         uint64_t g = first + r;
         if (g >= n) break;
-        const uint32_t* src = tok + r * PI_ROW;
-        int64_t* dst = out + g * row_stride;
-        uint32_t w0 = src[lane], w1 = lane < 30 ? src[32 + lane] : 0u;
-#define DK_PI_CH(CH, SH, MASK)                                                    \
-        dst[(CH) * 62 + lane] = (int64_t)((w0 >> (SH)) & (MASK));                     \
-        if (lane < 30) dst[(CH) * 62 + 32 + lane] = (int64_t)((w1 >> (SH)) & (MASK));
-        DK_PI_CH(0, 0, 63u)
-        DK_PI_CH(1, 6, 63u)
-        DK_PI_CH(2, 12, 7u)
-        DK_PI_CH(3, 15, 15u)
-        DK_PI_CH(4, 19, 3u)
-#undef DK_PI_CH
-        if (lane == 0) dst[310] = (int64_t)src[62];
+        write_row_pi(tok + r * PI_ROW, reinterpret_cast<long long*>(out) + g * row_stride, (uint32_t)lane);
     }
 }
 // Dense rows (row_stride == 311): four consecutive rows are exactly 311 sectors (4 x 2488 B = 311 x 32 B), so a warp writes its rows
@@ -334,6 +336,19 @@ __device__ __forceinline__ void write_rows_pi_dense(const uint32_t* __restrict__
         if (g >= n) break;
         const uint32_t rows_valid = (uint32_t)min((uint64_t)4, n - g);
         pi_dense_windows(tok + 4u * q * PI_ROW, reinterpret_cast<long long*>(out) + g * 311u, lane, rows_valid, std::make_integer_sequence<int, 39>{});
+    }
+}
+// `count` staged rows (smem rows 0..count-1) → the consecutive dense rows row0 .. row0+count-1 of `out` (row0 arbitrary): rows up to the
+// next multiple of four and the tail go row by row, everything between as sector-aligned 4-row streams.  `out` must be 32-byte aligned.
+__device__ __forceinline__ void write_rows_pi_dense_at(const uint32_t* __restrict__ tok, uint64_t row0, uint32_t count, long long* __restrict__ out) {
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
+    const uint32_t head = min(count, (uint32_t)((4u - (uint32_t)(row0 & 3ull)) & 3u));
+    const uint32_t groups = (count - head) / 4u, tail0 = head + 4u * groups;
+    for (uint32_t q = warp; q < groups; q += n_warps)
+        pi_dense_windows(tok + (head + 4u * q) * PI_ROW, out + (row0 + head + 4u * q) * 311u, lane, 4u, std::make_integer_sequence<int, 39>{});
+    for (uint32_t r = warp; r < head + (count - tail0); r += n_warps) {
+        const uint32_t sr = r < head ? r : tail0 + (r - head);
+        write_row_pi(tok + sr * PI_ROW, out + (row0 + sr) * 311u, lane);
     }
 }
 __global__ void __launch_bounds__(ENC_THREADS)

@@ -84,9 +84,8 @@ sp_scan_kernel(uint32_t n_blocks, const uint32_t* __restrict__ block_counts, uns
 
 __global__ void __launch_bounds__(SP_THREADS)
 sp_encode_kernel(uint64_t n, const dk_state* __restrict__ states, const uint64_t* __restrict__ allowed, uint8_t* __restrict__ flags_io,
-                 const unsigned long long* __restrict__ block_offsets, SpBuffers buf, long long* __restrict__ row_out) {
+                 const unsigned long long* __restrict__ block_offsets, SpBuffers buf, long long* __restrict__ row_out, bool dense_ok) {
     __shared__ uint32_t tok[SP_THREADS * PI_ROW];
-    __shared__ long long row_of[SP_THREADS];
     __shared__ uint32_t warp_count[SP_THREADS / 32];
     const uint64_t first = (uint64_t)blockIdx.x * SP_THREADS;
     const uint64_t i = first + threadIdx.x;
@@ -104,12 +103,11 @@ sp_encode_kernel(uint64_t n, const dk_state* __restrict__ states, const uint64_t
         if (r < buf.capacity) row = (long long)r;
         else { flags = (flags & ~SP_KEPT) | SP_DROPPED; flags_io[i] = (uint8_t)flags; }
     }
-    row_of[threadIdx.x] = row;
     if (i < n && row_out) row_out[i] = row;
     if (row >= 0) {
         alignas(16) dk_state s;
         load_state(states + i, s);
-        SmemSlotOut o{tok + threadIdx.x * PI_ROW};
+        SmemSlotOut o{tok + before * PI_ROW};                         // staged by RANK: the block's kept rows are consecutive in smem and in the buffer
         fdo_encode_pi(s, o);
         buf.player[row] = (uint8_t)(st_phase(s) == DK_PHASE_FINISHED ? 0u : st_cur(s));
         buf.game[row] = (uint32_t)i;
@@ -120,24 +118,14 @@ sp_encode_kernel(uint64_t n, const dk_state* __restrict__ states, const uint64_t
         }
     }
     __syncthreads();
-    // expand the staged rows: one warp per row, rows of one block are consecutive in the buffer
-    for (int r = warp; r < SP_THREADS; r += SP_THREADS / 32) {
-        const long long dst_row = row_of[r];
-        if (dst_row < 0) continue;
-        const uint32_t* src = tok + r * PI_ROW;
-        long long* dst = buf.states + (size_t)dst_row * 311u;
-        uint32_t w0 = src[lane], w1 = lane < 30 ? src[32 + lane] : 0u;
-#define DK_SP_CH(CH, SH, MASK)                                                    \
-        dst[(CH) * 62 + lane] = (long long)((w0 >> (SH)) & (MASK));                   \
-        if (lane < 30) dst[(CH) * 62 + 32 + lane] = (long long)((w1 >> (SH)) & (MASK));
-        DK_SP_CH(0, 0, 63u)
-        DK_SP_CH(1, 6, 63u)
-        DK_SP_CH(2, 12, 7u)
-        DK_SP_CH(3, 15, 15u)
-        DK_SP_CH(4, 19, 3u)
-#undef DK_SP_CH
-        if (lane == 0) dst[310] = (long long)src[62];
-    }
+    // rows block_offsets[b] .. + kept-in-block - 1, cut at the capacity
+    uint32_t cnt = 0;
+    for (uint32_t w = 0; w < SP_THREADS / 32; ++w) cnt += warp_count[w];
+    const unsigned long long row0 = block_offsets[blockIdx.x];
+    if (row0 >= buf.capacity) return;
+    cnt = (uint32_t)min((unsigned long long)cnt, buf.capacity - row0);
+    if (dense_ok) write_rows_pi_dense_at(tok, row0, cnt, buf.states);
+    else for (uint32_t r = warp; r < cnt; r += SP_THREADS / 32) write_row_pi(tok + r * PI_ROW, buf.states + (row0 + r) * 311u, lane);
 }
 
 // Stand-in for the search slot (tests / benches): one draw over the allowed set (MSB-first rank pick like FdoAllowedActions::random,
