@@ -29,6 +29,9 @@ DK_HD uint32_t fdo_card_token(uint32_t c) {
 // 62 slots x 5 channels (token, position, player, sub-position, team) + phase = 311 values.
 // The sink receives out.slot(n, token, position, player, sub-position, team) for the 62 slots and out.phase(v); row element
 // indices are n, 62+n, 124+n, 186+n, 248+n and 310.
+// Every access to the record uses a compile-time offset (the card / call loops run over all 48 / 10 positions under a predicate, the
+// hands are rotated with selects): the 128-byte record stays in registers instead of local memory, which matters because the encode
+// kernels configure almost the whole L1 as shared memory.
 template <class Out>
 DK_HD void fdo_encode_pi(const dk_state& s, Out& out) {
     const uint32_t cur = st_phase(s) == DK_PHASE_FINISHED ? 0u : st_cur(s);   // current_player.unwrap_or(BOTTOM) (:31-33)
@@ -37,18 +40,35 @@ DK_HD void fdo_encode_pi(const dk_state& s, Out& out) {
         out.slot(n, tok, pos, ply, sub, team);
         n++;
     };
-    const uint32_t start = st_game_start(s);
+    const uint32_t start = st_game_start(s), nres = s.n_reservations;
+    const uint32_t res4 = (uint32_t)s.reservations[0] | ((uint32_t)s.reservations[1] << 8) | ((uint32_t)s.reservations[2] << 16) | ((uint32_t)s.reservations[3] << 24);
+#pragma unroll
     for (uint32_t i = 0; i < 4u; ++i) {                                       // real reservations in play order (:43-81)
-        if (i < s.n_reservations) push(25u + s.reservations[i], i + 1u, ((start + i - cur) & 3u) + 1u, 0u, 0u);
-        else push(36u, 0u, 0u, 0u, 0u);
+        const bool made = i < nres;
+        push(made ? 25u + ((res4 >> (8u * i)) & 255u) : 36u, made ? i + 1u : 0u, made ? ((start + i - cur) & 3u) + 1u : 0u, 0u, 0u);
     }
-    const uint32_t ci = s.card_index;
-    for (uint32_t j = 0; j < ci; ++j) {                                       // played cards (:83-99)
-        uint32_t seat = (st_trick_start(s, j >> 2) + (j & 3u)) & 3u;
-        push(fdo_card_token(s.cards[j]), j + 5u, ((seat - cur) & 3u) + 1u, 0u, 0u);
+    const uint32_t ci = s.card_index, tricks = s.tricks;
+    const uint32_t* cards32 = reinterpret_cast<const uint32_t*>(s.cards);
+#pragma unroll
+    for (uint32_t t = 0; t < 12u; ++t) {                                      // played cards (:83-99), trick by trick
+        if (4u * t < ci) {                                                    // (uniform enough: games of a batch are at similar depths)
+            const uint32_t quad = cards32[t], lead = (tricks >> (2u * t)) & 3u;
+#pragma unroll
+            for (uint32_t k = 0; k < 4u; ++k) {
+                const uint32_t j = 4u * t + k;
+                if (j < ci) out.slot(4u + j, fdo_card_token((quad >> (8u * k)) & 255u), j + 5u, ((lead + k - cur) & 3u) + 1u, 0u, 0u);
+            }
+        }
     }
-    for (uint32_t i = 0; i < 4u; ++i) {                                       // all four hands from the seat to move (:102-121)
-        uint64_t h = s.hands[(cur + i) & 3u], b = h;
+    n = 4u + ci;
+    // the four hands from the seat to move (:102-121): rotate with selects instead of indexing by (cur + i) & 3
+    uint64_t h0 = s.hands[0], h1 = s.hands[1], h2 = s.hands[2], h3 = s.hands[3];
+    if (cur & 1u) { uint64_t t = h0; h0 = h1; h1 = h2; h2 = h3; h3 = t; }
+    if (cur & 2u) { uint64_t t0 = h0, t1 = h1; h0 = h2; h1 = h3; h2 = t0; h3 = t1; }
+#pragma unroll
+    for (uint32_t i = 0; i < 4u; ++i) {
+        const uint64_t h = i == 0u ? h0 : (i == 1u ? h1 : (i == 2u ? h2 : h3));
+        uint64_t b = h;
         while (b) {
             uint32_t pos = ffs0ll(b);
             b &= b - 1ull;
@@ -58,14 +78,17 @@ DK_HD void fdo_encode_pi(const dk_state& s, Out& out) {
         }
     }
     const uint32_t n_calls = st_n_calls(s), re = st_re_mask(s);
+    const uint32_t* ann32 = reinterpret_cast<const uint32_t*>(s.announcements);
     uint32_t sub = 0, last = 0xFFFFFFFFu;
-    for (uint32_t a = 0; a < n_calls && a < 10u; ++a) {                       // calls (:139-165); position = raw card_index + 1
-        uint32_t v = s.announcements[a], cidx = v & 63u, seat = (v >> 6) & 3u, lvl = (v >> 8) & 7u;
-        if (cidx != last) { last = cidx; sub = 0; }
-        push(lvl == 6u ? 38u : 37u + lvl, cidx + 1u, ((seat - cur) & 3u) + 1u, sub + 1u, ((re >> seat) & 1u) ? 1u : 2u);
-        sub++;
+#pragma unroll
+    for (uint32_t a = 0; a < 10u; ++a) {                                      // calls (:139-165); position = raw card_index + 1; then padding (:167-179)
+        const uint32_t v = (ann32[a >> 1] >> (16u * (a & 1u))) & 0xFFFFu, cidx = v & 63u, seat = (v >> 6) & 3u, lvl = (v >> 8) & 7u;
+        if (a < n_calls) {
+            if (cidx != last) { last = cidx; sub = 0; }
+            push(lvl == 6u ? 38u : 37u + lvl, cidx + 1u, ((seat - cur) & 3u) + 1u, sub + 1u, ((re >> seat) & 1u) ? 1u : 2u);
+            sub++;
+        } else push(37u, 0u, 0u, 0u, 0u);
     }
-    for (uint32_t a = n_calls; a < 10u; ++a) push(37u, 0u, 0u, 0u, 0u);         // (:167-179)
     out.phase(st_phase(s));                                                   // encode_phase (var1/phase.rs:9-18)
 }
 
