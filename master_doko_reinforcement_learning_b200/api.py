@@ -34,7 +34,8 @@ class DkRng(C.Structure):
 
 
 def library_path():
-    return _build.LIB_PATH
+    """In-tree libdoko_cuda.so; DOKO_CUDA_LIB points at another build of the same ABI (used by the tuning experiments)."""
+    return os.environ.get("DOKO_CUDA_LIB") or _build.LIB_PATH
 
 
 _LIB = None

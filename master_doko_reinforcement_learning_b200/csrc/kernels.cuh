@@ -642,13 +642,13 @@ fdo_pimc_kernel(RngParams rp, uint64_t n_roots, uint32_t n_det, uint32_t n_rollo
         uint32_t best_a = ACTION_NONE;
         // legal set of the determinized state: the mover's own hand and the public state do not depend on the sample, so this is the
         // root's legal set and the loop is uniform across the block; peers (same dl) share it exactly in any case
-        for (uint64_t m = fdo_state_legal_mask(det_state[dl]); m; m &= m - 1ull) {
+        for (uint64_t m = fdo_state_legal_mask<true>(det_state[dl]); m; m &= m - 1ull) {
             const uint32_t a = ffs0ll(m);
             alignas(16) dk_state s = det_state[dl];
-            fdo_state_apply(s, a);
+            fdo_state_apply<true>(s, a);                                  // indexed form: the record stays in local memory (237 registers otherwise)
             int32_t p[4];
             FdoLive g; FdoResume rs;
-            if (fdo_state_to_live(s, g, rs)) { fdo_play_to_end<false, false>(g, key, &rs, lut); fdo_final_points(g, p); }
+            if (fdo_state_to_live<true>(s, g, rs)) { fdo_play_to_end<false, false>(g, key, &rs, lut); fdo_final_points(g, p); }
             else { p[0] = s.points[0]; p[1] = s.points[1]; p[2] = s.points[2]; p[3] = s.points[3]; }
             const int v = (mover & 2u) ? ((mover & 1u) ? p[3] : p[2]) : ((mover & 1u) ? p[1] : p[0]);
             const int tot = __reduce_add_sync(peers, v);

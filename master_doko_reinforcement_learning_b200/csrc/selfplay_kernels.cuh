@@ -253,7 +253,10 @@ pack_replay_records_kernel(unsigned long long n_rows, const long long* __restric
 // is first replaced by determinization (first_sub + d) of the info-state (the dk_determinize stream).  Iteration `it` runs on the
 // Philox unit (first_id + root, (first_sub + d) * iterations + it).
 constexpr int UCT_THREADS = 64;
-__global__ void __launch_bounds__(UCT_THREADS, 16)
+#ifndef DK_UCT_MIN_BLOCKS
+#define DK_UCT_MIN_BLOCKS 16
+#endif
+__global__ void __launch_bounds__(UCT_THREADS, DK_UCT_MIN_BLOCKS)
 fdo_uct_kernel(RngParams rp, uint64_t n_trees, uint32_t trees_per_root, uint32_t iterations, double c, const double* __restrict__ ln_table, int determinize,
                const dk_state* __restrict__ states, UctNode* __restrict__ pool_base, uint32_t* __restrict__ visits_out, float* __restrict__ values_out,
                uint8_t* __restrict__ action_out, uint8_t* __restrict__ status_out) {

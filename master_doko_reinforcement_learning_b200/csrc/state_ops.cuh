@@ -32,6 +32,72 @@ DK_HD void st_set(uint32_t& word, uint32_t shift, uint32_t width, uint32_t v) {
 DK_HD uint32_t hand_any24(uint64_t h) { return (uint32_t)((h | (h >> 24)) & 0xFFFFFFull); }
 DK_HD uint32_t hand_both24(uint64_t h) { return (uint32_t)((h & (h >> 24)) & 0xFFFFFFull); }
 
+// ---- run-time indexed fields through compile-time offsets ----------------------------------------------------------------------
+// A seat / card position / call number known only at run time would make the compiler put the whole 128-byte record into local
+// memory (a dynamically indexed array cannot live in registers).  The transition functions below therefore reach those fields
+// through select chains over compile-time offsets: the record stays in registers in every kernel that only uses these functions
+// (0-byte stack frame for dk_apply / dk_legal_mask / the fused step + encode; the kernels configure most of the SM's L1 as shared
+// memory, so a local-memory record was served from L2).  The host simulator compiles the same code.
+// Every function that needs them takes IDX: false (default) = the select chains, true = plain indexed accesses for the kernels whose
+// register budget is better spent elsewhere and that keep the record in local memory anyway (the UCT search: 64 registers at 16
+// blocks per SM; the PIMC evaluator: the whole rollout state is live next to the record) — measured, profiles/r01_kernels_v17.json.
+template <bool IDX = false>
+DK_HD uint64_t st_hand(const dk_state& s, uint32_t p) {
+    if (IDX) return s.hands[p];
+    const uint64_t a = (p & 1u) ? s.hands[1] : s.hands[0], b = (p & 1u) ? s.hands[3] : s.hands[2];
+    return (p & 2u) ? b : a;
+}
+template <bool IDX = false>
+DK_HD void st_set_hand(dk_state& s, uint32_t p, uint64_t h) {
+    if (IDX) { s.hands[p] = h; return; }
+#pragma unroll
+    for (uint32_t q = 0; q < 4u; ++q) s.hands[q] = q == p ? h : s.hands[q];
+}
+DK_HD uint32_t st_word_of(const uint8_t* bytes, uint32_t w) {            // 32-bit word w of a byte field (little endian), w compile-time
+    return (uint32_t)bytes[4u * w] | ((uint32_t)bytes[4u * w + 1u] << 8) | ((uint32_t)bytes[4u * w + 2u] << 16) | ((uint32_t)bytes[4u * w + 3u] << 24);
+}
+DK_HD void st_set_word_of(uint8_t* bytes, uint32_t w, uint32_t v) {
+    bytes[4u * w] = (uint8_t)v; bytes[4u * w + 1u] = (uint8_t)(v >> 8); bytes[4u * w + 2u] = (uint8_t)(v >> 16); bytes[4u * w + 3u] = (uint8_t)(v >> 24);
+}
+// the four cards of trick t (byte k = k-th card; 0xFF = not played yet)
+template <bool IDX = false>
+DK_HD uint32_t st_quad(const dk_state& s, uint32_t t) {
+    if (IDX) return (uint32_t)s.cards[4u * t] | ((uint32_t)s.cards[4u * t + 1u] << 8) | ((uint32_t)s.cards[4u * t + 2u] << 16) | ((uint32_t)s.cards[4u * t + 3u] << 24);
+    uint32_t q = 0;
+#pragma unroll
+    for (uint32_t w = 0; w < 12u; ++w) q = w == t ? st_word_of(s.cards, w) : q;
+    return q;
+}
+template <bool IDX = false>
+DK_HD uint32_t st_card(const dk_state& s, uint32_t i) { return IDX ? (uint32_t)s.cards[i] : (st_quad<false>(s, i >> 2) >> (8u * (i & 3u))) & 255u; }
+template <bool IDX = false>
+DK_HD void st_set_card(dk_state& s, uint32_t i, uint32_t c) {
+    if (IDX) { s.cards[i] = (uint8_t)c; return; }
+    const uint32_t sh = 8u * (i & 3u), keep = ~(255u << sh), ins = c << sh, t = i >> 2;
+#pragma unroll
+    for (uint32_t w = 0; w < 12u; ++w) { const uint32_t old = st_word_of(s.cards, w); st_set_word_of(s.cards, w, w == t ? (old & keep) | ins : old); }
+}
+template <bool IDX = false>
+DK_HD void st_set_call(dk_state& s, uint32_t n, uint32_t v) {            // announcements[n] = v
+    if (IDX) { s.announcements[n] = (uint16_t)v; return; }
+#pragma unroll
+    for (uint32_t a = 0; a < 12u; ++a) s.announcements[a] = a == n ? (uint16_t)v : s.announcements[a];
+}
+template <bool IDX = false>
+DK_HD void st_push_reservation(dk_state& s, uint32_t code) {             // reservations[n_reservations++] = code
+    const uint32_t n = s.n_reservations;
+    if (IDX) { s.reservations[n] = (uint8_t)code; s.n_reservations = (uint8_t)(n + 1u); return; }
+#pragma unroll
+    for (uint32_t i = 0; i < 4u; ++i) s.reservations[i] = i == n ? (uint8_t)code : s.reservations[i];
+    s.n_reservations = (uint8_t)(n + 1u);
+}
+template <bool IDX = false>
+DK_HD void st_add_eyes(dk_state& s, uint32_t seat, uint32_t e) {
+    if (IDX) { s.eyes[seat] = (uint8_t)(s.eyes[seat] + e); return; }
+#pragma unroll
+    for (uint32_t p = 0; p < 4u; ++p) s.eyes[p] = (uint8_t)(s.eyes[p] + (p == seat ? e : 0u));
+}
+
 DK_HD void st_clear(dk_state& s) {
     for (int p = 0; p < 4; ++p) { s.hands[p] = 0; s.reservations[p] = 0xFF; s.eyes[p] = 0; s.points[p] = 0; }
     for (int i = 0; i < 48; ++i) s.cards[i] = 0xFF;
@@ -61,37 +127,40 @@ DK_HD uint32_t fdo_gt_from_res_code(uint32_t r) {       // solo reservation → 
     return r <= 5u ? r : (r == 8u ? 6u : r + 1u);
 }
 // The call a seat may make in the announcement phase (level 1..5) or 0.
+template <bool IDX = false>
 DK_HD uint32_t fdo_state_allowed_call(const dk_state& s, uint32_t seat) {
     uint32_t tag = st_team_tag(s);
     if (tag == TEAM_WEDDING_UNSOLVED || tag == TEAM_IN_RESERVATIONS) return 0;
     uint32_t w = tag == TEAM_WEDDING_SOLVED ? st_solved_idx(s) : 0u;
     bool is_re = (st_re_mask(s) >> seat) & 1u;
     uint32_t m = is_re ? st_re_low(s) : st_ko_low(s), e = is_re ? st_ko_low(s) : st_re_low(s);
-    return fdo_allowed_call(popcll(s.hands[seat]), m, e, w);
+    return fdo_allowed_call(popcll(st_hand<IDX>(s, seat)), m, e, w);
 }
 // FdoAllowedActions::calculate_allowed_actions (rs-full-doko/src/action/allowed_actions.rs:68-169); Finished → 0.
+template <bool IDX = false>
 DK_HD uint64_t fdo_state_legal_mask(const dk_state& s) {
     uint32_t phase = st_phase(s), cur = st_cur(s);
     if (phase == DK_PHASE_RESERVATION) {
         uint64_t m = (1ull << 24) | (0x7Full << 26);
-        if ((hand_both24(s.hands[cur]) >> CARD_CQ) & 1u) m |= 1ull << 25;
+        if ((hand_both24(st_hand<IDX>(s, cur)) >> CARD_CQ) & 1u) m |= 1ull << 25;
         return m;
     }
     if (phase == DK_PHASE_ANNOUNCEMENT) {
-        uint32_t call = fdo_state_allowed_call(s, cur);
+        uint32_t call = fdo_state_allowed_call<IDX>(s, cur);
         return (1ull << 38) | (call ? (1ull << (32u + call)) : 0ull);
     }
     if (phase == DK_PHASE_PLAY_CARD) {
-        uint32_t single = hand_any24(s.hands[cur]);
+        uint32_t single = hand_any24(st_hand<IDX>(s, cur));
         uint32_t ci = s.card_index, k = ci & 3u;
         if (k == 0u || st_n_tricks(s) >= 12u) return single;       // state.rs:360-372: no colour in the 12th trick
-        uint32_t first = s.cards[ci - k];
+        uint32_t first = st_quad<IDX>(s, ci >> 2) & 255u;
         uint32_t f = single & follow_mask(first, trump_mask_for_game_type(st_gt(s)));
         return f ? f : single;
     }
     return 0;
 }
 // internal_progress (announcement.rs:130-175) from seat p; sets phase / current seat / turns.
+template <bool IDX = false>
 DK_HD void fdo_state_progress(dk_state& s, uint32_t p) {
     uint32_t turns = st_turns(s);
     for (;;) {
@@ -100,7 +169,7 @@ DK_HD void fdo_state_progress(dk_state& s, uint32_t p) {
             st_set(s.meta, 2, 2, st_ann_start(s));
             break;
         }
-        if (fdo_state_allowed_call(s, p) == 0u) { turns++; p = (p + 1u) & 3u; continue; }
+        if (fdo_state_allowed_call<IDX>(s, p) == 0u) { turns++; p = (p + 1u) & 3u; continue; }
         st_set(s.meta, 0, 2, DK_PHASE_ANNOUNCEMENT);
         st_set(s.meta, 2, 2, p);
         break;
@@ -108,18 +177,20 @@ DK_HD void fdo_state_progress(dk_state& s, uint32_t p) {
     st_set(s.meta, 26, 3, turns);
 }
 // progress_next_card_or_announcement (state.rs:184-206) = start_round(current seat)
+template <bool IDX = false>
 DK_HD void fdo_state_start_round(dk_state& s) {
     st_set(s.meta, 26, 3, 0u);
     st_set(s.meta, 29, 2, st_cur(s));
-    fdo_state_progress(s, st_cur(s));
+    fdo_state_progress<IDX>(s, st_cur(s));
 }
-// Winner of completed trick t from the history (trick_winning_player_logic.rs:15-45).
-DK_HD uint32_t fdo_state_trick_winner(const dk_state& s, uint32_t t, uint32_t trump, uint32_t* win_card, uint32_t* eyes, uint32_t* fox_mask) {
-    uint32_t c0 = s.cards[4u * t];
+// Winner of a completed trick from its four cards (`quad`, byte k = k-th card) and lead seat (trick_winning_player_logic.rs:15-45).
+DK_HD uint32_t fdo_quad_winner(uint32_t quad, uint32_t lead, uint32_t trump, uint32_t* win_card, uint32_t* eyes, uint32_t* fox_mask) {
+    uint32_t c0 = quad & 255u;
     uint32_t follow = follow_mask(c0, trump);
     uint32_t best = 0, bestk = 0, bestc = c0, e = 0, fm = 0;
+#pragma unroll
     for (uint32_t k = 0; k < 4u; ++k) {
-        uint32_t c = s.cards[4u * t + k];
+        uint32_t c = (quad >> (8u * k)) & 255u;
         uint32_t pw = card_power(c, trump, follow);
         if (k == 0u || pw > best) { best = pw; bestk = k; bestc = c; }
         e += card_eyes_by_rank(c - 6u * card_suit(c));
@@ -128,22 +199,36 @@ DK_HD uint32_t fdo_state_trick_winner(const dk_state& s, uint32_t t, uint32_t tr
     if (win_card) *win_card = bestc;
     if (eyes) *eyes = e;
     if (fox_mask) *fox_mask = fm;
-    return (st_trick_start(s, t) + bestk) & 3u;
+    return (lead + bestk) & 3u;
+}
+template <bool IDX = false>
+DK_HD uint32_t fdo_state_trick_winner(const dk_state& s, uint32_t t, uint32_t trump, uint32_t* win_card, uint32_t* eyes, uint32_t* fox_mask) {
+    return fdo_quad_winner(st_quad<IDX>(s, t), st_trick_start(s, t), trump, win_card, eyes, fox_mask);
 }
 // FdoEndOfGameStats::calculate (stats/stats.rs:46-240) from the stored history.
 DK_HD void fdo_state_final_points(dk_state& s, uint32_t last_winner, uint32_t last_win_card) {
     uint32_t re = st_re_mask(s), trump = trump_mask_for_game_type(st_gt(s));
     uint32_t re_eyes = 0, re_tricks = 0;
+#pragma unroll
     for (uint32_t p = 0; p < 4u; ++p)
         if ((re >> p) & 1u) { re_eyes += s.eyes[p]; re_tricks += (s.num_tricks >> (4u * p)) & 15u; }
     int32_t extras = 0;
     if (popc(re) != 1u) {
+#pragma unroll
         for (uint32_t t = 0; t < 12u; ++t) {
-            uint32_t e, fm;
-            uint32_t w = t < 11u ? st_trick_start(s, t + 1u) : last_winner;
-            (void)fdo_state_trick_winner(s, t, trump, nullptr, &e, &fm);
+            // the winner of trick t leads trick t + 1, so only the eyes and the ♦A positions have to be re-read from the cards
+            uint32_t e = 0, fm = 0;
+            const uint32_t w = t < 11u ? st_trick_start(s, t + 1u) : last_winner, quad = st_word_of(s.cards, t);
+#pragma unroll
+            for (uint32_t k = 0; k < 4u; ++k) {
+                const uint32_t c = (quad >> (8u * k)) & 255u;
+                e += card_eyes_by_rank(c - 6u * card_suit(c));
+                fm |= (c == CARD_DA ? 1u : 0u) << k;
+            }
+            (void)trump;
             bool won_re = (re >> w) & 1u;
             if (e >= 40u) extras += won_re ? 1 : -1;                                  // doppelkopf.rs:8-26
+#pragma unroll
             for (uint32_t k = 0; k < 4u; ++k)
                 if ((fm >> k) & 1u) {                                                  // fuchs_gefangen.rs:9-60
                     bool played_re = (re >> ((st_trick_start(s, t) + k) & 3u)) & 1u;
@@ -154,35 +239,39 @@ DK_HD void fdo_state_final_points(dk_state& s, uint32_t last_winner, uint32_t la
     }
     int32_t ko;
     int32_t rp = fdo_score(re_eyes, re_tricks, popc(re), st_re_low(s), st_ko_low(s), extras, &ko);
+#pragma unroll
     for (uint32_t p = 0; p < 4u; ++p) s.points[p] = (int8_t)(((re >> p) & 1u) ? rp : ko);
 }
 // FdoState::play_action (rs-full-doko/src/state/state.rs:208-358).  Returns 0, or 1 if the action is not legal
 // (the reference would panic); the state is unchanged in that case.
+template <bool IDX = false>
 DK_HD uint32_t fdo_state_apply(dk_state& s, uint32_t action) {
-    if (action >= 39u || !((fdo_state_legal_mask(s) >> action) & 1ull)) return 1;
+    if (action >= 39u || !((fdo_state_legal_mask<IDX>(s) >> action) & 1ull)) return 1;
     uint32_t phase = st_phase(s), cur = st_cur(s);
     if (phase == DK_PHASE_RESERVATION) {
-        s.reservations[s.n_reservations++] = (uint8_t)fdo_res_code_from_action(action);
+        st_push_reservation<IDX>(s, fdo_res_code_from_action(action));
         uint32_t next = (cur + 1u) & 3u;
         st_set(s.meta, 2, 2, next);
         if (s.n_reservations == 4u) {
             uint32_t start = st_game_start(s);
-            uint32_t solo_i = 4, wed_i = 4;
+            uint32_t solo_i = 4, wed_i = 4, solo_code = 0;
+#pragma unroll
             for (uint32_t i = 0; i < 4u; ++i) {
                 uint32_t r = s.reservations[i];
-                if (r >= 2u && solo_i == 4u) solo_i = i;
+                if (r >= 2u && solo_i == 4u) { solo_i = i; solo_code = r; }
                 if (r == 1u) wed_i = i;
             }
             uint32_t gt, tag, re = 0, wed = 0;
-            if (solo_i < 4u) { gt = fdo_gt_from_res_code(s.reservations[solo_i]); tag = TEAM_NO_WEDDING; re = 1u << ((start + solo_i) & 3u); }
+            if (solo_i < 4u) { gt = fdo_gt_from_res_code(solo_code); tag = TEAM_NO_WEDDING; re = 1u << ((start + solo_i) & 3u); }
             else if (wed_i < 4u) { gt = GT_WEDDING; tag = TEAM_WEDDING_UNSOLVED; wed = (start + wed_i) & 3u; }
             else {
                 gt = GT_NORMAL; tag = TEAM_NO_WEDDING;
+#pragma unroll
                 for (uint32_t p = 0; p < 4u; ++p) if ((hand_any24(s.hands[p]) >> CARD_CQ) & 1u) re |= 1u << p;
             }
             st_set(s.meta, 6, 4, gt); st_set(s.meta, 10, 2, tag); st_set(s.meta, 12, 2, wed); st_set(s.meta, 16, 4, re);
             s.tricks = (s.tricks & 0xF0000000u) | next | (1u << 24);        // trick 0 led by the start seat
-            fdo_state_start_round(s);
+            fdo_state_start_round<IDX>(s);
         }
         return 0;
     }
@@ -193,25 +282,25 @@ DK_HD uint32_t fdo_state_apply(dk_state& s, uint32_t action) {
             turns = 0;
             uint32_t level = action - 32u;                                   // 33 → ReContra even for a counter (action.rs:297-299)
             uint32_t n = st_n_calls(s);
-            if (n < 12u) { s.announcements[n] = (uint16_t)(s.card_index | (cur << 6) | (level << 8)); st_set(s.tricks, 28, 4, n + 1u); }
+            if (n < 12u) { st_set_call<IDX>(s, n, s.card_index | (cur << 6) | (level << 8)); st_set(s.tricks, 28, 4, n + 1u); }
             if ((st_re_mask(s) >> cur) & 1u) st_set(s.meta, 20, 3, level); else st_set(s.meta, 23, 3, level);
         }
         st_set(s.meta, 26, 3, turns);
-        fdo_state_progress(s, (cur + 1u) & 3u);
+        fdo_state_progress<IDX>(s, (cur + 1u) & 3u);
         return 0;
     }
     // card
     uint32_t c = action;
-    uint64_t h = s.hands[cur];
+    uint64_t h = st_hand<IDX>(s, cur);
     if ((h >> (c + 24u)) & 1ull) h &= ~(1ull << (c + 24u)); else h &= ~(1ull << c);   // hand.remove: copy B first
-    s.hands[cur] = h;
+    st_set_hand<IDX>(s, cur, h);
     uint32_t ci = s.card_index;
-    s.cards[ci] = (uint8_t)c;
+    st_set_card<IDX>(s, ci, c);
     s.card_index = (uint8_t)(ci + 1u);
     if (((ci + 1u) & 3u) == 0u) {
         uint32_t t = ci >> 2, trump = trump_mask_for_game_type(st_gt(s)), wc, e;
-        uint32_t w = fdo_state_trick_winner(s, t, trump, &wc, &e, nullptr);
-        s.eyes[w] = (uint8_t)(s.eyes[w] + e);
+        uint32_t w = fdo_state_trick_winner<IDX>(s, t, trump, &wc, &e, nullptr);
+        st_add_eyes<IDX>(s, w, e);
         s.num_tricks = (uint16_t)(s.num_tricks + (1u << (4u * w)));
         if (st_team_tag(s) == TEAM_WEDDING_UNSOLVED) {                       // team_logic.rs:59-112
             uint32_t wed = st_wed_seat(s);
@@ -227,39 +316,43 @@ DK_HD uint32_t fdo_state_apply(dk_state& s, uint32_t action) {
         st_set(s.meta, 2, 2, w);
         st_set(s.tricks, 2u * (t + 1u), 2, w);
         st_set(s.tricks, 24, 4, t + 2u);
-        fdo_state_start_round(s);
+        fdo_state_start_round<IDX>(s);
         return 0;
     }
     st_set(s.meta, 2, 2, (cur + 1u) & 3u);
-    fdo_state_start_round(s);
+    fdo_state_start_round<IDX>(s);
     return 0;
 }
 // FdoAzEnvState::take_action_by_action_index(action, skip_single, _) (rs-doko-alpha-zero/src/env/envs/full_doko/full_doko.rs:121-154):
 // after the action, keep playing while exactly one non-call action is legal.
+template <bool IDX = false>
 DK_HD uint32_t fdo_state_apply_az(dk_state& s, uint32_t action, bool skip_single) {
-    uint32_t err = fdo_state_apply(s, action);
+    uint32_t err = fdo_state_apply<IDX>(s, action);
     if (err || !skip_single) return err;
     const uint64_t calls = 0x1Full << 33;
     for (;;) {
         if (st_phase(s) == DK_PHASE_FINISHED) break;
-        uint64_t m = fdo_state_legal_mask(s) & ~calls;
+        uint64_t m = fdo_state_legal_mask<IDX>(s) & ~calls;
         if (popcll(m) != 1u) break;
-        fdo_state_apply(s, ffs0ll(m));
+        fdo_state_apply<IDX>(s, ffs0ll(m));
     }
     return 0;
 }
 
 // Bridge: stored state → register-resident playout form.  Returns false when the game is already finished.
+template <bool IDX = false>
 DK_HD bool fdo_state_to_live(const dk_state& s, FdoLive& g, FdoResume& rs) {
     fdo_live_clear(g);
     uint32_t phase = st_phase(s);
     if (phase == DK_PHASE_FINISHED) return false;
-    uint32_t any[4], dup = 0;
-    for (uint32_t p = 0; p < 4u; ++p) { any[p] = hand_any24(s.hands[p]); dup |= hand_both24(s.hands[p]); }
+    uint32_t dup = 0;
+#pragma unroll
+    for (uint32_t p = 0; p < 4u; ++p) dup |= hand_both24(s.hands[p]);
     g.dup = dup;
     rs.n_res = s.n_reservations;
     rs.t0 = 0; rs.k0 = 0; rs.starts = 0; rs.ann_ci = 0; rs.ann_p = 0; rs.ann_turns = 0xFFFFFFFFu;
     rs.acc.follow = 0; rs.acc.best = 0; rs.acc.bestk = 0; rs.acc.bestc = 0; rs.acc.teyes = 0; rs.acc.foxm = 0;
+#pragma unroll
     for (uint32_t i = 0; i < 4u; ++i) rs.res_action[i] = i < s.n_reservations ? fdo_action_from_res_code(s.reservations[i]) : 0u;
     uint32_t base;
     if (phase == DK_PHASE_RESERVATION) {
@@ -269,12 +362,13 @@ DK_HD bool fdo_state_to_live(const dk_state& s, FdoLive& g, FdoResume& rs) {
         g.gt = st_gt(s); g.trump = trump_mask_for_game_type(g.gt);
         g.team_tag = st_team_tag(s); g.re_mask = st_re_mask(s); g.wed_seat = st_wed_seat(s); g.solved_idx = st_solved_idx(s);
         g.re_low = st_re_low(s); g.ko_low = st_ko_low(s);
+#pragma unroll
         for (uint32_t p = 0; p < 4u; ++p) { g.eyes |= (uint32_t)s.eyes[p] << (8u * p); }
         g.ntricks = s.num_tricks;
-        for (uint32_t t = 0; t < t0; ++t) {                                  // trackers of the completed tricks
-            // the winner of trick t leads trick t + 1, so only the eyes and the ♦A positions have to be re-read from the cards
+        // trackers of the completed tricks: the winner of trick t leads trick t + 1, so only the eyes and the ♦A positions have to be
+        // re-read from the cards
+        auto track = [&](uint32_t t, uint32_t quad) {
             uint32_t e = 0, fm = 0, w = st_trick_start(s, t + 1u);
-            const uint32_t quad = reinterpret_cast<const uint32_t*>(s.cards)[t];     // the trick's four cards (cards[] sits at byte 32 of the record)
 #pragma unroll
             for (uint32_t k = 0; k < 4u; ++k) {
                 const uint32_t c = (quad >> (8u * k)) & 255u;
@@ -285,11 +379,24 @@ DK_HD bool fdo_state_to_live(const dk_state& s, FdoLive& g, FdoResume& rs) {
             g.foxes = fdo_fox_record(g.foxes, fm, st_trick_start(s, t), w);
             rs.starts |= st_trick_start(s, t) << (2u * t);
             g.last_winner = w;
+        };
+        if (IDX) {
+#pragma unroll 1
+            for (uint32_t t = 0; t < t0; ++t) track(t, st_quad<true>(s, t));
+        } else {
+#pragma unroll
+            for (uint32_t t = 0; t < 12u; ++t) {                             // compile-time offsets
+                if (t >= t0) break;
+                track(t, st_word_of(s.cards, t));
+            }
         }
         base = st_trick_start(s, t0);
         rs.t0 = t0; rs.k0 = k0;
-        for (uint32_t k = 0; k < k0; ++k) {                                  // partial trick
-            uint32_t c = s.cards[4u * t0 + k];
+        const uint32_t quad0 = k0 ? st_quad<IDX>(s, t0) : 0u;
+#pragma unroll
+        for (uint32_t k = 0; k < 3u; ++k) {                                  // partial trick
+            if (k >= k0) break;
+            uint32_t c = (quad0 >> (8u * k)) & 255u;
             if (k == 0u) rs.acc.follow = follow_mask(c, g.trump);
             uint32_t pw = card_power(c, g.trump, rs.acc.follow);
             if (k == 0u || pw > rs.acc.best) { rs.acc.best = pw; rs.acc.bestk = k; rs.acc.bestc = c; }
@@ -299,8 +406,9 @@ DK_HD bool fdo_state_to_live(const dk_state& s, FdoLive& g, FdoResume& rs) {
         if (phase == DK_PHASE_ANNOUNCEMENT) { rs.ann_ci = ci; rs.ann_p = st_cur(s); rs.ann_turns = st_turns(s); }
         else { rs.ann_ci = ci + 1u; rs.ann_turns = 0xFFFFFFFFu; }            // the round before card ci is over
     }
-    g.base = base;
-    g.h0 = any[base]; g.h1 = any[(base + 1u) & 3u]; g.h2 = any[(base + 2u) & 3u]; g.h3 = any[(base + 3u) & 3u];
+    g.base = 0;
+    g.h0 = hand_any24(s.hands[0]); g.h1 = hand_any24(s.hands[1]); g.h2 = hand_any24(s.hands[2]); g.h3 = hand_any24(s.hands[3]);
+    fdo_rotate(g, base);                                                     // frame index 0 = seat `base` (selects, no indexed array)
     return true;
 }
 
@@ -308,23 +416,27 @@ DK_HD bool fdo_state_to_live(const dk_state& s, FdoLive& g, FdoResume& rs) {
 // rs-doko
 // =====================================================================================================================
 // calculate_allowed_actions_in_normal_game (rs-doko/src/action/allowed_actions.rs:131-198)
+template <bool IDX = false>
 DK_HD uint64_t doko_state_legal_mask(const dk_state& s) {
     uint32_t phase = st_phase(s), cur = st_cur(s);
-    if (phase == DK_PHASE_RESERVATION) return (1ull << 24) | (((hand_both24(s.hands[cur]) >> CARD_CQ) & 1u) ? (1ull << 25) : 0ull);
+    if (phase == DK_PHASE_RESERVATION) return (1ull << 24) | (((hand_both24(st_hand<IDX>(s, cur)) >> CARD_CQ) & 1u) ? (1ull << 25) : 0ull);
     if (phase == DK_PHASE_PLAY_CARD) {
-        uint32_t single = hand_any24(s.hands[cur]);
+        uint32_t single = hand_any24(st_hand<IDX>(s, cur));
         uint32_t ci = s.card_index, k = ci & 3u;
         if (k == 0u) return single;
-        uint32_t f = single & follow_mask(s.cards[ci - k], DOKO_TRUMP_MASK);
+        uint32_t f = single & follow_mask(st_quad<IDX>(s, ci >> 2) & 255u, DOKO_TRUMP_MASK);
         return f ? f : single;
     }
     return 0;
 }
+template <bool IDX = false>
 DK_HD uint32_t doko_state_trick_winner(const dk_state& s, uint32_t t, uint32_t* eyes) {
-    uint32_t follow = follow_mask(s.cards[4u * t], DOKO_TRUMP_MASK);
+    const uint32_t quad = st_quad<IDX>(s, t);
+    uint32_t follow = follow_mask(quad & 255u, DOKO_TRUMP_MASK);
     uint32_t best = 0, bestk = 0, e = 0;
+#pragma unroll
     for (uint32_t k = 0; k < 4u; ++k) {
-        uint32_t c = s.cards[4u * t + k];
+        uint32_t c = (quad >> (8u * k)) & 255u;
         uint32_t pw = card_power(c, DOKO_TRUMP_MASK, follow);
         if (k == 0u || pw > best) { best = pw; bestk = k; }
         e += card_eyes_by_rank(c - 6u * card_suit(c));
@@ -333,19 +445,22 @@ DK_HD uint32_t doko_state_trick_winner(const dk_state& s, uint32_t t, uint32_t* 
     return (st_trick_start(s, t) + bestk) & 3u;
 }
 // DoState::play_action (rs-doko/src/state/state.rs:189-309)
+template <bool IDX = false>
 DK_HD uint32_t doko_state_apply(dk_state& s, uint32_t action) {
-    if (action >= 26u || !((doko_state_legal_mask(s) >> action) & 1ull)) return 1;
+    if (action >= 26u || !((doko_state_legal_mask<IDX>(s) >> action) & 1ull)) return 1;
     uint32_t phase = st_phase(s), cur = st_cur(s);
     if (phase == DK_PHASE_RESERVATION) {
-        s.reservations[s.n_reservations++] = (uint8_t)(action == 25u ? 0u : 1u);   // DoReservation: Wedding 0, Healthy 1
+        st_push_reservation<IDX>(s, action == 25u ? 0u : 1u);                           // DoReservation: Wedding 0, Healthy 1
         uint32_t next = (cur + 1u) & 3u;
         st_set(s.meta, 2, 2, next);
         if (s.n_reservations == 4u) {
             uint32_t start = st_game_start(s), wed_i = 4;
+#pragma unroll
             for (uint32_t i = 0; i < 4u; ++i) if (s.reservations[i] == 0u) wed_i = i;
             uint32_t re = 0;
             if (wed_i < 4u) { st_set(s.meta, 6, 4, GT_WEDDING); st_set(s.meta, 10, 2, TEAM_WEDDING_UNSOLVED); st_set(s.meta, 12, 2, (start + wed_i) & 3u); }
             else {
+#pragma unroll
                 for (uint32_t p = 0; p < 4u; ++p) if ((hand_any24(s.hands[p]) >> CARD_CQ) & 1u) re |= 1u << p;
                 st_set(s.meta, 6, 4, GT_NORMAL); st_set(s.meta, 10, 2, TEAM_NO_WEDDING); st_set(s.meta, 16, 4, re);
             }
@@ -355,16 +470,16 @@ DK_HD uint32_t doko_state_apply(dk_state& s, uint32_t action) {
         return 0;
     }
     uint32_t c = action;
-    uint64_t h = s.hands[cur];
+    uint64_t h = st_hand<IDX>(s, cur);
     if ((h >> c) & 1ull) h &= ~(1ull << c); else h &= ~(1ull << (c + 24u));       // hand_remove: copy A first (rs-doko/src/hand/hand.rs:38-46)
-    s.hands[cur] = h;
+    st_set_hand<IDX>(s, cur, h);
     uint32_t ci = s.card_index;
-    s.cards[ci] = (uint8_t)c;
+    st_set_card<IDX>(s, ci, c);
     s.card_index = (uint8_t)(ci + 1u);
     if (((ci + 1u) & 3u) == 0u) {
         uint32_t t = ci >> 2, e;
-        uint32_t w = doko_state_trick_winner(s, t, &e);
-        s.eyes[w] = (uint8_t)(s.eyes[w] + e);
+        uint32_t w = doko_state_trick_winner<IDX>(s, t, &e);
+        st_add_eyes<IDX>(s, w, e);
         s.num_tricks = (uint16_t)(s.num_tricks + (1u << (4u * w)));
         if (st_team_tag(s) == TEAM_WEDDING_UNSOLVED) {
             uint32_t wed = st_wed_seat(s);
@@ -376,8 +491,10 @@ DK_HD uint32_t doko_state_apply(dk_state& s, uint32_t action) {
             st_set(s.meta, 2, 2, 0u);
             DokoLive g; doko_live_clear(g);
             g.re_mask = st_re_mask(s); g.ntricks = s.num_tricks;
+#pragma unroll
             for (uint32_t p = 0; p < 4u; ++p) g.eyes |= (uint32_t)s.eyes[p] << (8u * p);
             int32_t pts[4]; doko_final_points(g, pts);
+#pragma unroll
             for (uint32_t p = 0; p < 4u; ++p) s.points[p] = (int8_t)pts[p];
             return 0;
         }
@@ -389,15 +506,18 @@ DK_HD uint32_t doko_state_apply(dk_state& s, uint32_t action) {
     st_set(s.meta, 2, 2, (cur + 1u) & 3u);
     return 0;
 }
+template <bool IDX = false>
 DK_HD bool doko_state_to_live(const dk_state& s, DokoLive& g, DokoResume& rs) {
     doko_live_clear(g);
     uint32_t phase = st_phase(s);
     if (phase == DK_PHASE_FINISHED) return false;
-    uint32_t any[4], dup = 0;
-    for (uint32_t p = 0; p < 4u; ++p) { any[p] = hand_any24(s.hands[p]); dup |= hand_both24(s.hands[p]); }
+    uint32_t dup = 0;
+#pragma unroll
+    for (uint32_t p = 0; p < 4u; ++p) dup |= hand_both24(s.hands[p]);
     g.dup = dup;
     rs.n_res = s.n_reservations; rs.t0 = 0; rs.k0 = 0;
     rs.acc.follow = 0; rs.acc.best = 0; rs.acc.bestk = 0; rs.acc.teyes = 0;
+#pragma unroll
     for (uint32_t i = 0; i < 4u; ++i) rs.res_action[i] = i < s.n_reservations ? (s.reservations[i] == 0u ? 25u : 24u) : 0u;
     uint32_t base;
     if (phase == DK_PHASE_RESERVATION) base = st_game_start(s);
@@ -405,20 +525,25 @@ DK_HD bool doko_state_to_live(const dk_state& s, DokoLive& g, DokoResume& rs) {
         uint32_t ci = s.card_index, t0 = ci >> 2, k0 = ci & 3u;
         g.team_tag = st_team_tag(s); g.re_mask = st_re_mask(s); g.wed_seat = st_wed_seat(s); g.solved_idx = st_solved_idx(s);
         g.wedding = st_gt(s) == GT_WEDDING ? 1u : 0u;
+#pragma unroll
         for (uint32_t p = 0; p < 4u; ++p) g.eyes |= (uint32_t)s.eyes[p] << (8u * p);
         g.ntricks = s.num_tricks;
         base = st_trick_start(s, t0);
         rs.t0 = t0; rs.k0 = k0;
-        for (uint32_t k = 0; k < k0; ++k) {
-            uint32_t c = s.cards[4u * t0 + k];
+        const uint32_t quad0 = k0 ? st_quad<IDX>(s, t0) : 0u;
+#pragma unroll
+        for (uint32_t k = 0; k < 3u; ++k) {
+            if (k >= k0) break;
+            uint32_t c = (quad0 >> (8u * k)) & 255u;
             if (k == 0u) rs.acc.follow = follow_mask(c, DOKO_TRUMP_MASK);
             uint32_t pw = card_power(c, DOKO_TRUMP_MASK, rs.acc.follow);
             if (k == 0u || pw > rs.acc.best) { rs.acc.best = pw; rs.acc.bestk = k; }
             rs.acc.teyes += card_eyes_by_rank(c - 6u * card_suit(c));
         }
     }
-    g.base = base;
-    g.h0 = any[base]; g.h1 = any[(base + 1u) & 3u]; g.h2 = any[(base + 2u) & 3u]; g.h3 = any[(base + 3u) & 3u];
+    g.base = 0;
+    g.h0 = hand_any24(s.hands[0]); g.h1 = hand_any24(s.hands[1]); g.h2 = hand_any24(s.hands[2]); g.h3 = hand_any24(s.hands[3]);
+    doko_rotate(g, base);
     return true;
 }
 

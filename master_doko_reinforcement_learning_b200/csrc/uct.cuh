@@ -69,7 +69,7 @@ DK_HD double dk_dsqrt(double a) {
 // McFullDokoEnvState::allowed_actions(first_expansion) (env_state_full_doko.rs:132-172): below the root the solo / wedding
 // reservations disappear once any seat has declared a solo, and the announcement calls always.
 DK_HD uint64_t uct_allowed(const dk_state& s, bool first_expansion) {
-    uint64_t m = fdo_state_legal_mask(s);
+    uint64_t m = fdo_state_legal_mask<true>(s);
     if (!first_expansion) {
         for (uint32_t i = 0; i < s.n_reservations && i < 4u; ++i)
             if (s.reservations[i] >= 2u) m &= ~(0xFFull << 25);
@@ -206,7 +206,7 @@ DK_HD uint32_t uct_iteration(UctNode* __restrict__ pool, uint32_t& n_nodes, cons
         if (nch >= UCT_MAX_CHILDREN) return 1u;
         U4 blk = rng_block(key, SITE_EXPAND, 0);
         const uint32_t a = pick_msb_rank64(unexpanded, mulhi(blk.x, popcll(unexpanded)));
-        fdo_state_apply(s, a);                                                   // by_action
+        fdo_state_apply<true>(s, a);                                             // by_action (record in local memory)
         explore = n_nodes++;
         uct_init_node(pool[explore], s, node, a, false);
         pool[node].child[nch] = explore;
@@ -215,7 +215,7 @@ DK_HD uint32_t uct_iteration(UctNode* __restrict__ pool, uint32_t& n_nodes, cons
     int32_t p[4];                                                                // random_rollout (env_state_full_doko.rs:198-220) from `s`
     {
         FdoLive g; FdoResume rs;
-        if (fdo_state_to_live(s, g, rs)) { fdo_play_to_end<false, false>(g, key, &rs, lut); fdo_final_points(g, p); }
+        if (fdo_state_to_live<true>(s, g, rs)) { fdo_play_to_end<false, false>(g, key, &rs, lut); fdo_final_points(g, p); }
         else { p[0] = s.points[0]; p[1] = s.points[1]; p[2] = s.points[2]; p[3] = s.points[3]; }
     }
     uint32_t temp = explore;                                                     // backpropagate (:138-158)
