@@ -95,6 +95,11 @@ dk_status dk_init(int device, dk_ctx** out) {
         return DK_ERR_NO_DEVICE;
     }
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return DK_ERR_CUDA; }
+    {   // the kernels' lookup tables: evaluated here, resident in this device's memory from now on
+        std::vector<uint32_t> lut(dk::CARD_LUT_WORDS);
+        for (uint32_t i = 0; i < dk::CARD_LUT_WORDS; ++i) lut[i] = dk::lut_word(i);
+        if (cudaMemcpyToSymbol(dk::g_card_lut, lut.data(), lut.size() * sizeof(uint32_t)) != cudaSuccess) { cudaStreamDestroy(ctx->stream); delete ctx; return DK_ERR_CUDA; }
+    }
     *out = ctx;
     return DK_OK;
 }

@@ -136,9 +136,16 @@ DK_HD uint32_t rank_lut6_entry(uint32_t b) {
     for (uint32_t pos = 0; pos < 6u; ++pos) if ((b >> pos) & 1u) { e |= pos << (3u * j); j++; }
     return e;
 }
-constexpr uint32_t CARD_LUT_WORDS = 96u;     // [0,24) card attributes (card_lut_entry) | [24,31) fdo_thr_lut_word | [32,96) rank_lut6_entry
+// The lookup tables of the playout kernels, one word array: built once on the host (lut_word, fdo_rules.cuh), kept in device memory
+// and copied into shared memory by every block (kernels.cuh stage_card_lut).
+//   [0,24) card attributes (card_lut_entry) | [24,31) fdo_thr_lut_word | [32,96) rank_lut6_entry |
+//   [96,288) call thresholds of both teams by (wedding shift, re level, kontra level) (fdo_thr2_lut_word) |
+//   [288,352) 256 bytes: who calls in a segment of an announcement round, by (eligible seats, decision bits) (fdo_seg_lut_byte)
+constexpr uint32_t CARD_LUT_WORDS = 352u;
 constexpr uint32_t THR_LUT_BASE = 24u;
 constexpr uint32_t RANK_LUT_BASE = 32u;
+constexpr uint32_t THR2_LUT_BASE = 96u;
+constexpr uint32_t SEG_LUT_BASE = 288u;
 DK_HD uint32_t select_lsb24_lut(uint32_t x, uint32_t k, const uint32_t* __restrict__ lut) {
     uint32_t pos = 0, c;
     c = popc(x & 0xFFFu); if (k >= c) { k -= c; x >>= 12; pos = 12u; }

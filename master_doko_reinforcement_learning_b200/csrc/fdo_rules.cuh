@@ -59,6 +59,37 @@ DK_HD uint32_t fdo_min_cards_to_call_lut(uint32_t m, uint32_t e, uint32_t w, con
     return sub == 15u ? 99u : 11u - w - sub;
 }
 
+// Both teams' thresholds in one word, indexed by 64 w + 8 re_low + ko_low (w = wedding shift 0..2): thr_re | thr_ko << 8 (99 = never).
+DK_HD uint32_t fdo_thr2_lut_word(uint32_t i) {
+    const uint32_t w = i >> 6, re = (i >> 3) & 7u, ko = i & 7u;
+    return fdo_min_cards_to_call(re, ko, w) | (fdo_min_cards_to_call(ko, re, w) << 8);
+}
+// One segment of an announcement round: `win` (4 bits, bit d = the seat d places after the next seat to ask is eligible and is
+// reached before the count of consecutive passes hits 4), `hit` = the decision bits of those seats in visiting order (bit k = the
+// k-th eligible seat calls).  Entry = d | j << 2: the first caller is the (j+1)-th eligible seat, d places ahead.  0 when nobody calls.
+DK_HD uint32_t fdo_seg_lut_byte(uint32_t win, uint32_t hit) {
+    if (hit == 0u) return 0u;
+    uint32_t j = 0;
+    while (!((hit >> j) & 1u)) j++;
+    uint32_t wj = win;
+    for (uint32_t k = 0; k < j; ++k) wj &= wj - 1u;
+    if (wj == 0u) return 0u;                             // more decision bits than eligible seats: not a reachable index
+    uint32_t d = 0;
+    while (!((wj >> d) & 1u)) d++;
+    return d | (j << 2);
+}
+// Word i of the shared lookup table (layout: dk_common.cuh CARD_LUT_WORDS).
+DK_HD uint32_t lut_word(uint32_t i) {
+    if (i < 24u) return card_lut_entry(i);
+    if (i < 31u) return fdo_thr_lut_word(i - THR_LUT_BASE);
+    if (i < RANK_LUT_BASE) return 0u;
+    if (i < THR2_LUT_BASE) return rank_lut6_entry(i - RANK_LUT_BASE);
+    if (i < SEG_LUT_BASE) return fdo_thr2_lut_word(i - THR2_LUT_BASE);
+    uint32_t v = 0;
+    for (uint32_t b = 0; b < 4u; ++b) { const uint32_t idx = 4u * (i - SEG_LUT_BASE) + b; v |= fdo_seg_lut_byte(idx >> 4, idx & 15u) << (8u * b); }
+    return v;
+}
+
 // ---- scoring ----------------------------------------------------------------------------------------------------
 // Closed form of FdoEndOfGameStats::calculate (stats/stats.rs:46-240) and its callees re_won (win_conditions/re_won.rs),
 // kontra_won, FdoBasicWinningPointsDetails::calculate (basic_points/basic_winning_points.rs:48-284),
@@ -283,7 +314,9 @@ DK_HD void fdo_replay_announcements(FdoLive& g, const RngKey& key, uint32_t star
     if (ci >= 48u) return;
     const uint32_t re = g.re_mask & 15u;
     uint32_t re_low = g.re_low, ko_low = g.ko_low, ord = g.ann_count;
-    uint32_t thr_re = fdo_min_cards_to_call_lut(re_low, ko_low, w, lut), thr_ko = fdo_min_cards_to_call_lut(ko_low, re_low, w, lut);
+    const uint32_t* __restrict__ thr2 = lut + THR2_LUT_BASE + 64u * w;              // both teams' thresholds by 8 re_low + ko_low
+    const uint8_t* __restrict__ seg = reinterpret_cast<const uint8_t*>(lut + SEG_LUT_BASE);
+    uint32_t tp = thr2[8u * re_low + ko_low], thr_re = tp & 255u, thr_ko = tp >> 8;
     AnnBits st; st.buf = 0; st.avail = 0; st.next = 0; st.blk = 0; st.w.x = st.w.y = st.w.z = st.w.w = 0;
     if (WITH_ANN) fdo_ann_open(st, key, ord);                      // lock-step: every lane fetches its block (block 0 for a fresh game) before the loop
     // per-position values (recomputed when ci advances)
@@ -311,14 +344,10 @@ DK_HD void fdo_replay_announcements(FdoLive& g, const RngKey& key, uint32_t star
             turns = 0;
             continue;
         }
-        uint32_t j = ffs0(hit);                                   // j eligible seats pass, the (j+1)-th calls
+        const uint32_t sv = seg[16u * win + hit];                 // j eligible seats pass, the (j+1)-th calls: it sits d places after p
+        const uint32_t j = sv >> 2, d = sv & 3u;
         ord += j + 1u;
         fdo_ann_consume(st, key, j + 1u);
-        uint32_t wj = win;                                        // distance of the (j+1)-th eligible seat from p: win has <= 4 bits,
-        if (j > 0u) wj &= wj - 1u;                                //   so clearing the lowest set bit j times beats a generic rank select
-        if (j > 1u) wj &= wj - 1u;
-        if (j > 2u) wj &= wj - 1u;
-        uint32_t d = ffs0(wj);
         p = (p + d) & 3u;
         uint32_t is_re = (re >> p) & 1u;
         uint32_t c = cmax - ((played >> p) & 1u);
@@ -326,7 +355,7 @@ DK_HD void fdo_replay_announcements(FdoLive& g, const RngKey& key, uint32_t star
         ml = ml == 6u ? 0u : ml;
         uint32_t call = (ml < 5u && c + ml + w >= 11u) ? ml + 1u : 1u;   // next level, else the counter (recorded as Re/Kontra)
         if (is_re) re_low = call; else ko_low = call;             // announcement.rs:203-210
-        thr_re = fdo_min_cards_to_call_lut(re_low, ko_low, w, lut); thr_ko = fdo_min_cards_to_call_lut(ko_low, re_low, w, lut);
+        tp = thr2[8u * re_low + ko_low]; thr_re = tp & 255u; thr_ko = tp >> 8;
         turns = 0;
         p = (p + 1u) & 3u;
     }

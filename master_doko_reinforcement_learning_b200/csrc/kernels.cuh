@@ -35,11 +35,11 @@ struct SharedDeck {
     __device__ __forceinline__ void set8(uint32_t j, uint32_t v) { reinterpret_cast<uint8_t*>(base)[(j >> 2) * (PLAYOUT_THREADS * 4) + (j & 3u)] = (uint8_t)v; }
 };
 
-// Stage the 24-entry card attribute table in shared memory (first 24 threads), then sync.
-__device__ __forceinline__ void fill_card_lut(uint32_t* lut) {       // needs blockDim.x >= 64; caller syncs
-    if (threadIdx.x < 24) lut[threadIdx.x] = card_lut_entry(threadIdx.x);
-    else if (threadIdx.x < 31) lut[threadIdx.x] = fdo_thr_lut_word(threadIdx.x - THR_LUT_BASE);
-    if (threadIdx.x < 64) lut[RANK_LUT_BASE + threadIdx.x] = rank_lut6_entry(threadIdx.x);
+// The lookup tables (dk_common.cuh CARD_LUT_WORDS; 1.4 KB) live in device memory, written once per context by dk_init from the host
+// evaluation of lut_word; every block copies them into shared memory with coalesced loads (L2 hits).
+__device__ uint32_t g_card_lut[CARD_LUT_WORDS];
+__device__ __forceinline__ void fill_card_lut(uint32_t* lut) {       // caller syncs
+    for (uint32_t i = threadIdx.x; i < CARD_LUT_WORDS; i += blockDim.x) lut[i] = g_card_lut[i];
 }
 __device__ __forceinline__ void stage_card_lut(uint32_t* lut) {
     fill_card_lut(lut);

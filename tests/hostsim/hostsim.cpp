@@ -33,7 +33,7 @@ struct LocalDeck {
 const uint32_t* card_lut() {
     static uint32_t lut[dk::CARD_LUT_WORDS];
     static bool init = false;
-    if (!init) { for (uint32_t c = 0; c < 24; ++c) lut[c] = dk::card_lut_entry(c); for (uint32_t b = 0; b < 64; ++b) lut[dk::RANK_LUT_BASE + b] = dk::rank_lut6_entry(b); for (uint32_t m = 0; m < 7; ++m) lut[dk::THR_LUT_BASE + m] = dk::fdo_thr_lut_word(m); init = true; }
+    if (!init) { for (uint32_t i = 0; i < dk::CARD_LUT_WORDS; ++i) lut[i] = dk::lut_word(i); init = true; }
     return lut;
 }
 dk::RngKey make_key(uint64_t seed, uint64_t unit, uint32_t epoch) {
