@@ -21,6 +21,7 @@ struct dk_ctx {
     uint64_t launches = 0;
     std::string last_error;
     int sm_count = 0, cc_major = 0, cc_minor = 0;
+    bool fresh_smem_set = false;     // dynamic shared-memory opt-in of the fresh-game playout kernels done on this device
     size_t total_mem = 0;
     // scratch for the *_host entry points
     void* d_scratch = nullptr;
@@ -42,6 +43,11 @@ dk_status fail(dk_ctx* ctx, dk_status st, const std::string& msg) {
     if (ctx) ctx->last_error = msg;
     return st;
 }
+#define DK_TRY(expr)                                                                                    \
+    do {                                                                                                \
+        dk_status st__ = (expr);                                                                        \
+        if (st__ != DK_OK) return st__;                                                                 \
+    } while (0)
 #define DK_CUDA(ctx, call)                                                                              \
     do {                                                                                                \
         cudaError_t e__ = (call);                                                                       \
@@ -98,7 +104,10 @@ dk_status dk_init(int device, dk_ctx** out) {
     {   // the kernels' lookup tables: evaluated here, resident in this device's memory from now on
         std::vector<uint32_t> lut(dk::CARD_LUT_WORDS);
         for (uint32_t i = 0; i < dk::CARD_LUT_WORDS; ++i) lut[i] = dk::lut_word(i);
-        if (cudaMemcpyToSymbol(dk::g_card_lut, lut.data(), lut.size() * sizeof(uint32_t)) != cudaSuccess) { cudaStreamDestroy(ctx->stream); delete ctx; return DK_ERR_CUDA; }
+        std::vector<uint64_t> sel(dk::SEL12_WORDS / 2);
+        for (uint32_t h = 0; h < dk::SEL12_WORDS / 2; ++h) sel[h] = dk::sel12_entry(h);
+        if (cudaMemcpyToSymbol(dk::g_card_lut, lut.data(), lut.size() * sizeof(uint32_t)) != cudaSuccess ||
+            cudaMemcpyToSymbol(dk::g_sel12, sel.data(), sel.size() * sizeof(uint64_t)) != cudaSuccess) { cudaStreamDestroy(ctx->stream); delete ctx; return DK_ERR_CUDA; }
     }
     *out = ctx;
     return DK_OK;
@@ -135,17 +144,29 @@ dk_status dk_synchronize(dk_ctx* ctx, dk_stream stream) {
 
 uint64_t dk_launch_count(const dk_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+// The fresh-game playout kernels use more than the 48 KB of shared memory a kernel gets by default: opt in once per device.
+static dk_status fresh_smem_opt_in(dk_ctx* ctx) {
+    if (ctx->fresh_smem_set) return DK_OK;
+    const int bytes = (int)dk::FDO_FRESH_SMEM_BYTES;
+    DK_CUDA(ctx, cudaFuncSetAttribute(dk::fdo_playout_fresh_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    DK_CUDA(ctx, cudaFuncSetAttribute(dk::fdo_playout_fresh_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    DK_CUDA(ctx, cudaFuncSetAttribute(dk::doko_playout_fresh_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    DK_CUDA(ctx, cudaFuncSetAttribute(dk::doko_playout_fresh_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    ctx->fresh_smem_set = true;
+    return DK_OK;
+}
 static dk_status playout_launch(dk_ctx* ctx, int engine, uint32_t flags, size_t n, const dk_state* states, const dk::RngParams& rp,
                                 void* points_out, void* steps_out, bool compact, cudaStream_t s) {
     const bool with_ann = (flags & DK_PLAYOUT_WITH_ANNOUNCEMENTS) != 0;
     if (states == nullptr) {
-        unsigned grid = (unsigned)((n + dk::PLAYOUT_THREADS - 1) / dk::PLAYOUT_THREADS);
+        const unsigned fgrid = (unsigned)((n + dk::FDO_FRESH_THREADS - 1) / dk::FDO_FRESH_THREADS);
+        DK_TRY(fresh_smem_opt_in(ctx));
         if (engine == DK_FDO) {
-            if (with_ann) dk::fdo_playout_fresh_kernel<true><<<grid, dk::PLAYOUT_THREADS, 0, s>>>(rp, (uint64_t)n, points_out, steps_out, compact);
-            else dk::fdo_playout_fresh_kernel<false><<<grid, dk::PLAYOUT_THREADS, 0, s>>>(rp, (uint64_t)n, points_out, steps_out, compact);
+            if (with_ann) dk::fdo_playout_fresh_kernel<true><<<fgrid, dk::FDO_FRESH_THREADS, dk::FDO_FRESH_SMEM_BYTES, s>>>(rp, (uint64_t)n, points_out, steps_out, compact);
+            else dk::fdo_playout_fresh_kernel<false><<<fgrid, dk::FDO_FRESH_THREADS, dk::FDO_FRESH_SMEM_BYTES, s>>>(rp, (uint64_t)n, points_out, steps_out, compact);
             return check_launch(ctx, "fdo_playout_fresh_kernel");
         }
-        dk::doko_playout_fresh_kernel<false><<<grid, dk::PLAYOUT_THREADS, 0, s>>>(rp, (uint64_t)n, points_out, steps_out, compact, nullptr, nullptr);
+        dk::doko_playout_fresh_kernel<false><<<fgrid, dk::FDO_FRESH_THREADS, dk::FDO_FRESH_SMEM_BYTES, s>>>(rp, (uint64_t)n, points_out, steps_out, compact, nullptr, nullptr);
         return check_launch(ctx, "doko_playout_fresh_kernel");
     }
     unsigned grid = (unsigned)((n + dk::STATE_THREADS - 1) / dk::STATE_THREADS);
@@ -172,8 +193,9 @@ dk_status dk_playout_trace(dk_ctx* ctx, int engine, size_t n, const dk_rng* rng,
     if (engine != DK_DOKO) return fail(ctx, DK_ERR_UNSUPPORTED, "dk_playout_trace: only DK_DOKO records traces");
     if (n == 0) return DK_OK;
     DK_CUDA(ctx, cudaSetDevice(ctx->device));
-    unsigned grid = (unsigned)((n + dk::PLAYOUT_THREADS - 1) / dk::PLAYOUT_THREADS);
-    dk::doko_playout_fresh_kernel<true><<<grid, dk::PLAYOUT_THREADS, 0, pick_stream(ctx, stream)>>>(to_params(rng), (uint64_t)n, points_out, nullptr, false,
+    DK_TRY(fresh_smem_opt_in(ctx));
+    unsigned grid = (unsigned)((n + dk::FDO_FRESH_THREADS - 1) / dk::FDO_FRESH_THREADS);
+    dk::doko_playout_fresh_kernel<true><<<grid, dk::FDO_FRESH_THREADS, dk::FDO_FRESH_SMEM_BYTES, pick_stream(ctx, stream)>>>(to_params(rng), (uint64_t)n, points_out, nullptr, false,
                                                                                                     trace_out, (uint4*)aux_out);
     return check_launch(ctx, "doko_playout_fresh_kernel<trace>");
 }

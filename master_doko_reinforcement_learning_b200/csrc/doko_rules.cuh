@@ -57,12 +57,12 @@ DK_HD void doko_finish_reservations(DokoLive& g, const uint32_t res_action[4]) {
 struct DokoTrickAcc { uint32_t follow, best, bestk, teyes; };
 
 // Card step of frame seat K (rs-doko/src/action/allowed_actions.rs:153-192, state/state.rs:194-252).
-template <int K>
+template <int K, bool SEL12 = false>
 DK_HD uint32_t doko_card_step(DokoLive& g, uint32_t& h, DokoTrickAcc& a, uint32_t word, const uint32_t* __restrict__ lut) {
     uint32_t mask = h;
     if (K > 0) { uint32_t f = h & a.follow; mask = f ? f : h; }
     uint32_t idx = mulhi(word, popc(mask));
-    uint32_t c = pick_msb_rank24_lut(mask, idx, lut);
+    uint32_t c = SEL12 ? pick_msb_rank24_tab(mask, idx, reinterpret_cast<const uint64_t*>(lut + SEL12_LUT_BASE)) : pick_msb_rank24_lut(mask, idx, lut);
     uint32_t bit = 1u << c;
     uint32_t e = lut[c];
     uint32_t dbl = g.dup & bit;
@@ -112,7 +112,7 @@ struct DokoResume {
 };
 
 // trace (optional, FRESH only): 52 action ids in play order.
-template <bool FRESH, bool TRACE>
+template <bool FRESH, bool TRACE, bool SEL12 = false>
 DK_HD void doko_play_to_end(DokoLive& g, const RngKey& key, const DokoResume* rs, uint8_t* trace, const uint32_t* __restrict__ lut) {
     uint32_t n_res = FRESH ? 0u : rs->n_res;
     if (n_res < 4u) {
@@ -135,10 +135,10 @@ DK_HD void doko_play_to_end(DokoLive& g, const RngKey& key, const DokoResume* rs
         bool first = !FRESH && t == t0;
         if (first) { k0 = rs->k0; if (k0 > 0u) a = rs->acc; }
         uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
-        if (!first || k0 <= 0u) c0 = doko_card_step<0>(g, g.h0, a, blk.x, lut);
-        if (!first || k0 <= 1u) c1 = doko_card_step<1>(g, g.h1, a, blk.y, lut);
-        if (!first || k0 <= 2u) c2 = doko_card_step<2>(g, g.h2, a, blk.z, lut);
-        c3 = doko_card_step<3>(g, g.h3, a, blk.w, lut);
+        if (!first || k0 <= 0u) c0 = doko_card_step<0, SEL12>(g, g.h0, a, blk.x, lut);
+        if (!first || k0 <= 1u) c1 = doko_card_step<1, SEL12>(g, g.h1, a, blk.y, lut);
+        if (!first || k0 <= 2u) c2 = doko_card_step<2, SEL12>(g, g.h2, a, blk.z, lut);
+        c3 = doko_card_step<3, SEL12>(g, g.h3, a, blk.w, lut);
         if (TRACE) { trace[4 + 4 * t] = (uint8_t)c0; trace[5 + 4 * t] = (uint8_t)c1; trace[6 + 4 * t] = (uint8_t)c2; trace[7 + 4 * t] = (uint8_t)c3; }
         doko_trick_done(g, a, t);
     }
@@ -149,7 +149,7 @@ DK_HD void doko_live_clear(DokoLive& g) {
     g.re_mask = 0; g.wed_seat = 0; g.solved_idx = 0; g.wedding = 0; g.steps = 0;
 }
 
-template <bool TRACE, class Deck>
+template <bool TRACE, class Deck, bool SEL12 = false>
 DK_HD void doko_playout_fresh(const RngKey& key, Deck& deck, const uint32_t* __restrict__ lut, int32_t pts[4], uint32_t& steps, uint8_t* trace, uint32_t* aux) {
     DokoLive g;
     doko_live_clear(g);
@@ -158,7 +158,7 @@ DK_HD void doko_playout_fresh(const RngKey& key, Deck& deck, const uint32_t* __r
     fdo_deal(dummy, key, deck, ah, g.dup, start);        // same deal contract as the full engine
     g.h0 = ah[0]; g.h1 = ah[1]; g.h2 = ah[2]; g.h3 = ah[3];
     doko_rotate(g, start);
-    doko_play_to_end<true, TRACE>(g, key, nullptr, trace, lut);
+    doko_play_to_end<true, TRACE, SEL12>(g, key, nullptr, trace, lut);
     doko_final_points(g, pts);
     steps = g.steps;
     if (TRACE && aux) { aux[0] = g.wedding ? 1u : 0u; aux[1] = g.re_mask; aux[2] = g.eyes; aux[3] = g.ntricks; }

@@ -365,7 +365,7 @@ DK_HD void fdo_replay_announcements(FdoLive& g, const RngKey& key, uint32_t star
 struct TrickAcc { uint32_t follow, best, bestk, bestc, teyes, foxm; };
 
 // Card step of frame seat K (compile-time) with hand register `h` (action/allowed_actions.rs:97-140, state.rs:274-357).
-template <int K>
+template <int K, bool SEL12 = false>
 DK_HD void fdo_card_step(FdoLive& g, uint32_t& h, TrickAcc& a, uint32_t word, bool last_trick, const uint32_t* __restrict__ lut) {
     uint32_t mask = h;
     if (K > 0 && !last_trick) {                           // state.rs:360-372: no colour is enforced in the 12th trick
@@ -374,7 +374,7 @@ DK_HD void fdo_card_step(FdoLive& g, uint32_t& h, TrickAcc& a, uint32_t word, bo
     }
     uint32_t n = popc(mask);
     uint32_t idx = mulhi(word, n);
-    uint32_t c = pick_msb_rank24_lut(mask, idx, lut);
+    uint32_t c = SEL12 ? pick_msb_rank24_tab(mask, idx, reinterpret_cast<const uint64_t*>(lut + SEL12_LUT_BASE)) : pick_msb_rank24_lut(mask, idx, lut);
     uint32_t bit = 1u << c;
     uint32_t e = lut[c];
     uint32_t dbl = g.dup & bit;                           // hand.remove: a doubled card stays in the hand once
@@ -447,7 +447,7 @@ struct FdoResume {
 };
 
 // Plays the game to the end.  FRESH: hands/base already set by the deal, nothing played yet.
-template <bool WITH_ANN, bool FRESH>
+template <bool WITH_ANN, bool FRESH, bool SEL12 = false>
 DK_HD void fdo_play_to_end(FdoLive& g, const RngKey& key, const FdoResume* rs, const uint32_t* __restrict__ lut) {
     uint32_t n_res = FRESH ? 0u : rs->n_res;
     if (n_res < 4u) {
@@ -472,7 +472,7 @@ DK_HD void fdo_play_to_end(FdoLive& g, const RngKey& key, const FdoResume* rs, c
         if (first) { k0 = rs->k0; if (k0 > 0u) a = rs->acc; }
         bool last = t == 11u;
 #define DK_FDO_POS(K, HREG, WORD)                                                                      \
-        if (!first || k0 <= (uint32_t)(K)) fdo_card_step<K>(g, HREG, a, WORD, last, lut);
+        if (!first || k0 <= (uint32_t)(K)) fdo_card_step<K, SEL12>(g, HREG, a, WORD, last, lut);
         DK_FDO_POS(0, g.h0, blk.x)
         DK_FDO_POS(1, g.h1, blk.y)
         DK_FDO_POS(2, g.h2, blk.z)
@@ -486,7 +486,7 @@ DK_HD void fdo_play_to_end(FdoLive& g, const RngKey& key, const FdoResume* rs, c
 }
 
 // Fresh game: deal + reservations + 12 tricks + scoring.
-template <bool WITH_ANN, class Deck>
+template <bool WITH_ANN, class Deck, bool SEL12 = false>
 DK_HD void fdo_playout_fresh(const RngKey& key, Deck& deck, const uint32_t* __restrict__ lut, int32_t pts[4], uint32_t& steps) {
     FdoLive g;
     fdo_live_clear(g);
@@ -495,7 +495,7 @@ DK_HD void fdo_playout_fresh(const RngKey& key, Deck& deck, const uint32_t* __re
     g.h0 = ah[0]; g.h1 = ah[1]; g.h2 = ah[2]; g.h3 = ah[3];
     g.base = 0;
     fdo_rotate(g, start);
-    fdo_play_to_end<WITH_ANN, true>(g, key, nullptr, lut);
+    fdo_play_to_end<WITH_ANN, true, SEL12>(g, key, nullptr, lut);
     fdo_final_points(g, pts);
     steps = g.steps;
 }

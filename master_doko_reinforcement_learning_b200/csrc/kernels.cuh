@@ -26,20 +26,27 @@ struct RngParams {
 
 // Per-thread 12-word scratch in shared memory, word-interleaved across the block so that every access of a
 // warp hits 32 distinct banks regardless of the (data-dependent) word index.
-struct SharedDeck {
+template <int THREADS>
+struct SharedDeckT {
     uint32_t* base;  // &smem[threadIdx.x]
-    __device__ __forceinline__ uint32_t get(uint32_t w) const { return base[w * PLAYOUT_THREADS]; }
-    __device__ __forceinline__ void set(uint32_t w, uint32_t v) { base[w * PLAYOUT_THREADS] = v; }
+    __device__ __forceinline__ uint32_t get(uint32_t w) const { return base[w * THREADS]; }
+    __device__ __forceinline__ void set(uint32_t w, uint32_t v) { base[w * THREADS] = v; }
     // byte j of the thread's 48: byte (j & 3) of word (j >> 2); every lane stays in its own bank for any j
-    __device__ __forceinline__ uint32_t get8(uint32_t j) const { return reinterpret_cast<const uint8_t*>(base)[(j >> 2) * (PLAYOUT_THREADS * 4) + (j & 3u)]; }
-    __device__ __forceinline__ void set8(uint32_t j, uint32_t v) { reinterpret_cast<uint8_t*>(base)[(j >> 2) * (PLAYOUT_THREADS * 4) + (j & 3u)] = (uint8_t)v; }
+    __device__ __forceinline__ uint32_t get8(uint32_t j) const { return reinterpret_cast<const uint8_t*>(base)[(j >> 2) * (THREADS * 4) + (j & 3u)]; }
+    __device__ __forceinline__ void set8(uint32_t j, uint32_t v) { reinterpret_cast<uint8_t*>(base)[(j >> 2) * (THREADS * 4) + (j & 3u)] = (uint8_t)v; }
 };
+using SharedDeck = SharedDeckT<PLAYOUT_THREADS>;
 
 // The lookup tables (dk_common.cuh CARD_LUT_WORDS; 1.4 KB) live in device memory, written once per context by dk_init from the host
 // evaluation of lut_word; every block copies them into shared memory with coalesced loads (L2 hits).
 __device__ uint32_t g_card_lut[CARD_LUT_WORDS];
+__device__ uint4 g_sel12[SEL12_WORDS / 4];                           // the 12-bit rank-select table (sel12_entry), two entries per uint4
 __device__ __forceinline__ void fill_card_lut(uint32_t* lut) {       // caller syncs
     for (uint32_t i = threadIdx.x; i < CARD_LUT_WORDS; i += blockDim.x) lut[i] = g_card_lut[i];
+}
+__device__ __forceinline__ void fill_sel12(uint32_t* lut) {          // lut: 16-byte aligned, CARD_LUT_WORDS + SEL12_WORDS words; caller syncs
+    uint4* dst = reinterpret_cast<uint4*>(lut + SEL12_LUT_BASE);
+    for (uint32_t i = threadIdx.x; i < SEL12_WORDS / 4u; i += blockDim.x) dst[i] = g_sel12[i];
 }
 __device__ __forceinline__ void stage_card_lut(uint32_t* lut) {
     fill_card_lut(lut);
@@ -70,21 +77,34 @@ __device__ __forceinline__ void store_result(void* __restrict__ points, void* __
 
 // K2: fresh full-rules playouts.  Replaces FdoState::new_game + the random_action loop
 // (rs-full-doko/src/state/state.rs:169-178,378-431).  HBM traffic: 0 B in, 16 B points + 4 B steps out per game.
+#ifndef DK_FDO_FRESH_THREADS
+#define DK_FDO_FRESH_THREADS 384
+#endif
+// Fresh-game playout kernels (K1, K2): 3 blocks x 384 threads per SM, 51.6 KB dynamic shared memory per block (tables 33.4 KB + shuffle
+// scratch 18 KB).  320 x 4, 256 x 4 and 640 x 2 measure within 1 % (profiles/r01_k2_sel12_experiment.txt): the kernels are ALU-pipe bound.
+constexpr int FDO_FRESH_THREADS = DK_FDO_FRESH_THREADS;
+#ifndef DK_FDO_FRESH_BLOCKS
+#define DK_FDO_FRESH_BLOCKS 3
+#endif
+constexpr uint32_t FDO_FRESH_SMEM_BYTES = 4u * (CARD_LUT_WORDS + SEL12_WORDS + 12u * FDO_FRESH_THREADS);   // dynamic: above the 48 KB static limit
 template <bool WITH_ANN>
-__global__ void __launch_bounds__(PLAYOUT_THREADS)
+__global__ void __launch_bounds__(FDO_FRESH_THREADS, DK_FDO_FRESH_BLOCKS)
 fdo_playout_fresh_kernel(RngParams rp, uint64_t n, void* __restrict__ points, void* __restrict__ steps, bool compact) {
-    __shared__ uint32_t smem[12 * PLAYOUT_THREADS];
-    __shared__ uint32_t lut[CARD_LUT_WORDS];
-    stage_card_lut(lut);
-    uint64_t i = (uint64_t)blockIdx.x * PLAYOUT_THREADS + threadIdx.x;
+    extern __shared__ __align__(16) uint32_t fresh_smem[];
+    uint32_t* lut = fresh_smem;                                        // CARD_LUT_WORDS + SEL12_WORDS words (16-byte aligned, SEL12 part 8-byte aligned)
+    uint32_t* smem = fresh_smem + CARD_LUT_WORDS + SEL12_WORDS;        // the shuffle scratch: 12 words per thread, word-interleaved
+    fill_card_lut(lut);
+    fill_sel12(lut);
+    __syncthreads();
+    uint64_t i = (uint64_t)blockIdx.x * FDO_FRESH_THREADS + threadIdx.x;
     // Out-of-range lanes play game n-1 again (keeps the warp converged); they just do not store.
     uint64_t gi = i < n ? i : n - 1;
-    SharedDeck deck;
+    SharedDeckT<FDO_FRESH_THREADS> deck;
     deck.base = smem + threadIdx.x;
     RngKey key = make_key(rp, gi, 0, false);
     int32_t p[4];
     uint32_t s;
-    fdo_playout_fresh<WITH_ANN>(key, deck, lut, p, s);
+    fdo_playout_fresh<WITH_ANN, SharedDeckT<FDO_FRESH_THREADS>, true>(key, deck, lut, p, s);
     if (i < n) store_result(points, steps, i, p, s, compact);
 }
 
@@ -92,21 +112,24 @@ fdo_playout_fresh_kernel(RngParams rp, uint64_t n, void* __restrict__ points, vo
 // K1: fresh simplified-rules playouts (DoState::new_game + 52 random actions, rs-doko/src/state/state.rs:159-168,315-334).
 // TRACE additionally writes the 52 action ids and (wedding flag, re mask, packed eyes, packed tricks) per game.
 template <bool TRACE>
-__global__ void __launch_bounds__(PLAYOUT_THREADS)
+__global__ void __launch_bounds__(FDO_FRESH_THREADS, DK_FDO_FRESH_BLOCKS)
 doko_playout_fresh_kernel(RngParams rp, uint64_t n, void* __restrict__ points, void* __restrict__ steps, bool compact,
                           uint8_t* __restrict__ trace, uint4* __restrict__ aux) {
-    __shared__ uint32_t smem[12 * PLAYOUT_THREADS];
-    __shared__ uint32_t lut[CARD_LUT_WORDS];
-    stage_card_lut(lut);
-    uint64_t i = (uint64_t)blockIdx.x * PLAYOUT_THREADS + threadIdx.x;
+    extern __shared__ __align__(16) uint32_t fresh_smem[];
+    uint32_t* lut = fresh_smem;
+    uint32_t* smem = fresh_smem + CARD_LUT_WORDS + SEL12_WORDS;
+    fill_card_lut(lut);
+    fill_sel12(lut);
+    __syncthreads();
+    uint64_t i = (uint64_t)blockIdx.x * FDO_FRESH_THREADS + threadIdx.x;
     uint64_t gi = i < n ? i : n - 1;
-    SharedDeck deck;
+    SharedDeckT<FDO_FRESH_THREADS> deck;
     deck.base = smem + threadIdx.x;
     RngKey key = make_key(rp, gi, 0, false);
     int32_t p[4];
     uint32_t s, ax[4];
     uint8_t tr[52];
-    doko_playout_fresh<TRACE>(key, deck, lut, p, s, tr, ax);
+    doko_playout_fresh<TRACE, SharedDeckT<FDO_FRESH_THREADS>, true>(key, deck, lut, p, s, tr, ax);
     if (i < n) {
         store_result(points, steps, i, p, s, compact);
         if (TRACE) {

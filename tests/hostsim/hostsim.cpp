@@ -30,10 +30,14 @@ struct LocalDeck {
     uint32_t get8(uint32_t j) const { return (w[j >> 2] >> (8u * (j & 3u))) & 0xFFu; }
     void set8(uint32_t j, uint32_t v) { w[j >> 2] = (w[j >> 2] & ~(0xFFu << (8u * (j & 3u)))) | ((v & 0xFFu) << (8u * (j & 3u))); }
 };
-const uint32_t* card_lut() {
-    static uint32_t lut[dk::CARD_LUT_WORDS];
+const uint32_t* card_lut() {      // the shared-memory image of the fresh-game playout kernel: small tables + the 12-bit rank-select table
+    alignas(16) static uint32_t lut[dk::CARD_LUT_WORDS + dk::SEL12_WORDS];
     static bool init = false;
-    if (!init) { for (uint32_t i = 0; i < dk::CARD_LUT_WORDS; ++i) lut[i] = dk::lut_word(i); init = true; }
+    if (!init) {
+        for (uint32_t i = 0; i < dk::CARD_LUT_WORDS; ++i) lut[i] = dk::lut_word(i);
+        for (uint32_t h = 0; h < dk::SEL12_WORDS / 2; ++h) { uint64_t e = dk::sel12_entry(h); std::memcpy(lut + dk::SEL12_LUT_BASE + 2 * h, &e, 8); }
+        init = true;
+    }
     return lut;
 }
 dk::RngKey make_key(uint64_t seed, uint64_t unit, uint32_t epoch) {
@@ -47,7 +51,8 @@ SIM_API void sim_fdo_playout_fresh(uint64_t seed, uint32_t epoch, uint64_t first
         LocalDeck deck;
         dk::RngKey key = make_key(seed, first_id + i, epoch);
         int32_t p[4]; uint32_t s;
-        if (with_ann) dk::fdo_playout_fresh<true>(key, deck, card_lut(), p, s); else dk::fdo_playout_fresh<false>(key, deck, card_lut(), p, s);
+        // the fresh-game kernel's instantiation: rank select through the 12-bit table
+        if (with_ann) dk::fdo_playout_fresh<true, LocalDeck, true>(key, deck, card_lut(), p, s); else dk::fdo_playout_fresh<false, LocalDeck, true>(key, deck, card_lut(), p, s);
         for (int q = 0; q < 4; ++q) points[i * 4 + q] = p[q];
         steps[i] = s;
     }
@@ -57,7 +62,7 @@ SIM_API void sim_doko_playout_fresh(uint64_t seed, uint32_t epoch, uint64_t firs
         LocalDeck deck;
         dk::RngKey key = make_key(seed, first_id + i, epoch);
         int32_t p[4]; uint32_t s; uint8_t tr[52]; uint32_t ax[4];
-        dk::doko_playout_fresh<true>(key, deck, card_lut(), p, s, tr, ax);
+        dk::doko_playout_fresh<true, LocalDeck, true>(key, deck, card_lut(), p, s, tr, ax);
         for (int q = 0; q < 4; ++q) points[i * 4 + q] = p[q];
         steps[i] = s;
         if (trace) std::memcpy(trace + i * 52, tr, 52);
