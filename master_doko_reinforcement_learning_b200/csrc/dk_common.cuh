@@ -141,14 +141,16 @@ DK_HD uint32_t rank_lut6_entry(uint32_t b) {
 //   [0,24) card attributes (card_lut_entry) | [24,31) fdo_thr_lut_word | [32,96) rank_lut6_entry |
 //   [96,288) call thresholds of both teams by (wedding shift, re level, kontra level) (fdo_thr2_lut_word) |
 //   [288,352) 256 bytes: who calls in a segment of an announcement round, by (eligible seats, decision bits) (fdo_seg_lut_byte)
-constexpr uint32_t CARD_LUT_WORDS = 352u;
+constexpr uint32_t CARD_LUT_WORDS = 892u;
 constexpr uint32_t THR_LUT_BASE = 24u;
 constexpr uint32_t RANK_LUT_BASE = 32u;
 constexpr uint32_t THR2_LUT_BASE = 96u;
 constexpr uint32_t SEG_LUT_BASE = 288u;
 // Kernels that can afford 32 KB more shared memory per block (the fresh-game playouts) append the 12-bit rank-select table
 // (4096 x 64 bit, sel12_entry) at word SEL12_LUT_BASE; the others pick cards through the 64-entry table above.
-constexpr uint32_t SEL12_LUT_BASE = 352u;
+//   [352,892) 9 game types x 5 lead classes x 24 cards x 16 bit: strength of a card in a trick + its eyes (pow_lut_entry)
+constexpr uint32_t POW_LUT_BASE = 352u;
+constexpr uint32_t SEL12_LUT_BASE = 892u;
 constexpr uint32_t SEL12_WORDS = 8192u;
 DK_HD uint32_t select_lsb24_lut(uint32_t x, uint32_t k, const uint32_t* __restrict__ lut) {
     uint32_t pos = 0, c;
@@ -239,6 +241,22 @@ DK_HD uint32_t card_lut_entry(uint32_t c) {
     uint32_t tp = rank == 2u ? 4u + so : (rank == 3u ? 8u + so : (c == 7u ? 12u : plain));
     uint32_t eyes = card_eyes_by_rank(rank);
     return eyes | ((1u + eyes) << 4) | ((16u + tp) << 8) | (suit << 13);
+}
+// Strength-in-trick table: row (game type, lead class) x card, lead class = suit of the first card (0..3) when it is a plain card,
+// 4 when it is a trump.  Entry = card_power(card, trump mask of the game type, follow mask of the lead class) | eyes << 8: one 16-bit
+// shared-memory load per card replaces the select chain of card_power_lut (7 ALU instructions per card on the pipe that limits the
+// playout kernels).  pow_row = index of the row's first entry.
+DK_HD uint32_t pow_lut_entry(uint32_t gt, uint32_t cls, uint32_t c) {
+    const uint32_t trump = trump_mask_for_game_type(gt);
+    const uint32_t follow = cls == 4u ? trump : ((0x3Fu << (6u * cls)) & ~trump);
+    const uint32_t suit = card_suit(c);
+    return card_power(c, trump, follow) | (card_eyes_by_rank(c - 6u * suit) << 8);
+}
+DK_HD uint32_t pow_row(uint32_t gt, uint32_t first_card, uint32_t first_suit, uint32_t trump) {
+    return (gt * 5u + (((trump >> first_card) & 1u) ? 4u : first_suit)) * 24u;
+}
+DK_HD uint32_t pow_lookup(const uint32_t* __restrict__ lut, uint32_t row, uint32_t c) {
+    return reinterpret_cast<const uint16_t*>(lut + POW_LUT_BASE)[row + c];
 }
 DK_HD uint32_t follow_mask_lut(uint32_t c, uint32_t entry, uint32_t trump) {
     uint32_t suit_cards = 0x3Fu << (6u * (entry >> 13));

@@ -54,7 +54,7 @@ DK_HD void doko_finish_reservations(DokoLive& g, const uint32_t res_action[4]) {
     }
 }
 
-struct DokoTrickAcc { uint32_t follow, best, bestk, teyes; };
+struct DokoTrickAcc { uint32_t follow, best, bestk, teyes, prow; };   // prow: row of the strength table (game type 0 = the rs-doko trumps)
 
 // Card step of frame seat K (rs-doko/src/action/allowed_actions.rs:153-192, state/state.rs:194-252).
 template <int K, bool SEL12 = false>
@@ -64,14 +64,13 @@ DK_HD uint32_t doko_card_step(DokoLive& g, uint32_t& h, DokoTrickAcc& a, uint32_
     uint32_t idx = mulhi(word, popc(mask));
     uint32_t c = SEL12 ? pick_msb_rank24_tab(mask, idx, reinterpret_cast<const uint64_t*>(lut + SEL12_LUT_BASE)) : pick_msb_rank24_lut(mask, idx, lut);
     uint32_t bit = 1u << c;
-    uint32_t e = lut[c];
     uint32_t dbl = g.dup & bit;
     g.dup ^= dbl;
     h ^= bit ^ dbl;
-    if (K == 0) a.follow = follow_mask_lut(c, e, DOKO_TRUMP_MASK);
-    uint32_t pw = card_power_lut(bit, e, DOKO_TRUMP_MASK, a.follow);
+    if (K == 0) { const uint32_t e = lut[c]; a.follow = follow_mask_lut(c, e, DOKO_TRUMP_MASK); a.prow = pow_row(0u, c, e >> 13, DOKO_TRUMP_MASK); }
+    const uint32_t v = pow_lookup(lut, a.prow, c), pw = v & 255u;
     if (K == 0 || pw > a.best) { a.best = pw; a.bestk = (uint32_t)K; }
-    a.teyes += e & 15u;
+    a.teyes += v >> 8;
     g.steps++;
     return c;
 }
@@ -130,7 +129,7 @@ DK_HD void doko_play_to_end(DokoLive& g, const RngKey& key, const DokoResume* rs
     for (uint32_t t = t0; t < 12u; ++t) {
         U4 blk = rng_block(key, SITE_CARD, t);
         DokoTrickAcc a;
-        a.follow = 0; a.best = 0; a.bestk = 0; a.teyes = 0;
+        a.follow = 0; a.best = 0; a.bestk = 0; a.teyes = 0; a.prow = 0;
         uint32_t k0 = 0;
         bool first = !FRESH && t == t0;
         if (first) { k0 = rs->k0; if (k0 > 0u) a = rs->acc; }

@@ -85,6 +85,11 @@ DK_HD uint32_t lut_word(uint32_t i) {
     if (i < RANK_LUT_BASE) return 0u;
     if (i < THR2_LUT_BASE) return rank_lut6_entry(i - RANK_LUT_BASE);
     if (i < SEG_LUT_BASE) return fdo_thr2_lut_word(i - THR2_LUT_BASE);
+    if (i >= POW_LUT_BASE) {                             // two 16-bit entries per word
+        uint32_t v = 0;
+        for (uint32_t b = 0; b < 2u; ++b) { const uint32_t idx = 2u * (i - POW_LUT_BASE) + b; v |= pow_lut_entry(idx / 120u, (idx / 24u) % 5u, idx % 24u) << (16u * b); }
+        return v;
+    }
     uint32_t v = 0;
     for (uint32_t b = 0; b < 4u; ++b) { const uint32_t idx = 4u * (i - SEG_LUT_BASE) + b; v |= fdo_seg_lut_byte(idx >> 4, idx & 15u) << (8u * b); }
     return v;
@@ -362,7 +367,7 @@ DK_HD void fdo_replay_announcements(FdoLive& g, const RngKey& key, uint32_t star
     g.re_low = re_low; g.ko_low = ko_low; g.steps += ord - g.ann_count; g.ann_count = ord;
 }
 
-struct TrickAcc { uint32_t follow, best, bestk, bestc, teyes, foxm; };
+struct TrickAcc { uint32_t follow, best, bestk, bestc, teyes, foxm, prow; };   // prow: the trick's row of the strength table (pow_row)
 
 // Card step of frame seat K (compile-time) with hand register `h` (action/allowed_actions.rs:97-140, state.rs:274-357).
 template <int K, bool SEL12 = false>
@@ -376,14 +381,13 @@ DK_HD void fdo_card_step(FdoLive& g, uint32_t& h, TrickAcc& a, uint32_t word, bo
     uint32_t idx = mulhi(word, n);
     uint32_t c = SEL12 ? pick_msb_rank24_tab(mask, idx, reinterpret_cast<const uint64_t*>(lut + SEL12_LUT_BASE)) : pick_msb_rank24_lut(mask, idx, lut);
     uint32_t bit = 1u << c;
-    uint32_t e = lut[c];
     uint32_t dbl = g.dup & bit;                           // hand.remove: a doubled card stays in the hand once
     g.dup ^= dbl;
     h ^= bit ^ dbl;
-    if (K == 0) a.follow = follow_mask_lut(c, e, g.trump);
-    uint32_t pw = card_power_lut(bit, e, g.trump, a.follow);
+    if (K == 0) { const uint32_t e = lut[c]; a.follow = follow_mask_lut(c, e, g.trump); a.prow = pow_row(g.gt, c, e >> 13, g.trump); }
+    const uint32_t v = pow_lookup(lut, a.prow, c), pw = v & 255u;
     if (K == 0 || pw > a.best) { a.best = pw; a.bestk = (uint32_t)K; a.bestc = c; }   // strict: first of equals wins
-    a.teyes += e & 15u;
+    a.teyes += v >> 8;
     if (c == CARD_DA) a.foxm |= 1u << K;
     g.steps++;
 }
@@ -466,7 +470,7 @@ DK_HD void fdo_play_to_end(FdoLive& g, const RngKey& key, const FdoResume* rs, c
         starts |= g.base << (2u * t);
         U4 blk = rng_block(key, SITE_CARD, t);
         TrickAcc a;
-        a.follow = 0; a.best = 0; a.bestk = 0; a.bestc = 0; a.teyes = 0; a.foxm = 0;
+        a.follow = 0; a.best = 0; a.bestk = 0; a.bestc = 0; a.teyes = 0; a.foxm = 0; a.prow = 0;
         uint32_t k0 = 0;
         bool first = !FRESH && t == t0;
         if (first) { k0 = rs->k0; if (k0 > 0u) a = rs->acc; }

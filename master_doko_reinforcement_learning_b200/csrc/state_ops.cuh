@@ -351,7 +351,7 @@ DK_HD bool fdo_state_to_live(const dk_state& s, FdoLive& g, FdoResume& rs) {
     g.dup = dup;
     rs.n_res = s.n_reservations;
     rs.t0 = 0; rs.k0 = 0; rs.starts = 0; rs.ann_ci = 0; rs.ann_p = 0; rs.ann_turns = 0xFFFFFFFFu;
-    rs.acc.follow = 0; rs.acc.best = 0; rs.acc.bestk = 0; rs.acc.bestc = 0; rs.acc.teyes = 0; rs.acc.foxm = 0;
+    rs.acc.follow = 0; rs.acc.best = 0; rs.acc.bestk = 0; rs.acc.bestc = 0; rs.acc.teyes = 0; rs.acc.foxm = 0; rs.acc.prow = 0;
 #pragma unroll
     for (uint32_t i = 0; i < 4u; ++i) rs.res_action[i] = i < s.n_reservations ? fdo_action_from_res_code(s.reservations[i]) : 0u;
     uint32_t base;
@@ -397,7 +397,7 @@ DK_HD bool fdo_state_to_live(const dk_state& s, FdoLive& g, FdoResume& rs) {
         for (uint32_t k = 0; k < 3u; ++k) {                                  // partial trick
             if (k >= k0) break;
             uint32_t c = (quad0 >> (8u * k)) & 255u;
-            if (k == 0u) rs.acc.follow = follow_mask(c, g.trump);
+            if (k == 0u) { rs.acc.follow = follow_mask(c, g.trump); rs.acc.prow = pow_row(g.gt, c, card_suit(c), g.trump); }
             uint32_t pw = card_power(c, g.trump, rs.acc.follow);
             if (k == 0u || pw > rs.acc.best) { rs.acc.best = pw; rs.acc.bestk = k; rs.acc.bestc = c; }
             rs.acc.teyes += card_eyes_by_rank(c - 6u * card_suit(c));
@@ -516,7 +516,7 @@ DK_HD bool doko_state_to_live(const dk_state& s, DokoLive& g, DokoResume& rs) {
     for (uint32_t p = 0; p < 4u; ++p) dup |= hand_both24(s.hands[p]);
     g.dup = dup;
     rs.n_res = s.n_reservations; rs.t0 = 0; rs.k0 = 0;
-    rs.acc.follow = 0; rs.acc.best = 0; rs.acc.bestk = 0; rs.acc.teyes = 0;
+    rs.acc.follow = 0; rs.acc.best = 0; rs.acc.bestk = 0; rs.acc.teyes = 0; rs.acc.prow = 0;
 #pragma unroll
     for (uint32_t i = 0; i < 4u; ++i) rs.res_action[i] = i < s.n_reservations ? (s.reservations[i] == 0u ? 25u : 24u) : 0u;
     uint32_t base;
@@ -535,7 +535,7 @@ DK_HD bool doko_state_to_live(const dk_state& s, DokoLive& g, DokoResume& rs) {
         for (uint32_t k = 0; k < 3u; ++k) {
             if (k >= k0) break;
             uint32_t c = (quad0 >> (8u * k)) & 255u;
-            if (k == 0u) rs.acc.follow = follow_mask(c, DOKO_TRUMP_MASK);
+            if (k == 0u) { rs.acc.follow = follow_mask(c, DOKO_TRUMP_MASK); rs.acc.prow = pow_row(0u, c, card_suit(c), DOKO_TRUMP_MASK); }
             uint32_t pw = card_power(c, DOKO_TRUMP_MASK, rs.acc.follow);
             if (k == 0u || pw > rs.acc.best) { rs.acc.best = pw; rs.acc.bestk = k; }
             rs.acc.teyes += card_eyes_by_rank(c - 6u * card_suit(c));
