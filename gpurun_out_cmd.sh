@@ -1,3 +1,4 @@
 set -x
 mkdir -p gpurun_out
-ncu --set full --import-source on --clock-control none -k regex:fdo_playout_fresh -s 1 -c 1 -f -o gpurun_out/prof_k2_v9_2p24 python profiles/profile_playout.py --n 16777216 --launches 2 > gpurun_out/prof_k2_v9.log 2>&1
+for i in 1 2; do timeout 300 python -m pytest tests/test_gpu_selfplay.py tests/test_replay_record.py -m gpu -x -q 2>&1 | tail -1; done
+python profiles/experiments/n1_split.py > gpurun_out/n1_split6.txt 2>&1; tail -1 gpurun_out/n1_split6.txt

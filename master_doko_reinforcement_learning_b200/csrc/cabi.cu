@@ -373,7 +373,8 @@ struct dk_selfplay {
     uint8_t* flags = nullptr;                  // [max_games]
     uint32_t* block_counts = nullptr;          // [n_blocks]
     unsigned long long* block_offsets = nullptr;
-    unsigned long long* counters = nullptr;    // count, dropped, unfinished
+    unsigned long long* counters = nullptr;    // count, dropped, unfinished, rows before the turn (two slots used alternately)
+    int parity = 0;                            // which of counters[3], counters[4] holds the rows recorded before the next turn
     size_t turn_n = 0;
 };
 
@@ -391,8 +392,8 @@ dk_status dk_sp_create(dk_ctx* ctx, size_t max_games, const dk_sp_buffers* bufs,
     if (e == cudaSuccess) e = cudaMalloc(&sp->flags, max_games);
     if (e == cudaSuccess) e = cudaMalloc(&sp->block_counts, nb * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMalloc(&sp->block_offsets, nb * sizeof(unsigned long long));
-    if (e == cudaSuccess) e = cudaMalloc(&sp->counters, 3 * sizeof(unsigned long long));
-    if (e == cudaSuccess) e = cudaMemset(sp->counters, 0, 3 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc(&sp->counters, 5 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemset(sp->counters, 0, 5 * sizeof(unsigned long long));
     if (e != cudaSuccess) { dk_sp_destroy(sp); return fail(ctx, DK_ERR_CUDA, std::string("dk_sp_create: ") + cudaGetErrorString(e)); }
     *out = sp;
     return DK_OK;
@@ -408,7 +409,8 @@ dk_status dk_sp_reset(dk_selfplay* sp, dk_stream stream) {
     if (!sp) return DK_ERR_INVALID_ARGUMENT;
     dk_ctx* ctx = sp->ctx;
     DK_CUDA(ctx, cudaSetDevice(ctx->device));
-    DK_CUDA(ctx, cudaMemsetAsync(sp->counters, 0, 3 * sizeof(unsigned long long), pick_stream(ctx, stream)));
+    DK_CUDA(ctx, cudaMemsetAsync(sp->counters, 0, 5 * sizeof(unsigned long long), pick_stream(ctx, stream)));
+    sp->parity = 0;
     return DK_OK;
 }
 dk_status dk_sp_begin_turn(dk_selfplay* sp, size_t n, const dk_state* states, uint64_t az_epoch, float keep_prob, uint32_t flags, const dk_rng* rng,
@@ -420,16 +422,15 @@ dk_status dk_sp_begin_turn(dk_selfplay* sp, size_t n, const dk_state* states, ui
     DK_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t s = pick_stream(ctx, stream);
     unsigned nb = (unsigned)((n + dk::SP_THREADS - 1) / dk::SP_THREADS);
-    dk::sp_plan_kernel<<<nb, dk::SP_THREADS, 0, s>>>(to_params(rng), (uint64_t)n, states, az_epoch, keep_prob, (flags & DK_SP_SEARCH_FORCED) ? 1u : 0u,
-                                                     sp->allowed, sp->flags, sp->block_counts);
-    dk_status st = check_launch(ctx, "sp_plan_kernel");
-    if (st != DK_OK) return st;
-    dk::sp_scan_kernel<<<1, 1024, 0, s>>>(nb, sp->block_counts, sp->block_offsets, sp->counters, sp->counters + 1, sp->buf.capacity);
-    st = check_launch(ctx, "sp_scan_kernel");
-    if (st != DK_OK) return st;
-    dk::sp_encode_kernel<<<nb, dk::SP_THREADS, 0, s>>>((uint64_t)n, states, sp->allowed, sp->flags, sp->block_offsets, sp->buf, sp->rows,
-                                                       !((uintptr_t)sp->buf.states & 31u));
-    return check_launch(ctx, "sp_encode_kernel");
+    // one pass: plan + deterministic row numbers (decoupled look-back over block_offsets, ticket in block_counts[0]) + encode into the rows
+    DK_CUDA(ctx, cudaMemsetAsync(sp->block_counts, 0, sizeof(uint32_t), s));
+    DK_CUDA(ctx, cudaMemsetAsync(sp->block_offsets, 0, nb * sizeof(unsigned long long), s));
+    dk::sp_begin_kernel<<<nb, dk::SP_THREADS, 0, s>>>(to_params(rng), (uint64_t)n, states, az_epoch, keep_prob, (flags & DK_SP_SEARCH_FORCED) ? 1u : 0u,
+                                                      sp->allowed, sp->flags, sp->rows, sp->buf, sp->block_counts, sp->block_offsets,
+                                                      sp->counters + 3 + sp->parity, sp->counters + 3 + (1 - sp->parity), sp->counters,
+                                                      sp->counters + 1, !((uintptr_t)sp->buf.states & 31u));
+    sp->parity = 1 - sp->parity;
+    return check_launch(ctx, "sp_begin_kernel");
 }
 dk_status dk_sp_turn_view(dk_selfplay* sp, const uint64_t** allowed, const uint8_t** flags, const int64_t** rows) {
     if (!sp) return DK_ERR_INVALID_ARGUMENT;
@@ -471,7 +472,7 @@ dk_status dk_sp_counts(dk_selfplay* sp, uint64_t* rows, uint64_t* dropped, uint6
     if (!sp) return DK_ERR_INVALID_ARGUMENT;
     dk_ctx* ctx = sp->ctx;
     DK_CUDA(ctx, cudaSetDevice(ctx->device));
-    unsigned long long h[3];
+    unsigned long long h[3];   // count, dropped, unfinished
     cudaStream_t s = pick_stream(ctx, stream);
     DK_CUDA(ctx, cudaMemcpyAsync(h, sp->counters, sizeof h, cudaMemcpyDeviceToHost, s));
     DK_CUDA(ctx, cudaStreamSynchronize(s));

@@ -1,12 +1,12 @@
 // selfplay.cuh — AlphaZero self-play driver around the env-step/encode hot path, lock-step over a batch of games.
 //   self_play, ValueTarget::Default (rs-doko-alpha-zero/src/alpha_zero/train/self_play.rs:19-207)
 //   FdoAzEnvState (rs-doko-alpha-zero/src/env/envs/full_doko/full_doko.rs:43-172)
-// One TURN of all games = three small kernels + the caller's search in between:
-//   sp_plan    per game: terminal? epoch-filtered allowed set, forced move?, keep-experience draw → per-block row counts
-//   sp_scan    exclusive scan of the block counts behind the rows already recorded → deterministic row numbers
-//              (turn-major, game order inside a turn: the order in which a sequential driver over the games would push them)
-//   sp_encode  encode_state_pi of every kept game STRAIGHT INTO its row of the experience buffer (the network batcher reads the
-//              rows where they lie: no Vec<i64> copy, no host round trip), player / game / one-hot policy of forced moves
+// One TURN of all games = two kernels + the caller's search in between:
+//   sp_begin   one pass over the states.  Per game: terminal? epoch-filtered allowed set, forced move?, keep-experience draw; a
+//              decoupled look-back scan of the per-block row counts behind the rows already recorded gives deterministic row numbers
+//              (turn-major, game order inside a turn: the order in which a sequential driver over the games would push them);
+//              encode_state_pi of every kept game goes STRAIGHT INTO its row of the experience buffer (the network batcher reads the
+//              rows where they lie: no Vec<i64> copy, no host round trip), with player / game / one-hot policy of forced moves
 //   [search: caller fills policy[n][39] and action[n] for the games that are not forced]
 //   sp_apply   policy target → row, take_action_by_action_index(action, false, epoch)
 // and at the end sp_finalize rotates the final rewards into every row's value target (RotArr::new_from_0, rot_arr.rs:31-38).

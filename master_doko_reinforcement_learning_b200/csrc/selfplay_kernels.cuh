@@ -17,17 +17,49 @@ struct SpBuffers {
 
 constexpr int SP_THREADS = ENC_THREADS;   // plan / encode / apply use the same game → block mapping
 
+// Begin of a turn in ONE pass over the states (plan + row numbering + encode): every block
+//   1. takes the next block number from a ticket (so numbers follow the order in which blocks start — needed by the look-back),
+//   2. decides per game: terminal? epoch-filtered allowed set, forced move?, keep-experience draw,
+//   3. publishes its number of kept rows and encodes them into shared memory (staged by rank),
+//   4. obtains the number of rows kept by all earlier blocks with a decoupled look-back over the published (aggregate | inclusive)
+//      words — sums of integers, so the row numbers are the same deterministic turn-major / game-order numbers a sequential driver
+//      would produce, whatever the timing —
+//   5. writes its rows straight into the experience buffer as sector-aligned streams.
+// status[b]: bits 62-63 = 0 nothing yet, 1 the block's own count, 2 count of all blocks up to and including b (plus the rows recorded
+// before this turn); zeroed together with the ticket before the launch.
+constexpr unsigned long long SP_ST_AGG = 1ull << 62, SP_ST_INCL = 2ull << 62, SP_ST_VALUE = (1ull << 62) - 1ull;
+__device__ __forceinline__ unsigned long long sp_ld_status(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sp_st_status(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 __global__ void __launch_bounds__(SP_THREADS)
-sp_plan_kernel(RngParams rp, uint64_t n, const dk_state* __restrict__ states, uint64_t az_epoch, float keep_prob, uint32_t search_forced,
-               uint64_t* __restrict__ allowed_out, uint8_t* __restrict__ flags_out, uint32_t* __restrict__ block_counts) {
-    __shared__ uint4 stage[SP_THREADS * 8];
-    const uint64_t first = (uint64_t)blockIdx.x * SP_THREADS, i = first + threadIdx.x;
+sp_begin_kernel(RngParams rp, uint64_t n, const dk_state* __restrict__ states, uint64_t az_epoch, float keep_prob, uint32_t search_forced,
+                uint64_t* __restrict__ allowed_out, uint8_t* __restrict__ flags_out, long long* __restrict__ row_out, SpBuffers buf,
+                unsigned int* __restrict__ ticket, unsigned long long* __restrict__ status, const unsigned long long* __restrict__ rows_before,
+                unsigned long long* __restrict__ rows_after, unsigned long long* __restrict__ count, unsigned long long* __restrict__ dropped,
+                bool dense_ok) {
+    __shared__ __align__(16) uint32_t tok[SP_THREADS * PI_ROW];           // first the staged state records (16 KB), then the token rows
+    __shared__ uint32_t warp_count[SP_THREADS / 32];
+    __shared__ uint32_t s_bid;
+    __shared__ unsigned long long s_row0;
+    __shared__ uint8_t forced_act[SP_THREADS];                            // by rank: the forced move of the row, 0xFF if the row is searched
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_bid = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const uint32_t bid = s_bid;
+    const uint64_t first = (uint64_t)bid * SP_THREADS, i = first + threadIdx.x;
+    uint4* stage = reinterpret_cast<uint4*>(tok);
     StateStage<SP_THREADS>::load(states, first, n, stage);
+    alignas(16) dk_state s;
+    if (i < n) StateStage<SP_THREADS>::get(stage, s);
+    __syncthreads();                                                       // the stage is dead: tok may be overwritten from here on
     uint32_t flags = SP_DONE;
     uint64_t allowed = 0;
     if (i < n) {
-        alignas(16) dk_state s;
-        StateStage<SP_THREADS>::get(stage, s);
         if (st_phase(s) != DK_PHASE_FINISHED) {
             allowed = sp_az_allowed(s, az_epoch);
             flags = 0;
@@ -39,91 +71,71 @@ sp_plan_kernel(RngParams rp, uint64_t n, const dk_state* __restrict__ states, ui
             } else flags = SP_KEPT;
         }
         allowed_out[i] = allowed;
-        flags_out[i] = (uint8_t)flags;
     }
-    int c = __syncthreads_count((flags & SP_KEPT) != 0u);
-    if (threadIdx.x == 0) block_counts[blockIdx.x] = (uint32_t)c;
-}
-
-// Single block: block_offsets[b] = rows already recorded + sum of counts of the blocks before b; *count advances (saturating at the
-// capacity — rows beyond it are dropped by sp_encode and counted in *dropped).
-__global__ void __launch_bounds__(1024)
-sp_scan_kernel(uint32_t n_blocks, const uint32_t* __restrict__ block_counts, unsigned long long* __restrict__ block_offsets,
-               unsigned long long* __restrict__ count, unsigned long long* __restrict__ dropped, unsigned long long capacity) {
-    __shared__ unsigned long long warp_sum[32];
-    __shared__ unsigned long long carry;
-    if (threadIdx.x == 0) carry = *count;
-    __syncthreads();
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    for (uint32_t base = 0; base < n_blocks; base += 1024u) {
-        uint32_t b = base + threadIdx.x;
-        unsigned long long v = b < n_blocks ? block_counts[b] : 0ull, x = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, x, o); if ((int)lane >= o) x += y; }
-        if (lane == 31u) warp_sum[warp] = x;
-        __syncthreads();
-        if (warp == 0) {
-            unsigned long long w = warp_sum[lane], z = w;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, z, o); if ((int)lane >= o) z += y; }
-            warp_sum[lane] = z - w;                                  // exclusive prefix of the warp totals
-        }
-        __syncthreads();
-        unsigned long long excl = carry + warp_sum[warp] + (x - v);
-        if (b < n_blocks) block_offsets[b] = excl;
-        __syncthreads();
-        if (threadIdx.x == 1023u) carry = excl + v;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-        unsigned long long total = carry;                              // rows before this turn (<= capacity) + rows kept in it
-        if (total > capacity) { *dropped += total - capacity; total = capacity; }
-        *count = total;
-    }
-}
-
-__global__ void __launch_bounds__(SP_THREADS)
-sp_encode_kernel(uint64_t n, const dk_state* __restrict__ states, const uint64_t* __restrict__ allowed, uint8_t* __restrict__ flags_io,
-                 const unsigned long long* __restrict__ block_offsets, SpBuffers buf, long long* __restrict__ row_out, bool dense_ok) {
-    __shared__ uint32_t tok[SP_THREADS * PI_ROW];
-    __shared__ uint32_t warp_count[SP_THREADS / 32];
-    const uint64_t first = (uint64_t)blockIdx.x * SP_THREADS;
-    const uint64_t i = first + threadIdx.x;
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    uint32_t flags = i < n ? flags_io[i] : SP_DONE;
     const bool kept = (flags & SP_KEPT) != 0u;
     const unsigned ballot = __ballot_sync(0xFFFFFFFFu, kept);
     if (lane == 0) warp_count[warp] = popc(ballot);
     __syncthreads();
-    uint32_t before = popc(ballot & ((1u << lane) - 1u));
-    for (uint32_t w = 0; w < warp; ++w) before += warp_count[w];
-    long long row = -1;
+    uint32_t before = popc(ballot & ((1u << lane) - 1u)), cnt = 0;
+#pragma unroll
+    for (uint32_t w = 0; w < SP_THREADS / 32; ++w) { before += w < warp ? warp_count[w] : 0u; cnt += warp_count[w]; }
+    if (threadIdx.x == 0) sp_st_status(status + bid, SP_ST_AGG | cnt);
     if (kept) {
-        unsigned long long r = block_offsets[blockIdx.x] + before;
-        if (r < buf.capacity) row = (long long)r;
-        else { flags = (flags & ~SP_KEPT) | SP_DROPPED; flags_io[i] = (uint8_t)flags; }
-    }
-    if (i < n && row_out) row_out[i] = row;
-    if (row >= 0) {
-        alignas(16) dk_state s;
-        load_state(states + i, s);
-        SmemSlotOut o{tok + before * PI_ROW};                         // staged by RANK: the block's kept rows are consecutive in smem and in the buffer
+        SmemSlotOut o{tok + before * PI_ROW};                             // staged by RANK: the block's kept rows are consecutive in smem and in the buffer
         fdo_encode_pi(s, o);
-        buf.player[row] = (uint8_t)(st_phase(s) == DK_PHASE_FINISHED ? 0u : st_cur(s));
-        buf.game[row] = (uint32_t)i;
-        if (flags & SP_FORCED) {                                      // one-hot policy target of a forced move (self_play.rs:85-86)
-            const uint32_t a = ffs0ll(allowed[i]);
-            float* p = buf.policy + (size_t)row * N_ACTIONS;
-            for (uint32_t k = 0; k < N_ACTIONS; ++k) p[k] = k == a ? 1.0f : 0.0f;
+        forced_act[before] = (uint8_t)((flags & SP_FORCED) ? ffs0ll(allowed) : 0xFFu);
+    }
+    if (warp == 0) {                                                       // look-back: 32 predecessors per step, nearest first
+        unsigned long long excl = 0;
+        long long base = (long long)bid - 1;
+        for (;;) {
+            const long long idx = base - (long long)lane;
+            unsigned long long st;
+            if (idx >= 0) { do { st = sp_ld_status(status + idx); } while ((st >> 62) == 0ull); }
+            else st = SP_ST_INCL | (idx == -1 ? *rows_before : 0ull);     // virtual block -1: the rows recorded before this turn (a slot
+                                                                          //   no block of this launch writes: the last block may be done already)
+            const unsigned incl = __ballot_sync(0xFFFFFFFFu, (st >> 62) == 2ull);
+            const uint32_t stop = incl ? (uint32_t)(__ffs((int)incl) - 1) : 31u;      // lanes 0..stop contribute
+            unsigned long long v = lane <= stop ? (st & SP_ST_VALUE) : 0ull;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+            excl += v;
+            if (incl) break;
+            base -= 32;
+        }
+        if (lane == 0) {
+            sp_st_status(status + bid, SP_ST_INCL | (excl + cnt));
+            s_row0 = excl;
+            if (first + SP_THREADS >= n) {                                 // the last block closes the turn: rows before + rows kept in it
+                unsigned long long total = excl + cnt;
+                if (total > buf.capacity) { *dropped += total - buf.capacity; total = buf.capacity; }
+                *count = total;
+                *rows_after = total;
+            }
         }
     }
     __syncthreads();
-    // rows block_offsets[b] .. + kept-in-block - 1, cut at the capacity
-    uint32_t cnt = 0;
-    for (uint32_t w = 0; w < SP_THREADS / 32; ++w) cnt += warp_count[w];
-    const unsigned long long row0 = block_offsets[blockIdx.x];
+    const unsigned long long row0 = s_row0;
+    long long row = -1;
+    if (kept) {
+        const unsigned long long r = row0 + before;
+        if (r < buf.capacity) row = (long long)r;
+        else flags = (flags & ~SP_KEPT) | SP_DROPPED;
+    }
+    if (i < n) { flags_out[i] = (uint8_t)flags; if (row_out) row_out[i] = row; }
+    if (row >= 0) {
+        buf.player[row] = (uint8_t)(st_phase(s) == DK_PHASE_FINISHED ? 0u : st_cur(s));
+        buf.game[row] = (uint32_t)i;
+    }
     if (row0 >= buf.capacity) return;
     cnt = (uint32_t)min((unsigned long long)cnt, buf.capacity - row0);
+    // one-hot policy targets of the forced moves (self_play.rs:85-86): the block's rows are consecutive, so consecutive threads write
+    // consecutive floats (the rows of searched games are filled by sp_apply)
+    float* pol = buf.policy + (size_t)row0 * N_ACTIONS;
+    for (uint32_t e = threadIdx.x; e < cnt * N_ACTIONS; e += SP_THREADS) {
+        const uint32_t r = e / N_ACTIONS, a = e - r * N_ACTIONS, fa = forced_act[r];
+        if (fa != 0xFFu) pol[e] = a == fa ? 1.0f : 0.0f;
+    }
     if (dense_ok) write_rows_pi_dense_at(tok, row0, cnt, buf.states);
     else for (uint32_t r = warp; r < cnt; r += SP_THREADS / 32) write_row_pi(tok + r * PI_ROW, buf.states + (row0 + r) * 311u, lane);
 }
