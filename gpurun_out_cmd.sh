@@ -1,4 +1,4 @@
 set -x
 mkdir -p gpurun_out
-for i in 1 2; do timeout 300 python -m pytest tests/test_gpu_selfplay.py tests/test_replay_record.py -m gpu -x -q 2>&1 | tail -1; done
-python profiles/experiments/n1_split.py > gpurun_out/n1_split6.txt 2>&1; tail -1 gpurun_out/n1_split6.txt
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; tail -2 gpurun_out/pytest_gpu.log
+python profiles/bench_kernels.py > gpurun_out/kernels_v22.json 2> gpurun_out/kernels_v22.err

@@ -294,8 +294,8 @@ dk_status dk_leaf_rollouts(dk_ctx* ctx, size_t n_leaves, size_t rollouts_per_lea
     if (n_leaves == 0) return DK_OK;
     if (rollouts_per_leaf > 0x1000000ull || n_leaves > 0x7FFFFFFFull) return DK_ERR_INVALID_ARGUMENT;   // int32 block sums: |points| < 128
     DK_CUDA(ctx, cudaSetDevice(ctx->device));
-    dk::fdo_leaf_rollouts_kernel<<<(unsigned)n_leaves, dk::MATCH_THREADS, 0, pick_stream(ctx, stream)>>>(to_params(rng), (uint64_t)n_leaves, (uint32_t)rollouts_per_leaf,
-                                                                                                      determinize, states, (long long*)point_sum_out);
+    if (determinize) dk::fdo_leaf_rollouts_kernel<true><<<(unsigned)n_leaves, dk::MATCH_THREADS, 0, pick_stream(ctx, stream)>>>(to_params(rng), (uint64_t)n_leaves, (uint32_t)rollouts_per_leaf, states, (long long*)point_sum_out);
+    else dk::fdo_leaf_rollouts_kernel<false><<<(unsigned)n_leaves, dk::MATCH_THREADS, 0, pick_stream(ctx, stream)>>>(to_params(rng), (uint64_t)n_leaves, (uint32_t)rollouts_per_leaf, states, (long long*)point_sum_out);
     return check_launch(ctx, "fdo_leaf_rollouts_kernel");
 }
 

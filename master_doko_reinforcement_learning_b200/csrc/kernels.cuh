@@ -557,13 +557,22 @@ doko_assign_kernel(RngParams rp, uint64_t n_info, uint32_t samples, const dk_sta
     }
 }
 
-// K4: leaf-parallel rollouts, fused determinize → rollout → block reduction.  One block per leaf; rollout r uses the Philox
+// K4: leaf-parallel rollouts, [determinize →] rollout → block reduction.  One block per leaf; rollout r uses the Philox
 // unit (leaf id, r).  point_sum[leaf][seat] = exact integer sum of player_points over the rollouts (dead-end samples add 0).
-__global__ void __launch_bounds__(MATCH_THREADS)
-fdo_leaf_rollouts_kernel(RngParams rp, uint64_t n_leaves, uint32_t rollouts, int determinize, const dk_state* __restrict__ states,
-                         long long* __restrict__ point_sum) {
+// DET = false (rollouts from leaves that are determinized already, BASELINE config 4): the bridge from the stored record to the
+// register-resident playout form is the same for every rollout of the leaf, so it is built once per block in shared memory and the
+// kernel fits 64 registers (8 blocks per SM: 1024 leaves are resident at once instead of running in 1.7 waves).
+template <bool DET>
+#ifndef DK_LEAF_BLOCKS
+#define DK_LEAF_BLOCKS 7
+#endif
+__global__ void __launch_bounds__(MATCH_THREADS, DET ? 4 : DK_LEAF_BLOCKS)
+fdo_leaf_rollouts_kernel(RngParams rp, uint64_t n_leaves, uint32_t rollouts, const dk_state* __restrict__ states, long long* __restrict__ point_sum) {
     __shared__ MatchPrep prep;
     __shared__ __align__(16) dk_state leaf;
+    __shared__ FdoLive live0;
+    __shared__ FdoResume resume0;
+    __shared__ int live_ok;
     __shared__ int red[4];
     __shared__ uint32_t lut[CARD_LUT_WORDS];
     fill_card_lut(lut);
@@ -572,26 +581,34 @@ fdo_leaf_rollouts_kernel(RngParams rp, uint64_t n_leaves, uint32_t rollouts, int
     if (threadIdx.x < 8) reinterpret_cast<uint4*>(&leaf)[threadIdx.x] = __ldg(reinterpret_cast<const uint4*>(states + i) + threadIdx.x);
     if (threadIdx.x < 4) red[threadIdx.x] = 0;
     __syncthreads();
-    if (determinize && threadIdx.x == 0) fdo_match_prepare(leaf, prep);
+    if (threadIdx.x == 0) {
+        if (DET) fdo_match_prepare(leaf, prep);
+        else { FdoLive g; FdoResume rs; live_ok = fdo_state_to_live<true>(leaf, g, rs) ? 1 : 0; live0 = g; resume0 = rs; }
+    }
     __syncthreads();
     int acc[4] = {0, 0, 0, 0};
     for (uint32_t r = threadIdx.x; r < rollouts; r += MATCH_THREADS) {
         RngKey key = make_key(rp, i, rp.first_sub + r, true);
-        alignas(16) dk_state s = leaf;
-        uint32_t status = 0;
-        if (determinize && prep.valid) {
-            uint64_t h[4];
-            uint8_t res[4];
-            status = fdo_match_sample(prep, key, h, res);
-            fdo_state_with_hands_and_reservations(s, h, res);
-        }
-        if (status == 0u) {
+        int32_t p[4];
+        if (DET) {
+            alignas(16) dk_state s = leaf;
+            uint32_t status = 0;
+            if (prep.valid) {
+                uint64_t h[4];
+                uint8_t res[4];
+                status = fdo_match_sample(prep, key, h, res);
+                fdo_state_with_hands_and_reservations(s, h, res);
+            }
+            if (status != 0u) continue;
             FdoLive g; FdoResume rs;
-            int32_t p[4];
             if (fdo_state_to_live(s, g, rs)) { fdo_play_to_end<false, false>(g, key, &rs, lut); fdo_final_points(g, p); }
             else { p[0] = s.points[0]; p[1] = s.points[1]; p[2] = s.points[2]; p[3] = s.points[3]; }
-            acc[0] += p[0]; acc[1] += p[1]; acc[2] += p[2]; acc[3] += p[3];
-        }
+        } else if (live_ok) {
+            FdoLive g = live0;
+            fdo_play_to_end<false, false>(g, key, &resume0, lut);
+            fdo_final_points(g, p);
+        } else { p[0] = leaf.points[0]; p[1] = leaf.points[1]; p[2] = leaf.points[2]; p[3] = leaf.points[3]; }
+        acc[0] += p[0]; acc[1] += p[1]; acc[2] += p[2]; acc[3] += p[3];
     }
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
