@@ -273,6 +273,14 @@ def run_cuda(args):
             "peak_source": f"{info['sm_count']} SMs x 4 schedulers x {sm_mhz:.0f} MHz (median SM clock sampled during the timed region)",
             "warp_inst_per_game_step": wi_per_step,
             "counters_source": counters.get("source", "profiles/fdo_playout_counters.json missing: run the ncu pass"),
+            # the pipe that actually limits the kernel: ALU-pipe instructions (logic / select / compare / shift) issue at one warp
+            # instruction per TWO cycles per scheduler on sm_100 (measured: profiles/r01_int_rates.json).  ncu's own ALU-pipe
+            # utilisation of the captured launch, scaled by (capture duration / duration measured here) for the same number of games.
+            "alu_pipe": ({"frac": counters["alu_pipe_pct_of_peak"] / 100.0 * (counters["capture_kernel_ms"] / 1e3 / avg_kernel_s)
+                                  * (games_per_launch / counters["capture_games"]),
+                          "ncu_pct_at_capture": counters["alu_pipe_pct_of_peak"], "capture_kernel_ms": counters["capture_kernel_ms"],
+                          "peak_source": "sm__inst_executed_pipe_alu.sum.pct_of_peak_sustained_active; pipe rate 64 lanes/clk/SM (profiles/r01_int_rates.json)"}
+                         if counters.get("alu_pipe_pct_of_peak") and counters.get("capture_kernel_ms") else None),
             "hbm": {"bound": "hbm", "achieved": alg_bytes / avg_kernel_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
                     "frac": alg_bytes / avg_kernel_s / 1e9 / hbm_peak, "algorithmic_bytes_per_launch": alg_bytes,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s"},
