@@ -1,7 +1,9 @@
 set -x
 mkdir -p gpurun_out
-python profiles/sanitize_smoke.py > gpurun_out/sanitize_plain.log 2>&1; tail -3 gpurun_out/sanitize_plain.log
-./profiles/experiments/oracle_inst_count oracle/liboracle.so > gpurun_out/oracle_inst_count.json 2>&1; cat gpurun_out/oracle_inst_count.json
-cat /proc/sys/kernel/perf_event_paranoid
-python bench.py --steps 5 --warmup 3 > gpurun_out/bench_v9_1gpu.json 2> gpurun_out/bench_v9_1gpu.err; tail -1 gpurun_out/bench_v9_1gpu.json | cut -c1-600
-python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_v9_reference_arm.json 2>&1; tail -1 gpurun_out/bench_v9_reference_arm.json | cut -c1-300
+for rep in 1 2 3; do for l in 64_16_0 128_8_1; do DOKO_CUDA_LIB=$PWD/profiles/experiments/libs/libdoko_uct_$l.so python profiles/experiments/uct_cfg.py; done; done > gpurun_out/uct_cfg2.txt 2>&1; cat gpurun_out/uct_cfg2.txt | python -c "
+import sys, json
+for l in sys.stdin:
+    try: d = json.loads(l)
+    except Exception: print(l.strip()[:200]); continue
+    print(d['lib'], [round(d[k]['Miter_per_s']) for k in d if k != 'lib'])
+"

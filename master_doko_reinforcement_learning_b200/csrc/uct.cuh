@@ -190,44 +190,60 @@ DK_HD uint32_t uct_find_best_child(const UctNode* __restrict__ pool, uint32_t se
 // One iteration of monte_carlo_tree_search (mcts.rs:176-199): select → expand_single → random_rollout → backpropagate.
 // key = the iteration's Philox unit.  Returns 1 when a node would need more than UCT_MAX_CHILDREN children (cannot happen for
 // states reachable by the rules; reported instead of overflowing).
+// `sync()` is called between the four phases by EVERY thread (active or not): the kernel passes a block barrier so that all warps of
+// a block run the same phase — and hence the same stretch of this 100+ KB of code — at the same time; the host simulator passes a no-op.
+struct UctNoSync { DK_HD void operator()() const {} };
+template <class Sync = UctNoSync>
 DK_HD uint32_t uct_iteration(UctNode* __restrict__ pool, uint32_t& n_nodes, const RngKey& key, double c, const double* __restrict__ ln_table,
-                             const uint32_t* __restrict__ lut) {
-    uint32_t node = 0;
-    for (;;) {                                                                   // select_promising_node (:45-63)
-        const UctNode& n = pool[node];
-        if (uct_n_children(n) == 0u || (n.info & UCT_ACTION_MASK) != 0ull) break;
-        node = uct_find_best_child(pool, node, c, ln_table[n.visits]);
+                             const uint32_t* __restrict__ lut, bool active = true, Sync sync = Sync()) {
+    uint32_t node = 0, err = 0;
+    if (active) {
+        for (;;) {                                                               // select_promising_node (:45-63)
+            const UctNode& n = pool[node];
+            if (uct_n_children(n) == 0u || (n.info & UCT_ACTION_MASK) != 0ull) break;
+            node = uct_find_best_child(pool, node, c, ln_table[n.visits]);
+        }
     }
+    sync();
     uint32_t explore = node;
-    const uint64_t unexpanded = pool[node].info & UCT_ACTION_MASK;
-    alignas(16) dk_state s = pool[node].state;
-    if (unexpanded != 0ull) {                                                    // expand_single (:65-104)
-        const uint32_t nch = uct_n_children(pool[node]);
-        if (nch >= UCT_MAX_CHILDREN) return 1u;
-        U4 blk = rng_block(key, SITE_EXPAND, 0);
-        const uint32_t a = pick_msb_rank64(unexpanded, mulhi(blk.x, popcll(unexpanded)));
-        fdo_state_apply<true>(s, a);                                             // by_action (record in local memory)
-        explore = n_nodes++;
-        uct_init_node(pool[explore], s, node, a, false);
-        pool[node].child[nch] = explore;
-        pool[node].info = (pool[node].info & ~(1ull << a) & ~(15ull << 56)) | ((uint64_t)(nch + 1u) << 56);
+    alignas(16) dk_state s;
+    if (active) {
+        const uint64_t unexpanded = pool[node].info & UCT_ACTION_MASK;
+        s = pool[node].state;
+        if (unexpanded != 0ull) {                                                // expand_single (:65-104)
+            const uint32_t nch = uct_n_children(pool[node]);
+            if (nch >= UCT_MAX_CHILDREN) err = 1u;
+            else {
+                U4 blk = rng_block(key, SITE_EXPAND, 0);
+                const uint32_t a = pick_msb_rank64(unexpanded, mulhi(blk.x, popcll(unexpanded)));
+                fdo_state_apply<true>(s, a);                                     // by_action (record in local memory)
+                explore = n_nodes++;
+                uct_init_node(pool[explore], s, node, a, false);
+                pool[node].child[nch] = explore;
+                pool[node].info = (pool[node].info & ~(1ull << a) & ~(15ull << 56)) | ((uint64_t)(nch + 1u) << 56);
+            }
+        }
     }
-    int32_t p[4];                                                                // random_rollout (env_state_full_doko.rs:198-220) from `s`
-    {
+    sync();
+    int32_t p[4] = {0, 0, 0, 0};                                                 // random_rollout (env_state_full_doko.rs:198-220) from `s`
+    if (active && !err) {
         FdoLive g; FdoResume rs;
         if (fdo_state_to_live<true>(s, g, rs)) { fdo_play_to_end<false, false>(g, key, &rs, lut); fdo_final_points(g, p); }
         else { p[0] = s.points[0]; p[1] = s.points[1]; p[2] = s.points[2]; p[3] = s.points[3]; }
     }
-    uint32_t temp = explore;                                                     // backpropagate (:138-158)
-    for (;;) {
-        const uint32_t parent = pool[temp].parent;
-        pool[temp].visits += 1u;
-        if (parent == UCT_NONE) break;
-        const uint32_t cp = uct_cur(pool[parent]);
-        pool[temp].win += (long long)((cp & 2u) ? ((cp & 1u) ? p[3] : p[2]) : ((cp & 1u) ? p[1] : p[0]));
-        temp = parent;
+    sync();
+    if (active && !err) {
+        uint32_t temp = explore;                                                 // backpropagate (:138-158)
+        for (;;) {
+            const uint32_t parent = pool[temp].parent;
+            pool[temp].visits += 1u;
+            if (parent == UCT_NONE) break;
+            const uint32_t cp = uct_cur(pool[parent]);
+            pool[temp].win += (long long)((cp & 2u) ? ((cp & 1u) ? p[3] : p[2]) : ((cp & 1u) ? p[1] : p[0]));
+            temp = parent;
+        }
     }
-    return 0u;
+    return err;
 }
 
 // Moves of the root (mcts.rs:220-229) as mcts_policy.rs:96-118 consumes them: visits / values by action index and the move with
