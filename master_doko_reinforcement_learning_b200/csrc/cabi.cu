@@ -486,10 +486,12 @@ dk_status dk_pack_replay_records(dk_ctx* ctx, size_t n_rows, const int64_t* stat
     if (!ctx || !states || !value || !policy || !out || ((uintptr_t)out & 3u)) return DK_ERR_INVALID_ARGUMENT;
     if (n_rows == 0) return DK_OK;
     DK_CUDA(ctx, cudaSetDevice(ctx->device));
-    unsigned long long total = (unsigned long long)n_rows * dk::REPLAY_WORDS;
-    unsigned long long want = (total + 255ull) / 256ull, cap = (unsigned long long)ctx->sm_count * 32ull;
-    unsigned grid = (unsigned)(want < cap ? want : cap);
-    dk::pack_replay_records_kernel<<<grid, 256, 0, pick_stream(ctx, stream)>>>((unsigned long long)n_rows, (const long long*)states, value, policy, (uint32_t*)out);
+    const bool aligned16 = ((uintptr_t)out & 15u) == 0u;
+    unsigned long long want = aligned16 ? (n_rows + 3ull) / 4ull : ((unsigned long long)n_rows * dk::REPLAY_WORDS + dk::REPLAY_THREADS - 1) / dk::REPLAY_THREADS;
+    unsigned long long cap = (unsigned long long)ctx->sm_count * 32ull;
+    unsigned grid = (unsigned)(want < cap ? (want ? want : 1ull) : cap);
+    dk::pack_replay_records_kernel<<<grid, dk::REPLAY_THREADS, 0, pick_stream(ctx, stream)>>>((unsigned long long)n_rows, (const long long*)states, value, policy,
+                                                                                           (uint32_t*)out, aligned16);
     return check_launch(ctx, "pack_replay_records_kernel");
 }
 

@@ -238,26 +238,58 @@ sp_finalize_kernel(const unsigned long long* __restrict__ count, const dk_state*
 
 // The reference's on-disk experience record (DBRecord through bincode 1.3.3, experience_replay_buffer3.rs:11-20,94-121):
 //   u64 311 | 311 x i64 | u64 4 | 4 x f32 | u64 39 | 39 x f32 = 2684 bytes = 671 little-endian 32-bit words, records back to back.
-// Pure byte shuffling: one thread per output word, consecutive threads write consecutive words.
+// Pure byte shuffling.  Four consecutive records are exactly 671 x 16 bytes, so a block writes groups of four records as 671 aligned
+// 16-byte stores (one per thread and pass; 224 threads = three nearly full passes); the rows left over at the end go word by word.
 constexpr uint32_t REPLAY_WORDS = 671u;
-__global__ void __launch_bounds__(256)
+constexpr int REPLAY_THREADS = 224;
+__device__ __forceinline__ uint32_t replay_word(unsigned long long r, uint32_t w, const long long* __restrict__ states, const float* __restrict__ value,
+                                                const float* __restrict__ policy) {
+    if (w < 2u) return w == 0u ? 311u : 0u;
+    if (w < 624u) {
+        const unsigned long long x = (unsigned long long)__ldg(states + r * 311u + ((w - 2u) >> 1));
+        return (w & 1u) ? (uint32_t)(x >> 32) : (uint32_t)x;             // w - 2 even ⇔ w even ⇒ low half
+    }
+    if (w < 626u) return w == 624u ? 4u : 0u;
+    if (w < 630u) return __float_as_uint(__ldg(value + r * 4u + (w - 626u)));
+    if (w < 632u) return w == 630u ? 39u : 0u;
+    return __float_as_uint(__ldg(policy + r * 39u + (w - 632u)));
+}
+__global__ void __launch_bounds__(REPLAY_THREADS)
 pack_replay_records_kernel(unsigned long long n_rows, const long long* __restrict__ states, const float* __restrict__ value,
-                           const float* __restrict__ policy, uint32_t* __restrict__ out) {
-    const unsigned long long total = n_rows * REPLAY_WORDS;
-    for (unsigned long long g = (unsigned long long)blockIdx.x * 256u + threadIdx.x; g < total; g += (unsigned long long)gridDim.x * 256u) {
-        const unsigned long long r = g / REPLAY_WORDS;
-        const uint32_t w = (uint32_t)(g - r * REPLAY_WORDS);
-        uint32_t v;
-        if (w < 2u) v = w == 0u ? 311u : 0u;
-        else if (w < 624u) {
-            const uint32_t e = (w - 2u) >> 1;
-            const unsigned long long x = (unsigned long long)__ldg(states + r * 311u + e);
-            v = (w & 1u) ? (uint32_t)(x >> 32) : (uint32_t)x;           // w - 2 even ⇔ w even ⇒ low half
-        } else if (w < 626u) v = w == 624u ? 4u : 0u;
-        else if (w < 630u) v = __float_as_uint(__ldg(value + r * 4u + (w - 626u)));
-        else if (w < 632u) v = w == 630u ? 39u : 0u;
-        else v = __float_as_uint(__ldg(policy + r * 39u + (w - 632u)));
-        out[g] = v;
+                           const float* __restrict__ policy, uint32_t* __restrict__ out, bool aligned16) {
+    const unsigned long long n_groups = aligned16 ? n_rows / 4ull : 0ull;
+    for (unsigned long long g = blockIdx.x; g < n_groups; g += gridDim.x) {
+        uint4* dst = reinterpret_cast<uint4*>(out + g * 4ull * REPLAY_WORDS);
+        for (uint32_t e = threadIdx.x; e < REPLAY_WORDS; e += REPLAY_THREADS) {
+            const uint32_t q0 = 4u * e, r0 = q0 / REPLAY_WORDS, w0 = q0 - r0 * REPLAY_WORDS;
+            uint4 o;
+            if (w0 >= 2u && w0 + 3u < 624u) {
+                // all four words are observation halves of one record (93 % of the stores): 16 bytes copied from 8-byte aligned source
+                const long long* src = states + (g * 4ull + r0) * 311u + ((w0 - 2u) >> 1);
+                if (!(w0 & 1u)) {
+                    const unsigned long long a = (unsigned long long)__ldg(src), b = (unsigned long long)__ldg(src + 1);
+                    o = make_uint4((uint32_t)a, (uint32_t)(a >> 32), (uint32_t)b, (uint32_t)(b >> 32));
+                } else {
+                    const unsigned long long a = (unsigned long long)__ldg(src), b = (unsigned long long)__ldg(src + 1), c = (unsigned long long)__ldg(src + 2);
+                    o = make_uint4((uint32_t)(a >> 32), (uint32_t)b, (uint32_t)(b >> 32), (uint32_t)c);
+                }
+            } else {
+                uint32_t v[4];
+#pragma unroll
+                for (uint32_t k = 0; k < 4u; ++k) {
+                    const uint32_t q = q0 + k, r = q / REPLAY_WORDS, w = q - r * REPLAY_WORDS;
+                    v[k] = replay_word(g * 4ull + r, w, states, value, policy);
+                }
+                o = make_uint4(v[0], v[1], v[2], v[3]);
+            }
+            dst[e] = o;
+        }
+    }
+    // tail rows (and everything when the output is not 16-byte aligned): one word per thread
+    const unsigned long long row0 = n_groups * 4ull, tail_words = (n_rows - row0) * REPLAY_WORDS;
+    for (unsigned long long t = (unsigned long long)blockIdx.x * REPLAY_THREADS + threadIdx.x; t < tail_words; t += (unsigned long long)gridDim.x * REPLAY_THREADS) {
+        const unsigned long long r = t / REPLAY_WORDS;
+        out[row0 * REPLAY_WORDS + t] = replay_word(row0 + r, (uint32_t)(t - r * REPLAY_WORDS), states, value, policy);
     }
 }
 

@@ -41,3 +41,12 @@ def test_gpu_packer_matches_oracle(orc):
     torch.cuda.synchronize()
     want = oracle_lib.replay_records(orc, sp.states[:rows].cpu().numpy(), sp.value[:rows].cpu().numpy(), sp.policy[:rows].cpu().numpy())
     assert np.array_equal(rec.cpu().numpy(), want)
+    # a row count that is not a multiple of four (tail rows go word by word) and an output that is only 4-byte aligned (no 16-byte stores)
+    m = rows - (rows % 4) - 1
+    rec2 = dk.pack_replay_records(sp.states[:m], sp.value[:m], sp.policy[:m])
+    assert np.array_equal(rec2.cpu().numpy(), want[:m])
+    raw = torch.zeros((m * 2684 + 16,), dtype=torch.uint8, device="cuda")
+    out3 = raw[4:4 + m * 2684].view(m, 2684)
+    dk.pack_replay_records(sp.states[:m], sp.value[:m], sp.policy[:m], out=out3)
+    torch.cuda.synchronize()
+    assert np.array_equal(out3.cpu().numpy(), want[:m]) and int(raw[:4].sum()) == 0 and int(raw[4 + m * 2684:].sum()) == 0
