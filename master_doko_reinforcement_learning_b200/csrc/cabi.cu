@@ -611,16 +611,27 @@ static dk_status playout_host_impl(dk_ctx* ctx, int engine, uint32_t flags, size
     char* d_pts = base + b_states;
     char* d_steps = base + b_states + b_pts;
     if (states_host) DK_CUDA(ctx, cudaMemcpyAsync(d_states, states_host, b_states, cudaMemcpyHostToDevice, ctx->stream));
-    const size_t CH = (size_t)1 << 21;
-    const size_t n_chunks = (n + CH - 1) / CH;
+    // Chunks of 2^21 games so that the copy of chunk c overlaps the kernel of chunk c + 1; the last 2^21 games are cut into halves down
+    // to 2^18, because the copy of the final chunk is the one transfer nothing overlaps.
+    const size_t CH = (size_t)1 << 21, CH_MIN = (size_t)1 << 18;
+    std::vector<size_t> sizes;
+    {
+        size_t rem = n;
+        while (rem > CH) { sizes.push_back(CH); rem -= CH; }
+        for (size_t piece = CH / 2; piece >= CH_MIN && rem > CH_MIN; piece /= 2)
+            if (rem > piece) { sizes.push_back(piece); rem -= piece; }
+        if (rem) sizes.push_back(rem);
+    }
+    const size_t n_chunks = sizes.size();
     if (ctx->events.size() < n_chunks) {
         size_t old = ctx->events.size();
         ctx->events.resize(n_chunks);
         for (size_t e = old; e < n_chunks; ++e) DK_CUDA(ctx, cudaEventCreateWithFlags(&ctx->events[e], cudaEventDisableTiming));
     }
     dk::RngParams rp = to_params(rng);
+    size_t off = 0;
     for (size_t c = 0; c < n_chunks; ++c) {
-        size_t off = c * CH, cnt = n - off < CH ? n - off : CH;
+        const size_t cnt = sizes[c];
         dk::RngParams rc = rp;
         rc.first_id = rp.first_id + off;
         st = playout_launch(ctx, engine, flags, cnt, d_states ? d_states + off : nullptr, rc, d_pts + off * pb, d_steps + off * sb, compact, ctx->stream);
@@ -629,6 +640,7 @@ static dk_status playout_host_impl(dk_ctx* ctx, int engine, uint32_t flags, size
         DK_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->events[c], 0));
         if (points_out_host) DK_CUDA(ctx, cudaMemcpyAsync((char*)points_out_host + off * pb, d_pts + off * pb, cnt * pb, cudaMemcpyDeviceToHost, ctx->copy_stream));
         if (steps_out_host) DK_CUDA(ctx, cudaMemcpyAsync((char*)steps_out_host + off * sb, d_steps + off * sb, cnt * sb, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        off += cnt;
     }
     DK_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
     DK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
