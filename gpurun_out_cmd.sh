@@ -1,8 +1,7 @@
 set -x
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_playout.py -m gpu -x -q 2>&1 | tail -2
-python bench.py --steps 5 --warmup 3 > gpurun_out/bench_v10_1gpu.json 2> gpurun_out/bench_v10_1gpu.err; tail -1 gpurun_out/bench_v10_1gpu.json | python -c "
-import sys, json
-d = json.loads(sys.stdin.read())
-print(d['value'], d['e2e']['value'], d['e2e']['int32_api']['value'], d['roofline']['frac'], d['roofline']['alu_pipe'])
-"
+N=${NGPU:-2}
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511"
+timeout 300 $TR tests/multigpu_check.py > gpurun_out/multigpu_check_${N}gpu.txt 2>&1; tail -2 gpurun_out/multigpu_check_${N}gpu.txt
+timeout 300 $TR profiles/bench_scaling.py > gpurun_out/scaling_${N}gpu.json 2> gpurun_out/scaling_${N}gpu.err; tail -1 gpurun_out/scaling_${N}gpu.json; tail -3 gpurun_out/scaling_${N}gpu.err
+timeout 400 $TR bench.py --gpus $N --steps 5 --warmup 3 > gpurun_out/bench_${N}gpu.json 2> gpurun_out/bench_${N}gpu.err; tail -1 gpurun_out/bench_${N}gpu.json | cut -c1-200

@@ -115,8 +115,51 @@ def main():
     out["config4_leaf_rollouts_allreduce"] = {"sec": t, "rollouts_per_s": n_leaves * R * world / t, "leaves_total": n_leaves * world,
                                               "root_stats_identical_on_all_ranks": same}
     if world > 1:
+        ref_sums = all_sums.clone()
         t_ar = timed(lambda: dk.allreduce_root_stats(all_sums), iters=20)
         out["config4_allreduce_only_us"] = t_ar * 1e6
+        # the same work as a two-stream pipeline: the all-reduce of batch k (stream B) runs under the rollouts of batch k + 1 (stream A);
+        # two result buffers, events order "rollouts done -> reduce" and "reduce done -> buffer reusable"
+        sa, sb = torch.cuda.Stream(), torch.cuda.Stream()
+        bufs = [torch.zeros((n_leaves * world, 4), dtype=torch.int64, device="cuda") for _ in range(2)]
+        done = [torch.cuda.Event(), torch.cuda.Event()]
+        free = [torch.cuda.Event(), torch.cuda.Event()]
+        for e in free:
+            e.record(sb)
+        batch = [0]
+
+        def k4_pipelined():
+            b = batch[0] & 1
+            batch[0] += 1
+            sa.wait_event(free[b])
+            with torch.cuda.stream(sa):
+                bufs[b].zero_()
+                dk.leaf_rollouts(leaves, R, dk.rng(SEED, rank * n_leaves, 11), determinize=True, out=bufs[b][rank * n_leaves:(rank + 1) * n_leaves],
+                                 stream=sa.cuda_stream)
+                done[b].record(sa)
+            sb.wait_event(done[b])
+            dk.allreduce_root_stats(bufs[b], stream=sb.cuda_stream)
+            free[b].record(sb)
+
+        def run_pipelined(iters):
+            torch.cuda.synchronize()
+            dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                k4_pipelined()
+            torch.cuda.current_stream().wait_stream(sa)
+            torch.cuda.current_stream().wait_stream(sb)
+            e1.record()
+            torch.cuda.synchronize()
+            tt = torch.tensor([e0.elapsed_time(e1) / iters / 1e3], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return float(tt.item())
+
+        run_pipelined(4)
+        tp = run_pipelined(20)
+        same_p = bool(torch.equal(bufs[0], ref_sums) and torch.equal(bufs[1], ref_sums))
+        out["config4_pipelined"] = {"sec_per_batch": tp, "rollouts_per_s": n_leaves * R * world / tp, "equals_unpipelined_result": same_p}
     out["launches_rank0"] = dk.launch_count()
     if rank == 0:
         print(json.dumps(out))
