@@ -1,7 +1,5 @@
 set -x
 mkdir -p gpurun_out
-N=${NGPU:-2}
-TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511"
-timeout 300 $TR tests/multigpu_check.py > gpurun_out/multigpu_check_${N}gpu.txt 2>&1; tail -2 gpurun_out/multigpu_check_${N}gpu.txt
-timeout 300 $TR profiles/bench_scaling.py > gpurun_out/scaling_${N}gpu.json 2> gpurun_out/scaling_${N}gpu.err; tail -1 gpurun_out/scaling_${N}gpu.json; tail -3 gpurun_out/scaling_${N}gpu.err
-timeout 400 $TR bench.py --gpus $N --steps 5 --warmup 3 > gpurun_out/bench_${N}gpu.json 2> gpurun_out/bench_${N}gpu.err; tail -1 gpurun_out/bench_${N}gpu.json | cut -c1-200
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; tail -2 gpurun_out/pytest_gpu.log
+python profiles/experiments/assign_profile_run.py > gpurun_out/assign_now2.txt 2>&1; tail -1 gpurun_out/assign_now2.txt
+python profiles/bench_kernels.py > gpurun_out/kernels_v23.json 2> gpurun_out/kernels_v23.err

@@ -52,18 +52,24 @@ DK_HD void doko_assign_prepare(const dk_state& s, AssignPrep& m) {
 
 struct AssignState { Hand2 remaining, allowed[4], hand[4]; uint32_t len[4]; };
 
-// distribute_card (:284-316)
+// distribute_card (:284-316), branch-free: the receiving seat is selected by a mask, removing a card from a list that does not
+// hold it is a no-op
 DK_HD void doko_assign_distribute(AssignState& a, uint32_t player, uint32_t c) {
     const uint32_t bit = 1u << c;
 #pragma unroll
     for (uint32_t i = 0; i < 4u; ++i) {
-        if (i == player) { h2_add(a.hand[i], bit); a.len[i] -= 1u; }
-        if (a.allowed[i].a & bit) h2_remove_one(a.allowed[i], bit);
+        const bool mine = i == player;
+        h2_add(a.hand[i], mine ? bit : 0u);
+        a.len[i] -= mine ? 1u : 0u;
+        h2_remove_one(a.allowed[i], bit);
     }
     h2_remove_one(a.remaining, bit);
+    const uint32_t rem = a.remaining.a;
 #pragma unroll
-    for (uint32_t i = 0; i < 4u; ++i)
-        if (a.len[i] == 0u) { a.allowed[i].a &= ~a.remaining.a; a.allowed[i].b &= ~a.remaining.a; }
+    for (uint32_t i = 0; i < 4u; ++i) {
+        const uint32_t clr = a.len[i] == 0u ? rem : 0u;              // a full hand can take none of the remaining cards
+        a.allowed[i].a &= ~clr; a.allowed[i].b &= ~clr;
+    }
 }
 DK_HD uint32_t doko_assign_eligible(const AssignState& a, uint32_t bit) {
     uint32_t m = 0;
@@ -91,41 +97,51 @@ DK_HD uint32_t doko_assign_sample(const AssignPrep& p, const RngKey& key, uint64
     for (uint32_t i = 0; i < 4u; ++i) { a.allowed[i] = p.allowed[i]; a.len[i] = p.len[i]; a.hand[i].a = 0; a.hand[i].b = 0; }
     U4 blk; blk.x = blk.y = blk.z = blk.w = 0;
     uint32_t blk_id = 0xFFFFFFFFu, ord = 0, status = 0;
+    // One card is handed out per iteration, by ONE distribute call at the end of the body (the body is data dependent and diverges; a
+    // single call site keeps it small).  `pend` = the cards distribute_exactly_as_per_hand still has to give to `pend_seat`: the
+    // reference hands out that seat's whole list (a snapshot) before it looks at the other rules again.
+    Hand2 pend; pend.a = 0; pend.b = 0;
+    uint32_t pend_seat = 0;
     for (;;) {
-        // distribute_single_cards (:336-377): first remaining card (ascending id) with exactly one eligible seat — bit-parallel:
-        // "exactly one of four" = odd parity minus the triples
-        bool did = false;
-        {
-            uint32_t e0 = a.len[0] ? a.allowed[0].a : 0u, e1 = a.len[1] ? a.allowed[1].a : 0u, e2 = a.len[2] ? a.allowed[2].a : 0u, e3 = a.len[3] ? a.allowed[3].a : 0u;
-            uint32_t one = (e0 ^ e1 ^ e2 ^ e3) & ~((e0 & e1 & e2) | (e0 & e1 & e3) | (e0 & e2 & e3) | (e1 & e2 & e3)) & a.remaining.a;
+        uint32_t player, c;
+        if (pend.a) {
+            c = ffs0(pend.a);                                         // ascending card id, the second copy of a double right after the first
+            player = pend_seat;
+            h2_remove_one(pend, 1u << c);
+        } else {
+            // distribute_single_cards (:336-377): first remaining card (ascending id) with exactly one eligible seat — bit-parallel:
+            // "exactly one of four" = odd parity minus the triples
+            const uint32_t e0 = a.len[0] ? a.allowed[0].a : 0u, e1 = a.len[1] ? a.allowed[1].a : 0u, e2 = a.len[2] ? a.allowed[2].a : 0u,
+                           e3 = a.len[3] ? a.allowed[3].a : 0u;
+            const uint32_t one = (e0 ^ e1 ^ e2 ^ e3) & ~((e0 & e1 & e2) | (e0 & e1 & e3) | (e0 & e2 & e3) | (e1 & e2 & e3)) & a.remaining.a;
             if (one) {
-                uint32_t c = ffs0(one), bit = 1u << c;
-                doko_assign_distribute(a, (e0 & bit) ? 0u : ((e1 & bit) ? 1u : ((e2 & bit) ? 2u : 3u)), c);
-                did = true;
-            }
-        }
-        if (did) continue;
-        // distribute_exactly_as_per_hand (:379-417)
+                c = ffs0(one);
+                const uint32_t bit = 1u << c;
+                player = (e0 & bit) ? 0u : ((e1 & bit) ? 1u : ((e2 & bit) ? 2u : 3u));
+            } else {
+                // distribute_exactly_as_per_hand (:379-417): the first seat (ascending) whose open slots equal its list
+                uint32_t seat = 4u;
 #pragma unroll
-        for (uint32_t i = 0; i < 4u; ++i) {
-            if (!did && a.len[i] > 0u && a.len[i] == h2_count(a.allowed[i])) {
-                uint32_t sa = a.allowed[i].a, sb = a.allowed[i].b;
-                while (sa) { uint32_t c = ffs0(sa); sa &= sa - 1u; doko_assign_distribute(a, i, c); if ((sb >> c) & 1u) doko_assign_distribute(a, i, c); }
-                did = true;
+                for (uint32_t i = 0; i < 4u; ++i)
+                    if (seat == 4u && a.len[i] > 0u && a.len[i] == h2_count(a.allowed[i])) seat = i;
+                if (seat < 4u) {
+                    pend = seat == 0u ? a.allowed[0] : (seat == 1u ? a.allowed[1] : (seat == 2u ? a.allowed[2] : a.allowed[3]));
+                    pend_seat = seat;
+                    continue;
+                }
+                // distribute_single_card_randomly (:419-456)
+                const uint32_t n = h2_count(a.remaining);
+                if (n == 0u) break;
+                uint32_t w0, w1;
+                { uint32_t o = ord++; if ((o >> 2) != blk_id) { blk_id = o >> 2; blk = rng_block(key, SITE_ASSIGN, blk_id); } w0 = u4_word(blk, o & 3u); }
+                c = h2_select_adjacent(a.remaining, mulhi(w0, n));
+                const uint32_t e = doko_assign_eligible(a, 1u << c);
+                if (e == 0u) { status = 1u; break; }        // `.choose(rng).unwrap()` on an empty list would panic
+                { uint32_t o = ord++; if ((o >> 2) != blk_id) { blk_id = o >> 2; blk = rng_block(key, SITE_ASSIGN, blk_id); } w1 = u4_word(blk, o & 3u); }
+                player = select_lsb(e, mulhi(w1, popc(e)));
             }
         }
-        if (did) continue;
-        // distribute_single_card_randomly (:419-456)
-        uint32_t n = h2_count(a.remaining);
-        if (n == 0u) break;
-        uint32_t w0, w1;
-        { uint32_t o = ord++; if ((o >> 2) != blk_id) { blk_id = o >> 2; blk = rng_block(key, SITE_ASSIGN, blk_id); } w0 = u4_word(blk, o & 3u); }
-        uint32_t c = h2_select_adjacent(a.remaining, mulhi(w0, n));
-        uint32_t e = doko_assign_eligible(a, 1u << c);
-        if (e == 0u) { status = 1u; break; }            // `.choose(rng).unwrap()` on an empty list would panic
-        { uint32_t o = ord++; if ((o >> 2) != blk_id) { blk_id = o >> 2; blk = rng_block(key, SITE_ASSIGN, blk_id); } w1 = u4_word(blk, o & 3u); }
-        uint32_t seat = select_lsb(e, mulhi(w1, popc(e)));
-        doko_assign_distribute(a, seat, c);
+        doko_assign_distribute(a, player, c);
     }
 #pragma unroll
     for (uint32_t i = 0; i < 4u; ++i) hands_out[i] = (uint64_t)a.hand[i].a | ((uint64_t)a.hand[i].b << 24);

@@ -11,8 +11,9 @@ namespace dk {
 
 struct Hand2 { uint32_t a, b; };
 DK_HD bool h2_has(const Hand2& h, uint32_t bit) { return (h.a & bit) != 0u; }
-DK_HD void h2_add(Hand2& h, uint32_t bit) { if (h.a & bit) h.b |= bit; else h.a |= bit; }
-DK_HD void h2_remove_one(Hand2& h, uint32_t bit) { if (h.b & bit) h.b &= ~bit; else h.a &= ~bit; }   // also "remove_ignore"
+// branch-free (three logic operations each; `bit` may be 0 = no-op, and removing a card that is not there is a no-op)
+DK_HD void h2_add(Hand2& h, uint32_t bit) { const uint32_t t = h.a & bit; h.b |= t; h.a |= bit; }      // second copy goes to plane B
+DK_HD void h2_remove_one(Hand2& h, uint32_t bit) { const uint32_t t = h.b & bit; h.a &= ~(bit ^ t); h.b ^= t; }   // copy B first; also "remove_ignore"
 DK_HD uint32_t h2_len(const Hand2& h) { return popc(h.a) + popc(h.b); }
 
 // Constraint tables of one info-state.  The three hidden seats are kept in ABSOLUTE seat order in slots 0..2
