@@ -98,16 +98,24 @@ struct MatchState {
     uint32_t slots[3], must_q, status;
 };
 
-// CardMatchingState::assign_card (:49-76)
+// CardMatchingState::assign_card (:49-76), branch-free over compile-time slot numbers (the record of a sample stays in registers:
+// the indexed form put it into local memory — 13 % of the kernel's instructions were LDL / STL, profiles/r01_determinize_attribution.json):
+// the receiving slot is selected by a mask; removing a card from a set that does not hold it is a no-op.
+// (Tried and rejected: the rules as a one-card-per-iteration state machine with a single assign site, which is what sped up the
+// rs-doko sampler by 1.5x — here the lanes of a warp then sit in different rules and every iteration runs all of them: 2x slower.)
 DK_HD void fdo_match_assign(MatchState& m, uint32_t j, uint32_t c) {
     const uint32_t bit = 1u << c;
-    h2_add(m.assigned[j], bit);
-    m.slots[j] -= 1u;
     h2_remove_one(m.avail, bit);
 #pragma unroll
-    for (uint32_t o = 0; o < 3u; ++o)
-        if (o == j || (m.possible[o].a & bit)) h2_remove_one(m.possible[o], bit);
-    if (m.slots[j] == 0u) { m.possible[j].a = 0; m.possible[j].b = 0; }
+    for (uint32_t o = 0; o < 3u; ++o) {
+        const bool mine = o == j;
+        h2_add(m.assigned[o], mine ? bit : 0u);
+        m.slots[o] -= mine ? 1u : 0u;
+        h2_remove_one(m.possible[o], bit);                     // (o == j || possible[o] has the card): otherwise nothing to remove
+        const bool full = mine && m.slots[o] == 0u;
+        m.possible[o].a = full ? 0u : m.possible[o].a;
+        m.possible[o].b = full ? 0u : m.possible[o].b;
+    }
     if (c == CARD_CQ) m.must_q &= ~(1u << j);
 }
 // rule 1 (:78-113): walk a SNAPSHOT of the available cards (copy-A bits ascending, then copy-B bits) and hand every card that
