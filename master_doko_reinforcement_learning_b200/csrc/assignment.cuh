@@ -97,49 +97,42 @@ DK_HD uint32_t doko_assign_sample(const AssignPrep& p, const RngKey& key, uint64
     for (uint32_t i = 0; i < 4u; ++i) { a.allowed[i] = p.allowed[i]; a.len[i] = p.len[i]; a.hand[i].a = 0; a.hand[i].b = 0; }
     U4 blk; blk.x = blk.y = blk.z = blk.w = 0;
     uint32_t blk_id = 0xFFFFFFFFu, ord = 0, status = 0;
-    // One card is handed out per iteration, by ONE distribute call at the end of the body (the body is data dependent and diverges; a
-    // single call site keeps it small).  `pend` = the cards distribute_exactly_as_per_hand still has to give to `pend_seat`: the
-    // reference hands out that seat's whole list (a snapshot) before it looks at the other rules again.
-    Hand2 pend; pend.a = 0; pend.b = 0;
-    uint32_t pend_seat = 0;
+    // The body is data dependent and the lanes of a warp diverge in it, so it is kept small: the single-owner rule and the random rule
+    // share ONE distribute call at the end of the body, distribute_exactly_as_per_hand has the other (the first version had eleven
+    // inlined copies and spent 13 % of its instructions on register moves at the control-flow joins).
     for (;;) {
         uint32_t player, c;
-        if (pend.a) {
-            c = ffs0(pend.a);                                         // ascending card id, the second copy of a double right after the first
-            player = pend_seat;
-            h2_remove_one(pend, 1u << c);
+        // distribute_single_cards (:336-377): first remaining card (ascending id) with exactly one eligible seat — bit-parallel:
+        // "exactly one of four" = odd parity minus the triples
+        const uint32_t e0 = a.len[0] ? a.allowed[0].a : 0u, e1 = a.len[1] ? a.allowed[1].a : 0u, e2 = a.len[2] ? a.allowed[2].a : 0u,
+                       e3 = a.len[3] ? a.allowed[3].a : 0u;
+        const uint32_t one = (e0 ^ e1 ^ e2 ^ e3) & ~((e0 & e1 & e2) | (e0 & e1 & e3) | (e0 & e2 & e3) | (e1 & e2 & e3)) & a.remaining.a;
+        if (one) {
+            c = ffs0(one);
+            const uint32_t bit = 1u << c;
+            player = (e0 & bit) ? 0u : ((e1 & bit) ? 1u : ((e2 & bit) ? 2u : 3u));
         } else {
-            // distribute_single_cards (:336-377): first remaining card (ascending id) with exactly one eligible seat — bit-parallel:
-            // "exactly one of four" = odd parity minus the triples
-            const uint32_t e0 = a.len[0] ? a.allowed[0].a : 0u, e1 = a.len[1] ? a.allowed[1].a : 0u, e2 = a.len[2] ? a.allowed[2].a : 0u,
-                           e3 = a.len[3] ? a.allowed[3].a : 0u;
-            const uint32_t one = (e0 ^ e1 ^ e2 ^ e3) & ~((e0 & e1 & e2) | (e0 & e1 & e3) | (e0 & e2 & e3) | (e1 & e2 & e3)) & a.remaining.a;
-            if (one) {
-                c = ffs0(one);
-                const uint32_t bit = 1u << c;
-                player = (e0 & bit) ? 0u : ((e1 & bit) ? 1u : ((e2 & bit) ? 2u : 3u));
-            } else {
-                // distribute_exactly_as_per_hand (:379-417): the first seat (ascending) whose open slots equal its list
-                uint32_t seat = 4u;
+            // distribute_exactly_as_per_hand (:379-417): the first seat (ascending) whose open slots equal its list takes the whole list
+            // (a snapshot; ascending card id, the second copy of a double right after the first)
+            uint32_t seat = 4u;
 #pragma unroll
-                for (uint32_t i = 0; i < 4u; ++i)
-                    if (seat == 4u && a.len[i] > 0u && a.len[i] == h2_count(a.allowed[i])) seat = i;
-                if (seat < 4u) {
-                    pend = seat == 0u ? a.allowed[0] : (seat == 1u ? a.allowed[1] : (seat == 2u ? a.allowed[2] : a.allowed[3]));
-                    pend_seat = seat;
-                    continue;
-                }
-                // distribute_single_card_randomly (:419-456)
-                const uint32_t n = h2_count(a.remaining);
-                if (n == 0u) break;
-                uint32_t w0, w1;
-                { uint32_t o = ord++; if ((o >> 2) != blk_id) { blk_id = o >> 2; blk = rng_block(key, SITE_ASSIGN, blk_id); } w0 = u4_word(blk, o & 3u); }
-                c = h2_select_adjacent(a.remaining, mulhi(w0, n));
-                const uint32_t e = doko_assign_eligible(a, 1u << c);
-                if (e == 0u) { status = 1u; break; }        // `.choose(rng).unwrap()` on an empty list would panic
-                { uint32_t o = ord++; if ((o >> 2) != blk_id) { blk_id = o >> 2; blk = rng_block(key, SITE_ASSIGN, blk_id); } w1 = u4_word(blk, o & 3u); }
-                player = select_lsb(e, mulhi(w1, popc(e)));
+            for (uint32_t i = 0; i < 4u; ++i)
+                if (seat == 4u && a.len[i] > 0u && a.len[i] == h2_count(a.allowed[i])) seat = i;
+            if (seat < 4u) {
+                Hand2 pend = seat == 0u ? a.allowed[0] : (seat == 1u ? a.allowed[1] : (seat == 2u ? a.allowed[2] : a.allowed[3]));
+                while (pend.a) { const uint32_t cc = ffs0(pend.a); h2_remove_one(pend, 1u << cc); doko_assign_distribute(a, seat, cc); }
+                continue;
             }
+            // distribute_single_card_randomly (:419-456)
+            const uint32_t n = h2_count(a.remaining);
+            if (n == 0u) break;
+            uint32_t w0, w1;
+            { uint32_t o = ord++; if ((o >> 2) != blk_id) { blk_id = o >> 2; blk = rng_block(key, SITE_ASSIGN, blk_id); } w0 = u4_word(blk, o & 3u); }
+            c = h2_select_adjacent(a.remaining, mulhi(w0, n));
+            const uint32_t e = doko_assign_eligible(a, 1u << c);
+            if (e == 0u) { status = 1u; break; }            // `.choose(rng).unwrap()` on an empty list would panic
+            { uint32_t o = ord++; if ((o >> 2) != blk_id) { blk_id = o >> 2; blk = rng_block(key, SITE_ASSIGN, blk_id); } w1 = u4_word(blk, o & 3u); }
+            player = select_lsb(e, mulhi(w1, popc(e)));
         }
         doko_assign_distribute(a, player, c);
     }
