@@ -1,4 +1,4 @@
 set -x
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_matching.py -m gpu -x -q 2>&1 | tail -1
-python profiles/experiments/assign_profile_run.py > gpurun_out/assign_now3.txt 2>&1; tail -1 gpurun_out/assign_now3.txt
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; tail -2 gpurun_out/pytest_gpu.log
+python profiles/bench_kernels.py > gpurun_out/kernels_v26.json 2> gpurun_out/kernels_v26.err

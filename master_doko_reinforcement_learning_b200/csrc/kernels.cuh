@@ -630,6 +630,7 @@ fdo_leaf_rollouts_kernel(RngParams rp, uint64_t n_leaves, uint32_t rollouts, con
 // uniform across the block (the legal set of the mover does not depend on the hidden hands), so lanes stay in lock-step per action.
 constexpr int PIMC_THREADS = 128;
 constexpr int PIMC_MAX_DPB = 32;
+constexpr uint32_t PIMC_TAB = 96;    // (determinization, legal action) pairs per block whose post-action playout state is kept in shared memory
 __global__ void __launch_bounds__(PIMC_THREADS)
 fdo_pimc_kernel(RngParams rp, uint64_t n_roots, uint32_t n_det, uint32_t n_rollouts, uint32_t dpb, uint32_t blocks_per_root,
                 const dk_state* __restrict__ states, uint32_t* __restrict__ visits_out, long long* __restrict__ value_out,
@@ -640,6 +641,13 @@ fdo_pimc_kernel(RngParams rp, uint64_t n_roots, uint32_t n_det, uint32_t n_rollo
     __shared__ uint32_t wins[PIMC_MAX_DPB][N_ACTIONS];
     __shared__ uint8_t det_status[PIMC_MAX_DPB];
     __shared__ uint32_t lut[CARD_LUT_WORDS];
+    // (determinization, legal action) table: the state after the action in playout form — the same for all rollouts of the pair, so it
+    // is built once per block instead of once per rollout (apply + record → playout bridge were a quarter of the kernel)
+    __shared__ FdoLive tab_g[PIMC_TAB];
+    __shared__ FdoResume tab_rs[PIMC_TAB];
+    __shared__ signed char tab_pts[PIMC_TAB][4];
+    __shared__ uint8_t tab_live[PIMC_TAB];
+    __shared__ int tab_bad;
     const uint64_t root = blockIdx.x / blocks_per_root;
     const uint32_t d0 = (uint32_t)(blockIdx.x % blocks_per_root) * dpb;
     const uint32_t nd = min(dpb, n_det - d0);
@@ -668,6 +676,28 @@ fdo_pimc_kernel(RngParams rp, uint64_t n_roots, uint32_t n_det, uint32_t n_rollo
     __syncthreads();
     const uint32_t mover = st_cur(rootst);
     const uint32_t n_items = nd * n_rollouts;
+    // the legal set of the seat to move: its own hand and the public state do not depend on the sample (checked below: tab_bad)
+    const uint64_t m_root = finished ? 0ull : fdo_state_legal_mask<true>(det_state[0]);
+    const uint32_t n_legal = popcll(m_root);
+    const bool want_tab = nd * n_legal <= PIMC_TAB && n_legal > 0u;
+    if (threadIdx.x == 0) tab_bad = 0;
+    __syncthreads();
+    if (want_tab) {
+        for (uint32_t e = threadIdx.x; e < nd * n_legal; e += PIMC_THREADS) {
+            const uint32_t d = e / n_legal, k = e - d * n_legal;
+            if (fdo_state_legal_mask<true>(det_state[d]) != m_root) tab_bad = 1;
+            uint64_t mm = m_root;
+            for (uint32_t q = 0; q < k; ++q) mm &= mm - 1ull;
+            alignas(16) dk_state s = det_state[d];
+            fdo_state_apply<true>(s, ffs0ll(mm));
+            FdoLive g; FdoResume rs;
+            const bool lv = fdo_state_to_live<true>(s, g, rs);
+            tab_g[e] = g; tab_rs[e] = rs; tab_live[e] = lv ? 1 : 0;
+            tab_pts[e][0] = s.points[0]; tab_pts[e][1] = s.points[1]; tab_pts[e][2] = s.points[2]; tab_pts[e][3] = s.points[3];
+        }
+    }
+    __syncthreads();
+    const bool use_tab = want_tab && !tab_bad;
     for (uint32_t base = 0; base < n_items; base += PIMC_THREADS) {
         const uint32_t item = base + threadIdx.x;
         const bool on = item < n_items;
@@ -682,14 +712,20 @@ fdo_pimc_kernel(RngParams rp, uint64_t n_roots, uint32_t n_det, uint32_t n_rollo
         uint32_t best_a = ACTION_NONE;
         // legal set of the determinized state: the mover's own hand and the public state do not depend on the sample, so this is the
         // root's legal set and the loop is uniform across the block; peers (same dl) share it exactly in any case
-        for (uint64_t m = fdo_state_legal_mask<true>(det_state[dl]); m; m &= m - 1ull) {
+        uint32_t e = dl * n_legal;
+        for (uint64_t m = use_tab ? m_root : fdo_state_legal_mask<true>(det_state[dl]); m; m &= m - 1ull, ++e) {
             const uint32_t a = ffs0ll(m);
-            alignas(16) dk_state s = det_state[dl];
-            fdo_state_apply<true>(s, a);                                  // indexed form: the record stays in local memory (237 registers otherwise)
             int32_t p[4];
-            FdoLive g; FdoResume rs;
-            if (fdo_state_to_live<true>(s, g, rs)) { fdo_play_to_end<false, false>(g, key, &rs, lut); fdo_final_points(g, p); }
-            else { p[0] = s.points[0]; p[1] = s.points[1]; p[2] = s.points[2]; p[3] = s.points[3]; }
+            if (use_tab) {
+                if (tab_live[e]) { FdoLive g = tab_g[e]; fdo_play_to_end<false, false>(g, key, &tab_rs[e], lut); fdo_final_points(g, p); }
+                else { p[0] = tab_pts[e][0]; p[1] = tab_pts[e][1]; p[2] = tab_pts[e][2]; p[3] = tab_pts[e][3]; }
+            } else {                                                      // more (determinization, action) pairs than the table holds
+                alignas(16) dk_state s = det_state[dl];
+                fdo_state_apply<true>(s, a);                              // indexed form: the record stays in local memory (237 registers otherwise)
+                FdoLive g; FdoResume rs;
+                if (fdo_state_to_live<true>(s, g, rs)) { fdo_play_to_end<false, false>(g, key, &rs, lut); fdo_final_points(g, p); }
+                else { p[0] = s.points[0]; p[1] = s.points[1]; p[2] = s.points[2]; p[3] = s.points[3]; }
+            }
             const int v = (mover & 2u) ? ((mover & 1u) ? p[3] : p[2]) : ((mover & 1u) ? p[1] : p[0]);
             const int tot = __reduce_add_sync(peers, v);
             if (leader) atomicAdd(&vsum[dl][a], tot);
