@@ -1,4 +1,3 @@
 set -x
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; tail -2 gpurun_out/pytest_gpu.log
-python profiles/bench_kernels.py > gpurun_out/kernels_v26.json 2> gpurun_out/kernels_v26.err
+for t in 128 256 512; do DOKO_CUDA_LIB=$PWD/profiles/experiments/libs/libdoko_pimc$t.so python profiles/experiments/pimc_cfg.py; done > gpurun_out/pimc_cfg.txt 2>&1; cat gpurun_out/pimc_cfg.txt

@@ -628,7 +628,10 @@ fdo_leaf_rollouts_kernel(RngParams rp, uint64_t n_leaves, uint32_t rollouts, con
 // the seat to move followed by a _no_announcement rollout on the stream (root, d·R + r) shared by all actions (common random
 // numbers), adds points[mover] to value_sum[d][a] and one visit to the best action (first among equals).  The action loop is
 // uniform across the block (the legal set of the mover does not depend on the hidden hands), so lanes stay in lock-step per action.
-constexpr int PIMC_THREADS = 128;
+#ifndef DK_PIMC_THREADS
+#define DK_PIMC_THREADS 128
+#endif
+constexpr int PIMC_THREADS = DK_PIMC_THREADS;
 constexpr int PIMC_MAX_DPB = 32;
 constexpr uint32_t PIMC_TAB = 96;    // (determinization, legal action) pairs per block whose post-action playout state is kept in shared memory
 __global__ void __launch_bounds__(PIMC_THREADS)
