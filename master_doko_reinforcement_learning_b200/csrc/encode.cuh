@@ -100,6 +100,8 @@ DK_HD void fdo_encode_pi(const dk_state& s, Out& out) {
 // observer's entry is ignored), assumed reservations DK_RES_* by absolute seat or DK_RES_NONE.
 // Returns 0, or 1 when the reference would panic (a guessed hand larger than the real one ⇒ `hand.len() - assumed.len()` underflows,
 // or the slot count is not 62); the row is then zero-padded / truncated.
+// Like fdo_encode_pi, every access to the record and to the guesses uses a compile-time offset (seat rotations by selects, the card
+// and call loops over all positions under a predicate, the guessed reservations as one packed word): nothing lives in local memory.
 template <class Out>
 DK_HD uint32_t fdo_encode_ipi(const dk_state& s, const uint64_t assumed[4], const uint8_t assumed_res[4], uint32_t next_player, Out& out) {
     const uint32_t cur = st_phase(s) == DK_PHASE_FINISHED ? 0u : st_cur(s);
@@ -110,7 +112,9 @@ DK_HD uint32_t fdo_encode_ipi(const dk_state& s, const uint64_t assumed[4], cons
     };
     const uint32_t start = st_game_start(s), nres = s.n_reservations;
     const bool completed = nres == 4u;
+    const uint32_t ares4 = (uint32_t)assumed_res[0] | ((uint32_t)assumed_res[1] << 8) | ((uint32_t)assumed_res[2] << 16) | ((uint32_t)assumed_res[3] << 24);
     bool solo_seen = false;
+#pragma unroll
     for (uint32_t i = 0; i < 4u; ++i) {                                       // get_visible_reservations(observer) (visible_reservations_logic.rs:7-70)
         const uint32_t seat = (start + i) & 3u;
         uint32_t tok = 35u;                                                   // NoneYet
@@ -120,18 +124,33 @@ DK_HD uint32_t fdo_encode_ipi(const dk_state& s, const uint64_t assumed[4], cons
             else if (code == 1u) tok = (completed || seat == cur) ? 26u : 34u;
             else if (completed && !solo_seen) { tok = 25u + code; solo_seen = true; }
             else tok = 34u;                                                   // NotRevealed
-            if (tok == 34u && assumed_res[seat] != 0xFFu) tok = 25u + assumed_res[seat];
+            const uint32_t guess = (ares4 >> (8u * seat)) & 255u;
+            if (tok == 34u && guess != 0xFFu) tok = 25u + guess;
         }
         push(tok, i + 1u, ((seat - cur) & 3u) + 1u, 0u, 0u);
     }
-    const uint32_t ci = s.card_index;
-    for (uint32_t j = 0; j < ci; ++j) {                                       // played cards (:93-110)
-        uint32_t seat = (st_trick_start(s, j >> 2) + (j & 3u)) & 3u;
-        push(fdo_card_token(s.cards[j]), j + 5u, ((seat - cur) & 3u) + 1u, 0u, 0u);
+    const uint32_t ci = s.card_index, tricks = s.tricks;
+#pragma unroll
+    for (uint32_t t = 0; t < 12u; ++t) {                                      // played cards (:93-110), trick by trick
+        if (4u * t < ci) {
+            const uint32_t quad = st_word_of(s.cards, t), lead = (tricks >> (2u * t)) & 3u;
+#pragma unroll
+            for (uint32_t k = 0; k < 4u; ++k) {
+                const uint32_t j = 4u * t + k;
+                if (j < ci) out.slot(4u + j, fdo_card_token((quad >> (8u * k)) & 255u), j + 5u, ((lead + k - cur) & 3u) + 1u, 0u, 0u);
+            }
+        }
     }
+    n = 4u + ci;
+    // real and guessed hands from the observer on: rotate with selects instead of indexing by (cur + i) & 3
+    uint64_t r0 = s.hands[0], r1 = s.hands[1], r2 = s.hands[2], r3 = s.hands[3];
+    uint64_t g0 = assumed[0], g1 = assumed[1], g2 = assumed[2], g3 = assumed[3];
+    if (cur & 1u) { uint64_t t = r0; r0 = r1; r1 = r2; r2 = r3; r3 = t; t = g0; g0 = g1; g1 = g2; g2 = g3; g3 = t; }
+    if (cur & 2u) { uint64_t t0 = r0, t1 = r1; r0 = r2; r1 = r3; r2 = t0; r3 = t1; t0 = g0; t1 = g1; g0 = g2; g1 = g3; g2 = t0; g3 = t1; }
+#pragma unroll
     for (uint32_t i = 0; i < 4u; ++i) {
-        const uint32_t seat = (cur + i) & 3u;
-        const uint64_t real = s.hands[seat], h = i == 0u ? real : assumed[seat];
+        const uint64_t real = i == 0u ? r0 : (i == 1u ? r1 : (i == 2u ? r2 : r3));
+        const uint64_t h = i == 0u ? real : (i == 1u ? g1 : (i == 2u ? g2 : g3));
         for (uint64_t b = h; b; b &= b - 1ull) {
             uint32_t pos = ffs0ll(b);
             uint32_t c = pos < 24u ? pos : pos - 24u;
@@ -146,13 +165,15 @@ DK_HD uint32_t fdo_encode_ipi(const dk_state& s, const uint64_t assumed[4], cons
     }
     const uint32_t n_calls = st_n_calls(s), re = st_re_mask(s);
     uint32_t sub = 0, last = 0xFFFFFFFFu;
-    for (uint32_t a = 0; a < n_calls && a < 10u; ++a) {                       // calls (:191-215)
-        uint32_t v = s.announcements[a], cidx = v & 63u, seat = (v >> 6) & 3u, lvl = (v >> 8) & 7u;
-        if (cidx != last) { last = cidx; sub = 0; }
-        push(lvl == 6u ? 38u : 37u + lvl, cidx + 1u, ((seat - cur) & 3u) + 1u, sub + 1u, ((re >> seat) & 1u) ? 1u : 2u);
-        sub++;
+#pragma unroll
+    for (uint32_t a = 0; a < 10u; ++a) {                                      // calls (:191-215), then padding
+        const uint32_t v = s.announcements[a], cidx = v & 63u, seat = (v >> 6) & 3u, lvl = (v >> 8) & 7u;
+        if (a < n_calls) {
+            if (cidx != last) { last = cidx; sub = 0; }
+            push(lvl == 6u ? 38u : 37u + lvl, cidx + 1u, ((seat - cur) & 3u) + 1u, sub + 1u, ((re >> seat) & 1u) ? 1u : 2u);
+            sub++;
+        } else push(37u, 0u, 0u, 0u, 0u);
     }
-    for (uint32_t a = n_calls; a < 10u; ++a) push(37u, 0u, 0u, 0u, 0u);
     if (n != 62u) err = 1u;
     for (; n < 62u; ++n) out.slot(n, 0u, 0u, 0u, 0u, 0u);
     out.phase(((next_player - cur) & 3u) + 1u);
