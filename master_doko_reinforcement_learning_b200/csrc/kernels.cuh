@@ -563,10 +563,13 @@ doko_assign_kernel(RngParams rp, uint64_t n_info, uint32_t samples, const dk_sta
 // register-resident playout form is the same for every rollout of the leaf, so it is built once per block in shared memory and the
 // kernel fits 64 registers (8 blocks per SM: 1024 leaves are resident at once instead of running in 1.7 waves).
 template <bool DET>
+#ifndef DK_LEAF_DET_BLOCKS
+#define DK_LEAF_DET_BLOCKS 7
+#endif
 #ifndef DK_LEAF_BLOCKS
 #define DK_LEAF_BLOCKS 7
 #endif
-__global__ void __launch_bounds__(MATCH_THREADS, DET ? 4 : DK_LEAF_BLOCKS)
+__global__ void __launch_bounds__(MATCH_THREADS, DET ? DK_LEAF_DET_BLOCKS : DK_LEAF_BLOCKS)
 fdo_leaf_rollouts_kernel(RngParams rp, uint64_t n_leaves, uint32_t rollouts, const dk_state* __restrict__ states, long long* __restrict__ point_sum) {
     __shared__ MatchPrep prep;
     __shared__ __align__(16) dk_state leaf;
@@ -634,7 +637,10 @@ fdo_leaf_rollouts_kernel(RngParams rp, uint64_t n_leaves, uint32_t rollouts, con
 constexpr int PIMC_THREADS = DK_PIMC_THREADS;
 constexpr int PIMC_MAX_DPB = 32;
 constexpr uint32_t PIMC_TAB = 96;    // (determinization, legal action) pairs per block whose post-action playout state is kept in shared memory
-__global__ void __launch_bounds__(PIMC_THREADS)
+#ifndef DK_PIMC_BLOCKS
+#define DK_PIMC_BLOCKS 6
+#endif
+__global__ void __launch_bounds__(PIMC_THREADS, DK_PIMC_BLOCKS)
 fdo_pimc_kernel(RngParams rp, uint64_t n_roots, uint32_t n_det, uint32_t n_rollouts, uint32_t dpb, uint32_t blocks_per_root,
                 const dk_state* __restrict__ states, uint32_t* __restrict__ visits_out, long long* __restrict__ value_out,
                 uint8_t* __restrict__ status_out) {
