@@ -324,29 +324,40 @@ DK_HD void fdo_replay_announcements(FdoLive& g, const RngKey& key, uint32_t star
     uint32_t tp = thr2[8u * re_low + ko_low], thr_re = tp & 255u, thr_ko = tp >> 8;
     AnnBits st; st.buf = 0; st.avail = 0; st.next = 0; st.blk = 0; st.w.x = st.w.y = st.w.z = st.w.w = 0;
     if (WITH_ANN) fdo_ann_open(st, key, ord);                      // lock-step: every lane fetches its block (block 0 for a fresh game) before the loop
-    // per-position values (recomputed when ci advances)
+    // Eligibility of the four seats at once, one byte per ABSOLUTE seat:
+    //   cards4h  0x80 + cards on hand (the seats that already played in the running trick hold one card less); a seat's byte is
+    //            decremented when it plays, so no per-trick recomputation is needed
+    //   thr4     the threshold of the seat's team
+    // cards >= threshold  <=>  bit 7 of (cards4h - thr4) in that byte (thresholds are <= 99: no borrow crosses a byte); the four bits
+    // are gathered into a nibble by one multiplication (bit 8s -> bit 28 + s; the partial products do not collide).
+    const uint32_t re_spread = (re & 1u) | ((re & 2u) << 7) | ((re & 4u) << 14) | ((re & 8u) << 21);
+    const uint32_t ko_spread = 0x01010101u - re_spread;
+    uint32_t thr4 = thr_re * re_spread + thr_ko * ko_spread;
     uint32_t cmax = 12u - (ci >> 2);
-    uint32_t base = (starts >> (2u * (ci >> 2))) & 3u;
-    uint32_t played = ((1u << (ci & 3u)) - 1u) << base; played = (played | (played >> 4)) & 15u;   // seats that already played in this trick
+    uint32_t q;                                                    // the seat that plays card ci
+    uint32_t cards4h;
+    {
+        const uint32_t base = (starts >> (2u * (ci >> 2))) & 3u;
+        q = (base + (ci & 3u)) & 3u;
+        uint32_t played = ((1u << (ci & 3u)) - 1u) << base; played = (played | (played >> 4)) & 15u;   // seats that already played in this trick
+        cards4h = (0x80u + cmax) * 0x01010101u - ((played & 1u) | ((played & 2u) << 7) | ((played & 4u) << 14) | ((played & 8u) << 21));
+    }
+    uint32_t vis = (1u << (4u - turns)) - 1u;                      // the seats visited before the count reaches 4 (all four after the first segment)
     while (cmax >= (thr_re < thr_ko ? thr_re : thr_ko)) {         // else: monotone, nobody can ever call again
-        // eligibility by absolute seat: cards on hand >= the team's threshold
-        uint32_t e_re = cmax >= thr_re ? (cmax - 1u >= thr_re ? 15u : (~played & 15u)) : 0u;
-        uint32_t e_ko = cmax >= thr_ko ? (cmax - 1u >= thr_ko ? 15u : (~played & 15u)) : 0u;
-        uint32_t elig = (e_re & re) | (e_ko & ~re & 15u);
-        uint32_t rot = ((elig | (elig << 4)) >> p) & 15u;         // bit d: seat p + d is eligible
-        uint32_t win = rot & ((1u << (4u - turns)) - 1u);         // the seats visited before the count reaches 4
-        uint32_t m = popc(win);
-        uint32_t hit = (WITH_ANN && m) ? fdo_ann_peek(st, m) : 0u;
+        const uint32_t elig = ((((cards4h - thr4) >> 7) & 0x01010101u) * 0x10204080u) >> 28;
+        const uint32_t win = ((elig * 0x11u) >> p) & vis;          // bit d: seat p + d is eligible and reached
+        const uint32_t m = popc(win);
+        const uint32_t hit = WITH_ANN ? fdo_ann_peek(st, m) : 0u;  // (m == 0 reads no bit)
+        vis = 15u;
         if (hit == 0u) {                                          // everybody passes: RoundIsOver → card ci is played; next round
             ord += m;
             if (WITH_ANN) fdo_ann_consume(st, key, m);
+            cards4h -= 1u << (8u * q);
             ci++;
             if (ci >= 48u) break;
+            q = (ci & 3u) ? ((q + 1u) & 3u) : ((starts >> (2u * (ci >> 2))) & 3u);
+            p = q;
             cmax = 12u - (ci >> 2);
-            base = (starts >> (2u * (ci >> 2))) & 3u;
-            played = ((1u << (ci & 3u)) - 1u) << base; played = (played | (played >> 4)) & 15u;
-            p = (base + (ci & 3u)) & 3u;
-            turns = 0;
             continue;
         }
         const uint32_t sv = seg[16u * win + hit];                 // j eligible seats pass, the (j+1)-th calls: it sits d places after p
@@ -354,14 +365,14 @@ DK_HD void fdo_replay_announcements(FdoLive& g, const RngKey& key, uint32_t star
         ord += j + 1u;
         fdo_ann_consume(st, key, j + 1u);
         p = (p + d) & 3u;
-        uint32_t is_re = (re >> p) & 1u;
-        uint32_t c = cmax - ((played >> p) & 1u);
+        const uint32_t is_re = (re >> p) & 1u;
+        const uint32_t c = (cards4h >> (8u * p)) & 0x7Fu;
         uint32_t ml = is_re ? re_low : ko_low;
         ml = ml == 6u ? 0u : ml;
-        uint32_t call = (ml < 5u && c + ml + w >= 11u) ? ml + 1u : 1u;   // next level, else the counter (recorded as Re/Kontra)
+        const uint32_t call = (ml < 5u && c + ml + w >= 11u) ? ml + 1u : 1u;   // next level, else the counter (recorded as Re/Kontra)
         if (is_re) re_low = call; else ko_low = call;             // announcement.rs:203-210
         tp = thr2[8u * re_low + ko_low]; thr_re = tp & 255u; thr_ko = tp >> 8;
-        turns = 0;
+        thr4 = thr_re * re_spread + thr_ko * ko_spread;
         p = (p + 1u) & 3u;
     }
     g.re_low = re_low; g.ko_low = ko_low; g.steps += ord - g.ann_count; g.ann_count = ord;
