@@ -1,4 +1,4 @@
 set -x
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; tail -2 gpurun_out/pytest_gpu.log
-python profiles/experiments/k2_grid.py > gpurun_out/k2_now.txt 2>&1; cat gpurun_out/k2_now.txt
+ncu --set full --import-source on --clock-control none -k regex:fdo_playout_fresh -s 1 -c 1 -f -o gpurun_out/prof_k2_v10_2p24 python profiles/profile_playout.py --n 16777216 --launches 2 > gpurun_out/prof_k2_v10.log 2>&1
+python profiles/bench_kernels.py > gpurun_out/kernels_v29.json 2> gpurun_out/kernels_v29.err
