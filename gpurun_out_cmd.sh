@@ -1,4 +1,6 @@
 set -x
 mkdir -p gpurun_out
-ncu --set full --import-source on --clock-control none -k regex:fdo_playout_fresh -s 1 -c 1 -f -o gpurun_out/prof_k2_v10_2p24 python profiles/profile_playout.py --n 16777216 --launches 2 > gpurun_out/prof_k2_v10.log 2>&1
-python profiles/bench_kernels.py > gpurun_out/kernels_v29.json 2> gpurun_out/kernels_v29.err
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; tail -1 gpurun_out/smoke.log
+python bench.py --steps 5 --warmup 3 > gpurun_out/bench_v12_1gpu.json 2> gpurun_out/bench_v12_1gpu.err; tail -1 gpurun_out/bench_v12_1gpu.json | cut -c1-200
+python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_v12_reference_arm.json 2>&1; tail -1 gpurun_out/bench_v12_reference_arm.json | cut -c1-200
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_bench_v12.csv python bench.py --steps 2 --warmup 1 > gpurun_out/ncu_bench_v12.log 2>&1
