@@ -144,6 +144,35 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this rank's CPU threads to the NUMA node its GPU hangs off, BEFORE any pinned host buffer is allocated (first touch puts
+    the buffers on that node): with 8 ranks the device→host result copies otherwise all land on whichever node the ranks started on.
+    Host-side placement only; returns the node number or None when the topology cannot be read (then nothing is changed)."""
+    try:
+        import torch
+
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id if hasattr(torch.cuda.get_device_properties(local_rank), "pci_bus_id") else None
+        dom = getattr(torch.cuda.get_device_properties(local_rank), "pci_domain_id", 0)
+        devn = getattr(torch.cuda.get_device_properties(local_rank), "pci_device_id", 0)
+        if bus is None:
+            return None
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{devn:02x}.0/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 def run_cuda(args):
     import numpy as np
     import torch
@@ -157,6 +186,7 @@ def run_cuda(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the simulator has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
+    numa_node = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -297,7 +327,8 @@ def run_cuda(args):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 24, "d2h_bytes_per_step": n * 5,
                     "api": "dk_playout_host_compact (int8 points + uint8 steps into pinned host buffers, chunked so copies overlap the kernel)",
-                    "int32_api": {"value": e2e_int32, "d2h_bytes_per_step": n * 20, "api": "dk_playout_host"}},
+                    "int32_api": {"value": e2e_int32, "d2h_bytes_per_step": n * 20, "api": "dk_playout_host"},
+                    "host_numa_node_rank0": numa_node},
             "gpu_launches": launches,
             "roofline": roof,
         }
