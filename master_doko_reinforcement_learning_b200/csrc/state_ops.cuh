@@ -43,15 +43,19 @@ DK_HD uint32_t hand_both24(uint64_t h) { return (uint32_t)((h & (h >> 24)) & 0xF
 // blocks per SM; the PIMC evaluator: the whole rollout state is live next to the record) — measured, profiles/r01_kernels_v17.json.
 template <bool IDX = false>
 DK_HD uint64_t st_hand(const dk_state& s, uint32_t p) {
-    if (IDX) return s.hands[p];
-    const uint64_t a = (p & 1u) ? s.hands[1] : s.hands[0], b = (p & 1u) ? s.hands[3] : s.hands[2];
-    return (p & 2u) ? b : a;
+    if constexpr (IDX) return s.hands[p];
+    else {
+        const uint64_t a = (p & 1u) ? s.hands[1] : s.hands[0], b = (p & 1u) ? s.hands[3] : s.hands[2];
+        return (p & 2u) ? b : a;
+    }
 }
 template <bool IDX = false>
 DK_HD void st_set_hand(dk_state& s, uint32_t p, uint64_t h) {
-    if (IDX) { s.hands[p] = h; return; }
+    if constexpr (IDX) s.hands[p] = h;
+    else {
 #pragma unroll
-    for (uint32_t q = 0; q < 4u; ++q) s.hands[q] = q == p ? h : s.hands[q];
+        for (uint32_t q = 0; q < 4u; ++q) s.hands[q] = q == p ? h : s.hands[q];
+    }
 }
 DK_HD uint32_t st_word_of(const uint8_t* bytes, uint32_t w) {            // 32-bit word w of a byte field (little endian), w compile-time
     return (uint32_t)bytes[4u * w] | ((uint32_t)bytes[4u * w + 1u] << 8) | ((uint32_t)bytes[4u * w + 2u] << 16) | ((uint32_t)bytes[4u * w + 3u] << 24);
@@ -62,40 +66,50 @@ DK_HD void st_set_word_of(uint8_t* bytes, uint32_t w, uint32_t v) {
 // the four cards of trick t (byte k = k-th card; 0xFF = not played yet)
 template <bool IDX = false>
 DK_HD uint32_t st_quad(const dk_state& s, uint32_t t) {
-    if (IDX) return (uint32_t)s.cards[4u * t] | ((uint32_t)s.cards[4u * t + 1u] << 8) | ((uint32_t)s.cards[4u * t + 2u] << 16) | ((uint32_t)s.cards[4u * t + 3u] << 24);
-    uint32_t q = 0;
+    if constexpr (IDX) return (uint32_t)s.cards[4u * t] | ((uint32_t)s.cards[4u * t + 1u] << 8) | ((uint32_t)s.cards[4u * t + 2u] << 16) | ((uint32_t)s.cards[4u * t + 3u] << 24);
+    else {
+        uint32_t q = 0;
 #pragma unroll
-    for (uint32_t w = 0; w < 12u; ++w) q = w == t ? st_word_of(s.cards, w) : q;
-    return q;
+        for (uint32_t w = 0; w < 12u; ++w) q = w == t ? st_word_of(s.cards, w) : q;
+        return q;
+    }
 }
 template <bool IDX = false>
 DK_HD uint32_t st_card(const dk_state& s, uint32_t i) { return IDX ? (uint32_t)s.cards[i] : (st_quad<false>(s, i >> 2) >> (8u * (i & 3u))) & 255u; }
 template <bool IDX = false>
 DK_HD void st_set_card(dk_state& s, uint32_t i, uint32_t c) {
-    if (IDX) { s.cards[i] = (uint8_t)c; return; }
-    const uint32_t sh = 8u * (i & 3u), keep = ~(255u << sh), ins = c << sh, t = i >> 2;
+    if constexpr (IDX) s.cards[i] = (uint8_t)c;
+    else {
+        const uint32_t sh = 8u * (i & 3u), keep = ~(255u << sh), ins = c << sh, t = i >> 2;
 #pragma unroll
-    for (uint32_t w = 0; w < 12u; ++w) { const uint32_t old = st_word_of(s.cards, w); st_set_word_of(s.cards, w, w == t ? (old & keep) | ins : old); }
+        for (uint32_t w = 0; w < 12u; ++w) { const uint32_t old = st_word_of(s.cards, w); st_set_word_of(s.cards, w, w == t ? (old & keep) | ins : old); }
+    }
 }
 template <bool IDX = false>
 DK_HD void st_set_call(dk_state& s, uint32_t n, uint32_t v) {            // announcements[n] = v
-    if (IDX) { s.announcements[n] = (uint16_t)v; return; }
+    if constexpr (IDX) s.announcements[n] = (uint16_t)v;
+    else {
 #pragma unroll
-    for (uint32_t a = 0; a < 12u; ++a) s.announcements[a] = a == n ? (uint16_t)v : s.announcements[a];
+        for (uint32_t a = 0; a < 12u; ++a) s.announcements[a] = a == n ? (uint16_t)v : s.announcements[a];
+    }
 }
 template <bool IDX = false>
 DK_HD void st_push_reservation(dk_state& s, uint32_t code) {             // reservations[n_reservations++] = code
     const uint32_t n = s.n_reservations;
-    if (IDX) { s.reservations[n] = (uint8_t)code; s.n_reservations = (uint8_t)(n + 1u); return; }
+    if constexpr (IDX) s.reservations[n] = (uint8_t)code;
+    else {
 #pragma unroll
-    for (uint32_t i = 0; i < 4u; ++i) s.reservations[i] = i == n ? (uint8_t)code : s.reservations[i];
+        for (uint32_t i = 0; i < 4u; ++i) s.reservations[i] = i == n ? (uint8_t)code : s.reservations[i];
+    }
     s.n_reservations = (uint8_t)(n + 1u);
 }
 template <bool IDX = false>
 DK_HD void st_add_eyes(dk_state& s, uint32_t seat, uint32_t e) {
-    if (IDX) { s.eyes[seat] = (uint8_t)(s.eyes[seat] + e); return; }
+    if constexpr (IDX) s.eyes[seat] = (uint8_t)(s.eyes[seat] + e);
+    else {
 #pragma unroll
-    for (uint32_t p = 0; p < 4u; ++p) s.eyes[p] = (uint8_t)(s.eyes[p] + (p == seat ? e : 0u));
+        for (uint32_t p = 0; p < 4u; ++p) s.eyes[p] = (uint8_t)(s.eyes[p] + (p == seat ? e : 0u));
+    }
 }
 
 DK_HD void st_clear(dk_state& s) {
