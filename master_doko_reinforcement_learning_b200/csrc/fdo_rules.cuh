@@ -302,6 +302,12 @@ DK_HD void fdo_ann_consume(AnnBits& st, const RngKey& key, uint32_t n) {
     if (st.avail < 4u) fdo_ann_refill(st, key);
 }
 
+// Byte-parallel "cards on hand >= threshold of the seat's team" for the four seats: `cards4h` holds 0x80 + cards per byte (absolute
+// seat), `thr4` the threshold per byte (<= 99, so no borrow crosses a byte); bit 7 of each byte of the difference is the answer and one
+// multiplication gathers the four bits into a nibble (bit 8s -> bit 28 + s; the partial products land on distinct bits below 28).
+DK_HD uint32_t fdo_spread4(uint32_t nibble) { return (nibble & 1u) | ((nibble & 2u) << 7) | ((nibble & 4u) << 14) | ((nibble & 8u) << 21); }
+DK_HD uint32_t fdo_eligible_nibble(uint32_t cards4h, uint32_t thr4) { return ((((cards4h - thr4) >> 7) & 0x01010101u) * 0x10204080u) >> 28; }
+
 // The loop advances by SEGMENTS: from (seat p, `turns` consecutive no's) the next 4 - turns seats are visited unless somebody
 // calls; the eligible ones among them each consume one decision bit.  All-zero bits → the round is over (advance to the next
 // card); otherwise the first set bit is a call, which changes the levels and restarts the count.  Iterations per lane =
@@ -330,7 +336,7 @@ DK_HD void fdo_replay_announcements(FdoLive& g, const RngKey& key, uint32_t star
     //   thr4     the threshold of the seat's team
     // cards >= threshold  <=>  bit 7 of (cards4h - thr4) in that byte (thresholds are <= 99: no borrow crosses a byte); the four bits
     // are gathered into a nibble by one multiplication (bit 8s -> bit 28 + s; the partial products do not collide).
-    const uint32_t re_spread = (re & 1u) | ((re & 2u) << 7) | ((re & 4u) << 14) | ((re & 8u) << 21);
+    const uint32_t re_spread = fdo_spread4(re);
     const uint32_t ko_spread = 0x01010101u - re_spread;
     uint32_t thr4 = thr_re * re_spread + thr_ko * ko_spread;
     uint32_t cmax = 12u - (ci >> 2);
@@ -340,11 +346,11 @@ DK_HD void fdo_replay_announcements(FdoLive& g, const RngKey& key, uint32_t star
         const uint32_t base = (starts >> (2u * (ci >> 2))) & 3u;
         q = (base + (ci & 3u)) & 3u;
         uint32_t played = ((1u << (ci & 3u)) - 1u) << base; played = (played | (played >> 4)) & 15u;   // seats that already played in this trick
-        cards4h = (0x80u + cmax) * 0x01010101u - ((played & 1u) | ((played & 2u) << 7) | ((played & 4u) << 14) | ((played & 8u) << 21));
+        cards4h = (0x80u + cmax) * 0x01010101u - fdo_spread4(played);
     }
     uint32_t vis = (1u << (4u - turns)) - 1u;                      // the seats visited before the count reaches 4 (all four after the first segment)
     while (cmax >= (thr_re < thr_ko ? thr_re : thr_ko)) {         // else: monotone, nobody can ever call again
-        const uint32_t elig = ((((cards4h - thr4) >> 7) & 0x01010101u) * 0x10204080u) >> 28;
+        const uint32_t elig = fdo_eligible_nibble(cards4h, thr4);
         const uint32_t win = ((elig * 0x11u) >> p) & vis;          // bit d: seat p + d is eligible and reached
         const uint32_t m = popc(win);
         const uint32_t hit = WITH_ANN ? fdo_ann_peek(st, m) : 0u;  // (m == 0 reads no bit)

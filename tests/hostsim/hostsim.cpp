@@ -69,6 +69,13 @@ SIM_API void sim_doko_playout_fresh(uint64_t seed, uint32_t epoch, uint64_t firs
         if (aux) std::memcpy(aux + i * 4, ax, 16);
     }
 }
+// the byte-parallel eligibility test of the announcement replay: cards[4] on hand, thresholds of the two teams, re seats → nibble
+SIM_API uint32_t sim_fdo_eligible_nibble(const uint32_t cards[4], uint32_t thr_re, uint32_t thr_ko, uint32_t re) {
+    uint32_t c4 = 0x80808080u;
+    for (int s = 0; s < 4; ++s) c4 += cards[s] << (8 * s);
+    const uint32_t rs = dk::fdo_spread4(re & 15u);
+    return dk::fdo_eligible_nibble(c4, thr_re * rs + thr_ko * (0x01010101u - rs));
+}
 SIM_API uint32_t sim_fdo_allowed_call(uint32_t c, uint32_t m, uint32_t e, uint32_t w) { return dk::fdo_allowed_call(c, m, e, w); }
 SIM_API int32_t sim_fdo_score(uint32_t re_eyes, uint32_t re_tricks, uint32_t n_re, uint32_t rl, uint32_t kl, int32_t extras, int32_t* ko) {
     return dk::fdo_score(re_eyes, re_tricks, n_re, rl, kl, extras, ko);

@@ -126,6 +126,24 @@ def test_device_min_cards_to_call_is_the_threshold_of_allowed_call():
                     assert thr > 12, (m, e, w, thr)
 
 
+def test_device_byte_parallel_eligibility_matches_the_per_seat_comparison():
+    """The announcement replay decides "cards on hand >= threshold of the seat's team" for four seats with one byte-wise subtraction and
+    one multiplication (fdo_eligible_nibble): equal to the per-seat comparison for every hand-size pattern the game produces (all seats
+    hold c or c - 1 cards), both teams' thresholds incl. 99 = never, and every Re mask."""
+    import numpy as np
+
+    sim = hostsim_lib.load()
+    thresholds = list(range(0, 13)) + [99]
+    for cmax in range(1, 13):
+        for played in range(16):
+            cards = np.array([cmax - ((played >> s) & 1) for s in range(4)], dtype=np.uint32)
+            for thr_re in thresholds:
+                for thr_ko in thresholds:
+                    for re in range(16):
+                        want = sum(1 << s for s in range(4) if cards[s] >= (thr_re if (re >> s) & 1 else thr_ko))
+                        assert sim.sim_fdo_eligible_nibble(hostsim_lib.ptr(cards), thr_re, thr_ko, re) == want, (cmax, played, thr_re, thr_ko, re)
+
+
 def test_device_score_matches_oracle_exhaustively(orc):
     """Closed-form scoring (fdo_score) vs the literal stats.rs restatement over all calls x eyes x trick extremes x team sizes."""
     sim = hostsim_lib.load()
