@@ -83,6 +83,16 @@ SIM_API int32_t sim_fdo_score(uint32_t re_eyes, uint32_t re_tricks, uint32_t n_r
 SIM_API uint32_t sim_select_lsb24(uint32_t x, uint32_t k) { return dk::select_lsb24(x, k); }
 SIM_API uint32_t sim_select_lsb(uint32_t x, uint32_t k) { return dk::select_lsb(x, k); }
 SIM_API uint32_t sim_card_power(uint32_t c, uint32_t trump, uint32_t follow) { return dk::card_power(c, trump, follow); }
+// the table-driven forms the playout kernels use (the same shared-memory image, built by lut_word / sel12_entry)
+SIM_API uint32_t sim_pick_msb_rank24_tab(uint32_t mask, uint32_t idx) { return dk::pick_msb_rank24_tab(mask, idx, reinterpret_cast<const uint64_t*>(card_lut() + dk::SEL12_LUT_BASE)); }
+SIM_API uint32_t sim_pick_msb_rank24_lut(uint32_t mask, uint32_t idx) { return dk::pick_msb_rank24_lut(mask, idx, card_lut()); }
+SIM_API uint32_t sim_pick_msb_rank24(uint32_t mask, uint32_t idx) { return dk::pick_msb_rank24(mask, idx); }
+SIM_API uint32_t sim_pow_lookup(uint32_t gt, uint32_t first_card, uint32_t c) {      // strength | eyes << 8 of card c in a trick led with first_card
+    const uint32_t trump = dk::trump_mask_for_game_type(gt);
+    return dk::pow_lookup(card_lut(), dk::pow_row(gt, first_card, dk::card_suit(first_card), trump), c);
+}
+SIM_API uint32_t sim_seg_lut(uint32_t win, uint32_t hit) { return reinterpret_cast<const uint8_t*>(card_lut() + dk::SEG_LUT_BASE)[16u * win + hit]; }
+SIM_API uint32_t sim_thr2_lut(uint32_t w, uint32_t re_low, uint32_t ko_low) { return card_lut()[dk::THR2_LUT_BASE + 64u * w + 8u * re_low + ko_low]; }
 SIM_API uint32_t sim_trump_mask(uint32_t gt) { return dk::trump_mask_for_game_type(gt); }
 SIM_API uint32_t sim_follow_mask(uint32_t c, uint32_t trump) { return dk::follow_mask(c, trump); }
 

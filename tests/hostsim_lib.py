@@ -59,7 +59,8 @@ def load():
         L.sim_fdo_score.argtypes = [u32, u32, u32, u32, u32, i32, vp]
         L.sim_fdo_eligible_nibble.restype = u32
         L.sim_fdo_eligible_nibble.argtypes = [vp, u32, u32, u32]
-        for n in ("sim_fdo_min_cards_to_call", "sim_fdo_allowed_call", "sim_select_lsb24", "sim_select_lsb", "sim_card_power", "sim_trump_mask", "sim_follow_mask"):
+        for n in ("sim_fdo_min_cards_to_call", "sim_fdo_allowed_call", "sim_select_lsb24", "sim_select_lsb", "sim_card_power", "sim_trump_mask", "sim_follow_mask",
+                  "sim_pick_msb_rank24_tab", "sim_pick_msb_rank24_lut", "sim_pick_msb_rank24", "sim_pow_lookup", "sim_seg_lut", "sim_thr2_lut"):
             getattr(L, n).restype = u32
         _lib = L
     return _lib

@@ -144,6 +144,42 @@ def test_device_byte_parallel_eligibility_matches_the_per_seat_comparison():
                         assert sim.sim_fdo_eligible_nibble(hostsim_lib.ptr(cards), thr_re, thr_ko, re) == want, (cmax, played, thr_re, thr_ko, re)
 
 
+def test_device_lookup_tables_match_the_closed_forms():
+    """The shared-memory tables of the playout kernels against the functions they replace:
+    rank select (12-bit table and 64-entry table vs the popcount binary search, which test_select_by_rank pins against the reference's
+    select_by_rank), card strength + eyes (vs card_power / the eyes table), call thresholds of both teams, caller of a segment."""
+    import numpy as np
+
+    sim = hostsim_lib.load()
+    prng = np.random.default_rng(5)
+    masks = [int(x) for x in prng.integers(1, 1 << 24, size=3000)] + [1, 1 << 23, (1 << 24) - 1, 0xFFF, 0xFFF000, 0x800001]
+    for m in masks:
+        if bin(m).count("1") > 12:                                  # a hand holds at most 12 card types
+            m &= int(prng.integers(1, 1 << 24)) | 1
+        for idx in range(bin(m).count("1")):
+            want = sim.sim_pick_msb_rank24(m, idx)
+            assert sim.sim_pick_msb_rank24_tab(m, idx) == want and sim.sim_pick_msb_rank24_lut(m, idx) == want, (hex(m), idx)
+            assert want == [b for b in range(23, -1, -1) if (m >> b) & 1][idx]
+    eyes = [0, 10, 2, 3, 4, 11]
+    for gt in range(9):
+        trump = sim.sim_trump_mask(gt)
+        for first in range(24):
+            follow = sim.sim_follow_mask(first, trump)
+            for c in range(24):
+                v = sim.sim_pow_lookup(gt, first, c)
+                assert v & 255 == sim.sim_card_power(c, trump, follow) and v >> 8 == eyes[c % 6], (gt, first, c)
+    for w in (0, 1, 2):
+        for re_low in range(7):
+            for ko_low in range(7):
+                v = sim.sim_thr2_lut(w, re_low, ko_low)
+                assert v & 255 == sim.sim_fdo_min_cards_to_call(re_low, ko_low, w) and v >> 8 == sim.sim_fdo_min_cards_to_call(ko_low, re_low, w)
+    for win in range(16):
+        seats = [d for d in range(4) if (win >> d) & 1]
+        for hit in range(1, 1 << len(seats)):
+            j = (hit & -hit).bit_length() - 1                       # the first eligible seat whose decision bit is set
+            assert sim.sim_seg_lut(win, hit) == (seats[j] | (j << 2)), (win, hit)
+
+
 def test_device_score_matches_oracle_exhaustively(orc):
     """Closed-form scoring (fdo_score) vs the literal stats.rs restatement over all calls x eyes x trick extremes x team sizes."""
     sim = hostsim_lib.load()
