@@ -169,12 +169,12 @@ static dk_status playout_launch(dk_ctx* ctx, int engine, uint32_t flags, size_t 
         dk::doko_playout_fresh_kernel<false><<<fgrid, dk::FDO_FRESH_THREADS, dk::FDO_FRESH_SMEM_BYTES, s>>>(rp, (uint64_t)n, points_out, steps_out, compact, nullptr, nullptr);
         return check_launch(ctx, "doko_playout_fresh_kernel");
     }
-    unsigned grid = (unsigned)((n + dk::STATE_THREADS - 1) / dk::STATE_THREADS);
+    unsigned grid = (unsigned)((n + dk::PLAYOUT_STATE_THREADS - 1) / dk::PLAYOUT_STATE_THREADS);
     if (engine == DK_FDO) {
-        if (with_ann) dk::playout_state_kernel<DK_FDO, true><<<grid, dk::STATE_THREADS, 0, s>>>(rp, (uint64_t)n, states, 1u, points_out, steps_out, compact);
-        else dk::playout_state_kernel<DK_FDO, false><<<grid, dk::STATE_THREADS, 0, s>>>(rp, (uint64_t)n, states, 1u, points_out, steps_out, compact);
+        if (with_ann) dk::playout_state_kernel<DK_FDO, true><<<grid, dk::PLAYOUT_STATE_THREADS, 0, s>>>(rp, (uint64_t)n, states, 1u, points_out, steps_out, compact);
+        else dk::playout_state_kernel<DK_FDO, false><<<grid, dk::PLAYOUT_STATE_THREADS, 0, s>>>(rp, (uint64_t)n, states, 1u, points_out, steps_out, compact);
     } else {
-        dk::playout_state_kernel<DK_DOKO, false><<<grid, dk::STATE_THREADS, 0, s>>>(rp, (uint64_t)n, states, 1u, points_out, steps_out, compact);
+        dk::playout_state_kernel<DK_DOKO, false><<<grid, dk::PLAYOUT_STATE_THREADS, 0, s>>>(rp, (uint64_t)n, states, 1u, points_out, steps_out, compact);
     }
     return check_launch(ctx, "playout_state_kernel");
 }

@@ -464,13 +464,18 @@ fdo_step_encode_kernel(RngParams rp, uint64_t n, dk_state* __restrict__ states, 
 
 // K2/K4 from stored states: McEnvState::random_rollout (rs-doko-mcts/src/env/envs/env_state_full_doko.rs:198-220) and the
 // with-announcement loop.  unit = first_id + (i / per_unit), unit_hi = i % per_unit when per_unit > 1 (leaf rollouts).
+// 256-thread blocks, each with the full table set (12-bit rank select included: a quarter of this kernel's instructions were the
+// two-level rank select, profiles/r01_playout_state_attribution.json).
+constexpr int PLAYOUT_STATE_THREADS = 256;
 template <int ENGINE, bool WITH_ANN>
-__global__ void __launch_bounds__(STATE_THREADS)
+__global__ void __launch_bounds__(PLAYOUT_STATE_THREADS)
 playout_state_kernel(RngParams rp, uint64_t n, const dk_state* __restrict__ states, uint32_t per_unit, void* __restrict__ points,
                      void* __restrict__ steps, bool compact) {
-    __shared__ uint32_t lut[CARD_LUT_WORDS];
-    stage_card_lut(lut);
-    uint64_t i = (uint64_t)blockIdx.x * STATE_THREADS + threadIdx.x;
+    __shared__ __align__(16) uint32_t lut[CARD_LUT_WORDS + SEL12_WORDS];
+    fill_card_lut(lut);
+    fill_sel12(lut);
+    __syncthreads();
+    uint64_t i = (uint64_t)blockIdx.x * PLAYOUT_STATE_THREADS + threadIdx.x;
     if (i >= n) return;
     uint64_t unit = per_unit > 1u ? i / per_unit : i;
     RngKey key = make_key(rp, unit, per_unit > 1u ? (uint32_t)(i % per_unit) : 0u, per_unit > 1u);
@@ -480,11 +485,11 @@ playout_state_kernel(RngParams rp, uint64_t n, const dk_state* __restrict__ stat
     uint32_t st = 0;
     if (ENGINE == DK_FDO) {
         FdoLive g; FdoResume rs;
-        if (fdo_state_to_live(s, g, rs)) { fdo_play_to_end<WITH_ANN, false>(g, key, &rs, lut); fdo_final_points(g, p); st = g.steps; }
+        if (fdo_state_to_live(s, g, rs)) { fdo_play_to_end<WITH_ANN, false, true>(g, key, &rs, lut); fdo_final_points(g, p); st = g.steps; }
         else { p[0] = s.points[0]; p[1] = s.points[1]; p[2] = s.points[2]; p[3] = s.points[3]; }
     } else {
         DokoLive g; DokoResume rs;
-        if (doko_state_to_live(s, g, rs)) { doko_play_to_end<false, false>(g, key, &rs, nullptr, lut); doko_final_points(g, p); st = g.steps; }
+        if (doko_state_to_live(s, g, rs)) { doko_play_to_end<false, false, true>(g, key, &rs, nullptr, lut); doko_final_points(g, p); st = g.steps; }
         else { p[0] = s.points[0]; p[1] = s.points[1]; p[2] = s.points[2]; p[3] = s.points[3]; }
     }
     store_result(points, steps, i, p, st, compact);
@@ -577,8 +582,9 @@ fdo_leaf_rollouts_kernel(RngParams rp, uint64_t n_leaves, uint32_t rollouts, con
     __shared__ FdoResume resume0;
     __shared__ int live_ok;
     __shared__ int red[4];
-    __shared__ uint32_t lut[CARD_LUT_WORDS];
+    __shared__ __align__(16) uint32_t lut[CARD_LUT_WORDS + (DET ? 0u : SEL12_WORDS)];   // without determinization: the 12-bit rank-select table too
     fill_card_lut(lut);
+    if (!DET) fill_sel12(lut);
     uint64_t i = blockIdx.x;
     if (i >= n_leaves) return;
     if (threadIdx.x < 8) reinterpret_cast<uint4*>(&leaf)[threadIdx.x] = __ldg(reinterpret_cast<const uint4*>(states + i) + threadIdx.x);
@@ -608,7 +614,7 @@ fdo_leaf_rollouts_kernel(RngParams rp, uint64_t n_leaves, uint32_t rollouts, con
             else { p[0] = s.points[0]; p[1] = s.points[1]; p[2] = s.points[2]; p[3] = s.points[3]; }
         } else if (live_ok) {
             FdoLive g = live0;
-            fdo_play_to_end<false, false>(g, key, &resume0, lut);
+            fdo_play_to_end<false, false, true>(g, key, &resume0, lut);
             fdo_final_points(g, p);
         } else { p[0] = leaf.points[0]; p[1] = leaf.points[1]; p[2] = leaf.points[2]; p[3] = leaf.points[3]; }
         acc[0] += p[0]; acc[1] += p[1]; acc[2] += p[2]; acc[3] += p[3];
