@@ -143,6 +143,9 @@ DK_HD void fdo_match_rule1(MatchState& m) {
 }
 // rule 2 (:115-145): a seat whose open slots equal its possible cards takes them all.
 DK_HD bool fdo_match_rule2(MatchState& m) {
+    // fast exit (the common case): if no seat qualifies now, none will — nothing is assigned in between
+    if (!((m.slots[0] > 0u && m.slots[0] == h2_len(m.possible[0])) || (m.slots[1] > 0u && m.slots[1] == h2_len(m.possible[1])) ||
+          (m.slots[2] > 0u && m.slots[2] == h2_len(m.possible[2])))) return false;
     bool changed = false;
 #pragma unroll
     for (uint32_t j = 0; j < 3u; ++j) {
@@ -159,6 +162,7 @@ DK_HD bool fdo_match_rule2(MatchState& m) {
 }
 // rule 3 (:147-172): a seat that must hold a ♣Q gets one.
 DK_HD bool fdo_match_rule3(MatchState& m) {
+    if (m.must_q == 0u) return false;                          // the common case
     bool changed = false;
 #pragma unroll
     for (uint32_t j = 0; j < 3u; ++j)
