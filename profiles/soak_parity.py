@@ -1,0 +1,59 @@
+#!/usr/bin/env python3
+"""Parity soak (B200): the fresh-game playout kernels against the CPU oracle, bit for bit, on many seeds — far more games than the test
+suite plays (rare paths: weddings that stay unsolved, counter calls, Black announcements, 12-card hands of one suit ...).
+
+  python profiles/soak_parity.py --seconds 60
+Every round draws a new (seed, first_id, epoch), plays 2^20 games on the GPU (rs-full-doko with announcements, rs-full-doko with the
+no-announcement policy, rs-doko) and on the oracle (all host threads), and compares points and step counts of every game."""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    import numpy as np
+    import torch
+
+    import master_doko_reinforcement_learning_b200 as pkg
+    import oracle_lib
+
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--seconds", type=float, default=60.0)
+    ap.add_argument("--games", type=int, default=1 << 20)
+    a = ap.parse_args()
+    dk = pkg.DokoCuda(0)
+    L = oracle_lib.load()
+    prng = np.random.default_rng(20261018)
+    t0 = time.time()
+    rounds, games, steps_total, mismatches = 0, 0, 0, 0
+    hist = {}
+    while time.time() - t0 < a.seconds:
+        seed = int(prng.integers(0, 1 << 62))
+        first_id = int(prng.integers(0, 1 << 40))
+        epoch = int(prng.integers(0, 1 << 20))
+        for engine, ann in ((pkg.DK_FDO, True), (pkg.DK_FDO, False), (pkg.DK_DOKO, False)):
+            pts, st = dk.playout(engine, a.games, dk.rng(seed, first_id, epoch), flags=pkg.DK_PLAYOUT_WITH_ANNOUNCEMENTS if ann else 0)
+            torch.cuda.synchronize()
+            ref = oracle_lib.playout_philox(L, engine, a.games, seed, first_id=first_id, epoch=epoch, with_announcements=ann)
+            gp, gs = pts.cpu().numpy(), st.cpu().numpy().astype(np.uint32)
+            bad = int((gp != ref["points"]).any(axis=1).sum() + (gs != ref["steps"]).sum())
+            mismatches += bad
+            games += a.games
+            steps_total += int(ref["steps"].sum())
+            if engine == pkg.DK_FDO and ann:
+                for k in (int(ref["steps"].min()), int(ref["steps"].max())):
+                    hist[k] = hist.get(k, 0) + 1
+        rounds += 1
+    print(json.dumps({"rounds": rounds, "games_compared": games, "game_steps_compared": steps_total, "mismatching_games": mismatches,
+                      "seconds": time.time() - t0, "extreme_step_counts_seen": sorted(hist)}))
+    sys.exit(1 if mismatches else 0)
+
+
+if __name__ == "__main__":
+    main()
