@@ -21,6 +21,8 @@ struct dk_ctx {
     uint64_t launches = 0;
     std::string last_error;
     int sm_count = 0, cc_major = 0, cc_minor = 0;
+    void* pimc_ws = nullptr;         // workspace of dk_pimc_evaluate (post-action playout states per determinization and legal action)
+    size_t pimc_ws_bytes = 0;
     bool fresh_smem_set = false;     // dynamic shared-memory opt-in of the fresh-game playout kernels done on this device
     size_t total_mem = 0;
     // scratch for the *_host entry points
@@ -117,6 +119,7 @@ dk_status dk_destroy(dk_ctx* ctx) {
     if (!ctx) return DK_ERR_INVALID_ARGUMENT;
     cudaSetDevice(ctx->device);
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);
+    if (ctx->pimc_ws) cudaFree(ctx->pimc_ws);
     for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -318,17 +321,41 @@ dk_status dk_pimc_evaluate(dk_ctx* ctx, size_t n_roots, size_t n_det, size_t n_r
     // unit_hi of rollout (d, r) is (first_sub + d) * n_rollouts + r: keep it inside 32 bits; int32 block sums: |points| < 128
     if (n_rollouts == 0 || n_rollouts > 0x1000000ull || n_det > 0xFFFFFFFFull ||
         ((uint64_t)rng->first_sub + n_det) * n_rollouts > 0xFFFFFFFFull) return DK_ERR_INVALID_ARGUMENT;
-    uint32_t dpb = (uint32_t)(dk::PIMC_THREADS / n_rollouts);
-    if (dpb < 1u) dpb = 1u;
-    if (dpb > (uint32_t)dk::PIMC_MAX_DPB) dpb = dk::PIMC_MAX_DPB;
-    if (dpb > n_det) dpb = (uint32_t)n_det;
-    uint64_t blocks_per_root = (n_det + dpb - 1) / dpb;
-    if (n_roots * blocks_per_root > 0x7FFFFFFFull) return DK_ERR_INVALID_ARGUMENT;
     DK_CUDA(ctx, cudaSetDevice(ctx->device));
-    dk::fdo_pimc_kernel<<<(unsigned)(n_roots * blocks_per_root), dk::PIMC_THREADS, 0, pick_stream(ctx, stream)>>>(
-        to_params(rng), (uint64_t)n_roots, (uint32_t)n_det, (uint32_t)n_rollouts, dpb, (uint32_t)blocks_per_root, states, visits_out,
-        (long long*)value_sum_out, status_out);
-    return check_launch(ctx, "fdo_pimc_kernel");
+    cudaStream_t s = pick_stream(ctx, stream);
+    // two kernels (kernels.cuh "N2 in two kernels"): prepare every (root, determinization) at full width into a workspace, then one thread
+    // per (root, determinization, rollout); the outputs are accumulated with atomics, so they are zeroed first.  Roots go in chunks that
+    // keep the workspace below 1 GiB.
+    const size_t per_root = n_det * (dk::PIMC_MAX_LEGAL * sizeof(dk::PimcEntry) + sizeof(uint64_t));
+    size_t chunk = ((size_t)1 << 30) / per_root;
+    if (chunk < 1) chunk = 1;
+    if (chunk > n_roots) chunk = n_roots;
+    if (ctx->pimc_ws_bytes < chunk * per_root) {
+        if (ctx->pimc_ws) { cudaFree(ctx->pimc_ws); ctx->pimc_ws = nullptr; ctx->pimc_ws_bytes = 0; }
+        DK_CUDA(ctx, cudaMalloc(&ctx->pimc_ws, chunk * per_root));
+        ctx->pimc_ws_bytes = chunk * per_root;
+    }
+    if (visits_out) DK_CUDA(ctx, cudaMemsetAsync(visits_out, 0, n_roots * n_det * dk::N_ACTIONS * sizeof(uint32_t), s));
+    if (value_sum_out) DK_CUDA(ctx, cudaMemsetAsync(value_sum_out, 0, n_roots * n_det * dk::N_ACTIONS * sizeof(int64_t), s));
+    const uint64_t prep_chunks = (n_det + dk::PIMC_PREP_THREADS - 1) / dk::PIMC_PREP_THREADS;
+    const uint64_t roll_blocks = (n_det * n_rollouts + dk::PIMC_ROLL_THREADS - 1) / dk::PIMC_ROLL_THREADS;
+    if (roll_blocks > 0x7FFFFFFFull) return DK_ERR_INVALID_ARGUMENT;
+    for (size_t r0 = 0; r0 < n_roots; r0 += chunk) {
+        const size_t nr = n_roots - r0 < chunk ? n_roots - r0 : chunk;
+        if (nr * prep_chunks > 0x7FFFFFFFull || nr * roll_blocks > 0x7FFFFFFFull) return DK_ERR_INVALID_ARGUMENT;
+        dk::PimcEntry* ws = (dk::PimcEntry*)ctx->pimc_ws;
+        uint64_t* masks = (uint64_t*)((char*)ctx->pimc_ws + chunk * n_det * dk::PIMC_MAX_LEGAL * sizeof(dk::PimcEntry));
+        dk::pimc_prepare_kernel<<<(unsigned)(nr * prep_chunks), dk::PIMC_PREP_THREADS, 0, s>>>(to_params(rng), (uint64_t)r0, (uint64_t)nr, (uint32_t)n_det, states, ws, masks,
+                                                                                           status_out);
+        dk_status st = check_launch(ctx, "pimc_prepare_kernel");
+        if (st != DK_OK) return st;
+        dk::pimc_rollout_kernel<<<(unsigned)(nr * roll_blocks), dk::PIMC_ROLL_THREADS, 0, s>>>(to_params(rng), (uint64_t)r0, (uint32_t)n_det, (uint32_t)n_rollouts,
+                                                                                           (uint32_t)roll_blocks, states, ws, masks, visits_out,
+                                                                                           (unsigned long long*)value_sum_out);
+        st = check_launch(ctx, "pimc_rollout_kernel");
+        if (st != DK_OK) return st;
+    }
+    return DK_OK;
 }
 
 dk_status dk_fuse(dk_ctx* ctx, int strategy, size_t n_roots, size_t n_rows, const uint32_t* visits, const uint8_t* status, const uint64_t* allowed,
@@ -336,9 +363,9 @@ dk_status dk_fuse(dk_ctx* ctx, int strategy, size_t n_roots, size_t n_rows, cons
     if (!ctx || !visits || !allowed || !action_out || (strategy != DK_FUSE_MAX_N && strategy != DK_FUSE_AVERAGE) || n_rows > 0xFFFFFFFFull)
         return DK_ERR_INVALID_ARGUMENT;
     if (n_roots == 0) return DK_OK;
+    if (n_roots > 0x7FFFFFFFull) return DK_ERR_INVALID_ARGUMENT;                // one block per root
     DK_CUDA(ctx, cudaSetDevice(ctx->device));
-    unsigned grid = (unsigned)((n_roots + dk::STATE_THREADS - 1) / dk::STATE_THREADS);
-    dk::fuse_kernel<<<grid, dk::STATE_THREADS, 0, pick_stream(ctx, stream)>>>((uint32_t)strategy, (uint64_t)n_roots, (uint32_t)n_rows, visits, status, allowed,
+    dk::fuse_kernel<<<(unsigned)n_roots, dk::FUSE_THREADS, 0, pick_stream(ctx, stream)>>>((uint32_t)strategy, (uint64_t)n_roots, (uint32_t)n_rows, visits, status, allowed,
                                                                              action_out, n_success_out);
     return check_launch(ctx, "fuse_kernel");
 }
@@ -347,9 +374,9 @@ dk_status dk_pimc_root_stats(dk_ctx* ctx, size_t n_roots, size_t n_rows, const u
                              int64_t* stats, int accumulate, dk_stream stream) {
     if (!ctx || !visits || !allowed || !stats || n_rows > 0xFFFFFFFFull) return DK_ERR_INVALID_ARGUMENT;
     if (n_roots == 0) return DK_OK;
+    if (n_roots > 0x7FFFFFFFull) return DK_ERR_INVALID_ARGUMENT;                // one block per root
     DK_CUDA(ctx, cudaSetDevice(ctx->device));
-    unsigned grid = (unsigned)((n_roots + dk::STATE_THREADS - 1) / dk::STATE_THREADS);
-    dk::root_stats_kernel<<<grid, dk::STATE_THREADS, 0, pick_stream(ctx, stream)>>>((uint64_t)n_roots, (uint32_t)n_rows, visits, status, allowed,
+    dk::root_stats_kernel<<<(unsigned)n_roots, dk::FUSE_THREADS, 0, pick_stream(ctx, stream)>>>((uint64_t)n_roots, (uint32_t)n_rows, visits, status, allowed,
                                                                                    (long long*)stats, accumulate);
     return check_launch(ctx, "root_stats_kernel");
 }

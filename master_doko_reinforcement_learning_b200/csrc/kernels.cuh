@@ -632,152 +632,202 @@ fdo_leaf_rollouts_kernel(RngParams rp, uint64_t n_leaves, uint32_t rollouts, con
 
 // N2: flat Monte-Carlo PIMC evaluator (the per-sample policy slot of DefaultImpiPolicy::execute,
 // rs-doko-py-bridge/src/compare_impi/compare_impi.rs:223-262, filled with "every legal action × R rollouts" instead of a UCT search).
-// One block = one root × PIMC_DPB determinizations: thread 0 builds the constraint tables once, thread j samples determinization j
-// (stream (root, d) — the dk_determinize stream), then the block's threads take the (d, r) pairs; each plays EVERY legal action of
-// the seat to move followed by a _no_announcement rollout on the stream (root, d·R + r) shared by all actions (common random
-// numbers), adds points[mover] to value_sum[d][a] and one visit to the best action (first among equals).  The action loop is
-// uniform across the block (the legal set of the mover does not depend on the hidden hands), so lanes stay in lock-step per action.
-#ifndef DK_PIMC_THREADS
-#define DK_PIMC_THREADS 128
-#endif
-constexpr int PIMC_THREADS = DK_PIMC_THREADS;
-constexpr int PIMC_MAX_DPB = 32;
-constexpr uint32_t PIMC_TAB = 96;    // (determinization, legal action) pairs per block whose post-action playout state is kept in shared memory
-#ifndef DK_PIMC_BLOCKS
-#define DK_PIMC_BLOCKS 6
-#endif
-__global__ void __launch_bounds__(PIMC_THREADS, DK_PIMC_BLOCKS)
-fdo_pimc_kernel(RngParams rp, uint64_t n_roots, uint32_t n_det, uint32_t n_rollouts, uint32_t dpb, uint32_t blocks_per_root,
-                const dk_state* __restrict__ states, uint32_t* __restrict__ visits_out, long long* __restrict__ value_out,
-                uint8_t* __restrict__ status_out) {
+// Determinization d of a root is sampled on the stream (root, d) — the dk_determinize stream; rollout r of it plays EVERY legal action
+// of the seat to move followed by a _no_announcement rollout on the stream (root, d·R + r) shared by all actions (common random
+// numbers), adds points[mover] to value_sum[d][a] and one visit to the best action (first among equals).
+// A first version did all of it in one kernel (block = root × a few determinizations): with few rollouts per determinization a block
+// spent most of its life in the prologue (one thread building the constraint tables, a handful sampling, the rest waiting) —
+// 2.7e9 rollouts/s at 64 x 32 against 8e9 for the bare rollout kernel.  The work is split so that every phase runs at full width:
+//   pimc_prepare_kernel   block = root x 64 determinizations, thread = determinization: sample (the dk_determinize stream), legal set,
+//                         and for every legal action the state after it in playout form → workspace entry ((root * n_det + d) * 12 + k)
+//   pimc_rollout_kernel   thread = (root, determinization, rollout): one _no_announcement rollout per legal action from the workspace
+//                         entries (common random numbers), integer sums / winner counts added to the outputs with atomics (order
+//                         independent, bit-reproducible)
+struct PimcEntry {
+    FdoLive g;
+    FdoResume rs;
+    signed char pts[4];      // final points when the action ends the game (live == 0)
+    uint32_t live;
+};
+constexpr uint32_t PIMC_MAX_LEGAL = 12u;        // <= 12 card types in a hand, 9 reservations, 2 announcement actions
+constexpr int PIMC_PREP_THREADS = 64;
+__global__ void __launch_bounds__(PIMC_PREP_THREADS)
+pimc_prepare_kernel(RngParams rp, uint64_t root0, uint64_t n_roots, uint32_t n_det, const dk_state* __restrict__ states, PimcEntry* __restrict__ ws,
+                    uint64_t* __restrict__ masks, uint8_t* __restrict__ status_out) {
     __shared__ MatchPrep prep;
-    __shared__ __align__(16) dk_state det_state[PIMC_MAX_DPB];
-    __shared__ int vsum[PIMC_MAX_DPB][N_ACTIONS];
-    __shared__ uint32_t wins[PIMC_MAX_DPB][N_ACTIONS];
-    __shared__ uint8_t det_status[PIMC_MAX_DPB];
+    __shared__ __align__(16) dk_state rootst_s;
+    const uint32_t chunks = (n_det + PIMC_PREP_THREADS - 1) / PIMC_PREP_THREADS;
+    const uint64_t rl = blockIdx.x / chunks;                                  // root inside this launch
+    const uint32_t d = (uint32_t)(blockIdx.x % chunks) * PIMC_PREP_THREADS + threadIdx.x;
+    const uint64_t root = root0 + rl;
+    if (threadIdx.x < 8) reinterpret_cast<uint4*>(&rootst_s)[threadIdx.x] = __ldg(reinterpret_cast<const uint4*>(states + root) + threadIdx.x);
+    __syncthreads();
+    if (threadIdx.x == 0) fdo_match_prepare(rootst_s, prep);
+    __syncthreads();
+    if (d >= n_det) return;
+    const bool finished = !prep.valid;                                        // finished root: no legal action, rows stay zero
+    alignas(16) dk_state s = rootst_s;
+    uint32_t st = 0;
+    if (!finished) {
+        RngKey key = make_key(rp, root, rp.first_sub + d, true);
+        uint64_t h[4];
+        uint8_t res[4];
+        st = fdo_match_sample(prep, key, h, res);
+        if (st == 0u) fdo_state_with_hands_and_reservations(s, h, res);
+    }
+    const uint64_t row = rl * n_det + d;
+    if (status_out) status_out[root * n_det + d] = (uint8_t)st;
+    const uint64_t m = (finished || st != 0u) ? 0ull : fdo_state_legal_mask<true>(s);
+    masks[row] = m;
+    uint32_t k = 0;
+    for (uint64_t mm = m; mm && k < PIMC_MAX_LEGAL; mm &= mm - 1ull, ++k) {
+        alignas(16) dk_state t = s;
+        fdo_state_apply<true>(t, ffs0ll(mm));
+        PimcEntry& e = ws[row * PIMC_MAX_LEGAL + k];
+        FdoLive g; FdoResume rs;
+        const bool lv = fdo_state_to_live<true>(t, g, rs);
+        e.g = g; e.rs = rs; e.live = lv ? 1u : 0u;
+        e.pts[0] = t.points[0]; e.pts[1] = t.points[1]; e.pts[2] = t.points[2]; e.pts[3] = t.points[3];
+    }
+}
+constexpr int PIMC_ROLL_THREADS = 128;
+__global__ void __launch_bounds__(PIMC_ROLL_THREADS, 6)
+pimc_rollout_kernel(RngParams rp, uint64_t root0, uint32_t n_det, uint32_t n_rollouts, uint32_t blocks_per_root, const dk_state* __restrict__ states,
+                    const PimcEntry* __restrict__ ws, const uint64_t* __restrict__ masks, uint32_t* __restrict__ visits_out,
+                    unsigned long long* __restrict__ value_out) {
     __shared__ uint32_t lut[CARD_LUT_WORDS];
-    // (determinization, legal action) table: the state after the action in playout form — the same for all rollouts of the pair, so it
-    // is built once per block instead of once per rollout (apply + record → playout bridge were a quarter of the kernel)
-    __shared__ FdoLive tab_g[PIMC_TAB];
-    __shared__ FdoResume tab_rs[PIMC_TAB];
-    __shared__ signed char tab_pts[PIMC_TAB][4];
-    __shared__ uint8_t tab_live[PIMC_TAB];
-    __shared__ int tab_bad;
-    const uint64_t root = blockIdx.x / blocks_per_root;
-    const uint32_t d0 = (uint32_t)(blockIdx.x % blocks_per_root) * dpb;
-    const uint32_t nd = min(dpb, n_det - d0);
     fill_card_lut(lut);
-    if (threadIdx.x < 8) reinterpret_cast<uint4*>(&det_state[0])[threadIdx.x] = __ldg(reinterpret_cast<const uint4*>(states + root) + threadIdx.x);
-    for (uint32_t k = threadIdx.x; k < nd * N_ACTIONS; k += PIMC_THREADS) { (&vsum[0][0])[k] = 0; (&wins[0][0])[k] = 0u; }
     __syncthreads();
-    if (threadIdx.x == 0) fdo_match_prepare(det_state[0], prep);
-    __syncthreads();
-    const bool finished = !prep.valid;   // finished root: no legal action, rows stay zero
-    alignas(16) dk_state rootst = det_state[0];
-    __syncthreads();
-    if (threadIdx.x < nd) {
-        uint32_t st = 0;
-        alignas(16) dk_state s = rootst;
-        if (!finished) {
-            RngKey key = make_key(rp, root, rp.first_sub + d0 + threadIdx.x, true);
-            uint64_t h[4];
-            uint8_t res[4];
-            st = fdo_match_sample(prep, key, h, res);
-            if (st == 0u) fdo_state_with_hands_and_reservations(s, h, res);
-        }
-        det_state[threadIdx.x] = s;
-        det_status[threadIdx.x] = (uint8_t)st;
+    const uint64_t rl = blockIdx.x / blocks_per_root, root = root0 + rl;
+    const uint32_t item = (uint32_t)(blockIdx.x % blocks_per_root) * PIMC_ROLL_THREADS + threadIdx.x;
+    const uint32_t n_items = n_det * n_rollouts;
+    const bool on = item < n_items;
+    const uint32_t d = on ? item / n_rollouts : 0u, r = on ? item - d * n_rollouts : 0u;
+    const uint64_t row = rl * n_det + d;
+    const uint64_t m = on ? masks[row] : 0ull;
+    const bool live = m != 0ull;
+    const unsigned active = __ballot_sync(0xFFFFFFFFu, live);
+    if (!live) return;
+    const uint32_t mover = (__ldg(&states[root].meta) >> 2) & 3u;
+    const unsigned peers = __match_any_sync(active, d);                       // lanes of this warp that roll out the same determinization
+    const bool leader = (uint32_t)(__ffs((int)peers) - 1) == (threadIdx.x & 31u);
+    const RngKey key = make_key(rp, root, (rp.first_sub + d) * n_rollouts + r, true);
+    const uint64_t out_row = (root * n_det + d) * N_ACTIONS;
+    int best_v = 0;
+    uint32_t best_a = ACTION_NONE, k = 0;
+    for (uint64_t mm = m; mm && k < PIMC_MAX_LEGAL; mm &= mm - 1ull, ++k) {
+        const uint32_t a = ffs0ll(mm);
+        const PimcEntry& e = ws[row * PIMC_MAX_LEGAL + k];
+        int32_t p[4];
+        if (e.live) { FdoLive g = e.g; fdo_play_to_end<false, false>(g, key, &e.rs, lut); fdo_final_points(g, p); }
+        else { p[0] = e.pts[0]; p[1] = e.pts[1]; p[2] = e.pts[2]; p[3] = e.pts[3]; }
+        const int v = (mover & 2u) ? ((mover & 1u) ? p[3] : p[2]) : ((mover & 1u) ? p[1] : p[0]);
+        const int tot = __reduce_add_sync(peers, v);
+        if (leader && value_out) atomicAdd(value_out + out_row + a, (unsigned long long)(long long)tot);
+        if (best_a == ACTION_NONE || v > best_v) { best_a = a; best_v = v; }   // first among equals
     }
-    __syncthreads();
-    const uint32_t mover = st_cur(rootst);
-    const uint32_t n_items = nd * n_rollouts;
-    // the legal set of the seat to move: its own hand and the public state do not depend on the sample (checked below: tab_bad)
-    const uint64_t m_root = finished ? 0ull : fdo_state_legal_mask<true>(det_state[0]);
-    const uint32_t n_legal = popcll(m_root);
-    const bool want_tab = nd * n_legal <= PIMC_TAB && n_legal > 0u;
-    if (threadIdx.x == 0) tab_bad = 0;
-    __syncthreads();
-    if (want_tab) {
-        for (uint32_t e = threadIdx.x; e < nd * n_legal; e += PIMC_THREADS) {
-            const uint32_t d = e / n_legal, k = e - d * n_legal;
-            if (fdo_state_legal_mask<true>(det_state[d]) != m_root) tab_bad = 1;
-            uint64_t mm = m_root;
-            for (uint32_t q = 0; q < k; ++q) mm &= mm - 1ull;
-            alignas(16) dk_state s = det_state[d];
-            fdo_state_apply<true>(s, ffs0ll(mm));
-            FdoLive g; FdoResume rs;
-            const bool lv = fdo_state_to_live<true>(s, g, rs);
-            tab_g[e] = g; tab_rs[e] = rs; tab_live[e] = lv ? 1 : 0;
-            tab_pts[e][0] = s.points[0]; tab_pts[e][1] = s.points[1]; tab_pts[e][2] = s.points[2]; tab_pts[e][3] = s.points[3];
-        }
+    if (visits_out && best_a != ACTION_NONE) {
+        const unsigned same = __match_any_sync(peers, best_a);                // peers that voted for the same action: one atomic for all
+        if ((uint32_t)(__ffs((int)same) - 1) == (threadIdx.x & 31u)) atomicAdd(visits_out + out_row + best_a, (uint32_t)__popc(same));
     }
-    __syncthreads();
-    const bool use_tab = want_tab && !tab_bad;
-    for (uint32_t base = 0; base < n_items; base += PIMC_THREADS) {
-        const uint32_t item = base + threadIdx.x;
-        const bool on = item < n_items;
-        const uint32_t dl = on ? item / n_rollouts : 0u, r = on ? item - dl * n_rollouts : 0u;
-        const bool live = on && !finished && det_status[dl] == 0u;
-        const unsigned active = __ballot_sync(0xFFFFFFFFu, live);
-        if (!live) continue;
-        const unsigned peers = __match_any_sync(active, dl);
-        const bool leader = (uint32_t)(__ffs((int)peers) - 1) == (threadIdx.x & 31u);
-        const RngKey key = make_key(rp, root, (rp.first_sub + d0 + dl) * n_rollouts + r, true);
-        int best_v = 0;
-        uint32_t best_a = ACTION_NONE;
-        // legal set of the determinized state: the mover's own hand and the public state do not depend on the sample, so this is the
-        // root's legal set and the loop is uniform across the block; peers (same dl) share it exactly in any case
-        uint32_t e = dl * n_legal;
-        for (uint64_t m = use_tab ? m_root : fdo_state_legal_mask<true>(det_state[dl]); m; m &= m - 1ull, ++e) {
-            const uint32_t a = ffs0ll(m);
-            int32_t p[4];
-            if (use_tab) {
-                if (tab_live[e]) { FdoLive g = tab_g[e]; fdo_play_to_end<false, false>(g, key, &tab_rs[e], lut); fdo_final_points(g, p); }
-                else { p[0] = tab_pts[e][0]; p[1] = tab_pts[e][1]; p[2] = tab_pts[e][2]; p[3] = tab_pts[e][3]; }
-            } else {                                                      // more (determinization, action) pairs than the table holds
-                alignas(16) dk_state s = det_state[dl];
-                fdo_state_apply<true>(s, a);                              // indexed form: the record stays in local memory (237 registers otherwise)
-                FdoLive g; FdoResume rs;
-                if (fdo_state_to_live<true>(s, g, rs)) { fdo_play_to_end<false, false>(g, key, &rs, lut); fdo_final_points(g, p); }
-                else { p[0] = s.points[0]; p[1] = s.points[1]; p[2] = s.points[2]; p[3] = s.points[3]; }
-            }
-            const int v = (mover & 2u) ? ((mover & 1u) ? p[3] : p[2]) : ((mover & 1u) ? p[1] : p[0]);
-            const int tot = __reduce_add_sync(peers, v);
-            if (leader) atomicAdd(&vsum[dl][a], tot);
-            if (best_a == ACTION_NONE || v > best_v) { best_a = a; best_v = v; }
-        }
-        if (best_a != ACTION_NONE) atomicAdd(&wins[dl][best_a], 1u);
-    }
-    __syncthreads();
-    const uint64_t row0 = root * n_det + d0;
-    for (uint32_t k = threadIdx.x; k < nd * N_ACTIONS; k += PIMC_THREADS) {
-        if (visits_out) visits_out[row0 * N_ACTIONS + k] = (&wins[0][0])[k];
-        if (value_out) value_out[row0 * N_ACTIONS + k] = (long long)(&vsum[0][0])[k];
-    }
-    if (status_out && threadIdx.x < nd) status_out[row0 + threadIdx.x] = det_status[threadIdx.x];
 }
 
-// Fuse per root (thread per root; the rows of one root are contiguous).
-__global__ void __launch_bounds__(STATE_THREADS)
+// Fuse per root: one block of 64 threads per root, rows staged 64 at a time in shared memory.
+//   MaxN     the rank of every (row, allowed action) pair is computed by its own thread and added to the action's integer rank sum
+//            (shared-memory atomics; integers, so the sums are those of the sequential fuse_max_n), thread 0 takes the first minimum
+//   Average  thread a owns action a and adds the rows' f32 quotients in ROW ORDER (the reference's accumulation order, bit for bit);
+//            the row totals come from the staging pass
+// The statistics kernel of the sharded decision (rank sums, visit sums, successful rows) uses the same staging.
+constexpr int FUSE_THREADS = 64;
+struct FuseStage {
+    uint32_t v[FUSE_THREADS][N_ACTIONS];     // 64 rows
+    unsigned long long tot[FUSE_THREADS];
+    uint8_t ok[FUSE_THREADS];
+};
+// loads rows [r0, r0 + 64) of the root (coalesced), their totals and success flags; returns the number of rows staged
+__device__ __forceinline__ uint32_t fuse_stage_rows(FuseStage& sm, const uint32_t* __restrict__ v, const uint8_t* __restrict__ st, uint32_t r0, uint32_t n_rows) {
+    const uint32_t cnt = min((uint32_t)FUSE_THREADS, n_rows - r0);
+    __syncthreads();                                                          // the previous chunk has been consumed
+    for (uint32_t e = threadIdx.x; e < cnt * N_ACTIONS; e += FUSE_THREADS) (&sm.v[0][0])[e] = v[(size_t)r0 * N_ACTIONS + e];
+    __syncthreads();
+    if (threadIdx.x < cnt) {
+        unsigned long long t = 0;
+        for (uint32_t a = 0; a < N_ACTIONS; ++a) t += sm.v[threadIdx.x][a];
+        sm.tot[threadIdx.x] = t;
+        sm.ok[threadIdx.x] = (!st || st[r0 + threadIdx.x] == 0u) ? 1 : 0;
+    }
+    __syncthreads();
+    return cnt;
+}
+__global__ void __launch_bounds__(FUSE_THREADS)
 fuse_kernel(uint32_t strategy, uint64_t n_roots, uint32_t n_det, const uint32_t* __restrict__ visits, const uint8_t* __restrict__ status,
             const uint64_t* __restrict__ allowed, uint8_t* __restrict__ action_out, uint32_t* __restrict__ n_ok_out) {
-    uint64_t i = (uint64_t)blockIdx.x * STATE_THREADS + threadIdx.x;
+    __shared__ FuseStage sm;
+    __shared__ uint32_t rank_sum[N_ACTIONS];
+    __shared__ float avg_sum[N_ACTIONS];
+    __shared__ uint32_t n_ok_s;
+    const uint64_t i = blockIdx.x;
     if (i >= n_roots) return;
     const uint32_t* v = visits + i * n_det * N_ACTIONS;
     const uint8_t* st = status ? status + i * n_det : nullptr;
-    uint32_t n_ok = 0;
-    uint32_t a = strategy == 0u ? fuse_max_n(v, st, n_det, allowed[i], &n_ok) : fuse_average(v, st, n_det, &n_ok);
-    action_out[i] = (uint8_t)(n_ok == 0u ? ACTION_NONE : a);
-    if (n_ok_out) n_ok_out[i] = n_ok;
+    const uint64_t al = allowed[i];
+    if (threadIdx.x < N_ACTIONS) { rank_sum[threadIdx.x] = 0u; avg_sum[threadIdx.x] = 0.0f; }
+    if (threadIdx.x == 0) n_ok_s = 0u;
+    float my_sum = 0.0f;                                                      // Average: thread a < 39 owns action a
+    for (uint32_t r0 = 0; r0 < n_det; r0 += FUSE_THREADS) {
+        const uint32_t cnt = fuse_stage_rows(sm, v, st, r0, n_det);
+        if (threadIdx.x < cnt && sm.ok[threadIdx.x]) atomicAdd(&n_ok_s, 1u);
+        if (strategy == 0u) {
+            for (uint32_t e = threadIdx.x; e < cnt * N_ACTIONS; e += FUSE_THREADS) {
+                const uint32_t r = e / N_ACTIONS, a = e - r * N_ACTIONS;
+                if (sm.ok[r] && ((al >> a) & 1ull)) atomicAdd(&rank_sum[a], fuse_rank(sm.v[r], al, a));
+            }
+        } else if (threadIdx.x < N_ACTIONS) {
+            for (uint32_t r = 0; r < cnt; ++r)
+                if (sm.ok[r]) my_sum = f32_add(my_sum, f32_div((float)sm.v[r][threadIdx.x], (float)sm.tot[r]));
+        }
+    }
+    if (strategy != 0u && threadIdx.x < N_ACTIONS) avg_sum[threadIdx.x] = my_sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t best = 0;
+        if (strategy == 0u) {
+            uint32_t best_sum = 0xFFFFFFFFu;
+            for (uint32_t a = 0; a < N_ACTIONS; ++a) {
+                const uint32_t sum = ((al >> a) & 1ull) ? rank_sum[a] : 0xFFFFFFFFu;   // not allowed ⇒ u32::MAX (:31-38)
+                if (a == 0u || sum < best_sum) { best = a; best_sum = sum; }           // min_by_key keeps the FIRST minimum (:65-70)
+            }
+        } else {
+            for (uint32_t a = 1; a < N_ACTIONS; ++a) if (!(avg_sum[best] > avg_sum[a])) best = a;   // LAST of equal maxima, NaN as Equal (:113-119)
+        }
+        action_out[i] = (uint8_t)(n_ok_s == 0u ? ACTION_NONE : best);
+        if (n_ok_out) n_ok_out[i] = n_ok_s;
+    }
 }
-__global__ void __launch_bounds__(STATE_THREADS)
+__global__ void __launch_bounds__(FUSE_THREADS)
 root_stats_kernel(uint64_t n_roots, uint32_t n_det, const uint32_t* __restrict__ visits, const uint8_t* __restrict__ status,
                   const uint64_t* __restrict__ allowed, long long* __restrict__ stats, int accumulate) {
-    uint64_t i = (uint64_t)blockIdx.x * STATE_THREADS + threadIdx.x;
+    __shared__ FuseStage sm;
+    __shared__ unsigned long long acc[ROOT_STATS];
+    const uint64_t i = blockIdx.x;
     if (i >= n_roots) return;
     long long* out = stats + i * ROOT_STATS;
-    if (!accumulate) for (uint32_t k = 0; k < ROOT_STATS; ++k) out[k] = 0;
-    root_stats_accumulate(visits + i * n_det * N_ACTIONS, status ? status + i * n_det : nullptr, n_det, allowed[i], out);
+    const uint32_t* v = visits + i * n_det * N_ACTIONS;
+    const uint8_t* st = status ? status + i * n_det : nullptr;
+    const uint64_t al = allowed[i];
+    for (uint32_t k = threadIdx.x; k < ROOT_STATS; k += FUSE_THREADS) acc[k] = 0ull;
+    for (uint32_t r0 = 0; r0 < n_det; r0 += FUSE_THREADS) {
+        const uint32_t cnt = fuse_stage_rows(sm, v, st, r0, n_det);
+        if (threadIdx.x < cnt && sm.ok[threadIdx.x]) atomicAdd(&acc[2u * N_ACTIONS], 1ull);
+        for (uint32_t e = threadIdx.x; e < cnt * N_ACTIONS; e += FUSE_THREADS) {
+            const uint32_t r = e / N_ACTIONS, a = e - r * N_ACTIONS;
+            if (!sm.ok[r]) continue;
+            if ((al >> a) & 1ull) atomicAdd(&acc[a], (unsigned long long)fuse_rank(sm.v[r], al, a));
+            atomicAdd(&acc[N_ACTIONS + a], (unsigned long long)sm.v[r][a]);
+        }
+    }
+    __syncthreads();
+    for (uint32_t k = threadIdx.x; k < ROOT_STATS; k += FUSE_THREADS) out[k] = (accumulate ? out[k] : 0ll) + (long long)acc[k];
 }
 __global__ void __launch_bounds__(STATE_THREADS)
 root_pick_kernel(uint32_t strategy, uint64_t n_roots, const long long* __restrict__ stats, const uint64_t* __restrict__ allowed, uint8_t* __restrict__ action_out) {
