@@ -94,8 +94,8 @@ def main():
     d_states = dk.new_games(pkg.DK_DOKO, n_info, dk.rng(SEED, 0, 0))
     for k in range(20):                                       # 4 reservations + 16 cards: lowest legal action each turn
         m = dk.legal_mask(pkg.DK_DOKO, d_states)
-        act = (torch.log2((m & -m).to(torch.float64)).to(torch.uint8))
-        dk.apply(pkg.DK_DOKO, d_states, act)
+        act = ((torch.log2((m & -m).to(torch.float64)) + 0.5).to(torch.uint8))
+        assert int(dk.apply(pkg.DK_DOKO, d_states, act).sum()) == 0
     S2 = 1024
 
     def k3d():

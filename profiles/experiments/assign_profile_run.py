@@ -9,8 +9,8 @@ n_info, S = 4096, 1024
 d_states = dk.new_games(pkg.DK_DOKO, n_info, dk.rng(SEED, 0, 0))
 for k in range(20):
     m = dk.legal_mask(pkg.DK_DOKO, d_states)
-    act = torch.log2((m & -m).to(torch.float64)).to(torch.uint8)
-    dk.apply(pkg.DK_DOKO, d_states, act)
+    act = (torch.log2((m & -m).to(torch.float64)) + 0.5).to(torch.uint8)
+    assert int(dk.apply(pkg.DK_DOKO, d_states, act).sum()) == 0
 hands = torch.empty((n_info, S, 4), dtype=torch.int64, device="cuda")
 res = torch.empty((n_info, S, 4), dtype=torch.uint8, device="cuda")
 status = torch.empty((n_info, S), dtype=torch.uint8, device="cuda")

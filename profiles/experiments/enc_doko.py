@@ -9,8 +9,8 @@ n = 1 << 22
 states = dk.new_games(pkg.DK_DOKO, n, dk.rng(SEED, 0, 0))
 for k in range(24):
     m = dk.legal_mask(pkg.DK_DOKO, states)
-    act = torch.log2((m & -m).to(torch.float64)).to(torch.uint8)
-    dk.apply(pkg.DK_DOKO, states, act)
+    act = (torch.log2((m & -m).to(torch.float64)) + 0.5).to(torch.uint8)
+    assert int(dk.apply(pkg.DK_DOKO, states, act).sum()) == 0
 out = {}
 for layout, L, name in ((pkg.DK_LAYOUT_DO110, 110, "do110"), (pkg.DK_LAYOUT_DO114, 114, "do114")):
     obs = torch.empty((n, L), dtype=torch.int64, device="cuda")
