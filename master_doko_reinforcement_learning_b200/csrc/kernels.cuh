@@ -236,8 +236,15 @@ legal_mask_kernel(uint64_t n, const dk_state* __restrict__ states, uint64_t* __r
     StateStage<STATE_THREADS>::get(stage, s);
     mask_out[i] = ENGINE == DK_FDO ? fdo_state_legal_mask(s) : doko_state_legal_mask(s);
 }
+// 8 blocks of 128 threads per SM (64 registers, 8 bytes of spill in the full-rules instance): 0.283 -> 0.243 ms per 2^22 records.
+// A two-buffer cp.async pipeline over tiles (bytes in flight independent of the resident thread count) was measured and is
+// SLOWER (0.294 ms): the kernel is bound by the transition's instructions, not by memory latency
+// (profiles/r01_apply_occupancy_experiment.txt).
+#ifndef DK_APPLY_BLOCKS
+#define DK_APPLY_BLOCKS 8
+#endif
 template <int ENGINE>
-__global__ void __launch_bounds__(STATE_THREADS)
+__global__ void __launch_bounds__(STATE_THREADS, DK_APPLY_BLOCKS)
 apply_kernel(uint64_t n, dk_state* __restrict__ states, const uint8_t* __restrict__ action, uint32_t flags, uint8_t* __restrict__ err_out) {
     __shared__ uint4 stage[STATE_THREADS * 8];
     const uint64_t first = (uint64_t)blockIdx.x * STATE_THREADS, i = first + threadIdx.x;
