@@ -2,7 +2,7 @@
 """Parity soak (B200): the fresh-game playout kernels against the CPU oracle, bit for bit, on many seeds — far more games than the test
 suite plays (rare paths: weddings that stay unsolved, counter calls, Black announcements, 12-card hands of one suit ...).
 
-  python profiles/soak_parity.py --seconds 60
+  python tests/soak_parity.py --seconds 60
 Every round draws a new (seed, first_id, epoch), plays 2^20 games on the GPU (rs-full-doko with announcements, rs-full-doko with the
 no-announcement policy, rs-doko) and on the oracle (all host threads), and compares points and step counts of every game."""
 import argparse
