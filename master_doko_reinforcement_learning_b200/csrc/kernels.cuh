@@ -290,6 +290,26 @@ __device__ __forceinline__ void write_rows(const uint8_t* __restrict__ tok, int 
         for (int i = lane; i < len; i += 32) dst[i] = (int64_t)src[i];
     }
 }
+// Dense rows (row_stride == LEN, 32-byte aligned output): two consecutive rows are a whole number of sectors (2 x 880 B = 55,
+// 2 x 912 B = 57 sectors) and a block's first row starts on a sector boundary, so a warp writes its rows in PAIRS as one
+// sector-aligned stream of 2 x LEN i64 in aligned 256-byte windows (same finding as for the 311-token rows below: windows that start
+// mid-sector, which every second row does in the row-by-row form, cost a fifth of the store bandwidth).
+template <int LEN>
+__device__ __forceinline__ void write_rows_dense(const uint8_t* __restrict__ tok, uint64_t first, uint64_t n, int64_t* __restrict__ out) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int q = warp; q < ENC_THREADS / 2; q += ENC_THREADS / 32) {
+        const uint64_t g = first + 2u * q;
+        if (g >= n) break;
+        const int valid = n - g >= 2u ? 2 * LEN : LEN;
+        const uint8_t* src = tok + 2 * q * ENC_ROW;
+        int64_t* dst = out + g * LEN;
+#pragma unroll
+        for (int p0 = 0; p0 < 2 * LEN; p0 += 32) {
+            const int p = p0 + lane;
+            if (p < valid) dst[p] = (int64_t)src[p >= LEN ? p + (ENC_ROW - LEN) : p];
+        }
+    }
+}
 // encode_state_pi staging: one packed word per slot (token 6 b | position 6 b | player 3 b | sub-position 4 b | team 2 b) plus the phase;
 // 63 words per game (odd pitch → conflict-free), then each warp expands whole rows channel by channel: every store instruction writes
 // 32 (resp. 30) consecutive i64 = 256 contiguous bytes.
@@ -434,7 +454,9 @@ encode_kernel(uint64_t n, const dk_state* __restrict__ states, int64_t* __restri
         doko_encode(s, LAYOUT == DK_LAYOUT_DO114, o);
     }
     __syncthreads();
-    write_rows(tok, LAYOUT == DK_LAYOUT_DO114 ? 114 : 110, first, n, out, row_stride);
+    constexpr int LEN = LAYOUT == DK_LAYOUT_DO114 ? 114 : 110;
+    if (row_stride == (size_t)LEN && !(reinterpret_cast<uintptr_t>(out) & 31u)) write_rows_dense<LEN>(tok, first, n, out);   // uniform branch
+    else write_rows(tok, LEN, first, n, out, row_stride);
 }
 
 // K5: one lock-step self-play env step + observation: legal mask → one draw (SITE_STEP word 0, unit = game id,

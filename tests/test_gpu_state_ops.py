@@ -191,3 +191,33 @@ def test_argument_errors_are_status_codes_not_crashes(dk):
     m = dk.legal_mask(1, states)
     torch.cuda.synchronize()
     assert int((m != 0).sum()) == 4
+
+
+@pytest.mark.parametrize("n", [1, 2, 131, 257])
+def test_doko_encode_dense_pairs_ragged_strided_unaligned(dk, orc, n):
+    """rs-doko rows are written in sector-aligned PAIRS when the output is dense and 32-byte aligned: odd counts (last pair half
+    empty), padded strides and unaligned outputs (row-by-row path) must all give the oracle's rows."""
+    import torch
+
+    import master_doko_reinforcement_learning_b200 as pkg
+
+    states = dk.new_games(0, n, dk.rng(SEED, 900, 1))
+    objs = [Doko.new_game_philox(orc, SEED, 900 + i, 1) for i in range(n)]
+    for k in range(4 + 13):                                   # reservations + 13 cards: lowest legal action
+        acts = np.zeros(n, dtype=np.uint8)
+        for i, o in enumerate(objs):
+            m = int(o.allowed())
+            acts[i] = (m & -m).bit_length() - 1
+            o.play(int(acts[i]))
+        assert int(dk.apply(0, states, torch.from_numpy(acts).cuda()).sum()) == 0
+    for lay, with_res, length in ((pkg.DK_LAYOUT_DO110, False, 110), (pkg.DK_LAYOUT_DO114, True, 114)):
+        ref = np.stack([o.encode(with_res) for o in objs])
+        dense = dk.encode(lay, states)
+        assert dense.shape == (n, length) and np.array_equal(dense.cpu().numpy(), ref)
+        padded = torch.full((n, length + 7), -1, dtype=torch.int64, device="cuda")
+        dk.encode(lay, states, out=padded, row_stride=length + 7)
+        assert np.array_equal(padded[:, :length].cpu().numpy(), ref) and bool((padded[:, length:] == -1).all())
+        flat = torch.full((n * length + 3,), -1, dtype=torch.int64, device="cuda")
+        shifted = flat[1:1 + n * length].view(n, length)        # 8-byte aligned only
+        dk.encode(lay, states, out=shifted)
+        assert np.array_equal(shifted.cpu().numpy(), ref) and int(flat[0]) == -1 and bool((flat[1 + n * length:] == -1).all())
