@@ -513,7 +513,8 @@ dk_status dk_pack_replay_records(dk_ctx* ctx, size_t n_rows, const int64_t* stat
     if (!ctx || !states || !value || !policy || !out || ((uintptr_t)out & 3u)) return DK_ERR_INVALID_ARGUMENT;
     if (n_rows == 0) return DK_OK;
     DK_CUDA(ctx, cudaSetDevice(ctx->device));
-    const bool aligned16 = ((uintptr_t)out & 15u) == 0u;
+    // 16-byte stores and TMA bulk copies need 16-byte aligned buffers; anything else goes word by word
+    const bool aligned16 = (((uintptr_t)out | (uintptr_t)states | (uintptr_t)value | (uintptr_t)policy) & 15u) == 0u;
     unsigned long long want = aligned16 ? (n_rows + 3ull) / 4ull : ((unsigned long long)n_rows * dk::REPLAY_WORDS + dk::REPLAY_THREADS - 1) / dk::REPLAY_THREADS;
     unsigned long long cap = (unsigned long long)ctx->sm_count * 32ull;
     unsigned grid = (unsigned)(want < cap ? (want ? want : 1ull) : cap);

@@ -254,35 +254,81 @@ __device__ __forceinline__ uint32_t replay_word(unsigned long long r, uint32_t w
     if (w < 632u) return w == 630u ? 39u : 0u;
     return __float_as_uint(__ldg(policy + r * 39u + (w - 632u)));
 }
+// Groups of four records: the TMA engine brings the group's source words into shared memory — three bulk copies (cp.async.bulk:
+// 4 observation rows = 9952 B, 4 value rows = 64 B, 4 policy rows = 624 B; all 16-byte multiples at 16-byte aligned addresses)
+// that complete on an mbarrier, two staging buffers so the next group is in flight while the current one is written.  The record
+// image is the same for every group, so each thread computes ONCE where in the staging buffer the twelve words of its three
+// 16-byte output chunks come from (the six length words of a record are four constant slots behind the data); the loop body is
+// twelve shared-memory loads and three aligned 16-byte stores — no global loads on the LSU path at all.
+// History (2^21 rows, profiles/r01_n4_bench.json): every chunk from two or three overlapping 8-byte global loads 2.35 ms; records
+// assembled in shared memory by 4-byte cp.async (LDGSTS) copies 2.24 ms — ncu: 84 LDGSTS warp instructions per group at 8 cycles
+// each saturate the MIO queue (mio_throttle 11.4 warps per issue), 40 % excess L2->L1 sectors from sector-misaligned 128-byte requests.
+constexpr uint32_t REPLAY_STAGE_WORDS = 2664u;               // 2488 observation + 16 value + 156 policy + 4 constants (311, 0, 4, 39)
+__device__ __forceinline__ uint32_t replay_source_slot(uint32_t q) {      // word q of the four-record image -> staging slot
+    const uint32_t r = q / REPLAY_WORDS, w = q - r * REPLAY_WORDS;
+    if (w < 2u) return w == 0u ? 2660u : 2661u;
+    if (w < 624u) return r * 622u + (w - 2u);
+    if (w < 626u) return w == 624u ? 2662u : 2661u;
+    if (w < 630u) return 2488u + 4u * r + (w - 626u);
+    if (w < 632u) return w == 630u ? 2663u : 2661u;
+    return 2504u + 39u * r + (w - 632u);
+}
+__device__ __forceinline__ void replay_tma_fetch(unsigned long long g, uint32_t stage, uint32_t bar, const long long* __restrict__ states,
+                                                 const float* __restrict__ value, const float* __restrict__ policy) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(9952u + 64u + 624u) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(stage), "l"(states + g * 4ull * 311ull), "r"(9952u), "r"(bar) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(stage + 9952u), "l"(value + g * 16ull), "r"(64u), "r"(bar) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(stage + 10016u), "l"(policy + g * 156ull), "r"(624u), "r"(bar) : "memory");
+}
+__device__ __forceinline__ bool replay_mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0u;
+}
 __global__ void __launch_bounds__(REPLAY_THREADS)
 pack_replay_records_kernel(unsigned long long n_rows, const long long* __restrict__ states, const float* __restrict__ value,
                            const float* __restrict__ policy, uint32_t* __restrict__ out, bool aligned16) {
+    __shared__ __align__(128) uint32_t stage[2][REPLAY_STAGE_WORDS];
+    __shared__ __align__(8) unsigned long long full[2];
     const unsigned long long n_groups = aligned16 ? n_rows / 4ull : 0ull;
-    for (unsigned long long g = blockIdx.x; g < n_groups; g += gridDim.x) {
-        uint4* dst = reinterpret_cast<uint4*>(out + g * 4ull * REPLAY_WORDS);
-        for (uint32_t e = threadIdx.x; e < REPLAY_WORDS; e += REPLAY_THREADS) {
-            const uint32_t q0 = 4u * e, r0 = q0 / REPLAY_WORDS, w0 = q0 - r0 * REPLAY_WORDS;
-            uint4 o;
-            if (w0 >= 2u && w0 + 3u < 624u) {
-                // all four words are observation halves of one record (93 % of the stores): 16 bytes copied from 8-byte aligned source
-                const long long* src = states + (g * 4ull + r0) * 311u + ((w0 - 2u) >> 1);
-                if (!(w0 & 1u)) {
-                    const unsigned long long a = (unsigned long long)__ldg(src), b = (unsigned long long)__ldg(src + 1);
-                    o = make_uint4((uint32_t)a, (uint32_t)(a >> 32), (uint32_t)b, (uint32_t)(b >> 32));
-                } else {
-                    const unsigned long long a = (unsigned long long)__ldg(src), b = (unsigned long long)__ldg(src + 1), c = (unsigned long long)__ldg(src + 2);
-                    o = make_uint4((uint32_t)(a >> 32), (uint32_t)b, (uint32_t)(b >> 32), (uint32_t)c);
-                }
-            } else {
-                uint32_t v[4];
+    if (blockIdx.x < n_groups) {
+        const uint32_t st0 = (uint32_t)__cvta_generic_to_shared(stage[0]), st1 = (uint32_t)__cvta_generic_to_shared(stage[1]);
+        const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(&full[0]), bar1 = (uint32_t)__cvta_generic_to_shared(&full[1]);
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar1) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        if (threadIdx.x < 8u) {                                  // the constant slots of both buffers
+            const uint32_t k = threadIdx.x & 3u;
+            stage[threadIdx.x >> 2][2660u + k] = k == 0u ? 311u : (k == 1u ? 0u : (k == 2u ? 4u : 39u));
+        }
+        uint32_t slot[3][4];
 #pragma unroll
-                for (uint32_t k = 0; k < 4u; ++k) {
-                    const uint32_t q = q0 + k, r = q / REPLAY_WORDS, w = q - r * REPLAY_WORDS;
-                    v[k] = replay_word(g * 4ull + r, w, states, value, policy);
-                }
-                o = make_uint4(v[0], v[1], v[2], v[3]);
+        for (uint32_t c = 0; c < 3u; ++c) {
+            const uint32_t e = min(threadIdx.x + c * REPLAY_THREADS, REPLAY_WORDS - 1u);
+#pragma unroll
+            for (uint32_t k = 0; k < 4u; ++k) slot[c][k] = replay_source_slot(4u * e + k);
+        }
+        __syncthreads();                                         // barriers initialised, constants written
+        unsigned long long g = blockIdx.x;
+        if (threadIdx.x == 0) replay_tma_fetch(g, st0, bar0, states, value, policy);
+        for (uint32_t it = 0; g < n_groups; g += gridDim.x, ++it) {
+            const uint32_t b = it & 1u, parity = (it >> 1) & 1u;
+            __syncthreads();                                     // nobody still reads the other buffer (previous iteration)
+            const unsigned long long next = g + gridDim.x;
+            if (threadIdx.x == 0 && next < n_groups) replay_tma_fetch(next, b ? st0 : st1, b ? bar0 : bar1, states, value, policy);
+            while (!replay_mbar_try_wait(b ? bar1 : bar0, parity)) {}
+            const uint32_t* __restrict__ src = stage[b];
+            uint4* dst = reinterpret_cast<uint4*>(out + g * 4ull * REPLAY_WORDS);
+#pragma unroll
+            for (uint32_t c = 0; c < 3u; ++c) {
+                const uint32_t e = threadIdx.x + c * REPLAY_THREADS;
+                if (e < REPLAY_WORDS) dst[e] = make_uint4(src[slot[c][0]], src[slot[c][1]], src[slot[c][2]], src[slot[c][3]]);
             }
-            dst[e] = o;
         }
     }
     // tail rows (and everything when the output is not 16-byte aligned): one word per thread
