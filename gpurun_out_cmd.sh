@@ -1,4 +1,10 @@
 set -x
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_replay_record.py tests/test_gpu_selfplay.py -m gpu -x -q > gpurun_out/pytest_replay.log 2>&1; tail -15 gpurun_out/pytest_replay.log
-timeout 300 python profiles/experiments/n4_bench.py > gpurun_out/n4_bench3.txt 2>&1; tail -1 gpurun_out/n4_bench3.txt
+timeout 600 python -m pytest tests/test_gpu_state_ops.py tests/test_gpu_selfplay.py tests/test_gpu_uct.py -m gpu -x -q > gpurun_out/pytest_tma.log 2>&1; tail -15 gpurun_out/pytest_tma.log
+: > gpurun_out/state_ops_tma.txt
+for v in tma notma tma notma; do
+  if [ $v = notma ]; then export DOKO_CUDA_NO_TMA=1; else unset DOKO_CUDA_NO_TMA; fi
+  echo "variant=$v" >> gpurun_out/state_ops_tma.txt
+  timeout 300 python profiles/experiments/state_ops_bw.py >> gpurun_out/state_ops_tma.txt 2>&1
+done
+cat gpurun_out/state_ops_tma.txt | cut -c1-420

@@ -1,5 +1,6 @@
 // cabi.cu — the extern "C" boundary of libdoko_cuda.so (include/doko_cuda.h).
 // No torch types, no CPU fallback: every compute entry point launches sm_100a kernels or fails with a status code.
+#include <cuda.h>   // CUtensorMap and its enums only: the encoder is fetched with cudaGetDriverEntryPoint, libcuda is not linked
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 
@@ -21,6 +22,7 @@ struct dk_ctx {
     uint64_t launches = 0;
     std::string last_error;
     int sm_count = 0, cc_major = 0, cc_minor = 0;
+    void* tmap_encode = nullptr;     // cuTensorMapEncodeTiled
     void* pimc_ws = nullptr;         // workspace of dk_pimc_evaluate (post-action playout states per determinization and legal action)
     size_t pimc_ws_bytes = 0;
     bool fresh_smem_set = false;     // dynamic shared-memory opt-in of the fresh-game playout kernels done on this device
@@ -58,6 +60,28 @@ dk_status fail(dk_ctx* ctx, dk_status st, const std::string& msg) {
     } while (0)
 
 cudaStream_t pick_stream(dk_ctx* ctx, dk_stream s) { return s ? (cudaStream_t)s : ctx->stream; }
+
+// Tensor map of a record array ([n][128] bytes, tiles of up to 128 records, 128-byte swizzle) for the TMA kernels.  False when the
+// driver entry point is missing or refuses the array (then the callers use their cooperative-copy kernels).
+typedef CUresult (*dk_tmap_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                      const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+bool state_tensor_map(dk_ctx* ctx, const dk_state* states, size_t n, CUtensorMap* out) {
+    if (getenv("DOKO_CUDA_NO_TMA") || ((uintptr_t)states & 15u) || n >= (1ull << 31)) return false;
+    if (!ctx->tmap_encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn) {
+            cudaGetLastError();
+            return false;
+        }
+        ctx->tmap_encode = fn;
+    }
+    const cuuint64_t dims[2] = {128u, (cuuint64_t)n}, strides[1] = {128u};
+    const cuuint32_t box[2] = {128u, (cuuint32_t)(n < (size_t)dk::STATE_THREADS ? n : (size_t)dk::STATE_THREADS)}, elem[2] = {1u, 1u};
+    return ((dk_tmap_encode_fn)ctx->tmap_encode)(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<dk_state*>(states), dims, strides, box, elem,
+                                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 
 dk::RngParams to_params(const dk_rng* r) {
     dk::RngParams p;
@@ -226,6 +250,12 @@ dk_status dk_legal_mask(dk_ctx* ctx, int engine, size_t n, const dk_state* state
     if (n == 0) return DK_OK;
     DK_CUDA(ctx, cudaSetDevice(ctx->device));
     unsigned grid = (unsigned)((n + dk::STATE_THREADS - 1) / dk::STATE_THREADS);
+    CUtensorMap tmap;
+    if (state_tensor_map(ctx, states, n, &tmap)) {
+        if (engine == DK_FDO) dk::legal_mask_tma_kernel<DK_FDO><<<grid, dk::STATE_THREADS, 0, pick_stream(ctx, stream)>>>(tmap, (uint64_t)n, mask_out);
+        else dk::legal_mask_tma_kernel<DK_DOKO><<<grid, dk::STATE_THREADS, 0, pick_stream(ctx, stream)>>>(tmap, (uint64_t)n, mask_out);
+        return check_launch(ctx, "legal_mask_tma_kernel");
+    }
     if (engine == DK_FDO) dk::legal_mask_kernel<DK_FDO><<<grid, dk::STATE_THREADS, 0, pick_stream(ctx, stream)>>>((uint64_t)n, states, mask_out);
     else dk::legal_mask_kernel<DK_DOKO><<<grid, dk::STATE_THREADS, 0, pick_stream(ctx, stream)>>>((uint64_t)n, states, mask_out);
     return check_launch(ctx, "legal_mask_kernel");
@@ -236,6 +266,12 @@ dk_status dk_apply(dk_ctx* ctx, int engine, size_t n, dk_state* states, const ui
     if (n == 0) return DK_OK;
     DK_CUDA(ctx, cudaSetDevice(ctx->device));
     unsigned grid = (unsigned)((n + dk::STATE_THREADS - 1) / dk::STATE_THREADS);
+    CUtensorMap tmap;
+    if (state_tensor_map(ctx, states, n, &tmap)) {
+        if (engine == DK_FDO) dk::apply_tma_kernel<DK_FDO><<<grid, dk::STATE_THREADS, 0, pick_stream(ctx, stream)>>>(tmap, (uint64_t)n, action_idx, flags, err_out);
+        else dk::apply_tma_kernel<DK_DOKO><<<grid, dk::STATE_THREADS, 0, pick_stream(ctx, stream)>>>(tmap, (uint64_t)n, action_idx, flags, err_out);
+        return check_launch(ctx, "apply_tma_kernel");
+    }
     if (engine == DK_FDO) dk::apply_kernel<DK_FDO><<<grid, dk::STATE_THREADS, 0, pick_stream(ctx, stream)>>>((uint64_t)n, states, action_idx, flags, err_out);
     else dk::apply_kernel<DK_DOKO><<<grid, dk::STATE_THREADS, 0, pick_stream(ctx, stream)>>>((uint64_t)n, states, action_idx, flags, err_out);
     return check_launch(ctx, "apply_kernel");

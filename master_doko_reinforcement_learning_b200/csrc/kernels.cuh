@@ -1,5 +1,6 @@
 // kernels.cuh — __global__ entry points (sm_100a).  One thread = one game / sample / rollout.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <utility>
@@ -257,6 +258,72 @@ apply_kernel(uint64_t n, dk_state* __restrict__ states, const uint8_t* __restric
         if (err_out) err_out[i] = (uint8_t)err;
     }
     StateStage<STATE_THREADS>::store(states, first, n, stage);
+}
+// ---- record tiles through the TMA engine -------------------------------------------------------------------------------------
+// The record array is a [n][128 B] tensor; a tile of 128 records is moved by ONE cp.async.bulk.tensor instruction in each
+// direction.  The 128-byte swizzle mode of the tensor map places 16-byte chunk j of record t at t*8 + (j ^ (t & 7)) — exactly
+// the layout StateStage builds by hand — so the per-thread get / put stay conflict-free, and the 16 global + 16 shared-memory
+// instructions per thread of the cooperative copy disappear from the LSU / MIO path (what limited the record packer as well,
+// selfplay_kernels.cuh).  Rows past n are clipped by the engine (zero-filled on load, dropped on store).
+struct TmaTile {
+    static __device__ __forceinline__ uint32_t saddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+    static __device__ __forceinline__ void init(unsigned long long* bar) {          // one thread, before a __syncthreads
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(saddr(bar)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    static __device__ __forceinline__ void load(const CUtensorMap* tmap, uint4* stage, unsigned long long* bar, uint64_t first, uint32_t bytes) {   // one thread
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(saddr(bar)), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                     ::"r"(saddr(stage)), "l"(tmap), "r"(0), "r"((int)first), "r"(saddr(bar)) : "memory");
+    }
+    static __device__ __forceinline__ void wait(unsigned long long* bar, uint32_t parity) {                                                      // all threads
+        uint32_t ok = 0;
+        while (!ok)
+            asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(saddr(bar)), "r"(parity) : "memory");
+    }
+    static __device__ __forceinline__ void publish() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }    // writers, before the __syncthreads
+    static __device__ __forceinline__ void store(const CUtensorMap* tmap, const uint4* stage, uint64_t first) {                                   // one thread, after it
+        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(tmap), "r"(0), "r"((int)first), "r"(saddr(stage)) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");                // the block's shared memory must outlive the engine's read
+    }
+};
+template <int ENGINE>
+__global__ void __launch_bounds__(STATE_THREADS, DK_APPLY_BLOCKS)
+apply_tma_kernel(const __grid_constant__ CUtensorMap tmap, uint64_t n, const uint8_t* __restrict__ action, uint32_t flags, uint8_t* __restrict__ err_out) {
+    __shared__ __align__(1024) uint4 stage[STATE_THREADS * 8];
+    __shared__ __align__(8) unsigned long long bar;
+    const uint64_t first = (uint64_t)blockIdx.x * STATE_THREADS, i = first + threadIdx.x;
+    if (threadIdx.x == 0) TmaTile::init(&bar);
+    __syncthreads();
+    if (threadIdx.x == 0) TmaTile::load(&tmap, stage, &bar, first, (uint32_t)min((uint64_t)STATE_THREADS, n) * 128u);
+    const uint32_t a = i < n ? action[i] : 0u;
+    TmaTile::wait(&bar, 0u);
+    if (i < n) {
+        alignas(16) dk_state s;
+        StateStage<STATE_THREADS>::get(stage, s);
+        uint32_t err = ENGINE == DK_FDO ? fdo_state_apply_az(s, a, (flags & DK_APPLY_SKIP_SINGLE) != 0) : doko_state_apply(s, a);
+        if (!err) StateStage<STATE_THREADS>::put(stage, s);              // an illegal action leaves the record as it was
+        if (err_out) err_out[i] = (uint8_t)err;
+    }
+    TmaTile::publish();
+    __syncthreads();
+    if (threadIdx.x == 0) TmaTile::store(&tmap, stage, first);
+}
+template <int ENGINE>
+__global__ void __launch_bounds__(STATE_THREADS)
+legal_mask_tma_kernel(const __grid_constant__ CUtensorMap tmap, uint64_t n, uint64_t* __restrict__ mask_out) {
+    __shared__ __align__(1024) uint4 stage[STATE_THREADS * 8];
+    __shared__ __align__(8) unsigned long long bar;
+    const uint64_t first = (uint64_t)blockIdx.x * STATE_THREADS, i = first + threadIdx.x;
+    if (threadIdx.x == 0) TmaTile::init(&bar);
+    __syncthreads();
+    if (threadIdx.x == 0) TmaTile::load(&tmap, stage, &bar, first, (uint32_t)min((uint64_t)STATE_THREADS, n) * 128u);
+    TmaTile::wait(&bar, 0u);
+    if (i >= n) return;
+    alignas(16) dk_state s;
+    StateStage<STATE_THREADS>::get(stage, s);
+    mask_out[i] = ENGINE == DK_FDO ? fdo_state_legal_mask(s) : doko_state_legal_mask(s);
 }
 __global__ void __launch_bounds__(STATE_THREADS)
 terminal_kernel(uint64_t n, const dk_state* __restrict__ states, uint8_t* __restrict__ done_out, int4* __restrict__ points_out) {
