@@ -1,10 +1,11 @@
 set -x
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_state_ops.py tests/test_gpu_selfplay.py tests/test_gpu_uct.py -m gpu -x -q > gpurun_out/pytest_tma.log 2>&1; tail -15 gpurun_out/pytest_tma.log
-: > gpurun_out/state_ops_tma.txt
-for v in tma notma tma notma; do
-  if [ $v = notma ]; then export DOKO_CUDA_NO_TMA=1; else unset DOKO_CUDA_NO_TMA; fi
-  echo "variant=$v" >> gpurun_out/state_ops_tma.txt
-  timeout 300 python profiles/experiments/state_ops_bw.py >> gpurun_out/state_ops_tma.txt 2>&1
+DOKO_CUDA_APPLY_PIPE=1 timeout 600 python -m pytest tests/test_gpu_state_ops.py -m gpu -x -q > gpurun_out/pytest_pipe.log 2>&1; tail -5 gpurun_out/pytest_pipe.log
+: > gpurun_out/apply_tma_pipe.txt
+for mb in 4 5 6; do
+  export DOKO_CUDA_LIB=$PWD/profiles/experiments/libs/libdoko_applypipe$mb.so
+  echo "lib=pipe$mb" >> gpurun_out/apply_tma_pipe.txt
+  DOKO_CUDA_APPLY_PIPE=1 timeout 300 python profiles/experiments/state_ops_bw.py >> gpurun_out/apply_tma_pipe.txt 2>&1
 done
-cat gpurun_out/state_ops_tma.txt | cut -c1-420
+echo "lib=nopipe" >> gpurun_out/apply_tma_pipe.txt
+timeout 300 python profiles/experiments/state_ops_bw.py >> gpurun_out/apply_tma_pipe.txt 2>&1
