@@ -1,11 +1,7 @@
 set -x
 mkdir -p gpurun_out
-DOKO_CUDA_APPLY_PIPE=1 timeout 600 python -m pytest tests/test_gpu_state_ops.py -m gpu -x -q > gpurun_out/pytest_pipe.log 2>&1; tail -5 gpurun_out/pytest_pipe.log
-: > gpurun_out/apply_tma_pipe.txt
-for mb in 4 5 6; do
-  export DOKO_CUDA_LIB=$PWD/profiles/experiments/libs/libdoko_applypipe$mb.so
-  echo "lib=pipe$mb" >> gpurun_out/apply_tma_pipe.txt
-  DOKO_CUDA_APPLY_PIPE=1 timeout 300 python profiles/experiments/state_ops_bw.py >> gpurun_out/apply_tma_pipe.txt 2>&1
-done
-echo "lib=nopipe" >> gpurun_out/apply_tma_pipe.txt
-timeout 300 python profiles/experiments/state_ops_bw.py >> gpurun_out/apply_tma_pipe.txt 2>&1
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; tail -2 gpurun_out/pytest_gpu.log
+python -c 'import __graft_entry__ as g; g.smoke()' > gpurun_out/smoke.log 2>&1; tail -1 gpurun_out/smoke.log
+timeout 600 python profiles/sanitize_smoke.py > gpurun_out/sanitize_plain.log 2>&1; tail -2 gpurun_out/sanitize_plain.log
+python profiles/experiments/state_ops_bw.py > gpurun_out/state_ops_bw.txt 2>&1; tail -1 gpurun_out/state_ops_bw.txt
+python profiles/bench_kernels.py > gpurun_out/kernels_v40.json 2> gpurun_out/kernels_v40.err; tail -c 300 gpurun_out/kernels_v40.err
