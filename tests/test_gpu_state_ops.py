@@ -221,3 +221,45 @@ def test_doko_encode_dense_pairs_ragged_strided_unaligned(dk, orc, n):
         shifted = flat[1:1 + n * length].view(n, length)        # 8-byte aligned only
         dk.encode(lay, states, out=shifted)
         assert np.array_equal(shifted.cpu().numpy(), ref) and int(flat[0]) == -1 and bool((flat[1 + n * length:] == -1).all())
+
+
+@pytest.mark.parametrize("engine", [0, 1])
+def test_tma_tiles_equal_cooperative_copies(dk, engine):
+    """dk_legal_mask / dk_apply move record tiles with TMA tensor copies; DOKO_CUDA_NO_TMA=1 selects the cooperative-copy kernels.
+    Both must give identical masks, error flags and records at every step of 100 003 games (ragged last tile) played to the end
+    with random legal actions, illegal actions (finished games, deliberately wrong indices) included."""
+    import os
+
+    import torch
+
+    n = 100_003
+    a_states = dk.new_games(engine, n, dk.rng(SEED, 77, 9))
+    b_states = a_states.clone()
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    try:
+        for step in range(400):
+            os.environ.pop("DOKO_CUDA_NO_TMA", None)
+            m_a = dk.legal_mask(engine, a_states)
+            os.environ["DOKO_CUDA_NO_TMA"] = "1"
+            m_b = dk.legal_mask(engine, b_states)
+            assert torch.equal(m_a, m_b), f"masks differ at step {step}"
+            if int((m_a != 0).sum()) == 0:
+                break
+            # a random legal action per game: the r-th set bit of the mask; every 17th game (rotating) gets action 38 - that (mostly illegal)
+            bits = ((m_a.unsqueeze(1) >> torch.arange(39, device="cuda")) & 1).to(torch.int32)            # [n,39]
+            cnt = bits.sum(1).clamp(min=1)
+            r = (torch.rand(n, device="cuda", generator=gen) * cnt).to(torch.int32).clamp(max=cnt - 1)
+            act = ((bits.cumsum(1) > r.unsqueeze(1)) & (bits != 0)).to(torch.int32).argmax(1).to(torch.uint8)
+            act[step % 17::17] = 38 - act[step % 17::17]
+            os.environ.pop("DOKO_CUDA_NO_TMA", None)
+            e_a = dk.apply(engine, a_states, act)
+            os.environ["DOKO_CUDA_NO_TMA"] = "1"
+            e_b = dk.apply(engine, b_states, act)
+            assert torch.equal(e_a, e_b), f"error flags differ at step {step}"
+            assert torch.equal(a_states, b_states), f"records differ at step {step}"
+        else:
+            raise AssertionError("games did not finish")
+    finally:
+        os.environ.pop("DOKO_CUDA_NO_TMA", None)
+    done, _ = dk.terminal(engine, a_states)
+    assert int(done.sum()) == n
