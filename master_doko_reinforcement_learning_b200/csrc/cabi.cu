@@ -317,13 +317,19 @@ dk_status dk_determinize(dk_ctx* ctx, int engine, size_t n_info, size_t samples_
     if (n_info == 0 || samples_per_info == 0) return DK_OK;
     if (samples_per_info > 0xFFFFFFFFull || n_info > 0x7FFFFFFFull) return DK_ERR_INVALID_ARGUMENT;
     DK_CUDA(ctx, cudaSetDevice(ctx->device));
+    // Blocks per info-state: enough blocks for about 16 waves of 8 resident blocks per SM, at most one block per 128 samples.
+    const uint64_t per_info_max = (samples_per_info + dk::MATCH_THREADS - 1) / dk::MATCH_THREADS, want = (uint64_t)ctx->sm_count * 128u;
+    uint64_t splits = (want + n_info - 1) / n_info;
+    if (splits > per_info_max) splits = per_info_max;
+    if (splits < 1 || getenv("DOKO_CUDA_NO_SPLIT")) splits = 1;
+    const unsigned grid = (unsigned)(n_info * splits);            // n_info <= 2^31 - 1 and splits > 1 only while n_info * splits <= want + n_info
     if (engine == DK_DOKO) {
-        dk::doko_assign_kernel<<<(unsigned)n_info, dk::MATCH_THREADS, 0, pick_stream(ctx, stream)>>>(to_params(rng), (uint64_t)n_info, (uint32_t)samples_per_info,
-                                                                                               states, hands_out, reservations_out, status_out);
+        dk::doko_assign_kernel<<<grid, dk::MATCH_THREADS, 0, pick_stream(ctx, stream)>>>(to_params(rng), (uint64_t)n_info, (uint32_t)samples_per_info, (uint32_t)splits,
+                                                                                   states, hands_out, reservations_out, status_out);
         return check_launch(ctx, "doko_assign_kernel");
     }
-    dk::fdo_determinize_kernel<<<(unsigned)n_info, dk::MATCH_THREADS, 0, pick_stream(ctx, stream)>>>(to_params(rng), (uint64_t)n_info, (uint32_t)samples_per_info,
-                                                                                                   states, hands_out, reservations_out, status_out);
+    dk::fdo_determinize_kernel<<<grid, dk::MATCH_THREADS, 0, pick_stream(ctx, stream)>>>(to_params(rng), (uint64_t)n_info, (uint32_t)samples_per_info, (uint32_t)splits,
+                                                                                       states, hands_out, reservations_out, status_out);
     return check_launch(ctx, "fdo_determinize_kernel");
 }
 

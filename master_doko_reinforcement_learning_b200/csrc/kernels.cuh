@@ -597,10 +597,13 @@ playout_state_kernel(RngParams rp, uint64_t n, const dk_state* __restrict__ stat
 // HBM per sample: 32 B hands + 4 B reservations + 1 B status written; 128 B read per info-state.
 constexpr int MATCH_THREADS = 128;
 __global__ void __launch_bounds__(MATCH_THREADS)
-fdo_determinize_kernel(RngParams rp, uint64_t n_info, uint32_t samples, const dk_state* __restrict__ states, uint64_t* __restrict__ hands_out,
+fdo_determinize_kernel(RngParams rp, uint64_t n_info, uint32_t samples, uint32_t splits, const dk_state* __restrict__ states, uint64_t* __restrict__ hands_out,
                        uint8_t* __restrict__ res_out, uint8_t* __restrict__ status_out) {
     __shared__ MatchPrep prep;
-    uint64_t i = blockIdx.x;
+    // `splits` blocks share one info-state (sample smp belongs to block smp / MATCH_THREADS % splits): a single decision's 4096 samples
+    // spread over 32 SMs instead of one, and small batches do not end in a mostly empty last wave.  Sample ids, hence results, do not change.
+    const uint64_t i = blockIdx.x / splits;
+    const uint32_t part = blockIdx.x - (uint32_t)i * splits;
     if (i >= n_info) return;
     if (threadIdx.x == 0) {
         alignas(16) dk_state s;
@@ -608,7 +611,7 @@ fdo_determinize_kernel(RngParams rp, uint64_t n_info, uint32_t samples, const dk
         fdo_match_prepare(s, prep);
     }
     __syncthreads();
-    for (uint32_t smp = threadIdx.x; smp < samples; smp += MATCH_THREADS) {
+    for (uint32_t smp = part * MATCH_THREADS + threadIdx.x; smp < samples; smp += splits * MATCH_THREADS) {
         RngKey key = make_key(rp, i, rp.first_sub + smp, true);
         uint64_t h[4];
         uint8_t r[4];
@@ -628,11 +631,12 @@ fdo_determinize_kernel(RngParams rp, uint64_t n_info, uint32_t samples, const dk
 // K3 (rs-doko): sample_assignment (rs-doko-assignment/src/assignment.rs:493-581).  Same block = info-state / thread = sample shape.
 // reservations_out repeats the real reservations by absolute seat (the reference only replaces the hands).
 __global__ void __launch_bounds__(MATCH_THREADS)
-doko_assign_kernel(RngParams rp, uint64_t n_info, uint32_t samples, const dk_state* __restrict__ states, uint64_t* __restrict__ hands_out,
+doko_assign_kernel(RngParams rp, uint64_t n_info, uint32_t samples, uint32_t splits, const dk_state* __restrict__ states, uint64_t* __restrict__ hands_out,
                    uint8_t* __restrict__ res_out, uint8_t* __restrict__ status_out) {
     __shared__ AssignPrep prep;
     __shared__ uint32_t res_word;
-    uint64_t i = blockIdx.x;
+    const uint64_t i = blockIdx.x / splits;                        // `splits` blocks per info-state, see fdo_determinize_kernel
+    const uint32_t part = blockIdx.x - (uint32_t)i * splits;
     if (i >= n_info) return;
     if (threadIdx.x == 0) {
         alignas(16) dk_state s;
@@ -643,7 +647,7 @@ doko_assign_kernel(RngParams rp, uint64_t n_info, uint32_t samples, const dk_sta
         res_word = r;
     }
     __syncthreads();
-    for (uint32_t smp = threadIdx.x; smp < samples; smp += MATCH_THREADS) {
+    for (uint32_t smp = part * MATCH_THREADS + threadIdx.x; smp < samples; smp += splits * MATCH_THREADS) {
         RngKey key = make_key(rp, i, rp.first_sub + smp, true);
         uint64_t h[4];
         uint32_t st = doko_assign_sample(prep, key, h);
