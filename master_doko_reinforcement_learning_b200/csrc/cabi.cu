@@ -339,8 +339,15 @@ dk_status dk_leaf_rollouts(dk_ctx* ctx, size_t n_leaves, size_t rollouts_per_lea
     if (n_leaves == 0) return DK_OK;
     if (rollouts_per_leaf > 0x1000000ull || n_leaves > 0x7FFFFFFFull) return DK_ERR_INVALID_ARGUMENT;   // int32 block sums: |points| < 128
     DK_CUDA(ctx, cudaSetDevice(ctx->device));
-    if (determinize) dk::fdo_leaf_rollouts_kernel<true><<<(unsigned)n_leaves, dk::MATCH_THREADS, 0, pick_stream(ctx, stream)>>>(to_params(rng), (uint64_t)n_leaves, (uint32_t)rollouts_per_leaf, states, (long long*)point_sum_out);
-    else dk::fdo_leaf_rollouts_kernel<false><<<(unsigned)n_leaves, dk::MATCH_THREADS, 0, pick_stream(ctx, stream)>>>(to_params(rng), (uint64_t)n_leaves, (uint32_t)rollouts_per_leaf, states, (long long*)point_sum_out);
+    // Fewer leaves than one wave of blocks: several blocks per leaf (at most one per 128 rollouts), sums combined by integer atomics.
+    const uint64_t per_leaf_max = (rollouts_per_leaf + dk::MATCH_THREADS - 1) / dk::MATCH_THREADS, wave = (uint64_t)ctx->sm_count * DK_LEAF_BLOCKS;
+    uint64_t splits = wave / n_leaves;
+    if (splits > per_leaf_max) splits = per_leaf_max;
+    if (splits < 1 || getenv("DOKO_CUDA_NO_SPLIT")) splits = 1;
+    const unsigned grid = (unsigned)(n_leaves * splits);
+    if (splits > 1) DK_CUDA(ctx, cudaMemsetAsync(point_sum_out, 0, n_leaves * 4 * sizeof(int64_t), pick_stream(ctx, stream)));
+    if (determinize) dk::fdo_leaf_rollouts_kernel<true><<<grid, dk::MATCH_THREADS, 0, pick_stream(ctx, stream)>>>(to_params(rng), (uint64_t)n_leaves, (uint32_t)rollouts_per_leaf, (uint32_t)splits, states, (long long*)point_sum_out);
+    else dk::fdo_leaf_rollouts_kernel<false><<<grid, dk::MATCH_THREADS, 0, pick_stream(ctx, stream)>>>(to_params(rng), (uint64_t)n_leaves, (uint32_t)rollouts_per_leaf, (uint32_t)splits, states, (long long*)point_sum_out);
     return check_launch(ctx, "fdo_leaf_rollouts_kernel");
 }
 

@@ -675,7 +675,7 @@ template <bool DET>
 #define DK_LEAF_BLOCKS 7
 #endif
 __global__ void __launch_bounds__(MATCH_THREADS, DET ? DK_LEAF_DET_BLOCKS : DK_LEAF_BLOCKS)
-fdo_leaf_rollouts_kernel(RngParams rp, uint64_t n_leaves, uint32_t rollouts, const dk_state* __restrict__ states, long long* __restrict__ point_sum) {
+fdo_leaf_rollouts_kernel(RngParams rp, uint64_t n_leaves, uint32_t rollouts, uint32_t splits, const dk_state* __restrict__ states, long long* __restrict__ point_sum) {
     __shared__ MatchPrep prep;
     __shared__ __align__(16) dk_state leaf;
     __shared__ FdoLive live0;
@@ -685,7 +685,10 @@ fdo_leaf_rollouts_kernel(RngParams rp, uint64_t n_leaves, uint32_t rollouts, con
     __shared__ __align__(16) uint32_t lut[CARD_LUT_WORDS + (DET ? 0u : SEL12_WORDS)];   // without determinization: the 12-bit rank-select table too
     fill_card_lut(lut);
     if (!DET) fill_sel12(lut);
-    uint64_t i = blockIdx.x;
+    // `splits` blocks share one leaf when there are fewer leaves than one wave of blocks (rollout r belongs to block
+    // r / MATCH_THREADS % splits); their integer sums meet in point_sum by atomics (zeroed by the host), so the result does not change.
+    const uint64_t i = blockIdx.x / splits;
+    const uint32_t part = blockIdx.x - (uint32_t)i * splits;
     if (i >= n_leaves) return;
     if (threadIdx.x < 8) reinterpret_cast<uint4*>(&leaf)[threadIdx.x] = __ldg(reinterpret_cast<const uint4*>(states + i) + threadIdx.x);
     if (threadIdx.x < 4) red[threadIdx.x] = 0;
@@ -696,7 +699,7 @@ fdo_leaf_rollouts_kernel(RngParams rp, uint64_t n_leaves, uint32_t rollouts, con
     }
     __syncthreads();
     int acc[4] = {0, 0, 0, 0};
-    for (uint32_t r = threadIdx.x; r < rollouts; r += MATCH_THREADS) {
+    for (uint32_t r = part * MATCH_THREADS + threadIdx.x; r < rollouts; r += splits * MATCH_THREADS) {
         RngKey key = make_key(rp, i, rp.first_sub + r, true);
         int32_t p[4];
         if (DET) {
@@ -727,7 +730,10 @@ fdo_leaf_rollouts_kernel(RngParams rp, uint64_t n_leaves, uint32_t rollouts, con
         if ((threadIdx.x & 31) == 0) atomicAdd(&red[q], v);
     }
     __syncthreads();
-    if (threadIdx.x < 4) point_sum[4 * i + threadIdx.x] = (long long)red[threadIdx.x];
+    if (threadIdx.x < 4) {
+        if (splits == 1u) point_sum[4 * i + threadIdx.x] = (long long)red[threadIdx.x];
+        else atomicAdd(reinterpret_cast<unsigned long long*>(point_sum) + 4 * i + threadIdx.x, (unsigned long long)(long long)red[threadIdx.x]);
+    }
 }
 
 // N2: flat Monte-Carlo PIMC evaluator (the per-sample policy slot of DefaultImpiPolicy::execute,
