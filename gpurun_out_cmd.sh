@@ -1,5 +1,4 @@
 set -x
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_matching.py tests/test_gpu_pimc.py tests/test_gpu_full_size.py tests/test_gpu_playout.py -m gpu -x -q > gpurun_out/pytest_split.log 2>&1; tail -5 gpurun_out/pytest_split.log
-echo split > gpurun_out/k4_sizes.txt; timeout 600 python profiles/experiments/k4_sizes.py >> gpurun_out/k4_sizes.txt 2>&1
-echo nosplit >> gpurun_out/k4_sizes.txt; DOKO_CUDA_NO_SPLIT=1 timeout 600 python profiles/experiments/k4_sizes.py >> gpurun_out/k4_sizes.txt 2>&1
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/multigpu_check.py > gpurun_out/multigpu_check_2gpu.txt 2>&1; tail -6 gpurun_out/multigpu_check_2gpu.txt
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 5 --warmup 3 > gpurun_out/bench_v15_2gpu.json 2> gpurun_out/bench_v15_2gpu.err; tail -c 300 gpurun_out/bench_v15_2gpu.json
