@@ -1,4 +1,4 @@
 set -x
 mkdir -p gpurun_out
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/multigpu_check.py > gpurun_out/multigpu_check_2gpu.txt 2>&1; tail -6 gpurun_out/multigpu_check_2gpu.txt
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 5 --warmup 3 > gpurun_out/bench_v15_2gpu.json 2> gpurun_out/bench_v15_2gpu.err; tail -c 300 gpurun_out/bench_v15_2gpu.json
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:'legal_mask_tma|apply_tma' --launch-skip 4 -c 2 -o gpurun_out/prof_stateops_tma -f python profiles/experiments/state_ops_bw.py > gpurun_out/ncu_stateops.log 2>&1; tail -2 gpurun_out/ncu_stateops.log
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:pack_replay --launch-skip 2 -c 1 -o gpurun_out/prof_packer_v3 -f python profiles/experiments/n4_bench.py > gpurun_out/ncu_packer3.log 2>&1; tail -2 gpurun_out/ncu_packer3.log
