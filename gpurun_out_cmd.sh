@@ -1,3 +1,8 @@
 set -x
 mkdir -p gpurun_out
-timeout 400 ncu --set full --clock-control none --import-source on -k regex:'apply_tma' --launch-skip 3 -c 1 -o gpurun_out/prof_apply_tma -f python profiles/experiments/state_ops_bw.py > gpurun_out/ncu_apply.log 2>&1; tail -2 gpurun_out/ncu_apply.log
+: > gpurun_out/apply_idx.txt
+for mb in 8 10 12 default; do
+  if [ $mb = default ]; then unset DOKO_CUDA_LIB; else export DOKO_CUDA_LIB=$PWD/profiles/experiments/libs/libdoko_applyidx$mb.so; fi
+  echo "lib=idx$mb" >> gpurun_out/apply_idx.txt
+  timeout 300 python profiles/experiments/state_ops_bw.py >> gpurun_out/apply_idx.txt 2>&1
+done

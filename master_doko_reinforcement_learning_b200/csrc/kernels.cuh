@@ -241,6 +241,9 @@ legal_mask_kernel(uint64_t n, const dk_state* __restrict__ states, uint64_t* __r
 // A two-buffer cp.async pipeline over tiles (bytes in flight independent of the resident thread count) was measured and is
 // SLOWER (0.294 ms): the kernel is bound by the transition's instructions, not by memory latency
 // (profiles/r01_apply_occupancy_experiment.txt).
+#ifndef DK_APPLY_IDX
+#define DK_APPLY_IDX false
+#endif
 #ifndef DK_APPLY_BLOCKS
 #define DK_APPLY_BLOCKS 8
 #endif
@@ -302,7 +305,7 @@ apply_tma_kernel(const __grid_constant__ CUtensorMap tmap, uint64_t n, const uin
     if (i < n) {
         alignas(16) dk_state s;
         StateStage<STATE_THREADS>::get(stage, s);
-        uint32_t err = ENGINE == DK_FDO ? fdo_state_apply_az(s, a, (flags & DK_APPLY_SKIP_SINGLE) != 0) : doko_state_apply(s, a);
+        uint32_t err = ENGINE == DK_FDO ? fdo_state_apply_az<DK_APPLY_IDX>(s, a, (flags & DK_APPLY_SKIP_SINGLE) != 0) : doko_state_apply(s, a);
         if (!err) StateStage<STATE_THREADS>::put(stage, s);              // an illegal action leaves the record as it was
         if (err_out) err_out[i] = (uint8_t)err;
     }
