@@ -1,8 +1,4 @@
 set -x
 mkdir -p gpurun_out
-: > gpurun_out/apply_idx.txt
-for mb in 8 10 12 default; do
-  if [ $mb = default ]; then unset DOKO_CUDA_LIB; else export DOKO_CUDA_LIB=$PWD/profiles/experiments/libs/libdoko_applyidx$mb.so; fi
-  echo "lib=idx$mb" >> gpurun_out/apply_idx.txt
-  timeout 300 python profiles/experiments/state_ops_bw.py >> gpurun_out/apply_idx.txt 2>&1
-done
+timeout 600 python -m pytest tests/test_gpu_playout.py -m gpu -x -q > gpurun_out/pytest_host.log 2>&1; tail -3 gpurun_out/pytest_host.log
+python bench.py > gpurun_out/bench_v16.json 2> gpurun_out/bench_v16.err; tail -c 200 gpurun_out/bench_v16.err

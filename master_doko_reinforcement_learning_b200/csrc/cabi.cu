@@ -31,6 +31,8 @@ struct dk_ctx {
     void* d_scratch = nullptr;
     size_t d_scratch_bytes = 0;
     cudaStream_t copy_stream = nullptr;
+    cudaStream_t stream2 = nullptr;  // second compute stream of the *_host entry points (chunk kernels alternate, so a chunk's last wave overlaps the next chunk)
+    cudaEvent_t h2d_done = nullptr;
     std::vector<cudaEvent_t> events;
     // NCCL (loaded lazily)
     // ln(N) table of the UCT search (host libm values, see uct.cuh)
@@ -146,6 +148,8 @@ dk_status dk_destroy(dk_ctx* ctx) {
     if (ctx->pimc_ws) cudaFree(ctx->pimc_ws);
     for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+    if (ctx->h2d_done) cudaEventDestroy(ctx->h2d_done);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return DK_OK;
@@ -683,11 +687,17 @@ static dk_status playout_host_impl(dk_ctx* ctx, int engine, uint32_t flags, size
     dk_status st = ensure_scratch(ctx, b_states + b_pts + b_steps);
     if (st != DK_OK) return st;
     if (!ctx->copy_stream) DK_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    if (!ctx->stream2) DK_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+    if (!ctx->h2d_done) DK_CUDA(ctx, cudaEventCreateWithFlags(&ctx->h2d_done, cudaEventDisableTiming));
     char* base = (char*)ctx->d_scratch;
     dk_state* d_states = states_host ? (dk_state*)base : nullptr;
     char* d_pts = base + b_states;
     char* d_steps = base + b_states + b_pts;
-    if (states_host) DK_CUDA(ctx, cudaMemcpyAsync(d_states, states_host, b_states, cudaMemcpyHostToDevice, ctx->stream));
+    if (states_host) {
+        DK_CUDA(ctx, cudaMemcpyAsync(d_states, states_host, b_states, cudaMemcpyHostToDevice, ctx->stream));
+        DK_CUDA(ctx, cudaEventRecord(ctx->h2d_done, ctx->stream));
+        DK_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->h2d_done, 0));
+    }
     // Chunks of 2^21 games so that the copy of chunk c overlaps the kernel of chunk c + 1; the last 2^21 games are cut into halves down
     // to 2^18, because the copy of the final chunk is the one transfer nothing overlaps.
     const size_t CH = (size_t)1 << 21, CH_MIN = (size_t)1 << 18;
@@ -711,9 +721,11 @@ static dk_status playout_host_impl(dk_ctx* ctx, int engine, uint32_t flags, size
         const size_t cnt = sizes[c];
         dk::RngParams rc = rp;
         rc.first_id = rp.first_id + off;
-        st = playout_launch(ctx, engine, flags, cnt, d_states ? d_states + off : nullptr, rc, d_pts + off * pb, d_steps + off * sb, compact, ctx->stream);
+        // chunk kernels alternate between two streams: the blocks of chunk c + 1 fill the SMs that the last wave of chunk c leaves idle
+        cudaStream_t cs = (c & 1u) ? ctx->stream2 : ctx->stream;
+        st = playout_launch(ctx, engine, flags, cnt, d_states ? d_states + off : nullptr, rc, d_pts + off * pb, d_steps + off * sb, compact, cs);
         if (st != DK_OK) return st;
-        DK_CUDA(ctx, cudaEventRecord(ctx->events[c], ctx->stream));
+        DK_CUDA(ctx, cudaEventRecord(ctx->events[c], cs));
         DK_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->events[c], 0));
         if (points_out_host) DK_CUDA(ctx, cudaMemcpyAsync((char*)points_out_host + off * pb, d_pts + off * pb, cnt * pb, cudaMemcpyDeviceToHost, ctx->copy_stream));
         if (steps_out_host) DK_CUDA(ctx, cudaMemcpyAsync((char*)steps_out_host + off * sb, d_steps + off * sb, cnt * sb, cudaMemcpyDeviceToHost, ctx->copy_stream));
@@ -721,6 +733,7 @@ static dk_status playout_host_impl(dk_ctx* ctx, int engine, uint32_t flags, size
     }
     DK_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
     DK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    DK_CUDA(ctx, cudaStreamSynchronize(ctx->stream2));
     return DK_OK;
 }
 
