@@ -236,6 +236,11 @@ dk_status dk_new_games(dk_ctx* ctx, int engine, size_t n, const dk_rng* rng, dk_
     if (n == 0) return DK_OK;
     DK_CUDA(ctx, cudaSetDevice(ctx->device));
     unsigned grid = (unsigned)((n + dk::PLAYOUT_THREADS - 1) / dk::PLAYOUT_THREADS);
+    CUtensorMap tmap;
+    if (state_tensor_map(ctx, out, n, &tmap)) {
+        dk::new_games_tma_kernel<<<grid, dk::PLAYOUT_THREADS, 0, pick_stream(ctx, stream)>>>(tmap, to_params(rng), (uint64_t)n);
+        return check_launch(ctx, "new_games_tma_kernel");
+    }
     dk::new_games_kernel<<<grid, dk::PLAYOUT_THREADS, 0, pick_stream(ctx, stream)>>>(to_params(rng), (uint64_t)n, out);
     return check_launch(ctx, "new_games_kernel");
 }

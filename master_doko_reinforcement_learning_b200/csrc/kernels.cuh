@@ -313,6 +313,43 @@ apply_tma_kernel(const __grid_constant__ CUtensorMap tmap, uint64_t n, const uin
     __syncthreads();
     if (threadIdx.x == 0) TmaTile::store(&tmap, stage, first);
 }
+// dk_new_games with the records leaving as two TMA tile stores per block (the per-thread form writes every record with eight 16-byte
+// stores at a 128-byte stride: 256 sector accesses per warp).
+__global__ void __launch_bounds__(PLAYOUT_THREADS)
+new_games_tma_kernel(const __grid_constant__ CUtensorMap tmap, RngParams rp, uint64_t n) {
+    __shared__ __align__(1024) uint4 stage[PLAYOUT_THREADS * 8];       // PLAYOUT_THREADS / STATE_THREADS tiles of 16 KB
+    uint32_t* smem = reinterpret_cast<uint32_t*>(stage);               // the shuffle scratch (12 words per thread) lives in the tiles until the deal is done
+    const uint64_t first = (uint64_t)blockIdx.x * PLAYOUT_THREADS, i = first + threadIdx.x;
+    const uint64_t gi = i < n ? i : n - 1;
+    SharedDeck deck;
+    deck.base = smem + threadIdx.x;
+    RngKey key = make_key(rp, gi, 0, false);
+    FdoLive dummy;
+    uint32_t ah[4], dup, start;
+    fdo_deal(dummy, key, deck, ah, dup, start);
+    __syncthreads();                                                   // every deck is dealt: the scratch becomes the record tiles
+    {
+        uint64_t hands[4];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) hands[p] = (uint64_t)ah[p] | ((uint64_t)(ah[p] & dup) << 24);   // copy B = doubled cards
+        alignas(16) dk_state s;
+        st_new_game(s, hands, start);
+        StateStage<PLAYOUT_THREADS>::put(stage, s);      // tile threadIdx.x / 128, row threadIdx.x % 128, chunk j at j ^ (row & 7)
+    }
+    TmaTile::publish();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (uint32_t k = 0; k < (uint32_t)(PLAYOUT_THREADS / STATE_THREADS); ++k) {
+            const uint64_t f = first + k * STATE_THREADS;
+            if (f < n)
+                asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];"
+                             ::"l"(&tmap), "r"(0), "r"((int)f), "r"(TmaTile::saddr(stage + k * STATE_THREADS * 8)) : "memory");
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+}
 template <int ENGINE>
 __global__ void __launch_bounds__(STATE_THREADS)
 legal_mask_tma_kernel(const __grid_constant__ CUtensorMap tmap, uint64_t n, uint64_t* __restrict__ mask_out) {
