@@ -1,4 +1,8 @@
 set -x
 mkdir -p gpurun_out
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 5 --warmup 3 > gpurun_out/bench_v17_2gpu.json 2> gpurun_out/bench_v17_2gpu.err; tail -c 300 gpurun_out/bench_v17_2gpu.json
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 bench.py --impl reference --gpus 2 --steps 2 --warmup 1 > gpurun_out/bench_v17_2gpu_ref.json 2> gpurun_out/bench_v17_2gpu_ref.err; tail -c 200 gpurun_out/bench_v17_2gpu_ref.json
+: > gpurun_out/k3_blocks.txt
+for mb in default 10 12 14 16; do
+  if [ $mb = default ]; then unset DOKO_CUDA_LIB; else export DOKO_CUDA_LIB=$PWD/profiles/experiments/libs/libdoko_det$mb.so; fi
+  echo "lib=$mb" >> gpurun_out/k3_blocks.txt
+  timeout 300 python profiles/experiments/k3_sizes.py >> gpurun_out/k3_blocks.txt 2>&1
+done
