@@ -10,6 +10,7 @@ announcements → 48 cards → scoring) played to the end by the random policy W
 Prints ONE JSON line on rank 0.
 """
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -105,6 +106,22 @@ def cpu_baseline(n_threads, target_seconds=12.0):
     return {"value": steps / r["seconds"], "unit": UNIT, "cores": n_threads if n_threads > 0 else L.orc_hardware_threads(),
             "kind": "port", "sample": f"{sample} games ({steps} game steps) of the same seeded workload, oracle/liboracle.so, "
             f"{r['seconds']:.2f} s", "games_per_sec": sample / r["seconds"]}
+
+
+def cpu_baseline_determinizations(n_threads):
+    """card_matching of the oracle on the host cores: 4096 info-states made like BASELINE configs[2] x 4096 samples."""
+    import ctypes as C
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+
+    L = oracle_lib.load()
+    L.orc_cpu_baseline.restype = C.c_double
+    L.orc_cpu_baseline.argtypes = [C.c_int, C.c_uint64, C.c_uint64, C.c_uint32, C.c_int, C.POINTER(C.c_uint64)]
+    work = C.c_uint64()
+    sec = L.orc_cpu_baseline(3, SEED, 4096, 4096, n_threads, C.byref(work))
+    return {"value": work.value / sec, "unit": "determinizations/s", "cores": n_threads if n_threads > 0 else L.orc_hardware_threads(), "kind": "port",
+            "sample": f"{work.value} samples (4096 info-states x 4096), oracle/liboracle.so, {sec:.2f} s"}
 
 
 def run_reference(args):
@@ -277,6 +294,52 @@ def run_cuda(args):
     e2e_value = run_e2e(True)
     e2e_int32 = run_e2e(False)
 
+    # ---- second half of BASELINE.json's metric: determinizations/s on BASELINE configs[2] — 65 536 mid-game info-states per GPU
+    # (card_index 8 / 16 / 24 / 32 round-robin, observer = seat to move), 4096 consistent hidden-hand samples each (card_matching,
+    # rs-full-doko/src/matching/card_matching.rs:31-467), outputs (37 B per sample, 9.9 GB per pass) written to HBM.
+    def run_determinizations(passes=3):
+        n_info, samples = 1 << 16, 4096
+        st = dk.new_games(pkg.DK_FDO, n_info, dk.rng(SEED, rank * n_info, 3))
+        raw = st.view(torch.uint8).reshape(n_info, 128)
+        target = (8 * (1 + (torch.arange(n_info, device=dev) & 3))).to(torch.uint8)
+        for it in range(400):                                    # advance every game to its target card index with random legal actions
+            active = ((raw[:, 118] < target) & ((raw[:, 124] & 3) != 3)).nonzero().squeeze(1)    # byte 118 = card_index, meta bits 0-1 = phase (3 = finished)
+            if active.numel() == 0:
+                break
+            sub = st[active].contiguous()
+            dk.step_random_encode(sub, dk.rng(SEED, rank * n_info, 100 + it), want_obs=False)
+            st[active] = sub
+        hands = torch.empty((n_info, samples, 4), dtype=torch.int64, device=dev)
+        res = torch.empty((n_info, samples, 4), dtype=torch.uint8, device=dev)
+        status = torch.empty((n_info, samples), dtype=torch.uint8, device=dev)
+
+        def one_pass(epoch):
+            dk._check(dk.L.dk_determinize(dk.ctx, pkg.DK_FDO, n_info, samples, pkg.api._ptr(st), ctypes.byref(dk.rng(SEED, rank * n_info, epoch)),
+                                          pkg.api._ptr(hands), pkg.api._ptr(res), pkg.api._ptr(status), dk._stream()), "dk_determinize")
+
+        one_pass(0)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for k in range(passes):
+            one_pass(1 + k)
+        e1.record()
+        barrier()
+        tt = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        dead = (status != 0).sum(dtype=torch.int64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dist.all_reduce(dead, op=dist.ReduceOp.SUM)
+        ms = float(tt.item())
+        out = {"value": world * passes * n_info * samples / (ms / 1e3), "unit": "determinizations/s", "ms_per_pass": ms / passes,
+               "config": {"workload": "rs-full-doko card_matching, 65536 mid-game info-states per B200 x 4096 samples (BASELINE configs[2])",
+                          "info_states_per_gpu": n_info, "samples_per_info_state": samples, "bytes_written_per_sample": 37},
+               "dead_ends_last_pass": int(dead.item())}
+        del hands, res, status
+        return out
+
+    determinizations = run_determinizations()
+
     if rank == 0:
         games_per_launch = n
         steps_per_launch = all_steps / max(world * args.steps, 1)
@@ -334,6 +397,8 @@ def run_cuda(args):
         }
         if base:
             line["cpu_baseline"] = base
+            determinizations["cpu_baseline"] = cpu_baseline_determinizations(0)
+        line["determinizations"] = determinizations
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

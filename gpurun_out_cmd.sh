@@ -1,8 +1,3 @@
 set -x
 mkdir -p gpurun_out
-: > gpurun_out/k3_blocks.txt
-for mb in default 10 12 14 16; do
-  if [ $mb = default ]; then unset DOKO_CUDA_LIB; else export DOKO_CUDA_LIB=$PWD/profiles/experiments/libs/libdoko_det$mb.so; fi
-  echo "lib=$mb" >> gpurun_out/k3_blocks.txt
-  timeout 300 python profiles/experiments/k3_sizes.py >> gpurun_out/k3_blocks.txt 2>&1
-done
+( time python bench.py > gpurun_out/bench_v18.json 2> gpurun_out/bench_v18.err ) 2> gpurun_out/bench_v18.time; tail -3 gpurun_out/bench_v18.time; tail -c 400 gpurun_out/bench_v18.err
