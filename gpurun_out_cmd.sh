@@ -1,3 +1,3 @@
 set -x
 mkdir -p gpurun_out
-( time python bench.py > gpurun_out/bench_v18.json 2> gpurun_out/bench_v18.err ) 2> gpurun_out/bench_v18.time; tail -3 gpurun_out/bench_v18.time; tail -c 400 gpurun_out/bench_v18.err
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 5 --warmup 3 > gpurun_out/bench_v18_2gpu.json 2> gpurun_out/bench_v18_2gpu.err; tail -c 300 gpurun_out/bench_v18_2gpu.err
