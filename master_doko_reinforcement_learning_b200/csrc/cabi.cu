@@ -250,6 +250,11 @@ dk_status dk_from_deals(dk_ctx* ctx, int engine, size_t n, const uint64_t* hands
     if (n == 0) return DK_OK;
     DK_CUDA(ctx, cudaSetDevice(ctx->device));
     unsigned grid = (unsigned)((n + dk::STATE_THREADS - 1) / dk::STATE_THREADS);
+    CUtensorMap tmap;
+    if (!((uintptr_t)hands & 15u) && state_tensor_map(ctx, out, n, &tmap)) {
+        dk::from_deals_tma_kernel<<<grid, dk::STATE_THREADS, 0, pick_stream(ctx, stream)>>>(tmap, (uint64_t)n, hands, start);
+        return check_launch(ctx, "from_deals_tma_kernel");
+    }
     dk::from_deals_kernel<<<grid, dk::STATE_THREADS, 0, pick_stream(ctx, stream)>>>((uint64_t)n, hands, start, out);
     return check_launch(ctx, "from_deals_kernel");
 }

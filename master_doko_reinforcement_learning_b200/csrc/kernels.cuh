@@ -350,6 +350,22 @@ new_games_tma_kernel(const __grid_constant__ CUtensorMap tmap, RngParams rp, uin
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
 }
+__global__ void __launch_bounds__(STATE_THREADS)
+from_deals_tma_kernel(const __grid_constant__ CUtensorMap tmap, uint64_t n, const uint64_t* __restrict__ hands, const uint8_t* __restrict__ start) {
+    __shared__ __align__(1024) uint4 stage[STATE_THREADS * 8];
+    const uint64_t first = (uint64_t)blockIdx.x * STATE_THREADS, i = first + threadIdx.x;
+    if (i < n) {
+        const ulonglong2* hp = reinterpret_cast<const ulonglong2*>(hands + 4 * i);
+        const ulonglong2 h01 = __ldg(hp), h23 = __ldg(hp + 1);
+        uint64_t h[4] = {h01.x, h01.y, h23.x, h23.y};
+        alignas(16) dk_state s;
+        st_new_game(s, h, start[i] & 3u);
+        StateStage<STATE_THREADS>::put(stage, s);
+    }
+    TmaTile::publish();
+    __syncthreads();
+    if (threadIdx.x == 0) TmaTile::store(&tmap, stage, first);
+}
 template <int ENGINE>
 __global__ void __launch_bounds__(STATE_THREADS)
 legal_mask_tma_kernel(const __grid_constant__ CUtensorMap tmap, uint64_t n, uint64_t* __restrict__ mask_out) {

@@ -19,6 +19,12 @@ out = {}
 states = dk.alloc_states(n)
 t = timed(lambda: dk.new_games(pkg.DK_FDO, n, dk.rng(SEED, 0, 5), out=states))
 out["new_games"] = {"ms": t * 1e3, "GBps": n * 128 / t / 1e9, "frac": n * 128 / t / 1e9 / PEAK, "games_per_s": n / t}
+d_hands = states.view(torch.uint8).reshape(n, 128)[:, :32].contiguous().view(torch.int64).reshape(n, 4)
+d_start = ((states.view(torch.uint8).reshape(n, 128)[:, 124] >> 4) & 3).contiguous()
+st2 = dk.alloc_states(n)
+t = timed(lambda: dk.from_deals(pkg.DK_FDO, d_hands, d_start, out=st2))
+out["from_deals"] = {"ms": t * 1e3, "GBps": n * 161 / t / 1e9, "frac": n * 161 / t / 1e9 / PEAK, "equal_to_new_games": bool(torch.equal(st2, states))}
+del st2
 for k in range(30): dk.step_random_encode(states, dk.rng(SEED, 0, k), want_obs=False)
 mask = torch.empty((n,), dtype=torch.int64, device="cuda")
 t = timed(lambda: dk.legal_mask(pkg.DK_FDO, states, out=mask))
