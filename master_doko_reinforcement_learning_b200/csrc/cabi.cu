@@ -320,6 +320,11 @@ dk_status dk_step_random_encode(dk_ctx* ctx, size_t n, dk_state* states, const d
     if (n == 0) return DK_OK;
     DK_CUDA(ctx, cudaSetDevice(ctx->device));
     unsigned grid = (unsigned)((n + dk::ENC_THREADS - 1) / dk::ENC_THREADS);
+    CUtensorMap tmap;
+    if (state_tensor_map(ctx, states, n, &tmap)) {
+        dk::fdo_step_encode_tma_kernel<<<grid, dk::ENC_THREADS, 0, pick_stream(ctx, stream)>>>(tmap, to_params(rng), (uint64_t)n, flags, obs_out, row_stride, action_out);
+        return check_launch(ctx, "fdo_step_encode_tma_kernel");
+    }
     dk::fdo_step_encode_kernel<<<grid, dk::ENC_THREADS, 0, pick_stream(ctx, stream)>>>(to_params(rng), (uint64_t)n, states, flags, obs_out, row_stride, action_out);
     return check_launch(ctx, "fdo_step_encode_kernel");
 }
