@@ -32,7 +32,7 @@ extern "C" {
 #endif
 
 #define DK_VERSION_MAJOR 0
-#define DK_VERSION_MINOR 1
+#define DK_VERSION_MINOR 2
 
 typedef struct dk_ctx dk_ctx;
 typedef int32_t dk_status;
@@ -147,7 +147,12 @@ typedef struct dk_rng {
                            samples of one unit can be split over several calls or GPUs; 0 elsewhere */
 } dk_rng;
 
-/* ---- context ------------------------------------------------------------------------------- */
+/* ---- context -------------------------------------------------------------------------------
+ * One context per (process, GPU).  A context owns its scratch buffers (host entry points, PIMC workspace, UCT ln table): keep ONE call in
+ * flight per context — calls on different streams of the same context must be ordered by the caller; use one context per host thread
+ * for concurrent callers.  dk_destroy releases everything the context allocated, including an NCCL communicator left open.
+ * Alignment: record arrays (dk_state*) and every 16-byte vector output named below must be 16-byte aligned, 32-bit outputs 4-byte aligned;
+ * a misaligned pointer is refused with DK_ERR_INVALID_ARGUMENT (it would fault on the device). */
 DK_API dk_status dk_init(int device, dk_ctx** out);
 DK_API dk_status dk_destroy(dk_ctx* ctx);
 DK_API const char* dk_last_error(const dk_ctx* ctx); /* message of the last failing call on this context */
@@ -173,6 +178,26 @@ DK_API dk_status dk_from_deals(dk_ctx* ctx, int engine, size_t n, const uint64_t
  * A finished game yields mask 0. */
 DK_API dk_status dk_legal_mask(dk_ctx* ctx, int engine, size_t n, const dk_state* states /*[dev]*/, uint64_t* mask_out /*[dev] n*/,
                         dk_stream stream);
+/* AzEnvState::allowed_actions_by_action_index(is_secondary, epoch) and AzEnvState::number_of_allowed_actions(epoch) of FdoAzEnvState
+ * (rs-doko-alpha-zero/src/env/envs/full_doko/full_doko.rs:80-119; DK_FDO records): mask_out[i] (nullable) = the legal mask without the
+ * five announcement calls (actions 33..37) when is_secondary != 0 || az_epoch < DK_AZ_MIN_EPOCH; n_allowed_out[i] (nullable) = the number
+ * of allowed actions under the EPOCH filter alone (the reference's number_of_allowed_actions ignores is_secondary). */
+#define DK_AZ_MIN_EPOCH 10u
+DK_API dk_status dk_legal_mask_az(dk_ctx* ctx, size_t n, const dk_state* states /*[dev]*/, int is_secondary, uint64_t az_epoch,
+                                  uint64_t* mask_out /*[dev] n or NULL*/, uint8_t* n_allowed_out /*[dev] n or NULL*/, dk_stream stream);
+/* AzEnvState::id() (full_doko.rs:156-167): FxHasher64 (fxhash 0.2.1: hash = (rotl(hash, 5) ^ word) * 0x517cc1b727220a95 per 64-bit word)
+ * over the sixteen little-endian 64-bit words of the record and then the last action as one more word (last_action == NULL or
+ * DK_ACTION_NONE = None).  The record is canonical (one byte pattern per game state), so equal states <=> equal hash input, which is
+ * what id() promises; the values differ from the reference's, which hashes the in-memory layout of its own structs. */
+DK_API dk_status dk_state_id(dk_ctx* ctx, size_t n, const dk_state* states /*[dev]*/, const uint8_t* last_action /*[dev] n or NULL*/,
+                             uint64_t* id_out /*[dev] n*/, dk_stream stream);
+/* FdoAllowedActions::random (rs-game-utils/src/bit_flag.rs:86-94) over the legal set of the seat to move WITHOUT playing it: the draw of
+ * the random policies (FdoState::random_action_for_current_player[_no_announcement], rs-full-doko/src/state/state.rs:378-431; flags =
+ * DK_PLAYOUT_WITH_ANNOUNCEMENTS keeps the calls in the set) and of DefaultImpiPolicy's fallback when no determinization succeeded
+ * (rs-doko-py-bridge/src/compare_impi/compare_impi.rs:357-368; flags = 0).  Stream position: SITE_STEP word 0 of unit first_id + i, i.e.
+ * dk_step_random_encode with the same rng plays exactly this action.  A finished game yields DK_ACTION_NONE. */
+DK_API dk_status dk_random_action(dk_ctx* ctx, int engine, size_t n, const dk_state* states /*[dev]*/, const dk_rng* rng, uint32_t flags,
+                                  uint8_t* action_out /*[dev] n*/, dk_stream stream);
 /* replaces FdoState::play_action (rs-full-doko/src/state/state.rs:208-358) / McEnvState::by_action /
  *          AzEnvState::take_action_by_action_index; rs-doko: DoState::play_action (rs-doko/src/state/state.rs:189-309).
  * An illegal action (the reference would panic) sets err_out[i] != 0 and leaves state i unchanged. */
@@ -218,6 +243,41 @@ DK_API dk_status dk_playout_host(dk_ctx* ctx, int engine, uint32_t flags, size_t
  * instead of 20 over PCIe. */
 DK_API dk_status dk_playout_host_compact(dk_ctx* ctx, int engine, uint32_t flags, size_t n, const dk_state* states_host /*[host] or NULL*/,
                                          const dk_rng* rng, int8_t* points_out_host /*[host] n*4*/, uint8_t* steps_out_host /*[host] n*/);
+
+/* Packed host-transfer form: 2 bytes of points per game (+ 1 byte of steps when steps_out_host != NULL) instead of 5 / 20.  The four
+ * player_points take two values (Re seats / Kontra seats) and sum to zero (FdoEndOfGameStats::calculate, rs-full-doko/src/stats/stats.rs:215-231;
+ * rs-doko/src/stats/stats.rs:25-135), so v = (uint8)points[0] | same << 8, same bit j-1 = (points[j] == points[0]) for j = 1..3, is lossless:
+ * dk_unpack_points restores the four values. */
+DK_API dk_status dk_playout_host_packed(dk_ctx* ctx, int engine, uint32_t flags, size_t n, const dk_state* states_host /*[host] or NULL*/,
+                                        const dk_rng* rng, uint16_t* points_packed_out_host /*[host] n*/, uint8_t* steps_out_host /*[host] n or NULL*/);
+static inline void dk_unpack_points(uint16_t v, int32_t points[4]) {
+    const int32_t a = (int8_t)(v & 0xFFu);
+    const uint32_t same = (v >> 8) & 7u;
+    const int32_t k = 1 + (int32_t)(same & 1u) + (int32_t)((same >> 1) & 1u) + (int32_t)((same >> 2) & 1u);   /* seats that score like seat 0 */
+    const int32_t b = k == 4 ? a : -(k * a) / (4 - k);                                                        /* zero sum */
+    points[0] = a;
+    points[1] = (same & 1u) ? a : b;
+    points[2] = (same & 2u) ? a : b;
+    points[3] = (same & 4u) ? a : b;
+}
+
+/* Device-reduced playouts for evaluator-style callers (what EvFullDokoSingleGameEvaluationResult rows are aggregated to,
+ * rs-doko-evaluator/src/full_doko/evaluate_single_game.rs:50-75): the games are played like dk_playout and only their statistics leave the
+ * GPU — 2160 bytes per call instead of bytes per game.  All integer, order independent, identical for any sharding of the batch:
+ * summing the structs of several calls / ranks gives the statistics of the union (accumulate != 0 adds to *stats instead of overwriting). */
+typedef struct dk_playout_stats {
+    uint64_t games;            /* games played */
+    uint64_t game_steps;       /* sum of the number of play_action calls (number_of_actions) */
+    int64_t point_sum[4];      /* sum of player_points per absolute seat */
+    uint64_t point_sq_sum[4];  /* sum of player_points^2 per seat */
+    uint64_t wins[4];          /* games with player_points > 0 per seat */
+    uint64_t step_hist[256];   /* histogram of the number of actions per game (bin 255 = 255 and more) */
+} dk_playout_stats;
+DK_API dk_status dk_playout_summary(dk_ctx* ctx, int engine, uint32_t flags, size_t n, const dk_state* states /*[dev] or NULL*/, const dk_rng* rng,
+                                    dk_playout_stats* stats /*[dev]*/, int accumulate, dk_stream stream);
+/* Same with host buffers: states_host (or NULL = fresh games) is copied in, *stats_out_host is written before the call returns. */
+DK_API dk_status dk_playout_summary_host(dk_ctx* ctx, int engine, uint32_t flags, size_t n, const dk_state* states_host /*[host] or NULL*/,
+                                         const dk_rng* rng, dk_playout_stats* stats_out_host /*[host]*/);
 
 /* ---- determinization ---------------------------------------------------------------------------------
  * DK_DOKO replaces sample_assignment_full (rs-doko-assignment/src/assignment.rs:458-581): hands only; reservations_out repeats
@@ -285,7 +345,12 @@ DK_API dk_status dk_fuse(dk_ctx* ctx, int strategy, size_t n_roots, size_t n_row
  *   [0,39) MaxN rank sums of the allowed actions | [39,78) visit sums | [78] successful samples | [79] 0
  * (accumulate != 0 adds to `stats` instead of overwriting), the ranks sum them with dk_allreduce_root_stats, and dk_pimc_pick decides.
  * MaxN from the statistics is identical to dk_fuse over the union of the rows; Average is the arg-max of the summed visits (last among
- * equals), which is PolicyFusionAverageStrategy in exact arithmetic when every row has the same total. */
+ * equals), which is PolicyFusionAverageStrategy in exact arithmetic when every row has the same total.  KNOWN DIVERGENCE: with rows of
+ * unequal totals (UCT trees that hit a terminal root early, mixed rollout counts) or when the reference's f32 sums tie or round differently,
+ * the sharded Average pick can differ from dk_fuse / the reference on near-ties; gather the rows and call dk_fuse when bit parity with the
+ * single-GPU decision matters (tests/test_gpu_pimc.py pins both behaviours).  dk_pimc_pick returns DK_ACTION_NONE for a root without a
+ * successful sample: the reference then plays a random non-announcement action (compare_impi.rs:357-368) = dk_random_action(flags = 0),
+ * which master_doko_reinforcement_learning_b200.sharding.pimc_decide applies. */
 #define DK_ROOT_STATS 80u
 DK_API dk_status dk_pimc_root_stats(dk_ctx* ctx, size_t n_roots, size_t n_rows, const uint32_t* visits /*[dev]*/, const uint8_t* status /*[dev] or NULL*/,
                                     const uint64_t* allowed /*[dev]*/, int64_t* stats /*[dev] n_roots*DK_ROOT_STATS*/, int accumulate, dk_stream stream);

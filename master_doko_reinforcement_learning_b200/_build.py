@@ -28,12 +28,58 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+SASS_HASHES = os.path.join(PKG_DIR, "libdoko_cuda.sass.json")
+
+
+def write_sass_hashes():
+    """sha256 of every kernel's SASS in the built library → libdoko_cuda.sass.json (next to the .so, a build artefact).
+    bench.py compares them with the hashes recorded in profiles/kernel_counters.json: ncu counters that were taken on another build of a
+    kernel are reported as stale instead of silently feeding the roofline."""
+    import hashlib
+    import json
+
+    cuobjdump = os.path.join(os.path.dirname(find_nvcc()), "cuobjdump")
+    if not os.path.exists(cuobjdump):
+        cuobjdump = shutil.which("cuobjdump")
+    if not cuobjdump:
+        return None
+    txt = subprocess.run([cuobjdump, "-sass", LIB_PATH], capture_output=True, text=True, check=True).stdout
+    hashes, name, body = {}, None, []
+    for line in txt.splitlines():
+        t = line.strip()
+        if t.startswith("Function :"):
+            if name:
+                hashes[name] = hashlib.sha256("\n".join(body).encode()).hexdigest()
+            name, body = t.split(":", 1)[1].strip(), []
+        elif name and t.startswith("/*"):
+            body.append(t)
+    if name:
+        hashes[name] = hashlib.sha256("\n".join(body).encode()).hexdigest()
+    with open(SASS_HASHES, "w") as f:
+        json.dump(hashes, f, indent=0, sort_keys=True)
+    return hashes
+
+
+def sass_hashes():
+    """The hashes written by the last build ({} when the file is missing)."""
+    import json
+
+    try:
+        if os.path.getmtime(SASS_HASHES) + 1 < os.path.getmtime(LIB_PATH):
+            return {}
+        with open(SASS_HASHES) as f:
+            return json.load(f)
+    except OSError:
+        return {}
+
+
 def build_library(force=False, verbose=False):
     """Compile csrc/*.cu → libdoko_cuda.so for sm_100a.  Returns the library path."""
     if not force and not _stale():
         return LIB_PATH
     cmd = [find_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + SOURCES + ["-ldl"]
     subprocess.check_call(cmd, cwd=CSRC)
+    write_sass_hashes()
     return LIB_PATH
 
 

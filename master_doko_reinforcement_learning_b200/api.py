@@ -33,6 +33,37 @@ class DkRng(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("first_id", C.c_uint64), ("epoch", C.c_uint32), ("first_sub", C.c_uint32)]
 
 
+class DkPlayoutStats(C.Structure):
+    """include/doko_cuda.h:dk_playout_stats (2160 bytes)."""
+    _fields_ = [("games", C.c_uint64), ("game_steps", C.c_uint64), ("point_sum", C.c_int64 * 4), ("point_sq_sum", C.c_uint64 * 4),
+                ("wins", C.c_uint64 * 4), ("step_hist", C.c_uint64 * 256)]
+
+    def as_dict(self):
+        return {"games": int(self.games), "game_steps": int(self.game_steps), "point_sum": [int(x) for x in self.point_sum],
+                "point_sq_sum": [int(x) for x in self.point_sq_sum], "wins": [int(x) for x in self.wins],
+                "step_hist": np.array(self.step_hist, dtype=np.uint64)}
+
+
+assert C.sizeof(DkPlayoutStats) == 2160
+STATS_WORDS = 270
+AZ_MIN_EPOCH = 10
+
+
+def unpack_points(packed):
+    """dk_unpack_points for a uint16 numpy array [n] -> int32 [n,4] (the packed host-transfer form of dk_playout_host_packed)."""
+    v = np.asarray(packed, dtype=np.uint16)
+    a = (v & 0xFF).astype(np.int8).astype(np.int32)
+    same = (v >> 8) & 7
+    k = 1 + (same & 1) + ((same >> 1) & 1) + ((same >> 2) & 1)
+    k = k.astype(np.int32)
+    b = np.where(k == 4, a, -(k * a) // np.maximum(4 - k, 1))
+    out = np.empty(v.shape + (4,), dtype=np.int32)
+    out[..., 0] = a
+    for j in (1, 2, 3):
+        out[..., j] = np.where((same >> (j - 1)) & 1, a, b)
+    return out
+
+
 def library_path():
     """In-tree libdoko_cuda.so; DOKO_CUDA_LIB points at another build of the same ABI (used by the tuning experiments)."""
     return os.environ.get("DOKO_CUDA_LIB") or _build.LIB_PATH
@@ -66,6 +97,12 @@ def load_library():
     L.dk_playout.argtypes = [vp, i32, u32, sz, vp, C.POINTER(DkRng), vp, vp, vp]
     L.dk_playout_host.argtypes = [vp, i32, u32, sz, vp, C.POINTER(DkRng), vp, vp]
     L.dk_playout_host_compact.argtypes = [vp, i32, u32, sz, vp, C.POINTER(DkRng), vp, vp]
+    L.dk_playout_host_packed.argtypes = [vp, i32, u32, sz, vp, C.POINTER(DkRng), vp, vp]
+    L.dk_playout_summary.argtypes = [vp, i32, u32, sz, vp, C.POINTER(DkRng), vp, i32, vp]
+    L.dk_playout_summary_host.argtypes = [vp, i32, u32, sz, vp, C.POINTER(DkRng), C.POINTER(DkPlayoutStats)]
+    L.dk_legal_mask_az.argtypes = [vp, sz, vp, i32, u64, vp, vp, vp]
+    L.dk_state_id.argtypes = [vp, sz, vp, vp, vp, vp]
+    L.dk_random_action.argtypes = [vp, i32, sz, vp, C.POINTER(DkRng), u32, vp, vp]
     L.dk_playout_trace.argtypes = [vp, i32, sz, C.POINTER(DkRng), vp, vp, vp, vp]
     for name, args in (
         ("dk_new_games", [vp, i32, sz, C.POINTER(DkRng), vp, vp]),
@@ -105,11 +142,16 @@ def load_library():
 
 
 def _ptr(t):
-    """Device/host pointer of a torch tensor, numpy array or None."""
+    """Device/host pointer of a torch tensor, numpy array or None.  The C ABI takes dense buffers: a non-contiguous view would be read
+    and written with the wrong strides, so it is refused here (alignment is checked by the library itself)."""
     if t is None:
         return None
     if isinstance(t, np.ndarray):
+        if not t.flags["C_CONTIGUOUS"]:
+            raise DokoCudaError("non-contiguous numpy array passed to the C ABI")
         return t.ctypes.data_as(C.c_void_p)
+    if not t.is_contiguous():
+        raise DokoCudaError("non-contiguous tensor passed to the C ABI")
     return C.c_void_p(t.data_ptr())
 
 
@@ -144,13 +186,19 @@ class DokoCuda:
     def rng(seed, first_id=0, epoch=0, first_sub=0):
         return DkRng(int(seed) & 0xFFFFFFFFFFFFFFFF, int(first_id), int(epoch), int(first_sub))
 
-    @staticmethod
-    def _stream():
+    def _stream(self):
         import torch
 
         # torch's default stream is the legacy NULL stream; the C ABI reserves NULL for "the context's own stream",
         # so pass the explicit cudaStreamLegacy handle (0x1) to stay ordered with torch work and torch CUDA events.
-        return C.c_void_p(torch.cuda.current_stream().cuda_stream or 1)
+        # The stream is the current one of THIS context's device (not of torch's current device).
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream or 1)
+
+    def _on_device(self, *tensors):
+        """Device tensors handed to the library must live on the context's GPU."""
+        for t in tensors:
+            if t is not None and not isinstance(t, np.ndarray) and (not t.is_cuda or t.device.index != self.device):
+                raise DokoCudaError(f"tensor on {t.device} passed to the context of cuda:{self.device}")
 
     def device_info(self):
         sm, ma, mi, mem = C.c_int(), C.c_int(), C.c_int(), C.c_size_t()
@@ -161,7 +209,8 @@ class DokoCuda:
         return int(self.L.dk_launch_count(self.ctx))
 
     def synchronize(self, stream=None):
-        self._check(self.L.dk_synchronize(self.ctx, stream), "dk_synchronize")
+        """Waits for the work the wrapper queued: by default the torch stream every method launches on."""
+        self._check(self.L.dk_synchronize(self.ctx, stream if stream is not None else self._stream()), "dk_synchronize")
 
     # ---- playouts ----------------------------------------------------------------------------------------
     def playout(self, engine, n, rng, states=None, flags=0, points_out=None, steps_out=None, stream=None):
@@ -197,6 +246,33 @@ class DokoCuda:
                     "dk_playout_host_compact")
         return points_out, steps_out
 
+    def playout_host_packed(self, engine, n, rng, states=None, flags=0, points_out=None, steps_out=None, want_steps=True):
+        """dk_playout_host_packed: uint16 [n] packed points (+ uint8 [n] steps) in host buffers; decode with unpack_points."""
+        if points_out is None:
+            points_out = np.empty((n,), dtype=np.uint16)
+        if steps_out is None and want_steps:
+            steps_out = np.empty((n,), dtype=np.uint8)
+        self._check(self.L.dk_playout_host_packed(self.ctx, engine, flags, n, _ptr(states), C.byref(rng), _ptr(points_out), _ptr(steps_out)),
+                    "dk_playout_host_packed")
+        return points_out, steps_out
+
+    def playout_summary(self, engine, n, rng, states=None, flags=0, stats=None, accumulate=False, stream=None):
+        """dk_playout_summary: device-reduced statistics as an int64 cuda tensor [270] (word layout of dk_playout_stats)."""
+        import torch
+
+        self._on_device(states, stats)
+        if stats is None:
+            stats = torch.zeros((STATS_WORDS,), dtype=torch.int64, device=self._dev())
+        self._check(self.L.dk_playout_summary(self.ctx, engine, flags, n, _ptr(states), C.byref(rng), _ptr(stats), int(accumulate),
+                                              stream if stream is not None else self._stream()), "dk_playout_summary")
+        return stats
+
+    def playout_summary_host(self, engine, n, rng, states=None, flags=0):
+        """dk_playout_summary_host: the batch's statistics as a DkPlayoutStats struct in host memory (2160 bytes cross PCIe)."""
+        out = DkPlayoutStats()
+        self._check(self.L.dk_playout_summary_host(self.ctx, engine, flags, n, _ptr(states), C.byref(rng), C.byref(out)), "dk_playout_summary_host")
+        return out
+
     # ---- state records ---------------------------------------------------------------------------------------------------
     def _dev(self):
         import torch
@@ -228,6 +304,39 @@ class DokoCuda:
         n = states.shape[0]
         out = torch.empty((n,), dtype=torch.int64, device=self._dev()) if out is None else out
         self._check(self.L.dk_legal_mask(self.ctx, engine, n, _ptr(states), _ptr(out), stream if stream is not None else self._stream()), "dk_legal_mask")
+        return out
+
+    def legal_mask_az(self, states, is_secondary, az_epoch, want_count=True, stream=None):
+        """AzEnvState::allowed_actions_by_action_index(is_secondary, epoch) as masks (int64 [n]) and number_of_allowed_actions(epoch) (uint8 [n])."""
+        import torch
+
+        self._on_device(states)
+        n = states.shape[0]
+        mask = torch.empty((n,), dtype=torch.int64, device=self._dev())
+        cnt = torch.empty((n,), dtype=torch.uint8, device=self._dev()) if want_count else None
+        self._check(self.L.dk_legal_mask_az(self.ctx, n, _ptr(states), int(bool(is_secondary)), int(az_epoch), _ptr(mask), _ptr(cnt),
+                                            stream if stream is not None else self._stream()), "dk_legal_mask_az")
+        return mask, cnt
+
+    def random_action(self, engine, states, rng, flags=0, stream=None):
+        """FdoAllowedActions::random over the legal set without playing it (uint8 [n]; ACTION_NONE for finished games)."""
+        import torch
+
+        self._on_device(states)
+        n = states.shape[0]
+        out = torch.empty((n,), dtype=torch.uint8, device=self._dev())
+        self._check(self.L.dk_random_action(self.ctx, engine, n, _ptr(states), C.byref(rng), flags, _ptr(out),
+                                            stream if stream is not None else self._stream()), "dk_random_action")
+        return out
+
+    def state_id(self, states, last_action=None, stream=None):
+        """AzEnvState::id(): FxHasher64 over the record (+ last action), int64 [n] (bit pattern of the u64)."""
+        import torch
+
+        self._on_device(states, last_action)
+        n = states.shape[0]
+        out = torch.empty((n,), dtype=torch.int64, device=self._dev())
+        self._check(self.L.dk_state_id(self.ctx, n, _ptr(states), _ptr(last_action), _ptr(out), stream if stream is not None else self._stream()), "dk_state_id")
         return out
 
     def apply(self, engine, states, actions, flags=0, err_out=None, stream=None):
@@ -393,12 +502,16 @@ class DokoCuda:
 
     # ---- multi-GPU root statistics ----------------------------------------------------------------------------------------
     def comm_init(self, group=None):
-        """Create the library's NCCL communicator over the ranks of a torch.distributed group (torch is only the rendezvous)."""
-        import torch
+        """Create the library's NCCL communicator over the ranks of a torch.distributed group (torch is only the rendezvous that
+        carries the NCCL id); a single process without torch.distributed gets a one-rank communicator."""
         import torch.distributed as dist
 
-        world, rank = dist.get_world_size(group), dist.get_rank(group)
         ident = (C.c_char * 128)()
+        if not (dist.is_available() and dist.is_initialized()):
+            self._check(self.L.dk_comm_unique_id(self.ctx, ident), "dk_comm_unique_id")
+            self._check(self.L.dk_comm_init(self.ctx, 1, 0, ident), "dk_comm_init")
+            return
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
         if rank == 0:
             self._check(self.L.dk_comm_unique_id(self.ctx, ident), "dk_comm_unique_id")
         box = [bytes(ident.raw)]

@@ -63,6 +63,16 @@ dk_status fail(dk_ctx* ctx, dk_status st, const std::string& msg) {
 
 cudaStream_t pick_stream(dk_ctx* ctx, dk_stream s) { return s ? (cudaStream_t)s : ctx->stream; }
 
+// The kernels use 16-byte vector accesses on the record arrays and on the outputs named in the header, 4-byte ones on packed words.
+// A misaligned caller buffer (a sliced view, an offset Rust slice) would fault on the device — a sticky error for the whole CUDA
+// context — so it is refused here.  NULL passes (nullable arguments are checked for presence separately).
+bool aligned_to(const void* p, uintptr_t a) { return ((uintptr_t)p & (a - 1u)) == 0u; }
+dk_status misaligned(dk_ctx* ctx, const char* what) { return fail(ctx, DK_ERR_INVALID_ARGUMENT, std::string(what) + ": misaligned pointer"); }
+#define DK_ALIGNED(ctx, ptr, a)                                                                         \
+    do {                                                                                                \
+        if (!aligned_to((ptr), (a))) return misaligned((ctx), #ptr);                                    \
+    } while (0)
+
 // Tensor map of a record array ([n][128] bytes, tiles of up to 128 records, 128-byte swizzle) for the TMA kernels.  False when the
 // driver entry point is missing or refuses the array (then the callers use their cooperative-copy kernels).
 typedef CUresult (*dk_tmap_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -110,7 +120,7 @@ dk_status check_launch(dk_ctx* ctx, const char* what) {
 
 extern "C" {
 
-const char* dk_version(void) { return "doko_cuda 0.1 (sm_100a)"; }
+const char* dk_version(void) { return "doko_cuda 0.2 (sm_100a)"; }
 
 dk_status dk_init(int device, dk_ctx** out) {
     if (!out) return DK_ERR_INVALID_ARGUMENT;
@@ -144,8 +154,10 @@ dk_status dk_init(int device, dk_ctx** out) {
 dk_status dk_destroy(dk_ctx* ctx) {
     if (!ctx) return DK_ERR_INVALID_ARGUMENT;
     cudaSetDevice(ctx->device);
+    dk_comm_destroy(ctx);                                // a communicator the caller left open
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);
     if (ctx->pimc_ws) cudaFree(ctx->pimc_ws);
+    if (ctx->d_ln_table) cudaFree(ctx->d_ln_table);
     for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
@@ -187,25 +199,25 @@ static dk_status fresh_smem_opt_in(dk_ctx* ctx) {
     return DK_OK;
 }
 static dk_status playout_launch(dk_ctx* ctx, int engine, uint32_t flags, size_t n, const dk_state* states, const dk::RngParams& rp,
-                                void* points_out, void* steps_out, bool compact, cudaStream_t s) {
+                                void* points_out, void* steps_out, uint32_t mode, unsigned long long* stats, cudaStream_t s) {
     const bool with_ann = (flags & DK_PLAYOUT_WITH_ANNOUNCEMENTS) != 0;
     if (states == nullptr) {
         const unsigned fgrid = (unsigned)((n + dk::FDO_FRESH_THREADS - 1) / dk::FDO_FRESH_THREADS);
         DK_TRY(fresh_smem_opt_in(ctx));
         if (engine == DK_FDO) {
-            if (with_ann) dk::fdo_playout_fresh_kernel<true><<<fgrid, dk::FDO_FRESH_THREADS, dk::FDO_FRESH_SMEM_BYTES, s>>>(rp, (uint64_t)n, points_out, steps_out, compact);
-            else dk::fdo_playout_fresh_kernel<false><<<fgrid, dk::FDO_FRESH_THREADS, dk::FDO_FRESH_SMEM_BYTES, s>>>(rp, (uint64_t)n, points_out, steps_out, compact);
+            if (with_ann) dk::fdo_playout_fresh_kernel<true><<<fgrid, dk::FDO_FRESH_THREADS, dk::FDO_FRESH_SMEM_BYTES, s>>>(rp, (uint64_t)n, points_out, steps_out, mode, stats);
+            else dk::fdo_playout_fresh_kernel<false><<<fgrid, dk::FDO_FRESH_THREADS, dk::FDO_FRESH_SMEM_BYTES, s>>>(rp, (uint64_t)n, points_out, steps_out, mode, stats);
             return check_launch(ctx, "fdo_playout_fresh_kernel");
         }
-        dk::doko_playout_fresh_kernel<false><<<fgrid, dk::FDO_FRESH_THREADS, dk::FDO_FRESH_SMEM_BYTES, s>>>(rp, (uint64_t)n, points_out, steps_out, compact, nullptr, nullptr);
+        dk::doko_playout_fresh_kernel<false><<<fgrid, dk::FDO_FRESH_THREADS, dk::FDO_FRESH_SMEM_BYTES, s>>>(rp, (uint64_t)n, points_out, steps_out, mode, stats, nullptr, nullptr);
         return check_launch(ctx, "doko_playout_fresh_kernel");
     }
     unsigned grid = (unsigned)((n + dk::PLAYOUT_STATE_THREADS - 1) / dk::PLAYOUT_STATE_THREADS);
     if (engine == DK_FDO) {
-        if (with_ann) dk::playout_state_kernel<DK_FDO, true><<<grid, dk::PLAYOUT_STATE_THREADS, 0, s>>>(rp, (uint64_t)n, states, 1u, points_out, steps_out, compact);
-        else dk::playout_state_kernel<DK_FDO, false><<<grid, dk::PLAYOUT_STATE_THREADS, 0, s>>>(rp, (uint64_t)n, states, 1u, points_out, steps_out, compact);
+        if (with_ann) dk::playout_state_kernel<DK_FDO, true><<<grid, dk::PLAYOUT_STATE_THREADS, 0, s>>>(rp, (uint64_t)n, states, 1u, points_out, steps_out, mode, stats);
+        else dk::playout_state_kernel<DK_FDO, false><<<grid, dk::PLAYOUT_STATE_THREADS, 0, s>>>(rp, (uint64_t)n, states, 1u, points_out, steps_out, mode, stats);
     } else {
-        dk::playout_state_kernel<DK_DOKO, false><<<grid, dk::PLAYOUT_STATE_THREADS, 0, s>>>(rp, (uint64_t)n, states, 1u, points_out, steps_out, compact);
+        dk::playout_state_kernel<DK_DOKO, false><<<grid, dk::PLAYOUT_STATE_THREADS, 0, s>>>(rp, (uint64_t)n, states, 1u, points_out, steps_out, mode, stats);
     }
     return check_launch(ctx, "playout_state_kernel");
 }
@@ -215,7 +227,19 @@ dk_status dk_playout(dk_ctx* ctx, int engine, uint32_t flags, size_t n, const dk
     if (!ctx || !rng || (engine != DK_FDO && engine != DK_DOKO)) return DK_ERR_INVALID_ARGUMENT;
     if (n == 0) return DK_OK;
     DK_CUDA(ctx, cudaSetDevice(ctx->device));
-    return playout_launch(ctx, engine, flags, n, states, to_params(rng), points_out, steps_out, false, pick_stream(ctx, stream));
+    DK_ALIGNED(ctx, states, 16); DK_ALIGNED(ctx, points_out, 16); DK_ALIGNED(ctx, steps_out, 4);
+    return playout_launch(ctx, engine, flags, n, states, to_params(rng), points_out, steps_out, dk::OUT_INT32, nullptr, pick_stream(ctx, stream));
+}
+
+dk_status dk_playout_summary(dk_ctx* ctx, int engine, uint32_t flags, size_t n, const dk_state* states, const dk_rng* rng, dk_playout_stats* stats,
+                             int accumulate, dk_stream stream) {
+    if (!ctx || !rng || !stats || (engine != DK_FDO && engine != DK_DOKO)) return DK_ERR_INVALID_ARGUMENT;
+    DK_ALIGNED(ctx, states, 16); DK_ALIGNED(ctx, stats, 8);
+    DK_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = pick_stream(ctx, stream);
+    if (!accumulate) DK_CUDA(ctx, cudaMemsetAsync(stats, 0, sizeof(dk_playout_stats), s));
+    if (n == 0) return DK_OK;
+    return playout_launch(ctx, engine, flags, n, states, to_params(rng), nullptr, nullptr, dk::OUT_INT32, (unsigned long long*)stats, s);
 }
 
 dk_status dk_playout_trace(dk_ctx* ctx, int engine, size_t n, const dk_rng* rng, int32_t* points_out, uint8_t* trace_out, uint32_t* aux_out,
@@ -223,10 +247,11 @@ dk_status dk_playout_trace(dk_ctx* ctx, int engine, size_t n, const dk_rng* rng,
     if (!ctx || !rng) return DK_ERR_INVALID_ARGUMENT;
     if (engine != DK_DOKO) return fail(ctx, DK_ERR_UNSUPPORTED, "dk_playout_trace: only DK_DOKO records traces");
     if (n == 0) return DK_OK;
+    DK_ALIGNED(ctx, points_out, 16); DK_ALIGNED(ctx, aux_out, 16);
     DK_CUDA(ctx, cudaSetDevice(ctx->device));
     DK_TRY(fresh_smem_opt_in(ctx));
     unsigned grid = (unsigned)((n + dk::FDO_FRESH_THREADS - 1) / dk::FDO_FRESH_THREADS);
-    dk::doko_playout_fresh_kernel<true><<<grid, dk::FDO_FRESH_THREADS, dk::FDO_FRESH_SMEM_BYTES, pick_stream(ctx, stream)>>>(to_params(rng), (uint64_t)n, points_out, nullptr, false,
+    dk::doko_playout_fresh_kernel<true><<<grid, dk::FDO_FRESH_THREADS, dk::FDO_FRESH_SMEM_BYTES, pick_stream(ctx, stream)>>>(to_params(rng), (uint64_t)n, points_out, nullptr, dk::OUT_INT32, nullptr,
                                                                                                     trace_out, (uint4*)aux_out);
     return check_launch(ctx, "doko_playout_fresh_kernel<trace>");
 }
@@ -234,6 +259,7 @@ dk_status dk_playout_trace(dk_ctx* ctx, int engine, size_t n, const dk_rng* rng,
 dk_status dk_new_games(dk_ctx* ctx, int engine, size_t n, const dk_rng* rng, dk_state* out, dk_stream stream) {
     if (!ctx || !rng || !out || (engine != DK_FDO && engine != DK_DOKO)) return DK_ERR_INVALID_ARGUMENT;
     if (n == 0) return DK_OK;
+    DK_ALIGNED(ctx, out, 16);
     DK_CUDA(ctx, cudaSetDevice(ctx->device));
     unsigned grid = (unsigned)((n + dk::PLAYOUT_THREADS - 1) / dk::PLAYOUT_THREADS);
     CUtensorMap tmap;
@@ -248,6 +274,7 @@ dk_status dk_new_games(dk_ctx* ctx, int engine, size_t n, const dk_rng* rng, dk_
 dk_status dk_from_deals(dk_ctx* ctx, int engine, size_t n, const uint64_t* hands, const uint8_t* start, dk_state* out, dk_stream stream) {
     if (!ctx || !hands || !start || !out || (engine != DK_FDO && engine != DK_DOKO)) return DK_ERR_INVALID_ARGUMENT;
     if (n == 0) return DK_OK;
+    DK_ALIGNED(ctx, out, 16); DK_ALIGNED(ctx, hands, 8);
     DK_CUDA(ctx, cudaSetDevice(ctx->device));
     unsigned grid = (unsigned)((n + dk::STATE_THREADS - 1) / dk::STATE_THREADS);
     CUtensorMap tmap;
@@ -259,25 +286,57 @@ dk_status dk_from_deals(dk_ctx* ctx, int engine, size_t n, const uint64_t* hands
     return check_launch(ctx, "from_deals_kernel");
 }
 
-dk_status dk_legal_mask(dk_ctx* ctx, int engine, size_t n, const dk_state* states, uint64_t* mask_out, dk_stream stream) {
-    if (!ctx || !states || !mask_out || (engine != DK_FDO && engine != DK_DOKO)) return DK_ERR_INVALID_ARGUMENT;
+static dk_status legal_mask_launch(dk_ctx* ctx, int engine, size_t n, const dk_state* states, uint64_t* mask_out, uint64_t drop_mask, uint64_t drop_count,
+                                   uint8_t* count_out, dk_stream stream) {
     if (n == 0) return DK_OK;
+    DK_ALIGNED(ctx, states, 16); DK_ALIGNED(ctx, mask_out, 8);
     DK_CUDA(ctx, cudaSetDevice(ctx->device));
     unsigned grid = (unsigned)((n + dk::STATE_THREADS - 1) / dk::STATE_THREADS);
     CUtensorMap tmap;
     if (state_tensor_map(ctx, states, n, &tmap)) {
-        if (engine == DK_FDO) dk::legal_mask_tma_kernel<DK_FDO><<<grid, dk::STATE_THREADS, 0, pick_stream(ctx, stream)>>>(tmap, (uint64_t)n, mask_out);
-        else dk::legal_mask_tma_kernel<DK_DOKO><<<grid, dk::STATE_THREADS, 0, pick_stream(ctx, stream)>>>(tmap, (uint64_t)n, mask_out);
+        if (engine == DK_FDO) dk::legal_mask_tma_kernel<DK_FDO><<<grid, dk::STATE_THREADS, 0, pick_stream(ctx, stream)>>>(tmap, (uint64_t)n, mask_out, drop_mask, drop_count, count_out);
+        else dk::legal_mask_tma_kernel<DK_DOKO><<<grid, dk::STATE_THREADS, 0, pick_stream(ctx, stream)>>>(tmap, (uint64_t)n, mask_out, drop_mask, drop_count, count_out);
         return check_launch(ctx, "legal_mask_tma_kernel");
     }
-    if (engine == DK_FDO) dk::legal_mask_kernel<DK_FDO><<<grid, dk::STATE_THREADS, 0, pick_stream(ctx, stream)>>>((uint64_t)n, states, mask_out);
-    else dk::legal_mask_kernel<DK_DOKO><<<grid, dk::STATE_THREADS, 0, pick_stream(ctx, stream)>>>((uint64_t)n, states, mask_out);
+    if (engine == DK_FDO) dk::legal_mask_kernel<DK_FDO><<<grid, dk::STATE_THREADS, 0, pick_stream(ctx, stream)>>>((uint64_t)n, states, mask_out, drop_mask, drop_count, count_out);
+    else dk::legal_mask_kernel<DK_DOKO><<<grid, dk::STATE_THREADS, 0, pick_stream(ctx, stream)>>>((uint64_t)n, states, mask_out, drop_mask, drop_count, count_out);
     return check_launch(ctx, "legal_mask_kernel");
+}
+dk_status dk_legal_mask(dk_ctx* ctx, int engine, size_t n, const dk_state* states, uint64_t* mask_out, dk_stream stream) {
+    if (!ctx || !states || !mask_out || (engine != DK_FDO && engine != DK_DOKO)) return DK_ERR_INVALID_ARGUMENT;
+    return legal_mask_launch(ctx, engine, n, states, mask_out, 0ull, 0ull, nullptr, stream);
+}
+dk_status dk_legal_mask_az(dk_ctx* ctx, size_t n, const dk_state* states, int is_secondary, uint64_t az_epoch, uint64_t* mask_out, uint8_t* n_allowed_out,
+                           dk_stream stream) {
+    if (!ctx || !states || (!mask_out && !n_allowed_out)) return DK_ERR_INVALID_ARGUMENT;
+    const uint64_t calls = 0x1Full << 33;                                      // AnnouncementReContra .. AnnouncementBlack
+    const bool young = az_epoch < DK_AZ_MIN_EPOCH;
+    return legal_mask_launch(ctx, DK_FDO, n, states, mask_out, (is_secondary || young) ? calls : 0ull, young ? calls : 0ull, n_allowed_out, stream);
+}
+dk_status dk_random_action(dk_ctx* ctx, int engine, size_t n, const dk_state* states, const dk_rng* rng, uint32_t flags, uint8_t* action_out, dk_stream stream) {
+    if (!ctx || !states || !rng || !action_out || (engine != DK_FDO && engine != DK_DOKO)) return DK_ERR_INVALID_ARGUMENT;
+    if (n == 0) return DK_OK;
+    DK_ALIGNED(ctx, states, 16);
+    DK_CUDA(ctx, cudaSetDevice(ctx->device));
+    unsigned grid = (unsigned)((n + dk::STATE_THREADS - 1) / dk::STATE_THREADS);
+    if (engine == DK_FDO) dk::random_action_kernel<DK_FDO><<<grid, dk::STATE_THREADS, 0, pick_stream(ctx, stream)>>>(to_params(rng), (uint64_t)n, states, flags, action_out);
+    else dk::random_action_kernel<DK_DOKO><<<grid, dk::STATE_THREADS, 0, pick_stream(ctx, stream)>>>(to_params(rng), (uint64_t)n, states, flags, action_out);
+    return check_launch(ctx, "random_action_kernel");
+}
+dk_status dk_state_id(dk_ctx* ctx, size_t n, const dk_state* states, const uint8_t* last_action, uint64_t* id_out, dk_stream stream) {
+    if (!ctx || !states || !id_out) return DK_ERR_INVALID_ARGUMENT;
+    if (n == 0) return DK_OK;
+    DK_ALIGNED(ctx, states, 16); DK_ALIGNED(ctx, id_out, 8);
+    DK_CUDA(ctx, cudaSetDevice(ctx->device));
+    unsigned grid = (unsigned)((n + dk::STATE_THREADS - 1) / dk::STATE_THREADS);
+    dk::state_id_kernel<<<grid, dk::STATE_THREADS, 0, pick_stream(ctx, stream)>>>((uint64_t)n, states, last_action, id_out);
+    return check_launch(ctx, "state_id_kernel");
 }
 
 dk_status dk_apply(dk_ctx* ctx, int engine, size_t n, dk_state* states, const uint8_t* action_idx, uint32_t flags, uint8_t* err_out, dk_stream stream) {
     if (!ctx || !states || !action_idx || (engine != DK_FDO && engine != DK_DOKO)) return DK_ERR_INVALID_ARGUMENT;
     if (n == 0) return DK_OK;
+    DK_ALIGNED(ctx, states, 16);
     DK_CUDA(ctx, cudaSetDevice(ctx->device));
     unsigned grid = (unsigned)((n + dk::STATE_THREADS - 1) / dk::STATE_THREADS);
     CUtensorMap tmap;
@@ -294,6 +353,7 @@ dk_status dk_apply(dk_ctx* ctx, int engine, size_t n, dk_state* states, const ui
 dk_status dk_terminal(dk_ctx* ctx, int engine, size_t n, const dk_state* states, uint8_t* done_out, int32_t* points_out, dk_stream stream) {
     if (!ctx || !states || (engine != DK_FDO && engine != DK_DOKO)) return DK_ERR_INVALID_ARGUMENT;
     if (n == 0) return DK_OK;
+    DK_ALIGNED(ctx, states, 16); DK_ALIGNED(ctx, points_out, 16);
     DK_CUDA(ctx, cudaSetDevice(ctx->device));
     unsigned grid = (unsigned)((n + dk::STATE_THREADS - 1) / dk::STATE_THREADS);
     dk::terminal_kernel<<<grid, dk::STATE_THREADS, 0, pick_stream(ctx, stream)>>>((uint64_t)n, states, done_out, (int4*)points_out);
@@ -305,6 +365,7 @@ dk_status dk_encode(dk_ctx* ctx, int layout, size_t n, const dk_state* states, i
     size_t len = layout == DK_LAYOUT_FDO_PI311 ? 311 : (layout == DK_LAYOUT_DO114 ? 114 : (layout == DK_LAYOUT_DO110 ? 110 : 0));
     if (len == 0 || row_stride < len) return DK_ERR_INVALID_ARGUMENT;
     if (n == 0) return DK_OK;
+    DK_ALIGNED(ctx, states, 16); DK_ALIGNED(ctx, out, 8);
     DK_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t s = pick_stream(ctx, stream);
     unsigned grid = (unsigned)((n + dk::ENC_THREADS - 1) / dk::ENC_THREADS);
@@ -318,6 +379,7 @@ dk_status dk_step_random_encode(dk_ctx* ctx, size_t n, dk_state* states, const d
                                 uint8_t* action_out, dk_stream stream) {
     if (!ctx || !states || !rng || (obs_out && row_stride < 311)) return DK_ERR_INVALID_ARGUMENT;
     if (n == 0) return DK_OK;
+    DK_ALIGNED(ctx, states, 16); DK_ALIGNED(ctx, obs_out, 8);
     DK_CUDA(ctx, cudaSetDevice(ctx->device));
     unsigned grid = (unsigned)((n + dk::ENC_THREADS - 1) / dk::ENC_THREADS);
     CUtensorMap tmap;
@@ -335,6 +397,7 @@ dk_status dk_determinize(dk_ctx* ctx, int engine, size_t n_info, size_t samples_
     if (engine != DK_FDO && engine != DK_DOKO) return DK_ERR_INVALID_ARGUMENT;
     if (n_info == 0 || samples_per_info == 0) return DK_OK;
     if (samples_per_info > 0xFFFFFFFFull || n_info > 0x7FFFFFFFull) return DK_ERR_INVALID_ARGUMENT;
+    DK_ALIGNED(ctx, states, 16); DK_ALIGNED(ctx, hands_out, 16); DK_ALIGNED(ctx, reservations_out, 4);
     DK_CUDA(ctx, cudaSetDevice(ctx->device));
     // Blocks per info-state: enough blocks for about 16 waves of 8 resident blocks per SM, at most one block per 128 samples.
     const uint64_t per_info_max = (samples_per_info + dk::MATCH_THREADS - 1) / dk::MATCH_THREADS, want = (uint64_t)ctx->sm_count * 128u;
@@ -357,6 +420,7 @@ dk_status dk_leaf_rollouts(dk_ctx* ctx, size_t n_leaves, size_t rollouts_per_lea
     if (!ctx || !states || !rng || !point_sum_out) return DK_ERR_INVALID_ARGUMENT;
     if (n_leaves == 0) return DK_OK;
     if (rollouts_per_leaf > 0x1000000ull || n_leaves > 0x7FFFFFFFull) return DK_ERR_INVALID_ARGUMENT;   // int32 block sums: |points| < 128
+    DK_ALIGNED(ctx, states, 16); DK_ALIGNED(ctx, point_sum_out, 8);
     DK_CUDA(ctx, cudaSetDevice(ctx->device));
     // Fewer leaves than one wave of blocks: several blocks per leaf (at most one per 128 rollouts), sums combined by integer atomics.
     const uint64_t per_leaf_max = (rollouts_per_leaf + dk::MATCH_THREADS - 1) / dk::MATCH_THREADS, wave = (uint64_t)ctx->sm_count * DK_LEAF_BLOCKS;
@@ -374,6 +438,7 @@ dk_status dk_encode_ipi(dk_ctx* ctx, size_t n, const dk_state* states, const uin
                         const uint8_t* next_player, int64_t* out, size_t row_stride, uint8_t* err_out, dk_stream stream) {
     if (!ctx || !states || !assumed_hands || !assumed_reservations || !next_player || !out || row_stride < 311) return DK_ERR_INVALID_ARGUMENT;
     if (n == 0) return DK_OK;
+    DK_ALIGNED(ctx, states, 16); DK_ALIGNED(ctx, assumed_hands, 16); DK_ALIGNED(ctx, assumed_reservations, 4); DK_ALIGNED(ctx, out, 8);
     DK_CUDA(ctx, cudaSetDevice(ctx->device));
     unsigned grid = (unsigned)((n + dk::ENC_THREADS - 1) / dk::ENC_THREADS);
     dk::encode_ipi_kernel<<<grid, dk::ENC_THREADS, 0, pick_stream(ctx, stream)>>>((uint64_t)n, states, assumed_hands, assumed_reservations, next_player, out,
@@ -389,6 +454,7 @@ dk_status dk_pimc_evaluate(dk_ctx* ctx, size_t n_roots, size_t n_det, size_t n_r
     // unit_hi of rollout (d, r) is (first_sub + d) * n_rollouts + r: keep it inside 32 bits; int32 block sums: |points| < 128
     if (n_rollouts == 0 || n_rollouts > 0x1000000ull || n_det > 0xFFFFFFFFull ||
         ((uint64_t)rng->first_sub + n_det) * n_rollouts > 0xFFFFFFFFull) return DK_ERR_INVALID_ARGUMENT;
+    DK_ALIGNED(ctx, states, 16); DK_ALIGNED(ctx, visits_out, 4); DK_ALIGNED(ctx, value_sum_out, 8);
     DK_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t s = pick_stream(ctx, stream);
     // two kernels (kernels.cuh "N2 in two kernels"): prepare every (root, determinization) at full width into a workspace, then one thread
@@ -476,6 +542,7 @@ struct dk_selfplay {
 dk_status dk_sp_create(dk_ctx* ctx, size_t max_games, const dk_sp_buffers* bufs, dk_selfplay** out) {
     if (!ctx || !out || !bufs || max_games == 0 || max_games > 0x7FFFFFFFull * dk::SP_THREADS / 2) return DK_ERR_INVALID_ARGUMENT;
     if (!bufs->states || !bufs->policy || !bufs->value || !bufs->player || !bufs->game) return DK_ERR_INVALID_ARGUMENT;
+    DK_ALIGNED(ctx, bufs->states, 8); DK_ALIGNED(ctx, bufs->policy, 4); DK_ALIGNED(ctx, bufs->value, 16); DK_ALIGNED(ctx, bufs->game, 4);
     DK_CUDA(ctx, cudaSetDevice(ctx->device));
     dk_selfplay* sp = new dk_selfplay();
     sp->ctx = ctx; sp->max_games = max_games;
@@ -512,6 +579,7 @@ dk_status dk_sp_begin_turn(dk_selfplay* sp, size_t n, const dk_state* states, ui
                            dk_stream stream) {
     if (!sp || !states || !rng || n > sp->max_games) return DK_ERR_INVALID_ARGUMENT;
     dk_ctx* ctx = sp->ctx;
+    DK_ALIGNED(ctx, states, 16);
     sp->turn_n = n;
     if (n == 0) return DK_OK;
     DK_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -547,6 +615,7 @@ dk_status dk_sp_uniform_search(dk_selfplay* sp, const dk_rng* rng, float* policy
 dk_status dk_sp_end_turn(dk_selfplay* sp, dk_state* states, const float* policy, const uint8_t* action, uint8_t* err_out, dk_stream stream) {
     if (!sp || !states || !policy || !action) return DK_ERR_INVALID_ARGUMENT;
     dk_ctx* ctx = sp->ctx;
+    DK_ALIGNED(ctx, states, 16); DK_ALIGNED(ctx, policy, 4);
     size_t n = sp->turn_n;
     if (n == 0) return DK_OK;
     DK_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -557,6 +626,7 @@ dk_status dk_sp_end_turn(dk_selfplay* sp, dk_state* states, const float* policy,
 dk_status dk_sp_finalize(dk_selfplay* sp, const dk_state* states, dk_stream stream) {
     if (!sp || !states) return DK_ERR_INVALID_ARGUMENT;
     dk_ctx* ctx = sp->ctx;
+    DK_ALIGNED(ctx, states, 16);
     DK_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t s = pick_stream(ctx, stream);
     DK_CUDA(ctx, cudaMemsetAsync(sp->counters + 2, 0, sizeof(unsigned long long), s));
@@ -603,6 +673,7 @@ dk_status dk_uct_search(dk_ctx* ctx, size_t n_roots, size_t trees_per_root, int 
     if (iterations == 0 || iterations > 0x7FFFFFFFull || n_trees > 0x7FFFFFFFull * dk::UCT_THREADS / 2 ||
         ((uint64_t)rng->first_sub + trees_per_root) * iterations > 0xFFFFFFFFull || workspace_bytes < dk_uct_workspace_bytes(n_trees, iterations))
         return DK_ERR_INVALID_ARGUMENT;
+    DK_ALIGNED(ctx, states, 16); DK_ALIGNED(ctx, visits_out, 4); DK_ALIGNED(ctx, values_out, 4);
     DK_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t s = pick_stream(ctx, stream);
     if (ctx->ln_table_len < iterations + 1) {
@@ -692,11 +763,11 @@ dk_status dk_allreduce_root_stats(dk_ctx* ctx, size_t n_values, int64_t* values,
 // copied to the host on the copy stream, so the PCIe transfer overlaps the simulation (pinned host buffers make the copies truly
 // asynchronous; pageable ones still work).
 static dk_status playout_host_impl(dk_ctx* ctx, int engine, uint32_t flags, size_t n, const dk_state* states_host, const dk_rng* rng,
-                                   void* points_out_host, void* steps_out_host, bool compact) {
+                                   void* points_out_host, void* steps_out_host, uint32_t mode) {
     if (!ctx || !rng || (engine != DK_FDO && engine != DK_DOKO)) return DK_ERR_INVALID_ARGUMENT;
     if (n == 0) return DK_OK;
     DK_CUDA(ctx, cudaSetDevice(ctx->device));
-    const size_t pb = compact ? 4 : 16, sb = compact ? 1 : 4;
+    const size_t pb = mode == dk::OUT_INT32 ? 16 : (mode == dk::OUT_COMPACT ? 4 : 2), sb = mode == dk::OUT_INT32 ? 4 : 1;
     size_t b_states = states_host ? n * sizeof(dk_state) : 0, b_pts = n * pb, b_steps = n * sb;
     b_pts = (b_pts + 255) & ~(size_t)255;
     dk_status st = ensure_scratch(ctx, b_states + b_pts + b_steps);
@@ -738,7 +809,8 @@ static dk_status playout_host_impl(dk_ctx* ctx, int engine, uint32_t flags, size
         rc.first_id = rp.first_id + off;
         // chunk kernels alternate between two streams: the blocks of chunk c + 1 fill the SMs that the last wave of chunk c leaves idle
         cudaStream_t cs = (c & 1u) ? ctx->stream2 : ctx->stream;
-        st = playout_launch(ctx, engine, flags, cnt, d_states ? d_states + off : nullptr, rc, d_pts + off * pb, d_steps + off * sb, compact, cs);
+        st = playout_launch(ctx, engine, flags, cnt, d_states ? d_states + off : nullptr, rc, points_out_host ? d_pts + off * pb : nullptr,
+                            steps_out_host ? d_steps + off * sb : nullptr, mode, nullptr, cs);
         if (st != DK_OK) return st;
         DK_CUDA(ctx, cudaEventRecord(ctx->events[c], cs));
         DK_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->events[c], 0));
@@ -754,12 +826,32 @@ static dk_status playout_host_impl(dk_ctx* ctx, int engine, uint32_t flags, size
 
 dk_status dk_playout_host(dk_ctx* ctx, int engine, uint32_t flags, size_t n, const dk_state* states_host, const dk_rng* rng,
                           int32_t* points_out_host, uint32_t* steps_out_host) {
-    return playout_host_impl(ctx, engine, flags, n, states_host, rng, points_out_host, steps_out_host, false);
+    return playout_host_impl(ctx, engine, flags, n, states_host, rng, points_out_host, steps_out_host, dk::OUT_INT32);
 }
 
 dk_status dk_playout_host_compact(dk_ctx* ctx, int engine, uint32_t flags, size_t n, const dk_state* states_host, const dk_rng* rng,
                                   int8_t* points_out_host, uint8_t* steps_out_host) {
-    return playout_host_impl(ctx, engine, flags, n, states_host, rng, points_out_host, steps_out_host, true);
+    return playout_host_impl(ctx, engine, flags, n, states_host, rng, points_out_host, steps_out_host, dk::OUT_COMPACT);
+}
+
+dk_status dk_playout_host_packed(dk_ctx* ctx, int engine, uint32_t flags, size_t n, const dk_state* states_host, const dk_rng* rng,
+                                 uint16_t* points_packed_out_host, uint8_t* steps_out_host) {
+    return playout_host_impl(ctx, engine, flags, n, states_host, rng, points_packed_out_host, steps_out_host, dk::OUT_PACKED);
+}
+
+dk_status dk_playout_summary_host(dk_ctx* ctx, int engine, uint32_t flags, size_t n, const dk_state* states_host, const dk_rng* rng,
+                                  dk_playout_stats* stats_out_host) {
+    if (!ctx || !rng || !stats_out_host || (engine != DK_FDO && engine != DK_DOKO)) return DK_ERR_INVALID_ARGUMENT;
+    DK_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t b_states = states_host ? n * sizeof(dk_state) : 0, b_stats = (sizeof(dk_playout_stats) + 255) & ~(size_t)255;
+    DK_TRY(ensure_scratch(ctx, b_stats + b_states));
+    dk_playout_stats* d_stats = (dk_playout_stats*)ctx->d_scratch;
+    dk_state* d_states = states_host ? (dk_state*)((char*)ctx->d_scratch + b_stats) : nullptr;
+    if (states_host && n) DK_CUDA(ctx, cudaMemcpyAsync(d_states, states_host, b_states, cudaMemcpyHostToDevice, ctx->stream));
+    DK_TRY(dk_playout_summary(ctx, engine, flags, n, d_states, rng, d_stats, 0, ctx->stream));
+    DK_CUDA(ctx, cudaMemcpyAsync(stats_out_host, d_stats, sizeof(dk_playout_stats), cudaMemcpyDeviceToHost, ctx->stream));
+    DK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return DK_OK;
 }
 
 }  // extern "C"

@@ -64,15 +64,60 @@ __device__ __forceinline__ RngKey make_key(const RngParams& rp, uint64_t index, 
     return k;
 }
 
-// Playout results: int32[4] points + uint32 steps, or the compact host-transfer form int8[4] + uint8 (lossless: |points| < 128,
-// steps < 256) selected at run time (uniform branch).
-__device__ __forceinline__ void store_result(void* __restrict__ points, void* __restrict__ steps, uint64_t i, const int32_t p[4], uint32_t s, bool compact) {
-    if (compact) {
-        if (points) reinterpret_cast<char4*>(points)[i] = make_char4((signed char)p[0], (signed char)p[1], (signed char)p[2], (signed char)p[3]);
-        if (steps) reinterpret_cast<uint8_t*>(steps)[i] = (uint8_t)s;
-    } else {
+// Playout results, selected at run time (uniform branch) by `mode`:
+//   OUT_INT32    int32[4] points + uint32 steps (20 B per game)
+//   OUT_COMPACT  int8[4] + uint8 — lossless: |points| < 128, steps < 256 (5 B per game over PCIe)
+//   OUT_PACKED   uint16 points + uint8 steps (3 B per game; 2 B when the caller does not want the step counts).  The four points of a
+//                game take two values (Re seats / Kontra seats, FdoEndOfGameStats::calculate, stats.rs:215-231) and sum to zero, so seat 0's
+//                points (int8) plus "which of seats 1..3 score like seat 0" (3 bits) determine all four: decode with dk_unpack_points.
+enum : uint32_t { OUT_INT32 = 0u, OUT_COMPACT = 1u, OUT_PACKED = 2u };
+__device__ __forceinline__ uint32_t pack_points(const int32_t p[4]) {
+    const uint32_t same = (p[1] == p[0] ? 1u : 0u) | (p[2] == p[0] ? 2u : 0u) | (p[3] == p[0] ? 4u : 0u);
+    return ((uint32_t)p[0] & 255u) | (same << 8);
+}
+__device__ __forceinline__ void store_result(void* __restrict__ points, void* __restrict__ steps, uint64_t i, const int32_t p[4], uint32_t s, uint32_t mode) {
+    if (mode == OUT_INT32) {
         if (points) reinterpret_cast<int4*>(points)[i] = make_int4(p[0], p[1], p[2], p[3]);
         if (steps) reinterpret_cast<uint32_t*>(steps)[i] = s;
+    } else {
+        if (points) {
+            if (mode == OUT_COMPACT) reinterpret_cast<char4*>(points)[i] = make_char4((signed char)p[0], (signed char)p[1], (signed char)p[2], (signed char)p[3]);
+            else reinterpret_cast<uint16_t*>(points)[i] = (uint16_t)pack_points(p);
+        }
+        if (steps) reinterpret_cast<uint8_t*>(steps)[i] = (uint8_t)s;
+    }
+}
+
+// Device-side reduction of a playout batch (dk_playout_summary): what an evaluator keeps of a batch of games — counts, sums, sums of
+// squares, wins and the histogram of the number of actions — so that the device->host result is 2 KB per call instead of bytes per game
+// (the host-side ingest of per-game results is what stops scaling at 8 GPUs per host).  Integer sums: order independent, bit-reproducible.
+// Word layout of dk_playout_stats (include/doko_cuda.h): [0] games | [1] game steps | [2,6) point sums | [6,10) sums of squares |
+// [10,14) wins | [14,270) step histogram.
+constexpr uint32_t STATS_WORDS = 270u;
+struct BlockStats { uint32_t w[STATS_WORDS]; };   // per-block partial sums (32 bit: <= 640 games per block; point sums as two's complement)
+__device__ __forceinline__ void block_stats_clear(BlockStats& sm) {                 // caller syncs
+    for (uint32_t k = threadIdx.x; k < STATS_WORDS; k += blockDim.x) sm.w[k] = 0u;
+}
+// Every thread of the block calls this (valid = the thread holds a game of the batch); ends with the block's flush to `stats`.
+__device__ __forceinline__ void block_stats_add(BlockStats& sm, unsigned long long* __restrict__ stats, const int32_t p[4], uint32_t s, bool valid) {
+    const unsigned full = 0xFFFFFFFFu;
+    const bool lead = (threadIdx.x & 31u) == 0u;
+    const uint32_t g = (uint32_t)__popc(__ballot_sync(full, valid));
+    const uint32_t st = __reduce_add_sync(full, valid ? s : 0u);
+    if (lead) { atomicAdd(&sm.w[0], g); atomicAdd(&sm.w[1], st); }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int v = valid ? p[q] : 0;
+        const int sum = __reduce_add_sync(full, v);
+        const uint32_t sq = __reduce_add_sync(full, (uint32_t)(v * v));
+        const uint32_t wins = (uint32_t)__popc(__ballot_sync(full, v > 0));
+        if (lead) { atomicAdd(&sm.w[2 + q], (uint32_t)sum); atomicAdd(&sm.w[6 + q], sq); atomicAdd(&sm.w[10 + q], wins); }
+    }
+    if (valid) atomicAdd(&sm.w[14u + (s < 255u ? s : 255u)], 1u);
+    __syncthreads();
+    for (uint32_t k = threadIdx.x; k < STATS_WORDS; k += blockDim.x) {
+        const uint32_t v = sm.w[k];
+        if (v) atomicAdd(stats + k, (k >= 2u && k < 6u) ? (unsigned long long)(long long)(int32_t)v : (unsigned long long)v);   // point sums are signed
     }
 }
 
@@ -90,12 +135,14 @@ constexpr int FDO_FRESH_THREADS = DK_FDO_FRESH_THREADS;
 constexpr uint32_t FDO_FRESH_SMEM_BYTES = 4u * (CARD_LUT_WORDS + SEL12_WORDS + 12u * FDO_FRESH_THREADS);   // dynamic: above the 48 KB static limit
 template <bool WITH_ANN>
 __global__ void __launch_bounds__(FDO_FRESH_THREADS, DK_FDO_FRESH_BLOCKS)
-fdo_playout_fresh_kernel(RngParams rp, uint64_t n, void* __restrict__ points, void* __restrict__ steps, bool compact) {
+fdo_playout_fresh_kernel(RngParams rp, uint64_t n, void* __restrict__ points, void* __restrict__ steps, uint32_t mode, unsigned long long* __restrict__ stats) {
     extern __shared__ __align__(16) uint32_t fresh_smem[];
+    __shared__ BlockStats bstats;
     uint32_t* lut = fresh_smem;                                        // CARD_LUT_WORDS + SEL12_WORDS words (16-byte aligned, SEL12 part 8-byte aligned)
     uint32_t* smem = fresh_smem + CARD_LUT_WORDS + SEL12_WORDS;        // the shuffle scratch: 12 words per thread, word-interleaved
     fill_card_lut(lut);
     fill_sel12(lut);
+    if (stats) block_stats_clear(bstats);
     __syncthreads();
     uint64_t i = (uint64_t)blockIdx.x * FDO_FRESH_THREADS + threadIdx.x;
     // Out-of-range lanes play game n-1 again (keeps the warp converged); they just do not store.
@@ -106,7 +153,8 @@ fdo_playout_fresh_kernel(RngParams rp, uint64_t n, void* __restrict__ points, vo
     int32_t p[4];
     uint32_t s;
     fdo_playout_fresh<WITH_ANN, SharedDeckT<FDO_FRESH_THREADS>, true>(key, deck, lut, p, s);
-    if (i < n) store_result(points, steps, i, p, s, compact);
+    if (i < n) store_result(points, steps, i, p, s, mode);
+    if (stats) block_stats_add(bstats, stats, p, s, i < n);          // uniform branch
 }
 
 
@@ -114,13 +162,15 @@ fdo_playout_fresh_kernel(RngParams rp, uint64_t n, void* __restrict__ points, vo
 // TRACE additionally writes the 52 action ids and (wedding flag, re mask, packed eyes, packed tricks) per game.
 template <bool TRACE>
 __global__ void __launch_bounds__(FDO_FRESH_THREADS, DK_FDO_FRESH_BLOCKS)
-doko_playout_fresh_kernel(RngParams rp, uint64_t n, void* __restrict__ points, void* __restrict__ steps, bool compact,
+doko_playout_fresh_kernel(RngParams rp, uint64_t n, void* __restrict__ points, void* __restrict__ steps, uint32_t mode, unsigned long long* __restrict__ stats,
                           uint8_t* __restrict__ trace, uint4* __restrict__ aux) {
     extern __shared__ __align__(16) uint32_t fresh_smem[];
+    __shared__ BlockStats bstats;
     uint32_t* lut = fresh_smem;
     uint32_t* smem = fresh_smem + CARD_LUT_WORDS + SEL12_WORDS;
     fill_card_lut(lut);
     fill_sel12(lut);
+    if (stats) block_stats_clear(bstats);
     __syncthreads();
     uint64_t i = (uint64_t)blockIdx.x * FDO_FRESH_THREADS + threadIdx.x;
     uint64_t gi = i < n ? i : n - 1;
@@ -132,12 +182,13 @@ doko_playout_fresh_kernel(RngParams rp, uint64_t n, void* __restrict__ points, v
     uint8_t tr[52];
     doko_playout_fresh<TRACE, SharedDeckT<FDO_FRESH_THREADS>, true>(key, deck, lut, p, s, tr, ax);
     if (i < n) {
-        store_result(points, steps, i, p, s, compact);
+        store_result(points, steps, i, p, s, mode);
         if (TRACE) {
             if (trace) for (int k = 0; k < 52; ++k) trace[i * 52 + k] = tr[k];
             if (aux) aux[i] = make_uint4(ax[0], ax[1], ax[2], ax[3]);
         }
     }
+    if (stats) block_stats_add(bstats, stats, p, s, i < n);          // uniform branch
 }
 
 // ---- state record I/O --------------------------------------------------------------------------------------------------
@@ -226,16 +277,25 @@ from_deals_kernel(uint64_t n, const uint64_t* __restrict__ hands, const uint8_t*
     st_new_game(s, h, start[i] & 3u);
     store_state(out + i, s);
 }
+// dk_legal_mask / dk_legal_mask_az: the mask written is legal & ~drop_mask (AzEnvState::allowed_actions_by_action_index removes the calls
+// when is_secondary || epoch < MIN_EPOCH), the count is popc(legal & ~drop_count) (number_of_allowed_actions(epoch) looks at the epoch only;
+// rs-doko-alpha-zero/src/env/envs/full_doko/full_doko.rs:80-119).
+__device__ __forceinline__ void store_legal(uint64_t legal, uint64_t i, uint64_t* __restrict__ mask_out, uint64_t drop_mask, uint64_t drop_count,
+                                            uint8_t* __restrict__ count_out) {
+    if (mask_out) mask_out[i] = legal & ~drop_mask;
+    if (count_out) count_out[i] = (uint8_t)popcll(legal & ~drop_count);
+}
 template <int ENGINE>
 __global__ void __launch_bounds__(STATE_THREADS)
-legal_mask_kernel(uint64_t n, const dk_state* __restrict__ states, uint64_t* __restrict__ mask_out) {
+legal_mask_kernel(uint64_t n, const dk_state* __restrict__ states, uint64_t* __restrict__ mask_out, uint64_t drop_mask, uint64_t drop_count,
+                  uint8_t* __restrict__ count_out) {
     __shared__ uint4 stage[STATE_THREADS * 8];
     const uint64_t first = (uint64_t)blockIdx.x * STATE_THREADS, i = first + threadIdx.x;
     StateStage<STATE_THREADS>::load(states, first, n, stage);
     if (i >= n) return;
     alignas(16) dk_state s;
     StateStage<STATE_THREADS>::get(stage, s);
-    mask_out[i] = ENGINE == DK_FDO ? fdo_state_legal_mask(s) : doko_state_legal_mask(s);
+    store_legal(ENGINE == DK_FDO ? fdo_state_legal_mask(s) : doko_state_legal_mask(s), i, mask_out, drop_mask, drop_count, count_out);
 }
 // 8 blocks of 128 threads per SM (64 registers, 8 bytes of spill in the full-rules instance): 0.283 -> 0.243 ms per 2^22 records.
 // A two-buffer cp.async pipeline over tiles (bytes in flight independent of the resident thread count) was measured and is
@@ -368,7 +428,8 @@ from_deals_tma_kernel(const __grid_constant__ CUtensorMap tmap, uint64_t n, cons
 }
 template <int ENGINE>
 __global__ void __launch_bounds__(STATE_THREADS)
-legal_mask_tma_kernel(const __grid_constant__ CUtensorMap tmap, uint64_t n, uint64_t* __restrict__ mask_out) {
+legal_mask_tma_kernel(const __grid_constant__ CUtensorMap tmap, uint64_t n, uint64_t* __restrict__ mask_out, uint64_t drop_mask, uint64_t drop_count,
+                      uint8_t* __restrict__ count_out) {
     __shared__ __align__(1024) uint4 stage[STATE_THREADS * 8];
     __shared__ __align__(8) unsigned long long bar;
     const uint64_t first = (uint64_t)blockIdx.x * STATE_THREADS, i = first + threadIdx.x;
@@ -379,7 +440,53 @@ legal_mask_tma_kernel(const __grid_constant__ CUtensorMap tmap, uint64_t n, uint
     if (i >= n) return;
     alignas(16) dk_state s;
     StateStage<STATE_THREADS>::get(stage, s);
-    mask_out[i] = ENGINE == DK_FDO ? fdo_state_legal_mask(s) : doko_state_legal_mask(s);
+    store_legal(ENGINE == DK_FDO ? fdo_state_legal_mask(s) : doko_state_legal_mask(s), i, mask_out, drop_mask, drop_count, count_out);
+}
+// dk_state_id: AzEnvState::id() (rs-doko-alpha-zero/src/env/envs/full_doko/full_doko.rs:156-167) = FxHasher64 over the state and the last
+// action.  The hash function is fxhash 0.2.1's (hash = (hash.rotate_left(5) ^ word) * 0x517cc1b727220a95 per 64-bit word), fed with the
+// sixteen little-endian 64-bit words of the record followed by the last action as one more word (DK_ACTION_NONE = None); the reference
+// feeds its own in-memory layout of FdoState + FdoObservation, so the VALUES differ by construction — equal states give equal ids and
+// the record is canonical (one byte pattern per state), which is the property an id() caller can rely on.  (No caller exists in the
+// reference; the author marks the function as wrong.)
+__device__ __forceinline__ uint64_t fx_add(uint64_t h, uint64_t w) { return (((h << 5) | (h >> 59)) ^ w) * 0x517cc1b727220a95ull; }
+__global__ void __launch_bounds__(STATE_THREADS)
+state_id_kernel(uint64_t n, const dk_state* __restrict__ states, const uint8_t* __restrict__ last_action, uint64_t* __restrict__ id_out) {
+    __shared__ uint4 stage[STATE_THREADS * 8];
+    const uint64_t first = (uint64_t)blockIdx.x * STATE_THREADS, i = first + threadIdx.x;
+    StateStage<STATE_THREADS>::load(states, first, n, stage);
+    if (i >= n) return;
+    uint64_t h = 0;
+    const uint32_t t = threadIdx.x;
+#pragma unroll
+    for (uint32_t j = 0; j < 8u; ++j) {
+        const uint4 q = stage[t * 8u + (j ^ (t & 7u))];
+        h = fx_add(h, (uint64_t)q.x | ((uint64_t)q.y << 32));
+        h = fx_add(h, (uint64_t)q.z | ((uint64_t)q.w << 32));
+    }
+    h = fx_add(h, last_action ? (uint64_t)last_action[i] : (uint64_t)ACTION_NONE);
+    id_out[i] = h;
+}
+// dk_random_action: FdoAllowedActions::random (rs-game-utils/src/bit_flag.rs:86-94) over the legal set of the seat to move, with or
+// without the announcement calls — the draw of the random policies (FdoState::random_action_for_current_player[_no_announcement],
+// state.rs:378-431) and of DefaultImpiPolicy's fallback (compare_impi.rs:357-368) WITHOUT playing it.  Same stream position as the
+// lock-step env step (SITE_STEP word 0 of the unit): dk_step_random_encode with the same rng plays exactly this action.
+template <int ENGINE>
+__global__ void __launch_bounds__(STATE_THREADS)
+random_action_kernel(RngParams rp, uint64_t n, const dk_state* __restrict__ states, uint32_t flags, uint8_t* __restrict__ action_out) {
+    __shared__ uint4 stage[STATE_THREADS * 8];
+    const uint64_t first = (uint64_t)blockIdx.x * STATE_THREADS, i = first + threadIdx.x;
+    StateStage<STATE_THREADS>::load(states, first, n, stage);
+    if (i >= n) return;
+    alignas(16) dk_state s;
+    StateStage<STATE_THREADS>::get(stage, s);
+    uint64_t legal = ENGINE == DK_FDO ? fdo_state_legal_mask(s) : doko_state_legal_mask(s);
+    if (!(flags & DK_PLAYOUT_WITH_ANNOUNCEMENTS)) legal &= ~(0x1Full << 33);
+    uint32_t a = ACTION_NONE;
+    if (legal) {
+        const U4 blk = rng_block(make_key(rp, i, 0, false), SITE_STEP, 0);
+        a = pick_msb_rank64(legal, mulhi(blk.x, popcll(legal)));
+    }
+    action_out[i] = (uint8_t)a;
 }
 __global__ void __launch_bounds__(STATE_THREADS)
 terminal_kernel(uint64_t n, const dk_state* __restrict__ states, uint8_t* __restrict__ done_out, int4* __restrict__ points_out) {
@@ -663,13 +770,17 @@ constexpr int PLAYOUT_STATE_THREADS = 256;
 template <int ENGINE, bool WITH_ANN>
 __global__ void __launch_bounds__(PLAYOUT_STATE_THREADS)
 playout_state_kernel(RngParams rp, uint64_t n, const dk_state* __restrict__ states, uint32_t per_unit, void* __restrict__ points,
-                     void* __restrict__ steps, bool compact) {
+                     void* __restrict__ steps, uint32_t mode, unsigned long long* __restrict__ stats) {
     __shared__ __align__(16) uint32_t lut[CARD_LUT_WORDS + SEL12_WORDS];
+    __shared__ BlockStats bstats;
     fill_card_lut(lut);
     fill_sel12(lut);
+    if (stats) block_stats_clear(bstats);
     __syncthreads();
-    uint64_t i = (uint64_t)blockIdx.x * PLAYOUT_STATE_THREADS + threadIdx.x;
-    if (i >= n) return;
+    const uint64_t i_raw = (uint64_t)blockIdx.x * PLAYOUT_STATE_THREADS + threadIdx.x;
+    const bool valid = i_raw < n;
+    if (!valid && !stats) return;
+    const uint64_t i = valid ? i_raw : n - 1;                          // with a summary every thread stays for the block reduction
     uint64_t unit = per_unit > 1u ? i / per_unit : i;
     RngKey key = make_key(rp, unit, per_unit > 1u ? (uint32_t)(i % per_unit) : 0u, per_unit > 1u);
     alignas(16) dk_state s;
@@ -685,7 +796,8 @@ playout_state_kernel(RngParams rp, uint64_t n, const dk_state* __restrict__ stat
         if (doko_state_to_live(s, g, rs)) { doko_play_to_end<false, false, true>(g, key, &rs, nullptr, lut); doko_final_points(g, p); st = g.steps; }
         else { p[0] = s.points[0]; p[1] = s.points[1]; p[2] = s.points[2]; p[3] = s.points[3]; }
     }
-    store_result(points, steps, i, p, st, compact);
+    if (valid) store_result(points, steps, i, p, st, mode);
+    if (stats) block_stats_add(bstats, stats, p, st, valid);          // uniform branch
 }
 
 

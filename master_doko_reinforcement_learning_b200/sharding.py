@@ -32,7 +32,9 @@ def pimc_decide(dk, states, n_det, strategy, rng_seed, first_id=0, epoch=0, n_ro
     """Sharded PIMC move decision (DefaultImpiPolicy::execute, compare_impi.rs:212-372): every rank takes a contiguous share of the
     determinizations of EVERY root (sample numbers first_sub .. first_sub+count-1), evaluates them with the flat Monte-Carlo policy
     (`n_rollouts`) or the UCT search (`uct_iterations`), reduces them to integer root statistics, all-reduces those and picks.
-    All ranks return the same actions (uint8 [n], 0xFF = no successful sample)."""
+    A root without a single successful sample gets the reference's fallback: a random action among the allowed non-announcement
+    actions (compare_impi.rs:357-368; dk_random_action on the stream (rng_seed, first_id + i, epoch)) — the same on every rank, since the
+    statistics are.  All ranks return (actions uint8 [n] — 0xFF only for finished games —, stats int64 [n, ROOT_STATS])."""
     import torch.distributed as dist
 
     world, rank = (dist.get_world_size(group), dist.get_rank(group)) if dist.is_available() and dist.is_initialized() else (1, 0)
@@ -53,4 +55,8 @@ def pimc_decide(dk, states, n_det, strategy, rng_seed, first_id=0, epoch=0, n_ro
         stats = torch.zeros((states.shape[0], ROOT_STATS), dtype=torch.int64, device=states.device)
     if world > 1:
         dk.allreduce_root_stats(stats)
-    return dk.pimc_pick(strategy, stats, allowed), stats
+    import torch
+
+    action = dk.pimc_pick(strategy, stats, allowed)
+    fallback = dk.random_action(1, states, dk.rng(rng_seed, first_id, epoch), flags=0)
+    return torch.where(action == 0xFF, fallback, action), stats

@@ -746,3 +746,120 @@ ORC_API double orc_cpu_baseline(int kind, uint64_t seed, uint64_t n_units, uint3
     if (work_out) *work_out = total;
     return sec;
 }
+
+// ---- bulk checkers for the full-size GPU parity tests (tests/test_gpu_parity_at_size.py) -------------------------------------------
+// A batch of oracle states made by a recipe, exported as dk_state records for the GPU and kept as oracle objects for the checks:
+// game first_id + i is dealt from the Philox stream (unit, epoch) and advanced with the random policy (announcements included).
+//   mode 0  BASELINE config 3: until card_index reaches 8 / 16 / 24 / 32 (round-robin over i)
+//   mode 1  the reference's determinization soak (rs-full-doko-cmd/src/main.rs:190-283 tests card_matching at EVERY state of a game):
+//           (i * 2654435761 >> 16) % 96 actions, never the last card — reservation-phase, announcement-phase and card-phase states
+// rs-doko (engine 0): 4 reservations + the same number of cards.
+namespace {
+struct BulkStates { int engine = DK_FDO; std::vector<fdo::State> f; std::vector<doko::State> d; };
+template <class F> void parallel_for(uint64_t n, int n_threads, F&& body) {
+    if (n_threads <= 0) n_threads = (int)std::thread::hardware_concurrency();
+    if (n_threads < 1) n_threads = 1;
+    std::vector<std::thread> th;
+    uint64_t per = (n + n_threads - 1) / n_threads;
+    for (int t = 0; t < n_threads; ++t) {
+        uint64_t lo = (uint64_t)t * per, hi = lo + per > n ? n : lo + per;
+        if (lo >= hi) break;
+        th.emplace_back([=, &body] { for (uint64_t i = lo; i < hi; ++i) body(i); });
+    }
+    for (auto& x : th) x.join();
+}
+}  // namespace
+ORC_API void* orc_bulk_make(int engine, uint64_t n, uint64_t seed, uint64_t first_id, uint32_t epoch, int mode, dk_state* recs_out, int n_threads) {
+    BulkStates* b = new BulkStates();
+    b->engine = engine;
+    if (engine == DK_FDO) b->f.resize((size_t)n); else b->d.resize((size_t)n);
+    parallel_for(n, n_threads, [&](uint64_t i) {
+        const uint64_t unit = first_id + i;
+        PhiloxStream r(seed, (uint32_t)unit, (uint32_t)(unit >> 32), epoch);
+        const int quota = (int)((((uint32_t)i * 2654435761u) >> 16) % 96u);
+        const int target = 8 * (1 + (int)(i & 3));
+        if (engine == DK_FDO) {
+            fdo::State s = fdo::State::new_game(r);
+            if (mode == 0) { while (s.current_phase != fdo::PH_FINISHED && s.card_index < target) s.random_action_for_current_player(r); }
+            else for (int k = 0; k < quota; ++k) {
+                if (s.current_phase == fdo::PH_PLAYCARD && s.card_index == 47) break;
+                if (s.random_action_for_current_player(r)) break;
+            }
+            b->f[(size_t)i] = s;
+            if (recs_out) export_fdo(s, recs_out + i);
+        } else {
+            doko::State s = doko::State::new_game(r);
+            const int steps = mode == 0 ? 4 + target : (quota < 51 ? quota : 51);
+            for (int k = 0; k < steps; ++k) if (s.random_action_for_current_player(r)) break;
+            b->d[(size_t)i] = s;
+            if (recs_out) export_doko(s, recs_out + i);
+        }
+    });
+    return b;
+}
+ORC_API void orc_bulk_free(void* h) { delete (BulkStates*)h; }
+// card_matching (engine 1) / sample_assignment_full (engine 0): S samples per state on the stream (first_id + i, first_sub + s, epoch).
+// hands_out[(i*S+s)*4], res_out[(i*S+s)*4] (DK_RES_* / 0xFF; engine 1 only), status_out[i*S+s], consistent_out[i*S+s] (engine 1, nullable:
+// is_consistent's reason code, 0 = consistent, -1 = not checked because the sample failed).
+ORC_API double orc_bulk_determinize(const void* h, uint32_t S, uint64_t seed, uint64_t first_id, uint32_t epoch, uint32_t first_sub, uint64_t* hands_out,
+                                    uint8_t* res_out, uint8_t* status_out, int8_t* consistent_out, int n_threads) {
+    const BulkStates& b = *(const BulkStates*)h;
+    const uint64_t n = b.engine == DK_FDO ? b.f.size() : b.d.size();
+    auto t0 = std::chrono::steady_clock::now();
+    parallel_for(n, n_threads, [&](uint64_t i) {
+        const uint64_t unit = first_id + i;
+        for (uint32_t s = 0; s < S; ++s) {
+            const uint64_t o = i * S + s;
+            PhiloxStream r(seed, (uint32_t)unit, first_sub + s, epoch);
+            if (b.engine == DK_FDO) {
+                fdo::Hand oh[4]; int ores[4] = {-1, -1, -1, -1}; int status = 2;
+                const fdo::State& st = b.f[(size_t)i];
+                if (st.current_phase != fdo::PH_FINISHED) { try { status = fdo::card_matching(st, r, oh, ores); } catch (const std::exception&) { status = 9; } }
+                for (int p = 0; p < 4; ++p) { hands_out[o * 4 + p] = status == 2 ? 0 : oh[p].bits; if (res_out) res_out[o * 4 + p] = (status == 2 || ores[p] < 0) ? (uint8_t)DK_RES_NONE : (uint8_t)ores[p]; }
+                status_out[o] = (uint8_t)status;
+                if (consistent_out) {
+                    int rc = -1;
+                    if (status == 0) { int ar[4]; for (int p = 0; p < 4; ++p) ar[p] = ores[p] < 0 ? (int)fdo::R_NONE : ores[p]; try { rc = fdo::is_consistent(st, oh, ar); } catch (const std::exception&) { rc = 99; } }
+                    consistent_out[o] = (int8_t)rc;
+                }
+            } else {
+                uint64_t hands[4] = {0, 0, 0, 0}; int status = 9;
+                try { status = doko::sample_assignment_full(b.d[(size_t)i], r, hands); } catch (const std::exception&) {}
+                for (int p = 0; p < 4; ++p) hands_out[o * 4 + p] = hands[p];
+                status_out[o] = (uint8_t)status;
+            }
+        }
+    });
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+// [card_matching →] random_rollout (no-announcement policy) R times per state on the stream (first_id + i, first_sub + r, epoch):
+// sums_out[i*4 + seat] = exact sum of player_points (failed samples add 0), the quantity dk_leaf_rollouts returns.
+ORC_API double orc_bulk_leaf_rollouts(const void* h, uint32_t R, uint64_t seed, uint64_t first_id, uint32_t epoch, uint32_t first_sub, int determinize,
+                                      int64_t* sums_out, int n_threads) {
+    const BulkStates& b = *(const BulkStates*)h;
+    const uint64_t n = b.f.size();
+    auto t0 = std::chrono::steady_clock::now();
+    parallel_for(n, n_threads, [&](uint64_t i) {
+        int64_t acc[4] = {0, 0, 0, 0};
+        for (uint32_t k = 0; k < R; ++k) {
+            int32_t pts[4]; 
+            if (orc_fdo_leaf_rollout_philox(&b.f[(size_t)i], seed, first_id + i, first_sub + k, epoch, determinize, pts, nullptr) == 0)
+                for (int p = 0; p < 4; ++p) acc[p] += pts[p];
+        }
+        for (int p = 0; p < 4; ++p) sums_out[i * 4 + p] = acc[p];
+    });
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+// Lock-step env step (dk_step_random_encode) on every state of the batch: returns the actions; states advance in place.
+ORC_API void orc_bulk_step(void* h, uint64_t seed, uint64_t first_id, uint32_t epoch, int with_announcements, int skip_single, uint8_t* action_out,
+                           dk_state* recs_out, int64_t* obs_out, int n_threads) {
+    BulkStates& b = *(BulkStates*)h;
+    parallel_for(b.f.size(), n_threads, [&](uint64_t i) {
+        fdo::State& s = b.f[(size_t)i];
+        int a = 0xFF;
+        if (s.current_phase != fdo::PH_FINISHED) a = orc_fdo_step_site(&s, seed, first_id + i, epoch, with_announcements, skip_single);
+        if (action_out) action_out[i] = (uint8_t)a;
+        if (recs_out) export_fdo(s, recs_out + i);
+        if (obs_out) fdo::encode_state_pi(s, obs_out + i * 311);
+    });
+}

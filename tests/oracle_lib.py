@@ -146,6 +146,14 @@ def load():
     L.orc_fuse_max_n.argtypes = [vp, u64, u64]
     L.orc_fuse_average.argtypes = [vp, u64]
     L.orc_fdo_flat_mc_philox.argtypes = [vp, u64, u64, u32, u32, u32, vp, vp]
+    L.orc_bulk_make.restype = vp
+    L.orc_bulk_make.argtypes = [i32, u64, u64, u64, u32, i32, vp, i32]
+    L.orc_bulk_free.argtypes = [vp]
+    L.orc_bulk_determinize.restype = dbl
+    L.orc_bulk_determinize.argtypes = [vp, u32, u64, u64, u32, u32, vp, vp, vp, vp, i32]
+    L.orc_bulk_leaf_rollouts.restype = dbl
+    L.orc_bulk_leaf_rollouts.argtypes = [vp, u32, u64, u64, u32, u32, i32, vp, i32]
+    L.orc_bulk_step.argtypes = [vp, u64, u64, u32, i32, i32, vp, vp, vp, i32]
     _lib = L
     return L
 
@@ -394,3 +402,60 @@ def replay_records(L, states, value, policy):
     vp = C.c_void_p
     L.orc_replay_records(st.shape[0], st.ctypes.data_as(vp), va.ctypes.data_as(vp), po.ctypes.data_as(vp), out.ctypes.data_as(vp))
     return out
+
+
+class Bulk:
+    """A batch of oracle states made by a recipe (oracle/capi.cpp orc_bulk_make) + their dk_state records (self.recs, numpy [n] of
+    DK_STATE_DTYPE) for the GPU.  mode 0 = BASELINE config 3 mid-game states, mode 1 = states at every stage of a game (the reference's
+    determinization soak, rs-full-doko-cmd/src/main.rs:190-283)."""
+
+    def __init__(self, L, engine, n, seed, first_id=0, epoch=0, mode=0, n_threads=0):
+        self.L, self.engine, self.n, self.seed, self.first_id = L, engine, n, seed, first_id
+        self.recs = np.zeros(n, dtype=DK_STATE_DTYPE)
+        self.h = C.c_void_p(L.orc_bulk_make(engine, n, seed, first_id, epoch, mode, self.recs.ctypes.data_as(C.c_void_p), n_threads))
+
+    def __del__(self):
+        try:
+            self.L.orc_bulk_free(self.h)
+        except Exception:
+            pass
+
+    def bytes(self):
+        """uint8 [n,128] copy of the records (what the tests upload)."""
+        return np.frombuffer(self.recs.tobytes(), dtype=np.uint8).reshape(self.n, 128).copy()
+
+    def determinize(self, S, epoch, first_sub=0, want_consistent=True, n_threads=0):
+        """(hands u64 [n,S,4], res u8 [n,S,4], status u8 [n,S], consistent i8 [n,S] or None, seconds)."""
+        hands = np.zeros((self.n, S, 4), dtype=np.uint64)
+        res = np.full((self.n, S, 4), 0xFF, dtype=np.uint8)
+        status = np.zeros((self.n, S), dtype=np.uint8)
+        cons = np.zeros((self.n, S), dtype=np.int8) if (want_consistent and self.engine == 1) else None
+        vp = C.c_void_p
+        sec = self.L.orc_bulk_determinize(self.h, S, self.seed, self.first_id, epoch, first_sub, hands.ctypes.data_as(vp), res.ctypes.data_as(vp),
+                                          status.ctypes.data_as(vp), cons.ctypes.data_as(vp) if cons is not None else None, n_threads)
+        return hands, res, status, cons, sec
+
+    def leaf_rollouts(self, R, epoch, first_sub=0, determinize=True, n_threads=0):
+        sums = np.zeros((self.n, 4), dtype=np.int64)
+        sec = self.L.orc_bulk_leaf_rollouts(self.h, R, self.seed, self.first_id, epoch, first_sub, int(determinize), sums.ctypes.data_as(C.c_void_p), n_threads)
+        return sums, sec
+
+    def step(self, epoch, with_announcements=True, skip_single=False, want_recs=False, want_obs=False, n_threads=0):
+        """One lock-step env step of every state (dk_step_random_encode): (actions u8 [n], recs or None, obs i64 [n,311] or None)."""
+        act = np.zeros(self.n, dtype=np.uint8)
+        recs = np.zeros(self.n, dtype=DK_STATE_DTYPE) if want_recs else None
+        obs = np.zeros((self.n, 311), dtype=np.int64) if want_obs else None
+        vp = C.c_void_p
+        self.L.orc_bulk_step(self.h, self.seed, self.first_id, epoch, int(with_announcements), int(skip_single), act.ctypes.data_as(vp),
+                             recs.ctypes.data_as(vp) if want_recs else None, obs.ctypes.data_as(vp) if want_obs else None, n_threads)
+        return act, recs, obs
+
+
+def fx_hash_record(rec_bytes, last_action=0xFF):
+    """FxHasher64 (fxhash 0.2.1, the hasher of AzEnvState::id(), rs-doko-alpha-zero/src/env/envs/full_doko/full_doko.rs:156-167) over the
+    sixteen little-endian u64 words of a 128-byte record and the last action: hash = (rotl(hash, 5) ^ word) * 0x517cc1b727220a95."""
+    words = list(np.frombuffer(bytes(rec_bytes), dtype="<u8")) + [last_action]
+    h, M = 0, (1 << 64) - 1
+    for w in words:
+        h = ((((h << 5) | (h >> 59)) & M) ^ int(w)) * 0x517CC1B727220A95 & M
+    return h
