@@ -249,6 +249,12 @@ def run_cuda(args):
 
     import master_doko_reinforcement_learning_b200 as pkg
 
+    # The JSON line is the ONLY thing this process may print on stdout: libraries that write to file descriptor 1 themselves (NCCL prints
+    # its version banner there) are pointed at stderr for the duration of the run; the line goes to the saved descriptor at the end.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
     world = env_int("WORLD_SIZE", 1)
     rank = env_int("RANK", 0)
     local_rank = env_int("LOCAL_RANK", 0)
@@ -593,7 +599,7 @@ def run_cuda(args):
         line["determinizations"] = determinizations
         line["config3_leaf_rollouts"] = config3
         line["config4_step_encode"] = config4
-        print(json.dumps(line))
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 

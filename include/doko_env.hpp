@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "doko_cuda.h"
+#include "doko_state_view.hpp"
 
 namespace doko {
 
@@ -91,6 +92,24 @@ class EnvBatch {
     void allowed_actions(uint64_t* mask_out_dev, dk_stream stream = nullptr) const {
         ctx_.check(dk_legal_mask(ctx_.get(), engine_, len(), states(), mask_out_dev, stream), "dk_legal_mask");
     }
+    // AzEnvState::allowed_actions_by_action_index(is_secondary, epoch) as masks and number_of_allowed_actions(epoch) (either may be null)
+    void allowed_actions_by_action_index(bool is_secondary, uint64_t epoch, uint64_t* mask_out_dev, uint8_t* n_allowed_out_dev, dk_stream stream = nullptr) const {
+        ctx_.check(dk_legal_mask_az(ctx_.get(), len(), states(), is_secondary ? 1 : 0, epoch, mask_out_dev, n_allowed_out_dev, stream), "dk_legal_mask_az");
+    }
+    // AzEnvState::id() of every game (last_action_dev may be null = None)
+    void id(const uint8_t* last_action_dev, uint64_t* id_out_dev, dk_stream stream = nullptr) const {
+        ctx_.check(dk_state_id(ctx_.get(), len(), states(), last_action_dev, id_out_dev, stream), "dk_state_id");
+    }
+    // FdoAllowedActions::random over the legal set of every game, without playing it
+    void random_action(const dk_rng& rng, bool with_announcements, uint8_t* action_out_dev, dk_stream stream = nullptr) const {
+        ctx_.check(dk_random_action(ctx_.get(), engine_, len(), states(), &rng, with_announcements ? DK_PLAYOUT_WITH_ANNOUNCEMENTS : 0u, action_out_dev, stream),
+                   "dk_random_action");
+    }
+    // the batch played to the end, only its statistics kept (what an evaluator aggregates); stats_dev in device memory
+    void playout_summary(const dk_rng& rng, bool with_announcements, dk_playout_stats* stats_dev, bool accumulate = false, dk_stream stream = nullptr) const {
+        ctx_.check(dk_playout_summary(ctx_.get(), engine_, with_announcements ? DK_PLAYOUT_WITH_ANNOUNCEMENTS : 0u, len(), states(), &rng, stats_dev, accumulate ? 1 : 0,
+                                      stream), "dk_playout_summary");
+    }
     // McEnvState::by_action / AzEnvState::take_action_by_action_index(action, skip_single, _), in place
     void take_action_by_action_index(const uint8_t* action_dev, bool skip_single, uint8_t* err_out_dev = nullptr, dk_stream stream = nullptr) {
         ctx_.check(dk_apply(ctx_.get(), engine_, len(), states(), action_dev, skip_single ? DK_APPLY_SKIP_SINGLE : 0u, err_out_dev, stream), "dk_apply");
@@ -139,6 +158,108 @@ class EnvBatch {
     Context& ctx_;
     int engine_;
     DeviceBuffer<dk_state> states_;
+};
+
+// ONE game by value — the drop-in shape of the reference's env types (McFullDokoEnvState, rs-doko-mcts/src/env/envs/env_state_full_doko.rs:62-220;
+// FdoAzEnvState, rs-doko-alpha-zero/src/env/envs/full_doko/full_doko.rs:16-172): a 128-byte record on the host plus the last action,
+// every trait method = one C-ABI call on a one-record batch (record up, result down).  Correct but latency bound (≈ 10 µs per call): code that
+// drives many games should hold them in an EnvBatch and call the same methods once per lock-step.  Copyable like the reference's states.
+class FdoEnvState {
+   public:
+    FdoEnvState(Context& ctx, const dk_state& record, int last_action = DK_ACTION_NONE) : ctx_(&ctx), rec_(record), last_action_(last_action) {}
+    // FdoState::new_game_from_hand_and_start_player (state.rs:125-166)
+    static FdoEnvState new_game_from_hand_and_start_player(Context& ctx, const uint64_t hands[4], int start_player) {
+        DeviceBuffer<uint64_t> h(4); DeviceBuffer<uint8_t> s(1); DeviceBuffer<dk_state> out(1);
+        const uint8_t sp = (uint8_t)start_player;
+        copy_in(h.data(), hands, 4 * sizeof(uint64_t)); copy_in(s.data(), &sp, 1);
+        ctx.check(dk_from_deals(ctx.get(), DK_FDO, 1, h.data(), s.data(), out.data(), legacy()), "dk_from_deals");
+        return FdoEnvState(ctx, out.to_host()[0]);
+    }
+    const dk_state& record() const { return rec_; }
+    FdoStateView view() const { return from_record(rec_); }
+
+    size_t current_player() const { return (rec_.meta >> 2) & 3u; }                       // BOTTOM when finished (full_doko.rs:46-48)
+    bool is_terminal() const { return (rec_.meta & 3u) == DK_PHASE_FINISHED; }
+    int last_action() const { return last_action_; }                                      // DK_ACTION_NONE = None
+    // McEnvState::allowed_actions(first_expansion) (env_state_full_doko.rs:132-172): below the root no calls, and no solo / wedding
+    // reservation once any seat has declared a solo
+    uint64_t allowed_actions(bool first_expansion) const {
+        uint64_t m = legal_mask(false, 1u << 20);
+        if (!first_expansion) {
+            for (int i = 0; i < rec_.n_reservations && i < 4; ++i) if (rec_.reservations[i] >= DK_RES_DIAMONDS_SOLO) m &= ~(0xFFull << 25);
+            m &= ~(0x1Full << 33);
+        }
+        return m;
+    }
+    // AzEnvState::allowed_actions_by_action_index(is_secondary, epoch) as action indices; number_of_allowed_actions(epoch)
+    std::vector<size_t> allowed_actions_by_action_index(bool is_secondary, uint64_t epoch) const {
+        std::vector<size_t> idx;
+        for (uint64_t m = legal_mask(is_secondary, epoch); m; m &= m - 1) idx.push_back((size_t)__builtin_ctzll(m));
+        return idx;
+    }
+    size_t number_of_allowed_actions(uint64_t epoch) const { return (size_t)__builtin_popcountll(legal_mask(false, epoch)); }
+    // McEnvState::by_action / AzEnvState::take_action_by_action_index(action, skip_single, epoch): a NEW state; an illegal action throws
+    // (the reference panics)
+    FdoEnvState take_action_by_action_index(size_t action, bool skip_single, uint64_t /*epoch*/ = 0) const {
+        DeviceBuffer<dk_state> st(1); DeviceBuffer<uint8_t> a(1), err(1);
+        const uint8_t ab = (uint8_t)action;
+        copy_in(st.data(), &rec_, sizeof rec_); copy_in(a.data(), &ab, 1);
+        ctx_->check(dk_apply(ctx_->get(), DK_FDO, 1, st.data(), a.data(), skip_single ? DK_APPLY_SKIP_SINGLE : 0u, err.data(), legacy()), "dk_apply");
+        if (err.to_host()[0]) throw DokoError(DK_ERR_INVALID_ARGUMENT, "take_action_by_action_index: action is not allowed in this state");
+        return FdoEnvState(*ctx_, st.to_host()[0], (int)action);
+    }
+    FdoEnvState by_action(size_t action) const { return take_action_by_action_index(action, false); }
+    // rewards_or_none: player_points (McEnvState: as f64; AzEnvState: / 8 as f32); false when the game is not over
+    bool rewards_or_none(double out[4]) const {
+        if (!is_terminal()) return false;
+        for (int p = 0; p < 4; ++p) out[p] = (double)rec_.points[p];
+        return true;
+    }
+    bool rewards_or_none(float out[4]) const {
+        if (!is_terminal()) return false;
+        for (int p = 0; p < 4; ++p) out[p] = (float)rec_.points[p] / 8.0f;
+        return true;
+    }
+    // McEnvState::random_rollout: the _no_announcement policy to the end of the game on the stream (rng.seed, rng.first_id, rng.epoch)
+    void random_rollout(const dk_rng& rng, double out[4]) const {
+        int32_t pts[4];
+        ctx_->check(dk_playout_host(ctx_->get(), DK_FDO, 0u, 1, &rec_, &rng, pts, nullptr), "dk_playout_host");
+        for (int p = 0; p < 4; ++p) out[p] = (double)pts[p];
+    }
+    // AzEnvState::encode_into_memory(&mut [i64; 311])
+    void encode_into_memory(int64_t memory[DK_OBS_LEN_FDO_PI311]) const {
+        DeviceBuffer<dk_state> st(1); DeviceBuffer<int64_t> obs(DK_OBS_LEN_FDO_PI311);
+        copy_in(st.data(), &rec_, sizeof rec_);
+        ctx_->check(dk_encode(ctx_->get(), DK_LAYOUT_FDO_PI311, 1, st.data(), obs.data(), DK_OBS_LEN_FDO_PI311, legacy()), "dk_encode");
+        const std::vector<int64_t> h = obs.to_host();
+        for (int i = 0; i < DK_OBS_LEN_FDO_PI311; ++i) memory[i] = h[i];
+    }
+    // AzEnvState::id()
+    uint64_t id() const {
+        DeviceBuffer<dk_state> st(1); DeviceBuffer<uint8_t> a(1); DeviceBuffer<uint64_t> out(1);
+        const uint8_t ab = (uint8_t)last_action_;
+        copy_in(st.data(), &rec_, sizeof rec_); copy_in(a.data(), &ab, 1);
+        ctx_->check(dk_state_id(ctx_->get(), 1, st.data(), a.data(), out.data(), legacy()), "dk_state_id");
+        return out.to_host()[0];
+    }
+    bool operator==(const FdoEnvState& o) const { return std::memcmp(&rec_, &o.rec_, sizeof rec_) == 0 && last_action_ == o.last_action_; }
+
+   private:
+    // All calls of this class run on the legacy default stream, the stream cudaMemcpy uses: record up, kernel, result down are ordered
+    // without an explicit synchronisation.
+    static dk_stream legacy() { return (dk_stream)cudaStreamLegacy; }
+    static void copy_in(void* dst_dev, const void* src, size_t bytes) {
+        if (cudaMemcpy(dst_dev, src, bytes, cudaMemcpyHostToDevice) != cudaSuccess) throw DokoError(DK_ERR_CUDA, "cudaMemcpy H2D failed");
+    }
+    uint64_t legal_mask(bool is_secondary, uint64_t epoch) const {
+        DeviceBuffer<dk_state> st(1); DeviceBuffer<uint64_t> m(1);
+        copy_in(st.data(), &rec_, sizeof rec_);
+        ctx_->check(dk_legal_mask_az(ctx_->get(), 1, st.data(), is_secondary ? 1 : 0, epoch, m.data(), nullptr, legacy()), "dk_legal_mask_az");
+        return m.to_host()[0];
+    }
+    Context* ctx_;
+    dk_state rec_;
+    int last_action_;
 };
 
 // PolicyFusionFn::fuse (policy_fusion.rs:9-16) for a batch of roots; strategy = DK_FUSE_MAX_N (PolicyFusionMaxN) or DK_FUSE_AVERAGE

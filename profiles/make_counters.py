@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Writes / updates profiles/kernel_counters.json from ncu_summary.py digests.
 
-    python profiles/make_counters.py <mangled kernel name> <summary.json> <units per launch> <unit name> [source label]
+    python profiles/make_counters.py <mangled kernel name> <summary.json> <units per launch> <unit name> [source label] [games per launch]
 
 Takes the LAST launch of the kernel in the digest (warmed up), records warp instructions per unit, pipe / issue utilisation, DRAM
 bytes and the capture's duration, and ties them to the sha256 of the kernel's SASS in the library that was profiled
@@ -46,7 +46,7 @@ def main():
         "issue_active_pct": k.get("smsp__issue_active.avg.pct_of_peak_sustained_active"),
         "dram_bytes_per_launch": ((scaled(k, "dram__bytes_read.sum", BYTES) or 0.0) + (scaled(k, "dram__bytes_write.sum", BYTES) or 0.0)) or None,
         "capture_kernel_ms": scaled(k, "gpu__time_duration.sum", MS),
-        "capture_games": units if unit_name == "game" else None,
+        "capture_games": float(sys.argv[6]) if len(sys.argv) > 6 else (units if unit_name == "game" else None),
         "registers_per_thread": k.get("launch__registers_per_thread"),
         "source": label, "sass_sha256": hashes.get(mangled),
     }
