@@ -407,7 +407,10 @@ DK_API dk_status dk_sp_counts(dk_selfplay* sp, uint64_t* rows, uint64_t* dropped
  * bincode::serialize (rs-doko-alpha-zero/src/alpha_zero/net/experience_replay_buffer3.rs:11-20,94-121; bincode 1.3.3, heapless 0.8.0):
  *   u64 311 | 311 x i64 | u64 4 | 4 x f32 | u64 39 | 39 x f32, little endian, DK_REPLAY_RECORD_BYTES each, back to back in `out`
  * (4-byte aligned).  One D2H copy of `out` then holds exactly the values `append_slice` inserts into sled (the random u64 keys and the
- * store itself stay on the host side). */
+ * store itself stay on the host side).
+ * PINNING: the reference holds no golden bytes of this record and cannot be run here, so the layout is pinned to an independent encoder of
+ * the bincode 1.x specification and its committed output (tests/golden/bincode_v1.py, dbrecord_golden.json) — not to bytes produced by the
+ * Rust crate itself; treat the entry point as EXPERIMENTAL until a maintainer has round-tripped one record through bincode::deserialize. */
 #define DK_REPLAY_RECORD_BYTES 2684u
 DK_API dk_status dk_pack_replay_records(dk_ctx* ctx, size_t n_rows, const int64_t* states /*[dev] n_rows*311*/, const float* value /*[dev] n_rows*4*/,
                                         const float* policy /*[dev] n_rows*39*/, uint8_t* out /*[dev] n_rows*DK_REPLAY_RECORD_BYTES*/, dk_stream stream);

@@ -6,6 +6,7 @@
 #include <chrono>
 #include <cstdint>
 #include <cstring>
+#include <functional>
 #include <thread>
 #include <vector>
 
@@ -753,6 +754,7 @@ ORC_API double orc_cpu_baseline(int kind, uint64_t seed, uint64_t n_units, uint3
 //   mode 0  BASELINE config 3: until card_index reaches 8 / 16 / 24 / 32 (round-robin over i)
 //   mode 1  the reference's determinization soak (rs-full-doko-cmd/src/main.rs:190-283 tests card_matching at EVERY state of a game):
 //           (i * 2654435761 >> 16) % 96 actions, never the last card — reservation-phase, announcement-phase and card-phase states
+//   mode 2  late-game states for the support-set test: until card_index reaches 34 + i % 13 (<= 10 hidden cards)
 // rs-doko (engine 0): 4 reservations + the same number of cards.
 namespace {
 struct BulkStates { int engine = DK_FDO; std::vector<fdo::State> f; std::vector<doko::State> d; };
@@ -777,10 +779,10 @@ ORC_API void* orc_bulk_make(int engine, uint64_t n, uint64_t seed, uint64_t firs
         const uint64_t unit = first_id + i;
         PhiloxStream r(seed, (uint32_t)unit, (uint32_t)(unit >> 32), epoch);
         const int quota = (int)((((uint32_t)i * 2654435761u) >> 16) % 96u);
-        const int target = 8 * (1 + (int)(i & 3));
+        const int target = mode == 2 ? 34 + (int)(i % 13) : 8 * (1 + (int)(i & 3));
         if (engine == DK_FDO) {
             fdo::State s = fdo::State::new_game(r);
-            if (mode == 0) { while (s.current_phase != fdo::PH_FINISHED && s.card_index < target) s.random_action_for_current_player(r); }
+            if (mode == 0 || mode == 2) { while (s.current_phase != fdo::PH_FINISHED && s.card_index < target) s.random_action_for_current_player(r); }
             else for (int k = 0; k < quota; ++k) {
                 if (s.current_phase == fdo::PH_PLAYCARD && s.card_index == 47) break;
                 if (s.random_action_for_current_player(r)) break;
@@ -862,4 +864,68 @@ ORC_API void orc_bulk_step(void* h, uint64_t seed, uint64_t first_id, uint32_t e
         if (recs_out) export_fdo(s, recs_out + i);
         if (obs_out) fdo::encode_state_pi(s, obs_out + i * 311);
     });
+}
+
+// ---- support set of the determinizer (tests/test_card_matching_support.py) -------------------------------------------------------
+// Every assignment of the hidden cards to the three hidden seats (hand sizes kept) for which SOME assignment of the hidden
+// reservations passes is_consistent — the full support a consistent sampler may draw from; card_matching's greedy rules reach a
+// subset of it.  Late-game states only (the number of assignments is a multinomial).  out_hands[k*4 + seat]; returns the number of
+// members, or -1 when it exceeds `max`.
+ORC_API int64_t orc_fdo_enumerate_consistent_hands(const void* h, int64_t max, uint64_t* out_hands) {
+    const fdo::State& s = *(const fdo::State*)h;
+    const int obs = s.observing_player();
+    int count[24] = {0};
+    for (int p = 0; p < 4; ++p) {
+        if (p == obs) continue;
+        for (int c = 0; c < 24; ++c) count[c] += (int)((s.hands[p].bits >> c) & 1) + (int)((s.hands[p].bits >> (c + 24)) & 1);
+    }
+    int seats[3], cap[3], k = 0;
+    for (int p = 0; p < 4; ++p) if (p != obs) { seats[k] = p; cap[k] = (int)s.hands[p].len(); k++; }
+    int visible[4]; fdo::get_visible_reservations(s.reservations_round, obs, visible);
+    int have[3][24] = {{0}};
+    int64_t n_out = 0;
+    bool overflow = false;
+    auto emit = [&]() {
+        fdo::Hand hands[4];
+        hands[obs] = s.hands[obs];
+        for (int j = 0; j < 3; ++j) {
+            uint64_t bits = 0;
+            for (int c = 0; c < 24; ++c) { if (have[j][c] >= 1) bits |= 1ull << c; if (have[j][c] == 2) bits |= 1ull << (c + 24); }
+            hands[seats[j]].bits = bits;
+        }
+        // hidden reservations: a NotRevealed seat declared a solo or a wedding — try both kinds
+        int opts[4][2], nopt[4];
+        for (int p = 0; p < 4; ++p) {
+            const int vr = visible[p];
+            if (vr == fdo::VR_NONE_YET) { opts[p][0] = fdo::R_NONE; nopt[p] = 1; }
+            else if (vr == fdo::VR_NOT_REVEALED) { opts[p][0] = fdo::R_DIAMONDS_SOLO; opts[p][1] = fdo::R_WEDDING; nopt[p] = 2; }
+            else if (vr == fdo::VR_HEALTHY) { opts[p][0] = fdo::R_HEALTHY; nopt[p] = 1; }
+            else if (vr == fdo::VR_WEDDING) { opts[p][0] = fdo::R_WEDDING; nopt[p] = 1; }
+            else { opts[p][0] = vr - fdo::VR_DIAMONDS_SOLO + fdo::R_DIAMONDS_SOLO; nopt[p] = 1; }
+        }
+        bool ok = false;
+        for (int a = 0; a < nopt[0] && !ok; ++a) for (int b = 0; b < nopt[1] && !ok; ++b) for (int c = 0; c < nopt[2] && !ok; ++c) for (int d = 0; d < nopt[3] && !ok; ++d) {
+            int res[4] = {opts[0][a], opts[1][b], opts[2][c], opts[3][d]};
+            ok = fdo::is_consistent(s, hands, res) == 0;
+        }
+        if (!ok) return;
+        if (n_out >= max) { overflow = true; return; }
+        for (int p = 0; p < 4; ++p) out_hands[n_out * 4 + p] = hands[p].bits;
+        n_out++;
+    };
+    std::function<void(int)> rec = [&](int c) {
+        if (overflow) return;
+        while (c < 24 && count[c] == 0) c++;
+        if (c == 24) { if (cap[0] == 0 && cap[1] == 0 && cap[2] == 0) emit(); return; }
+        const int n = count[c];
+        for (int a = 0; a <= n; ++a) for (int b = 0; a + b <= n; ++b) {
+            const int d = n - a - b;
+            if (a > cap[0] || b > cap[1] || d > cap[2]) continue;
+            have[0][c] = a; have[1][c] = b; have[2][c] = d; cap[0] -= a; cap[1] -= b; cap[2] -= d;
+            rec(c + 1);
+            cap[0] += a; cap[1] += b; cap[2] += d; have[0][c] = have[1][c] = have[2][c] = 0;
+        }
+    };
+    rec(0);
+    return overflow ? -1 : n_out;
 }

@@ -154,6 +154,8 @@ def load():
     L.orc_bulk_leaf_rollouts.restype = dbl
     L.orc_bulk_leaf_rollouts.argtypes = [vp, u32, u64, u64, u32, u32, i32, vp, i32]
     L.orc_bulk_step.argtypes = [vp, u64, u64, u32, i32, i32, vp, vp, vp, i32]
+    L.orc_fdo_enumerate_consistent_hands.restype = C.c_int64
+    L.orc_fdo_enumerate_consistent_hands.argtypes = [vp, C.c_int64, vp]
     _lib = L
     return L
 
@@ -258,6 +260,14 @@ class Fdo:
 
     def is_consistent(self, hands, res):
         return self.L.orc_fdo_is_consistent(self.h, (C.c_uint64 * 4)(*hands), (C.c_uint8 * 4)(*res))
+
+    def consistent_hands(self, max_members=200_000):
+        """Every assignment of the hidden cards (hand sizes kept) that passes is_consistent with some hidden reservations: uint64 [k,4]."""
+        out = np.zeros((max_members, 4), dtype=np.uint64)
+        k = self.L.orc_fdo_enumerate_consistent_hands(self.h, max_members, out.ctypes.data_as(C.c_void_p))
+        if k < 0:
+            raise RuntimeError("support set larger than max_members")
+        return out[:k].copy()
 
     def leaf_rollout(self, seed, unit, rollout, epoch=0, determinize=True):
         pts = (C.c_int32 * 4)()

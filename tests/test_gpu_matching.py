@@ -137,3 +137,34 @@ def test_doko_assignment_support_sets_on_gpu(dk):
         assert int(status.max()) == 0
         seen = {canonical([int(x) for x in h]) for h in hands[0].cpu().numpy().astype(np.uint64)}
         assert len(seen) == case["n_unique"] and expected_set(case) <= seen
+
+
+def test_card_matching_support_set_on_gpu(dk, orc):
+    """10^5 GPU samples per late-game info-state (<= 10 hidden cards) all land inside the enumerated set of is_consistent assignments
+    (tests/test_card_matching_support.py builds the same sets for the oracle), and together they reach practically all of it: the greedy
+    rules of card_matching leave no consistent assignment of these states unreachable."""
+    import torch
+
+    from oracle_lib import Bulk
+
+    b = Bulk(orc, 1, 96, SEED, first_id=4000, epoch=3, mode=2)
+    S = 100_000
+    hands, _, status = dk.determinize(1, to_dev_bytes(b.bytes()), S, dk.rng(SEED, 4000, 8))
+    torch.cuda.synchronize()
+    assert int(status.max()) == 0
+    hands = hands.cpu().numpy().astype(np.uint64)
+    total = reached = 0
+    key = [("h", "<u8", 4)]
+    for i in range(b.n):
+        support = Fdo.from_dk_state(orc, b.recs[i:i + 1]).consistent_hands()
+        seen = np.unique(np.ascontiguousarray(hands[i]).view(key))
+        assert np.isin(seen, np.ascontiguousarray(support).view(key)).all(), f"state {i}: a GPU sample outside the consistent set"
+        total += len(support)
+        reached += len(seen)
+    assert total > 5000 and reached >= 0.999 * total, (reached, total)
+
+
+def to_dev_bytes(raw):
+    import torch
+
+    return torch.from_numpy(raw).cuda()
