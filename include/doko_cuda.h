@@ -428,8 +428,9 @@ DK_API dk_status dk_pack_replay_records(dk_ctx* ctx, size_t n_rows, const int64_
  *   visits_out[t*39 + a], values_out[t*39 + a] = win_score / visits as f32 (0 for actions without a child), t = i*trees_per_root + d
  *   action_out[t] = move with the most visits (last among equals in child order), DK_ACTION_NONE if the root has no child
  *   status_out[t] != 0: determinization dead end (row = 0).
- * workspace: caller-owned device memory, 16-byte aligned, >= dk_uct_workspace_bytes(n_roots * trees_per_root, iterations)
- * (208 bytes per node, iterations + 1 nodes per tree). */
+ * workspace: caller-owned device memory, >= dk_uct_workspace_bytes(n_roots * trees_per_root, iterations) bytes (288 bytes per node —
+ * a 160-byte statistics block and the 128-byte record —, iterations + 1 nodes per tree, plus 24 bytes of control words per tree);
+ * iterations <= 2^24.  One iteration of all trees is three kernel launches (select + backpropagation, expansion, rollout). */
 DK_API size_t dk_uct_workspace_bytes(size_t n_trees, size_t iterations);
 DK_API dk_status dk_uct_search(dk_ctx* ctx, size_t n_roots, size_t trees_per_root, int determinize, size_t iterations, float uct_exploration_constant,
                                const dk_state* states /*[dev]*/, const dk_rng* rng, void* workspace /*[dev]*/, size_t workspace_bytes,

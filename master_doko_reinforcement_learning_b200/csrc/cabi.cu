@@ -23,6 +23,8 @@ struct dk_ctx {
     std::string last_error;
     int sm_count = 0, cc_major = 0, cc_minor = 0;
     void* tmap_encode = nullptr;     // cuTensorMapEncodeTiled
+    void* leaf_ws = nullptr;         // samples of dk_leaf_rollouts(determinize): K3's output for one chunk of leaves
+    size_t leaf_ws_bytes = 0;
     void* pimc_ws = nullptr;         // workspace of dk_pimc_evaluate (post-action playout states per determinization and legal action)
     size_t pimc_ws_bytes = 0;
     bool fresh_smem_set = false;     // dynamic shared-memory opt-in of the fresh-game playout kernels done on this device
@@ -38,6 +40,8 @@ struct dk_ctx {
     // ln(N) table of the UCT search (host libm values, see uct.cuh)
     double* d_ln_table = nullptr;
     size_t ln_table_len = 0;
+    void* d_vis_table = nullptr;     // (1 / v, 1 / sqrt(v)) as floats for the f32 filter of the selection
+    size_t vis_table_len = 0;
     void* nccl_lib = nullptr;
     void* nccl_comm = nullptr;
     int nccl_ranks = 0, nccl_rank = 0;
@@ -157,7 +161,9 @@ dk_status dk_destroy(dk_ctx* ctx) {
     dk_comm_destroy(ctx);                                // a communicator the caller left open
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);
     if (ctx->pimc_ws) cudaFree(ctx->pimc_ws);
+    if (ctx->leaf_ws) cudaFree(ctx->leaf_ws);
     if (ctx->d_ln_table) cudaFree(ctx->d_ln_table);
+    if (ctx->d_vis_table) cudaFree(ctx->d_vis_table);
     for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
@@ -422,16 +428,50 @@ dk_status dk_leaf_rollouts(dk_ctx* ctx, size_t n_leaves, size_t rollouts_per_lea
     if (rollouts_per_leaf > 0x1000000ull || n_leaves > 0x7FFFFFFFull) return DK_ERR_INVALID_ARGUMENT;   // int32 block sums: |points| < 128
     DK_ALIGNED(ctx, states, 16); DK_ALIGNED(ctx, point_sum_out, 8);
     DK_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = pick_stream(ctx, stream);
     // Fewer leaves than one wave of blocks: several blocks per leaf (at most one per 128 rollouts), sums combined by integer atomics.
     const uint64_t per_leaf_max = (rollouts_per_leaf + dk::MATCH_THREADS - 1) / dk::MATCH_THREADS, wave = (uint64_t)ctx->sm_count * DK_LEAF_BLOCKS;
     uint64_t splits = wave / n_leaves;
     if (splits > per_leaf_max) splits = per_leaf_max;
     if (splits < 1 || getenv("DOKO_CUDA_NO_SPLIT")) splits = 1;
-    const unsigned grid = (unsigned)(n_leaves * splits);
-    if (splits > 1) DK_CUDA(ctx, cudaMemsetAsync(point_sum_out, 0, n_leaves * 4 * sizeof(int64_t), pick_stream(ctx, stream)));
-    if (determinize) dk::fdo_leaf_rollouts_kernel<true><<<grid, dk::MATCH_THREADS, 0, pick_stream(ctx, stream)>>>(to_params(rng), (uint64_t)n_leaves, (uint32_t)rollouts_per_leaf, (uint32_t)splits, states, (long long*)point_sum_out);
-    else dk::fdo_leaf_rollouts_kernel<false><<<grid, dk::MATCH_THREADS, 0, pick_stream(ctx, stream)>>>(to_params(rng), (uint64_t)n_leaves, (uint32_t)rollouts_per_leaf, (uint32_t)splits, states, (long long*)point_sum_out);
-    return check_launch(ctx, "fdo_leaf_rollouts_kernel");
+    if (splits > 1) DK_CUDA(ctx, cudaMemsetAsync(point_sum_out, 0, n_leaves * 4 * sizeof(int64_t), s));
+    const dk::RngParams rp = to_params(rng);
+    if (!determinize || rollouts_per_leaf == 0) {
+        dk::fdo_leaf_rollouts_kernel<false><<<(unsigned)(n_leaves * splits), dk::MATCH_THREADS, 0, s>>>(rp, 0ull, (uint64_t)n_leaves, (uint32_t)rollouts_per_leaf, (uint32_t)splits, states,
+                                                                                                     nullptr, nullptr, nullptr, (long long*)point_sum_out);
+        return check_launch(ctx, "fdo_leaf_rollouts_kernel");
+    }
+    // Determinized rollouts = K3 into a scratch buffer (hands 32 B + reservations 4 B + status 1 B per rollout, at most 256 MiB per
+    // chunk of leaves) + the rollout kernel reading its samples: each kernel runs at its own occupancy.
+    const size_t R = rollouts_per_leaf, per_leaf = ((R * 37 + 255) & ~(size_t)255) + 512;
+    size_t chunk = ((size_t)256 << 20) / per_leaf;
+    if (chunk < 1) chunk = 1;
+    if (chunk > n_leaves) chunk = n_leaves;
+    const size_t b_hands = (chunk * R * 32 + 255) & ~(size_t)255, b_res = (chunk * R * 4 + 255) & ~(size_t)255, b_status = (chunk * R + 255) & ~(size_t)255;
+    if (ctx->leaf_ws_bytes < b_hands + b_res + b_status) {
+        DK_CUDA(ctx, cudaStreamSynchronize(s));
+        if (ctx->leaf_ws) { cudaFree(ctx->leaf_ws); ctx->leaf_ws = nullptr; ctx->leaf_ws_bytes = 0; }
+        DK_CUDA(ctx, cudaMalloc(&ctx->leaf_ws, b_hands + b_res + b_status));
+        ctx->leaf_ws_bytes = b_hands + b_res + b_status;
+    }
+    uint64_t* d_hands = (uint64_t*)ctx->leaf_ws;
+    uint8_t* d_res = (uint8_t*)ctx->leaf_ws + b_hands;
+    uint8_t* d_status = d_res + b_res;
+    for (size_t l0 = 0; l0 < n_leaves; l0 += chunk) {
+        const size_t nl = n_leaves - l0 < chunk ? n_leaves - l0 : chunk;
+        dk::RngParams rc = rp;
+        rc.first_id = rp.first_id + l0;                                               // sample unit = first_id + leaf
+        const uint64_t det_per_max = (R + dk::MATCH_THREADS - 1) / dk::MATCH_THREADS, want = (uint64_t)ctx->sm_count * 128u;
+        uint64_t dsplits = (want + nl - 1) / nl;
+        if (dsplits > det_per_max) dsplits = det_per_max;
+        if (dsplits < 1 || getenv("DOKO_CUDA_NO_SPLIT")) dsplits = 1;
+        dk::fdo_determinize_kernel<<<(unsigned)(nl * dsplits), dk::MATCH_THREADS, 0, s>>>(rc, (uint64_t)nl, (uint32_t)R, (uint32_t)dsplits, states + l0, d_hands, d_res, d_status);
+        DK_TRY(check_launch(ctx, "fdo_determinize_kernel"));
+        dk::fdo_leaf_rollouts_kernel<true><<<(unsigned)(nl * splits), dk::MATCH_THREADS, 0, s>>>(rp, (uint64_t)l0, (uint64_t)nl, (uint32_t)R, (uint32_t)splits, states, d_hands, d_res, d_status,
+                                                                                                (long long*)point_sum_out);
+        DK_TRY(check_launch(ctx, "fdo_leaf_rollouts_kernel"));
+    }
+    return DK_OK;
 }
 
 dk_status dk_encode_ipi(dk_ctx* ctx, size_t n, const dk_state* states, const uint64_t* assumed_hands, const uint8_t* assumed_reservations,
@@ -662,37 +702,56 @@ dk_status dk_pack_replay_records(dk_ctx* ctx, size_t n_rows, const int64_t* stat
 }
 
 // ---- UCT search -------------------------------------------------------------------------------------------
-size_t dk_uct_workspace_bytes(size_t n_trees, size_t iterations) { return n_trees * (iterations + 1) * sizeof(dk::UctNode); }
+size_t dk_uct_workspace_bytes(size_t n_trees, size_t iterations) { return (size_t)dk::uct_workspace_bytes(n_trees, iterations); }
 
 dk_status dk_uct_search(dk_ctx* ctx, size_t n_roots, size_t trees_per_root, int determinize, size_t iterations, float uct_exploration_constant,
                         const dk_state* states, const dk_rng* rng, void* workspace, size_t workspace_bytes, uint32_t* visits_out, float* values_out,
                         uint8_t* action_out, uint8_t* status_out, dk_stream stream) {
-    if (!ctx || !states || !rng || !workspace || trees_per_root == 0 || ((uintptr_t)workspace & 15u)) return DK_ERR_INVALID_ARGUMENT;
+    if (!ctx || !states || !rng || !workspace || trees_per_root == 0) return DK_ERR_INVALID_ARGUMENT;
     if (n_roots == 0) return DK_OK;
     const size_t n_trees = n_roots * trees_per_root;
-    if (iterations == 0 || iterations > 0x7FFFFFFFull || n_trees > 0x7FFFFFFFull * dk::UCT_THREADS / 2 ||
+    if (iterations == 0 || iterations > dk::UCT_MAX_ITERATIONS || n_trees > 0x7FFFFFFFull * dk::UCT_THREADS / 2 || trees_per_root > 0xFFFFFFFFull ||
         ((uint64_t)rng->first_sub + trees_per_root) * iterations > 0xFFFFFFFFull || workspace_bytes < dk_uct_workspace_bytes(n_trees, iterations))
         return DK_ERR_INVALID_ARGUMENT;
     DK_ALIGNED(ctx, states, 16); DK_ALIGNED(ctx, visits_out, 4); DK_ALIGNED(ctx, values_out, 4);
     DK_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t s = pick_stream(ctx, stream);
     if (ctx->ln_table_len < iterations + 1) {
-        // ln via the HOST libm (what Rust's f64::ln calls), so that selection is bit-identical to the CPU reference path
+        // ln via the HOST libm (what Rust's f64::ln calls), so that selection is bit-identical to the CPU reference path; the f32 filter's
+        // 1 / v and 1 / sqrt(v) factors are evaluated in f64 and rounded once (uct.cuh UctTables)
         std::vector<double> t(iterations + 1);
         t[0] = 0.0;
         for (size_t n = 1; n <= iterations; ++n) t[n] = std::log((double)n);
+        const size_t vlen = iterations + 1;
+        std::vector<dk::UctF2> vt(vlen);
+        vt[0].x = 1.0f; vt[0].y = 1.0f;
+        for (size_t v = 1; v < vlen; ++v) { vt[v].x = (float)(1.0 / (double)v); vt[v].y = (float)(1.0 / std::sqrt((double)v)); }
         DK_CUDA(ctx, cudaStreamSynchronize(s));
         if (ctx->d_ln_table) cudaFree(ctx->d_ln_table);
-        ctx->d_ln_table = nullptr; ctx->ln_table_len = 0;
+        if (ctx->d_vis_table) cudaFree(ctx->d_vis_table);
+        ctx->d_ln_table = nullptr; ctx->d_vis_table = nullptr; ctx->ln_table_len = 0; ctx->vis_table_len = 0;
         DK_CUDA(ctx, cudaMalloc(&ctx->d_ln_table, t.size() * sizeof(double)));
+        DK_CUDA(ctx, cudaMalloc(&ctx->d_vis_table, vt.size() * sizeof(dk::UctF2)));
         DK_CUDA(ctx, cudaMemcpy(ctx->d_ln_table, t.data(), t.size() * sizeof(double), cudaMemcpyHostToDevice));
-        ctx->ln_table_len = t.size();
+        DK_CUDA(ctx, cudaMemcpy(ctx->d_vis_table, vt.data(), vt.size() * sizeof(dk::UctF2), cudaMemcpyHostToDevice));
+        ctx->ln_table_len = t.size(); ctx->vis_table_len = vt.size();
     }
-    unsigned grid = (unsigned)((n_trees + dk::UCT_THREADS - 1) / dk::UCT_THREADS);
-    dk::fdo_uct_kernel<<<grid, dk::UCT_THREADS, 0, s>>>(to_params(rng), (uint64_t)n_trees, (uint32_t)trees_per_root, (uint32_t)iterations,
-                                                        (double)uct_exploration_constant, ctx->d_ln_table, determinize, states, (dk::UctNode*)workspace,
-                                                        visits_out, values_out, action_out, status_out);
-    return check_launch(ctx, "fdo_uct_kernel");
+    const dk::UctPool P = dk::uct_carve(workspace, n_trees, iterations, getenv("DOKO_CUDA_UCT_TREE_MAJOR") != nullptr);
+    const dk::RngParams rp = to_params(rng);
+    dk::UctTables T; T.ln = ctx->d_ln_table; T.vis_tab = (const dk::UctF2*)ctx->d_vis_table;
+    const unsigned grid = (unsigned)((n_trees + dk::UCT_THREADS - 1) / dk::UCT_THREADS);
+    const unsigned grid_roll = (unsigned)((n_trees + dk::UCT_ROLLOUT_THREADS - 1) / dk::UCT_ROLLOUT_THREADS);
+    const double c = (double)uct_exploration_constant;
+    dk::uct_root_kernel<<<grid, dk::UCT_THREADS, 0, s>>>(rp, P, (uint32_t)trees_per_root, determinize, states, visits_out, values_out);
+    DK_TRY(check_launch(ctx, "uct_root_kernel"));
+    // One iteration of every tree = two launches (uct.cuh): all SMs run the same phase, each phase has its own register budget.
+    for (uint32_t it = 0; it < (uint32_t)iterations; ++it) {
+        dk::uct_tree_kernel<<<grid, dk::UCT_THREADS, 0, s>>>(rp, P, (uint32_t)trees_per_root, (uint32_t)iterations, it, c, T);
+        dk::uct_rollout_kernel<<<grid_roll, dk::UCT_ROLLOUT_THREADS, 0, s>>>(rp, P, (uint32_t)trees_per_root, (uint32_t)iterations, it);
+        ctx->launches += 2;
+    }
+    dk::uct_moves_kernel<<<grid, dk::UCT_THREADS, 0, s>>>(P, visits_out, values_out, action_out, status_out);
+    return check_launch(ctx, "uct kernels");
 }
 
 // ---- NCCL (dlopen; the only exchange step of the path) ---------------------------------------------------------------------

@@ -223,15 +223,16 @@ struct StateStage {
         }
         __syncthreads();
     }
-    static __device__ __forceinline__ void get(const uint4* sm, dk_state& s) {
+    static __device__ __forceinline__ void get(const uint4* sm, dk_state& s) { get_row(sm, threadIdx.x, s); }
+    static __device__ __forceinline__ void put(uint4* sm, const dk_state& s) { put_row(sm, threadIdx.x, s); }
+    // record `t` of the tile (any thread may take any row; rows taken out of order cost a few bank conflicts on the idle LSU pipe)
+    static __device__ __forceinline__ void get_row(const uint4* sm, uint32_t t, dk_state& s) {
         uint4* d4 = reinterpret_cast<uint4*>(&s);
-        const uint32_t t = threadIdx.x;
 #pragma unroll
         for (uint32_t j = 0; j < 8u; ++j) d4[j] = sm[t * 8u + (j ^ (t & 7u))];
     }
-    static __device__ __forceinline__ void put(uint4* sm, const dk_state& s) {
+    static __device__ __forceinline__ void put_row(uint4* sm, uint32_t t, const dk_state& s) {
         const uint4* s4 = reinterpret_cast<const uint4*>(&s);
-        const uint32_t t = threadIdx.x;
 #pragma unroll
         for (uint32_t j = 0; j < 8u; ++j) sm[t * 8u + (j ^ (t & 7u))] = s4[j];
     }
@@ -351,22 +352,58 @@ struct TmaTile {
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");                // the block's shared memory must outlive the engine's read
     }
 };
+// The transition's cost is its DIVERGENCE: a tile holds records in every phase, and a warp whose lanes sit in the reservation, the
+// announcement and the card phase (with or without a trick to close) runs all of those paths one after the other — 12.7 of 32 lanes,
+// ALU pipe 85 %, 0.75 of the HBM copy peak (profiles/r01_final_apply_tma_ncu_summary.json).  The tile is in shared memory anyway, so
+// the block SORTS its records by the path they will take (a counting sort over six classes: ballots + one prefix over the warps) and
+// thread j applies record perm[j]: warps become (nearly) uniform and the instruction stream shrinks accordingly.
+#ifndef DK_APPLY_SORT
+#define DK_APPLY_SORT 1
+#endif
 template <int ENGINE>
 __global__ void __launch_bounds__(STATE_THREADS, DK_APPLY_BLOCKS)
 apply_tma_kernel(const __grid_constant__ CUtensorMap tmap, uint64_t n, const uint8_t* __restrict__ action, uint32_t flags, uint8_t* __restrict__ err_out) {
     __shared__ __align__(1024) uint4 stage[STATE_THREADS * 8];
     __shared__ __align__(8) unsigned long long bar;
-    const uint64_t first = (uint64_t)blockIdx.x * STATE_THREADS, i = first + threadIdx.x;
+    __shared__ uint32_t cls_count[STATE_THREADS / 32][8];
+    __shared__ uint8_t perm[STATE_THREADS];
+    const uint64_t first = (uint64_t)blockIdx.x * STATE_THREADS;
     if (threadIdx.x == 0) TmaTile::init(&bar);
     __syncthreads();
     if (threadIdx.x == 0) TmaTile::load(&tmap, stage, &bar, first, (uint32_t)min((uint64_t)STATE_THREADS, n) * 128u);
-    const uint32_t a = i < n ? action[i] : 0u;
     TmaTile::wait(&bar, 0u);
+    uint32_t row = threadIdx.x;
+    if (DK_APPLY_SORT) {
+        // class of the own row from its last chunk (bytes 112..127: eyes, trick counts, card_index, n_reservations, points, meta)
+        const uint32_t t = threadIdx.x, lane = t & 31u, warp = t >> 5;
+        const uint4 last = stage[t * 8u + (7u ^ (t & 7u))];
+        const uint32_t phase = last.w & 3u, ci = (last.y >> 16) & 255u;
+        uint32_t cls = phase == DK_PHASE_RESERVATION ? 0u : (phase == DK_PHASE_ANNOUNCEMENT ? 1u : (phase == DK_PHASE_PLAY_CARD ? ((ci & 3u) == 3u ? (ci == 47u ? 4u : 3u) : 2u) : 5u));
+        if (first + t >= n) cls = 6u;
+        uint32_t before = 0, mine = 0;
+#pragma unroll
+        for (uint32_t c = 0; c < 7u; ++c) {
+            const uint32_t b = __ballot_sync(0xFFFFFFFFu, cls == c);
+            if (lane == 0) cls_count[warp][c] = (uint32_t)__popc(b);
+            if (cls == c) mine = (uint32_t)__popc(b & ((1u << lane) - 1u));
+        }
+        __syncthreads();
+#pragma unroll
+        for (uint32_t c = 0; c < 7u; ++c)
+#pragma unroll
+            for (uint32_t w = 0; w < (uint32_t)(STATE_THREADS / 32); ++w)
+                before += (c < cls || (c == cls && w < warp)) ? cls_count[w][c] : 0u;
+        perm[before + mine] = (uint8_t)t;
+        __syncthreads();
+        row = perm[t];
+    }
+    const uint64_t i = first + row;
     if (i < n) {
+        const uint32_t a = action[i];
         alignas(16) dk_state s;
-        StateStage<STATE_THREADS>::get(stage, s);
+        StateStage<STATE_THREADS>::get_row(stage, row, s);
         uint32_t err = ENGINE == DK_FDO ? fdo_state_apply_az<DK_APPLY_IDX>(s, a, (flags & DK_APPLY_SKIP_SINGLE) != 0) : doko_state_apply(s, a);
-        if (!err) StateStage<STATE_THREADS>::put(stage, s);              // an illegal action leaves the record as it was
+        if (!err) StateStage<STATE_THREADS>::put_row(stage, row, s);     // an illegal action leaves the record as it was
         if (err_out) err_out[i] = (uint8_t)err;
     }
     TmaTile::publish();
@@ -873,62 +910,73 @@ doko_assign_kernel(RngParams rp, uint64_t n_info, uint32_t samples, uint32_t spl
 
 // K4: leaf-parallel rollouts, [determinize →] rollout → block reduction.  One block per leaf; rollout r uses the Philox
 // unit (leaf id, r).  point_sum[leaf][seat] = exact integer sum of player_points over the rollouts (dead-end samples add 0).
-// DET = false (rollouts from leaves that are determinized already, BASELINE config 4): the bridge from the stored record to the
-// register-resident playout form is the same for every rollout of the leaf, so it is built once per block in shared memory and the
-// kernel fits 64 registers (8 blocks per SM: 1024 leaves are resident at once instead of running in 1.7 waves).
+// The bridge from the stored record to the register-resident playout form (trick history trackers, partial trick, announcement
+// resume point: fdo_state_to_live) is the same for every rollout of the leaf, so it is built ONCE per block in shared memory.
+// Determinized rollouts (DET) run as TWO kernels: K3 (fdo_determinize_kernel) writes the samples of a chunk of leaves to a scratch
+// buffer at its own occupancy (54 registers), this kernel reads rollout r's sample (37 bytes, coalesced) and only replaces what
+// card_matching changes — the four hands, the doubled-card mask and, in the reservation phase, the hidden reservations of the seats
+// that have declared.  History: sampler + record clone + bridge + playout in one loop body, 3.1e9 rollouts/s (72 registers, 400 B
+// of local memory per thread); bridge hoisted out of the loop, sampler still inside: 3.2e9 (the sampler's ~3200 instructions per
+// sample and its register file decide); two kernels: see DESIGN.md §3.
 template <bool DET>
-#ifndef DK_LEAF_DET_BLOCKS
-#define DK_LEAF_DET_BLOCKS 7
-#endif
 #ifndef DK_LEAF_BLOCKS
-#define DK_LEAF_BLOCKS 7
+#define DK_LEAF_BLOCKS 6
 #endif
-__global__ void __launch_bounds__(MATCH_THREADS, DET ? DK_LEAF_DET_BLOCKS : DK_LEAF_BLOCKS)
-fdo_leaf_rollouts_kernel(RngParams rp, uint64_t n_leaves, uint32_t rollouts, uint32_t splits, const dk_state* __restrict__ states, long long* __restrict__ point_sum) {
-    __shared__ MatchPrep prep;
+__global__ void __launch_bounds__(MATCH_THREADS, DK_LEAF_BLOCKS)
+fdo_leaf_rollouts_kernel(RngParams rp, uint64_t leaf0, uint64_t n_leaves, uint32_t rollouts, uint32_t splits, const dk_state* __restrict__ states,
+                         const uint64_t* __restrict__ smp_hands, const uint8_t* __restrict__ smp_res, const uint8_t* __restrict__ smp_status,
+                         long long* __restrict__ point_sum) {
     __shared__ __align__(16) dk_state leaf;
     __shared__ FdoLive live0;
     __shared__ FdoResume resume0;
     __shared__ int live_ok;
     __shared__ int red[4];
-    __shared__ __align__(16) uint32_t lut[CARD_LUT_WORDS + (DET ? 0u : SEL12_WORDS)];   // without determinization: the 12-bit rank-select table too
+    __shared__ __align__(16) uint32_t lut[CARD_LUT_WORDS + SEL12_WORDS];   // the full table set, 12-bit rank select included
     fill_card_lut(lut);
-    if (!DET) fill_sel12(lut);
+    fill_sel12(lut);
     // `splits` blocks share one leaf when there are fewer leaves than one wave of blocks (rollout r belongs to block
     // r / MATCH_THREADS % splits); their integer sums meet in point_sum by atomics (zeroed by the host), so the result does not change.
-    const uint64_t i = blockIdx.x / splits;
-    const uint32_t part = blockIdx.x - (uint32_t)i * splits;
-    if (i >= n_leaves) return;
+    const uint64_t li = blockIdx.x / splits;                       // leaf inside this launch
+    const uint32_t part = blockIdx.x - (uint32_t)li * splits;
+    if (li >= n_leaves) return;
+    const uint64_t i = leaf0 + li;
     if (threadIdx.x < 8) reinterpret_cast<uint4*>(&leaf)[threadIdx.x] = __ldg(reinterpret_cast<const uint4*>(states + i) + threadIdx.x);
     if (threadIdx.x < 4) red[threadIdx.x] = 0;
     __syncthreads();
     if (threadIdx.x == 0) {
-        if (DET) fdo_match_prepare(leaf, prep);
-        else { FdoLive g; FdoResume rs; live_ok = fdo_state_to_live<true>(leaf, g, rs) ? 1 : 0; live0 = g; resume0 = rs; }
+        FdoLive g; FdoResume rs;
+        live_ok = fdo_state_to_live<true>(leaf, g, rs) ? 1 : 0;
+        live0 = g; resume0 = rs;
     }
     __syncthreads();
     int acc[4] = {0, 0, 0, 0};
     for (uint32_t r = part * MATCH_THREADS + threadIdx.x; r < rollouts; r += splits * MATCH_THREADS) {
         RngKey key = make_key(rp, i, rp.first_sub + r, true);
         int32_t p[4];
-        if (DET) {
-            alignas(16) dk_state s = leaf;
-            uint32_t status = 0;
-            if (prep.valid) {
-                uint64_t h[4];
-                uint8_t res[4];
-                status = fdo_match_sample(prep, key, h, res);
-                fdo_state_with_hands_and_reservations(s, h, res);
+        if (!live_ok) { p[0] = leaf.points[0]; p[1] = leaf.points[1]; p[2] = leaf.points[2]; p[3] = leaf.points[3]; }
+        else if (DET) {
+            const uint64_t o = li * rollouts + r;                                     // sample of (leaf, rollout) in the scratch buffer
+            if (smp_status[o] != 0u) continue;                                        // a dead end adds nothing
+            const ulonglong2 h01 = __ldg(reinterpret_cast<const ulonglong2*>(smp_hands + 4 * o)), h23 = __ldg(reinterpret_cast<const ulonglong2*>(smp_hands + 4 * o) + 1);
+            const uint32_t res4 = __ldg(reinterpret_cast<const uint32_t*>(smp_res) + o);
+            FdoLive g = live0;
+            FdoResume rs = resume0;
+            // clone_with_different_hands_and_reservations (state.rs:96-119) on the playout form: frame seat k = absolute seat base + k
+            const uint32_t base = g.base;
+            const uint32_t any[4] = {hand_any24(h01.x), hand_any24(h01.y), hand_any24(h23.x), hand_any24(h23.y)};
+            g.dup = hand_both24(h01.x) | hand_both24(h01.y) | hand_both24(h23.x) | hand_both24(h23.y);
+            g.h0 = any[base & 3u]; g.h1 = any[(base + 1u) & 3u]; g.h2 = any[(base + 2u) & 3u]; g.h3 = any[(base + 3u) & 3u];
+            if (rs.n_res < 4u) {                                                      // reservation phase: frame base = game start seat
+#pragma unroll
+                for (uint32_t k = 0; k < 3u; ++k) if (k < rs.n_res) rs.res_action[k] = fdo_action_from_res_code((res4 >> (8u * ((base + k) & 3u))) & 255u);
             }
-            if (status != 0u) continue;
-            FdoLive g; FdoResume rs;
-            if (fdo_state_to_live(s, g, rs)) { fdo_play_to_end<false, false>(g, key, &rs, lut); fdo_final_points(g, p); }
-            else { p[0] = s.points[0]; p[1] = s.points[1]; p[2] = s.points[2]; p[3] = s.points[3]; }
-        } else if (live_ok) {
+            fdo_play_to_end<false, false, true>(g, key, &rs, lut);
+            fdo_final_points(g, p);
+        } else {
             FdoLive g = live0;
             fdo_play_to_end<false, false, true>(g, key, &resume0, lut);
             fdo_final_points(g, p);
-        } else { p[0] = leaf.points[0]; p[1] = leaf.points[1]; p[2] = leaf.points[2]; p[3] = leaf.points[3]; }
+        }
         acc[0] += p[0]; acc[1] += p[1]; acc[2] += p[2]; acc[3] += p[3];
     }
 #pragma unroll

@@ -339,67 +339,69 @@ pack_replay_records_kernel(unsigned long long n_rows, const long long* __restric
     }
 }
 
-// N3: one UCT tree per thread.  Tree t = root (t / trees_per_root), sub-index d = t % trees_per_root; with `determinize` the root state
-// is first replaced by determinization (first_sub + d) of the info-state (the dk_determinize stream).  Iteration `it` runs on the
-// Philox unit (first_id + root, (first_sub + d) * iterations + it).
-// Block shape and phase barriers, measured three times alternating (profiles/r01_uct_phase_sync_experiment.txt; Miter/s at 16 k / 131 k
-// trees): 64 x 16 without barriers 122 / 418, 128 x 8 with a block barrier between select / expand / rollout / backpropagate 123 / 436.
-// At a million resident trees (14 GB of nodes) both forms vary between 680 and 900 from run to run — the random node traffic decides.
-// The kernel is 120 KB of code and its top stall at high tree counts is instruction fetch; the barriers keep the four warps of a block in
-// the same stretch of code.
-#ifndef DK_UCT_THREADS
-#define DK_UCT_THREADS 128
+// N3: one UCT tree per thread, one kernel per phase (uct.cuh).  Tree t = root (t / trees_per_root), sub-index d = t % trees_per_root;
+// with `determinize` the root state is first replaced by determinization (first_sub + d) of the info-state (the dk_determinize stream).
+// Iteration `it` runs on the Philox unit (first_id + root, (first_sub + d) * iterations + it).
+#ifndef DK_UCT_TREE_BLOCKS
+#define DK_UCT_TREE_BLOCKS 8
 #endif
-#ifndef DK_UCT_MIN_BLOCKS
-#define DK_UCT_MIN_BLOCKS 8
+#ifndef DK_UCT_EXPAND_IDX
+#define DK_UCT_EXPAND_IDX true      // the expansion's record in local memory (128 B, no spills): the register form spilled 700 B at 64 registers
 #endif
-#ifndef DK_UCT_PHASE_SYNC
-#define DK_UCT_PHASE_SYNC 1
+#ifndef DK_UCT_ROLLOUT_BLOCKS
+#define DK_UCT_ROLLOUT_BLOCKS 4      // 64 registers: 1024 trees resident per SM (3 blocks of 80 registers measured 7 % slower at 131 072 trees)
 #endif
-constexpr int UCT_THREADS = DK_UCT_THREADS;
-struct UctBlockSync { __device__ __forceinline__ void operator()() const { if (DK_UCT_PHASE_SYNC) __syncthreads(); } };
-__global__ void __launch_bounds__(UCT_THREADS, DK_UCT_MIN_BLOCKS)
-fdo_uct_kernel(RngParams rp, uint64_t n_trees, uint32_t trees_per_root, uint32_t iterations, double c, const double* __restrict__ ln_table, int determinize,
-               const dk_state* __restrict__ states, UctNode* __restrict__ pool_base, uint32_t* __restrict__ visits_out, float* __restrict__ values_out,
-               uint8_t* __restrict__ action_out, uint8_t* __restrict__ status_out) {
-    __shared__ uint32_t lut[CARD_LUT_WORDS];
-    stage_card_lut(lut);
-    const uint64_t t_raw = (uint64_t)blockIdx.x * UCT_THREADS + threadIdx.x;
-    const bool in_range = t_raw < n_trees;
-    if (!DK_UCT_PHASE_SYNC && !in_range) return;
-    const uint64_t t = in_range ? t_raw : n_trees - 1;                 // (out-of-range threads idle through the barriers)
+constexpr int UCT_THREADS = 128;
+__device__ __forceinline__ RngKey uct_iteration_key(const RngParams& rp, uint64_t t, uint32_t trees_per_root, uint32_t iterations, uint32_t it) {
     const uint64_t root = t / trees_per_root;
     const uint32_t sub = rp.first_sub + (uint32_t)(t - root * trees_per_root);
-    UctNode* pool = pool_base + t * ((uint64_t)iterations + 1ull);
-    uint32_t status = 0;
+    return make_key(rp, root, sub * iterations + it, true);
+}
+__global__ void __launch_bounds__(UCT_THREADS)
+uct_root_kernel(RngParams rp, UctPool P, uint32_t trees_per_root, int determinize, const dk_state* __restrict__ states, uint32_t* __restrict__ visits_out,
+                float* __restrict__ values_out) {
+    const uint64_t t = (uint64_t)blockIdx.x * UCT_THREADS + threadIdx.x;
+    if (t >= P.n_trees) return;
+    const uint64_t root = t / trees_per_root;
+    const uint32_t sub = rp.first_sub + (uint32_t)(t - root * trees_per_root);
+    alignas(16) dk_state s;
+    load_state(states + root, s);
+    uct_phase_root(P, t, s, determinize != 0, make_key(rp, root, sub, true));
+    if (visits_out) for (uint32_t a = 0; a < N_ACTIONS; ++a) visits_out[t * N_ACTIONS + a] = 0u;
+    if (values_out) for (uint32_t a = 0; a < N_ACTIONS; ++a) values_out[t * N_ACTIONS + a] = 0.0f;
+}
+// select(it) + expand(it)
+__global__ void __launch_bounds__(UCT_THREADS, DK_UCT_TREE_BLOCKS)
+uct_tree_kernel(RngParams rp, UctPool P, uint32_t trees_per_root, uint32_t iterations, uint32_t it, double c, UctTables T) {
+    const uint64_t t = (uint64_t)blockIdx.x * UCT_THREADS + threadIdx.x;
+    if (t >= P.n_trees) return;
+    if (!(P.ctl[t] & UCT_CTL_ACTIVE)) return;
+    uct_phase_tree<DK_UCT_EXPAND_IDX>(P, t, it, c, T, uct_iteration_key(rp, t, trees_per_root, iterations, it));
+}
+// rollout(it) + backpropagate(it)
+constexpr int UCT_ROLLOUT_THREADS = 256;
+__global__ void __launch_bounds__(UCT_ROLLOUT_THREADS, DK_UCT_ROLLOUT_BLOCKS)
+uct_rollout_kernel(RngParams rp, UctPool P, uint32_t trees_per_root, uint32_t iterations, uint32_t it) {
+    __shared__ __align__(16) uint32_t lut[CARD_LUT_WORDS + SEL12_WORDS];
+    fill_card_lut(lut);
+    fill_sel12(lut);
+    __syncthreads();
+    const uint64_t t = (uint64_t)blockIdx.x * UCT_ROLLOUT_THREADS + threadIdx.x;
+    if (t >= P.n_trees) return;
+    const uint32_t ctl = P.ctl[t];
+    if (!(ctl & UCT_CTL_ACTIVE)) return;
+    if (ctl & UCT_CTL_ROLLOUT) uct_phase_rollout<true>(P, t, uct_iteration_key(rp, t, trees_per_root, iterations, it), lut);
+    uct_phase_backprop(P, t);
+}
+__global__ void __launch_bounds__(UCT_THREADS)
+uct_moves_kernel(UctPool P, uint32_t* __restrict__ visits_out, float* __restrict__ values_out, uint8_t* __restrict__ action_out, uint8_t* __restrict__ status_out) {
+    const uint64_t t = (uint64_t)blockIdx.x * UCT_THREADS + threadIdx.x;
+    if (t >= P.n_trees) return;
+    const uint32_t status = P.status[t];
     uint32_t best = 0xFFu;
-    if (in_range) {
-        alignas(16) dk_state s;
-        load_state(states + root, s);
-        if (determinize && st_phase(s) != DK_PHASE_FINISHED) {
-            MatchPrep prep;
-            fdo_match_prepare(s, prep);
-            uint64_t h[4];
-            uint8_t res[4];
-            status = fdo_match_sample(prep, make_key(rp, root, sub, true), h, res);
-            if (status == 0u) fdo_state_with_hands_and_reservations(s, h, res);
-        }
-        if (visits_out) for (uint32_t a = 0; a < N_ACTIONS; ++a) visits_out[t * N_ACTIONS + a] = 0u;
-        if (values_out) for (uint32_t a = 0; a < N_ACTIONS; ++a) values_out[t * N_ACTIONS + a] = 0.0f;
-        if (status == 0u) uct_init_node(pool[0], s, UCT_NONE, 63u, true);
-    }
-    bool active = in_range && status == 0u;
-    uint32_t n_nodes = 1;
-    for (uint32_t it = 0; it < iterations; ++it) {
-        if (!DK_UCT_PHASE_SYNC && !active) break;
-        RngKey key = make_key(rp, root, sub * iterations + it, true);
-        if (uct_iteration(pool, n_nodes, key, c, ln_table, lut, active, UctBlockSync())) { status = 3u; active = false; }
-    }
-    if (in_range) {
-        if (status == 0u) best = uct_moves(pool, visits_out ? visits_out + t * N_ACTIONS : (uint32_t*)nullptr, values_out ? values_out + t * N_ACTIONS : (float*)nullptr);
-        if (action_out) action_out[t] = (uint8_t)best;
-        if (status_out) status_out[t] = (uint8_t)status;
-    }
+    if (status == 0u) best = uct_moves(P, t, visits_out ? visits_out + t * N_ACTIONS : (uint32_t*)nullptr, values_out ? values_out + t * N_ACTIONS : (float*)nullptr);
+    if (action_out) action_out[t] = (uint8_t)best;
+    if (status_out) status_out[t] = (uint8_t)status;
 }
 
 }  // namespace dk

@@ -1,8 +1,39 @@
-// uct.cuh — the reference's UCT search over the full-rules game, one tree per thread.
+// uct.cuh — the reference's UCT search over the full-rules game, one tree per thread, one KERNEL PER PHASE.
 //   rs-doko-mcts/src/mcts/node.rs:21-260 (McNode), mcts.rs:45-250 (MCTS::monte_carlo_tree_search),
 //   rs-doko-mcts/src/env/envs/env_state_full_doko.rs:62-220 (McFullDokoEnvState), rs-doko-evaluator/.../mcts_policy.rs:96-118.
-// A tree lives in a private slice of a device pool: iterations + 1 nodes of 208 bytes (the 128-byte state, exact integer win sum,
-// visits, parent, the unexpanded-action mask and up to 12 child indices in insertion order — the order find_best_child walks).
+//
+// Round 1 ran the whole iteration (select → expand → rollout → backpropagate) as one 100 KB kernel body: ncu showed 15 warps per
+// issue slot waiting for instructions (the blocks of an SM sat in different phases and evicted each other's code), 14.5 of 32 lanes
+// and 4.35e8 iterations/s (profiles/r01_uct_ncu_summary.json).  Now an iteration of ALL trees is two launches, so every SM
+// executes one phase's code at a time and each phase has its own register budget:
+//   uct_tree_kernel     select_promising_node (dependent loads, latency bound: the per-level data is ONE block of at most five
+//                       sectors) + expand_single (pick an unexpanded action, play it on the node's record, append the child)
+//   uct_rollout_kernel  the K2-style _no_announcement playout from the new record (lock-step card loop, full table set), then
+//                       backpropagate: the memory-bound walk up of the warps that are done overlaps the playouts still running
+// Per-tree hand-over between the launches (selected node, node to roll out from, packed result) is 4 bytes per tree and launch.
+//
+// Data layout.  A tree owns `iterations + 1` node slots.  A node is split in two arrays:
+//   UctHead (160 B = 5 sectors)  sector 0: info | children 0-3;  sector 1: children 4-11;  sectors 2-4: (visits, exact integer
+//                                win sum) of the children, IN INSERTION ORDER (the order find_best_child walks)
+//   dk_state (128 B)             McNode::state
+// The statistics of a node live in ITS PARENT's block: selection at a node reads one contiguous block instead of the node plus twelve
+// scattered children (round 1: 13 sectors in 13 lines per level), and backpropagation updates the slot it came through.  A node's own
+// visit count — the N of ln N — is 1 + the visits of its children (the iteration that created it plus every later one through it);
+// the root's is the iteration number.  A child entry also carries HOW MANY ACTIONS its target had when it was created, so the walk
+// knows before it loads a block which sectors it needs (two for <= 4 actions, all five only for wide nodes).
+//
+// Single-action nodes are skipped.  Below the root every announcement-phase state has exactly one action (NoAnnouncement; the calls
+// are removed, env_state_full_doko.rs:132-172), so an early-game path is mostly chains of such nodes between two card nodes: their
+// only child is chosen whatever its numbers are and nobody ever reads their statistics.  The child entry of a multi-action node (an
+// ANCHOR; the root always is one) therefore points at the END of the chain below that child — the first node that is an anchor
+// itself or still has its action to expand — and is moved when the chain grows.  The tree keeps the reference's shape (every chain
+// node is a node, created by its own iteration with its own rollout); only the walks skip them.  Measured before this change: paths
+// of 15-20 levels, 217 MB of DRAM reads per iteration of 131 072 trees for the walk up alone (profiles/r02_uct_rollout_v3_*.json).
+//
+// The walk down records its anchors — (node, slot, seat to move) per level, <= 53 levels: root + 4 reservations + 48 cards — in a
+// per-tree path buffer ([level][tree], coalesced).  Backpropagation reads that list and updates the slots with INDEPENDENT
+// read-modify-writes: no parent pointers, no dependent loads on the way up.
+//
 // The f64 UCT arithmetic is done in the reference's order with explicitly rounded operations (no FMA contraction); ln(N) comes from
 // a table the host fills with libm's log, the function Rust's f64::ln lowers to, so selection is bit-identical to the CPU path.
 #pragma once
@@ -16,19 +47,74 @@ constexpr uint32_t UCT_MAX_CHILDREN = 12u;       // distinct card types in a han
 constexpr uint32_t UCT_NONE = 0xFFFFFFFFu;
 constexpr uint64_t UCT_ACTION_MASK = (1ull << 39) - 1ull;
 
-struct alignas(16) UctNode {
-    dk_state state;                   // McNode::state
-    long long win;                    // win_score: a sum of integer points, exact
-    uint32_t visits;
-    uint32_t parent;                  // UCT_NONE for the root
-    uint64_t info;                    // bits 0-38 unexpanded_actions | 40-41 current_player | 42 is_terminal | 48-53 last_action | 56-59 #children
-    uint32_t child[UCT_MAX_CHILDREN];
+struct UctStat { uint32_t vis; int32_t win; };   // win_score: a sum of integer points, exact (|points| < 128, < 2^24 iterations)
+struct alignas(32) UctHead {
+    uint64_t info;                    // bits 0-38 unexpanded_actions | 40-41 current_player | 42 is_terminal | 44-47 #actions at creation |
+                                      // 48-53 last_action | 56-59 #children
+    uint32_t spare[2];
+    uint32_t child[UCT_MAX_CHILDREN]; // bits 0-23 node at the end of the single-action chain below child k | bits 28-31 #actions of that node
+    UctStat stat[UCT_MAX_CHILDREN];   // visits / win_score of child k
 };
-static_assert(sizeof(UctNode) == 208, "UctNode layout");
+static_assert(sizeof(UctHead) == 160, "UctHead layout");
+constexpr uint32_t UCT_NODE_MASK = 0x00FFFFFFu;
+constexpr uint64_t UCT_MAX_ITERATIONS = (1ull << 24) - 2ull;   // int32 win sums, 24-bit node indices
+constexpr uint32_t UCT_MAX_PATH = 56u;                          // anchors on a path: root + 4 reservations + 48 cards = 53
+DK_HD uint32_t uct_path_entry(uint32_t node, uint32_t slot, uint32_t cur) { return node | (slot << 24) | (cur << 28); }
 
-DK_HD uint32_t uct_n_children(const UctNode& n) { return (uint32_t)(n.info >> 56) & 15u; }
-DK_HD uint32_t uct_cur(const UctNode& n) { return (uint32_t)(n.info >> 40) & 3u; }
-DK_HD uint32_t uct_last_action(const UctNode& n) { return (uint32_t)(n.info >> 48) & 63u; }
+// Per-tree control words (one array each, [n_trees]): what the phases hand to each other.
+enum : uint32_t { UCT_CTL_ACTIVE = 1u, UCT_CTL_ROLLOUT = 2u };
+struct UctPool {
+    UctHead* heads;       // [iterations + 1][n_trees]
+    dk_state* states;     // [iterations + 1][n_trees]
+    uint32_t* path;       // [UCT_MAX_PATH][n_trees]: the anchors of the current iteration's path (uct_path_entry)
+    uint32_t* path_len;
+    uint8_t* root_action; // [n_trees][16]: action of the root's child k (the root's entries point past single-action chains)
+    uint32_t* ctl;        // UCT_CTL_* flags
+    uint32_t* explore;    // node the rollout starts from
+    uint32_t* result;     // player_points of the rollout, int8 per seat
+    uint32_t* n_nodes;
+    uint32_t* status;     // 0 ok, determinization status, 3 = a node would need more than UCT_MAX_CHILDREN children / a path more than UCT_MAX_PATH anchors
+    uint64_t n_trees;
+    uint64_t node_stride, tree_stride;   // element (node, tree) of heads / states: node * node_stride + tree * tree_stride
+    DK_HD UctHead& head(uint64_t t, uint32_t node) const { return heads[(uint64_t)node * node_stride + t * tree_stride]; }
+    DK_HD dk_state& state(uint64_t t, uint32_t node) const { return states[(uint64_t)node * node_stride + t * tree_stride]; }
+    DK_HD uint32_t& path_at(uint64_t t, uint32_t level) const { return path[(uint64_t)level * ((n_trees + 63ull) & ~63ull) + t]; }
+};
+// Carves the caller's workspace (256-byte aligned inside): heads | states | path buffer | control arrays.
+DK_HD uint64_t uct_workspace_bytes(uint64_t n_trees, uint64_t iterations) {
+    const uint64_t arr = (n_trees * 4ull + 255ull) & ~255ull;
+    return 256ull + n_trees * (iterations + 1ull) * (sizeof(UctHead) + sizeof(dk_state)) + (UCT_MAX_PATH + 6ull) * arr + ((n_trees * 16ull + 255ull) & ~255ull);
+}
+// tree_major = false: [node][tree] (the node every tree appends in an iteration and the root level are contiguous across a warp);
+// tree_major = true: [tree][node] (a tree's nodes share a few pages).
+inline UctPool uct_carve(void* workspace, uint64_t n_trees, uint64_t iterations, bool tree_major = false) {
+    char* p = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(workspace) + 255u) & ~(uintptr_t)255u);
+    UctPool P;
+    P.n_trees = n_trees;
+    P.node_stride = tree_major ? 1ull : n_trees;
+    P.tree_stride = tree_major ? iterations + 1ull : 1ull;
+    P.heads = reinterpret_cast<UctHead*>(p); p += n_trees * (iterations + 1ull) * sizeof(UctHead);
+    P.states = reinterpret_cast<dk_state*>(p); p += n_trees * (iterations + 1ull) * sizeof(dk_state);
+    const uint64_t arr = (n_trees * 4ull + 255ull) & ~255ull;
+    P.path = reinterpret_cast<uint32_t*>(p); p += UCT_MAX_PATH * arr;
+    P.path_len = reinterpret_cast<uint32_t*>(p); p += arr;
+    P.ctl = reinterpret_cast<uint32_t*>(p); p += arr;
+    P.explore = reinterpret_cast<uint32_t*>(p); p += arr;
+    P.result = reinterpret_cast<uint32_t*>(p); p += arr;
+    P.n_nodes = reinterpret_cast<uint32_t*>(p); p += arr;
+    P.status = reinterpret_cast<uint32_t*>(p); p += arr;
+    P.root_action = reinterpret_cast<uint8_t*>(p);
+    return P;
+}
+
+DK_HD uint32_t uct_n_children(uint64_t info) { return (uint32_t)(info >> 56) & 15u; }
+DK_HD uint32_t uct_n_actions(uint64_t info) { return (uint32_t)(info >> 44) & 15u; }
+DK_HD uint32_t uct_cur(uint64_t info) { return (uint32_t)(info >> 40) & 3u; }
+DK_HD uint32_t uct_last_action(uint64_t info) { return (uint32_t)(info >> 48) & 63u; }
+DK_HD uint32_t uct_pack_points(const int32_t p[4]) {
+    return ((uint32_t)p[0] & 255u) | (((uint32_t)p[1] & 255u) << 8) | (((uint32_t)p[2] & 255u) << 16) | (((uint32_t)p[3] & 255u) << 24);
+}
+DK_HD int32_t uct_unpack_point(uint32_t packed, uint32_t seat) { return (int32_t)(int8_t)((packed >> (8u * seat)) & 255u); }
 
 DK_HD double dk_inf() {
 #if defined(__CUDA_ARCH__)
@@ -68,20 +154,24 @@ DK_HD double dk_dsqrt(double a) {
 
 // McFullDokoEnvState::allowed_actions(first_expansion) (env_state_full_doko.rs:132-172): below the root the solo / wedding
 // reservations disappear once any seat has declared a solo, and the announcement calls always.
+template <bool IDX = true>
 DK_HD uint64_t uct_allowed(const dk_state& s, bool first_expansion) {
-    uint64_t m = fdo_state_legal_mask<true>(s);
+    uint64_t m = fdo_state_legal_mask<IDX>(s);
     if (!first_expansion) {
-        for (uint32_t i = 0; i < s.n_reservations && i < 4u; ++i)
-            if (s.reservations[i] >= 2u) m &= ~(0xFFull << 25);
+        bool solo = false;
+#pragma unroll
+        for (uint32_t i = 0; i < 4u; ++i) solo |= i < s.n_reservations && s.reservations[i] >= 2u;
+        if (solo) m &= ~(0xFFull << 25);
         m &= ~(0x1Full << 33);
     }
     return m;
 }
-DK_HD void uct_init_node(UctNode& n, const dk_state& s, uint32_t parent, uint32_t last_action, bool root) {   // node.rs:138-200
-    n.state = s;
-    n.win = 0; n.visits = 0; n.parent = parent;
+template <bool IDX = true>
+DK_HD uint64_t uct_node_info(const dk_state& s, uint32_t last_action, bool root) {                 // node.rs:138-200
     const bool terminal = st_phase(s) == DK_PHASE_FINISHED;
-    n.info = uct_allowed(s, root) | ((uint64_t)(terminal ? 0u : st_cur(s)) << 40) | ((uint64_t)(terminal ? 1u : 0u) << 42) | ((uint64_t)(last_action & 63u) << 48);
+    const uint64_t allowed = uct_allowed<IDX>(s, root);
+    return allowed | ((uint64_t)(terminal ? 0u : st_cur(s)) << 40) | ((uint64_t)(terminal ? 1u : 0u) << 42) | ((uint64_t)popcll(allowed) << 44) |
+           ((uint64_t)(last_action & 63u) << 48);
 }
 
 DK_HD float dk_fdiv_fast(float a, float b) {
@@ -101,8 +191,8 @@ DK_HD double uct_value_exact(long long win, uint32_t vis, double min_q, double s
 }
 
 // find_best_child (node.rs:258-278): the child with the strictly greatest f64 UCT value, first in child order among equals.
+// Returns the SLOT of the child.  vis / win: the statistics of the nch <= W children in insertion order (entries >= nch are ignored).
 //
-// The children's (visits, win) pairs are fetched first, all loads in flight together (one memory round trip per tree level).
 // The f64 divisions and square roots of the reference are software sequences of ~30 instructions each on the GPU, so the
 // decision is taken in two stages that TOGETHER are bit-identical to evaluating every child in f64:
 //   1. a cheap f32 evaluation u~ with a proven error bound |u~ - u| <= eps.  Only children with u~ >= max(u~) - 2 eps can be the
@@ -113,54 +203,63 @@ DK_HD double uct_value_exact(long long win, uint32_t vis, double min_q, double s
 //      when span~ < 4e-3 or a child has no visits.
 //   2. the survivors are evaluated exactly.  The exact min / max Q come from the children that are minimal / maximal as RATIONALS
 //      (integer cross-multiplication; IEEE division is monotone, so the rounded extremes are the extremes of the rounded values).
-DK_HD uint32_t uct_find_best_child(const UctNode* __restrict__ pool, uint32_t self, double c, double ln_n, bool use_filter = true) {   // ln_n = ln(visits of `self`)
-    const UctNode& p = pool[self];
-    const uint32_t nch = uct_n_children(p);
-    uint32_t idx[UCT_MAX_CHILDREN], vis[UCT_MAX_CHILDREN];
-    long long win[UCT_MAX_CHILDREN];
-#pragma unroll
-    for (uint32_t k = 0; k < UCT_MAX_CHILDREN; ++k) idx[k] = k < nch ? p.child[k] : self;
-#pragma unroll
-    for (uint32_t k = 0; k < UCT_MAX_CHILDREN; ++k) { vis[k] = pool[idx[k]].visits; win[k] = pool[idx[k]].win; }
+// vis_tab[v] = (float(1 / v), float(1 / sqrt(v))) for every visit count a search can reach (v <= iterations; host-computed in f64,
+// rounded once): the filter's division and square root become two multiplications (same error budget: each factor is within half an
+// ulp), and the lookup is one unconditional 8-byte load.
+struct UctF2 { float x, y; };
+struct UctTables { const double* ln; const UctF2* vis_tab; };
+DK_HD UctF2 uct_vis_factors(const UctTables& T, uint32_t v) { return T.vis_tab[v]; }
+template <uint32_t W = UCT_MAX_CHILDREN>
+DK_HD uint32_t uct_best_slot(uint32_t nch, const uint32_t vis[W], const int32_t win[W], uint32_t parent_visits, double c, double ln_n, const UctTables& T,
+                             bool use_filter = true) {
     uint32_t cand = (1u << nch) - 1u;
     {   // stage 1: f32 filter
-        float qf[UCT_MAX_CHILDREN];
+        float qf[W], rs[W];
         float minf = 3.0e38f, maxf = -3.0e38f;
         bool any_unvisited = false;
 #pragma unroll
-        for (uint32_t k = 0; k < UCT_MAX_CHILDREN; ++k) {
+        for (uint32_t k = 0; k < W; ++k) {
             const bool on = k < nch;
             any_unvisited |= on && vis[k] == 0u;
-            const float qk = dk_fdiv_fast((float)win[k], (float)(vis[k] ? vis[k] : 1u));
-            qf[k] = qk;
+            const UctF2 f = uct_vis_factors(T, on && vis[k] ? vis[k] : 1u);
+            const float qk = (float)win[k] * f.x;
+            qf[k] = qk; rs[k] = f.y;
             if (on && qk < minf) minf = qk;
             if (on && qk > maxf) maxf = qk;
         }
         const float spanf = maxf - minf;
-        if (use_filter && !any_unvisited && spanf >= 4.0e-3f && p.visits < (1u << 24)) {
-            const float cf = (float)c, lnf = (float)ln_n;
+        if (use_filter && !any_unvisited && spanf >= 4.0e-3f && parent_visits < (1u << 24)) {
+            const float cf = (float)c, expl = cf * sqrtf((float)ln_n);
             const float eps = dk_fdiv_fast(1.0e-3f, spanf) + 4.0e-5f * cf + 4.0e-5f;
             const float scale = dk_fdiv_fast(2.0f, spanf);
-            float uf[UCT_MAX_CHILDREN];
+            float uf[W];
             float top = -3.0e38f;
 #pragma unroll
-            for (uint32_t k = 0; k < UCT_MAX_CHILDREN; ++k) {
-                const float u = (qf[k] - minf) * scale - 1.0f + cf * sqrtf(dk_fdiv_fast(lnf, (float)(vis[k] ? vis[k] : 1u)));
+            for (uint32_t k = 0; k < W; ++k) {
+                const float u = (qf[k] - minf) * scale - 1.0f + expl * rs[k];
                 uf[k] = u;
                 if (k < nch && u > top) top = u;
             }
             const float thr = top - 2.0f * eps;
             uint32_t m = 0;
 #pragma unroll
-            for (uint32_t k = 0; k < UCT_MAX_CHILDREN; ++k) m |= (k < nch && uf[k] >= thr) ? (1u << k) : 0u;
+            for (uint32_t k = 0; k < W; ++k) m |= (k < nch && uf[k] >= thr) ? (1u << k) : 0u;
             cand = m;
-            if ((m & (m - 1u)) == 0u) {                                   // a single survivor: it is the exact arg-max
-                uint32_t best = self;
-#pragma unroll
-                for (uint32_t k = 0; k < UCT_MAX_CHILDREN; ++k) if ((m >> k) & 1u) best = idx[k];
-                return best;
-            }
+            if ((m & (m - 1u)) == 0u) return ffs0(m);                     // a single survivor: it is the exact arg-max
         }
+    }
+    {   // Candidates with IDENTICAL statistics have identical exact values (same inputs, same arithmetic), and the first in child order
+        // wins among equals: when every candidate carries the first candidate's numbers — the common tie of a young tree, siblings
+        // visited equally often with equal results — the decision needs no f64 at all.  Only valid when the candidates are ALL children
+        // or survivors of the filter (then no other child can beat them), which is what `cand` holds here.
+        const uint32_t first = ffs0(cand);
+        uint32_t v0 = 0; int32_t w0 = 0;
+        bool same = true;
+#pragma unroll
+        for (uint32_t k = 0; k < W; ++k) { v0 = k == first ? vis[k] : v0; w0 = k == first ? win[k] : w0; }
+#pragma unroll
+        for (uint32_t k = 0; k < W; ++k) same &= !((cand >> k) & 1u) || (vis[k] == v0 && win[k] == w0);
+        if (same) return first;
     }
     // stage 2: exact evaluation of the survivors.  Extremes of Q as rationals: win_a / vis_a < win_b / vis_b  <=>  win_a vis_b < win_b vis_a
     // (unvisited children count as Q = 0 = 0 / 1).
@@ -168,7 +267,7 @@ DK_HD uint32_t uct_find_best_child(const UctNode* __restrict__ pool, uint32_t se
     uint32_t lo_v = 0, hi_v = 0;
 #pragma unroll 1
     for (uint32_t k = 0; k < nch; ++k) {
-        const long long w = vis[k] ? win[k] : 0;
+        const long long w = vis[k] ? (long long)win[k] : 0;
         const uint32_t v = vis[k] ? vis[k] : 1u;
         if (lo_v == 0u || w * (long long)lo_v < lo_w * (long long)v) { lo_w = w; lo_v = v; }
         if (hi_v == 0u || w * (long long)hi_v > hi_w * (long long)v) { hi_w = w; hi_v = v; }
@@ -181,83 +280,158 @@ DK_HD uint32_t uct_find_best_child(const UctNode* __restrict__ pool, uint32_t se
 #pragma unroll 1
     for (uint32_t k = 0; k < nch; ++k) {
         if (!((cand >> k) & 1u)) continue;
-        const double u = uct_value_exact(win[k], vis[k], min_q, span, flat, ln_n, c);
-        if (u > best_uct) { best_uct = u; best = idx[k]; }
+        const double u = uct_value_exact((long long)win[k], vis[k], min_q, span, flat, ln_n, c);
+        if (u > best_uct) { best_uct = u; best = k; }
     }
     return best;
 }
 
-// One iteration of monte_carlo_tree_search (mcts.rs:176-199): select → expand_single → random_rollout → backpropagate.
-// key = the iteration's Philox unit.  Returns 1 when a node would need more than UCT_MAX_CHILDREN children (cannot happen for
-// states reachable by the rules; reported instead of overflowing).
-// `sync()` is called between the four phases by EVERY thread (active or not): the kernel passes a block barrier so that all warps of
-// a block run the same phase — and hence the same stretch of this 100+ KB of code — at the same time; the host simulator passes a no-op.
-struct UctNoSync { DK_HD void operator()() const {} };
-template <class Sync = UctNoSync>
-DK_HD uint32_t uct_iteration(UctNode* __restrict__ pool, uint32_t& n_nodes, const RngKey& key, double c, const double* __restrict__ ln_table,
-                             const uint32_t* __restrict__ lut, bool active = true, Sync sync = Sync()) {
-    uint32_t node = 0, err = 0;
-    if (active) {
-        for (;;) {                                                               // select_promising_node (:45-63)
-            const UctNode& n = pool[node];
-            if (uct_n_children(n) == 0u || (n.info & UCT_ACTION_MASK) != 0ull) break;
-            node = uct_find_best_child(pool, node, c, ln_table[n.visits]);
-        }
+// ---- the phases of one iteration, per tree (the kernels in selfplay_kernels.cuh call these; the host simulator runs them in sequence) ----
+
+// Root of a tree (mcts.rs:160-175): [determinize →] McNode::new_root_node.  Returns the tree's status (0 = searching).
+DK_HD uint32_t uct_phase_root(const UctPool& P, uint64_t t, const dk_state& root_state, bool determinize, const RngKey& det_key) {
+    alignas(16) dk_state s = root_state;
+    uint32_t status = 0;
+    if (determinize && st_phase(s) != DK_PHASE_FINISHED) {
+        MatchPrep prep;
+        fdo_match_prepare(s, prep);
+        uint64_t h[4];
+        uint8_t res[4];
+        status = fdo_match_sample(prep, det_key, h, res);
+        if (status == 0u) fdo_state_with_hands_and_reservations(s, h, res);
     }
-    sync();
+    P.status[t] = status;
+    P.n_nodes[t] = 1u;
+    P.explore[t] = 0u; P.result[t] = 0u; P.path_len[t] = 0u;
+    P.ctl[t] = status == 0u ? UCT_CTL_ACTIVE : 0u;
+    if (status == 0u) {
+        P.head(t, 0u).info = uct_node_info<true>(s, 63u, true);
+        P.state(t, 0u) = s;
+    }
+    return status;
+}
+
+// backpropagate (mcts.rs:138-158): every node on the path from `explore` to the root gains one visit and
+// result[parent.current_player] — kept in the parent's slot of that node; the parents that keep statistics are the anchors the walk
+// down recorded.  Independent read-modify-writes, four in flight.
+DK_HD void uct_phase_backprop(const UctPool& P, uint64_t t) {
+    const uint32_t packed = P.result[t], len = P.path_len[t];
+#pragma unroll 4
+    for (uint32_t l = 0; l < len; ++l) {
+        const uint32_t e = P.path_at(t, l);
+        UctStat& st = P.head(t, e & UCT_NODE_MASK).stat[(e >> 24) & 15u];
+        UctStat v = st;
+        v.vis += 1u;
+        v.win += uct_unpack_point(packed, e >> 28);
+        st = v;
+    }
+}
+
+// One level of select_promising_node at a node with n_actions actions (nch of them expanded): the slot chosen by
+// find_best_child.  ONE code path for every node width — the lanes of a warp sit at nodes of different widths, and separate paths
+// per width ran one after the other (5.6 of 32 lanes, profiles/r02_uct_select_v2_ncu_summary.json); only the LOADS depend on the
+// width: the statistics sectors of children 4-7 / 8-11 are fetched for nodes that can have such children.
+DK_HD uint32_t uct_select_level(const UctHead& h, uint32_t n_actions, uint32_t nch, bool is_root, uint32_t root_visits, double c, const UctTables& T) {
+    uint32_t vis[UCT_MAX_CHILDREN];
+    int32_t win[UCT_MAX_CHILDREN];
+    uint32_t total = 1u;                                  // the node's own visits: the iteration that created it + those through its children
+#pragma unroll
+    for (uint32_t k = 0; k < UCT_MAX_CHILDREN; ++k) {
+        const bool need = k < 4u || (k < 8u ? n_actions > 4u : n_actions > 8u);
+        UctStat st; st.vis = 0u; st.win = 0;
+        if (need) st = h.stat[k];
+        vis[k] = st.vis; win[k] = st.win;
+        total += k < nch ? st.vis : 0u;
+    }
+    const uint32_t n = is_root ? root_visits : total;
+    return uct_best_slot<UCT_MAX_CHILDREN>(nch, vis, win, n, c, T.ln[n], T);
+}
+
+// select_promising_node (mcts.rs:45-63) + expand_single (mcts.rs:65-104) of one iteration.
+// Selection: down from the root while the node has children and nothing left to expand; root_visits = number of iterations
+// backpropagated so far (every iteration adds one visit to the root).  Expansion at the node reached: a random unexpanded action
+// (SITE_EXPAND word 0 of the iteration's stream), by_action on the node's record, the child appended.  Leaves `explore`, the path of
+// anchors and the ctl flags (rollout needed, or the result is the terminal record's points) for the rollout / backpropagation phase.
+template <bool IDX>
+DK_HD void uct_phase_tree(const UctPool& P, uint64_t t, uint32_t root_visits, double c, const UctTables& T, const RngKey& key) {
+    uint32_t node = 0u, len = 0u;
+    uint32_t n_actions = uct_n_actions(P.head(t, 0u).info);
+    uint64_t info;
+    for (;;) {
+        const UctHead& h = P.head(t, node);
+        info = h.info;
+        const uint32_t nch = uct_n_children(info);
+        if (nch == 0u || (info & UCT_ACTION_MASK) != 0ull) break;
+        // (a node with children and nothing to expand is an anchor: entries never point at an expanded single-action node; a
+        // single-action ROOT takes slot 0 whatever the numbers are)
+        const uint32_t slot = n_actions <= 1u ? 0u : uct_select_level(h, n_actions, nch, node == 0u, root_visits, c, T);
+        if (len >= UCT_MAX_PATH) { P.status[t] = 3u; P.ctl[t] = 0u; return; }
+        P.path_at(t, len++) = uct_path_entry(node, slot, uct_cur(info));
+        const uint32_t entry = h.child[slot];
+        node = entry & UCT_NODE_MASK;
+        n_actions = entry >> 28;
+    }
+    const uint64_t unexpanded = info & UCT_ACTION_MASK;
     uint32_t explore = node;
-    alignas(16) dk_state s;
-    if (active) {
-        const uint64_t unexpanded = pool[node].info & UCT_ACTION_MASK;
-        s = pool[node].state;
-        if (unexpanded != 0ull) {                                                // expand_single (:65-104)
-            const uint32_t nch = uct_n_children(pool[node]);
-            if (nch >= UCT_MAX_CHILDREN) err = 1u;
-            else {
-                U4 blk = rng_block(key, SITE_EXPAND, 0);
-                const uint32_t a = pick_msb_rank64(unexpanded, mulhi(blk.x, popcll(unexpanded)));
-                fdo_state_apply<true>(s, a);                                     // by_action (record in local memory)
-                explore = n_nodes++;
-                uct_init_node(pool[explore], s, node, a, false);
-                pool[node].child[nch] = explore;
-                pool[node].info = (pool[node].info & ~(1ull << a) & ~(15ull << 56)) | ((uint64_t)(nch + 1u) << 56);
-            }
+    alignas(16) dk_state s = P.state(t, node);
+    if (unexpanded != 0ull) {
+        const uint32_t nch = uct_n_children(info);
+        if (nch >= UCT_MAX_CHILDREN || len >= UCT_MAX_PATH) { P.status[t] = 3u; P.ctl[t] = 0u; return; }     // cannot happen for states reachable by the rules
+        const U4 blk = rng_block(key, SITE_EXPAND, 0);
+        const uint32_t a = pick_msb_rank64(unexpanded, mulhi(blk.x, popcll(unexpanded)));
+        fdo_state_apply<IDX>(s, a);                                                  // by_action
+        explore = P.n_nodes[t];
+        P.n_nodes[t] = explore + 1u;
+        const uint64_t child_info = uct_node_info<IDX>(s, a, false);
+        P.head(t, explore).info = child_info;
+        P.state(t, explore) = s;
+        const uint32_t entry = explore | (uct_n_actions(child_info) << 28);
+        if (n_actions > 1u || node == 0u) {                                          // the node is an anchor: the child gets its slot
+            UctHead& h = P.head(t, node);
+            UctStat zero; zero.vis = 0u; zero.win = 0;
+            h.stat[nch] = zero; h.child[nch] = entry;
+            h.info = (info & ~(1ull << a) & ~(15ull << 56)) | ((uint64_t)(nch + 1u) << 56);
+            P.path_at(t, len++) = uct_path_entry(node, nch, uct_cur(info));
+            if (node == 0u) P.root_action[t * 16u + nch] = (uint8_t)a;
+        } else {                                                                      // the end of a single-action chain: the chain grows, the
+            const uint32_t owner = P.path_at(t, len - 1u);                            // anchor's entry moves to its new end
+            P.head(t, owner & UCT_NODE_MASK).child[(owner >> 24) & 15u] = entry;
         }
     }
-    sync();
-    int32_t p[4] = {0, 0, 0, 0};                                                 // random_rollout (env_state_full_doko.rs:198-220) from `s`
-    if (active && !err) {
-        FdoLive g; FdoResume rs;
-        if (fdo_state_to_live<true>(s, g, rs)) { fdo_play_to_end<false, false>(g, key, &rs, lut); fdo_final_points(g, p); }
-        else { p[0] = s.points[0]; p[1] = s.points[1]; p[2] = s.points[2]; p[3] = s.points[3]; }
+    P.explore[t] = explore;
+    P.path_len[t] = len;
+    if (st_phase(s) == DK_PHASE_FINISHED) {                                          // nothing to roll out: the rewards are the record's points
+        const int32_t p[4] = {s.points[0], s.points[1], s.points[2], s.points[3]};
+        P.result[t] = uct_pack_points(p);
+        P.ctl[t] = UCT_CTL_ACTIVE;
+    } else {
+        P.ctl[t] = UCT_CTL_ACTIVE | UCT_CTL_ROLLOUT;
     }
-    sync();
-    if (active && !err) {
-        uint32_t temp = explore;                                                 // backpropagate (:138-158)
-        for (;;) {
-            const uint32_t parent = pool[temp].parent;
-            pool[temp].visits += 1u;
-            if (parent == UCT_NONE) break;
-            const uint32_t cp = uct_cur(pool[parent]);
-            pool[temp].win += (long long)((cp & 2u) ? ((cp & 1u) ? p[3] : p[2]) : ((cp & 1u) ? p[1] : p[0]));
-            temp = parent;
-        }
-    }
-    return err;
+}
+
+// random_rollout (env_state_full_doko.rs:198-220) from the node chosen by the expansion; SEL12 = the caller's table holds the 12-bit rank select.
+template <bool SEL12>
+DK_HD void uct_phase_rollout(const UctPool& P, uint64_t t, const RngKey& key, const uint32_t* __restrict__ lut) {
+    alignas(16) dk_state s = P.state(t, P.explore[t]);
+    int32_t p[4] = {0, 0, 0, 0};
+    FdoLive g; FdoResume rs;
+    if (fdo_state_to_live(s, g, rs)) { fdo_play_to_end<false, false, SEL12>(g, key, &rs, lut); fdo_final_points(g, p); }
+    else { p[0] = s.points[0]; p[1] = s.points[1]; p[2] = s.points[2]; p[3] = s.points[3]; }
+    P.result[t] = uct_pack_points(p);
 }
 
 // Moves of the root (mcts.rs:220-229) as mcts_policy.rs:96-118 consumes them: visits / values by action index and the move with
 // the most visits (max_by_key keeps the LAST maximum in child order); returns ACTION 0xFF when the root has no child.
 template <class VisitT>
-DK_HD uint32_t uct_moves(const UctNode* __restrict__ pool, VisitT* __restrict__ visits, float* __restrict__ values) {
-    const UctNode& root = pool[0];
+DK_HD uint32_t uct_moves(const UctPool& P, uint64_t t, VisitT* __restrict__ visits, float* __restrict__ values) {
+    const UctHead& root = P.head(t, 0u);
     uint32_t best = 0xFFu, best_visits = 0;
-    for (uint32_t k = 0; k < uct_n_children(root); ++k) {
-        const UctNode& ch = pool[root.child[k]];
-        const uint32_t a = uct_last_action(ch);
-        if (visits) visits[a] = (VisitT)ch.visits;
-        if (values) values[a] = (float)dk_ddiv((double)ch.win, (double)ch.visits);
-        if (best == 0xFFu || ch.visits >= best_visits) { best = a; best_visits = ch.visits; }
+    const uint32_t nch = uct_n_children(root.info);
+    for (uint32_t k = 0; k < nch; ++k) {
+        const uint32_t a = P.root_action[t * 16u + k], v = root.stat[k].vis;
+        if (visits) visits[a] = (VisitT)v;
+        if (values) values[a] = (float)dk_ddiv((double)root.stat[k].win, (double)v);
+        if (best == 0xFFu || v >= best_visits) { best = a; best_visits = v; }
     }
     return best;
 }

@@ -240,14 +240,26 @@ SIM_API uint32_t sim_fdo_uct_search(const dk_state* root, uint64_t seed, uint64_
     }
     std::vector<double> ln_table(iterations + 1, 0.0);
     for (uint32_t n = 1; n <= iterations; ++n) ln_table[n] = std::log((double)n);
-    std::vector<dk::UctNode> pool(iterations + 1);
-    dk::uct_init_node(pool[0], s, dk::UCT_NONE, 63u, true);
-    uint32_t n_nodes = 1;
+    // the kernels' phases, run in sequence for ONE tree (n_trees = 1) on a host workspace carved like the device one
+    std::vector<char> ws((size_t)dk::uct_workspace_bytes(1, iterations));
+    const dk::UctPool P = dk::uct_carve(ws.data(), 1, iterations);
+    dk::RngKey det_key = key; det_key.unit_hi = sub;
+    // (the determinization above already replaced `s`; uct_phase_root is handed the result and told not to determinize again)
+    if (dk::uct_phase_root(P, 0, s, false, det_key)) return P.status[0];
+    const size_t vlen = iterations + 1;
+    std::vector<dk::UctF2> vis_tab(vlen);
+    vis_tab[0].x = vis_tab[0].y = 1.0f;
+    for (size_t v = 1; v < vlen; ++v) { vis_tab[v].x = (float)(1.0 / (double)v); vis_tab[v].y = (float)(1.0 / std::sqrt((double)v)); }
+    dk::UctTables T; T.ln = ln_table.data(); T.vis_tab = vis_tab.data();
     for (uint32_t it = 0; it < iterations; ++it) {
+        if (!(P.ctl[0] & dk::UCT_CTL_ACTIVE)) return P.status[0];
         key.unit_hi = sub * iterations + it;
-        if (dk::uct_iteration(pool.data(), n_nodes, key, (double)uct_c, ln_table.data(), card_lut())) return 3;
+        dk::uct_phase_tree<false>(P, 0, it, (double)uct_c, T, key);                            // uct_tree_kernel
+        if (!(P.ctl[0] & dk::UCT_CTL_ACTIVE)) return P.status[0];
+        if (P.ctl[0] & dk::UCT_CTL_ROLLOUT) dk::uct_phase_rollout<false>(P, 0, key, card_lut());   // uct_rollout_kernel
+        dk::uct_phase_backprop(P, 0);
     }
-    uint32_t best = dk::uct_moves(pool.data(), visits, values);
+    uint32_t best = dk::uct_moves(P, 0, visits, values);
     *action_out = best == 0xFFu ? -1 : (int32_t)best;
     return 0;
 }
@@ -257,14 +269,19 @@ SIM_API uint32_t sim_fdo_min_cards_to_call(uint32_t m, uint32_t e, uint32_t w) {
     return a == b ? a : 0xFFFFFFFFu;     // closed form and table form must agree
 }
 
-// find_best_child on a synthetic family: child index chosen with the f32 filter (low byte) and by the all-f64 evaluation (next byte)
+// find_best_child on a synthetic family: child slot chosen with the f32 filter (low byte) and by the all-f64 evaluation (next byte)
 SIM_API uint32_t sim_uct_select_check(uint32_t nch, const uint32_t* vis, const long long* win, uint32_t parent_visits, float uct_c) {
-    std::vector<dk::UctNode> pool(nch + 1);
-    std::memset(pool.data(), 0, pool.size() * sizeof(dk::UctNode));
-    pool[0].visits = parent_visits; pool[0].parent = dk::UCT_NONE; pool[0].info = (uint64_t)nch << 56;
-    for (uint32_t k = 0; k < nch; ++k) { pool[0].child[k] = k + 1; pool[k + 1].visits = vis[k]; pool[k + 1].win = win[k]; pool[k + 1].parent = 0; }
+    uint32_t v[dk::UCT_MAX_CHILDREN] = {0};
+    int32_t w[dk::UCT_MAX_CHILDREN] = {0};
+    for (uint32_t k = 0; k < nch; ++k) { v[k] = vis[k]; w[k] = (int32_t)win[k]; }
     const double ln_n = std::log((double)parent_visits);
-    uint32_t a = dk::uct_find_best_child(pool.data(), 0, (double)uct_c, ln_n, true);
-    uint32_t b = dk::uct_find_best_child(pool.data(), 0, (double)uct_c, ln_n, false);
+    // the filter's (1 / v, 1 / sqrt(v)) table, as dk_uct_search builds it
+    static std::vector<dk::UctF2> vis_tab;
+    const size_t TAB = ((size_t)1 << 22) + 4;      // covers every visit count the test family uses
+    if (vis_tab.empty()) { vis_tab.resize(TAB); vis_tab[0].x = vis_tab[0].y = 1.0f; for (size_t i = 1; i < TAB; ++i) { vis_tab[i].x = (float)(1.0 / (double)i); vis_tab[i].y = (float)(1.0 / std::sqrt((double)i)); } }
+    for (uint32_t k = 0; k < nch; ++k) if (vis[k] >= TAB) return 0xFFFFFFFFu;
+    dk::UctTables T; T.ln = nullptr; T.vis_tab = vis_tab.data();
+    uint32_t a = dk::uct_best_slot(nch, v, w, parent_visits, (double)uct_c, ln_n, T, true) + 1u;
+    uint32_t b = dk::uct_best_slot(nch, v, w, parent_visits, (double)uct_c, ln_n, T, false) + 1u;
     return (a & 255u) | ((b & 255u) << 8);
 }
