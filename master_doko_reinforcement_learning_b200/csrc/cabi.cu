@@ -347,8 +347,9 @@ dk_status dk_apply(dk_ctx* ctx, int engine, size_t n, dk_state* states, const ui
     unsigned grid = (unsigned)((n + dk::STATE_THREADS - 1) / dk::STATE_THREADS);
     CUtensorMap tmap;
     if (state_tensor_map(ctx, states, n, &tmap)) {
-        if (engine == DK_FDO) dk::apply_tma_kernel<DK_FDO><<<grid, dk::STATE_THREADS, 0, pick_stream(ctx, stream)>>>(tmap, (uint64_t)n, action_idx, flags, err_out);
-        else dk::apply_tma_kernel<DK_DOKO><<<grid, dk::STATE_THREADS, 0, pick_stream(ctx, stream)>>>(tmap, (uint64_t)n, action_idx, flags, err_out);
+        const unsigned tgrid = (unsigned)((n + dk::STATE_THREADS * DK_APPLY_TILES - 1) / (dk::STATE_THREADS * DK_APPLY_TILES));
+        if (engine == DK_FDO) dk::apply_tma_kernel<DK_FDO><<<tgrid, dk::STATE_THREADS, 0, pick_stream(ctx, stream)>>>(tmap, (uint64_t)n, action_idx, flags, err_out);
+        else dk::apply_tma_kernel<DK_DOKO><<<tgrid, dk::STATE_THREADS, 0, pick_stream(ctx, stream)>>>(tmap, (uint64_t)n, action_idx, flags, err_out);
         return check_launch(ctx, "apply_tma_kernel");
     }
     if (engine == DK_FDO) dk::apply_kernel<DK_FDO><<<grid, dk::STATE_THREADS, 0, pick_stream(ctx, stream)>>>((uint64_t)n, states, action_idx, flags, err_out);

@@ -360,55 +360,85 @@ struct TmaTile {
 #ifndef DK_APPLY_SORT
 #define DK_APPLY_SORT 1
 #endif
+// Tiles per block.  With the instruction count halved the kernel waited for memory (long_scoreboard + barrier stalls,
+// profiles/r02_apply_v2_ncu_summary.json).  What removed the wait was taking the action bytes into shared memory while the tile is in
+// flight (after the sort the action of ANOTHER row is needed: a dependent global load on the critical path before): 0.874 -> 0.974 of
+// the HBM copy peak.  Two tiles in flight per block (DK_APPLY_TILES=2: 33 KB of shared memory, 6 blocks per SM) measured SLOWER, 0.865.
+#ifndef DK_APPLY_TILES
+#define DK_APPLY_TILES 1
+#endif
 template <int ENGINE>
 __global__ void __launch_bounds__(STATE_THREADS, DK_APPLY_BLOCKS)
 apply_tma_kernel(const __grid_constant__ CUtensorMap tmap, uint64_t n, const uint8_t* __restrict__ action, uint32_t flags, uint8_t* __restrict__ err_out) {
-    __shared__ __align__(1024) uint4 stage[STATE_THREADS * 8];
-    __shared__ __align__(8) unsigned long long bar;
-    __shared__ uint32_t cls_count[STATE_THREADS / 32][8];
+    __shared__ __align__(1024) uint4 stage_all[DK_APPLY_TILES][STATE_THREADS * 8];
+    __shared__ __align__(8) unsigned long long bar[DK_APPLY_TILES];
+    __shared__ uint32_t cls_count[32];
     __shared__ uint8_t perm[STATE_THREADS];
-    const uint64_t first = (uint64_t)blockIdx.x * STATE_THREADS;
-    if (threadIdx.x == 0) TmaTile::init(&bar);
-    __syncthreads();
-    if (threadIdx.x == 0) TmaTile::load(&tmap, stage, &bar, first, (uint32_t)min((uint64_t)STATE_THREADS, n) * 128u);
-    TmaTile::wait(&bar, 0u);
-    uint32_t row = threadIdx.x;
-    if (DK_APPLY_SORT) {
-        // class of the own row from its last chunk (bytes 112..127: eyes, trick counts, card_index, n_reservations, points, meta)
-        const uint32_t t = threadIdx.x, lane = t & 31u, warp = t >> 5;
-        const uint4 last = stage[t * 8u + (7u ^ (t & 7u))];
-        const uint32_t phase = last.w & 3u, ci = (last.y >> 16) & 255u;
-        uint32_t cls = phase == DK_PHASE_RESERVATION ? 0u : (phase == DK_PHASE_ANNOUNCEMENT ? 1u : (phase == DK_PHASE_PLAY_CARD ? ((ci & 3u) == 3u ? (ci == 47u ? 4u : 3u) : 2u) : 5u));
-        if (first + t >= n) cls = 6u;
-        uint32_t before = 0, mine = 0;
+    __shared__ uint8_t act_s[DK_APPLY_TILES][STATE_THREADS];
+    const uint64_t first0 = (uint64_t)blockIdx.x * (STATE_THREADS * DK_APPLY_TILES);
+    if (threadIdx.x == 0) {
 #pragma unroll
-        for (uint32_t c = 0; c < 7u; ++c) {
-            const uint32_t b = __ballot_sync(0xFFFFFFFFu, cls == c);
-            if (lane == 0) cls_count[warp][c] = (uint32_t)__popc(b);
-            if (cls == c) mine = (uint32_t)__popc(b & ((1u << lane) - 1u));
+        for (int b = 0; b < DK_APPLY_TILES; ++b) TmaTile::init(&bar[b]);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int b = 0; b < DK_APPLY_TILES; ++b) {
+        const uint64_t first = first0 + (uint64_t)b * STATE_THREADS;
+        if (first >= n) break;
+        if (threadIdx.x == 0) TmaTile::load(&tmap, stage_all[b], &bar[b], first, (uint32_t)min((uint64_t)STATE_THREADS, n) * 128u);
+        act_s[b][threadIdx.x] = first + threadIdx.x < n ? action[first + threadIdx.x] : (uint8_t)0;   // (in flight with the tile; read after the sort's barriers)
+    }
+#pragma unroll
+    for (int b = 0; b < DK_APPLY_TILES; ++b) {
+        const uint64_t first = first0 + (uint64_t)b * STATE_THREADS;
+        if (first >= n) break;                                           // uniform
+        uint4* stage = stage_all[b];
+        TmaTile::wait(&bar[b], 0u);
+        uint32_t row = threadIdx.x;
+        if (DK_APPLY_SORT) {
+            // class of the own row from its last chunk (bytes 112..127: eyes, trick counts, card_index, n_reservations, points, meta)
+            const uint32_t t = threadIdx.x, lane = t & 31u, warp = t >> 5;
+            const uint4 last = stage[t * 8u + (7u ^ (t & 7u))];
+            const uint32_t phase = last.w & 3u, ci = (last.y >> 16) & 255u;
+            uint32_t cls = phase == DK_PHASE_RESERVATION ? 0u : (phase == DK_PHASE_ANNOUNCEMENT ? 1u : (phase == DK_PHASE_PLAY_CARD ? ((ci & 3u) == 3u ? (ci == 47u ? 4u : 3u) : 2u) : 5u));
+            if (first + t >= n) cls = 6u;
+            constexpr uint32_t NW = STATE_THREADS / 32;                      // 7 classes x 4 warps = 28 counters: one warp-wide scan
+            static_assert(7u * NW <= 32u, "class counters must fit one warp");
+            uint32_t mine = 0;
+#pragma unroll
+            for (uint32_t c = 0; c < 7u; ++c) {
+                const uint32_t bl = __ballot_sync(0xFFFFFFFFu, cls == c);
+                if (lane == 0) cls_count[c * NW + warp] = (uint32_t)__popc(bl);
+                if (cls == c) mine = (uint32_t)__popc(bl & ((1u << lane) - 1u));
+            }
+            __syncthreads();
+            // exclusive prefix over (class, warp) in class-major order, computed by every warp for itself (no second barrier)
+            const uint32_t v = lane < 7u * NW ? cls_count[lane] : 0u;
+            uint32_t incl = v;
+#pragma unroll
+            for (uint32_t d = 1; d < 32u; d <<= 1) { const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += up; }
+            const uint32_t before = __shfl_sync(0xFFFFFFFFu, incl - v, cls * NW + warp);
+            perm[before + mine] = (uint8_t)t;
+            __syncthreads();
+            row = perm[t];
+        } else __syncthreads();                                          // act_s is read across threads either way
+        const uint64_t i = first + row;
+        if (i < n) {
+            const uint32_t a = act_s[b][row];
+            alignas(16) dk_state s;
+            StateStage<STATE_THREADS>::get_row(stage, row, s);
+            uint32_t err = ENGINE == DK_FDO ? fdo_state_apply_az<DK_APPLY_IDX>(s, a, (flags & DK_APPLY_SKIP_SINGLE) != 0) : doko_state_apply(s, a);
+            if (!err) StateStage<STATE_THREADS>::put_row(stage, row, s);     // an illegal action leaves the record as it was
+            if (err_out) err_out[i] = (uint8_t)err;
         }
-        __syncthreads();
-#pragma unroll
-        for (uint32_t c = 0; c < 7u; ++c)
-#pragma unroll
-            for (uint32_t w = 0; w < (uint32_t)(STATE_THREADS / 32); ++w)
-                before += (c < cls || (c == cls && w < warp)) ? cls_count[w][c] : 0u;
-        perm[before + mine] = (uint8_t)t;
-        __syncthreads();
-        row = perm[t];
+        TmaTile::publish();
+        __syncthreads();                                                 // (also: perm / cls_count are free for the next tile)
+        if (threadIdx.x == 0) {
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(&tmap), "r"(0), "r"((int)first), "r"(TmaTile::saddr(stage)) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
     }
-    const uint64_t i = first + row;
-    if (i < n) {
-        const uint32_t a = action[i];
-        alignas(16) dk_state s;
-        StateStage<STATE_THREADS>::get_row(stage, row, s);
-        uint32_t err = ENGINE == DK_FDO ? fdo_state_apply_az<DK_APPLY_IDX>(s, a, (flags & DK_APPLY_SKIP_SINGLE) != 0) : doko_state_apply(s, a);
-        if (!err) StateStage<STATE_THREADS>::put_row(stage, row, s);     // an illegal action leaves the record as it was
-        if (err_out) err_out[i] = (uint8_t)err;
-    }
-    TmaTile::publish();
-    __syncthreads();
-    if (threadIdx.x == 0) TmaTile::store(&tmap, stage, first);
+    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the block's shared memory must outlive the engine's reads
 }
 // dk_new_games with the records leaving as two TMA tile stores per block (the per-thread form writes every record with eight 16-byte
 // stores at a 128-byte stride: 256 sector accesses per warp).

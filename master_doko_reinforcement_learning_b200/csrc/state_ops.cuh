@@ -174,19 +174,36 @@ DK_HD uint64_t fdo_state_legal_mask(const dk_state& s) {
     return 0;
 }
 // internal_progress (announcement.rs:130-175) from seat p; sets phase / current seat / turns.
+// The reference asks the seats one after the other (seats with an empty allowed set are skipped and count as a "no") until one may
+// call or four consecutive no's end the round.  Here the four seats are decided at once: a seat may call iff its hand holds at least
+// the threshold of its team (fdo_min_cards_to_call is exactly "fdo_allowed_call != 0"), one byte per seat as in the playout kernels
+// (fdo_eligible_nibble); the first eligible seat among the next 4 - turns is found with one bit scan.  Straight-line code instead of
+// up to four rounds of run-time-indexed hand reads — the loop was the largest single item of the transition's instruction count
+// (profiles/r02_apply_sorted_ncu_summary.json).
 template <bool IDX = false>
 DK_HD void fdo_state_progress(dk_state& s, uint32_t p) {
     uint32_t turns = st_turns(s);
-    for (;;) {
-        if (turns == 4u) {                                          // RoundIsOver(starting_player)
-            st_set(s.meta, 0, 2, DK_PHASE_PLAY_CARD);
-            st_set(s.meta, 2, 2, st_ann_start(s));
-            break;
-        }
-        if (fdo_state_allowed_call<IDX>(s, p) == 0u) { turns++; p = (p + 1u) & 3u; continue; }
+    const uint32_t tag = st_team_tag(s);
+    uint32_t elig = 0;
+    if (tag == TEAM_WEDDING_SOLVED || tag == TEAM_NO_WEDDING) {
+        const uint32_t w = tag == TEAM_WEDDING_SOLVED ? st_solved_idx(s) : 0u, re = st_re_mask(s), rl = st_re_low(s), kl = st_ko_low(s);
+        const uint32_t thr_re = fdo_min_cards_to_call(rl, kl, w), thr_ko = fdo_min_cards_to_call(kl, rl, w);
+        const uint32_t re_spread = fdo_spread4(re);
+        const uint32_t thr4 = thr_re * re_spread + thr_ko * (0x01010101u - re_spread);
+        const uint32_t cards4h = 0x80808080u + (popcll(s.hands[0]) | (popcll(s.hands[1]) << 8) | (popcll(s.hands[2]) << 16) | (popcll(s.hands[3]) << 24));
+        elig = fdo_eligible_nibble(cards4h, thr4);
+    }
+    const uint32_t left = 4u - (turns < 4u ? turns : 4u);                 // seats still to ask before the round is over
+    const uint32_t win = ((elig * 0x11u) >> p) & ((1u << left) - 1u);     // bit d: seat p + d may call and is reached
+    if (win == 0u) {                                                      // RoundIsOver(starting_player)
+        turns = 4u;
+        st_set(s.meta, 0, 2, DK_PHASE_PLAY_CARD);
+        st_set(s.meta, 2, 2, st_ann_start(s));
+    } else {
+        const uint32_t d = ffs0(win);
+        turns += d;
         st_set(s.meta, 0, 2, DK_PHASE_ANNOUNCEMENT);
-        st_set(s.meta, 2, 2, p);
-        break;
+        st_set(s.meta, 2, 2, (p + d) & 3u);
     }
     st_set(s.meta, 26, 3, turns);
 }
