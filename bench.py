@@ -465,6 +465,27 @@ def run_cuda(args):
                            "stale": c.get("stale") if c else "no counters", "counters_source": c.get("source") if c else None,
                            "hbm": {"achieved": 37 * per_s / world / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": 37 * per_s / world / 1e9 / hbm_peak,
                                    "algorithmic_bytes_per_sample": 37}}
+        # the same configuration for the simplified engine: rs-doko-assignment's sample_assignment (rs-doko-assignment/src/assignment.rs:493-581)
+        sd = dk.new_games(pkg.DK_DOKO, n_info, dk.rng(SEED, rank * n_info, 3))
+        raw = sd.view(torch.uint8).reshape(n_info, 128)
+        target = (8 * (1 + (torch.arange(n_info, device=dev) & 3))).to(torch.uint8)
+        for it in range(60):                                      # 4 reservations, then cards up to the target index, with random legal actions
+            active = ((raw[:, 118] < target) & ((raw[:, 124] & 3) != 3)).nonzero().squeeze(1)
+            if active.numel() == 0:
+                break
+            sub = sd[active].contiguous()
+            act = dk.random_action(pkg.DK_DOKO, sub, dk.rng(SEED, rank * n_info, 300 + it))
+            dk.apply(pkg.DK_DOKO, sub, act)
+            sd[active] = sub
+
+        def one_pass_doko(epoch):
+            dk._check(dk.L.dk_determinize(dk.ctx, pkg.DK_DOKO, n_info, samples, pkg.api._ptr(sd), ctypes.byref(dk.rng(SEED, rank * n_info, epoch)),
+                                          pkg.api._ptr(hands), pkg.api._ptr(res), pkg.api._ptr(status), dk._stream()), "dk_determinize")
+
+        ms_d = timed_iters(one_pass_doko, passes, 3, flush=False)
+        out["rs_doko_assignment"] = {"value": world * passes * n_info * samples / (ms_d / 1e3), "unit": "determinizations/s", "ms_per_pass": ms_d / passes,
+                                     "dead_ends_last_pass": sum_over_ranks(int((status != 0).sum())),
+                                     "config": {"workload": "rs-doko-assignment sample_assignment, 65536 mid-game info-states per B200 x 4096 samples (BASELINE configs[2], simplified engine)"}}
         del hands, res, status
         return out
 
@@ -593,6 +614,7 @@ def run_cuda(args):
             line["cpu_baseline"] = cpu_baseline(0)
             config0["cpu_baseline"] = cpu_baseline_config0(0)
             determinizations["cpu_baseline"] = cpu_baseline_kind(3, 4096, 4096, 0, "determinizations/s", "card_matching samples (4096 info-states x 4096)")
+            determinizations["rs_doko_assignment"]["cpu_baseline"] = cpu_baseline_kind(30, 2048, 512, 0, "determinizations/s", "sample_assignment samples (2048 info-states x 512)")
             config3["cpu_baseline"] = cpu_baseline_kind(4, 1024, 1024, 0, "rollouts/s", "determinized leaf rollouts (1024 leaves x 1024)")
             config4["cpu_baseline"] = cpu_baseline_kind(5, 1 << 18, 16, 0, "step-encodes/s", "lock-step env steps + encode_state_pi")
         line["config0_rs_doko_playouts"] = config0

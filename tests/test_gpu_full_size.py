@@ -117,3 +117,38 @@ def test_config4_leaf_rollouts_8192_x_1024(dk, orc):
         st, pts, _ = o.leaf_rollout(SEED, 0, r, 9, True)
         exp += np.array(pts) if st == 0 else 0
     assert np.array_equal(sums[0].cpu().numpy(), exp)
+
+
+def test_config3_sample_assignment_64k_x_4096(dk, orc):
+    """BASELINE configs[2] for the simplified engine (rs-doko-assignment): 65 536 mid-game info-states x 4096 samples = 2.7e8
+    sample_assignment draws.  Every sample keeps the hand sizes and the card multiset, the observer keeps its hand, no dead ends,
+    splitting the sample axis changes nothing; 64 info-states x 64 samples spread over the batch are compared with the oracle."""
+    import torch
+
+    from oracle_lib import Bulk
+
+    n, S = 1 << 16, 4096
+    b = Bulk(orc, 0, n, SEED, first_id=0, epoch=0, mode=0)
+    states = torch.from_numpy(b.bytes()).cuda()
+    hands, _, status = dk.determinize(0, states, S, dk.rng(SEED, 0, 6))
+    torch.cuda.synchronize()
+    assert int(status.max()) == 0
+    real = states[:, :32].contiguous().view(torch.int64).view(n, 4)
+    meta = states[:, 124:128].contiguous().view(torch.int32).view(n)
+    obs_seat = ((meta >> 2) & 3).long()
+    assert torch.equal(popcount64(hands), popcount64(real)[:, None, :].expand(n, S, 4))
+    # the multiset: per card type the number of copies over the four hands (copy A bits 0-23, copy B bits 24-47)
+    cnt = lambda h: ((h & 0xFFFFFF).unsqueeze(-1) >> torch.arange(24, device="cuda") & 1).sum(-2) + ((h >> 24 & 0xFFFFFF).unsqueeze(-1) >> torch.arange(24, device="cuda") & 1).sum(-2)
+    sub = torch.arange(0, n, 257, device="cuda")
+    assert torch.equal(cnt(hands[sub][:, ::64]), cnt(real[sub])[:, None, :].expand(len(sub), S // 64, 24))
+    own = torch.gather(hands, 2, obs_seat[:, None, None].expand(n, S, 1))[..., 0]
+    assert torch.equal(own, torch.gather(real, 1, obs_seat[:, None])[:, 0][:, None].expand(n, S))
+    del own
+    h_a, _, _ = dk.determinize(0, states[:1024], S // 2, dk.rng(SEED, 0, 6, first_sub=0))
+    h_b, _, _ = dk.determinize(0, states[:1024], S // 2, dk.rng(SEED, 0, 6, first_sub=S // 2))
+    assert torch.equal(torch.cat([h_a, h_b], 1), hands[:1024])
+    pick = np.arange(0, n, n // 64)[:64]
+    small = Bulk(orc, 0, n, SEED, first_id=0, epoch=0, mode=0)         # (the recipe is deterministic: same states)
+    h_o, _, s_o, _, _ = small.determinize(64, epoch=6)
+    got = hands[torch.from_numpy(pick).cuda()][:, :64].cpu().numpy().astype(np.uint64)
+    assert np.array_equal(got, h_o[pick]) and int(s_o[pick].max()) == 0

@@ -164,3 +164,41 @@ def test_fuse_matches_oracle_on_random_rows(dk, orc):
                 assert action[i] == 0xFF
             else:
                 assert action[i] == oracle_lib.fuse(orc, strategy, ok, int(allowed[i])), (i, strategy)
+
+
+def test_pimc_decide_falls_back_to_a_random_action_without_successful_samples(dk, orc):
+    """DefaultImpiPolicy::execute (compare_impi.rs:357-368): when no determinization succeeded, a random allowed non-announcement action
+    is played.  Forced here by marking every sample of some roots as failed; the other roots keep the fused decision."""
+    import torch
+
+    from master_doko_reinforcement_learning_b200.sharding import pimc_decide
+    from oracle_lib import Bulk
+
+    b = Bulk(orc, 1, 64, SEED, first_id=300, epoch=3, mode=1)
+    states = torch.from_numpy(b.bytes()).cuda()
+    real = dk.pimc_evaluate
+
+    def failing(states_, n_det, n_rollouts, rng, want_values=True, stream=None):
+        v, val, st = real(states_, n_det, n_rollouts, rng, want_values=want_values, stream=stream)
+        st[::4] = 1                                                   # every sample of every fourth root is a dead end
+        return v, val, st
+
+    dk.pimc_evaluate = failing
+    try:
+        act, stats = pimc_decide(dk, states, 8, 0, SEED, first_id=300, epoch=5, n_rollouts=8)
+    finally:
+        dk.pimc_evaluate = real
+    torch.cuda.synchronize()
+    allowed = dk.legal_mask(1, states)
+    v, _, st = dk.pimc_evaluate(states, 8, 8, dk.rng(SEED, 300, 5), want_values=False)
+    fused = dk.fuse(0, v, allowed, st)[0].cpu().numpy()
+    fallback = dk.random_action(1, states, dk.rng(SEED, 300, 5), flags=0).cpu().numpy()
+    act = act.cpu().numpy()
+    assert (stats[::4, 78] == 0).all()                                # no successful sample counted for the forced roots
+    assert np.array_equal(act[::4], fallback[::4])
+    keep = np.ones(64, dtype=bool); keep[::4] = False
+    assert np.array_equal(act[keep], np.where(fused[keep] == 0xFF, fallback[keep], fused[keep]))
+    legal = allowed.cpu().numpy().astype(np.uint64)
+    calls = np.uint64(0x1F << 33)
+    for i in range(0, 64, 4):                                         # the fallback is an allowed non-announcement action
+        assert (int(legal[i]) & ~int(calls)) >> int(act[i]) & 1
