@@ -40,8 +40,9 @@ struct dk_ctx {
     // ln(N) table of the UCT search (host libm values, see uct.cuh)
     double* d_ln_table = nullptr;
     size_t ln_table_len = 0;
-    void* d_vis_table = nullptr;     // (1 / v, 1 / sqrt(v)) as floats for the f32 filter of the selection
-    size_t vis_table_len = 0;
+    // side streams of the UCT search (parts of a batch run phase-shifted) and the events that fork / join them
+    cudaStream_t uct_streams[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t uct_fork = nullptr, uct_join[3] = {nullptr, nullptr, nullptr};
     void* nccl_lib = nullptr;
     void* nccl_comm = nullptr;
     int nccl_ranks = 0, nccl_rank = 0;
@@ -163,10 +164,11 @@ dk_status dk_destroy(dk_ctx* ctx) {
     if (ctx->pimc_ws) cudaFree(ctx->pimc_ws);
     if (ctx->leaf_ws) cudaFree(ctx->leaf_ws);
     if (ctx->d_ln_table) cudaFree(ctx->d_ln_table);
-    if (ctx->d_vis_table) cudaFree(ctx->d_vis_table);
     for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+    for (int i = 0; i < 3; ++i) { if (ctx->uct_streams[i]) cudaStreamDestroy(ctx->uct_streams[i]); if (ctx->uct_join[i]) cudaEventDestroy(ctx->uct_join[i]); }
+    if (ctx->uct_fork) cudaEventDestroy(ctx->uct_fork);
     if (ctx->h2d_done) cudaEventDestroy(ctx->h2d_done);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -718,38 +720,56 @@ dk_status dk_uct_search(dk_ctx* ctx, size_t n_roots, size_t trees_per_root, int 
     DK_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t s = pick_stream(ctx, stream);
     if (ctx->ln_table_len < iterations + 1) {
-        // ln via the HOST libm (what Rust's f64::ln calls), so that selection is bit-identical to the CPU reference path; the f32 filter's
-        // 1 / v and 1 / sqrt(v) factors are evaluated in f64 and rounded once (uct.cuh UctTables)
+        // ln via the HOST libm (what Rust's f64::ln calls), so that selection is bit-identical to the CPU reference path
         std::vector<double> t(iterations + 1);
         t[0] = 0.0;
         for (size_t n = 1; n <= iterations; ++n) t[n] = std::log((double)n);
-        const size_t vlen = iterations + 1;
-        std::vector<dk::UctF2> vt(vlen);
-        vt[0].x = 1.0f; vt[0].y = 1.0f;
-        for (size_t v = 1; v < vlen; ++v) { vt[v].x = (float)(1.0 / (double)v); vt[v].y = (float)(1.0 / std::sqrt((double)v)); }
         DK_CUDA(ctx, cudaStreamSynchronize(s));
         if (ctx->d_ln_table) cudaFree(ctx->d_ln_table);
-        if (ctx->d_vis_table) cudaFree(ctx->d_vis_table);
-        ctx->d_ln_table = nullptr; ctx->d_vis_table = nullptr; ctx->ln_table_len = 0; ctx->vis_table_len = 0;
+        ctx->d_ln_table = nullptr; ctx->ln_table_len = 0;
         DK_CUDA(ctx, cudaMalloc(&ctx->d_ln_table, t.size() * sizeof(double)));
-        DK_CUDA(ctx, cudaMalloc(&ctx->d_vis_table, vt.size() * sizeof(dk::UctF2)));
         DK_CUDA(ctx, cudaMemcpy(ctx->d_ln_table, t.data(), t.size() * sizeof(double), cudaMemcpyHostToDevice));
-        DK_CUDA(ctx, cudaMemcpy(ctx->d_vis_table, vt.data(), vt.size() * sizeof(dk::UctF2), cudaMemcpyHostToDevice));
-        ctx->ln_table_len = t.size(); ctx->vis_table_len = vt.size();
+        ctx->ln_table_len = t.size();
     }
     const dk::UctPool P = dk::uct_carve(workspace, n_trees, iterations, getenv("DOKO_CUDA_UCT_TREE_MAJOR") != nullptr);
     const dk::RngParams rp = to_params(rng);
-    dk::UctTables T; T.ln = ctx->d_ln_table; T.vis_tab = (const dk::UctF2*)ctx->d_vis_table;
+    dk::UctTables T; T.ln = ctx->d_ln_table;
     const unsigned grid = (unsigned)((n_trees + dk::UCT_THREADS - 1) / dk::UCT_THREADS);
-    const unsigned grid_roll = (unsigned)((n_trees + dk::UCT_ROLLOUT_THREADS - 1) / dk::UCT_ROLLOUT_THREADS);
     const double c = (double)uct_exploration_constant;
     dk::uct_root_kernel<<<grid, dk::UCT_THREADS, 0, s>>>(rp, P, (uint32_t)trees_per_root, determinize, states, visits_out, values_out);
     DK_TRY(check_launch(ctx, "uct_root_kernel"));
     // One iteration of every tree = two launches (uct.cuh): all SMs run the same phase, each phase has its own register budget.
+    // Large batches are cut into parts that iterate on their own streams: trees are independent, both phases wait on memory with a
+    // third of the issue slots in use (profiles/r02_uct_*_v6_ncu_summary.json), so one part's walk fills the other's rollout and the
+    // launch gaps disappear.  DOKO_CUDA_UCT_PARTS = 1 .. 4 overrides the choice.
+    unsigned parts = n_trees >= 65536 ? 3u : 1u;
+    if (const char* e = getenv("DOKO_CUDA_UCT_PARTS")) { const int v = atoi(e); if (v >= 1 && v <= 4) parts = (unsigned)v; }
+    if ((size_t)parts * 256u > n_trees) parts = 1u;
+    for (unsigned p = 1; p < parts; ++p) {
+        if (!ctx->uct_streams[p - 1]) DK_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->uct_streams[p - 1], cudaStreamNonBlocking));
+        if (!ctx->uct_join[p - 1]) DK_CUDA(ctx, cudaEventCreateWithFlags(&ctx->uct_join[p - 1], cudaEventDisableTiming));
+    }
+    if (parts > 1u) {
+        if (!ctx->uct_fork) DK_CUDA(ctx, cudaEventCreateWithFlags(&ctx->uct_fork, cudaEventDisableTiming));
+        DK_CUDA(ctx, cudaEventRecord(ctx->uct_fork, s));
+        for (unsigned p = 1; p < parts; ++p) DK_CUDA(ctx, cudaStreamWaitEvent(ctx->uct_streams[p - 1], ctx->uct_fork, 0));
+    }
+    const size_t per_part = ((n_trees + parts - 1) / parts + 255u) & ~(size_t)255u;      // whole blocks of either kernel
     for (uint32_t it = 0; it < (uint32_t)iterations; ++it) {
-        dk::uct_tree_kernel<<<grid, dk::UCT_THREADS, 0, s>>>(rp, P, (uint32_t)trees_per_root, (uint32_t)iterations, it, c, T);
-        dk::uct_rollout_kernel<<<grid_roll, dk::UCT_ROLLOUT_THREADS, 0, s>>>(rp, P, (uint32_t)trees_per_root, (uint32_t)iterations, it);
-        ctx->launches += 2;
+        for (unsigned p = 0; p < parts; ++p) {
+            const size_t t0 = (size_t)p * per_part, t1 = t0 + per_part < n_trees ? t0 + per_part : n_trees;
+            if (t0 >= t1) continue;
+            cudaStream_t ps = p == 0 ? s : ctx->uct_streams[p - 1];
+            const unsigned g_tree = (unsigned)((t1 - t0 + dk::UCT_THREADS - 1) / dk::UCT_THREADS);
+            const unsigned g_roll = (unsigned)((t1 - t0 + dk::UCT_ROLLOUT_THREADS - 1) / dk::UCT_ROLLOUT_THREADS);
+            dk::uct_tree_kernel<<<g_tree, dk::UCT_THREADS, 0, ps>>>(rp, P, (uint32_t)trees_per_root, (uint32_t)iterations, it, c, T, t0, t1);
+            dk::uct_rollout_kernel<<<g_roll, dk::UCT_ROLLOUT_THREADS, 0, ps>>>(rp, P, (uint32_t)trees_per_root, (uint32_t)iterations, it, t0, t1);
+            ctx->launches += 2;
+        }
+    }
+    for (unsigned p = 1; p < parts; ++p) {
+        DK_CUDA(ctx, cudaEventRecord(ctx->uct_join[p - 1], ctx->uct_streams[p - 1]));
+        DK_CUDA(ctx, cudaStreamWaitEvent(s, ctx->uct_join[p - 1], 0));
     }
     dk::uct_moves_kernel<<<grid, dk::UCT_THREADS, 0, s>>>(P, visits_out, values_out, action_out, status_out);
     return check_launch(ctx, "uct kernels");

@@ -339,7 +339,8 @@ pack_replay_records_kernel(unsigned long long n_rows, const long long* __restric
     }
 }
 
-// N3: one UCT tree per thread, one kernel per phase (uct.cuh).  Tree t = root (t / trees_per_root), sub-index d = t % trees_per_root;
+// N3: one UCT tree per thread, one kernel per phase (uct.cuh); the per-iteration kernels work on a range [t_begin, t_end) of the trees, so
+// that the host can run parts of a batch on different streams (the tree phase of one part overlaps the rollouts of another).  Tree t = root (t / trees_per_root), sub-index d = t % trees_per_root;
 // with `determinize` the root state is first replaced by determinization (first_sub + d) of the info-state (the dk_determinize stream).
 // Iteration `it` runs on the Philox unit (first_id + root, (first_sub + d) * iterations + it).
 #ifndef DK_UCT_TREE_BLOCKS
@@ -372,26 +373,28 @@ uct_root_kernel(RngParams rp, UctPool P, uint32_t trees_per_root, int determiniz
 }
 // select(it) + expand(it)
 __global__ void __launch_bounds__(UCT_THREADS, DK_UCT_TREE_BLOCKS)
-uct_tree_kernel(RngParams rp, UctPool P, uint32_t trees_per_root, uint32_t iterations, uint32_t it, double c, UctTables T) {
-    const uint64_t t = (uint64_t)blockIdx.x * UCT_THREADS + threadIdx.x;
-    if (t >= P.n_trees) return;
+uct_tree_kernel(RngParams rp, UctPool P, uint32_t trees_per_root, uint32_t iterations, uint32_t it, double c, UctTables T, uint64_t t_begin, uint64_t t_end) {
+    const uint64_t t = t_begin + (uint64_t)blockIdx.x * UCT_THREADS + threadIdx.x;
+    if (t >= t_end) return;
     if (!(P.ctl[t] & UCT_CTL_ACTIVE)) return;
     uct_phase_tree<DK_UCT_EXPAND_IDX>(P, t, it, c, T, uct_iteration_key(rp, t, trees_per_root, iterations, it));
 }
 // rollout(it) + backpropagate(it)
 constexpr int UCT_ROLLOUT_THREADS = 256;
 __global__ void __launch_bounds__(UCT_ROLLOUT_THREADS, DK_UCT_ROLLOUT_BLOCKS)
-uct_rollout_kernel(RngParams rp, UctPool P, uint32_t trees_per_root, uint32_t iterations, uint32_t it) {
+uct_rollout_kernel(RngParams rp, UctPool P, uint32_t trees_per_root, uint32_t iterations, uint32_t it, uint64_t t_begin, uint64_t t_end) {
     __shared__ __align__(16) uint32_t lut[CARD_LUT_WORDS + SEL12_WORDS];
     fill_card_lut(lut);
     fill_sel12(lut);
     __syncthreads();
-    const uint64_t t = (uint64_t)blockIdx.x * UCT_ROLLOUT_THREADS + threadIdx.x;
-    if (t >= P.n_trees) return;
+    const uint64_t t = t_begin + (uint64_t)blockIdx.x * UCT_ROLLOUT_THREADS + threadIdx.x;
+    if (t >= t_end) return;
     const uint32_t ctl = P.ctl[t];
     if (!(ctl & UCT_CTL_ACTIVE)) return;
-    if (ctl & UCT_CTL_ROLLOUT) uct_phase_rollout<true>(P, t, uct_iteration_key(rp, t, trees_per_root, iterations, it), lut);
-    uct_phase_backprop(P, t);
+    uint32_t packed;
+    if (ctl & UCT_CTL_ROLLOUT) packed = uct_phase_rollout<true>(P, t, uct_iteration_key(rp, t, trees_per_root, iterations, it), lut);
+    else packed = P.result[t];                                    // a terminal record: its points, left by the tree phase
+    uct_phase_backprop(P, t, packed);
 }
 __global__ void __launch_bounds__(UCT_THREADS)
 uct_moves_kernel(UctPool P, uint32_t* __restrict__ visits_out, float* __restrict__ values_out, uint8_t* __restrict__ action_out, uint8_t* __restrict__ status_out) {

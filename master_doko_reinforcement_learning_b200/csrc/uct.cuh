@@ -11,6 +11,9 @@
 //   uct_rollout_kernel  the K2-style _no_announcement playout from the new record (lock-step card loop, full table set), then
 //                       backpropagate: the memory-bound walk up of the warps that are done overlaps the playouts still running
 // Per-tree hand-over between the launches (selected node, node to roll out from, packed result) is 4 bytes per tree and launch.
+// Measured at 131 072 trees x 256 iterations (profiles/r02_uct_history.json): 4.35e8 iterations/s (round 1) -> 8.4e8 (two kernels,
+// compact blocks, chain skipping, path buffer) -> 9.9e8 (backpropagation as 64-bit reductions, one memory round trip per level of
+// the walk, special-function f32 filter) -> 1.09e9 with the batch cut into three parts on three streams (cabi.cu: dk_uct_search).
 //
 // Data layout.  A tree owns `iterations + 1` node slots.  A node is split in two arrays:
 //   UctHead (160 B = 5 sectors)  sector 0: info | children 0-3;  sector 1: children 4-11;  sectors 2-4: (visits, exact integer
@@ -181,6 +184,25 @@ DK_HD float dk_fdiv_fast(float a, float b) {
     return a / b;
 #endif
 }
+// 1 / sqrt(v) and ln(n) for the f32 filter: one special-function instruction each on the device (MUFU.RSQ: relative error <= 2^-22;
+// MUFU.LG2 * ln 2: relative error <= 2^-21.4 for n >= 2, exactly 0 for n = 1); the host simulator uses libm — the filter's outcome
+// does not depend on which (see uct_best_slot).
+DK_HD float dk_rsqrt_fast(float v) {
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+#else
+    return 1.0f / __builtin_sqrtf(v);
+#endif
+}
+DK_HD float dk_logf_fast(float v) {
+#if defined(__CUDA_ARCH__)
+    return __logf(v);
+#else
+    return __builtin_logf(v);
+#endif
+}
 
 // Exact UCT value of one child (node.rs:238-256 with min_max_normalized_q :202-236) from exact min / max Q of its siblings.
 DK_HD double uct_value_exact(long long win, uint32_t vis, double min_q, double span, bool flat, double ln_n, double c) {
@@ -196,21 +218,21 @@ DK_HD double uct_value_exact(long long win, uint32_t vis, double min_q, double s
 // The f64 divisions and square roots of the reference are software sequences of ~30 instructions each on the GPU, so the
 // decision is taken in two stages that TOGETHER are bit-identical to evaluating every child in f64:
 //   1. a cheap f32 evaluation u~ with a proven error bound |u~ - u| <= eps.  Only children with u~ >= max(u~) - 2 eps can be the
-//      exact arg-max (and all exact ties are among them).  Almost always exactly one child survives and is returned — no f64 at all.
-//      Bound: Q = win / visits with |Q| <= 128 has an absolute f32 error <= 5e-5, hence numerator and span of the normalisation
-//      <= 1.2e-4 each and the normalised Q <= 5e-4 / span~ + 1e-6; the exploration term has a relative error <= 5e-7 and a
-//      magnitude <= 4.64 c (N < 2^31).  eps = 1e-3 / span~ + 4e-5 c + 4e-5 leaves a factor >= 2 everywhere; the filter is skipped
-//      when span~ < 4e-3 or a child has no visits.
+//      exact arg-max (and all exact ties are among them).  Almost always exactly one child survives and is returned — no f64 at all
+//      (measured on the host simulator over 256-iteration searches: 98 % of the levels; `same` below takes most of the rest).
+//      Bound: Q = win * rcp(visits) (win exact in f32, reciprocal <= 1 ulp, product 0.5 ulp) with |Q| <= 128 has an absolute error
+//      <= 5e-5, hence numerator and span of the normalisation <= 1.2e-4 each and the normalised Q <= 5e-4 / span~ + 1e-6; the
+//      exploration term c * sqrt(ln N) * rsqrt(visits) has a relative error <= 1e-6 (ln N 3e-7 halved by the root, rsqrt 2.4e-7,
+//      four roundings of 6e-8) and a magnitude <= 4.64 c (N < 2^31).  eps = 1e-3 / span~ + 4e-5 c + 4e-5 leaves a factor >= 2
+//      everywhere; the filter is skipped when span~ < 4e-3 or a child has no visits.
 //   2. the survivors are evaluated exactly.  The exact min / max Q come from the children that are minimal / maximal as RATIONALS
 //      (integer cross-multiplication; IEEE division is monotone, so the rounded extremes are the extremes of the rounded values).
-// vis_tab[v] = (float(1 / v), float(1 / sqrt(v))) for every visit count a search can reach (v <= iterations; host-computed in f64,
-// rounded once): the filter's division and square root become two multiplications (same error budget: each factor is within half an
-// ulp), and the lookup is one unconditional 8-byte load.
-struct UctF2 { float x, y; };
-struct UctTables { const double* ln; const UctF2* vis_tab; };
-DK_HD UctF2 uct_vis_factors(const UctTables& T, uint32_t v) { return T.vis_tab[v]; }
+// Round 2 (first form) looked (1 / v, 1 / sqrt(v)) up in a table: twelve dependent 8-byte loads per level behind the statistics load —
+// a second round trip on the walk's critical path and 24 LSU instructions; now the two factors are special-function instructions.
+// `ln_tab` (host libm values) is read only by stage 2.
+struct UctTables { const double* ln; };
 template <uint32_t W = UCT_MAX_CHILDREN>
-DK_HD uint32_t uct_best_slot(uint32_t nch, const uint32_t vis[W], const int32_t win[W], uint32_t parent_visits, double c, double ln_n, const UctTables& T,
+DK_HD uint32_t uct_best_slot(uint32_t nch, const uint32_t vis[W], const int32_t win[W], uint32_t parent_visits, double c, const double* ln_tab, double ln_host,
                              bool use_filter = true) {
     uint32_t cand = (1u << nch) - 1u;
     {   // stage 1: f32 filter
@@ -221,15 +243,15 @@ DK_HD uint32_t uct_best_slot(uint32_t nch, const uint32_t vis[W], const int32_t 
         for (uint32_t k = 0; k < W; ++k) {
             const bool on = k < nch;
             any_unvisited |= on && vis[k] == 0u;
-            const UctF2 f = uct_vis_factors(T, on && vis[k] ? vis[k] : 1u);
-            const float qk = (float)win[k] * f.x;
-            qf[k] = qk; rs[k] = f.y;
-            if (on && qk < minf) minf = qk;
-            if (on && qk > maxf) maxf = qk;
+            const float vf = (float)(vis[k] ? vis[k] : 1u);
+            const float qk = dk_fdiv_fast((float)win[k], vf);
+            qf[k] = qk; rs[k] = dk_rsqrt_fast(vf);
+            minf = on ? fminf(minf, qk) : minf;
+            maxf = on ? fmaxf(maxf, qk) : maxf;
         }
         const float spanf = maxf - minf;
         if (use_filter && !any_unvisited && spanf >= 4.0e-3f && parent_visits < (1u << 24)) {
-            const float cf = (float)c, expl = cf * sqrtf((float)ln_n);
+            const float cf = (float)c, expl = cf * sqrtf(dk_logf_fast((float)parent_visits));
             const float eps = dk_fdiv_fast(1.0e-3f, spanf) + 4.0e-5f * cf + 4.0e-5f;
             const float scale = dk_fdiv_fast(2.0f, spanf);
             float uf[W];
@@ -238,7 +260,7 @@ DK_HD uint32_t uct_best_slot(uint32_t nch, const uint32_t vis[W], const int32_t 
             for (uint32_t k = 0; k < W; ++k) {
                 const float u = (qf[k] - minf) * scale - 1.0f + expl * rs[k];
                 uf[k] = u;
-                if (k < nch && u > top) top = u;
+                top = k < nch ? fmaxf(top, u) : top;
             }
             const float thr = top - 2.0f * eps;
             uint32_t m = 0;
@@ -248,7 +270,7 @@ DK_HD uint32_t uct_best_slot(uint32_t nch, const uint32_t vis[W], const int32_t 
             if ((m & (m - 1u)) == 0u) return ffs0(m);                     // a single survivor: it is the exact arg-max
         }
     }
-    {   // Candidates with IDENTICAL statistics have identical exact values (same inputs, same arithmetic), and the first in child order
+    if (use_filter) {   // Candidates with IDENTICAL statistics have identical exact values (same inputs, same arithmetic), and the first in child order
         // wins among equals: when every candidate carries the first candidate's numbers — the common tie of a young tree, siblings
         // visited equally often with equal results — the decision needs no f64 at all.  Only valid when the candidates are ALL children
         // or survivors of the filter (then no other child can beat them), which is what `cand` holds here.
@@ -261,6 +283,24 @@ DK_HD uint32_t uct_best_slot(uint32_t nch, const uint32_t vis[W], const int32_t 
         for (uint32_t k = 0; k < W; ++k) same &= !((cand >> k) & 1u) || (vis[k] == v0 && win[k] == w0);
         if (same) return first;
     }
+    if (use_filter && cand == (1u << nch) - 1u && c >= 1.0e-3 && parent_visits >= 2u) {
+        // Every child has the same Q as a RATIONAL (late in a game the result often no longer depends on the move): the rounded
+        // quotients are identical, the span is exactly 0 and each value is 1 + c * sqrt(ln N / visits) — evaluated by the same rounded
+        // operations for every child, hence non-increasing in `visits`, and STRICTLY decreasing for c >= 1e-3: two visit counts
+        // below 2^24 move ln N / visits by a relative 2^-24 at least, its root by 2^-25, and c * root >= 2e-7 keeps that gap far
+        // above the half-ulp of 1 + c * root.  So the arg-max is the first child with the fewest visits: no f64 evaluation.
+        // (45 % of the levels the filter cannot decide, measured on the host simulator; unvisited children cannot occur on a walk
+        // but are excluded anyway.)
+        bool all_equal = vis[0] != 0u;
+        uint32_t best = 0u, best_v = vis[0];
+#pragma unroll
+        for (uint32_t k = 1; k < W; ++k) {
+            const bool on = k < nch;
+            all_equal &= !on || (vis[k] != 0u && (long long)win[k] * (long long)vis[0] == (long long)win[0] * (long long)vis[k]);
+            if (on && vis[k] < best_v) { best_v = vis[k]; best = k; }
+        }
+        if (all_equal) return best;
+    }
     // stage 2: exact evaluation of the survivors.  Extremes of Q as rationals: win_a / vis_a < win_b / vis_b  <=>  win_a vis_b < win_b vis_a
     // (unvisited children count as Q = 0 = 0 / 1).
     long long lo_w = 0, hi_w = 0;
@@ -272,6 +312,7 @@ DK_HD uint32_t uct_best_slot(uint32_t nch, const uint32_t vis[W], const int32_t 
         if (lo_v == 0u || w * (long long)lo_v < lo_w * (long long)v) { lo_w = w; lo_v = v; }
         if (hi_v == 0u || w * (long long)hi_v > hi_w * (long long)v) { hi_w = w; hi_v = v; }
     }
+    const double ln_n = ln_tab ? ln_tab[parent_visits] : ln_host;
     const double min_q = dk_ddiv((double)lo_w, (double)lo_v), max_q = dk_ddiv((double)hi_w, (double)hi_v);
     const double span = dk_dadd(max_q, -min_q);
     const bool flat = fabs(span) < 2.220446049250313e-16;            // f64::EPSILON
@@ -313,38 +354,82 @@ DK_HD uint32_t uct_phase_root(const UctPool& P, uint64_t t, const dk_state& root
 
 // backpropagate (mcts.rs:138-158): every node on the path from `explore` to the root gains one visit and
 // result[parent.current_player] — kept in the parent's slot of that node; the parents that keep statistics are the anchors the walk
-// down recorded.  Independent read-modify-writes, four in flight.
-DK_HD void uct_phase_backprop(const UctPool& P, uint64_t t) {
-    const uint32_t packed = P.result[t], len = P.path_len[t];
-#pragma unroll 4
+// down recorded.  On the device a slot is ONE 64-bit reduction (visits in the low word gain 1 and never carry; the exact integer win
+// sum in the high word gains the points modulo 2^32): nothing is read back, so a path costs one round trip for its (coalesced) entries
+// and then only fire-and-forget traffic.  The read-modify-write form waited for every slot in turn — 60 % of the rollout kernel's
+// warp time (profiles/r02_uct_rollout_v4_ncu_summary.json: the compiler cannot prove that path buffer and heads do not alias).
+DK_HD void uct_phase_backprop(const UctPool& P, uint64_t t, uint32_t packed) {
+    const uint32_t len = P.path_len[t];
+#if defined(__CUDA_ARCH__)
+    for (uint32_t l0 = 0; l0 < len; l0 += 8u) {
+        uint32_t e[8];
+#pragma unroll
+        for (uint32_t j = 0; j < 8u; ++j) e[j] = l0 + j < len ? P.path_at(t, l0 + j) : 0u;
+#pragma unroll
+        for (uint32_t j = 0; j < 8u; ++j)
+            if (l0 + j < len) {
+                UctStat* st = &P.head(t, e[j] & UCT_NODE_MASK).stat[(e[j] >> 24) & 15u];
+                const unsigned long long add = 1ull | ((unsigned long long)(uint32_t)uct_unpack_point(packed, e[j] >> 28) << 32);
+                atomicAdd(reinterpret_cast<unsigned long long*>(st), add);
+            }
+    }
+#else
     for (uint32_t l = 0; l < len; ++l) {
         const uint32_t e = P.path_at(t, l);
         UctStat& st = P.head(t, e & UCT_NODE_MASK).stat[(e >> 24) & 15u];
-        UctStat v = st;
-        v.vis += 1u;
-        v.win += uct_unpack_point(packed, e >> 28);
-        st = v;
+        st.vis += 1u;
+        st.win += uct_unpack_point(packed, e >> 28);
     }
+#endif
 }
 
-// One level of select_promising_node at a node with n_actions actions (nch of them expanded): the slot chosen by
+// Everything the walk needs from one node, fetched as ONE batch: the info word and — by the width the parent's entry announced —
+// the statistics sectors and the child entries (the entry of the chosen slot is then picked from a small local array: the dependent
+// re-read of `child[slot]` after the decision cost 0.6 us per level even from the cache).  The loads are volatile asm on the device: they are issued BEFORE the info word is examined (a
+// plain load would be sunk below the test that ends the walk, which made a level three dependent round trips: info, statistics,
+// entry — profiles/r02_uct_tree_v4_ncu_summary.json).  Slots that are not loaded read as zero.
+DK_HD void uct_load_level(const UctHead& h, uint32_t width, uint64_t& info, uint32_t vis[UCT_MAX_CHILDREN], int32_t win[UCT_MAX_CHILDREN],
+                          uint32_t child[UCT_MAX_CHILDREN]) {
+#if defined(__CUDA_ARCH__)
+    const char* base = reinterpret_cast<const char*>(&h);
+    uint32_t lo, hi;
+    asm volatile("ld.global.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "l"(base));
+#pragma unroll
+    for (uint32_t g = 0; g < UCT_MAX_CHILDREN / 2u; ++g) {
+        uint32_t a = 0u, b = 0u, c = 0u, d = 0u;
+        const bool need = g < 2u || (g < 4u ? width > 4u : width > 8u);
+        if (need) asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "+r"(a), "+r"(b), "+r"(c), "+r"(d) : "l"(base + 64u + 16u * g));
+        vis[2u * g] = a; win[2u * g] = (int32_t)b; vis[2u * g + 1u] = c; win[2u * g + 1u] = (int32_t)d;
+    }
+#pragma unroll
+    for (uint32_t g = 0; g < UCT_MAX_CHILDREN / 4u; ++g) {
+        uint32_t a = 0u, b = 0u, c = 0u, d = 0u;
+        const bool need = g < 1u || (g < 2u ? width > 4u : width > 8u);
+        if (need) asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "+r"(a), "+r"(b), "+r"(c), "+r"(d) : "l"(base + 16u + 16u * g));
+        child[4u * g] = a; child[4u * g + 1u] = b; child[4u * g + 2u] = c; child[4u * g + 3u] = d;
+    }
+    info = (uint64_t)lo | ((uint64_t)hi << 32);
+#else
+    info = h.info;
+    for (uint32_t k = 0; k < UCT_MAX_CHILDREN; ++k) {
+        const bool need = k < 4u || (k < 8u ? width > 4u : width > 8u);
+        vis[k] = need ? h.stat[k].vis : 0u;
+        win[k] = need ? h.stat[k].win : 0;
+        child[k] = need ? h.child[k] : 0u;
+    }
+#endif
+}
+
+// One level of select_promising_node at a node with nch expanded children (all of its actions): the slot chosen by
 // find_best_child.  ONE code path for every node width — the lanes of a warp sit at nodes of different widths, and separate paths
-// per width ran one after the other (5.6 of 32 lanes, profiles/r02_uct_select_v2_ncu_summary.json); only the LOADS depend on the
-// width: the statistics sectors of children 4-7 / 8-11 are fetched for nodes that can have such children.
-DK_HD uint32_t uct_select_level(const UctHead& h, uint32_t n_actions, uint32_t nch, bool is_root, uint32_t root_visits, double c, const UctTables& T) {
-    uint32_t vis[UCT_MAX_CHILDREN];
-    int32_t win[UCT_MAX_CHILDREN];
+// per width ran one after the other (5.6 of 32 lanes, profiles/r02_uct_select_v2_ncu_summary.json).
+DK_HD uint32_t uct_select_level(const uint32_t vis[UCT_MAX_CHILDREN], const int32_t win[UCT_MAX_CHILDREN], uint32_t nch, bool is_root, uint32_t root_visits,
+                                double c, const UctTables& T) {
     uint32_t total = 1u;                                  // the node's own visits: the iteration that created it + those through its children
 #pragma unroll
-    for (uint32_t k = 0; k < UCT_MAX_CHILDREN; ++k) {
-        const bool need = k < 4u || (k < 8u ? n_actions > 4u : n_actions > 8u);
-        UctStat st; st.vis = 0u; st.win = 0;
-        if (need) st = h.stat[k];
-        vis[k] = st.vis; win[k] = st.win;
-        total += k < nch ? st.vis : 0u;
-    }
+    for (uint32_t k = 0; k < UCT_MAX_CHILDREN; ++k) total += k < nch ? vis[k] : 0u;
     const uint32_t n = is_root ? root_visits : total;
-    return uct_best_slot<UCT_MAX_CHILDREN>(nch, vis, win, n, c, T.ln[n], T);
+    return uct_best_slot<UCT_MAX_CHILDREN>(nch, vis, win, n, c, T.ln, 0.0);
 }
 
 // select_promising_node (mcts.rs:45-63) + expand_single (mcts.rs:65-104) of one iteration.
@@ -354,23 +439,28 @@ DK_HD uint32_t uct_select_level(const UctHead& h, uint32_t n_actions, uint32_t n
 // anchors and the ctl flags (rollout needed, or the result is the terminal record's points) for the rollout / backpropagation phase.
 template <bool IDX>
 DK_HD void uct_phase_tree(const UctPool& P, uint64_t t, uint32_t root_visits, double c, const UctTables& T, const RngKey& key) {
-    uint32_t node = 0u, len = 0u;
-    uint32_t n_actions = uct_n_actions(P.head(t, 0u).info);
+    uint32_t node = 0u, len = 0u, last_entry = 0u;
+    uint32_t width = 15u;                                 // the root's width is not known before its info word: all sectors
     uint64_t info;
     for (;;) {
         const UctHead& h = P.head(t, node);
-        info = h.info;
+        uint32_t vis[UCT_MAX_CHILDREN];
+        int32_t win[UCT_MAX_CHILDREN];
+        uint32_t child[UCT_MAX_CHILDREN];
+        uct_load_level(h, width, info, vis, win, child);
         const uint32_t nch = uct_n_children(info);
         if (nch == 0u || (info & UCT_ACTION_MASK) != 0ull) break;
         // (a node with children and nothing to expand is an anchor: entries never point at an expanded single-action node; a
         // single-action ROOT takes slot 0 whatever the numbers are)
-        const uint32_t slot = n_actions <= 1u ? 0u : uct_select_level(h, n_actions, nch, node == 0u, root_visits, c, T);
+        const uint32_t slot = uct_n_actions(info) <= 1u ? 0u : uct_select_level(vis, win, nch, node == 0u, root_visits, c, T);
         if (len >= UCT_MAX_PATH) { P.status[t] = 3u; P.ctl[t] = 0u; return; }
-        P.path_at(t, len++) = uct_path_entry(node, slot, uct_cur(info));
-        const uint32_t entry = h.child[slot];
+        last_entry = uct_path_entry(node, slot, uct_cur(info));
+        P.path_at(t, len++) = last_entry;
+        const uint32_t entry = child[slot];
         node = entry & UCT_NODE_MASK;
-        n_actions = entry >> 28;
+        width = entry >> 28;
     }
+    const uint32_t n_actions = uct_n_actions(info);
     const uint64_t unexpanded = info & UCT_ACTION_MASK;
     uint32_t explore = node;
     alignas(16) dk_state s = P.state(t, node);
@@ -394,8 +484,7 @@ DK_HD void uct_phase_tree(const UctPool& P, uint64_t t, uint32_t root_visits, do
             P.path_at(t, len++) = uct_path_entry(node, nch, uct_cur(info));
             if (node == 0u) P.root_action[t * 16u + nch] = (uint8_t)a;
         } else {                                                                      // the end of a single-action chain: the chain grows, the
-            const uint32_t owner = P.path_at(t, len - 1u);                            // anchor's entry moves to its new end
-            P.head(t, owner & UCT_NODE_MASK).child[(owner >> 24) & 15u] = entry;
+            P.head(t, last_entry & UCT_NODE_MASK).child[(last_entry >> 24) & 15u] = entry;   // anchor's entry moves to its new end
         }
     }
     P.explore[t] = explore;
@@ -411,13 +500,13 @@ DK_HD void uct_phase_tree(const UctPool& P, uint64_t t, uint32_t root_visits, do
 
 // random_rollout (env_state_full_doko.rs:198-220) from the node chosen by the expansion; SEL12 = the caller's table holds the 12-bit rank select.
 template <bool SEL12>
-DK_HD void uct_phase_rollout(const UctPool& P, uint64_t t, const RngKey& key, const uint32_t* __restrict__ lut) {
+DK_HD uint32_t uct_phase_rollout(const UctPool& P, uint64_t t, const RngKey& key, const uint32_t* __restrict__ lut) {
     alignas(16) dk_state s = P.state(t, P.explore[t]);
     int32_t p[4] = {0, 0, 0, 0};
     FdoLive g; FdoResume rs;
     if (fdo_state_to_live(s, g, rs)) { fdo_play_to_end<false, false, SEL12>(g, key, &rs, lut); fdo_final_points(g, p); }
     else { p[0] = s.points[0]; p[1] = s.points[1]; p[2] = s.points[2]; p[3] = s.points[3]; }
-    P.result[t] = uct_pack_points(p);
+    return uct_pack_points(p);
 }
 
 // Moves of the root (mcts.rs:220-229) as mcts_policy.rs:96-118 consumes them: visits / values by action index and the move with

@@ -246,18 +246,15 @@ SIM_API uint32_t sim_fdo_uct_search(const dk_state* root, uint64_t seed, uint64_
     dk::RngKey det_key = key; det_key.unit_hi = sub;
     // (the determinization above already replaced `s`; uct_phase_root is handed the result and told not to determinize again)
     if (dk::uct_phase_root(P, 0, s, false, det_key)) return P.status[0];
-    const size_t vlen = iterations + 1;
-    std::vector<dk::UctF2> vis_tab(vlen);
-    vis_tab[0].x = vis_tab[0].y = 1.0f;
-    for (size_t v = 1; v < vlen; ++v) { vis_tab[v].x = (float)(1.0 / (double)v); vis_tab[v].y = (float)(1.0 / std::sqrt((double)v)); }
-    dk::UctTables T; T.ln = ln_table.data(); T.vis_tab = vis_tab.data();
+    dk::UctTables T; T.ln = ln_table.data();
     for (uint32_t it = 0; it < iterations; ++it) {
         if (!(P.ctl[0] & dk::UCT_CTL_ACTIVE)) return P.status[0];
         key.unit_hi = sub * iterations + it;
         dk::uct_phase_tree<false>(P, 0, it, (double)uct_c, T, key);                            // uct_tree_kernel
         if (!(P.ctl[0] & dk::UCT_CTL_ACTIVE)) return P.status[0];
-        if (P.ctl[0] & dk::UCT_CTL_ROLLOUT) dk::uct_phase_rollout<false>(P, 0, key, card_lut());   // uct_rollout_kernel
-        dk::uct_phase_backprop(P, 0);
+        uint32_t packed = P.result[0];
+        if (P.ctl[0] & dk::UCT_CTL_ROLLOUT) packed = dk::uct_phase_rollout<false>(P, 0, key, card_lut());   // uct_rollout_kernel
+        dk::uct_phase_backprop(P, 0, packed);
     }
     uint32_t best = dk::uct_moves(P, 0, visits, values);
     *action_out = best == 0xFFu ? -1 : (int32_t)best;
@@ -275,13 +272,7 @@ SIM_API uint32_t sim_uct_select_check(uint32_t nch, const uint32_t* vis, const l
     int32_t w[dk::UCT_MAX_CHILDREN] = {0};
     for (uint32_t k = 0; k < nch; ++k) { v[k] = vis[k]; w[k] = (int32_t)win[k]; }
     const double ln_n = std::log((double)parent_visits);
-    // the filter's (1 / v, 1 / sqrt(v)) table, as dk_uct_search builds it
-    static std::vector<dk::UctF2> vis_tab;
-    const size_t TAB = ((size_t)1 << 22) + 4;      // covers every visit count the test family uses
-    if (vis_tab.empty()) { vis_tab.resize(TAB); vis_tab[0].x = vis_tab[0].y = 1.0f; for (size_t i = 1; i < TAB; ++i) { vis_tab[i].x = (float)(1.0 / (double)i); vis_tab[i].y = (float)(1.0 / std::sqrt((double)i)); } }
-    for (uint32_t k = 0; k < nch; ++k) if (vis[k] >= TAB) return 0xFFFFFFFFu;
-    dk::UctTables T; T.ln = nullptr; T.vis_tab = vis_tab.data();
-    uint32_t a = dk::uct_best_slot(nch, v, w, parent_visits, (double)uct_c, ln_n, T, true) + 1u;
-    uint32_t b = dk::uct_best_slot(nch, v, w, parent_visits, (double)uct_c, ln_n, T, false) + 1u;
+    uint32_t a = dk::uct_best_slot(nch, v, w, parent_visits, (double)uct_c, nullptr, ln_n, true) + 1u;
+    uint32_t b = dk::uct_best_slot(nch, v, w, parent_visits, (double)uct_c, nullptr, ln_n, false) + 1u;
     return (a & 255u) | ((b & 255u) << 8);
 }

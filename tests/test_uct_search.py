@@ -116,13 +116,14 @@ def test_search_prefers_the_winning_card(orc):
 
 def test_two_stage_selection_equals_all_f64_selection():
     """uct_find_best_child takes the decision with an f32 filter + exact evaluation of the survivors; it must pick the same child as
-    evaluating every child in f64 (what the reference does), in particular on exact ties and on near ties below the f32 resolution."""
+    evaluating every child in f64 (what the reference does), in particular on exact ties and on near ties below the f32 resolution.  (The all-f64 side also skips the
+    two integer shortcuts — identical statistics, equal rational Q — so they are checked against the plain evaluation too.)"""
     sim = hostsim_lib.load()
     prng = np.random.default_rng(12)
     n_cases = 0
     for trial in range(40000):
         nch = int(prng.integers(1, 13))
-        kind = trial % 8
+        kind = trial % 9
         if kind == 0:                                    # random statistics
             vis = prng.integers(1, 2000, size=nch)
             win = np.array([int(prng.integers(-60, 61)) * int(v) + int(prng.integers(-v, v + 1)) for v in vis])
@@ -144,13 +145,16 @@ def test_two_stage_selection_equals_all_f64_selection():
         elif kind == 6:                                  # Q equal, exploration decides: visit counts differ by one
             v = int(prng.integers(10, 5000)); q = int(prng.integers(-40, 41))
             vis = v + prng.integers(0, 2, size=nch); win = q * vis
+        elif kind == 7:                                  # Q equal as rationals at the top of the visit range: adjacent huge visit counts
+            v = int(prng.integers(1 << 20, (1 << 22) - 4)); q = int(prng.integers(-127, 128))
+            vis = v + prng.integers(0, 3, size=nch); win = q * vis
         else:                                            # extremes of the value range
             vis = prng.integers(1, 1 << 20, size=nch); win = vis * prng.choice([-127, 127, 0, 126], size=nch)
         vis = np.ascontiguousarray(vis, dtype=np.uint32); win = np.ascontiguousarray(win, dtype=np.int64)
         parent = int(vis.sum()) + 1
         if parent >= 1 << 23:
             parent = int(vis.max()) + 1
-        c = float(prng.choice([0.0, 0.1, 0.5, 1.4, 2.0, 4.0, 25.0]))
+        c = float(prng.choice([0.0, 1.0e-4, 1.0e-3, 0.1, 0.5, 1.4, 2.0, 4.0, 25.0]))
         r = sim.sim_uct_select_check(nch, hostsim_lib.ptr(vis), hostsim_lib.ptr(win), parent, c)
         assert (r & 255) == (r >> 8), (trial, kind, nch, vis, win, parent, c, r & 255, r >> 8)
         n_cases += 1
