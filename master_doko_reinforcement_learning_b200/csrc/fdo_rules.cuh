@@ -481,24 +481,37 @@ DK_HD void fdo_play_to_end(FdoLive& g, const RngKey& key, const FdoResume* rs, c
         g.steps += 4u - n_res;
         fdo_finish_reservations(g, ra);
     }
-    uint32_t t0 = FRESH ? 0u : rs->t0;
+    uint32_t t = FRESH ? 0u : rs->t0;
     uint32_t starts = FRESH ? 0u : rs->starts;
-    for (uint32_t t = t0; t < 12u; ++t) {
+    // A resumed game first finishes its current (possibly partial) trick; the remaining tricks run through the same unconditional
+    // body as a fresh game.  With the `is this position already played` tests inside the one loop, the loop body was divergent code:
+    // the shared-memory window base (a uniform register on sm_100) was recomputed at every table access — 4 of ~45 instructions per
+    // card step of the kernels that start from stored records (profiles/r02_k4_roll_v1 attribution).
+    if (!FRESH && t < 12u) {
         starts |= g.base << (2u * t);
-        U4 blk = rng_block(key, SITE_CARD, t);
+        const U4 blk = rng_block(key, SITE_CARD, t);
         TrickAcc a;
         a.follow = 0; a.best = 0; a.bestk = 0; a.bestc = 0; a.teyes = 0; a.foxm = 0; a.prow = 0;
-        uint32_t k0 = 0;
-        bool first = !FRESH && t == t0;
-        if (first) { k0 = rs->k0; if (k0 > 0u) a = rs->acc; }
-        bool last = t == 11u;
-#define DK_FDO_POS(K, HREG, WORD)                                                                      \
-        if (!first || k0 <= (uint32_t)(K)) fdo_card_step<K, SEL12>(g, HREG, a, WORD, last, lut);
-        DK_FDO_POS(0, g.h0, blk.x)
-        DK_FDO_POS(1, g.h1, blk.y)
-        DK_FDO_POS(2, g.h2, blk.z)
-        DK_FDO_POS(3, g.h3, blk.w)
-#undef DK_FDO_POS
+        const uint32_t k0 = rs->k0;
+        if (k0 > 0u) a = rs->acc;
+        const bool last = t == 11u;
+        if (k0 <= 0u) fdo_card_step<0, SEL12>(g, g.h0, a, blk.x, last, lut);
+        if (k0 <= 1u) fdo_card_step<1, SEL12>(g, g.h1, a, blk.y, last, lut);
+        if (k0 <= 2u) fdo_card_step<2, SEL12>(g, g.h2, a, blk.z, last, lut);
+        fdo_card_step<3, SEL12>(g, g.h3, a, blk.w, last, lut);
+        fdo_trick_done(g, a, t);
+        ++t;
+    }
+    for (; t < 12u; ++t) {
+        starts |= g.base << (2u * t);
+        const U4 blk = rng_block(key, SITE_CARD, t);
+        TrickAcc a;
+        a.follow = 0; a.best = 0; a.bestk = 0; a.bestc = 0; a.teyes = 0; a.foxm = 0; a.prow = 0;
+        const bool last = t == 11u;
+        fdo_card_step<0, SEL12>(g, g.h0, a, blk.x, last, lut);
+        fdo_card_step<1, SEL12>(g, g.h1, a, blk.y, last, lut);
+        fdo_card_step<2, SEL12>(g, g.h2, a, blk.z, last, lut);
+        fdo_card_step<3, SEL12>(g, g.h3, a, blk.w, last, lut);
         fdo_trick_done(g, a, t);
     }
     // announcement rounds (see fdo_replay_announcements): fresh games start with the round before card 0

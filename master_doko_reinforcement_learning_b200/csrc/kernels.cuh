@@ -876,11 +876,13 @@ __global__ void __launch_bounds__(MATCH_THREADS)
 fdo_determinize_kernel(RngParams rp, uint64_t n_info, uint32_t samples, uint32_t splits, const dk_state* __restrict__ states, uint64_t* __restrict__ hands_out,
                        uint8_t* __restrict__ res_out, uint8_t* __restrict__ status_out) {
     __shared__ MatchPrep prep;
+    __shared__ uint32_t rank6[64];                                 // rank-select table of rule 4 (dk_common.cuh rank_lut6_entry)
     // `splits` blocks share one info-state (sample smp belongs to block smp / MATCH_THREADS % splits): a single decision's 4096 samples
     // spread over 32 SMs instead of one, and small batches do not end in a mostly empty last wave.  Sample ids, hence results, do not change.
     const uint64_t i = blockIdx.x / splits;
     const uint32_t part = blockIdx.x - (uint32_t)i * splits;
     if (i >= n_info) return;
+    if (threadIdx.x >= 64) rank6[threadIdx.x - 64] = rank_lut6_entry(threadIdx.x - 64);
     if (threadIdx.x == 0) {
         alignas(16) dk_state s;
         load_state(states + i, s);
@@ -891,7 +893,7 @@ fdo_determinize_kernel(RngParams rp, uint64_t n_info, uint32_t samples, uint32_t
         RngKey key = make_key(rp, i, rp.first_sub + smp, true);
         uint64_t h[4];
         uint8_t r[4];
-        uint32_t st = prep.valid ? fdo_match_sample(prep, key, h, r) : 2u;
+        uint32_t st = prep.valid ? fdo_match_sample(prep, key, h, r, rank6) : 2u;
         if (!prep.valid) { h[0] = h[1] = h[2] = h[3] = 0; r[0] = r[1] = r[2] = r[3] = 0xFF; }
         uint64_t o = i * samples + smp;
         if (hands_out) {

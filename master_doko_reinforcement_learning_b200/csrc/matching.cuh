@@ -93,14 +93,26 @@ DK_HD void fdo_match_prepare(const dk_state& s, MatchPrep& m) {
     }
 }
 
+// The sample's working state.  The reference keeps a "possible cards" multiset per hidden seat and removes an assigned card from
+// every one of them (:49-76).  Those multisets are always the AVAILABLE multiset restricted to the card types the seat may hold —
+// both lose one copy of the same card at the same moment — so only the 24-bit type mask `allow` is kept per seat (0 once the seat is
+// full) and possible[o] is (avail.a & allow[o], avail.b & allow[o]) wherever a rule reads it.  An assignment then touches the
+// available set, one hand and one counter instead of four multisets: the ALU pipe is what bounds this kernel (84 % busy, LSU 2 %;
+// profiles/r02_k3_v1_ncu_summary.json: 32 % of the instructions were assign_card).
+// `len[o]` = |possible[o]|, kept up to date by assign_card (every seat that could have held the card loses one): rule 2 fires for a
+// seat exactly when len == slots, which replaces six population counts per iteration of the rule loop.  A seat without open slots is
+// parked at MATCH_LEN_DONE (never equal to a slot count; its `allow` is empty, so nothing is subtracted any more).
+constexpr uint32_t MATCH_LEN_DONE = 255u;
 struct MatchState {
-    Hand2 avail, possible[3], assigned[3];
+    Hand2 avail, assigned[3];
+    uint32_t allow[3];
+    uint32_t len[3];
     uint32_t slots[3], must_q, status;
 };
 
 // CardMatchingState::assign_card (:49-76), branch-free over compile-time slot numbers (the record of a sample stays in registers:
 // the indexed form put it into local memory — 13 % of the kernel's instructions were LDL / STL, profiles/r01_determinize_attribution.json):
-// the receiving slot is selected by a mask; removing a card from a set that does not hold it is a no-op.
+// the receiving slot is selected by a mask.
 // (Tried and rejected: the rules as a one-card-per-iteration state machine with a single assign site, which is what sped up the
 // rs-doko sampler by 1.5x — here the lanes of a warp then sit in different rules and every iteration runs all of them: 2x slower.)
 DK_HD void fdo_match_assign(MatchState& m, uint32_t j, uint32_t c) {
@@ -111,20 +123,20 @@ DK_HD void fdo_match_assign(MatchState& m, uint32_t j, uint32_t c) {
         const bool mine = o == j;
         h2_add(m.assigned[o], mine ? bit : 0u);
         m.slots[o] -= mine ? 1u : 0u;
-        h2_remove_one(m.possible[o], bit);                     // (o == j || possible[o] has the card): otherwise nothing to remove
         const bool full = mine && m.slots[o] == 0u;
-        m.possible[o].a = full ? 0u : m.possible[o].a;
-        m.possible[o].b = full ? 0u : m.possible[o].b;
+        m.len[o] -= (m.allow[o] & bit) ? 1u : 0u;
+        m.len[o] = full ? MATCH_LEN_DONE : m.len[o];
+        m.allow[o] = full ? 0u : m.allow[o];                              // a full seat can hold nothing more
     }
-    if (c == CARD_CQ) m.must_q &= ~(1u << j);
+    if (m.must_q != 0u && c == CARD_CQ) m.must_q &= ~(1u << j);           // (must_q is almost always empty)
 }
 // rule 1 (:78-113): walk a SNAPSHOT of the available cards (copy-A bits ascending, then copy-B bits) and hand every card that
 // exactly one hidden seat can hold to that seat.  The seats' possible sets only change when a card is assigned, so between two
 // assignments the "exactly one owner" mask is constant: instead of visiting every card, jump to the next snapshot card whose bit is
 // set in that mask (bit-parallel, exact).
 DK_HD uint32_t fdo_match_single_owner_mask(const MatchState& m) {
-    uint32_t p0 = m.possible[0].a, p1 = m.possible[1].a, p2 = m.possible[2].a;
-    return (p0 ^ p1 ^ p2) & ~(p0 & p1 & p2);                  // odd parity minus "all three" = exactly one
+    const uint32_t p0 = m.allow[0], p1 = m.allow[1], p2 = m.allow[2];
+    return m.avail.a & (p0 ^ p1 ^ p2) & ~(p0 & p1 & p2);      // odd parity minus "all three" = exactly one
 }
 DK_HD void fdo_match_rule1(MatchState& m) {
     uint32_t snap[2] = {m.avail.a, m.avail.b};
@@ -136,22 +148,22 @@ DK_HD void fdo_match_rule1(MatchState& m) {
             if (cand == 0u) break;
             uint32_t c = ffs0(cand), bit = 1u << c;
             todo &= ~(bit | (bit - 1u));                          // everything up to and including c has been visited
-            uint32_t j = (m.possible[0].a & bit) ? 0u : ((m.possible[1].a & bit) ? 1u : 2u);
+            uint32_t j = (m.allow[0] & bit) ? 0u : ((m.allow[1] & bit) ? 1u : 2u);
             fdo_match_assign(m, j, c);
         }
     }
 }
 // rule 2 (:115-145): a seat whose open slots equal its possible cards takes them all.
+DK_HD uint32_t fdo_match_possible_len(const MatchState& m, uint32_t j) { return popc(m.avail.a & m.allow[j]) + popc(m.avail.b & m.allow[j]); }
 DK_HD bool fdo_match_rule2(MatchState& m) {
     // fast exit (the common case): if no seat qualifies now, none will — nothing is assigned in between
-    if (!((m.slots[0] > 0u && m.slots[0] == h2_len(m.possible[0])) || (m.slots[1] > 0u && m.slots[1] == h2_len(m.possible[1])) ||
-          (m.slots[2] > 0u && m.slots[2] == h2_len(m.possible[2])))) return false;
+    if (m.len[0] != m.slots[0] && m.len[1] != m.slots[1] && m.len[2] != m.slots[2]) return false;
     bool changed = false;
 #pragma unroll
     for (uint32_t j = 0; j < 3u; ++j) {
-        if (m.slots[j] > 0u && m.slots[j] == h2_len(m.possible[j])) {
+        if (m.len[j] == m.slots[j]) {
             changed = true;
-            uint32_t snap[2] = {m.possible[j].a, m.possible[j].b};
+            uint32_t snap[2] = {m.avail.a & m.allow[j], m.avail.b & m.allow[j]};
             for (uint32_t plane = 0; plane < 2u; ++plane) {
                 uint32_t bits = snap[plane];
                 while (bits) { uint32_t c = ffs0(bits); bits &= bits - 1u; fdo_match_assign(m, j, c); }
@@ -166,22 +178,27 @@ DK_HD bool fdo_match_rule3(MatchState& m) {
     bool changed = false;
 #pragma unroll
     for (uint32_t j = 0; j < 3u; ++j)
-        if (((m.must_q >> j) & 1u) && (m.possible[j].a & (1u << CARD_CQ))) { changed = true; fdo_match_assign(m, j, CARD_CQ); }
+        if (((m.must_q >> j) & 1u) && (m.avail.a & m.allow[j] & (1u << CARD_CQ))) { changed = true; fdo_match_assign(m, j, CARD_CQ); }
     return changed;
 }
 
 struct MatchRng { U4 blk; uint32_t blk_id, count; };
 
 // One sample: execute (:207-238) + hidden reservations (:418-464).  hands_out / res_out by ABSOLUTE seat.
-DK_HD uint32_t fdo_match_sample(const MatchPrep& p, const RngKey& key, uint64_t hands_out[4], uint8_t res_out[4]) {
+// rank6 (optional): the 64-entry rank-select table (rank_lut6_entry) in shared memory — the card of rule 4 then comes from two popc
+// levels and one lookup on the idle LSU pipe instead of five compare / shift levels on the ALU pipe.
+DK_HD uint32_t fdo_match_sample(const MatchPrep& p, const RngKey& key, uint64_t hands_out[4], uint8_t res_out[4], const uint32_t* __restrict__ rank6 = nullptr) {
     MatchState m;
     m.avail = p.avail; m.must_q = p.must_q; m.status = 0;
 #pragma unroll
-    for (uint32_t j = 0; j < 3u; ++j) { m.possible[j] = p.possible[j]; m.slots[j] = p.slots[j]; m.assigned[j].a = 0; m.assigned[j].b = 0; }
+    for (uint32_t j = 0; j < 3u; ++j) {
+        m.allow[j] = p.possible[j].a; m.slots[j] = p.slots[j]; m.assigned[j].a = 0; m.assigned[j].b = 0;
+        m.len[j] = p.slots[j] ? h2_len(p.possible[j]) : MATCH_LEN_DONE;
+    }
     MatchRng r; r.blk_id = 0xFFFFFFFFu; r.count = 0; r.blk.x = r.blk.y = r.blk.z = r.blk.w = 0;
     for (;;) {
         if ((m.avail.a | m.avail.b) == 0u) break;
-        fdo_match_rule1(m);
+        if (fdo_match_single_owner_mask(m) != 0u) fdo_match_rule1(m);     // (rule 1 finds nothing while the mask is empty)
         if (fdo_match_rule2(m)) continue;
         if (fdo_match_rule3(m)) continue;
         if ((m.avail.a | m.avail.b) == 0u) break;
@@ -191,9 +208,11 @@ DK_HD uint32_t fdo_match_sample(const MatchPrep& p, const RngKey& key, uint64_t 
         uint32_t ord = r.count++;
         if ((ord >> 2) != r.blk_id) { r.blk_id = ord >> 2; r.blk = rng_block(key, SITE_MATCH_CARD, ord >> 2); }
         uint32_t idx = mulhi(u4_word(r.blk, ord & 3u), n);
-        uint32_t c = idx < na ? select_lsb24(m.avail.a, idx) : select_lsb24(m.avail.b, idx - na);
+        const bool first_plane = idx < na;
+        const uint32_t plane = first_plane ? m.avail.a : m.avail.b, k = first_plane ? idx : idx - na;
+        uint32_t c = rank6 ? select_lsb24_lut(plane, k, rank6 - RANK_LUT_BASE) : select_lsb24(plane, k);
         uint32_t bit = 1u << c;
-        uint32_t j = (m.possible[0].a & bit) ? 0u : ((m.possible[1].a & bit) ? 1u : ((m.possible[2].a & bit) ? 2u : 3u));
+        uint32_t j = (m.allow[0] & bit) ? 0u : ((m.allow[1] & bit) ? 1u : ((m.allow[2] & bit) ? 2u : 3u));
         if (j == 3u) { m.status = 1u; break; }                // `.first().unwrap()` would panic: dead end
         fdo_match_assign(m, j, c);
     }

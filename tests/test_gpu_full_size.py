@@ -142,7 +142,9 @@ def test_config3_sample_assignment_64k_x_4096(dk, orc):
     sub = torch.arange(0, n, 257, device="cuda")
     assert torch.equal(cnt(hands[sub][:, ::64]), cnt(real[sub])[:, None, :].expand(len(sub), S // 64, 24))
     own = torch.gather(hands, 2, obs_seat[:, None, None].expand(n, S, 1))[..., 0]
-    assert torch.equal(own, torch.gather(real, 1, obs_seat[:, None])[:, 0][:, None].expand(n, S))
+    # (the sampler returns the observer's hand in canonical copy order, hand_from_vec(hand_to_vec(own)): copy A filled first)
+    canon = lambda h: (((h | (h >> 24)) & 0xFFFFFF) | (((h & (h >> 24)) & 0xFFFFFF) << 24))
+    assert torch.equal(own, canon(torch.gather(real, 1, obs_seat[:, None])[:, 0])[:, None].expand(n, S))
     del own
     h_a, _, _ = dk.determinize(0, states[:1024], S // 2, dk.rng(SEED, 0, 6, first_sub=0))
     h_b, _, _ = dk.determinize(0, states[:1024], S // 2, dk.rng(SEED, 0, 6, first_sub=S // 2))
