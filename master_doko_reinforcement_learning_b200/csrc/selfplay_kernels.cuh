@@ -371,7 +371,15 @@ uct_root_kernel(RngParams rp, UctPool P, uint32_t trees_per_root, int determiniz
     if (visits_out) for (uint32_t a = 0; a < N_ACTIONS; ++a) visits_out[t * N_ACTIONS + a] = 0u;
     if (values_out) for (uint32_t a = 0; a < N_ACTIONS; ++a) values_out[t * N_ACTIONS + a] = 0.0f;
 }
-// select(it) + expand(it)
+// select(it) + expand(it): thread = tree for the whole phase (uct_phase_tree).
+// Tried and rejected (profiles/r02_uct_tree_v8_packed_levels_ncu_summary.json): a LEVEL-SYNCHRONOUS walk inside the block — after
+// every level the trees still walking are packed densely onto the first threads, ordered by the width class of their node (4 / 8 / 12
+// child slots, evaluated by class-specialised code), per-tree walk state in shared memory.  It does what it promises for the lanes
+// (13.5 -> 18.6 of 32) and the instruction count (29.9 M -> 26.4 M per launch of 131 072 trees), but every level of a block now ends
+// in two barriers behind a DRAM round trip: 8.1 warps per issue slot wait at the barrier, issue utilisation drops from 40 % to 25 %,
+// the kernel goes from 85 to 110 us and the search from 1.09e9 to 0.92e9 iterations/s.  Sorting the trees once per launch by their
+// previous path length instead was measured on the host simulator: 0.63 -> 0.67 of the lanes (a path's length says little about the
+// next one's; a perfect sort would give 0.84).
 __global__ void __launch_bounds__(UCT_THREADS, DK_UCT_TREE_BLOCKS)
 uct_tree_kernel(RngParams rp, UctPool P, uint32_t trees_per_root, uint32_t iterations, uint32_t it, double c, UctTables T, uint64_t t_begin, uint64_t t_end) {
     const uint64_t t = t_begin + (uint64_t)blockIdx.x * UCT_THREADS + threadIdx.x;

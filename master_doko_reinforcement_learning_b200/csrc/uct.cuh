@@ -65,7 +65,7 @@ constexpr uint32_t UCT_MAX_PATH = 56u;                          // anchors on a 
 DK_HD uint32_t uct_path_entry(uint32_t node, uint32_t slot, uint32_t cur) { return node | (slot << 24) | (cur << 28); }
 
 // Per-tree control words (one array each, [n_trees]): what the phases hand to each other.
-enum : uint32_t { UCT_CTL_ACTIVE = 1u, UCT_CTL_ROLLOUT = 2u };
+enum : uint32_t { UCT_CTL_ACTIVE = 1u, UCT_CTL_ROLLOUT = 2u, UCT_CTL_WIDTH_SHIFT = 8u, UCT_CTL_WIDTH_MASK = 15u << 8 };   // bits 8-11: #actions of the root
 struct UctPool {
     UctHead* heads;       // [iterations + 1][n_trees]
     dk_state* states;     // [iterations + 1][n_trees]
@@ -344,11 +344,14 @@ DK_HD uint32_t uct_phase_root(const UctPool& P, uint64_t t, const dk_state& root
     P.status[t] = status;
     P.n_nodes[t] = 1u;
     P.explore[t] = 0u; P.result[t] = 0u; P.path_len[t] = 0u;
-    P.ctl[t] = status == 0u ? UCT_CTL_ACTIVE : 0u;
+    uint32_t ctl = 0u;
     if (status == 0u) {
-        P.head(t, 0u).info = uct_node_info<true>(s, 63u, true);
+        const uint64_t info = uct_node_info<true>(s, 63u, true);
+        P.head(t, 0u).info = info;
         P.state(t, 0u) = s;
+        ctl = UCT_CTL_ACTIVE | (uct_n_actions(info) << UCT_CTL_WIDTH_SHIFT);
     }
+    P.ctl[t] = ctl;
     return status;
 }
 
@@ -437,29 +440,10 @@ DK_HD uint32_t uct_select_level(const uint32_t vis[UCT_MAX_CHILDREN], const int3
 // backpropagated so far (every iteration adds one visit to the root).  Expansion at the node reached: a random unexpanded action
 // (SITE_EXPAND word 0 of the iteration's stream), by_action on the node's record, the child appended.  Leaves `explore`, the path of
 // anchors and the ctl flags (rollout needed, or the result is the terminal record's points) for the rollout / backpropagation phase.
+// expand_single (mcts.rs:65-104) at the node the walk ended in (`info` = its info word, `len` anchors on the path, `last_entry` = the
+// last of them) + the hand-over to the rollout / backpropagation phase.
 template <bool IDX>
-DK_HD void uct_phase_tree(const UctPool& P, uint64_t t, uint32_t root_visits, double c, const UctTables& T, const RngKey& key) {
-    uint32_t node = 0u, len = 0u, last_entry = 0u;
-    uint32_t width = 15u;                                 // the root's width is not known before its info word: all sectors
-    uint64_t info;
-    for (;;) {
-        const UctHead& h = P.head(t, node);
-        uint32_t vis[UCT_MAX_CHILDREN];
-        int32_t win[UCT_MAX_CHILDREN];
-        uint32_t child[UCT_MAX_CHILDREN];
-        uct_load_level(h, width, info, vis, win, child);
-        const uint32_t nch = uct_n_children(info);
-        if (nch == 0u || (info & UCT_ACTION_MASK) != 0ull) break;
-        // (a node with children and nothing to expand is an anchor: entries never point at an expanded single-action node; a
-        // single-action ROOT takes slot 0 whatever the numbers are)
-        const uint32_t slot = uct_n_actions(info) <= 1u ? 0u : uct_select_level(vis, win, nch, node == 0u, root_visits, c, T);
-        if (len >= UCT_MAX_PATH) { P.status[t] = 3u; P.ctl[t] = 0u; return; }
-        last_entry = uct_path_entry(node, slot, uct_cur(info));
-        P.path_at(t, len++) = last_entry;
-        const uint32_t entry = child[slot];
-        node = entry & UCT_NODE_MASK;
-        width = entry >> 28;
-    }
+DK_HD void uct_phase_expand(const UctPool& P, uint64_t t, uint32_t node, uint64_t info, uint32_t len, uint32_t last_entry, const RngKey& key, uint32_t ctl_keep) {
     const uint32_t n_actions = uct_n_actions(info);
     const uint64_t unexpanded = info & UCT_ACTION_MASK;
     uint32_t explore = node;
@@ -492,10 +476,38 @@ DK_HD void uct_phase_tree(const UctPool& P, uint64_t t, uint32_t root_visits, do
     if (st_phase(s) == DK_PHASE_FINISHED) {                                          // nothing to roll out: the rewards are the record's points
         const int32_t p[4] = {s.points[0], s.points[1], s.points[2], s.points[3]};
         P.result[t] = uct_pack_points(p);
-        P.ctl[t] = UCT_CTL_ACTIVE;
+        P.ctl[t] = UCT_CTL_ACTIVE | ctl_keep;
     } else {
-        P.ctl[t] = UCT_CTL_ACTIVE | UCT_CTL_ROLLOUT;
+        P.ctl[t] = UCT_CTL_ACTIVE | UCT_CTL_ROLLOUT | ctl_keep;
     }
+}
+
+// The whole tree phase of ONE tree by one thread.
+template <bool IDX>
+DK_HD void uct_phase_tree(const UctPool& P, uint64_t t, uint32_t root_visits, double c, const UctTables& T, const RngKey& key) {
+    uint32_t node = 0u, len = 0u, last_entry = 0u;
+    uint32_t width = 15u;                                 // the root's width is not known before its info word: all sectors
+    const uint32_t ctl_keep = P.ctl[t] & UCT_CTL_WIDTH_MASK;
+    uint64_t info;
+    for (;;) {
+        const UctHead& h = P.head(t, node);
+        uint32_t vis[UCT_MAX_CHILDREN];
+        int32_t win[UCT_MAX_CHILDREN];
+        uint32_t child[UCT_MAX_CHILDREN];
+        uct_load_level(h, width, info, vis, win, child);
+        const uint32_t nch = uct_n_children(info);
+        if (nch == 0u || (info & UCT_ACTION_MASK) != 0ull) break;
+        // (a node with children and nothing to expand is an anchor: entries never point at an expanded single-action node; a
+        // single-action ROOT takes slot 0 whatever the numbers are)
+        const uint32_t slot = uct_n_actions(info) <= 1u ? 0u : uct_select_level(vis, win, nch, node == 0u, root_visits, c, T);
+        if (len >= UCT_MAX_PATH) { P.status[t] = 3u; P.ctl[t] = 0u; return; }
+        last_entry = uct_path_entry(node, slot, uct_cur(info));
+        P.path_at(t, len++) = last_entry;
+        const uint32_t entry = child[slot];
+        node = entry & UCT_NODE_MASK;
+        width = entry >> 28;
+    }
+    uct_phase_expand<IDX>(P, t, node, info, len, last_entry, key, ctl_keep);
 }
 
 // random_rollout (env_state_full_doko.rs:198-220) from the node chosen by the expansion; SEL12 = the caller's table holds the 12-bit rank select.
