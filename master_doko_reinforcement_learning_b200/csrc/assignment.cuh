@@ -50,10 +50,16 @@ DK_HD void doko_assign_prepare(const dk_state& s, AssignPrep& m) {
     }
 }
 
-struct AssignState { Hand2 remaining, allowed[4], hand[4]; uint32_t len[4]; };
+// The sample's working state.  The reference keeps one "allowed" list per seat and removes a distributed card from every one of
+// them (:284-316); the lists are always the REMAINING multiset restricted to the card types the seat may hold, so only the 24-bit
+// type mask `allow` is kept per seat (0 for a seat without open slots — the reference clears a full hand's list, and never offers
+// anything to a seat whose hand is already complete) together with the list's length `cnt` (parked at ASSIGN_CNT_DONE when the seat is
+// full): the eight population counts per iteration of distribute_exactly_as_per_hand's test and the per-seat multiset updates of
+// distribute_card become a compare and a decrement (same technique as the full-rules sampler, matching.cuh).
+constexpr uint32_t ASSIGN_CNT_DONE = 255u;
+struct AssignState { Hand2 remaining, hand[4]; uint32_t allow[4], len[4], cnt[4], n_remaining; };
 
-// distribute_card (:284-316), branch-free: the receiving seat is selected by a mask, removing a card from a list that does not
-// hold it is a no-op
+// distribute_card (:284-316), branch-free: the receiving seat is selected by a mask
 DK_HD void doko_assign_distribute(AssignState& a, uint32_t player, uint32_t c) {
     const uint32_t bit = 1u << c;
 #pragma unroll
@@ -61,20 +67,18 @@ DK_HD void doko_assign_distribute(AssignState& a, uint32_t player, uint32_t c) {
         const bool mine = i == player;
         h2_add(a.hand[i], mine ? bit : 0u);
         a.len[i] -= mine ? 1u : 0u;
-        h2_remove_one(a.allowed[i], bit);
+        a.cnt[i] -= (a.allow[i] & bit) ? 1u : 0u;
+        const bool full = mine && a.len[i] == 0u;                    // a full hand can take none of the remaining cards
+        a.cnt[i] = full ? ASSIGN_CNT_DONE : a.cnt[i];
+        a.allow[i] = full ? 0u : a.allow[i];
     }
     h2_remove_one(a.remaining, bit);
-    const uint32_t rem = a.remaining.a;
-#pragma unroll
-    for (uint32_t i = 0; i < 4u; ++i) {
-        const uint32_t clr = a.len[i] == 0u ? rem : 0u;              // a full hand can take none of the remaining cards
-        a.allowed[i].a &= ~clr; a.allowed[i].b &= ~clr;
-    }
+    a.n_remaining -= 1u;
 }
 DK_HD uint32_t doko_assign_eligible(const AssignState& a, uint32_t bit) {
     uint32_t m = 0;
 #pragma unroll
-    for (uint32_t i = 0; i < 4u; ++i) if ((a.allowed[i].a & bit) && a.len[i] > 0u) m |= 1u << i;
+    for (uint32_t i = 0; i < 4u; ++i) if (a.allow[i] & bit) m |= 1u << i;
     return m;
 }
 // k-th element (0-based) of a multiset listed in ascending card id with doubles adjacent.
@@ -89,12 +93,42 @@ DK_HD uint32_t h2_select_adjacent(const Hand2& h, uint32_t k) {
     }
     return lo;
 }
-// sample_assignment (:493-581).  Returns 0 ok, 1 dead end.
-DK_HD uint32_t doko_assign_sample(const AssignPrep& p, const RngKey& key, uint64_t hands_out[4]) {
+// The same with a 64-entry table for the last level: three halvings (12 / 6 / 3 card types, two population counts each), then
+// entry (a & 7) | (b & 7) << 3 lists the offsets of the group's elements, two bits each (adj3_entry).
+DK_HD uint32_t adj3_entry(uint32_t idx) {
+    const uint32_t a3 = idx & 7u, b3 = (idx >> 3) & 7u;
+    uint32_t e = 0, j = 0;
+    for (uint32_t pos = 0; pos < 3u; ++pos) {
+        if ((a3 >> pos) & 1u) { e |= pos << (2u * j); j++; }
+        if ((a3 >> pos) & (b3 >> pos) & 1u) { e |= pos << (2u * j); j++; }
+    }
+    return e;
+}
+DK_HD uint32_t h2_select_adjacent_lut(const Hand2& h, uint32_t k, const uint32_t* __restrict__ adj3) {
+    uint32_t xa = h.a, xb = h.b, pos = 0, c;
+    c = popc(xa & 0xFFFu) + popc(xb & 0xFFFu); if (k >= c) { k -= c; xa >>= 12; xb >>= 12; pos = 12u; }
+    c = popc(xa & 0x3Fu) + popc(xb & 0x3Fu);   if (k >= c) { k -= c; xa >>= 6;  xb >>= 6;  pos += 6u; }
+    c = popc(xa & 7u) + popc(xb & 7u);         if (k >= c) { k -= c; xa >>= 3;  xb >>= 3;  pos += 3u; }
+    return pos + ((adj3[(xa & 7u) | ((xb & 7u) << 3)] >> (2u * k)) & 3u);
+}
+// k-th set bit (0-based, from the LSB) of a 4-bit mask
+DK_HD uint32_t select_lsb4(uint32_t e, uint32_t k) {
+    uint32_t pos = 0, seen = 0;
+#pragma unroll
+    for (uint32_t i = 0; i < 4u; ++i) { const uint32_t on = (e >> i) & 1u; pos = (on && seen == k) ? i : pos; seen += on; }
+    return pos;
+}
+// sample_assignment (:493-581).  Returns 0 ok, 1 dead end.  adj3 (optional): the table of h2_select_adjacent_lut in shared memory.
+DK_HD uint32_t doko_assign_sample(const AssignPrep& p, const RngKey& key, uint64_t hands_out[4], const uint32_t* __restrict__ adj3 = nullptr) {
     AssignState a;
     a.remaining = p.remaining;
+    a.n_remaining = h2_count(p.remaining);
 #pragma unroll
-    for (uint32_t i = 0; i < 4u; ++i) { a.allowed[i] = p.allowed[i]; a.len[i] = p.len[i]; a.hand[i].a = 0; a.hand[i].b = 0; }
+    for (uint32_t i = 0; i < 4u; ++i) {
+        a.len[i] = p.len[i]; a.hand[i].a = 0; a.hand[i].b = 0;
+        a.allow[i] = p.len[i] ? p.allowed[i].a : 0u;
+        a.cnt[i] = p.len[i] ? h2_count(p.allowed[i]) : ASSIGN_CNT_DONE;
+    }
     U4 blk; blk.x = blk.y = blk.z = blk.w = 0;
     uint32_t blk_id = 0xFFFFFFFFu, ord = 0, status = 0;
     // The body is data dependent and the lanes of a warp diverge in it, so it is kept small: the single-owner rule and the random rule
@@ -104,8 +138,7 @@ DK_HD uint32_t doko_assign_sample(const AssignPrep& p, const RngKey& key, uint64
         uint32_t player, c;
         // distribute_single_cards (:336-377): first remaining card (ascending id) with exactly one eligible seat — bit-parallel:
         // "exactly one of four" = odd parity minus the triples
-        const uint32_t e0 = a.len[0] ? a.allowed[0].a : 0u, e1 = a.len[1] ? a.allowed[1].a : 0u, e2 = a.len[2] ? a.allowed[2].a : 0u,
-                       e3 = a.len[3] ? a.allowed[3].a : 0u;
+        const uint32_t e0 = a.allow[0], e1 = a.allow[1], e2 = a.allow[2], e3 = a.allow[3];
         const uint32_t one = (e0 ^ e1 ^ e2 ^ e3) & ~((e0 & e1 & e2) | (e0 & e1 & e3) | (e0 & e2 & e3) | (e1 & e2 & e3)) & a.remaining.a;
         if (one) {
             c = ffs0(one);
@@ -117,22 +150,24 @@ DK_HD uint32_t doko_assign_sample(const AssignPrep& p, const RngKey& key, uint64
             uint32_t seat = 4u;
 #pragma unroll
             for (uint32_t i = 0; i < 4u; ++i)
-                if (seat == 4u && a.len[i] > 0u && a.len[i] == h2_count(a.allowed[i])) seat = i;
+                if (seat == 4u && a.len[i] == a.cnt[i]) seat = i;
             if (seat < 4u) {
-                Hand2 pend = seat == 0u ? a.allowed[0] : (seat == 1u ? a.allowed[1] : (seat == 2u ? a.allowed[2] : a.allowed[3]));
+                const uint32_t al = seat == 0u ? a.allow[0] : (seat == 1u ? a.allow[1] : (seat == 2u ? a.allow[2] : a.allow[3]));
+                Hand2 pend; pend.a = a.remaining.a & al; pend.b = a.remaining.b & al;
                 while (pend.a) { const uint32_t cc = ffs0(pend.a); h2_remove_one(pend, 1u << cc); doko_assign_distribute(a, seat, cc); }
                 continue;
             }
             // distribute_single_card_randomly (:419-456)
-            const uint32_t n = h2_count(a.remaining);
+            const uint32_t n = a.n_remaining;
             if (n == 0u) break;
             uint32_t w0, w1;
             { uint32_t o = ord++; if ((o >> 2) != blk_id) { blk_id = o >> 2; blk = rng_block(key, SITE_ASSIGN, blk_id); } w0 = u4_word(blk, o & 3u); }
-            c = h2_select_adjacent(a.remaining, mulhi(w0, n));
+            const uint32_t k = mulhi(w0, n);
+            c = adj3 ? h2_select_adjacent_lut(a.remaining, k, adj3) : h2_select_adjacent(a.remaining, k);
             const uint32_t e = doko_assign_eligible(a, 1u << c);
             if (e == 0u) { status = 1u; break; }            // `.choose(rng).unwrap()` on an empty list would panic
             { uint32_t o = ord++; if ((o >> 2) != blk_id) { blk_id = o >> 2; blk = rng_block(key, SITE_ASSIGN, blk_id); } w1 = u4_word(blk, o & 3u); }
-            player = select_lsb(e, mulhi(w1, popc(e)));
+            player = select_lsb4(e, mulhi(w1, popc(e)));
         }
         doko_assign_distribute(a, player, c);
     }

@@ -913,9 +913,11 @@ doko_assign_kernel(RngParams rp, uint64_t n_info, uint32_t samples, uint32_t spl
                    uint8_t* __restrict__ res_out, uint8_t* __restrict__ status_out) {
     __shared__ AssignPrep prep;
     __shared__ uint32_t res_word;
+    __shared__ uint32_t adj3[64];                                  // last level of the multiset rank select (assignment.cuh adj3_entry)
     const uint64_t i = blockIdx.x / splits;                        // `splits` blocks per info-state, see fdo_determinize_kernel
     const uint32_t part = blockIdx.x - (uint32_t)i * splits;
     if (i >= n_info) return;
+    if (threadIdx.x >= 64) adj3[threadIdx.x - 64] = adj3_entry(threadIdx.x - 64);
     if (threadIdx.x == 0) {
         alignas(16) dk_state s;
         load_state(states + i, s);
@@ -928,7 +930,7 @@ doko_assign_kernel(RngParams rp, uint64_t n_info, uint32_t samples, uint32_t spl
     for (uint32_t smp = part * MATCH_THREADS + threadIdx.x; smp < samples; smp += splits * MATCH_THREADS) {
         RngKey key = make_key(rp, i, rp.first_sub + smp, true);
         uint64_t h[4];
-        uint32_t st = doko_assign_sample(prep, key, h);
+        uint32_t st = doko_assign_sample(prep, key, h, adj3);
         uint64_t o = i * samples + smp;
         if (hands_out) {
             ulonglong2* dst = reinterpret_cast<ulonglong2*>(hands_out + 4 * o);

@@ -135,7 +135,14 @@ SIM_API int sim_playout_from_state(int engine, const dk_state* s, uint64_t seed,
 SIM_API uint32_t sim_fdo_determinize(const dk_state* s, uint64_t seed, uint64_t unit, uint32_t sample, uint32_t epoch, uint64_t hands[4], uint8_t res[4]) {
     dk::MatchPrep prep; dk::fdo_match_prepare(*s, prep);
     dk::RngKey key = make_key(seed, unit, epoch); key.unit_hi = sample;
-    return dk::fdo_match_sample(prep, key, hands, res);
+    // both forms of rule 4's rank select (compare / shift levels, and the kernel's 64-entry table) must give the same sample
+    uint32_t rank6[64];
+    for (uint32_t i = 0; i < 64u; ++i) rank6[i] = dk::rank_lut6_entry(i);
+    uint64_t h2[4]; uint8_t r2[4];
+    const uint32_t st2 = dk::fdo_match_sample(prep, key, h2, r2, rank6);
+    const uint32_t st = dk::fdo_match_sample(prep, key, hands, res);
+    if (st != st2 || std::memcmp(h2, hands, sizeof(h2)) != 0 || std::memcmp(r2, res, 4) != 0) return 0xFFFFFFFFu;
+    return st;
 }
 SIM_API uint32_t sim_fdo_leaf_rollout(const dk_state* s, uint64_t seed, uint64_t unit, uint32_t rollout, uint32_t epoch, int determinize, int32_t* points, uint32_t* steps) {
     dk::RngKey key = make_key(seed, unit, epoch); key.unit_hi = rollout;
@@ -160,7 +167,14 @@ SIM_API uint32_t sim_fdo_leaf_rollout(const dk_state* s, uint64_t seed, uint64_t
 SIM_API uint32_t sim_doko_assign(const dk_state* s, uint64_t seed, uint64_t unit, uint32_t sample, uint32_t epoch, uint64_t hands[4]) {
     dk::AssignPrep prep; dk::doko_assign_prepare(*s, prep);
     dk::RngKey key = make_key(seed, unit, epoch); key.unit_hi = sample;
-    return dk::doko_assign_sample(prep, key, hands);
+    // both forms of the multiset rank select (binary search / table for the last level, the kernel's) must give the same sample
+    uint32_t adj3[64];
+    for (uint32_t i = 0; i < 64u; ++i) adj3[i] = dk::adj3_entry(i);
+    uint64_t h2[4];
+    const uint32_t st2 = dk::doko_assign_sample(prep, key, h2, adj3);
+    const uint32_t st = dk::doko_assign_sample(prep, key, hands);
+    if (st != st2 || std::memcmp(h2, hands, sizeof(h2)) != 0) return 0xFFFFFFFFu;
+    return st;
 }
 
 SIM_API uint32_t sim_fdo_ann_bits(uint64_t seed, uint64_t unit, uint32_t epoch, uint32_t ord, uint32_t m) {
