@@ -57,13 +57,16 @@ DK_HD void doko_assign_prepare(const dk_state& s, AssignPrep& m) {
 // full): the eight population counts per iteration of distribute_exactly_as_per_hand's test and the per-seat multiset updates of
 // distribute_card become a compare and a decrement (same technique as the full-rules sampler, matching.cuh).
 constexpr uint32_t ASSIGN_CNT_DONE = 255u;
-struct AssignState { Hand2 remaining, hand[4]; uint32_t allow[4], len[4], cnt[4], n_remaining; };
+// The three HIDDEN seats are kept in absolute seat order in slots 0..2 (seat of slot j = j + (j >= observer), the order every rule
+// of the reference walks them in); the observer never receives a card, so carrying it through the loops as a fourth seat (first form)
+// cost a quarter of distribute_card and the wider "exactly one of four" mask.
+struct AssignState { Hand2 remaining, hand[3]; uint32_t allow[3], len[3], cnt[3], n_remaining; };
 
 // distribute_card (:284-316), branch-free: the receiving seat is selected by a mask
 DK_HD void doko_assign_distribute(AssignState& a, uint32_t player, uint32_t c) {
     const uint32_t bit = 1u << c;
 #pragma unroll
-    for (uint32_t i = 0; i < 4u; ++i) {
+    for (uint32_t i = 0; i < 3u; ++i) {
         const bool mine = i == player;
         h2_add(a.hand[i], mine ? bit : 0u);
         a.len[i] -= mine ? 1u : 0u;
@@ -78,7 +81,7 @@ DK_HD void doko_assign_distribute(AssignState& a, uint32_t player, uint32_t c) {
 DK_HD uint32_t doko_assign_eligible(const AssignState& a, uint32_t bit) {
     uint32_t m = 0;
 #pragma unroll
-    for (uint32_t i = 0; i < 4u; ++i) if (a.allow[i] & bit) m |= 1u << i;
+    for (uint32_t i = 0; i < 3u; ++i) if (a.allow[i] & bit) m |= 1u << i;
     return m;
 }
 // k-th element (0-based) of a multiset listed in ascending card id with doubles adjacent.
@@ -111,11 +114,11 @@ DK_HD uint32_t h2_select_adjacent_lut(const Hand2& h, uint32_t k, const uint32_t
     c = popc(xa & 7u) + popc(xb & 7u);         if (k >= c) { k -= c; xa >>= 3;  xb >>= 3;  pos += 3u; }
     return pos + ((adj3[(xa & 7u) | ((xb & 7u) << 3)] >> (2u * k)) & 3u);
 }
-// k-th set bit (0-based, from the LSB) of a 4-bit mask
-DK_HD uint32_t select_lsb4(uint32_t e, uint32_t k) {
+// k-th set bit (0-based, from the LSB) of a 3-bit mask
+DK_HD uint32_t select_lsb3(uint32_t e, uint32_t k) {
     uint32_t pos = 0, seen = 0;
 #pragma unroll
-    for (uint32_t i = 0; i < 4u; ++i) { const uint32_t on = (e >> i) & 1u; pos = (on && seen == k) ? i : pos; seen += on; }
+    for (uint32_t i = 0; i < 3u; ++i) { const uint32_t on = (e >> i) & 1u; pos = (on && seen == k) ? i : pos; seen += on; }
     return pos;
 }
 // sample_assignment (:493-581).  Returns 0 ok, 1 dead end.  adj3 (optional): the table of h2_select_adjacent_lut in shared memory.
@@ -123,11 +126,16 @@ DK_HD uint32_t doko_assign_sample(const AssignPrep& p, const RngKey& key, uint64
     AssignState a;
     a.remaining = p.remaining;
     a.n_remaining = h2_count(p.remaining);
+    const uint32_t obs = p.observer;
 #pragma unroll
-    for (uint32_t i = 0; i < 4u; ++i) {
-        a.len[i] = p.len[i]; a.hand[i].a = 0; a.hand[i].b = 0;
-        a.allow[i] = p.len[i] ? p.allowed[i].a : 0u;
-        a.cnt[i] = p.len[i] ? h2_count(p.allowed[i]) : ASSIGN_CNT_DONE;
+    for (uint32_t j = 0; j < 3u; ++j) {
+        // slot j = absolute seat j + (j >= obs): a select over compile-time seats, no indexed access
+        const bool up = j >= obs;
+        const uint32_t ln = up ? p.len[j + 1u] : p.len[j];
+        const Hand2 al = up ? p.allowed[j + 1u] : p.allowed[j];
+        a.len[j] = ln; a.hand[j].a = 0; a.hand[j].b = 0;
+        a.allow[j] = ln ? al.a : 0u;
+        a.cnt[j] = ln ? h2_count(al) : ASSIGN_CNT_DONE;
     }
     U4 blk; blk.x = blk.y = blk.z = blk.w = 0;
     uint32_t blk_id = 0xFFFFFFFFu, ord = 0, status = 0;
@@ -137,22 +145,22 @@ DK_HD uint32_t doko_assign_sample(const AssignPrep& p, const RngKey& key, uint64
     for (;;) {
         uint32_t player, c;
         // distribute_single_cards (:336-377): first remaining card (ascending id) with exactly one eligible seat — bit-parallel:
-        // "exactly one of four" = odd parity minus the triples
-        const uint32_t e0 = a.allow[0], e1 = a.allow[1], e2 = a.allow[2], e3 = a.allow[3];
-        const uint32_t one = (e0 ^ e1 ^ e2 ^ e3) & ~((e0 & e1 & e2) | (e0 & e1 & e3) | (e0 & e2 & e3) | (e1 & e2 & e3)) & a.remaining.a;
+        // "exactly one of the three hidden seats" = odd parity minus "all three"
+        const uint32_t e0 = a.allow[0], e1 = a.allow[1], e2 = a.allow[2];
+        const uint32_t one = (e0 ^ e1 ^ e2) & ~(e0 & e1 & e2) & a.remaining.a;
         if (one) {
             c = ffs0(one);
             const uint32_t bit = 1u << c;
-            player = (e0 & bit) ? 0u : ((e1 & bit) ? 1u : ((e2 & bit) ? 2u : 3u));
+            player = (e0 & bit) ? 0u : ((e1 & bit) ? 1u : 2u);
         } else {
             // distribute_exactly_as_per_hand (:379-417): the first seat (ascending) whose open slots equal its list takes the whole list
             // (a snapshot; ascending card id, the second copy of a double right after the first)
-            uint32_t seat = 4u;
+            uint32_t seat = 3u;
 #pragma unroll
-            for (uint32_t i = 0; i < 4u; ++i)
-                if (seat == 4u && a.len[i] == a.cnt[i]) seat = i;
-            if (seat < 4u) {
-                const uint32_t al = seat == 0u ? a.allow[0] : (seat == 1u ? a.allow[1] : (seat == 2u ? a.allow[2] : a.allow[3]));
+            for (uint32_t i = 0; i < 3u; ++i)
+                if (seat == 3u && a.len[i] == a.cnt[i]) seat = i;
+            if (seat < 3u) {
+                const uint32_t al = seat == 0u ? a.allow[0] : (seat == 1u ? a.allow[1] : a.allow[2]);
                 Hand2 pend; pend.a = a.remaining.a & al; pend.b = a.remaining.b & al;
                 while (pend.a) { const uint32_t cc = ffs0(pend.a); h2_remove_one(pend, 1u << cc); doko_assign_distribute(a, seat, cc); }
                 continue;
@@ -167,13 +175,17 @@ DK_HD uint32_t doko_assign_sample(const AssignPrep& p, const RngKey& key, uint64
             const uint32_t e = doko_assign_eligible(a, 1u << c);
             if (e == 0u) { status = 1u; break; }            // `.choose(rng).unwrap()` on an empty list would panic
             { uint32_t o = ord++; if ((o >> 2) != blk_id) { blk_id = o >> 2; blk = rng_block(key, SITE_ASSIGN, blk_id); } w1 = u4_word(blk, o & 3u); }
-            player = select_lsb4(e, mulhi(w1, popc(e)));
+            player = select_lsb3(e, mulhi(w1, popc(e)));
         }
         doko_assign_distribute(a, player, c);
     }
+    uint64_t hs[3];
 #pragma unroll
-    for (uint32_t i = 0; i < 4u; ++i) hands_out[i] = (uint64_t)a.hand[i].a | ((uint64_t)a.hand[i].b << 24);
-    hands_out[p.observer] = (uint64_t)p.obs_a | ((uint64_t)p.obs_b << 24);     // hand_from_vec(hand_to_vec(own)): canonical copy order
+    for (uint32_t j = 0; j < 3u; ++j) hs[j] = (uint64_t)a.hand[j].a | ((uint64_t)a.hand[j].b << 24);
+    const uint64_t own = (uint64_t)p.obs_a | ((uint64_t)p.obs_b << 24);     // hand_from_vec(hand_to_vec(own)): canonical copy order
+#pragma unroll
+    for (uint32_t seat = 0; seat < 4u; ++seat)
+        hands_out[seat] = seat == obs ? own : (seat == 0u ? hs[0] : (seat == 1u ? (obs == 0u ? hs[0] : hs[1]) : (seat == 2u ? (obs <= 1u ? hs[1] : hs[2]) : hs[2])));
     return status;
 }
 
