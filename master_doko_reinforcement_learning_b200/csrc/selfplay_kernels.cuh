@@ -344,13 +344,13 @@ pack_replay_records_kernel(unsigned long long n_rows, const long long* __restric
 // with `determinize` the root state is first replaced by determinization (first_sub + d) of the info-state (the dk_determinize stream).
 // Iteration `it` runs on the Philox unit (first_id + root, (first_sub + d) * iterations + it).
 #ifndef DK_UCT_TREE_BLOCKS
-#define DK_UCT_TREE_BLOCKS 8
+#define DK_UCT_TREE_BLOCKS 6        // 80 registers, no spills: since the batch runs in parts (cabi.cu) a part still fits one wave (+2-4 %)
 #endif
 #ifndef DK_UCT_EXPAND_IDX
 #define DK_UCT_EXPAND_IDX true      // the expansion's record in local memory (128 B, no spills): the register form spilled 700 B at 64 registers
 #endif
 #ifndef DK_UCT_ROLLOUT_BLOCKS
-#define DK_UCT_ROLLOUT_BLOCKS 4      // 64 registers: 1024 trees resident per SM (3 blocks of 80 registers measured 7 % slower at 131 072 trees)
+#define DK_UCT_ROLLOUT_BLOCKS 3      // 80 registers, no spills (as one launch over 131 072 trees 4 blocks of 64 registers were 7 % faster: 1.15 waves; in parts every launch is one wave)
 #endif
 constexpr int UCT_THREADS = 128;
 __device__ __forceinline__ RngKey uct_iteration_key(const RngParams& rp, uint64_t t, uint32_t trees_per_root, uint32_t iterations, uint32_t it) {
