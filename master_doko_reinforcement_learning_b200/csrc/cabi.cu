@@ -149,7 +149,10 @@ dk_status dk_init(int device, dk_ctx** out) {
         for (uint32_t i = 0; i < dk::CARD_LUT_WORDS; ++i) lut[i] = dk::lut_word(i);
         std::vector<uint64_t> sel(dk::SEL12_WORDS / 2);
         for (uint32_t h = 0; h < dk::SEL12_WORDS / 2; ++h) sel[h] = dk::sel12_entry(h);
+        std::vector<uint32_t> ann(dk::ANN_LUT_WORDS);
+        for (uint32_t i = 0; i < dk::ANN_LUT_WORDS; ++i) ann[i] = dk::lut_word(dk::ANN_LUT_BASE + i);
         if (cudaMemcpyToSymbol(dk::g_card_lut, lut.data(), lut.size() * sizeof(uint32_t)) != cudaSuccess ||
+            cudaMemcpyToSymbol(dk::g_ann_lut, ann.data(), ann.size() * sizeof(uint32_t)) != cudaSuccess ||
             cudaMemcpyToSymbol(dk::g_sel12, sel.data(), sel.size() * sizeof(uint64_t)) != cudaSuccess) { cudaStreamDestroy(ctx->stream); delete ctx; return DK_ERR_CUDA; }
     }
     *out = ctx;

@@ -137,21 +137,26 @@ DK_HD uint32_t rank_lut6_entry(uint32_t b) {
     return e;
 }
 // The lookup tables of the playout kernels, one word array: built once on the host (lut_word, fdo_rules.cuh), kept in device memory
-// and copied into shared memory by every block (kernels.cuh stage_card_lut).
-//   [0,24) card attributes (card_lut_entry) | [24,31) fdo_thr_lut_word | [32,96) rank_lut6_entry |
-//   [96,288) call thresholds of both teams by (wedding shift, re level, kontra level) (fdo_thr2_lut_word) |
-//   [288,352) 256 bytes: who calls in a segment of an announcement round, by (eligible seats, decision bits) (fdo_seg_lut_byte)
-constexpr uint32_t CARD_LUT_WORDS = 892u;
+// and copied into shared memory by every block (kernels.cuh fill_card_lut / fill_sel12 / fill_ann_lut).  Three regions, so that a
+// kernel stages only what it reads:
+//   CARD   [0,24) card attributes (card_lut_entry) | [24,31) fdo_thr_lut_word | [32,96) rank_lut6_entry |
+//          [96,1176) 9 game types x 5 lead classes x 24 cards x 32 bit: the card's record for the trick accumulator (pow_lut_entry)
+//   SEL12  [1176,9368) the 12-bit rank-select table (4096 x 64 bit, sel12_entry) of the kernels that can afford 32 KB more shared
+//          memory per block; the others pick cards through the 64-entry table above
+//   ANN    [9368,9560) call thresholds of both teams by (wedding shift, re level, kontra level) (fdo_thr2_lut_word) |
+//          [9560,9624) 256 bytes: who calls in a segment of an announcement round, by (eligible seats, decision bits)
+//          (fdo_seg_lut_byte) — read only by the announcement replay, i.e. by the kernels that report game steps or play with calls
+constexpr uint32_t CARD_LUT_WORDS = 1176u;
 constexpr uint32_t THR_LUT_BASE = 24u;
 constexpr uint32_t RANK_LUT_BASE = 32u;
-constexpr uint32_t THR2_LUT_BASE = 96u;
-constexpr uint32_t SEG_LUT_BASE = 288u;
-// Kernels that can afford 32 KB more shared memory per block (the fresh-game playouts) append the 12-bit rank-select table
-// (4096 x 64 bit, sel12_entry) at word SEL12_LUT_BASE; the others pick cards through the 64-entry table above.
-//   [352,892) 9 game types x 5 lead classes x 24 cards x 16 bit: strength of a card in a trick + its eyes (pow_lut_entry)
-constexpr uint32_t POW_LUT_BASE = 352u;
-constexpr uint32_t SEL12_LUT_BASE = 892u;
+constexpr uint32_t POW_LUT_BASE = 96u;
+constexpr uint32_t SEL12_LUT_BASE = 1176u;
 constexpr uint32_t SEL12_WORDS = 8192u;
+constexpr uint32_t ANN_LUT_BASE = SEL12_LUT_BASE + SEL12_WORDS;
+constexpr uint32_t ANN_LUT_WORDS = 256u;
+constexpr uint32_t THR2_LUT_BASE = ANN_LUT_BASE;
+constexpr uint32_t SEG_LUT_BASE = ANN_LUT_BASE + 192u;
+constexpr uint32_t FULL_LUT_WORDS = ANN_LUT_BASE + ANN_LUT_WORDS;
 DK_HD uint32_t select_lsb24_lut(uint32_t x, uint32_t k, const uint32_t* __restrict__ lut) {
     uint32_t pos = 0, c;
     c = popc(x & 0xFFFu); if (k >= c) { k -= c; x >>= 12; pos = 12u; }
@@ -243,21 +248,34 @@ DK_HD uint32_t card_lut_entry(uint32_t c) {
     return eyes | ((1u + eyes) << 4) | ((16u + tp) << 8) | (suit << 13);
 }
 // Strength-in-trick table: row (game type, lead class) x card, lead class = suit of the first card (0..3) when it is a plain card,
-// 4 when it is a trump.  Entry = card_power(card, trump mask of the game type, follow mask of the lead class) | eyes << 8: one 16-bit
-// shared-memory load per card replaces the select chain of card_power_lut (7 ALU instructions per card on the pipe that limits the
-// playout kernels).  pow_row = index of the row's first entry.
+// 4 when it is a trump.  One 32-bit shared-memory load per card gives everything the trick accumulator needs, laid out so that the
+// accumulator is ONE max, ONE add and one multiply-add per card (the ALU pipe limits the playout kernels; the compare / three selects
+// / mask of the first form were 5 of its ~28 ALU instructions per card step):
+//   bits 0-7 eyes | bit 8 the card is a ♦A | bits 9-10 zero (the caller ORs in 3 - position) | bits 11-15 card id | bits 16-23
+//   card_power(card, trump mask of the game type, follow mask of the lead class).
+// max over (entry | (3 - k) << 9) of the four cards = the winning card: the strength decides; cards of equal positive strength are
+// copies of one card type (every strength > 0 belongs to one type within a row), so their low bits are equal and the position field
+// makes the FIRST of them win (strict `>` in the reference); a strength-0 card never beats the first card, whose strength is positive.
+constexpr uint32_t POW_K_SHIFT = 9u, POW_CARD_SHIFT = 11u, POW_PW_SHIFT = 16u, POW_FOX_BIT = 0x100u;
 DK_HD uint32_t pow_lut_entry(uint32_t gt, uint32_t cls, uint32_t c) {
     const uint32_t trump = trump_mask_for_game_type(gt);
     const uint32_t follow = cls == 4u ? trump : ((0x3Fu << (6u * cls)) & ~trump);
     const uint32_t suit = card_suit(c);
-    return card_power(c, trump, follow) | (card_eyes_by_rank(c - 6u * suit) << 8);
+    return card_eyes_by_rank(c - 6u * suit) | (c == 5u ? POW_FOX_BIT : 0u) | (c << POW_CARD_SHIFT) | (card_power(c, trump, follow) << POW_PW_SHIFT);
+}
+// The same record from a card played earlier (the bridge from a stored record to the playout form).
+DK_HD uint32_t pow_entry_of(uint32_t c, uint32_t trump, uint32_t follow) {
+    const uint32_t suit = card_suit(c);
+    return card_eyes_by_rank(c - 6u * suit) | (c == 5u ? POW_FOX_BIT : 0u) | (c << POW_CARD_SHIFT) | (card_power(c, trump, follow) << POW_PW_SHIFT);
 }
 DK_HD uint32_t pow_row(uint32_t gt, uint32_t first_card, uint32_t first_suit, uint32_t trump) {
     return (gt * 5u + (((trump >> first_card) & 1u) ? 4u : first_suit)) * 24u;
 }
-DK_HD uint32_t pow_lookup(const uint32_t* __restrict__ lut, uint32_t row, uint32_t c) {
-    return reinterpret_cast<const uint16_t*>(lut + POW_LUT_BASE)[row + c];
-}
+DK_HD uint32_t pow_lookup(const uint32_t* __restrict__ lut, uint32_t row, uint32_t c) { return lut[POW_LUT_BASE + row + c]; }
+// Trick accumulator shared by both engines: `best` = max of (entry | (3 - k) << 9), `acc` = sum of the entries (its low byte is the
+// trick's eyes: at most 44, no carry out of the byte matters), `fox` = sum of (entry & ♦A bit) << k.
+DK_HD uint32_t pow_best_k(uint32_t best) { return 3u - ((best >> POW_K_SHIFT) & 3u); }
+DK_HD uint32_t pow_best_card(uint32_t best) { return (best >> POW_CARD_SHIFT) & 31u; }
 DK_HD uint32_t follow_mask_lut(uint32_t c, uint32_t entry, uint32_t trump) {
     uint32_t suit_cards = 0x3Fu << (6u * (entry >> 13));
     return ((trump >> c) & 1u) ? trump : (suit_cards & ~trump);

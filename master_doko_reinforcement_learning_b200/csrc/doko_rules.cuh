@@ -54,7 +54,8 @@ DK_HD void doko_finish_reservations(DokoLive& g, const uint32_t res_action[4]) {
     }
 }
 
-struct DokoTrickAcc { uint32_t follow, best, bestk, teyes, prow; };   // prow: row of the strength table (game type 0 = the rs-doko trumps)
+struct DokoTrickAcc { uint32_t follow, best, acc, prow; };   // best / acc: dk_common.cuh pow_lut_entry; prow: row of that table (game type 0 = the rs-doko trumps)
+DK_HD void doko_trick_acc_clear(DokoTrickAcc& a) { a.follow = 0; a.best = 0; a.acc = 0; a.prow = 0; }
 
 // Card step of frame seat K (rs-doko/src/action/allowed_actions.rs:153-192, state/state.rs:194-252).
 template <int K, bool SEL12 = false>
@@ -68,22 +69,23 @@ DK_HD uint32_t doko_card_step(DokoLive& g, uint32_t& h, DokoTrickAcc& a, uint32_
     g.dup ^= dbl;
     h ^= bit ^ dbl;
     if (K == 0) { const uint32_t e = lut[c]; a.follow = follow_mask_lut(c, e, DOKO_TRUMP_MASK); a.prow = pow_row(0u, c, e >> 13, DOKO_TRUMP_MASK); }
-    const uint32_t v = pow_lookup(lut, a.prow, c), pw = v & 255u;
-    if (K == 0 || pw > a.best) { a.best = pw; a.bestk = (uint32_t)K; }
-    a.teyes += v >> 8;
+    const uint32_t v = pow_lookup(lut, a.prow, c), cand = v | ((3u - (uint32_t)K) << POW_K_SHIFT);
+    a.best = (K == 0 || cand > a.best) ? cand : a.best;
+    a.acc += v;
     g.steps++;
     return c;
 }
 
 DK_HD void doko_trick_done(DokoLive& g, const DokoTrickAcc& a, uint32_t t) {
-    uint32_t w = (g.base + a.bestk) & 3u;
-    g.eyes += a.teyes << (8u * w);
+    const uint32_t bestk = pow_best_k(a.best);
+    uint32_t w = (g.base + bestk) & 3u;
+    g.eyes += (a.acc & 255u) << (8u * w);
     g.ntricks += 1u << (4u * w);
     if (g.team_tag == TEAM_WEDDING_UNSOLVED) {
         if (w != g.wed_seat) { g.team_tag = TEAM_WEDDING_SOLVED; g.solved_idx = t; g.re_mask = (1u << g.wed_seat) | (1u << w); }
         else if (t == 2u) { g.team_tag = TEAM_WEDDING_SOLVED; g.solved_idx = 2u; g.re_mask = 1u << g.wed_seat; }
     }
-    doko_rotate(g, a.bestk);
+    doko_rotate(g, bestk);
 }
 
 // calculate_end_of_game_stats (rs-doko/src/stats/stats.rs:25-135): Re wins iff re_eyes > kontra_eyes (120:120 → Kontra);
@@ -129,7 +131,7 @@ DK_HD void doko_play_to_end(DokoLive& g, const RngKey& key, const DokoResume* rs
     for (uint32_t t = t0; t < 12u; ++t) {
         U4 blk = rng_block(key, SITE_CARD, t);
         DokoTrickAcc a;
-        a.follow = 0; a.best = 0; a.bestk = 0; a.teyes = 0; a.prow = 0;
+        doko_trick_acc_clear(a);
         uint32_t k0 = 0;
         bool first = !FRESH && t == t0;
         if (first) { k0 = rs->k0; if (k0 > 0u) a = rs->acc; }

@@ -78,18 +78,15 @@ DK_HD uint32_t fdo_seg_lut_byte(uint32_t win, uint32_t hit) {
     while (!((wj >> d) & 1u)) d++;
     return d | (j << 2);
 }
-// Word i of the shared lookup table (layout: dk_common.cuh CARD_LUT_WORDS).
+// Word i of the shared lookup table (layout: dk_common.cuh CARD_LUT_WORDS; the SEL12 region is filled from sel12_entry).
 DK_HD uint32_t lut_word(uint32_t i) {
     if (i < 24u) return card_lut_entry(i);
     if (i < 31u) return fdo_thr_lut_word(i - THR_LUT_BASE);
     if (i < RANK_LUT_BASE) return 0u;
-    if (i < THR2_LUT_BASE) return rank_lut6_entry(i - RANK_LUT_BASE);
+    if (i < POW_LUT_BASE) return rank_lut6_entry(i - RANK_LUT_BASE);
+    if (i < CARD_LUT_WORDS) { const uint32_t idx = i - POW_LUT_BASE; return pow_lut_entry(idx / 120u, (idx / 24u) % 5u, idx % 24u); }
+    if (i < THR2_LUT_BASE) return 0u;                    // (SEL12 region)
     if (i < SEG_LUT_BASE) return fdo_thr2_lut_word(i - THR2_LUT_BASE);
-    if (i >= POW_LUT_BASE) {                             // two 16-bit entries per word
-        uint32_t v = 0;
-        for (uint32_t b = 0; b < 2u; ++b) { const uint32_t idx = 2u * (i - POW_LUT_BASE) + b; v |= pow_lut_entry(idx / 120u, (idx / 24u) % 5u, idx % 24u) << (16u * b); }
-        return v;
-    }
     uint32_t v = 0;
     for (uint32_t b = 0; b < 4u; ++b) { const uint32_t idx = 4u * (i - SEG_LUT_BASE) + b; v |= fdo_seg_lut_byte(idx >> 4, idx & 15u) << (8u * b); }
     return v;
@@ -384,7 +381,8 @@ DK_HD void fdo_replay_announcements(FdoLive& g, const RngKey& key, uint32_t star
     g.re_low = re_low; g.ko_low = ko_low; g.steps += ord - g.ann_count; g.ann_count = ord;
 }
 
-struct TrickAcc { uint32_t follow, best, bestk, bestc, teyes, foxm, prow; };   // prow: the trick's row of the strength table (pow_row)
+struct TrickAcc { uint32_t follow, best, acc, fox, prow; };   // best / acc / fox: dk_common.cuh pow_lut_entry; prow: the trick's row of that table (pow_row)
+DK_HD void trick_acc_clear(TrickAcc& a) { a.follow = 0; a.best = 0; a.acc = 0; a.fox = 0; a.prow = 0; }
 
 // Card step of frame seat K (compile-time) with hand register `h` (action/allowed_actions.rs:97-140, state.rs:274-357).
 template <int K, bool SEL12 = false>
@@ -402,10 +400,10 @@ DK_HD void fdo_card_step(FdoLive& g, uint32_t& h, TrickAcc& a, uint32_t word, bo
     g.dup ^= dbl;
     h ^= bit ^ dbl;
     if (K == 0) { const uint32_t e = lut[c]; a.follow = follow_mask_lut(c, e, g.trump); a.prow = pow_row(g.gt, c, e >> 13, g.trump); }
-    const uint32_t v = pow_lookup(lut, a.prow, c), pw = v & 255u;
-    if (K == 0 || pw > a.best) { a.best = pw; a.bestk = (uint32_t)K; a.bestc = c; }   // strict: first of equals wins
-    a.teyes += v >> 8;
-    if (c == CARD_DA) a.foxm |= 1u << K;
+    const uint32_t v = pow_lookup(lut, a.prow, c), cand = v | ((3u - (uint32_t)K) << POW_K_SHIFT);
+    a.best = (K == 0 || cand > a.best) ? cand : a.best;               // one max: first of equals wins through the position field
+    a.acc += v;
+    a.fox += (v & POW_FOX_BIT) * (1u << K);
     g.steps++;
 }
 
@@ -418,18 +416,19 @@ DK_HD uint32_t fdo_fox_record(uint32_t foxes, uint32_t foxm, uint32_t lead, uint
 
 // Book-keeping when a trick is complete (state.rs:293-352, team/team_logic.rs:59-112, additional_points/*.rs).
 DK_HD void fdo_trick_done(FdoLive& g, const TrickAcc& a, uint32_t t) {
-    uint32_t w = (g.base + a.bestk) & 3u;
-    g.eyes += a.teyes << (8u * w);
+    const uint32_t bestk = pow_best_k(a.best), teyes = a.acc & 255u, foxm = (a.fox >> 8) & 15u;
+    uint32_t w = (g.base + bestk) & 3u;
+    g.eyes += teyes << (8u * w);
     g.ntricks += 1u << (4u * w);
-    if (a.teyes >= 40u) g.dkc += 1u << (4u * w);
-    g.foxes = fdo_fox_record(g.foxes, a.foxm, g.base, w);
+    if (teyes >= 40u) g.dkc += 1u << (4u * w);
+    g.foxes = fdo_fox_record(g.foxes, foxm, g.base, w);
     if (g.team_tag == TEAM_WEDDING_UNSOLVED) {
         if (w != g.wed_seat) { g.team_tag = TEAM_WEDDING_SOLVED; g.solved_idx = t; g.re_mask = (1u << g.wed_seat) | (1u << w); }
         else if (t == 2u) { g.team_tag = TEAM_WEDDING_SOLVED; g.solved_idx = 2u; g.re_mask = 1u << g.wed_seat; }
     }
-    if (t == 11u) g.karl = a.bestc == CARD_CJ ? 1u : 0u;
+    if (t == 11u) g.karl = pow_best_card(a.best) == CARD_CJ ? 1u : 0u;
     g.last_winner = w;
-    fdo_rotate(g, a.bestk);
+    fdo_rotate(g, bestk);
 }
 
 // Final scoring from the accumulated trackers → player_points per ABSOLUTE seat.
@@ -468,7 +467,9 @@ struct FdoResume {
 };
 
 // Plays the game to the end.  FRESH: hands/base already set by the deal, nothing played yet.
-template <bool WITH_ANN, bool FRESH, bool SEL12 = false>
+// STEPS = false (only with the no-announcement policy): the caller wants the points only, so the announcement rounds — which then
+// change nothing but the step count — are not replayed and the ANN region of the table is not needed (leaf rollouts, PIMC, UCT).
+template <bool WITH_ANN, bool FRESH, bool SEL12 = false, bool STEPS = true>
 DK_HD void fdo_play_to_end(FdoLive& g, const RngKey& key, const FdoResume* rs, const uint32_t* __restrict__ lut) {
     uint32_t n_res = FRESH ? 0u : rs->n_res;
     if (n_res < 4u) {
@@ -491,7 +492,7 @@ DK_HD void fdo_play_to_end(FdoLive& g, const RngKey& key, const FdoResume* rs, c
         starts |= g.base << (2u * t);
         const U4 blk = rng_block(key, SITE_CARD, t);
         TrickAcc a;
-        a.follow = 0; a.best = 0; a.bestk = 0; a.bestc = 0; a.teyes = 0; a.foxm = 0; a.prow = 0;
+        trick_acc_clear(a);
         const uint32_t k0 = rs->k0;
         if (k0 > 0u) a = rs->acc;
         const bool last = t == 11u;
@@ -506,7 +507,7 @@ DK_HD void fdo_play_to_end(FdoLive& g, const RngKey& key, const FdoResume* rs, c
         starts |= g.base << (2u * t);
         const U4 blk = rng_block(key, SITE_CARD, t);
         TrickAcc a;
-        a.follow = 0; a.best = 0; a.bestk = 0; a.bestc = 0; a.teyes = 0; a.foxm = 0; a.prow = 0;
+        trick_acc_clear(a);
         const bool last = t == 11u;
         fdo_card_step<0, SEL12>(g, g.h0, a, blk.x, last, lut);
         fdo_card_step<1, SEL12>(g, g.h1, a, blk.y, last, lut);
@@ -515,6 +516,7 @@ DK_HD void fdo_play_to_end(FdoLive& g, const RngKey& key, const FdoResume* rs, c
         fdo_trick_done(g, a, t);
     }
     // announcement rounds (see fdo_replay_announcements): fresh games start with the round before card 0
+    if (!WITH_ANN && !STEPS) return;
     if (FRESH) fdo_replay_announcements<WITH_ANN>(g, key, starts, 0u, starts & 3u, 0u, lut);
     else fdo_replay_announcements<WITH_ANN>(g, key, starts, rs->ann_ci, rs->ann_p, rs->ann_turns, lut);
 }

@@ -38,10 +38,14 @@ struct SharedDeckT {
 };
 using SharedDeck = SharedDeckT<PLAYOUT_THREADS>;
 
-// The lookup tables (dk_common.cuh CARD_LUT_WORDS; 1.4 KB) live in device memory, written once per context by dk_init from the host
+// The lookup tables (dk_common.cuh CARD_LUT_WORDS ...; 4.7 KB + 32 KB + 1 KB) live in device memory, written once per context by dk_init from the host
 // evaluation of lut_word; every block copies them into shared memory with coalesced loads (L2 hits).
 __device__ uint32_t g_card_lut[CARD_LUT_WORDS];
 __device__ uint4 g_sel12[SEL12_WORDS / 4];                           // the 12-bit rank-select table (sel12_entry), two entries per uint4
+__device__ uint32_t g_ann_lut[ANN_LUT_WORDS];                        // the announcement replay's tables (ANN region)
+__device__ __forceinline__ void fill_ann_lut(uint32_t* lut) {        // lut: FULL_LUT_WORDS words; caller syncs
+    for (uint32_t i = threadIdx.x; i < ANN_LUT_WORDS; i += blockDim.x) lut[ANN_LUT_BASE + i] = g_ann_lut[i];
+}
 __device__ __forceinline__ void fill_card_lut(uint32_t* lut) {       // caller syncs
     for (uint32_t i = threadIdx.x; i < CARD_LUT_WORDS; i += blockDim.x) lut[i] = g_card_lut[i];
 }
@@ -132,16 +136,17 @@ constexpr int FDO_FRESH_THREADS = DK_FDO_FRESH_THREADS;
 #ifndef DK_FDO_FRESH_BLOCKS
 #define DK_FDO_FRESH_BLOCKS 3
 #endif
-constexpr uint32_t FDO_FRESH_SMEM_BYTES = 4u * (CARD_LUT_WORDS + SEL12_WORDS + 12u * FDO_FRESH_THREADS);   // dynamic: above the 48 KB static limit
+constexpr uint32_t FDO_FRESH_SMEM_BYTES = 4u * (FULL_LUT_WORDS + 12u * FDO_FRESH_THREADS);   // dynamic: above the 48 KB static limit
 template <bool WITH_ANN>
 __global__ void __launch_bounds__(FDO_FRESH_THREADS, DK_FDO_FRESH_BLOCKS)
 fdo_playout_fresh_kernel(RngParams rp, uint64_t n, void* __restrict__ points, void* __restrict__ steps, uint32_t mode, unsigned long long* __restrict__ stats) {
     extern __shared__ __align__(16) uint32_t fresh_smem[];
     __shared__ BlockStats bstats;
-    uint32_t* lut = fresh_smem;                                        // CARD_LUT_WORDS + SEL12_WORDS words (16-byte aligned, SEL12 part 8-byte aligned)
-    uint32_t* smem = fresh_smem + CARD_LUT_WORDS + SEL12_WORDS;        // the shuffle scratch: 12 words per thread, word-interleaved
+    uint32_t* lut = fresh_smem;                                        // FULL_LUT_WORDS words (16-byte aligned, SEL12 part 8-byte aligned)
+    uint32_t* smem = fresh_smem + FULL_LUT_WORDS;                      // the shuffle scratch: 12 words per thread, word-interleaved
     fill_card_lut(lut);
     fill_sel12(lut);
+    fill_ann_lut(lut);
     if (stats) block_stats_clear(bstats);
     __syncthreads();
     uint64_t i = (uint64_t)blockIdx.x * FDO_FRESH_THREADS + threadIdx.x;
@@ -838,10 +843,11 @@ template <int ENGINE, bool WITH_ANN>
 __global__ void __launch_bounds__(PLAYOUT_STATE_THREADS)
 playout_state_kernel(RngParams rp, uint64_t n, const dk_state* __restrict__ states, uint32_t per_unit, void* __restrict__ points,
                      void* __restrict__ steps, uint32_t mode, unsigned long long* __restrict__ stats) {
-    __shared__ __align__(16) uint32_t lut[CARD_LUT_WORDS + SEL12_WORDS];
+    __shared__ __align__(16) uint32_t lut[FULL_LUT_WORDS];
     __shared__ BlockStats bstats;
     fill_card_lut(lut);
     fill_sel12(lut);
+    fill_ann_lut(lut);
     if (stats) block_stats_clear(bstats);
     __syncthreads();
     const uint64_t i_raw = (uint64_t)blockIdx.x * PLAYOUT_STATE_THREADS + threadIdx.x;
@@ -965,7 +971,7 @@ fdo_leaf_rollouts_kernel(RngParams rp, uint64_t leaf0, uint64_t n_leaves, uint32
     __shared__ FdoResume resume0;
     __shared__ int live_ok;
     __shared__ int red[4];
-    __shared__ __align__(16) uint32_t lut[CARD_LUT_WORDS + SEL12_WORDS];   // the full table set, 12-bit rank select included
+    __shared__ __align__(16) uint32_t lut[CARD_LUT_WORDS + SEL12_WORDS];   // card tables + 12-bit rank select; no ANN region: only the points are wanted
     fill_card_lut(lut);
     fill_sel12(lut);
     // `splits` blocks share one leaf when there are fewer leaves than one wave of blocks (rollout r belongs to block
@@ -1004,11 +1010,11 @@ fdo_leaf_rollouts_kernel(RngParams rp, uint64_t leaf0, uint64_t n_leaves, uint32
 #pragma unroll
                 for (uint32_t k = 0; k < 3u; ++k) if (k < rs.n_res) rs.res_action[k] = fdo_action_from_res_code((res4 >> (8u * ((base + k) & 3u))) & 255u);
             }
-            fdo_play_to_end<false, false, true>(g, key, &rs, lut);
+            fdo_play_to_end<false, false, true, false>(g, key, &rs, lut);
             fdo_final_points(g, p);
         } else {
             FdoLive g = live0;
-            fdo_play_to_end<false, false, true>(g, key, &resume0, lut);
+            fdo_play_to_end<false, false, true, false>(g, key, &resume0, lut);
             fdo_final_points(g, p);
         }
         acc[0] += p[0]; acc[1] += p[1]; acc[2] += p[2]; acc[3] += p[3];
@@ -1116,7 +1122,7 @@ pimc_rollout_kernel(RngParams rp, uint64_t root0, uint32_t n_det, uint32_t n_rol
         const uint32_t a = ffs0ll(mm);
         const PimcEntry& e = ws[row * PIMC_MAX_LEGAL + k];
         int32_t p[4];
-        if (e.live) { FdoLive g = e.g; fdo_play_to_end<false, false>(g, key, &e.rs, lut); fdo_final_points(g, p); }
+        if (e.live) { FdoLive g = e.g; fdo_play_to_end<false, false, false, false>(g, key, &e.rs, lut); fdo_final_points(g, p); }
         else { p[0] = e.pts[0]; p[1] = e.pts[1]; p[2] = e.pts[2]; p[3] = e.pts[3]; }
         const int v = (mover & 2u) ? ((mover & 1u) ? p[3] : p[2]) : ((mover & 1u) ? p[1] : p[0]);
         const int tot = __reduce_add_sync(peers, v);

@@ -382,7 +382,7 @@ DK_HD bool fdo_state_to_live(const dk_state& s, FdoLive& g, FdoResume& rs) {
     g.dup = dup;
     rs.n_res = s.n_reservations;
     rs.t0 = 0; rs.k0 = 0; rs.starts = 0; rs.ann_ci = 0; rs.ann_p = 0; rs.ann_turns = 0xFFFFFFFFu;
-    rs.acc.follow = 0; rs.acc.best = 0; rs.acc.bestk = 0; rs.acc.bestc = 0; rs.acc.teyes = 0; rs.acc.foxm = 0; rs.acc.prow = 0;
+    trick_acc_clear(rs.acc);
 #pragma unroll
     for (uint32_t i = 0; i < 4u; ++i) rs.res_action[i] = i < s.n_reservations ? fdo_action_from_res_code(s.reservations[i]) : 0u;
     uint32_t base;
@@ -429,10 +429,10 @@ DK_HD bool fdo_state_to_live(const dk_state& s, FdoLive& g, FdoResume& rs) {
             if (k >= k0) break;
             uint32_t c = (quad0 >> (8u * k)) & 255u;
             if (k == 0u) { rs.acc.follow = follow_mask(c, g.trump); rs.acc.prow = pow_row(g.gt, c, card_suit(c), g.trump); }
-            uint32_t pw = card_power(c, g.trump, rs.acc.follow);
-            if (k == 0u || pw > rs.acc.best) { rs.acc.best = pw; rs.acc.bestk = k; rs.acc.bestc = c; }
-            rs.acc.teyes += card_eyes_by_rank(c - 6u * card_suit(c));
-            if (c == CARD_DA) rs.acc.foxm |= 1u << k;
+            const uint32_t v = pow_entry_of(c, g.trump, rs.acc.follow), cand = v | ((3u - k) << POW_K_SHIFT);
+            if (k == 0u || cand > rs.acc.best) rs.acc.best = cand;
+            rs.acc.acc += v;
+            rs.acc.fox += (v & POW_FOX_BIT) << k;
         }
         if (phase == DK_PHASE_ANNOUNCEMENT) { rs.ann_ci = ci; rs.ann_p = st_cur(s); rs.ann_turns = st_turns(s); }
         else { rs.ann_ci = ci + 1u; rs.ann_turns = 0xFFFFFFFFu; }            // the round before card ci is over
@@ -547,7 +547,7 @@ DK_HD bool doko_state_to_live(const dk_state& s, DokoLive& g, DokoResume& rs) {
     for (uint32_t p = 0; p < 4u; ++p) dup |= hand_both24(s.hands[p]);
     g.dup = dup;
     rs.n_res = s.n_reservations; rs.t0 = 0; rs.k0 = 0;
-    rs.acc.follow = 0; rs.acc.best = 0; rs.acc.bestk = 0; rs.acc.teyes = 0; rs.acc.prow = 0;
+    doko_trick_acc_clear(rs.acc);
 #pragma unroll
     for (uint32_t i = 0; i < 4u; ++i) rs.res_action[i] = i < s.n_reservations ? (s.reservations[i] == 0u ? 25u : 24u) : 0u;
     uint32_t base;
@@ -567,9 +567,9 @@ DK_HD bool doko_state_to_live(const dk_state& s, DokoLive& g, DokoResume& rs) {
             if (k >= k0) break;
             uint32_t c = (quad0 >> (8u * k)) & 255u;
             if (k == 0u) { rs.acc.follow = follow_mask(c, DOKO_TRUMP_MASK); rs.acc.prow = pow_row(0u, c, card_suit(c), DOKO_TRUMP_MASK); }
-            uint32_t pw = card_power(c, DOKO_TRUMP_MASK, rs.acc.follow);
-            if (k == 0u || pw > rs.acc.best) { rs.acc.best = pw; rs.acc.bestk = k; }
-            rs.acc.teyes += card_eyes_by_rank(c - 6u * card_suit(c));
+            const uint32_t v = pow_entry_of(c, DOKO_TRUMP_MASK, rs.acc.follow), cand = v | ((3u - k) << POW_K_SHIFT);
+            if (k == 0u || cand > rs.acc.best) rs.acc.best = cand;
+            rs.acc.acc += v;
         }
     }
     g.base = 0;

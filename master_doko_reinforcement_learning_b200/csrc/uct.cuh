@@ -516,7 +516,7 @@ DK_HD uint32_t uct_phase_rollout(const UctPool& P, uint64_t t, const RngKey& key
     alignas(16) dk_state s = P.state(t, P.explore[t]);
     int32_t p[4] = {0, 0, 0, 0};
     FdoLive g; FdoResume rs;
-    if (fdo_state_to_live(s, g, rs)) { fdo_play_to_end<false, false, SEL12>(g, key, &rs, lut); fdo_final_points(g, p); }
+    if (fdo_state_to_live(s, g, rs)) { fdo_play_to_end<false, false, SEL12, false>(g, key, &rs, lut); fdo_final_points(g, p); }
     else { p[0] = s.points[0]; p[1] = s.points[1]; p[2] = s.points[2]; p[3] = s.points[3]; }
     return uct_pack_points(p);
 }

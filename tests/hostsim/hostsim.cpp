@@ -31,10 +31,11 @@ struct LocalDeck {
     void set8(uint32_t j, uint32_t v) { w[j >> 2] = (w[j >> 2] & ~(0xFFu << (8u * (j & 3u)))) | ((v & 0xFFu) << (8u * (j & 3u))); }
 };
 const uint32_t* card_lut() {      // the shared-memory image of the fresh-game playout kernel: small tables + the 12-bit rank-select table
-    alignas(16) static uint32_t lut[dk::CARD_LUT_WORDS + dk::SEL12_WORDS];
+    alignas(16) static uint32_t lut[dk::FULL_LUT_WORDS];
     static bool init = false;
     if (!init) {
         for (uint32_t i = 0; i < dk::CARD_LUT_WORDS; ++i) lut[i] = dk::lut_word(i);
+        for (uint32_t i = dk::ANN_LUT_BASE; i < dk::FULL_LUT_WORDS; ++i) lut[i] = dk::lut_word(i);
         for (uint32_t h = 0; h < dk::SEL12_WORDS / 2; ++h) { uint64_t e = dk::sel12_entry(h); std::memcpy(lut + dk::SEL12_LUT_BASE + 2 * h, &e, 8); }
         init = true;
     }
@@ -87,7 +88,7 @@ SIM_API uint32_t sim_card_power(uint32_t c, uint32_t trump, uint32_t follow) { r
 SIM_API uint32_t sim_pick_msb_rank24_tab(uint32_t mask, uint32_t idx) { return dk::pick_msb_rank24_tab(mask, idx, reinterpret_cast<const uint64_t*>(card_lut() + dk::SEL12_LUT_BASE)); }
 SIM_API uint32_t sim_pick_msb_rank24_lut(uint32_t mask, uint32_t idx) { return dk::pick_msb_rank24_lut(mask, idx, card_lut()); }
 SIM_API uint32_t sim_pick_msb_rank24(uint32_t mask, uint32_t idx) { return dk::pick_msb_rank24(mask, idx); }
-SIM_API uint32_t sim_pow_lookup(uint32_t gt, uint32_t first_card, uint32_t c) {      // strength | eyes << 8 of card c in a trick led with first_card
+SIM_API uint32_t sim_pow_lookup(uint32_t gt, uint32_t first_card, uint32_t c) {      // the trick-accumulator record of card c in a trick led with first_card
     const uint32_t trump = dk::trump_mask_for_game_type(gt);
     return dk::pow_lookup(card_lut(), dk::pow_row(gt, first_card, dk::card_suit(first_card), trump), c);
 }

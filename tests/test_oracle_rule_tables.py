@@ -167,7 +167,14 @@ def test_device_lookup_tables_match_the_closed_forms():
             follow = sim.sim_follow_mask(first, trump)
             for c in range(24):
                 v = sim.sim_pow_lookup(gt, first, c)
-                assert v & 255 == sim.sim_card_power(c, trump, follow) and v >> 8 == eyes[c % 6], (gt, first, c)
+                # the trick accumulator's record: eyes | ♦A bit | empty position field | card id | strength (dk_common.cuh pow_lut_entry)
+                assert v >> 16 == sim.sim_card_power(c, trump, follow) and v & 255 == eyes[c % 6], (gt, first, c)
+                assert (v >> 11) & 31 == c and (v >> 9) & 3 == 0 and ((v >> 8) & 1) == (1 if c == 5 else 0), (gt, first, c)
+            # what the one-max trick winner rests on: within a row, two different card types never share a positive strength, and the
+            # card that leads has a positive one
+            row = [sim.sim_pow_lookup(gt, first, c) >> 16 for c in range(24)]
+            positive = [x for x in row if x > 0]
+            assert len(positive) == len(set(positive)) and row[first] > 0, (gt, first)
     for w in (0, 1, 2):
         for re_low in range(7):
             for ko_low in range(7):
