@@ -76,6 +76,19 @@ DK_HD uint32_t doko_card_step(DokoLive& g, uint32_t& h, DokoTrickAcc& a, uint32_
     return c;
 }
 
+// The twelfth trick played from its first card: every seat holds one card (see fdo_card_step_last).
+template <int K>
+DK_HD uint32_t doko_card_step_last(DokoLive& g, uint32_t& h, DokoTrickAcc& a, const uint32_t* __restrict__ lut) {
+    const uint32_t c = ffs0(h);
+    h = 0u;
+    if (K == 0) { const uint32_t e = lut[c]; a.prow = pow_row(0u, c, e >> 13, DOKO_TRUMP_MASK); }
+    const uint32_t v = pow_lookup(lut, a.prow, c), cand = v | ((3u - (uint32_t)K) << POW_K_SHIFT);
+    a.best = (K == 0 || cand > a.best) ? cand : a.best;
+    a.acc += v;
+    g.steps++;
+    return c;
+}
+
 DK_HD void doko_trick_done(DokoLive& g, const DokoTrickAcc& a, uint32_t t) {
     const uint32_t bestk = pow_best_k(a.best);
     uint32_t w = (g.base + bestk) & 3u;
@@ -127,21 +140,42 @@ DK_HD void doko_play_to_end(DokoLive& g, const RngKey& key, const DokoResume* rs
         if (TRACE) { trace[0] = (uint8_t)ra[0]; trace[1] = (uint8_t)ra[1]; trace[2] = (uint8_t)ra[2]; trace[3] = (uint8_t)ra[3]; }
         doko_finish_reservations(g, ra);
     }
-    uint32_t t0 = FRESH ? 0u : rs->t0;
-    for (uint32_t t = t0; t < 12u; ++t) {
-        U4 blk = rng_block(key, SITE_CARD, t);
+    uint32_t t = FRESH ? 0u : rs->t0;
+    // (same shape as fdo_play_to_end: a resumed game first finishes its partial trick; the loop body is unconditional; the twelfth
+    // trick, when it starts from its first card, is four forced moves and needs neither its Philox block nor a rank select)
+    if (!FRESH && t < 12u) {
+        const U4 blk = rng_block(key, SITE_CARD, t);
         DokoTrickAcc a;
         doko_trick_acc_clear(a);
-        uint32_t k0 = 0;
-        bool first = !FRESH && t == t0;
-        if (first) { k0 = rs->k0; if (k0 > 0u) a = rs->acc; }
-        uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
-        if (!first || k0 <= 0u) c0 = doko_card_step<0, SEL12>(g, g.h0, a, blk.x, lut);
-        if (!first || k0 <= 1u) c1 = doko_card_step<1, SEL12>(g, g.h1, a, blk.y, lut);
-        if (!first || k0 <= 2u) c2 = doko_card_step<2, SEL12>(g, g.h2, a, blk.z, lut);
-        c3 = doko_card_step<3, SEL12>(g, g.h3, a, blk.w, lut);
+        const uint32_t k0 = rs->k0;
+        if (k0 > 0u) a = rs->acc;
+        if (k0 <= 0u) doko_card_step<0, SEL12>(g, g.h0, a, blk.x, lut);
+        if (k0 <= 1u) doko_card_step<1, SEL12>(g, g.h1, a, blk.y, lut);
+        if (k0 <= 2u) doko_card_step<2, SEL12>(g, g.h2, a, blk.z, lut);
+        doko_card_step<3, SEL12>(g, g.h3, a, blk.w, lut);
+        doko_trick_done(g, a, t);
+        ++t;
+    }
+    for (; t < 11u; ++t) {
+        const U4 blk = rng_block(key, SITE_CARD, t);
+        DokoTrickAcc a;
+        doko_trick_acc_clear(a);
+        const uint32_t c0 = doko_card_step<0, SEL12>(g, g.h0, a, blk.x, lut);
+        const uint32_t c1 = doko_card_step<1, SEL12>(g, g.h1, a, blk.y, lut);
+        const uint32_t c2 = doko_card_step<2, SEL12>(g, g.h2, a, blk.z, lut);
+        const uint32_t c3 = doko_card_step<3, SEL12>(g, g.h3, a, blk.w, lut);
         if (TRACE) { trace[4 + 4 * t] = (uint8_t)c0; trace[5 + 4 * t] = (uint8_t)c1; trace[6 + 4 * t] = (uint8_t)c2; trace[7 + 4 * t] = (uint8_t)c3; }
         doko_trick_done(g, a, t);
+    }
+    if (t == 11u) {
+        DokoTrickAcc a;
+        doko_trick_acc_clear(a);
+        const uint32_t c0 = doko_card_step_last<0>(g, g.h0, a, lut);
+        const uint32_t c1 = doko_card_step_last<1>(g, g.h1, a, lut);
+        const uint32_t c2 = doko_card_step_last<2>(g, g.h2, a, lut);
+        const uint32_t c3 = doko_card_step_last<3>(g, g.h3, a, lut);
+        if (TRACE) { trace[48] = (uint8_t)c0; trace[49] = (uint8_t)c1; trace[50] = (uint8_t)c2; trace[51] = (uint8_t)c3; }
+        doko_trick_done(g, a, 11u);
     }
 }
 

@@ -407,6 +407,22 @@ DK_HD void fdo_card_step(FdoLive& g, uint32_t& h, TrickAcc& a, uint32_t word, bo
     g.steps++;
 }
 
+// Card step of the TWELFTH trick when it is played from its first card: every seat holds exactly one card and no colour is enforced
+// (state.rs:360-372), so the pick has one choice — mulhi(word, 1) = 0 whatever the word is.  The trick's Philox block and the four
+// rank selects are not computed at all (the words of a site are addressed by card index, so nothing else moves in the stream):
+// about 150 of a game's 5000 instructions.
+template <int K>
+DK_HD void fdo_card_step_last(FdoLive& g, uint32_t& h, TrickAcc& a, const uint32_t* __restrict__ lut) {
+    const uint32_t c = ffs0(h);
+    h = 0u;
+    if (K == 0) { const uint32_t e = lut[c]; a.prow = pow_row(g.gt, c, e >> 13, g.trump); }
+    const uint32_t v = pow_lookup(lut, a.prow, c), cand = v | ((3u - (uint32_t)K) << POW_K_SHIFT);
+    a.best = (K == 0 || cand > a.best) ? cand : a.best;
+    a.acc += v;
+    a.fox += (v & POW_FOX_BIT) * (1u << K);
+    g.steps++;
+}
+
 // ♦A log: one 8-bit record per trick that contained a ♦A (at most two): absolute seats that played one (4 bits) << 2 | winner seat.
 // foxm is frame-relative (bit k = k-th card of the trick), lead = absolute seat of the trick's first card.
 DK_HD uint32_t fdo_fox_record(uint32_t foxes, uint32_t foxm, uint32_t lead, uint32_t winner) {
@@ -503,17 +519,26 @@ DK_HD void fdo_play_to_end(FdoLive& g, const RngKey& key, const FdoResume* rs, c
         fdo_trick_done(g, a, t);
         ++t;
     }
-    for (; t < 12u; ++t) {
+    for (; t < 11u; ++t) {
         starts |= g.base << (2u * t);
         const U4 blk = rng_block(key, SITE_CARD, t);
         TrickAcc a;
         trick_acc_clear(a);
-        const bool last = t == 11u;
-        fdo_card_step<0, SEL12>(g, g.h0, a, blk.x, last, lut);
-        fdo_card_step<1, SEL12>(g, g.h1, a, blk.y, last, lut);
-        fdo_card_step<2, SEL12>(g, g.h2, a, blk.z, last, lut);
-        fdo_card_step<3, SEL12>(g, g.h3, a, blk.w, last, lut);
+        fdo_card_step<0, SEL12>(g, g.h0, a, blk.x, false, lut);
+        fdo_card_step<1, SEL12>(g, g.h1, a, blk.y, false, lut);
+        fdo_card_step<2, SEL12>(g, g.h2, a, blk.z, false, lut);
+        fdo_card_step<3, SEL12>(g, g.h3, a, blk.w, false, lut);
         fdo_trick_done(g, a, t);
+    }
+    if (t == 11u) {                                       // the last trick from its first card: forced moves (fdo_card_step_last)
+        starts |= g.base << 22;
+        TrickAcc a;
+        trick_acc_clear(a);
+        fdo_card_step_last<0>(g, g.h0, a, lut);
+        fdo_card_step_last<1>(g, g.h1, a, lut);
+        fdo_card_step_last<2>(g, g.h2, a, lut);
+        fdo_card_step_last<3>(g, g.h3, a, lut);
+        fdo_trick_done(g, a, 11u);
     }
     // announcement rounds (see fdo_replay_announcements): fresh games start with the round before card 0
     if (!WITH_ANN && !STEPS) return;
