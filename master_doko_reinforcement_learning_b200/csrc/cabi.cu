@@ -145,15 +145,10 @@ dk_status dk_init(int device, dk_ctx** out) {
     }
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return DK_ERR_CUDA; }
     {   // the kernels' lookup tables: evaluated here, resident in this device's memory from now on
-        std::vector<uint32_t> lut(dk::CARD_LUT_WORDS);
-        for (uint32_t i = 0; i < dk::CARD_LUT_WORDS; ++i) lut[i] = dk::lut_word(i);
-        std::vector<uint64_t> sel(dk::SEL12_WORDS / 2);
-        for (uint32_t h = 0; h < dk::SEL12_WORDS / 2; ++h) sel[h] = dk::sel12_entry(h);
-        std::vector<uint32_t> ann(dk::ANN_LUT_WORDS);
-        for (uint32_t i = 0; i < dk::ANN_LUT_WORDS; ++i) ann[i] = dk::lut_word(dk::ANN_LUT_BASE + i);
-        if (cudaMemcpyToSymbol(dk::g_card_lut, lut.data(), lut.size() * sizeof(uint32_t)) != cudaSuccess ||
-            cudaMemcpyToSymbol(dk::g_ann_lut, ann.data(), ann.size() * sizeof(uint32_t)) != cudaSuccess ||
-            cudaMemcpyToSymbol(dk::g_sel12, sel.data(), sel.size() * sizeof(uint64_t)) != cudaSuccess) { cudaStreamDestroy(ctx->stream); delete ctx; return DK_ERR_CUDA; }
+        std::vector<uint32_t> lut(dk::FULL_LUT_WORDS);
+        for (uint32_t i = 0; i < dk::FULL_LUT_WORDS; ++i) lut[i] = dk::lut_word(i);
+        for (uint32_t h = 0; h < dk::SEL12_WORDS / 2; ++h) { const uint64_t e = dk::sel12_entry(h); std::memcpy(&lut[dk::SEL12_LUT_BASE + 2u * h], &e, 8); }
+        if (cudaMemcpyToSymbol(dk::g_lut, lut.data(), lut.size() * sizeof(uint32_t)) != cudaSuccess) { cudaStreamDestroy(ctx->stream); delete ctx; return DK_ERR_CUDA; }
     }
     *out = ctx;
     return DK_OK;

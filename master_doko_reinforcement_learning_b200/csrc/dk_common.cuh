@@ -137,7 +137,7 @@ DK_HD uint32_t rank_lut6_entry(uint32_t b) {
     return e;
 }
 // The lookup tables of the playout kernels, one word array: built once on the host (lut_word, fdo_rules.cuh), kept in device memory
-// and copied into shared memory by every block (kernels.cuh fill_card_lut / fill_sel12 / fill_ann_lut).  Three regions, so that a
+// and copied into shared memory by every block (kernels.cuh stage_lut: one bulk copy of a prefix of the image).  Three regions, so that a
 // kernel stages only what it reads:
 //   CARD   [0,24) card attributes (card_lut_entry) | [24,31) fdo_thr_lut_word | [32,96) rank_lut6_entry |
 //          [96,1176) 9 game types x 5 lead classes x 24 cards x 32 bit: the card's record for the trick accumulator (pow_lut_entry)

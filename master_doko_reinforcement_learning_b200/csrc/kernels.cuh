@@ -38,25 +38,28 @@ struct SharedDeckT {
 };
 using SharedDeck = SharedDeckT<PLAYOUT_THREADS>;
 
-// The lookup tables (dk_common.cuh CARD_LUT_WORDS ...; 4.7 KB + 32 KB + 1 KB) live in device memory, written once per context by dk_init from the host
-// evaluation of lut_word; every block copies them into shared memory with coalesced loads (L2 hits).
-__device__ uint32_t g_card_lut[CARD_LUT_WORDS];
-__device__ uint4 g_sel12[SEL12_WORDS / 4];                           // the 12-bit rank-select table (sel12_entry), two entries per uint4
-__device__ uint32_t g_ann_lut[ANN_LUT_WORDS];                        // the announcement replay's tables (ANN region)
-__device__ __forceinline__ void fill_ann_lut(uint32_t* lut) {        // lut: FULL_LUT_WORDS words; caller syncs
-    for (uint32_t i = threadIdx.x; i < ANN_LUT_WORDS; i += blockDim.x) lut[ANN_LUT_BASE + i] = g_ann_lut[i];
+// The lookup tables (dk_common.cuh: CARD 4.7 KB | SEL12 32 KB | ANN 1 KB) live in device memory as ONE image, written once per context
+// by dk_init from the host evaluation of lut_word / sel12_entry.  A block stages the prefix of the image it reads with ONE bulk copy of
+// the TMA engine (cp.async.bulk global -> shared, completion on an mbarrier) issued by thread 0.  The cooperative form — every thread
+// copying its share with LDG / STS — was 2.5 % of the fresh-playout kernel's instructions (25 words per thread) and 5 % of the UCT
+// rollout kernel's (37 words per thread for ONE rollout), profiles/r02_k2_v5 attribution.
+__device__ __align__(16) uint32_t g_lut[FULL_LUT_WORDS];
+__device__ __forceinline__ void stage_lut(uint32_t* lut, uint32_t words) {       // lut: 16-byte aligned; words * 4 a multiple of 16; ends with a block barrier
+    __shared__ __align__(8) unsigned long long lut_bar;
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&lut_bar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(words * 4u) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"((uint32_t)__cvta_generic_to_shared(lut)), "l"(g_lut), "r"(words * 4u), "r"(bar) : "memory");
+    }
+    __syncthreads();                                                             // the barrier is initialised before anybody polls it
+    uint32_t ok = 0;
+    while (!ok)
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(bar), "r"(0u) : "memory");
 }
-__device__ __forceinline__ void fill_card_lut(uint32_t* lut) {       // caller syncs
-    for (uint32_t i = threadIdx.x; i < CARD_LUT_WORDS; i += blockDim.x) lut[i] = g_card_lut[i];
-}
-__device__ __forceinline__ void fill_sel12(uint32_t* lut) {          // lut: 16-byte aligned, CARD_LUT_WORDS + SEL12_WORDS words; caller syncs
-    uint4* dst = reinterpret_cast<uint4*>(lut + SEL12_LUT_BASE);
-    for (uint32_t i = threadIdx.x; i < SEL12_WORDS / 4u; i += blockDim.x) dst[i] = g_sel12[i];
-}
-__device__ __forceinline__ void stage_card_lut(uint32_t* lut) {
-    fill_card_lut(lut);
-    __syncthreads();
-}
+__device__ __forceinline__ void stage_card_lut(uint32_t* lut) { stage_lut(lut, CARD_LUT_WORDS); }
 
 __device__ __forceinline__ RngKey make_key(const RngParams& rp, uint64_t index, uint32_t unit_hi_override, bool use_override) {
     uint64_t unit = rp.first_id + index;
@@ -144,9 +147,7 @@ fdo_playout_fresh_kernel(RngParams rp, uint64_t n, void* __restrict__ points, vo
     __shared__ BlockStats bstats;
     uint32_t* lut = fresh_smem;                                        // FULL_LUT_WORDS words (16-byte aligned, SEL12 part 8-byte aligned)
     uint32_t* smem = fresh_smem + FULL_LUT_WORDS;                      // the shuffle scratch: 12 words per thread, word-interleaved
-    fill_card_lut(lut);
-    fill_sel12(lut);
-    fill_ann_lut(lut);
+    stage_lut(lut, FULL_LUT_WORDS);
     if (stats) block_stats_clear(bstats);
     __syncthreads();
     uint64_t i = (uint64_t)blockIdx.x * FDO_FRESH_THREADS + threadIdx.x;
@@ -173,8 +174,7 @@ doko_playout_fresh_kernel(RngParams rp, uint64_t n, void* __restrict__ points, v
     __shared__ BlockStats bstats;
     uint32_t* lut = fresh_smem;
     uint32_t* smem = fresh_smem + CARD_LUT_WORDS + SEL12_WORDS;
-    fill_card_lut(lut);
-    fill_sel12(lut);
+    stage_lut(lut, CARD_LUT_WORDS + SEL12_WORDS);
     if (stats) block_stats_clear(bstats);
     __syncthreads();
     uint64_t i = (uint64_t)blockIdx.x * FDO_FRESH_THREADS + threadIdx.x;
@@ -845,9 +845,7 @@ playout_state_kernel(RngParams rp, uint64_t n, const dk_state* __restrict__ stat
                      void* __restrict__ steps, uint32_t mode, unsigned long long* __restrict__ stats) {
     __shared__ __align__(16) uint32_t lut[FULL_LUT_WORDS];
     __shared__ BlockStats bstats;
-    fill_card_lut(lut);
-    fill_sel12(lut);
-    fill_ann_lut(lut);
+    stage_lut(lut, FULL_LUT_WORDS);
     if (stats) block_stats_clear(bstats);
     __syncthreads();
     const uint64_t i_raw = (uint64_t)blockIdx.x * PLAYOUT_STATE_THREADS + threadIdx.x;
@@ -972,8 +970,7 @@ fdo_leaf_rollouts_kernel(RngParams rp, uint64_t leaf0, uint64_t n_leaves, uint32
     __shared__ int live_ok;
     __shared__ int red[4];
     __shared__ __align__(16) uint32_t lut[CARD_LUT_WORDS + SEL12_WORDS];   // card tables + 12-bit rank select; no ANN region: only the points are wanted
-    fill_card_lut(lut);
-    fill_sel12(lut);
+    stage_lut(lut, CARD_LUT_WORDS + SEL12_WORDS);
     // `splits` blocks share one leaf when there are fewer leaves than one wave of blocks (rollout r belongs to block
     // r / MATCH_THREADS % splits); their integer sums meet in point_sum by atomics (zeroed by the host), so the result does not change.
     const uint64_t li = blockIdx.x / splits;                       // leaf inside this launch
@@ -1098,8 +1095,8 @@ __global__ void __launch_bounds__(PIMC_ROLL_THREADS, 6)
 pimc_rollout_kernel(RngParams rp, uint64_t root0, uint32_t n_det, uint32_t n_rollouts, uint32_t blocks_per_root, const dk_state* __restrict__ states,
                     const PimcEntry* __restrict__ ws, const uint64_t* __restrict__ masks, uint32_t* __restrict__ visits_out,
                     unsigned long long* __restrict__ value_out) {
-    __shared__ uint32_t lut[CARD_LUT_WORDS];
-    fill_card_lut(lut);
+    __shared__ __align__(16) uint32_t lut[CARD_LUT_WORDS];
+    stage_lut(lut, CARD_LUT_WORDS);
     __syncthreads();
     const uint64_t rl = blockIdx.x / blocks_per_root, root = root0 + rl;
     const uint32_t item = (uint32_t)(blockIdx.x % blocks_per_root) * PIMC_ROLL_THREADS + threadIdx.x;

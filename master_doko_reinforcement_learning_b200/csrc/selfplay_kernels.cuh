@@ -392,8 +392,7 @@ constexpr int UCT_ROLLOUT_THREADS = 256;
 __global__ void __launch_bounds__(UCT_ROLLOUT_THREADS, DK_UCT_ROLLOUT_BLOCKS)
 uct_rollout_kernel(RngParams rp, UctPool P, uint32_t trees_per_root, uint32_t iterations, uint32_t it, uint64_t t_begin, uint64_t t_end) {
     __shared__ __align__(16) uint32_t lut[CARD_LUT_WORDS + SEL12_WORDS];
-    fill_card_lut(lut);
-    fill_sel12(lut);
+    stage_lut(lut, CARD_LUT_WORDS + SEL12_WORDS);
     __syncthreads();
     const uint64_t t = t_begin + (uint64_t)blockIdx.x * UCT_ROLLOUT_THREADS + threadIdx.x;
     if (t >= t_end) return;
