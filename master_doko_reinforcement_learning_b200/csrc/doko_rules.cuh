@@ -184,13 +184,15 @@ DK_HD void doko_live_clear(DokoLive& g) {
     g.re_mask = 0; g.wed_seat = 0; g.solved_idx = 0; g.wedding = 0; g.steps = 0;
 }
 
-template <bool TRACE, class Deck, bool SEL12 = false>
-DK_HD void doko_playout_fresh(const RngKey& key, Deck& deck, const uint32_t* __restrict__ lut, int32_t pts[4], uint32_t& steps, uint8_t* trace, uint32_t* aux) {
+template <bool TRACE, class Deck, bool SEL12 = false, class Ready = NoWait>
+DK_HD void doko_playout_fresh(const RngKey& key, Deck& deck, const uint32_t* __restrict__ lut, int32_t pts[4], uint32_t& steps, uint8_t* trace, uint32_t* aux,
+                              Ready tables_ready = Ready()) {
     DokoLive g;
     doko_live_clear(g);
     FdoLive dummy; dummy.base = 0;
     uint32_t ah[4], start;
     fdo_deal(dummy, key, deck, ah, g.dup, start);        // same deal contract as the full engine
+    tables_ready();
     g.h0 = ah[0]; g.h1 = ah[1]; g.h2 = ah[2]; g.h3 = ah[3];
     doko_rotate(g, start);
     doko_play_to_end<true, TRACE, SEL12>(g, key, nullptr, trace, lut);

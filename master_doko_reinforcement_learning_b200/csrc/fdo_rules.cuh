@@ -546,13 +546,16 @@ DK_HD void fdo_play_to_end(FdoLive& g, const RngKey& key, const FdoResume* rs, c
     else fdo_replay_announcements<WITH_ANN>(g, key, starts, rs->ann_ci, rs->ann_p, rs->ann_turns, lut);
 }
 
-// Fresh game: deal + reservations + 12 tricks + scoring.
-template <bool WITH_ANN, class Deck, bool SEL12 = false>
-DK_HD void fdo_playout_fresh(const RngKey& key, Deck& deck, const uint32_t* __restrict__ lut, int32_t pts[4], uint32_t& steps) {
+// Fresh game: deal + reservations + 12 tricks + scoring.  `tables_ready` is called between the deal (which reads no table) and the
+// first table access: the kernels wait there for the bulk copy that stages the tables, so the copy runs under the deal.
+struct NoWait { DK_HD void operator()() const {} };
+template <bool WITH_ANN, class Deck, bool SEL12 = false, class Ready = NoWait>
+DK_HD void fdo_playout_fresh(const RngKey& key, Deck& deck, const uint32_t* __restrict__ lut, int32_t pts[4], uint32_t& steps, Ready tables_ready = Ready()) {
     FdoLive g;
     fdo_live_clear(g);
     uint32_t ah[4], start;
     fdo_deal(g, key, deck, ah, g.dup, start);
+    tables_ready();
     g.h0 = ah[0]; g.h1 = ah[1]; g.h2 = ah[2]; g.h3 = ah[3];
     g.base = 0;
     fdo_rotate(g, start);

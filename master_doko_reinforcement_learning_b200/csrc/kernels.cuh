@@ -44,7 +44,9 @@ using SharedDeck = SharedDeckT<PLAYOUT_THREADS>;
 // copying its share with LDG / STS — was 2.5 % of the fresh-playout kernel's instructions (25 words per thread) and 5 % of the UCT
 // rollout kernel's (37 words per thread for ONE rollout), profiles/r02_k2_v5 attribution.
 __device__ __align__(16) uint32_t g_lut[FULL_LUT_WORDS];
-__device__ __forceinline__ void stage_lut(uint32_t* lut, uint32_t words) {       // lut: 16-byte aligned; words * 4 a multiple of 16; ends with a block barrier
+// stage_lut_begin issues the copy (and ends with a block barrier); the returned handle is polled by stage_lut_wait before the first
+// table access — the fresh-game kernels deal their cards in between.
+__device__ __forceinline__ uint32_t stage_lut_begin(uint32_t* lut, uint32_t words) {   // lut: 16-byte aligned; words * 4 a multiple of 16
     __shared__ __align__(8) unsigned long long lut_bar;
     const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&lut_bar);
     if (threadIdx.x == 0) {
@@ -55,10 +57,15 @@ __device__ __forceinline__ void stage_lut(uint32_t* lut, uint32_t words) {      
                      ::"r"((uint32_t)__cvta_generic_to_shared(lut)), "l"(g_lut), "r"(words * 4u), "r"(bar) : "memory");
     }
     __syncthreads();                                                             // the barrier is initialised before anybody polls it
+    return bar;
+}
+__device__ __forceinline__ void stage_lut_wait(uint32_t bar) {
     uint32_t ok = 0;
     while (!ok)
         asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(bar), "r"(0u) : "memory");
 }
+__device__ __forceinline__ void stage_lut(uint32_t* lut, uint32_t words) { stage_lut_wait(stage_lut_begin(lut, words)); }
+struct LutReady { uint32_t bar; __device__ __forceinline__ void operator()() const { stage_lut_wait(bar); } };
 __device__ __forceinline__ void stage_card_lut(uint32_t* lut) { stage_lut(lut, CARD_LUT_WORDS); }
 
 __device__ __forceinline__ RngKey make_key(const RngParams& rp, uint64_t index, uint32_t unit_hi_override, bool use_override) {
@@ -147,9 +154,8 @@ fdo_playout_fresh_kernel(RngParams rp, uint64_t n, void* __restrict__ points, vo
     __shared__ BlockStats bstats;
     uint32_t* lut = fresh_smem;                                        // FULL_LUT_WORDS words (16-byte aligned, SEL12 part 8-byte aligned)
     uint32_t* smem = fresh_smem + FULL_LUT_WORDS;                      // the shuffle scratch: 12 words per thread, word-interleaved
-    stage_lut(lut, FULL_LUT_WORDS);
     if (stats) block_stats_clear(bstats);
-    __syncthreads();
+    const LutReady ready{stage_lut_begin(lut, FULL_LUT_WORDS)};        // (ends with a block barrier; the copy runs under the deal)
     uint64_t i = (uint64_t)blockIdx.x * FDO_FRESH_THREADS + threadIdx.x;
     // Out-of-range lanes play game n-1 again (keeps the warp converged); they just do not store.
     uint64_t gi = i < n ? i : n - 1;
@@ -158,7 +164,7 @@ fdo_playout_fresh_kernel(RngParams rp, uint64_t n, void* __restrict__ points, vo
     RngKey key = make_key(rp, gi, 0, false);
     int32_t p[4];
     uint32_t s;
-    fdo_playout_fresh<WITH_ANN, SharedDeckT<FDO_FRESH_THREADS>, true>(key, deck, lut, p, s);
+    fdo_playout_fresh<WITH_ANN, SharedDeckT<FDO_FRESH_THREADS>, true, LutReady>(key, deck, lut, p, s, ready);
     if (i < n) store_result(points, steps, i, p, s, mode);
     if (stats) block_stats_add(bstats, stats, p, s, i < n);          // uniform branch
 }
@@ -174,9 +180,8 @@ doko_playout_fresh_kernel(RngParams rp, uint64_t n, void* __restrict__ points, v
     __shared__ BlockStats bstats;
     uint32_t* lut = fresh_smem;
     uint32_t* smem = fresh_smem + CARD_LUT_WORDS + SEL12_WORDS;
-    stage_lut(lut, CARD_LUT_WORDS + SEL12_WORDS);
     if (stats) block_stats_clear(bstats);
-    __syncthreads();
+    const LutReady ready{stage_lut_begin(lut, CARD_LUT_WORDS + SEL12_WORDS)};
     uint64_t i = (uint64_t)blockIdx.x * FDO_FRESH_THREADS + threadIdx.x;
     uint64_t gi = i < n ? i : n - 1;
     SharedDeckT<FDO_FRESH_THREADS> deck;
@@ -185,7 +190,7 @@ doko_playout_fresh_kernel(RngParams rp, uint64_t n, void* __restrict__ points, v
     int32_t p[4];
     uint32_t s, ax[4];
     uint8_t tr[52];
-    doko_playout_fresh<TRACE, SharedDeckT<FDO_FRESH_THREADS>, true>(key, deck, lut, p, s, tr, ax);
+    doko_playout_fresh<TRACE, SharedDeckT<FDO_FRESH_THREADS>, true, LutReady>(key, deck, lut, p, s, tr, ax, ready);
     if (i < n) {
         store_result(points, steps, i, p, s, mode);
         if (TRACE) {
