@@ -139,18 +139,20 @@ DK_HD uint32_t rank_lut6_entry(uint32_t b) {
 // The lookup tables of the playout kernels, one word array: built once on the host (lut_word, fdo_rules.cuh), kept in device memory
 // and copied into shared memory by every block (kernels.cuh stage_lut: one bulk copy of a prefix of the image).  Three regions, so that a
 // kernel stages only what it reads:
-//   CARD   [0,24) card attributes (card_lut_entry) | [24,31) fdo_thr_lut_word | [32,96) rank_lut6_entry |
-//          [96,1176) 9 game types x 5 lead classes x 24 cards x 32 bit: the card's record for the trick accumulator (pow_lut_entry)
-//   SEL12  [1176,9368) the 12-bit rank-select table (4096 x 64 bit, sel12_entry) of the kernels that can afford 32 KB more shared
+//   CARD   [0,216) 9 game types x 24 cards: what a card means as the FIRST card of a trick (lead_lut_entry) | [216,223)
+//          fdo_thr_lut_word | [224,288) rank_lut6_entry | [288,1128) 7 trump sets x 5 lead classes x 24 cards x 32 bit: the card's
+//          record for the trick accumulator (pow_lut_entry)
+//   SEL12  [1128,9320) the 12-bit rank-select table (4096 x 64 bit, sel12_entry) of the kernels that can afford 32 KB more shared
 //          memory per block; the others pick cards through the 64-entry table above
-//   ANN    [9368,9560) call thresholds of both teams by (wedding shift, re level, kontra level) (fdo_thr2_lut_word) |
-//          [9560,9624) 256 bytes: who calls in a segment of an announcement round, by (eligible seats, decision bits)
+//   ANN    [9320,9512) call thresholds of both teams by (wedding shift, re level, kontra level) (fdo_thr2_lut_word) |
+//          [9512,9576) 256 bytes: who calls in a segment of an announcement round, by (eligible seats, decision bits)
 //          (fdo_seg_lut_byte) — read only by the announcement replay, i.e. by the kernels that report game steps or play with calls
-constexpr uint32_t CARD_LUT_WORDS = 1176u;
-constexpr uint32_t THR_LUT_BASE = 24u;
-constexpr uint32_t RANK_LUT_BASE = 32u;
-constexpr uint32_t POW_LUT_BASE = 96u;
-constexpr uint32_t SEL12_LUT_BASE = 1176u;
+constexpr uint32_t CARD_LUT_WORDS = 1128u;
+constexpr uint32_t LEAD_LUT_BASE = 0u;
+constexpr uint32_t THR_LUT_BASE = 216u;
+constexpr uint32_t RANK_LUT_BASE = 224u;
+constexpr uint32_t POW_LUT_BASE = 288u;
+constexpr uint32_t SEL12_LUT_BASE = 1128u;
 constexpr uint32_t SEL12_WORDS = 8192u;
 constexpr uint32_t ANN_LUT_BASE = SEL12_LUT_BASE + SEL12_WORDS;
 constexpr uint32_t ANN_LUT_WORDS = 256u;
@@ -235,20 +237,8 @@ DK_HD uint32_t card_power(uint32_t c, uint32_t trump, uint32_t follow) {
     return (trump & bit) ? 16u + tp : ((follow & bit) ? cp : 0u);
 }
 
-// Per-card attribute word for the lock-step card loop (24 entries; staged in shared memory by the playout kernels: the lanes
-// of a warp index it with their own card, 24 words sit in 24 distinct banks, equal cards broadcast → conflict-free, and the
-// lookups run on the otherwise idle LSU pipe instead of the saturated ALU pipe):
-//   bits 0-3 eyes | 4-7 plain power (1 + eyes) | 8-12 trump power (16 + trump_to_rank order) | 13-14 suit
-DK_HD uint32_t card_lut_entry(uint32_t c) {
-    uint32_t suit = card_suit(c), rank = c - 6u * suit;
-    uint32_t so = suit ^ (suit >> 1);
-    uint32_t plain = (0x310020u >> (4u * rank)) & 15u;
-    uint32_t tp = rank == 2u ? 4u + so : (rank == 3u ? 8u + so : (c == 7u ? 12u : plain));
-    uint32_t eyes = card_eyes_by_rank(rank);
-    return eyes | ((1u + eyes) << 4) | ((16u + tp) << 8) | (suit << 13);
-}
-// Strength-in-trick table: row (game type, lead class) x card, lead class = suit of the first card (0..3) when it is a plain card,
-// 4 when it is a trump.  One 32-bit shared-memory load per card gives everything the trick accumulator needs, laid out so that the
+// Strength-in-trick table: row (trump set, lead class) x card.  Trump set = game type with Normal / Wedding / ♦-solo folded into one
+// (pow_trump_set: they share their trumps), lead class = suit of the first card (0..3) when it is a plain card, 4 when it is a trump.  One 32-bit shared-memory load per card gives everything the trick accumulator needs, laid out so that the
 // accumulator is ONE max, ONE add and one multiply-add per card (the ALU pipe limits the playout kernels; the compare / three selects
 // / mask of the first form were 5 of its ~28 ALU instructions per card step):
 //   bits 0-7 eyes | bit 8 the card is a ♦A | bits 9-10 zero (the caller ORs in 3 - position) | bits 11-15 card id | bits 16-23
@@ -257,8 +247,9 @@ DK_HD uint32_t card_lut_entry(uint32_t c) {
 // copies of one card type (every strength > 0 belongs to one type within a row), so their low bits are equal and the position field
 // makes the FIRST of them win (strict `>` in the reference); a strength-0 card never beats the first card, whose strength is positive.
 constexpr uint32_t POW_K_SHIFT = 9u, POW_CARD_SHIFT = 11u, POW_PW_SHIFT = 16u, POW_FOX_BIT = 0x100u;
-DK_HD uint32_t pow_lut_entry(uint32_t gt, uint32_t cls, uint32_t c) {
-    const uint32_t trump = trump_mask_for_game_type(gt);
+DK_HD uint32_t pow_trump_set(uint32_t gt) { return gt <= 2u ? 0u : gt - 2u; }           // 0 = the normal trumps, 1..6 = ♥ ♠ ♣ trumpless queens jacks solo
+DK_HD uint32_t pow_lut_entry(uint32_t ts, uint32_t cls, uint32_t c) {
+    const uint32_t trump = trump_mask_for_game_type(ts == 0u ? 0u : ts + 2u);
     const uint32_t follow = cls == 4u ? trump : ((0x3Fu << (6u * cls)) & ~trump);
     const uint32_t suit = card_suit(c);
     return card_eyes_by_rank(c - 6u * suit) | (c == 5u ? POW_FOX_BIT : 0u) | (c << POW_CARD_SHIFT) | (card_power(c, trump, follow) << POW_PW_SHIFT);
@@ -269,19 +260,22 @@ DK_HD uint32_t pow_entry_of(uint32_t c, uint32_t trump, uint32_t follow) {
     return card_eyes_by_rank(c - 6u * suit) | (c == 5u ? POW_FOX_BIT : 0u) | (c << POW_CARD_SHIFT) | (card_power(c, trump, follow) << POW_PW_SHIFT);
 }
 DK_HD uint32_t pow_row(uint32_t gt, uint32_t first_card, uint32_t first_suit, uint32_t trump) {
-    return (gt * 5u + (((trump >> first_card) & 1u) ? 4u : first_suit)) * 24u;
+    return (pow_trump_set(gt) * 5u + (((trump >> first_card) & 1u) ? 4u : first_suit)) * 24u;
 }
+// What card c means as the first card of a trick in game type gt: the follow mask of the trick (bits 0-23) and its row of the
+// strength table, as row / 8 in bits 24-31 — one shared-memory load + two decode instructions at the first card of every trick
+// instead of the suit / trump select chain (8 instructions on the ALU pipe).
+DK_HD uint32_t lead_lut_entry(uint32_t gt, uint32_t c) {
+    const uint32_t trump = trump_mask_for_game_type(gt);
+    return follow_mask(c, trump) | ((pow_row(gt, c, card_suit(c), trump) / 8u) << 24);
+}
+DK_HD uint32_t lead_lookup(const uint32_t* __restrict__ lut, uint32_t gt, uint32_t c) { return lut[LEAD_LUT_BASE + gt * 24u + c]; }
+DK_HD uint32_t lead_follow(uint32_t e) { return e & 0xFFFFFFu; }
+DK_HD uint32_t lead_row(uint32_t e) { return (e >> 24) * 8u; }
 DK_HD uint32_t pow_lookup(const uint32_t* __restrict__ lut, uint32_t row, uint32_t c) { return lut[POW_LUT_BASE + row + c]; }
 // Trick accumulator shared by both engines: `best` = max of (entry | (3 - k) << 9), `acc` = sum of the entries (its low byte is the
 // trick's eyes: at most 44, no carry out of the byte matters), `fox` = sum of (entry & ♦A bit) << k.
 DK_HD uint32_t pow_best_k(uint32_t best) { return 3u - ((best >> POW_K_SHIFT) & 3u); }
 DK_HD uint32_t pow_best_card(uint32_t best) { return (best >> POW_CARD_SHIFT) & 31u; }
-DK_HD uint32_t follow_mask_lut(uint32_t c, uint32_t entry, uint32_t trump) {
-    uint32_t suit_cards = 0x3Fu << (6u * (entry >> 13));
-    return ((trump >> c) & 1u) ? trump : (suit_cards & ~trump);
-}
-DK_HD uint32_t card_power_lut(uint32_t bit, uint32_t entry, uint32_t trump, uint32_t follow) {
-    return (trump & bit) ? ((entry >> 8) & 31u) : ((follow & bit) ? ((entry >> 4) & 15u) : 0u);
-}
 
 }  // namespace dk

@@ -68,7 +68,7 @@ DK_HD uint32_t doko_card_step(DokoLive& g, uint32_t& h, DokoTrickAcc& a, uint32_
     uint32_t dbl = g.dup & bit;
     g.dup ^= dbl;
     h ^= bit ^ dbl;
-    if (K == 0) { const uint32_t e = lut[c]; a.follow = follow_mask_lut(c, e, DOKO_TRUMP_MASK); a.prow = pow_row(0u, c, e >> 13, DOKO_TRUMP_MASK); }
+    if (K == 0) { const uint32_t e = lead_lookup(lut, 0u, c); a.follow = lead_follow(e); a.prow = lead_row(e); }   // (game type 0 = the rs-doko trumps)
     const uint32_t v = pow_lookup(lut, a.prow, c), cand = v | ((3u - (uint32_t)K) << POW_K_SHIFT);
     a.best = (K == 0 || cand > a.best) ? cand : a.best;
     a.acc += v;
@@ -81,7 +81,7 @@ template <int K>
 DK_HD uint32_t doko_card_step_last(DokoLive& g, uint32_t& h, DokoTrickAcc& a, const uint32_t* __restrict__ lut) {
     const uint32_t c = ffs0(h);
     h = 0u;
-    if (K == 0) { const uint32_t e = lut[c]; a.prow = pow_row(0u, c, e >> 13, DOKO_TRUMP_MASK); }
+    if (K == 0) a.prow = lead_row(lead_lookup(lut, 0u, c));
     const uint32_t v = pow_lookup(lut, a.prow, c), cand = v | ((3u - (uint32_t)K) << POW_K_SHIFT);
     a.best = (K == 0 || cand > a.best) ? cand : a.best;
     a.acc += v;

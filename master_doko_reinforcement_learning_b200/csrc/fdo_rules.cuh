@@ -80,8 +80,8 @@ DK_HD uint32_t fdo_seg_lut_byte(uint32_t win, uint32_t hit) {
 }
 // Word i of the shared lookup table (layout: dk_common.cuh CARD_LUT_WORDS; the SEL12 region is filled from sel12_entry).
 DK_HD uint32_t lut_word(uint32_t i) {
-    if (i < 24u) return card_lut_entry(i);
-    if (i < 31u) return fdo_thr_lut_word(i - THR_LUT_BASE);
+    if (i < THR_LUT_BASE) return lead_lut_entry(i / 24u, i % 24u);
+    if (i < THR_LUT_BASE + 7u) return fdo_thr_lut_word(i - THR_LUT_BASE);
     if (i < RANK_LUT_BASE) return 0u;
     if (i < POW_LUT_BASE) return rank_lut6_entry(i - RANK_LUT_BASE);
     if (i < CARD_LUT_WORDS) { const uint32_t idx = i - POW_LUT_BASE; return pow_lut_entry(idx / 120u, (idx / 24u) % 5u, idx % 24u); }
@@ -399,7 +399,7 @@ DK_HD void fdo_card_step(FdoLive& g, uint32_t& h, TrickAcc& a, uint32_t word, bo
     uint32_t dbl = g.dup & bit;                           // hand.remove: a doubled card stays in the hand once
     g.dup ^= dbl;
     h ^= bit ^ dbl;
-    if (K == 0) { const uint32_t e = lut[c]; a.follow = follow_mask_lut(c, e, g.trump); a.prow = pow_row(g.gt, c, e >> 13, g.trump); }
+    if (K == 0) { const uint32_t e = lead_lookup(lut, g.gt, c); a.follow = lead_follow(e); a.prow = lead_row(e); }
     const uint32_t v = pow_lookup(lut, a.prow, c), cand = v | ((3u - (uint32_t)K) << POW_K_SHIFT);
     a.best = (K == 0 || cand > a.best) ? cand : a.best;               // one max: first of equals wins through the position field
     a.acc += v;
@@ -415,7 +415,7 @@ template <int K>
 DK_HD void fdo_card_step_last(FdoLive& g, uint32_t& h, TrickAcc& a, const uint32_t* __restrict__ lut) {
     const uint32_t c = ffs0(h);
     h = 0u;
-    if (K == 0) { const uint32_t e = lut[c]; a.prow = pow_row(g.gt, c, e >> 13, g.trump); }
+    if (K == 0) a.prow = lead_row(lead_lookup(lut, g.gt, c));
     const uint32_t v = pow_lookup(lut, a.prow, c), cand = v | ((3u - (uint32_t)K) << POW_K_SHIFT);
     a.best = (K == 0 || cand > a.best) ? cand : a.best;
     a.acc += v;
