@@ -170,6 +170,9 @@ DK_HD void fdo_live_clear(FdoLive& g) {
 // [c0,c0,c1,c1,...] using words 1..47; seat p receives positions 12p..12p+11 (add: copy A first, then copy B)
 // (rs-full-doko/src/state/state.rs:169-178, hand/hand.rs:116-188).  `Deck` provides 48 bytes of per-thread scratch, set up
 // a word at a time and then byte-addressed (shared memory on the device, word-interleaved across the block: conflict-free).  Position i is final after step i, so its card goes straight into seat i/12's hand.
+// Only the steps i = 47..12 are executed: the steps i = 11..1 permute positions 0..11 among themselves — all of them seat 0's — so
+// seat 0 simply holds what the other three seats did not get (two copies of every type minus the copies given away).  Words 37..47 of
+// the site (two Philox blocks and eleven draws, 270 of a game's 4700 instructions) are never computed; nothing else moves in the stream.
 template <class Deck>
 DK_HD void fdo_deal(FdoLive& g, const RngKey& key, Deck& deck, uint32_t abs_hand[4], uint32_t& dup, uint32_t& start) {
 #pragma unroll
@@ -178,29 +181,30 @@ DK_HD void fdo_deal(FdoLive& g, const RngKey& key, Deck& deck, uint32_t abs_hand
     uint32_t d = 0;
     start = 0;
 #pragma unroll
-    for (uint32_t b = 0; b < 12; ++b) {
+    for (uint32_t b = 0; b < 10; ++b) {                   // ord = 0 .. 36 <=> i = 47 .. 12
         U4 blk = rng_block(key, SITE_DEAL, b);
         uint32_t ws[4] = {blk.x, blk.y, blk.z, blk.w};
 #pragma unroll
         for (uint32_t q = 0; q < 4; ++q) {
             uint32_t ord = 4u * b + q;
             if (ord == 0u) { start = mulhi(ws[q], 4u); continue; }
-            uint32_t i = 48u - ord;                       // 47 .. 1
+            if (ord > 36u) continue;
+            uint32_t i = 48u - ord;                       // 47 .. 12
             uint32_t j = mulhi(ws[q], i + 1u);
             uint32_t ci = deck.get8(i);                   // card currently at position i (byte access: no shift / mask arithmetic)
             uint32_t cj = deck.get8(j);                   // card that ends up at position i
             deck.set8(j, ci);
             uint32_t bit = 1u << cj;
-            uint32_t seat = i / 12u;
+            uint32_t seat = i / 12u;                      // 3, 2 or 1
             d |= h[seat] & bit;
             h[seat] |= bit;
         }
     }
-    {   // position 0
-        uint32_t c0 = deck.get8(0);
-        uint32_t bit = 1u << c0;
-        d |= h[0] & bit;
-        h[0] |= bit;
+    {   // seat 0: per card type, the copies nobody else holds
+        const uint32_t any = h[1] | h[2] | h[3];
+        const uint32_t two = (h[1] & h[2]) | (h[1] & h[3]) | (h[2] & h[3]) | d;      // both copies given away
+        h[0] = 0xFFFFFFu & ~two;
+        d |= 0xFFFFFFu & ~any;                                                          // both copies stay with seat 0
     }
     abs_hand[0] = h[0]; abs_hand[1] = h[1]; abs_hand[2] = h[2]; abs_hand[3] = h[3];
     dup = d;
