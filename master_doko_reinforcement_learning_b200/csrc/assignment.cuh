@@ -149,6 +149,24 @@ DK_HD uint32_t doko_assign_sample(const AssignPrep& p, const RngKey& key, uint64
         const uint32_t e0 = a.allow[0], e1 = a.allow[1], e2 = a.allow[2];
         const uint32_t one = (e0 ^ e1 ^ e2) & ~(e0 & e1 & e2) & a.remaining.a;
         if (one) {
+            // The last open seat takes what is left (see fdo_match_sample): one hidden seat open, every remaining card type allowed
+            // for it, counts equal — distribute_single_cards would hand it the remaining multiset card by card and the sample would
+            // be complete, without a draw in between.
+            const uint32_t al = e0 | e1 | e2;
+            const bool one_open = ((e0 | e1) == 0u) | ((e0 | e2) == 0u) | ((e1 | e2) == 0u);
+            if (one_open && (a.remaining.a & ~al) == 0u) {
+                const uint32_t j = e0 ? 0u : (e1 ? 1u : 2u);
+                const uint32_t ln = j == 0u ? a.len[0] : (j == 1u ? a.len[1] : a.len[2]);
+                if (a.n_remaining == ln) {
+#pragma unroll
+                    for (uint32_t o = 0; o < 3u; ++o) {
+                        const uint32_t xa = o == j ? a.remaining.a : 0u, xb = o == j ? a.remaining.b : 0u;
+                        a.hand[o].b |= xb | (a.hand[o].a & xa);
+                        a.hand[o].a |= xa;
+                    }
+                    break;
+                }
+            }
             c = ffs0(one);
             const uint32_t bit = 1u << c;
             player = (e0 & bit) ? 0u : ((e1 & bit) ? 1u : 2u);

@@ -198,7 +198,31 @@ DK_HD uint32_t fdo_match_sample(const MatchPrep& p, const RngKey& key, uint64_t 
     MatchRng r; r.blk_id = 0xFFFFFFFFu; r.count = 0; r.blk.x = r.blk.y = r.blk.z = r.blk.w = 0;
     for (;;) {
         if ((m.avail.a | m.avail.b) == 0u) break;
-        if (fdo_match_single_owner_mask(m) != 0u) fdo_match_rule1(m);     // (rule 1 finds nothing while the mask is empty)
+        if (fdo_match_single_owner_mask(m) != 0u) {                       // (rule 1 finds nothing while the mask is empty)
+            // The LAST open seat takes what is left.  Rule 4 hands a card to the first seat in seat order that can hold it, so the
+            // seats fill up one after the other and a third of a sample's cards (7.5 of 21, host-simulator counts) reach the last seat
+            // through rule 1, one assign_card each.  When one seat is open, every available card type is allowed for it and the
+            // counts agree, rule 1 would assign exactly the available multiset to it and the sample would be complete (no rule
+            // draws in between): do that as one multiset addition.  Any other situation (a card nobody may hold: a dead end) takes
+            // the general path, so partial results stay identical too.
+            const uint32_t a0 = m.allow[0], a1 = m.allow[1], a2 = m.allow[2], al = a0 | a1 | a2;
+            const bool one_open = ((a0 | a1) == 0u) | ((a0 | a2) == 0u) | ((a1 | a2) == 0u);
+            if (one_open && (m.avail.a & ~al) == 0u) {
+                const uint32_t j = a0 ? 0u : (a1 ? 1u : 2u);
+                const uint32_t sl = j == 0u ? m.slots[0] : (j == 1u ? m.slots[1] : m.slots[2]);
+                if (popc(m.avail.a) + popc(m.avail.b) == sl) {
+#pragma unroll
+                    for (uint32_t o = 0; o < 3u; ++o) {
+                        const uint32_t xa = o == j ? m.avail.a : 0u, xb = o == j ? m.avail.b : 0u;
+                        m.assigned[o].b |= xb | (m.assigned[o].a & xa);
+                        m.assigned[o].a |= xa;
+                    }
+                    m.avail.a = 0u; m.avail.b = 0u;
+                    break;
+                }
+            }
+            fdo_match_rule1(m);
+        }
         if (fdo_match_rule2(m)) continue;
         if (fdo_match_rule3(m)) continue;
         if ((m.avail.a | m.avail.b) == 0u) break;
