@@ -110,25 +110,30 @@ struct MatchState {
     uint32_t slots[3], must_q, status;
 };
 
-// CardMatchingState::assign_card (:49-76), branch-free over compile-time slot numbers (the record of a sample stays in registers:
-// the indexed form put it into local memory — 13 % of the kernel's instructions were LDL / STL, profiles/r01_determinize_attribution.json):
-// the receiving slot is selected by a mask.
+// CardMatchingState::assign_card (:49-76) over compile-time slot numbers (the record of a sample stays in registers: the indexed
+// form put it into local memory — 13 % of the kernel's instructions were LDL / STL, profiles/r01_determinize_attribution.json).
 // (Tried and rejected: the rules as a one-card-per-iteration state machine with a single assign site, which is what sped up the
 // rs-doko sampler by 1.5x — here the lanes of a warp then sit in different rules and every iteration runs all of them: 2x slower.)
-DK_HD void fdo_match_assign(MatchState& m, uint32_t j, uint32_t c) {
+template <uint32_t J>
+DK_HD void fdo_match_assign_to(MatchState& m, uint32_t c) {
     const uint32_t bit = 1u << c;
     h2_remove_one(m.avail, bit);
+    h2_add(m.assigned[J], bit);
+    m.slots[J] -= 1u;
+    const bool full = m.slots[J] == 0u;
 #pragma unroll
-    for (uint32_t o = 0; o < 3u; ++o) {
-        const bool mine = o == j;
-        h2_add(m.assigned[o], mine ? bit : 0u);
-        m.slots[o] -= mine ? 1u : 0u;
-        const bool full = mine && m.slots[o] == 0u;
-        m.len[o] -= (m.allow[o] & bit) ? 1u : 0u;
-        m.len[o] = full ? MATCH_LEN_DONE : m.len[o];
-        m.allow[o] = full ? 0u : m.allow[o];                              // a full seat can hold nothing more
-    }
-    if (m.must_q != 0u && c == CARD_CQ) m.must_q &= ~(1u << j);           // (must_q is almost always empty)
+    for (uint32_t o = 0; o < 3u; ++o) m.len[o] -= (o == J || (m.allow[o] & bit)) ? 1u : 0u;       // (the receiving slot always could hold the card)
+    m.len[J] = full ? MATCH_LEN_DONE : m.len[J];
+    m.allow[J] = full ? 0u : m.allow[J];                                   // a full seat can hold nothing more
+    if (m.must_q != 0u && c == CARD_CQ) m.must_q &= ~(1u << J);           // (must_q is almost always empty)
+}
+// The receiving slot as a compile-time constant: a block works on ONE info-state, so its threads fill the same seats in the same order
+// (rule 4 hands a card to the first seat in seat order that can hold it) and `j` is almost always uniform over a warp — three
+// specialised bodies of 18 instructions behind a switch instead of one branch-free body of 49 that updates every slot under a mask.
+DK_HD void fdo_match_assign(MatchState& m, uint32_t j, uint32_t c) {
+    if (j == 0u) fdo_match_assign_to<0>(m, c);
+    else if (j == 1u) fdo_match_assign_to<1>(m, c);
+    else fdo_match_assign_to<2>(m, c);
 }
 // rule 1 (:78-113): walk a SNAPSHOT of the available cards (copy-A bits ascending, then copy-B bits) and hand every card that
 // exactly one hidden seat can hold to that seat.  The seats' possible sets only change when a card is assigned, so between two
