@@ -125,7 +125,7 @@ DK_HD void fdo_match_assign_to(MatchState& m, uint32_t c) {
     for (uint32_t o = 0; o < 3u; ++o) m.len[o] -= (o == J || (m.allow[o] & bit)) ? 1u : 0u;       // (the receiving slot always could hold the card)
     m.len[J] = full ? MATCH_LEN_DONE : m.len[J];
     m.allow[J] = full ? 0u : m.allow[J];                                   // a full seat can hold nothing more
-    if (m.must_q != 0u && c == CARD_CQ) m.must_q &= ~(1u << J);           // (must_q is almost always empty)
+    // (`must_q` is not touched: rule 3 reads "must still receive a ♣Q" as "had to at the start and holds none yet")
 }
 // The receiving slot as a compile-time constant: a block works on ONE info-state, so its threads fill the same seats in the same order
 // (rule 4 hands a card to the first seat in seat order that can hold it) and `j` is almost always uniform over a warp — three
@@ -177,13 +177,16 @@ DK_HD bool fdo_match_rule2(MatchState& m) {
     }
     return changed;
 }
-// rule 3 (:147-172): a seat that must hold a ♣Q gets one.
+// rule 3 (:147-172): a seat that must hold a ♣Q gets one.  The reference clears a seat's obligation when the seat receives a ♣Q by
+// whatever rule; here the obligation mask stays as the info-state gave it (block-uniform, almost always empty: one test) and the seat's
+// assigned hand says whether it has been met.
 DK_HD bool fdo_match_rule3(MatchState& m) {
     if (m.must_q == 0u) return false;                          // the common case
     bool changed = false;
+    const uint32_t CQ = 1u << CARD_CQ;
 #pragma unroll
     for (uint32_t j = 0; j < 3u; ++j)
-        if (((m.must_q >> j) & 1u) && (m.avail.a & m.allow[j] & (1u << CARD_CQ))) { changed = true; fdo_match_assign(m, j, CARD_CQ); }
+        if (((m.must_q >> j) & 1u) && !(m.assigned[j].a & CQ) && (m.avail.a & m.allow[j] & CQ)) { changed = true; fdo_match_assign(m, j, CARD_CQ); }
     return changed;
 }
 
@@ -201,8 +204,7 @@ DK_HD uint32_t fdo_match_sample(const MatchPrep& p, const RngKey& key, uint64_t 
         m.len[j] = p.slots[j] ? h2_len(p.possible[j]) : MATCH_LEN_DONE;
     }
     MatchRng r; r.blk_id = 0xFFFFFFFFu; r.count = 0; r.blk.x = r.blk.y = r.blk.z = r.blk.w = 0;
-    for (;;) {
-        if ((m.avail.a | m.avail.b) == 0u) break;
+    for (;;) {                                                            // (with nothing left to assign no rule fires and the test before rule 4 ends the loop)
         if (fdo_match_single_owner_mask(m) != 0u) {                       // (rule 1 finds nothing while the mask is empty)
             // The LAST open seat takes what is left.  Rule 4 hands a card to the first seat in seat order that can hold it, so the
             // seats fill up one after the other and a third of a sample's cards (7.5 of 21, host-simulator counts) reach the last seat
