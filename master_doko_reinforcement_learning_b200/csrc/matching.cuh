@@ -26,6 +26,7 @@ struct MatchPrep {
     uint32_t observer;
     uint32_t played_q;      // 2 bits per ABSOLUTE seat: ♣Q already played by that seat
     uint32_t visible;       // 4 bits per ABSOLUTE seat: 0 NoneYet, 1 NotRevealed, else 2 + FdoReservation code (revealed)
+    uint32_t hidden_res;    // != 0: some seat's reservation is NotRevealed, so a sample draws reservations (SITE_MATCH_RESERVATION)
     uint32_t obs_a, obs_b;  // the observer's real hand
     uint32_t valid;         // 0 when the game is finished (card_matching would panic)
 };
@@ -57,6 +58,9 @@ DK_HD void fdo_match_prepare(const dk_state& s, MatchPrep& m) {
         vis |= v << (4u * seat);
     }
     m.visible = vis;
+    uint32_t hidden = 0;
+    for (uint32_t seat = 0; seat < 4u; ++seat) hidden |= ((vis >> (4u * seat)) & 15u) == 1u ? 1u << seat : 0u;
+    m.hidden_res = hidden;
     uint32_t pq = 0;
     const uint32_t ci = s.card_index;
     for (uint32_t j = 0; j < ci; ++j)
@@ -252,7 +256,8 @@ DK_HD uint32_t fdo_match_sample(const MatchPrep& p, const RngKey& key, uint64_t 
 #pragma unroll
     for (uint32_t j = 0; j < 3u; ++j) { uint32_t seat = j + (j >= obs ? 1u : 0u); oa[seat] = m.assigned[j].a; ob[seat] = m.assigned[j].b; }
     oa[obs] = p.obs_a; ob[obs] = p.obs_b;
-    U4 rb = rng_block(key, SITE_MATCH_RESERVATION, 0);
+    U4 rb; rb.x = rb.y = rb.z = rb.w = 0;
+    if (p.hidden_res != 0u) rb = rng_block(key, SITE_MATCH_RESERVATION, 0);   // (block-uniform; in the card phase every reservation is known)
     const uint32_t CQ = 1u << CARD_CQ;
     for (uint32_t seat = 0; seat < 4u; ++seat) {
         hands_out[seat] = (uint64_t)oa[seat] | ((uint64_t)ob[seat] << 24);
