@@ -186,14 +186,15 @@ DK_HD uint32_t doko_assign_sample(const AssignPrep& p, const RngKey& key, uint64
             // distribute_single_card_randomly (:419-456)
             const uint32_t n = a.n_remaining;
             if (n == 0u) break;
-            uint32_t w0, w1;
+            // one word of SITE_ASSIGN per card: the card and then its seat are chained draws from it (draw_chain, dk_common.cuh; relative
+            // bias <= 36*3 / 2^32) — the sampler drew two words per card before, 18 of a sample's Philox blocks instead of 9
+            uint32_t w0;
             { uint32_t o = ord++; if ((o >> 2) != blk_id) { blk_id = o >> 2; blk = rng_block(key, SITE_ASSIGN, blk_id); } w0 = u4_word(blk, o & 3u); }
-            const uint32_t k = mulhi(w0, n);
+            const uint32_t k = draw_chain(w0, n);
             c = adj3 ? h2_select_adjacent_lut(a.remaining, k, adj3) : h2_select_adjacent(a.remaining, k);
             const uint32_t e = doko_assign_eligible(a, 1u << c);
             if (e == 0u) { status = 1u; break; }            // `.choose(rng).unwrap()` on an empty list would panic
-            { uint32_t o = ord++; if ((o >> 2) != blk_id) { blk_id = o >> 2; blk = rng_block(key, SITE_ASSIGN, blk_id); } w1 = u4_word(blk, o & 3u); }
-            player = select_lsb3(e, mulhi(w1, popc(e)));
+            player = select_lsb3(e, draw_chain(w0, popc(e)));
         }
         doko_assign_distribute(a, player, c);
     }

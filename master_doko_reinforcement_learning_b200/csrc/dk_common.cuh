@@ -40,6 +40,15 @@ DK_HD uint32_t mulhi(uint32_t a, uint32_t b) {
     return (uint32_t)(((uint64_t)a * b) >> 32);
 #endif
 }
+// Chained draw (DESIGN.md "Philox parity contract"): one 32-bit word serves several draws in a row.  (idx, rest) = (high, low) half of
+// v * n: idx is the draw over n choices, the low half is the fractional part of v * n / 2^32 — uniform again on a grid of spacing
+// n / 2^32 — and feeds the next draw.  After the draws n_0 .. n_{k-1} the word has become word * n_0 * .. * n_{k-1} mod 2^32, so a
+// caller that resumes in the middle of a chain needs only that product; the relative bias of a draw is below n_0 * .. * n_k / 2^32.
+DK_HD uint32_t draw_chain(uint32_t& v, uint32_t n) {
+    const uint64_t p = (uint64_t)v * n;
+    v = (uint32_t)p;
+    return (uint32_t)(p >> 32);
+}
 DK_HD uint32_t ffs0(uint32_t x) {  // index of lowest set bit (x != 0)
 #if defined(__CUDA_ARCH__)
     return (uint32_t)(__ffs((int)x) - 1);
@@ -67,7 +76,8 @@ DK_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) {  // low 32 bits
 // Parity stream shared with the oracle (DESIGN.md "Philox parity contract"):
 //   counter = (unit_lo, unit_hi, site<<16 | block, epoch), key = (seed_lo, seed_hi);
 //   decision k of call-site class `site` inside one unit uses word (k & 3) of block (k >> 2),
-//   mapped onto n choices by idx = mulhi(word, n); announcement decisions take one BIT each (fdo_rules.cuh AnnStream).
+//   mapped onto n choices by idx = mulhi(word, n); announcement decisions take one BIT each (fdo_rules.cuh AnnStream);
+//   the deal draws three times from a word and a trick's four card draws share the word of the trick (draw_chain below).
 enum Site : uint32_t {
     SITE_DEAL = 0, SITE_RESERVATION = 1, SITE_ANNOUNCEMENT = 2, SITE_CARD = 3,
     SITE_MATCH_CARD = 4, SITE_MATCH_RESERVATION = 5, SITE_ASSIGN = 6, SITE_STEP = 7, SITE_KEEP = 8, SITE_EXPAND = 9

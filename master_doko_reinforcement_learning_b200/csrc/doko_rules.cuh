@@ -59,10 +59,10 @@ DK_HD void doko_trick_acc_clear(DokoTrickAcc& a) { a.follow = 0; a.best = 0; a.a
 
 // Card step of frame seat K (rs-doko/src/action/allowed_actions.rs:153-192, state/state.rs:194-252).
 template <int K, bool SEL12 = false>
-DK_HD uint32_t doko_card_step(DokoLive& g, uint32_t& h, DokoTrickAcc& a, uint32_t word, const uint32_t* __restrict__ lut) {
+DK_HD uint32_t doko_card_step(DokoLive& g, uint32_t& h, DokoTrickAcc& a, uint32_t& word, const uint32_t* __restrict__ lut) {
     uint32_t mask = h;
     if (K > 0) { uint32_t f = h & a.follow; mask = f ? f : h; }
-    uint32_t idx = mulhi(word, popc(mask));
+    uint32_t idx = draw_chain(word, popc(mask));         // the trick's word serves its four draws in a row (dk_common.cuh)
     uint32_t c = SEL12 ? pick_msb_rank24_tab(mask, idx, reinterpret_cast<const uint64_t*>(lut + SEL12_LUT_BASE)) : pick_msb_rank24_lut(mask, idx, lut);
     uint32_t bit = 1u << c;
     uint32_t dbl = g.dup & bit;
@@ -123,6 +123,7 @@ struct DokoResume {
     uint32_t res_action[4];
     uint32_t t0, k0;
     DokoTrickAcc acc;
+    uint32_t chain_mul;    // product of the legal-card counts of the k0 plays already made in trick t0 (see FdoResume)
 };
 
 // trace (optional, FRESH only): 52 action ids in play order.
@@ -143,27 +144,32 @@ DK_HD void doko_play_to_end(DokoLive& g, const RngKey& key, const DokoResume* rs
     uint32_t t = FRESH ? 0u : rs->t0;
     // (same shape as fdo_play_to_end: a resumed game first finishes its partial trick; the loop body is unconditional; the twelfth
     // trick, when it starts from its first card, is four forced moves and needs neither its Philox block nor a rank select)
+    // (card draws: trick t takes word t & 3 of block t >> 2 of SITE_CARD, chained over the trick's four plays — see fdo_play_to_end)
+    U4 cblk;
+    cblk.x = cblk.y = cblk.z = cblk.w = 0u;
     if (!FRESH && t < 12u) {
-        const U4 blk = rng_block(key, SITE_CARD, t);
+        cblk = rng_block(key, SITE_CARD, t >> 2);
+        uint32_t word = u4_word(cblk, t & 3u) * rs->chain_mul;
         DokoTrickAcc a;
         doko_trick_acc_clear(a);
         const uint32_t k0 = rs->k0;
         if (k0 > 0u) a = rs->acc;
-        if (k0 <= 0u) doko_card_step<0, SEL12>(g, g.h0, a, blk.x, lut);
-        if (k0 <= 1u) doko_card_step<1, SEL12>(g, g.h1, a, blk.y, lut);
-        if (k0 <= 2u) doko_card_step<2, SEL12>(g, g.h2, a, blk.z, lut);
-        doko_card_step<3, SEL12>(g, g.h3, a, blk.w, lut);
+        if (k0 <= 0u) doko_card_step<0, SEL12>(g, g.h0, a, word, lut);
+        if (k0 <= 1u) doko_card_step<1, SEL12>(g, g.h1, a, word, lut);
+        if (k0 <= 2u) doko_card_step<2, SEL12>(g, g.h2, a, word, lut);
+        doko_card_step<3, SEL12>(g, g.h3, a, word, lut);
         doko_trick_done(g, a, t);
         ++t;
     }
     for (; t < 11u; ++t) {
-        const U4 blk = rng_block(key, SITE_CARD, t);
+        if ((t & 3u) == 0u) cblk = rng_block(key, SITE_CARD, t >> 2);
+        uint32_t word = u4_word(cblk, t & 3u);
         DokoTrickAcc a;
         doko_trick_acc_clear(a);
-        const uint32_t c0 = doko_card_step<0, SEL12>(g, g.h0, a, blk.x, lut);
-        const uint32_t c1 = doko_card_step<1, SEL12>(g, g.h1, a, blk.y, lut);
-        const uint32_t c2 = doko_card_step<2, SEL12>(g, g.h2, a, blk.z, lut);
-        const uint32_t c3 = doko_card_step<3, SEL12>(g, g.h3, a, blk.w, lut);
+        const uint32_t c0 = doko_card_step<0, SEL12>(g, g.h0, a, word, lut);
+        const uint32_t c1 = doko_card_step<1, SEL12>(g, g.h1, a, word, lut);
+        const uint32_t c2 = doko_card_step<2, SEL12>(g, g.h2, a, word, lut);
+        const uint32_t c3 = doko_card_step<3, SEL12>(g, g.h3, a, word, lut);
         if (TRACE) { trace[4 + 4 * t] = (uint8_t)c0; trace[5 + 4 * t] = (uint8_t)c1; trace[6 + 4 * t] = (uint8_t)c2; trace[7 + 4 * t] = (uint8_t)c3; }
         doko_trick_done(g, a, t);
     }

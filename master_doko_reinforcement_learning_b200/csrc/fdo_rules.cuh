@@ -166,13 +166,16 @@ DK_HD void fdo_live_clear(FdoLive& g) {
     g.last_winner = 0; g.steps = 0; g.ann_count = 0;
 }
 
-// Deal: start seat = draw(4) from word 0 of SITE_DEAL, then a Durstenfeld shuffle (i = 47..1, j = draw(i+1), swap) of
-// [c0,c0,c1,c1,...] using words 1..47; seat p receives positions 12p..12p+11 (add: copy A first, then copy B)
-// (rs-full-doko/src/state/state.rs:169-178, hand/hand.rs:116-188).  `Deck` provides 48 bytes of per-thread scratch, set up
-// a word at a time and then byte-addressed (shared memory on the device, word-interleaved across the block: conflict-free).  Position i is final after step i, so its card goes straight into seat i/12's hand.
+// Deal: draw 0 is the start seat (draw(4)), draws s = 1..47 are the steps i = 48 - s = 47..1 of a Durstenfeld shuffle (j = draw(i+1),
+// swap) of [c0,c0,c1,c1,...]; seat p receives positions 12p..12p+11 (add: copy A first, then copy B)
+// (rs-full-doko/src/state/state.rs:169-178, hand/hand.rs:116-188).  Draw s takes word min(s / 3, 11) of SITE_DEAL for s <= 36: three
+// chained draws per word (draw_chain; the twelfth word serves the four draws 33..36), so the whole deal is THREE Philox blocks — it was
+// ten with one word per draw, 280 of a game's 4700 instructions.  Relative bias of a draw <= 48*47*46 / 2^32 = 2.4e-5.
+// `Deck` provides 48 bytes of per-thread scratch, set up a word at a time and then byte-addressed (shared memory on the device,
+// word-interleaved across the block: conflict-free).  Position i is final after step i, so its card goes straight into seat i/12's hand.
 // Only the steps i = 47..12 are executed: the steps i = 11..1 permute positions 0..11 among themselves — all of them seat 0's — so
-// seat 0 simply holds what the other three seats did not get (two copies of every type minus the copies given away).  Words 37..47 of
-// the site (two Philox blocks and eleven draws, 270 of a game's 4700 instructions) are never computed; nothing else moves in the stream.
+// seat 0 simply holds what the other three seats did not get (two copies of every type minus the copies given away).  The draws
+// 37..47 (words 12..15 of the site, three per word) are never computed.
 template <class Deck>
 DK_HD void fdo_deal(FdoLive& g, const RngKey& key, Deck& deck, uint32_t abs_hand[4], uint32_t& dup, uint32_t& start) {
 #pragma unroll
@@ -181,23 +184,27 @@ DK_HD void fdo_deal(FdoLive& g, const RngKey& key, Deck& deck, uint32_t abs_hand
     uint32_t d = 0;
     start = 0;
 #pragma unroll
-    for (uint32_t b = 0; b < 10; ++b) {                   // ord = 0 .. 36 <=> i = 47 .. 12
+    for (uint32_t b = 0; b < 3; ++b) {                    // draws 0 .. 36 <=> start seat, i = 47 .. 12
         U4 blk = rng_block(key, SITE_DEAL, b);
         uint32_t ws[4] = {blk.x, blk.y, blk.z, blk.w};
 #pragma unroll
         for (uint32_t q = 0; q < 4; ++q) {
-            uint32_t ord = 4u * b + q;
-            if (ord == 0u) { start = mulhi(ws[q], 4u); continue; }
-            if (ord > 36u) continue;
-            uint32_t i = 48u - ord;                       // 47 .. 12
-            uint32_t j = mulhi(ws[q], i + 1u);
-            uint32_t ci = deck.get8(i);                   // card currently at position i (byte access: no shift / mask arithmetic)
-            uint32_t cj = deck.get8(j);                   // card that ends up at position i
-            deck.set8(j, ci);
-            uint32_t bit = 1u << cj;
-            uint32_t seat = i / 12u;                      // 3, 2 or 1
-            d |= h[seat] & bit;
-            h[seat] |= bit;
+            const uint32_t word = 4u * b + q;
+            uint32_t v = ws[q];
+#pragma unroll
+            for (uint32_t e = 0; e < (word == 11u ? 4u : 3u); ++e) {
+                const uint32_t ord = 3u * word + e;
+                if (ord == 0u) { start = draw_chain(v, 4u); continue; }
+                uint32_t i = 48u - ord;                   // 47 .. 12
+                uint32_t j = draw_chain(v, i + 1u);
+                uint32_t ci = deck.get8(i);               // card currently at position i (byte access: no shift / mask arithmetic)
+                uint32_t cj = deck.get8(j);               // card that ends up at position i
+                deck.set8(j, ci);
+                uint32_t bit = 1u << cj;
+                uint32_t seat = i / 12u;                  // 3, 2 or 1
+                d |= h[seat] & bit;
+                h[seat] |= bit;
+            }
         }
     }
     {   // seat 0: per card type, the copies nobody else holds
@@ -395,14 +402,14 @@ DK_HD void trick_acc_clear(TrickAcc& a) { a.follow = 0; a.best = 0; a.acc = 0; a
 
 // Card step of frame seat K (compile-time) with hand register `h` (action/allowed_actions.rs:97-140, state.rs:274-357).
 template <int K, bool SEL12 = false>
-DK_HD void fdo_card_step(FdoLive& g, uint32_t& h, TrickAcc& a, uint32_t word, bool last_trick, const uint32_t* __restrict__ lut) {
+DK_HD void fdo_card_step(FdoLive& g, uint32_t& h, TrickAcc& a, uint32_t& word, bool last_trick, const uint32_t* __restrict__ lut) {
     uint32_t mask = h;
     if (K > 0 && !last_trick) {                           // state.rs:360-372: no colour is enforced in the 12th trick
         uint32_t f = h & a.follow;
         mask = f ? f : h;
     }
     uint32_t n = popc(mask);
-    uint32_t idx = mulhi(word, n);
+    uint32_t idx = draw_chain(word, n);                   // the trick's word serves its four draws in a row (dk_common.cuh)
     uint32_t c = SEL12 ? pick_msb_rank24_tab(mask, idx, reinterpret_cast<const uint64_t*>(lut + SEL12_LUT_BASE)) : pick_msb_rank24_lut(mask, idx, lut);
     uint32_t bit = 1u << c;
     uint32_t dbl = g.dup & bit;                           // hand.remove: a doubled card stays in the hand once
@@ -489,6 +496,8 @@ struct FdoResume {
     uint32_t ann_ci, ann_p, ann_turns;   // where the announcement protocol resumes: round before card ann_ci, next ABSOLUTE
                            // seat to ask, turns without call.  Phase PlayCard (round already over) → ann_ci = card_index + 1.
     TrickAcc acc;          // partial trick accumulator (valid when k0 > 0)
+    uint32_t chain_mul;    // product of the legal-card counts of the k0 plays already made in trick t0 (1 when k0 == 0): the trick's
+                           // word times this product is where the chained card draws of the trick continue (draw_chain)
 };
 
 // Plays the game to the end.  FRESH: hands/base already set by the deal, nothing played yet.
@@ -513,30 +522,36 @@ DK_HD void fdo_play_to_end(FdoLive& g, const RngKey& key, const FdoResume* rs, c
     // body as a fresh game.  With the `is this position already played` tests inside the one loop, the loop body was divergent code:
     // the shared-memory window base (a uniform register on sm_100) was recomputed at every table access — 4 of ~45 instructions per
     // card step of the kernels that start from stored records (profiles/r02_k4_roll_v1 attribution).
+    // Card draws: trick t takes word t & 3 of block t >> 2 of SITE_CARD, its four draws chained through draw_chain — three Philox blocks
+    // per game instead of eleven (320 of a game's 4700 instructions).  The block stays in registers over four tricks.
+    U4 cblk;
+    cblk.x = cblk.y = cblk.z = cblk.w = 0u;
     if (!FRESH && t < 12u) {
         starts |= g.base << (2u * t);
-        const U4 blk = rng_block(key, SITE_CARD, t);
+        cblk = rng_block(key, SITE_CARD, t >> 2);
+        uint32_t word = u4_word(cblk, t & 3u) * rs->chain_mul;
         TrickAcc a;
         trick_acc_clear(a);
         const uint32_t k0 = rs->k0;
         if (k0 > 0u) a = rs->acc;
         const bool last = t == 11u;
-        if (k0 <= 0u) fdo_card_step<0, SEL12>(g, g.h0, a, blk.x, last, lut);
-        if (k0 <= 1u) fdo_card_step<1, SEL12>(g, g.h1, a, blk.y, last, lut);
-        if (k0 <= 2u) fdo_card_step<2, SEL12>(g, g.h2, a, blk.z, last, lut);
-        fdo_card_step<3, SEL12>(g, g.h3, a, blk.w, last, lut);
+        if (k0 <= 0u) fdo_card_step<0, SEL12>(g, g.h0, a, word, last, lut);
+        if (k0 <= 1u) fdo_card_step<1, SEL12>(g, g.h1, a, word, last, lut);
+        if (k0 <= 2u) fdo_card_step<2, SEL12>(g, g.h2, a, word, last, lut);
+        fdo_card_step<3, SEL12>(g, g.h3, a, word, last, lut);
         fdo_trick_done(g, a, t);
         ++t;
     }
     for (; t < 11u; ++t) {
         starts |= g.base << (2u * t);
-        const U4 blk = rng_block(key, SITE_CARD, t);
+        if ((t & 3u) == 0u) cblk = rng_block(key, SITE_CARD, t >> 2);
+        uint32_t word = u4_word(cblk, t & 3u);
         TrickAcc a;
         trick_acc_clear(a);
-        fdo_card_step<0, SEL12>(g, g.h0, a, blk.x, false, lut);
-        fdo_card_step<1, SEL12>(g, g.h1, a, blk.y, false, lut);
-        fdo_card_step<2, SEL12>(g, g.h2, a, blk.z, false, lut);
-        fdo_card_step<3, SEL12>(g, g.h3, a, blk.w, false, lut);
+        fdo_card_step<0, SEL12>(g, g.h0, a, word, false, lut);
+        fdo_card_step<1, SEL12>(g, g.h1, a, word, false, lut);
+        fdo_card_step<2, SEL12>(g, g.h2, a, word, false, lut);
+        fdo_card_step<3, SEL12>(g, g.h3, a, word, false, lut);
         fdo_trick_done(g, a, t);
     }
     if (t == 11u) {                                       // the last trick from its first card: forced moves (fdo_card_step_last)

@@ -1003,15 +1003,8 @@ fdo_leaf_rollouts_kernel(RngParams rp, uint64_t leaf0, uint64_t n_leaves, uint32
             const uint32_t res4 = __ldg(reinterpret_cast<const uint32_t*>(smp_res) + o);
             FdoLive g = live0;
             FdoResume rs = resume0;
-            // clone_with_different_hands_and_reservations (state.rs:96-119) on the playout form: frame seat k = absolute seat base + k
-            const uint32_t base = g.base;
-            const uint32_t any[4] = {hand_any24(h01.x), hand_any24(h01.y), hand_any24(h23.x), hand_any24(h23.y)};
-            g.dup = hand_both24(h01.x) | hand_both24(h01.y) | hand_both24(h23.x) | hand_both24(h23.y);
-            g.h0 = any[base & 3u]; g.h1 = any[(base + 1u) & 3u]; g.h2 = any[(base + 2u) & 3u]; g.h3 = any[(base + 3u) & 3u];
-            if (rs.n_res < 4u) {                                                      // reservation phase: frame base = game start seat
-#pragma unroll
-                for (uint32_t k = 0; k < 3u; ++k) if (k < rs.n_res) rs.res_action[k] = fdo_action_from_res_code((res4 >> (8u * ((base + k) & 3u))) & 255u);
-            }
+            const uint64_t sh[4] = {h01.x, h01.y, h23.x, h23.y};
+            fdo_live_with_sample(g, rs, leaf, sh, res4);
             fdo_play_to_end<false, false, true, false>(g, key, &rs, lut);
             fdo_final_points(g, p);
         } else {

@@ -194,7 +194,9 @@ DK_HD bool fdo_match_rule3(MatchState& m) {
     return changed;
 }
 
-struct MatchRng { U4 blk; uint32_t blk_id, count; };
+// Rule 4's draws are chained three to a word (draw_chain, dk_common.cuh): use k of SITE_MATCH_CARD takes word k / 3 — a sample makes 13
+// of them on average, so one or two Philox blocks instead of four; relative bias of a draw <= 36*35*34 / 2^32 = 1e-5.
+struct MatchRng { U4 blk; uint32_t blk_id, words, v, left; };   // cached block, its index, words consumed, what is left of the running word, draws left in it
 
 // One sample: execute (:207-238) + hidden reservations (:418-464).  hands_out / res_out by ABSOLUTE seat.
 // rank6 (optional): the 64-entry rank-select table (rank_lut6_entry) in shared memory — the card of rule 4 then comes from two popc
@@ -207,7 +209,7 @@ DK_HD uint32_t fdo_match_sample(const MatchPrep& p, const RngKey& key, uint64_t 
         m.allow[j] = p.possible[j].a; m.slots[j] = p.slots[j]; m.assigned[j].a = 0; m.assigned[j].b = 0;
         m.len[j] = p.slots[j] ? h2_len(p.possible[j]) : MATCH_LEN_DONE;
     }
-    MatchRng r; r.blk_id = 0xFFFFFFFFu; r.count = 0; r.blk.x = r.blk.y = r.blk.z = r.blk.w = 0;
+    MatchRng r; r.blk_id = 0xFFFFFFFFu; r.words = 0; r.v = 0; r.left = 0; r.blk.x = r.blk.y = r.blk.z = r.blk.w = 0;
     for (;;) {                                                            // (with nothing left to assign no rule fires and the test before rule 4 ends the loop)
         if (fdo_match_single_owner_mask(m) != 0u) {                       // (rule 1 finds nothing while the mask is empty)
             // The LAST open seat takes what is left.  Rule 4 hands a card to the first seat in seat order that can hold it, so the
@@ -240,9 +242,14 @@ DK_HD uint32_t fdo_match_sample(const MatchPrep& p, const RngKey& key, uint64_t 
         // rule 4 (:174-204): a uniformly chosen available card (ascending-bit index over both planes) goes to the FIRST seat
         // in seat order that can hold it
         uint32_t na = popc(m.avail.a), n = na + popc(m.avail.b);
-        uint32_t ord = r.count++;
-        if ((ord >> 2) != r.blk_id) { r.blk_id = ord >> 2; r.blk = rng_block(key, SITE_MATCH_CARD, ord >> 2); }
-        uint32_t idx = mulhi(u4_word(r.blk, ord & 3u), n);
+        if (r.left == 0u) {
+            const uint32_t wi = r.words++;
+            if ((wi >> 2) != r.blk_id) { r.blk_id = wi >> 2; r.blk = rng_block(key, SITE_MATCH_CARD, wi >> 2); }
+            r.v = u4_word(r.blk, wi & 3u);
+            r.left = 3u;
+        }
+        r.left--;
+        uint32_t idx = draw_chain(r.v, n);
         const bool first_plane = idx < na;
         const uint32_t plane = first_plane ? m.avail.a : m.avail.b, k = first_plane ? idx : idx - na;
         uint32_t c = rank6 ? select_lsb24_lut(plane, k, rank6 - RANK_LUT_BASE) : select_lsb24(plane, k);

@@ -370,6 +370,14 @@ DK_HD uint32_t fdo_state_apply_az(dk_state& s, uint32_t action, bool skip_single
     return 0;
 }
 
+// The chained card draws of a trick (draw_chain): how many card types the k-th play of the running trick chose from — the seat's hand
+// (`hand_any`: its card types NOW) with the played card `c` back in it, restricted to the led colour (`follow`, k > 0) when it can
+// follow.  A playout that resumes inside a trick continues the chain at word * product of these counts (FdoResume::chain_mul).
+DK_HD uint32_t chain_count(uint32_t hand_any, uint32_t c, uint32_t k, uint32_t follow) {
+    const uint32_t had = hand_any | (1u << c), f = k ? had & follow : 0u;
+    return popc(f ? f : had);
+}
+
 // Bridge: stored state → register-resident playout form.  Returns false when the game is already finished.
 template <bool IDX = false>
 DK_HD bool fdo_state_to_live(const dk_state& s, FdoLive& g, FdoResume& rs) {
@@ -381,7 +389,7 @@ DK_HD bool fdo_state_to_live(const dk_state& s, FdoLive& g, FdoResume& rs) {
     for (uint32_t p = 0; p < 4u; ++p) dup |= hand_both24(s.hands[p]);
     g.dup = dup;
     rs.n_res = s.n_reservations;
-    rs.t0 = 0; rs.k0 = 0; rs.starts = 0; rs.ann_ci = 0; rs.ann_p = 0; rs.ann_turns = 0xFFFFFFFFu;
+    rs.t0 = 0; rs.k0 = 0; rs.starts = 0; rs.ann_ci = 0; rs.ann_p = 0; rs.ann_turns = 0xFFFFFFFFu; rs.chain_mul = 1u;
     trick_acc_clear(rs.acc);
 #pragma unroll
     for (uint32_t i = 0; i < 4u; ++i) rs.res_action[i] = i < s.n_reservations ? fdo_action_from_res_code(s.reservations[i]) : 0u;
@@ -433,6 +441,7 @@ DK_HD bool fdo_state_to_live(const dk_state& s, FdoLive& g, FdoResume& rs) {
             if (k == 0u || cand > rs.acc.best) rs.acc.best = cand;
             rs.acc.acc += v;
             rs.acc.fox += (v & POW_FOX_BIT) << k;
+            rs.chain_mul *= chain_count(hand_any24(st_hand<IDX>(s, (base + k) & 3u)), c, k, rs.acc.follow);
         }
         if (phase == DK_PHASE_ANNOUNCEMENT) { rs.ann_ci = ci; rs.ann_p = st_cur(s); rs.ann_turns = st_turns(s); }
         else { rs.ann_ci = ci + 1u; rs.ann_turns = 0xFFFFFFFFu; }            // the round before card ci is over
@@ -441,6 +450,29 @@ DK_HD bool fdo_state_to_live(const dk_state& s, FdoLive& g, FdoResume& rs) {
     g.h0 = hand_any24(s.hands[0]); g.h1 = hand_any24(s.hands[1]); g.h2 = hand_any24(s.hands[2]); g.h3 = hand_any24(s.hands[3]);
     fdo_rotate(g, base);                                                     // frame index 0 = seat `base` (selects, no indexed array)
     return true;
+}
+
+// clone_with_different_hands_and_reservations (state.rs:96-119) on the PLAYOUT form: (g, rs) is the bridge of the info-state `leaf`
+// (fdo_state_to_live, built once per leaf), `hands` a card_matching sample by absolute seat, `res4` its reservations (one byte per
+// absolute seat).  Only what the sample changes is replaced: the four hands, the doubled-card mask, in the reservation phase the
+// hidden reservations of the seats that have declared, and — inside a trick — the product that positions the trick's chained card
+// draws (chain_count over the SAMPLED hands: the oracle positions its stream on the determinized state).
+DK_HD void fdo_live_with_sample(FdoLive& g, FdoResume& rs, const dk_state& leaf, const uint64_t hands[4], uint32_t res4) {
+    const uint32_t base = g.base;                                                 // frame seat k = absolute seat base + k
+    const uint32_t any[4] = {hand_any24(hands[0]), hand_any24(hands[1]), hand_any24(hands[2]), hand_any24(hands[3])};
+    g.dup = hand_both24(hands[0]) | hand_both24(hands[1]) | hand_both24(hands[2]) | hand_both24(hands[3]);
+    g.h0 = any[base & 3u]; g.h1 = any[(base + 1u) & 3u]; g.h2 = any[(base + 2u) & 3u]; g.h3 = any[(base + 3u) & 3u];
+    if (rs.n_res < 4u) {                                                          // reservation phase: frame base = game start seat
+#pragma unroll
+        for (uint32_t k = 0; k < 3u; ++k) if (k < rs.n_res) rs.res_action[k] = fdo_action_from_res_code((res4 >> (8u * ((base + k) & 3u))) & 255u);
+    }
+    if (rs.k0 > 0u) {
+        const uint32_t quad0 = st_quad<true>(leaf, rs.t0);
+        uint32_t m = 1u;
+#pragma unroll
+        for (uint32_t k = 0; k < 3u; ++k) if (k < rs.k0) m *= chain_count(any[(base + k) & 3u], (quad0 >> (8u * k)) & 255u, k, rs.acc.follow);
+        rs.chain_mul = m;
+    }
 }
 
 // =====================================================================================================================
@@ -546,7 +578,7 @@ DK_HD bool doko_state_to_live(const dk_state& s, DokoLive& g, DokoResume& rs) {
 #pragma unroll
     for (uint32_t p = 0; p < 4u; ++p) dup |= hand_both24(s.hands[p]);
     g.dup = dup;
-    rs.n_res = s.n_reservations; rs.t0 = 0; rs.k0 = 0;
+    rs.n_res = s.n_reservations; rs.t0 = 0; rs.k0 = 0; rs.chain_mul = 1u;
     doko_trick_acc_clear(rs.acc);
 #pragma unroll
     for (uint32_t i = 0; i < 4u; ++i) rs.res_action[i] = i < s.n_reservations ? (s.reservations[i] == 0u ? 25u : 24u) : 0u;
@@ -570,6 +602,7 @@ DK_HD bool doko_state_to_live(const dk_state& s, DokoLive& g, DokoResume& rs) {
             const uint32_t v = pow_entry_of(c, DOKO_TRUMP_MASK, rs.acc.follow), cand = v | ((3u - k) << POW_K_SHIFT);
             if (k == 0u || cand > rs.acc.best) rs.acc.best = cand;
             rs.acc.acc += v;
+            rs.chain_mul *= chain_count(hand_any24(st_hand<IDX>(s, (base + k) & 3u)), c, k, rs.acc.follow);
         }
     }
     g.base = 0;

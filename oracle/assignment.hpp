@@ -100,7 +100,7 @@ inline int distribute_single_card_randomly(AssignState& a, Rng& rng) {          
     int card = a.remaining[rng.below(SITE_ASSIGN, (uint32_t)a.remaining.size())];
     std::vector<int> p = players_for(a, card);
     if (p.empty()) return 2;
-    int player = p[rng.below(SITE_ASSIGN, (uint32_t)p.size())];
+    int player = p[rng.below_chained(SITE_ASSIGN, (uint32_t)p.size())];   // the seat comes from the card's word (chained draw, rng.hpp)
     distribute_card(a, player, card);
     return 1;
 }

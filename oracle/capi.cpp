@@ -53,6 +53,21 @@ ORC_API void orc_philox_block(const uint32_t ctr[4], const uint32_t key[2], uint
 ORC_API uint32_t orc_philox_word(uint64_t seed, uint32_t unit_lo, uint32_t unit_hi, uint32_t epoch, uint32_t site, uint32_t ordinal) {
     return philox_word(seed, unit_lo, unit_hi, epoch, site, ordinal);
 }
+// `count` consecutive draws of sub-stream `site` of the parity stream, starting at ordinal `first` (inside a trick, `chain_mul` is the
+// product of the counts already drawn from the trick's word: Rng::set_card_position).
+ORC_API void orc_philox_draws(uint64_t seed, uint32_t unit_lo, uint32_t unit_hi, uint32_t epoch, uint32_t site, uint32_t first, uint32_t chain_mul,
+                              int count, const uint32_t* n, uint32_t* out) {
+    PhiloxStream r(seed, unit_lo, unit_hi, epoch);
+    if (site == SITE_CARD) r.set_card_position(first, chain_mul); else r.set_ordinal((Site)site, first);
+    for (int i = 0; i < count; ++i) out[i] = r.below((Site)site, n[i]);
+}
+// `count` (draw, chained draw) pairs of sub-stream `site`: below(site, n0[i]) and then below_chained(site, n1[i]) from the same word.
+ORC_API void orc_philox_pair_draws(uint64_t seed, uint32_t unit_lo, uint32_t unit_hi, uint32_t epoch, uint32_t site, uint32_t first, int count,
+                                   const uint32_t* n0, const uint32_t* n1, uint32_t* out0, uint32_t* out1) {
+    PhiloxStream r(seed, unit_lo, unit_hi, epoch);
+    r.set_ordinal((Site)site, first);
+    for (int i = 0; i < count; ++i) { out0[i] = r.below((Site)site, n0[i]); out1[i] = r.below_chained((Site)site, n1[i]); }
+}
 ORC_API void orc_smallrng_u64(uint64_t seed, int count, uint64_t* out) { SmallRngStream r(seed); for (int i = 0; i < count; ++i) out[i] = r.next_u64(); }
 ORC_API void orc_smallrng_ranges(uint64_t seed, int count, const uint32_t* n, uint32_t* out) {
     SmallRngStream r(seed); for (int i = 0; i < count; ++i) out[i] = r.range_u32(n[i]);
@@ -128,7 +143,7 @@ ORC_API int orc_fdo_encode_pi(const void* h, int64_t out[311]) { return guarded(
 ORC_API int orc_fdo_random_step_philox(void* h, uint64_t seed, uint64_t unit, uint32_t epoch, int with_announcements, uint32_t ann_ordinal) {
     fdo::State& s = *(fdo::State*)h;
     PhiloxStream r(seed, (uint32_t)unit, (uint32_t)(unit >> 32), epoch);
-    r.set_ordinal(SITE_CARD, (uint32_t)s.card_index); r.set_ordinal(SITE_RESERVATION, (uint32_t)s.reservations_round.len);
+    s.position_streams(r);
     r.set_ordinal(SITE_ANNOUNCEMENT, ann_ordinal);
     int a = -1;
     bool fin = with_announcements ? s.random_action_for_current_player(r, &a) : s.random_action_for_current_player_no_announcement(r, &a);
@@ -309,8 +324,7 @@ ORC_API void orc_doko_export(const void* h, dk_state* out) { export_doko(*(const
 ORC_API int orc_doko_random_step_philox(void* h, uint64_t seed, uint64_t unit, uint32_t epoch) {
     doko::State& s = *(doko::State*)h;
     PhiloxStream r(seed, (uint32_t)unit, (uint32_t)(unit >> 32), epoch);
-    int ci = 0; for (int t = 0; t < 12; ++t) for (int k = 0; k < 4; ++k) ci += s.tricks[t].present && s.tricks[t].cards[k] >= 0;
-    r.set_ordinal(SITE_CARD, (uint32_t)ci); r.set_ordinal(SITE_RESERVATION, (uint32_t)s.reservations_round.len());
+    s.position_streams(r);
     int a = -1; bool fin = s.random_action_for_current_player(r, &a);
     return fin ? -1 : a;
 }
@@ -436,7 +450,7 @@ ORC_API void orc_fdo_random_rollout_philox(const void* h, uint64_t seed, uint64_
                                            int32_t points[4], uint32_t* steps) {
     fdo::State s = *(const fdo::State*)h;
     PhiloxStream r(seed, (uint32_t)unit, rollout, epoch);
-    r.set_ordinal(SITE_CARD, (uint32_t)s.card_index); r.set_ordinal(SITE_RESERVATION, (uint32_t)s.reservations_round.len);
+    s.position_streams(r);
     uint32_t before = s.n_play_actions;
     for (;;) { bool fin = with_announcements ? s.random_action_for_current_player(r) : s.random_action_for_current_player_no_announcement(r); if (fin) break; }
     for (int p = 0; p < 4; ++p) points[p] = s.end_of_game_stats.player_points[p];
@@ -464,7 +478,7 @@ ORC_API int orc_fdo_leaf_rollout_philox(const void* h, uint64_t seed, uint64_t u
         status = fdo::card_matching(s, r, oh, ores);
         s = fdo::with_hands_and_reservations(s, oh, ores);
     }
-    r.set_ordinal(SITE_CARD, (uint32_t)s.card_index); r.set_ordinal(SITE_RESERVATION, (uint32_t)s.reservations_round.len);
+    s.position_streams(r);
     uint32_t before = s.n_play_actions;
     if (status == 0) {
         for (;;) { if (s.random_action_for_current_player_no_announcement(r)) break; }
@@ -714,7 +728,7 @@ ORC_API double orc_cpu_baseline(int kind, uint64_t seed, uint64_t n_units, uint3
                             PhiloxStream r(seed, (uint32_t)unit, k, 1); fdo::Hand oh[4]; int ores[4];
                             if (fdo::card_matching(s, r, oh, ores)) continue;
                             fdo::State d = fdo::with_hands_and_reservations(s, oh, ores);
-                            r.set_ordinal(SITE_CARD, (uint32_t)d.card_index); r.set_ordinal(SITE_RESERVATION, (uint32_t)d.reservations_round.len);
+                            d.position_streams(r);
                             for (;;) { if (d.random_action_for_current_player_no_announcement(r)) break; }
                             sink += d.end_of_game_stats.player_points[0]; done++;
                         }

@@ -263,6 +263,23 @@ struct State {                                                           // stat
         int obs = current_player < 0 ? 0 : current_player;
         return calculate_allowed_actions_in_normal_game(current_phase, current_trick_color(), hands[obs]);
     }
+    int card_index() const { int ci = 0; for (int t = 0; t < 12; ++t) for (int k = 0; k < 4; ++k) ci += tricks[t].present && tricks[t].cards[k] >= 0; return ci; }
+    // Chained card draws (rng.hpp PhiloxStream::chain; see fdo::State::card_chain_mul).  rs-doko enforces the colour in every trick.
+    uint32_t card_chain_mul() const {
+        if (current_phase != PH_PLAYCARD || current_trick_index >= 12 || !tricks[current_trick_index].present) return 1;
+        const Trick& t = tricks[current_trick_index];
+        uint32_t mul = 1;
+        for (int k = 0; k < 4 && t.cards[k] >= 0; ++k) {
+            const uint64_t h = hand_add(hands[(t.start_player + k) % 4], t.cards[k]);
+            const Color col = k > 0 ? card_to_color_in_normal_game(t.cards[0]) : COLOR_NONE;
+            mul *= (uint32_t)__builtin_popcountll(calculate_allowed_actions_in_normal_game(PH_PLAYCARD, col, h));
+        }
+        return mul;
+    }
+    void position_streams(Rng& rng) const {
+        rng.set_card_position((uint32_t)card_index(), card_chain_mul());
+        rng.set_ordinal(SITE_RESERVATION, (uint32_t)reservations_round.len());
+    }
     bool random_action_for_current_player(Rng& rng, int* action_out = nullptr) {  // :315-334
         if (current_phase == PH_FINISHED) return true;
         uint64_t allowed = allowed_actions();

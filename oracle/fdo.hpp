@@ -836,6 +836,26 @@ struct State {
         } else throw std::runtime_error("Invalid action");
     }
 
+    // Chained card draws (rng.hpp PhiloxStream::chain): the product of the numbers of legal card types the plays already made in the
+    // running trick chose from (1 at the start of a trick) — each recomputed from this state: the seat's hand with its card back in
+    // it under the colour rule of its turn.  Rng::set_card_position(card_index, card_chain_mul()) resumes the stream inside a trick.
+    uint32_t card_chain_mul() const {
+        if (n_tricks == 0 || current_phase == PH_FINISHED) return 1;
+        const Trick& t = tricks[n_tricks - 1];
+        if (t.len == 4) return 1;
+        uint32_t mul = 1;
+        for (int k = 0; k < t.len; ++k) {
+            Hand h = hands[t.player_at(k)];
+            h.add(t.cards[k]);
+            const Color col = (k > 0 && n_tricks < 12) ? card_to_color(t.cards[0], game_type) : COLOR_NONE;
+            mul *= (uint32_t)popcount64(calculate_allowed_actions(PH_PLAYCARD, col, h, game_type, 0));
+        }
+        return mul;
+    }
+    void position_streams(Rng& rng) const {      // sub-streams of the state-derived sites at this state's ordinals
+        rng.set_card_position((uint32_t)card_index, card_chain_mul());
+        rng.set_ordinal(SITE_RESERVATION, (uint32_t)reservations_round.len);
+    }
     static Site site_for_phase(int phase) {
         return phase == PH_RESERVATION ? SITE_RESERVATION : (phase == PH_ANNOUNCEMENT ? SITE_ANNOUNCEMENT : SITE_CARD);
     }

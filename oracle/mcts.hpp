@@ -114,8 +114,7 @@ inline std::vector<Move> search(const fdo::State& root_state, double c, uint32_t
             t.nodes[node].children.push_back(explore);
         }
         fdo::State r = t.nodes[explore].state;                                                    // random_rollout (env_state_full_doko.rs:198-220)
-        rng.set_ordinal(SITE_CARD, (uint32_t)r.card_index);
-        rng.set_ordinal(SITE_RESERVATION, (uint32_t)r.reservations_round.len);
+        r.position_streams(rng);
         for (;;) { if (r.random_action_for_current_player_no_announcement(rng)) break; }
         double result[4];
         for (int p = 0; p < 4; ++p) result[p] = (double)r.end_of_game_stats.player_points[p];

@@ -88,8 +88,7 @@ inline int flat_mc(const fdo::State& root, uint64_t seed, uint64_t unit, uint32_
             t.play_action(a);
             if (t.current_phase != fdo::PH_FINISHED) {
                 PhiloxStream rr(seed, (uint32_t)unit, det * n_rollouts + r, epoch);
-                rr.set_ordinal(SITE_CARD, (uint32_t)t.card_index);
-                rr.set_ordinal(SITE_RESERVATION, (uint32_t)t.reservations_round.len);
+                t.position_streams(rr);
                 for (;;) { if (t.random_action_for_current_player_no_announcement(rr)) break; }
             }
             int32_t v = t.end_of_game_stats.player_points[mover];

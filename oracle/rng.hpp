@@ -20,7 +20,8 @@
 //    (unit_lo, unit_hi, site<<16 | block, epoch), key = 64-bit seed.  Every reference RNG call
 //    site is a "site"; its k-th use inside one unit (game / sample / rollout) takes word k of
 //    that site's stream and maps it with idx = (uint64(w) * n) >> 32 (announcement decisions, which
-//    are two-way, take one bit each).  See DESIGN.md "Philox parity contract".
+//    are two-way, take one bit each; the deal draws three times from a word and the four card draws
+//    of a trick share the trick's word — `chain` below).  See DESIGN.md "Philox parity contract".
 #pragma once
 #include <cstdint>
 #include <cstring>
@@ -32,15 +33,15 @@ namespace oracle {
 // Call sites of the reference that consume randomness (one Philox sub-stream each).
 // ---------------------------------------------------------------------------------------------
 enum Site : uint32_t {
-    SITE_DEAL = 0,         // start player (word 0) + 47 shuffle draws (words 1..47)
+    SITE_DEAL = 0,         // draw 0 = start player, draws 1..47 = the shuffle; draw s takes word min(s / 3, 11) for s <= 36 (chained)
                            //   rs-full-doko/src/state/state.rs:169-178, hand/hand.rs:174-188
                            //   rs-doko/src/state/state.rs:159-168,     hand/hand_random.rs:44-60
     SITE_RESERVATION = 1,  // allowed.random() in the reservation phase; word = #reservations made
     SITE_ANNOUNCEMENT = 2, // allowed.random() in the announcement phase; word = k-th decision of the call
-    SITE_CARD = 3,         // allowed.random() in the card phase; word = card_index (0..47)
-    SITE_MATCH_CARD = 4,   // card_matching rule 4 `.choose(rng)`  (card_matching.rs:182-186); word = k-th rule-4 use
+    SITE_CARD = 3,         // allowed.random() in the card phase; word = card_index / 4 (the trick), its four draws chained
+    SITE_MATCH_CARD = 4,   // card_matching rule 4 `.choose(rng)`  (card_matching.rs:182-186); k-th rule-4 use = word k / 3, chained
     SITE_MATCH_RESERVATION = 5, // hidden reservation `.choose(rng)` (card_matching.rs:450); word = seat index
-    SITE_ASSIGN = 6,       // rs-doko-assignment random card / random player (assignment.rs:419-445)
+    SITE_ASSIGN = 6,       // rs-doko-assignment random card / random player (assignment.rs:419-445): one word per card, the seat chained
     SITE_STEP = 7,         // lock-step env step (config 5): one decision per call, word 0
     SITE_KEEP = 8,         // self_play's `rng.gen::<f32>() < probability_of_keeping_experience` (self_play.rs:88); word 0 of the turn's epoch
     SITE_EXPAND = 9,       // MCTS expand_single's `unexpanded_actions.random(rng)` (rs-doko-mcts/src/mcts/mcts.rs:78-80); word 0 of the iteration's unit
@@ -58,8 +59,13 @@ struct Rng {
     virtual uint32_t choose_unsized(Site site, uint32_t count) = 0;
     // Random start player: `rng.random_range(0..4)` / `gen_range(0..4)`.
     virtual uint32_t start_player() = 0;
+    // A further draw from the word the LAST below(site, ..) took (chained draws, PhiloxStream::chain); a sequential generator just draws again.
+    virtual uint32_t below_chained(Site site, uint32_t n) { return below(site, n); }
     // Position the sub-stream of `site` at word `ordinal` (no-op for a sequential generator).
     virtual void set_ordinal(Site, uint32_t) {}
+    // Position the card-phase sub-stream at `card_index`; inside a trick `chain_mul` is the product of the numbers of legal card types
+    // the plays already made in that trick chose from (State::card_chain_mul()) — where the trick's chained draws continue.
+    virtual void set_card_position(uint32_t card_index, uint32_t chain_mul) { (void)chain_mul; set_ordinal(SITE_CARD, card_index); }
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -102,6 +108,16 @@ struct PhiloxStream final : Rng {
     uint64_t seed;
     uint32_t unit_lo, unit_hi, epoch;
     uint32_t ordinal[SITE_COUNT];
+    // Chained draws.  (idx, rest) = (high, low) half of v * n: idx is the draw over n choices, the low half is the fractional part of
+    // v * n / 2^32 — uniform again, on a grid of spacing n / 2^32 — and feeds the next draw of the chain.  After the draws n_0..n_{k-1}
+    // the word has become word * n_0 * .. * n_{k-1} mod 2^32; the relative bias of draw k is below n_0 * .. * n_k / 2^32
+    // (deal: 48*47*46 / 2^32 = 2.4e-5; a trick: 12^4 / 2^32 = 4.8e-6).
+    uint32_t deal_word = 0xFFFFFFFFu, deal_v = 0;     // SITE_DEAL: word of the running chain and what is left of it
+    uint32_t card_trick = 0xFFFFFFFFu, card_v = 0;    // SITE_CARD: trick of the running chain and what is left of its word
+    uint32_t card_mul = 1;                            // factor for the first draw after set_card_position (resume inside a trick)
+    uint32_t match_word = 0xFFFFFFFFu, match_v = 0;   // SITE_MATCH_CARD: three chained draws per word
+    uint32_t last_v[SITE_COUNT] = {};                 // what the last one-word draw of a site left of its word (below_chained)
+    static uint32_t chain(uint32_t& v, uint32_t n) { uint64_t p = (uint64_t)v * n; v = (uint32_t)p; return (uint32_t)(p >> 32); }
 
     PhiloxStream(uint64_t seed_, uint32_t unit_lo_, uint32_t unit_hi_ = 0, uint32_t epoch_ = 0)
         : seed(seed_), unit_lo(unit_lo_), unit_hi(unit_hi_), epoch(epoch_) {
@@ -118,9 +134,47 @@ struct PhiloxStream final : Rng {
             uint32_t w = philox_word(seed, unit_lo, unit_hi, epoch, site, k >> 5);
             return n == 2 ? ((w >> (k & 31)) & 1u) : 0u;
         }
-        return mul_shift(word(site), n);
+        if (site == SITE_DEAL) {
+            // Draw s of the deal (0 = start seat, s = 1..47 the shuffle step i = 48 - s) takes word s / 3: three chained draws per
+            // word.  The twelfth word (index 11) serves the four draws 33..36, so that the draws which decide the hands (the steps
+            // i = 47..12; the steps 11..1 only permute seat 0's own positions) come from exactly three Philox blocks.
+            uint32_t k = ordinal[site]++;
+            uint32_t w = k < 33 ? k / 3 : (k < 37 ? 11u : 12u + (k - 37) / 3);
+            if (w != deal_word) { deal_word = w; deal_v = philox_word(seed, unit_lo, unit_hi, epoch, site, w); }
+            return chain(deal_v, n);
+        }
+        if (site == SITE_CARD) {
+            // The draw at card_index ci belongs to trick ci / 4, which owns word ci / 4 of the site; the trick's draws are chained.
+            uint32_t ci = ordinal[site]++;
+            if ((ci >> 2) != card_trick) {
+                card_trick = ci >> 2;
+                card_v = philox_word(seed, unit_lo, unit_hi, epoch, site, ci >> 2) * card_mul;
+            }
+            card_mul = 1;
+            return chain(card_v, n);
+        }
+        if (site == SITE_MATCH_CARD) {
+            // rule 4's k-th use takes word k / 3: three chained draws per word (bias <= 36*35*34 / 2^32 = 1e-5)
+            uint32_t k = ordinal[site]++;
+            if (k / 3 != match_word) { match_word = k / 3; match_v = philox_word(seed, unit_lo, unit_hi, epoch, site, k / 3); }
+            return chain(match_v, n);
+        }
+        last_v[site] = word(site);
+        return chain(last_v[site], n);
     }
-    void set_ordinal(Site site, uint32_t o) override { ordinal[site] = o; }
+    uint32_t below_chained(Site site, uint32_t n) override { return chain(last_v[site], n); }
+    void set_ordinal(Site site, uint32_t o) override {
+        ordinal[site] = o;
+        if (site == SITE_MATCH_CARD) match_word = 0xFFFFFFFFu;
+        if (site == SITE_DEAL) deal_word = 0xFFFFFFFFu;
+        if (site == SITE_CARD) {
+            if (o & 3u) throw std::runtime_error("set_ordinal(SITE_CARD) inside a trick: use set_card_position");
+            card_trick = 0xFFFFFFFFu; card_mul = 1;
+        }
+    }
+    void set_card_position(uint32_t card_index, uint32_t chain_mul) override {
+        ordinal[SITE_CARD] = card_index; card_trick = 0xFFFFFFFFu; card_mul = (card_index & 3u) ? chain_mul : 1u;
+    }
     uint32_t start_player() override { return below(SITE_DEAL, 4); }
     // Durstenfeld, descending: for i in 47..1: j = draw(i+1); swap(i, j).
     void shuffle48(uint8_t* cards) override {

@@ -149,9 +149,9 @@ SIM_API uint32_t sim_fdo_leaf_rollout(const dk_state* s, uint64_t seed, uint64_t
     dk::RngKey key = make_key(seed, unit, epoch); key.unit_hi = rollout;
     dk_state st = *s;
     uint32_t status = 0;
+    uint64_t hands[4] = {0, 0, 0, 0}; uint8_t res[4] = {0, 0, 0, 0};
     if (determinize) {
         dk::MatchPrep prep; dk::fdo_match_prepare(st, prep);
-        uint64_t hands[4]; uint8_t res[4];
         status = dk::fdo_match_sample(prep, key, hands, res);
         dk::fdo_state_with_hands_and_reservations(st, hands, res);
     }
@@ -162,6 +162,17 @@ SIM_API uint32_t sim_fdo_leaf_rollout(const dk_state* s, uint64_t seed, uint64_t
     if (!dk::fdo_state_to_live(st, g, rs)) { for (int p = 0; p < 4; ++p) points[p] = st.points[p]; return 0; }
     dk::fdo_play_to_end<false, false>(g, key, &rs, card_lut());
     dk::fdo_final_points(g, points); *steps = g.steps;
+    if (determinize) {
+        // the leaf-rollout kernel's form: the bridge of the INFO-STATE (built once per leaf), then only what the sample changes
+        // (fdo_live_with_sample) — must give the same game as bridging the determinized record
+        dk::FdoLive g2; dk::FdoResume rs2;
+        if (!dk::fdo_state_to_live<true>(*s, g2, rs2)) return 0xFFFFFFFEu;
+        const uint32_t res4 = (uint32_t)res[0] | ((uint32_t)res[1] << 8) | ((uint32_t)res[2] << 16) | ((uint32_t)res[3] << 24);
+        dk::fdo_live_with_sample(g2, rs2, *s, hands, res4);
+        dk::fdo_play_to_end<false, false, true, false>(g2, key, &rs2, card_lut());
+        int32_t p2[4]; dk::fdo_final_points(g2, p2);
+        if (std::memcmp(p2, points, sizeof(p2)) != 0) return 0xFFFFFFFDu;
+    }
     return 0;
 }
 

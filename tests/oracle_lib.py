@@ -80,6 +80,10 @@ def load():
     L.orc_select_by_rank.argtypes = [u64, u64]
     L.orc_philox_word.restype = u32
     L.orc_philox_word.argtypes = [u64, u32, u32, u32, u32, u32]
+    L.orc_philox_pair_draws.restype = None
+    L.orc_philox_pair_draws.argtypes = [u64, u32, u32, u32, u32, u32, i32, vp, vp, vp, vp]
+    L.orc_philox_draws.restype = None
+    L.orc_philox_draws.argtypes = [u64, u32, u32, u32, u32, u32, u32, i32, vp, vp]
     for name in ("orc_fdo_new", "orc_fdo_new_game_philox", "orc_fdo_new_game_smallrng", "orc_fdo_clone", "orc_fdo_import",
                  "orc_doko_new", "orc_doko_new_game_philox", "orc_doko_new_game_smallrng_play", "orc_doko_clone",
                  "orc_fdo_with_hands_and_reservations"):

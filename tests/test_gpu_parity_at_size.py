@@ -142,6 +142,23 @@ def test_all_8192_leaves_x_64_rollouts_equal_oracle(dk, orc, determinize):
     assert torch.equal(a + c, sums)
 
 
+@pytest.mark.parametrize("determinize", [True, False])
+def test_leaves_at_every_game_stage_equal_oracle(dk, orc, determinize):
+    """Leaves of the reference's soak recipe (reservation-, announcement- and card-phase states, most of them INSIDE a trick): the
+    chained card draws of the running trick continue from the legal-card counts of the plays already made — for determinized rollouts
+    counted on the SAMPLED hands (fdo_live_with_sample).  Exact integer point sums of every leaf == the oracle's."""
+    import torch
+
+    n, R = 2048, 48
+    b = Bulk(orc, 1, n, SEED, first_id=1 << 20, epoch=3, mode=1)
+    ci, phase = b.recs["card_index"], b.recs["meta"] & 3
+    assert ((ci & 3) != 0).sum() > n // 3 and (phase == 0).sum() > 20 and (phase == 1).sum() > n // 20
+    sums = dk.leaf_rollouts(dev(b.bytes()), R, dk.rng(SEED, 1 << 20, 9), determinize=determinize)
+    torch.cuda.synchronize()
+    exp, _ = b.leaf_rollouts(R, epoch=9, determinize=determinize)
+    assert np.array_equal(sums.cpu().numpy(), exp)
+
+
 def test_lockstep_steps_2p16_games_tokens_records_actions(dk, orc):
     """BASELINE config 5's check: after each lock-step env step the 311-token rows, the records and the actions of 2^16 games == oracle
     (games at every stage, so reservation, announcement, card and final steps are all in one batch); with and without skip_single."""

@@ -38,11 +38,14 @@ def test_card_matching_soak(orc, kind):
                 else:
                     n_dead += 1
                 n_states += 1
-            if step % 6 == 0:
+            # every state of the game, so leaves INSIDE a trick are covered: the chained card draws of the running trick continue from
+            # the legal-card counts of the plays already made (bridge: FdoResume::chain_mul; determinized: fdo_live_with_sample, which
+            # the simulator entry point checks against bridging the determinized record)
+            for det in (1, 0):
                 pts = np.zeros(4, dtype=np.int32)
                 steps = C.c_uint32()
-                st = sim.sim_fdo_leaf_rollout(hostsim_lib.ptr(rec), SEED, g, step, 9, 1, hostsim_lib.ptr(pts), C.byref(steps))
-                assert (st, list(pts), steps.value) == tuple(o.leaf_rollout(SEED, g, step, 9, True))
+                st = sim.sim_fdo_leaf_rollout(hostsim_lib.ptr(rec), SEED, g, step, 9, det, hostsim_lib.ptr(pts), C.byref(steps))
+                assert (st, list(pts), steps.value) == tuple(o.leaf_rollout(SEED, g, step, 9, bool(det))), f"game {g} step {step} det {det}"
             m = o.allowed()
             legal = [a for a in range(39) if (m >> a) & 1]
             # weighted like rs-full-doko-cmd: mostly cards / no-announcement, sometimes calls

@@ -30,6 +30,87 @@ def test_philox_word_layout(orc):
             assert orc.orc_philox_word(seed, unit_lo, unit_hi, epoch, site, k) == out[k & 3]
 
 
+def _draws(orc, seed, unit_lo, unit_hi, epoch, site, first, chain_mul, ns):
+    n = np.array(ns, dtype=np.uint32)
+    out = np.zeros(len(ns), dtype=np.uint32)
+    orc.orc_philox_draws(seed, unit_lo, unit_hi, epoch, site, first, chain_mul, len(ns), n.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+    return [int(x) for x in out]
+
+
+def test_chained_draws_closed_form(orc):
+    """DESIGN.md "Philox parity contract", written out independently of the oracle's stream object:
+    deal  — draw s (0 = start seat, s >= 1 the shuffle step i = 48 - s) takes word min(s // 3, 11) for s <= 36, chained;
+    cards — the draw at card_index ci takes word ci // 4 (its trick), the trick's four draws chained; a stream positioned inside a trick
+            continues at word * (product of the counts already drawn);
+    rule 4 of card_matching — its k-th use takes word k // 3, chained;
+    a chained draw over n after the counts n_0..n_{k-1}: idx = ((word * n_0 * .. * n_{k-1} mod 2^32) * n) >> 32;
+    the other sites take one word per draw: idx = (word * n) >> 32."""
+    seed, ul, uh, ep = 0x0123456789ABCDEF, 4711, 3, 6
+    word = lambda site, k: orc.orc_philox_word(seed, ul, uh, ep, site, k)
+    M = 1 << 32
+    # deal (site 0): the 37 draws that decide the hands
+    ns = [4] + [49 - s for s in range(1, 37)]
+    exp, mul, cur = [], 1, None
+    for s, n in enumerate(ns):
+        w = min(s // 3, 11)
+        if w != cur:
+            cur, mul = w, 1
+        exp.append((((word(0, w) * mul) % M) * n) >> 32)
+        mul = (mul * n) % M
+    assert _draws(orc, seed, ul, uh, ep, 0, 0, 1, ns) == exp
+    assert all(0 <= e < n for e, n in zip(exp, ns))
+    # cards (site 3): 11 tricks of four draws with ragged counts; then the same stream entered inside every trick
+    rng = np.random.default_rng(3)
+    ns = [int(x) for x in rng.integers(1, 13, size=44)]
+    exp = []
+    for ci, n in enumerate(ns):
+        mul = int(np.prod(ns[ci & ~3:ci], dtype=np.uint64)) % M if ci & 3 else 1
+        exp.append((((word(3, ci >> 2) * mul) % M) * n) >> 32)
+    assert _draws(orc, seed, ul, uh, ep, 3, 0, 1, ns) == exp
+    for first in range(44):
+        mul = int(np.prod(ns[first & ~3:first], dtype=np.uint64)) if first & 3 else 1
+        assert _draws(orc, seed, ul, uh, ep, 3, first, mul, ns[first:]) == exp[first:], first
+    # card_matching's rule 4 (site 4): use k takes word k // 3, three chained draws per word
+    ns = [int(x) for x in rng.integers(1, 37, size=20)]
+    exp = []
+    for k, n in enumerate(ns):
+        mul = int(np.prod(ns[k - k % 3:k], dtype=np.uint64)) % M
+        exp.append((((word(4, k // 3) * mul) % M) * n) >> 32)
+    assert _draws(orc, seed, ul, uh, ep, 4, 0, 1, ns) == exp
+    # the rs-doko sampler (site 6): one word per card — the card draw, then the seat draw chained to it
+    n0 = np.array(rng.integers(1, 37, size=15), dtype=np.uint32)
+    n1 = np.array(rng.integers(1, 4, size=15), dtype=np.uint32)
+    o0, o1 = np.zeros(15, dtype=np.uint32), np.zeros(15, dtype=np.uint32)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    orc.orc_philox_pair_draws(seed, ul, uh, ep, 6, 0, 15, p(n0), p(n1), p(o0), p(o1))
+    for k in range(15):
+        w = word(6, k)
+        assert int(o0[k]) == (w * int(n0[k])) >> 32 and int(o1[k]) == ((w * int(n0[k])) % M * int(n1[k])) >> 32
+    # one word per draw everywhere else (reservations, hidden reservations, the rs-doko sampler's card draw — its seat draw is chained to
+    # the card's word: tests/test_hostsim_assignment.py pins it against the device logic —, lock-step step, keep, expand)
+    for site in (1, 5, 6, 7, 8, 9):
+        ns = [int(x) for x in rng.integers(1, 40, size=9)]
+        assert _draws(orc, seed, ul, uh, ep, site, 2, 1, ns) == [(word(site, 2 + k) * n) >> 32 for k, n in enumerate(ns)]
+
+
+def test_chained_draws_are_jointly_uniform():
+    """The chain's claim: the draws taken from one word are independent and uniform up to n_0 * .. * n_k / 2^32.  Counted over a
+    regular grid of 2^24 words for a trick-like chain (12, 11, 7, 5) and a deal-like chain (48, 47, 46): every joint cell holds its
+    share of the grid to within 1.5 % or 2.5 words (the grid has 3631 resp. 162 words per cell; a wrong chain — the same word reused, or a
+    fixed multiplier instead of the drawn count — misses by tens of percent)."""
+    w = (np.arange(1 << 24, dtype=np.uint64) * np.uint64(256) + np.uint64(97))
+    for ns in ((12, 11, 7, 5), (48, 47, 46)):
+        v, cell = w.copy(), np.zeros(len(w), dtype=np.int64)
+        for n in ns:
+            p = v * np.uint64(n)
+            cell = cell * n + (p >> np.uint64(32)).astype(np.int64)
+            v = p & np.uint64(0xFFFFFFFF)
+        cells = int(np.prod(ns))
+        counts = np.bincount(cell, minlength=cells)
+        exp = len(w) / cells
+        assert len(counts) == cells and abs(counts - exp).max() <= max(0.015 * exp, 2.5), (ns, counts.min(), counts.max(), exp)
+
+
 def test_smallrng_stale_vectors_are_documented(orc):
     """The three rs-doko SmallRng vectors recorded under rand 0.9.0-alpha.2 do NOT hold under the pinned rand 0.9.0:
     they contradict the two vectors that do reproduce (tests/test_oracle_encoders.py).  Record what rand 0.9.0 semantics give."""
