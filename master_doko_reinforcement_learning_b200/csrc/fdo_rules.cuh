@@ -325,6 +325,9 @@ DK_HD uint32_t fdo_eligible_nibble(uint32_t cards4h, uint32_t thr4) { return (((
 // calls; the eligible ones among them each consume one decision bit.  All-zero bits → the round is over (advance to the next
 // card); otherwise the first set bit is a call, which changes the levels and restarts the count.  Iterations per lane =
 // #calls + #rounds (about 16) instead of #asks + #rounds (about 26), and there is no Philox code inside the loop.
+#ifndef DK_REPLAY_ITER
+#define DK_REPLAY_ITER()   // host experiments count the loop's iterations per game here (profiles/experiments/replay_balance.cpp)
+#endif
 template <bool WITH_ANN>
 DK_HD void fdo_replay_announcements(FdoLive& g, const RngKey& key, uint32_t starts, uint32_t ci, uint32_t p, uint32_t turns, const uint32_t* __restrict__ lut) {
     const bool wedding = g.team_tag == TEAM_WEDDING_SOLVED;       // (an unsolved wedding cannot survive trick 2)
@@ -363,6 +366,7 @@ DK_HD void fdo_replay_announcements(FdoLive& g, const RngKey& key, uint32_t star
     }
     uint32_t vis = (1u << (4u - turns)) - 1u;                      // the seats visited before the count reaches 4 (all four after the first segment)
     while (cmax >= (thr_re < thr_ko ? thr_re : thr_ko)) {         // else: monotone, nobody can ever call again
+        DK_REPLAY_ITER();
         const uint32_t elig = fdo_eligible_nibble(cards4h, thr4);
         const uint32_t win = ((elig * 0x11u) >> p) & vis;          // bit d: seat p + d is eligible and reached
         const uint32_t m = popc(win);
