@@ -100,7 +100,7 @@ inline Color card_to_color(int card, int game_type) {
 // reference (NOT derived from card_to_color; the test-suite checks both agree).
 struct ColorMasks { uint64_t m[5]; };
 inline uint64_t mk(std::initializer_list<int> cs) { uint64_t r = 0; for (int c : cs) r |= card_bit(c); return r; }
-inline ColorMasks get_color_masks_for_game_type(int game_type) {
+inline ColorMasks build_color_masks_for_game_type(int game_type) {
     const uint64_t jacks = mk({DJ, HJ, SJ, CJ}), queens = mk({DQ, HQ, SQ, CQ});
     const uint64_t d4 = mk({D9, DK, D10, DA}), h3 = mk({H9, HK, HA}), s4 = mk({S9, SK, S10, SA}), c4 = mk({C9, CK, C10, CA});
     ColorMasks r;
@@ -132,6 +132,13 @@ inline ColorMasks get_color_masks_for_game_type(int game_type) {
         default: throw std::runtime_error("color masks: bad game type");
     }
     return r;
+}
+
+// (the written-out masks above, evaluated once per game type: the reference's `match` returns constants)
+inline const ColorMasks& get_color_masks_for_game_type(int game_type) {
+    static const struct Table { ColorMasks t[GT_JACKS_SOLO + 1]; Table() { for (int g = GT_NORMAL; g <= GT_JACKS_SOLO; ++g) t[g] = build_color_masks_for_game_type(g); } } tab;
+    if (game_type < GT_NORMAL || game_type > GT_JACKS_SOLO) throw std::runtime_error("color masks: bad game type");
+    return tab.t[game_type];
 }
 
 // ---- is_greater_in_trick: card/card_in_trick_logic.rs:17-141 ----------------------------------
