@@ -538,15 +538,32 @@ def run_cuda(args):
         st = dk.new_games(pkg.DK_FDO, n5, dk.rng(SEED, rank * n5, 5))
         for k in range(24):
             dk.step_random_encode(st, dk.rng(SEED, rank * n5, k), want_obs=False)
+        st0 = st.clone()
         obs = torch.empty((n5, 311), dtype=torch.int64, device=dev)
         act = torch.empty((n5,), dtype=torch.uint8, device=dev)
         ms = timed_iters(lambda k: dk.step_random_encode(st, dk.rng(SEED, rank * n5, 100 + k), obs_out=obs, action_out=act), K, max(W, 3), flush=False)
+        # the same steps with narrow observation rows (dk_step_random_encode_narrow: int32 — what the reference's Python side turns the rows
+        # into before the network sees them — and uint8), each from the same records
+        narrow = {}
+        for name, dt, nbytes in (("int32", torch.int32, 4), ("uint8", torch.uint8, 1)):
+            stn = st0.clone()
+            obn = torch.empty((n5, 311), dtype=dt, device=dev)
+            msn = timed_iters(lambda k: dk.step_random_encode_narrow(stn, dk.rng(SEED, rank * n5, 100 + k), obs_out=obn, action_out=act), K, max(W, 3), flush=False)
+            per_s_n = world * K * n5 / (msn / 1e3)
+            bpg = 256 + 311 * nbytes
+            narrow[name] = {"value": per_s_n, "unit": "step-encodes/s", "ms_per_step": msn / K,
+                            "roofline": {"bound": "hbm", "kernel": "fdo_step_encode_narrow_kernel", "achieved": bpg * per_s_n / world / 1e9, "peak": hbm_peak,
+                                         "unit": "GB/s", "frac": bpg * per_s_n / world / 1e9 / hbm_peak, "algorithmic_bytes_per_game": bpg},
+                            "same_records_and_tokens_as_i64": bool(torch.equal(stn.view(torch.uint8), st.view(torch.uint8)) and torch.equal(obn.to(torch.int64), obs))}
+            del stn, obn
+        del st0
         per_s = world * K * n5 / (ms / 1e3)
         gbs = 2744 * per_s / world / 1e9
         done, _ = dk.terminal(pkg.DK_FDO, st)
         out = {"value": per_s, "unit": "step-encodes/s", "ms_per_step": ms / K,
                "roofline": {"bound": "hbm", "kernel": "fdo_step_encode_tma_kernel", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
                             "algorithmic_bytes_per_game": 2744, "peak_source": hbm_peak_source},
+               "narrow_rows": narrow,
                "games_finished_after_timing": sum_over_ranks(int(done.sum())),
                "config": {"workload": "AlphaZero self-play env step + encode_state_pi (311 x i64), 2^22 games in lock-step per B200 (BASELINE configs[4])",
                           "games_per_gpu": n5, "l2": "512 MB of records in, 10.4 GB of tokens out per step: larger than L2"}}

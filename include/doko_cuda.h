@@ -221,6 +221,17 @@ DK_API dk_status dk_step_random_encode(dk_ctx* ctx, size_t n, dk_state* states /
                                 int64_t* obs_out /*[dev]*/, size_t row_stride, uint8_t* action_out /*[dev] n*/,
                                 dk_stream stream);
 
+/* Narrow observation rows: the same token VALUES as dk_encode / dk_step_random_encode (every value is < 256), written as int32
+ * (elem_bytes = 4) or uint8 (elem_bytes = 1) instead of the reference's i64.  The reference's Python side narrows its Vec<i64> rows to
+ * int32 before the network sees them (rs-doko-py-bridge/.../az_doko.py:369); a caller that keeps the tokens on the device asks for
+ * that row directly and the HBM-bound encoders move 1244 / 311 B per observation instead of 2488 B.  Dense rows only (row stride =
+ * layout length); `out` must be 32-byte aligned.  Not a drop-in for encode_into_memory (that is dk_encode): an addition beside it. */
+DK_API dk_status dk_encode_narrow(dk_ctx* ctx, int layout, int elem_bytes, size_t n, const dk_state* states /*[dev]*/,
+                           void* out /*[dev] n * len * elem_bytes*/, dk_stream stream);
+DK_API dk_status dk_step_random_encode_narrow(dk_ctx* ctx, size_t n, dk_state* states /*[dev] in/out*/, const dk_rng* rng, uint32_t flags,
+                                       int elem_bytes, void* obs_out /*[dev] n * 311 * elem_bytes*/, uint8_t* action_out /*[dev] n, may be NULL*/,
+                                       dk_stream stream);
+
 /* ---- playouts --------------------------------------------------------------------------------------
  * replaces the loop `while !state.random_action_for_current_player[_no_announcement](rng) {}` and
  *          McEnvState::random_rollout (rs-doko-mcts/src/env/envs/env_state_full_doko.rs:198-220,

@@ -122,6 +122,13 @@ class EnvBatch {
     void encode_into_memory(int layout, int64_t* out_dev, size_t row_stride, dk_stream stream = nullptr) const {
         ctx_.check(dk_encode(ctx_.get(), layout, len(), states(), out_dev, row_stride, stream), "dk_encode");
     }
+    // the same rows as int32 (what the reference's Python side narrows them to) or uint8: dense [n][len] (dk_encode_narrow)
+    void encode_into_memory_i32(int layout, int32_t* out_dev, dk_stream stream = nullptr) const {
+        ctx_.check(dk_encode_narrow(ctx_.get(), layout, 4, len(), states(), out_dev, stream), "dk_encode_narrow");
+    }
+    void encode_into_memory_u8(int layout, uint8_t* out_dev, dk_stream stream = nullptr) const {
+        ctx_.check(dk_encode_narrow(ctx_.get(), layout, 1, len(), states(), out_dev, stream), "dk_encode_narrow");
+    }
     // McEnvState::random_rollout for every game (no-announcement policy unless with_announcements)
     void random_rollout(const dk_rng& rng, bool with_announcements, int32_t* points_out_dev, uint32_t* steps_out_dev = nullptr, dk_stream stream = nullptr) const {
         ctx_.check(dk_playout(ctx_.get(), engine_, with_announcements ? DK_PLAYOUT_WITH_ANNOUNCEMENTS : 0u, len(), states(), &rng, points_out_dev, steps_out_dev, stream),

@@ -112,6 +112,8 @@ def load_library():
         ("dk_terminal", [vp, i32, sz, vp, vp, vp, vp]),
         ("dk_encode", [vp, i32, sz, vp, vp, sz, vp]),
         ("dk_step_random_encode", [vp, sz, vp, C.POINTER(DkRng), u32, vp, sz, vp, vp]),
+        ("dk_encode_narrow", [vp, i32, i32, sz, vp, vp, vp]),
+        ("dk_step_random_encode_narrow", [vp, sz, vp, C.POINTER(DkRng), u32, i32, vp, vp, vp]),
         ("dk_determinize", [vp, i32, sz, sz, vp, C.POINTER(DkRng), vp, vp, vp, vp]),
         ("dk_leaf_rollouts", [vp, sz, sz, i32, vp, C.POINTER(DkRng), vp, vp]),
         ("dk_encode_ipi", [vp, sz, vp, vp, vp, vp, vp, sz, vp, vp]),
@@ -377,6 +379,38 @@ class DokoCuda:
             action_out = torch.empty((n,), dtype=torch.uint8, device=self._dev())
         self._check(self.L.dk_step_random_encode(self.ctx, n, _ptr(states), C.byref(rng), flags, _ptr(obs_out), row_stride, _ptr(action_out),
                                                  stream if stream is not None else self._stream()), "dk_step_random_encode")
+        return obs_out, action_out
+
+    def encode_narrow(self, layout, states, dtype=None, out=None, stream=None):
+        """dk_encode_narrow: the rows of `encode` as int32 (default) or uint8 — dense [n, len], the values are identical."""
+        import torch
+
+        n = states.shape[0]
+        dtype = (out.dtype if out is not None else torch.int32) if dtype is None else dtype
+        if dtype not in (torch.int32, torch.uint8):
+            raise ValueError("narrow observation rows are int32 or uint8")
+        out = torch.empty((n, OBS_LEN[layout]), dtype=dtype, device=self._dev()) if out is None else out
+        if out.dtype != dtype or tuple(out.shape) != (n, OBS_LEN[layout]):
+            raise ValueError("out must be a dense [n, len] tensor of the requested dtype")
+        self._check(self.L.dk_encode_narrow(self.ctx, layout, 4 if dtype == torch.int32 else 1, n, _ptr(states), _ptr(out),
+                                            stream if stream is not None else self._stream()), "dk_encode_narrow")
+        return out
+
+    def step_random_encode_narrow(self, states, rng, flags=DK_PLAYOUT_WITH_ANNOUNCEMENTS, dtype=None, obs_out=None, action_out=None, stream=None):
+        """dk_step_random_encode_narrow: one lock-step env step + the new states' 311-token rows as int32 (default) or uint8."""
+        import torch
+
+        n = states.shape[0]
+        dtype = (obs_out.dtype if obs_out is not None else torch.int32) if dtype is None else dtype
+        if dtype not in (torch.int32, torch.uint8):
+            raise ValueError("narrow observation rows are int32 or uint8")
+        obs_out = torch.empty((n, 311), dtype=dtype, device=self._dev()) if obs_out is None else obs_out
+        if obs_out.dtype != dtype or tuple(obs_out.shape) != (n, 311):
+            raise ValueError("obs_out must be a dense [n, 311] tensor of the requested dtype")
+        if action_out is None:
+            action_out = torch.empty((n,), dtype=torch.uint8, device=self._dev())
+        self._check(self.L.dk_step_random_encode_narrow(self.ctx, n, _ptr(states), C.byref(rng), flags, 4 if dtype == torch.int32 else 1, _ptr(obs_out),
+                                                        _ptr(action_out), stream if stream is not None else self._stream()), "dk_step_random_encode_narrow")
         return obs_out, action_out
 
     def playout_trace(self, engine, n, rng, stream=None):

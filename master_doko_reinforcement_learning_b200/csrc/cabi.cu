@@ -398,6 +398,43 @@ dk_status dk_step_random_encode(dk_ctx* ctx, size_t n, dk_state* states, const d
     return check_launch(ctx, "fdo_step_encode_kernel");
 }
 
+dk_status dk_encode_narrow(dk_ctx* ctx, int layout, int elem_bytes, size_t n, const dk_state* states, void* out, dk_stream stream) {
+    if (!ctx || !states || !out || (elem_bytes != 1 && elem_bytes != 4)) return DK_ERR_INVALID_ARGUMENT;
+    if (layout != DK_LAYOUT_FDO_PI311 && layout != DK_LAYOUT_DO114 && layout != DK_LAYOUT_DO110) return DK_ERR_INVALID_ARGUMENT;
+    if (n == 0) return DK_OK;
+    DK_ALIGNED(ctx, states, 16); DK_ALIGNED(ctx, out, 32);
+    DK_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = pick_stream(ctx, stream);
+    const unsigned grid = (unsigned)((n + dk::ENC_THREADS - 1) / dk::ENC_THREADS);
+    const uint64_t m = (uint64_t)n;
+    if (elem_bytes == 4) {
+        int32_t* o = (int32_t*)out;
+        if (layout == DK_LAYOUT_FDO_PI311) dk::encode_pi_narrow_kernel<int32_t><<<grid, dk::ENC_THREADS, 0, s>>>(m, states, o);
+        else if (layout == DK_LAYOUT_DO114) dk::encode_narrow_kernel<DK_LAYOUT_DO114, int32_t><<<grid, dk::ENC_THREADS, 0, s>>>(m, states, o);
+        else dk::encode_narrow_kernel<DK_LAYOUT_DO110, int32_t><<<grid, dk::ENC_THREADS, 0, s>>>(m, states, o);
+    } else {
+        uint8_t* o = (uint8_t*)out;
+        if (layout == DK_LAYOUT_FDO_PI311) dk::encode_pi_narrow_kernel<uint8_t><<<grid, dk::ENC_THREADS, 0, s>>>(m, states, o);
+        else if (layout == DK_LAYOUT_DO114) dk::encode_narrow_kernel<DK_LAYOUT_DO114, uint8_t><<<grid, dk::ENC_THREADS, 0, s>>>(m, states, o);
+        else dk::encode_narrow_kernel<DK_LAYOUT_DO110, uint8_t><<<grid, dk::ENC_THREADS, 0, s>>>(m, states, o);
+    }
+    return check_launch(ctx, "encode_narrow_kernel");
+}
+
+dk_status dk_step_random_encode_narrow(dk_ctx* ctx, size_t n, dk_state* states, const dk_rng* rng, uint32_t flags, int elem_bytes, void* obs_out,
+                                       uint8_t* action_out, dk_stream stream) {
+    if (!ctx || !states || !rng || !obs_out || (elem_bytes != 1 && elem_bytes != 4)) return DK_ERR_INVALID_ARGUMENT;
+    if (n == 0) return DK_OK;
+    DK_ALIGNED(ctx, states, 16); DK_ALIGNED(ctx, obs_out, 32);
+    DK_CUDA(ctx, cudaSetDevice(ctx->device));
+    const unsigned grid = (unsigned)((n + dk::ENC_THREADS - 1) / dk::ENC_THREADS);
+    if (elem_bytes == 4)
+        dk::fdo_step_encode_narrow_kernel<int32_t><<<grid, dk::ENC_THREADS, 0, pick_stream(ctx, stream)>>>(to_params(rng), (uint64_t)n, states, flags, (int32_t*)obs_out, action_out);
+    else
+        dk::fdo_step_encode_narrow_kernel<uint8_t><<<grid, dk::ENC_THREADS, 0, pick_stream(ctx, stream)>>>(to_params(rng), (uint64_t)n, states, flags, (uint8_t*)obs_out, action_out);
+    return check_launch(ctx, "fdo_step_encode_narrow_kernel");
+}
+
 dk_status dk_determinize(dk_ctx* ctx, int engine, size_t n_info, size_t samples_per_info, const dk_state* states, const dk_rng* rng,
                          uint64_t* hands_out, uint8_t* reservations_out, uint8_t* status_out, dk_stream stream) {
     if (!ctx || !states || !rng) return DK_ERR_INVALID_ARGUMENT;

@@ -839,6 +839,94 @@ fdo_step_encode_tma_kernel(const __grid_constant__ CUtensorMap tmap, RngParams r
     }
 }
 
+// ---- narrow observation rows (int32 / uint8; dk_encode_narrow, dk_step_random_encode_narrow) ------------------------------------------
+// The reference's rows are i64 (`Vec<i64>`), and its Python side narrows them to int32 at once (rs-doko-py-bridge: az_doko.py:369); a
+// caller that keeps the tokens on the device can ask for that row directly: 1244 B (int32) or 311 B (uint8) per observation instead
+// of 2488 B — the encoders are HBM bound, so this is their speed.  Every token value is < 256.
+// The block stages its 128 rows as ONE dense byte image (row pitch = row length, no padding), so the block's output IS that image,
+// widened: no (row, channel, slot) decode at all.  int32: a thread turns 4 staged bytes (one LDS.32) into one 16-byte store, a warp
+// instruction writes 512 contiguous bytes; uint8: 16-byte copies.  Dense rows only; `out` 32-byte aligned (a block's image then
+// starts on a sector boundary: 128 x LEN x sizeof(T) is a multiple of 32).
+struct DenseSlotOut {                       // encode_state_pi / encode_state_ipi sink: channel-major row of 311 bytes
+    uint8_t* row;
+    __device__ __forceinline__ void slot(uint32_t n, uint32_t tok, uint32_t pos, uint32_t ply, uint32_t sub, uint32_t team) const {
+        row[n] = (uint8_t)tok; row[62u + n] = (uint8_t)pos; row[124u + n] = (uint8_t)ply; row[186u + n] = (uint8_t)sub; row[248u + n] = (uint8_t)team;
+    }
+    __device__ __forceinline__ void phase(uint32_t v) const { row[310] = (uint8_t)v; }
+};
+template <typename T>
+__device__ __forceinline__ void write_dense_image(const uint8_t* __restrict__ img, uint32_t bytes, T* __restrict__ dst) {
+    static_assert(sizeof(T) == 1 || sizeof(T) == 4, "narrow rows are uint8 or int32");
+    if (sizeof(T) == 1) {
+        const uint32_t n16 = bytes >> 4;
+        for (uint32_t q = threadIdx.x; q < n16; q += blockDim.x) reinterpret_cast<uint4*>(dst)[q] = reinterpret_cast<const uint4*>(img)[q];
+        for (uint32_t e = (n16 << 4) + threadIdx.x; e < bytes; e += blockDim.x) dst[e] = (T)img[e];
+    } else {
+        const uint32_t n4 = bytes >> 2;
+        for (uint32_t q = threadIdx.x; q < n4; q += blockDim.x) {
+            const uint32_t w = reinterpret_cast<const uint32_t*>(img)[q];
+            reinterpret_cast<int4*>(dst)[q] = make_int4((int)(w & 255u), (int)((w >> 8) & 255u), (int)((w >> 16) & 255u), (int)(w >> 24));
+        }
+        for (uint32_t e = (n4 << 2) + threadIdx.x; e < bytes; e += blockDim.x) dst[e] = (T)img[e];
+    }
+}
+template <typename T>
+__global__ void __launch_bounds__(ENC_THREADS)
+encode_pi_narrow_kernel(uint64_t n, const dk_state* __restrict__ states, T* __restrict__ out) {
+    __shared__ __align__(16) uint8_t img[ENC_THREADS * 311];
+    const uint64_t first = (uint64_t)blockIdx.x * ENC_THREADS, i = first + threadIdx.x;
+    if (i < n) {
+        alignas(16) dk_state s;
+        load_state(states + i, s);
+        DenseSlotOut o{img + threadIdx.x * 311u};
+        fdo_encode_pi(s, o);
+    }
+    __syncthreads();
+    write_dense_image<T>(img, (uint32_t)min((uint64_t)ENC_THREADS, n - first) * 311u, out + first * 311u);
+}
+template <int LAYOUT, typename T>
+__global__ void __launch_bounds__(ENC_THREADS)
+encode_narrow_kernel(uint64_t n, const dk_state* __restrict__ states, T* __restrict__ out) {
+    constexpr uint32_t LEN = LAYOUT == DK_LAYOUT_DO114 ? 114u : 110u;
+    __shared__ __align__(16) uint8_t img[ENC_THREADS * LEN];
+    const uint64_t first = (uint64_t)blockIdx.x * ENC_THREADS, i = first + threadIdx.x;
+    if (i < n) {
+        alignas(16) dk_state s;
+        load_state(states + i, s);
+        SmemRowOut o{img + threadIdx.x * LEN};
+        doko_encode(s, LAYOUT == DK_LAYOUT_DO114, o);
+    }
+    __syncthreads();
+    write_dense_image<T>(img, (uint32_t)min((uint64_t)ENC_THREADS, n - first) * LEN, out + first * LEN);
+}
+// K5 with narrow rows: the same env step (legal mask -> SITE_STEP draw -> play_action [-> forced moves]) as fdo_step_encode_kernel.
+// Algorithmic HBM bytes per game: 128 read + 128 written + 311 x sizeof(T) written (1500 B int32, 567 B uint8; i64: 2744 B).
+template <typename T>
+__global__ void __launch_bounds__(ENC_THREADS)
+fdo_step_encode_narrow_kernel(RngParams rp, uint64_t n, dk_state* __restrict__ states, uint32_t flags, T* __restrict__ obs, uint8_t* __restrict__ action_out) {
+    __shared__ __align__(16) uint8_t img[ENC_THREADS * 311];
+    const uint64_t first = (uint64_t)blockIdx.x * ENC_THREADS, i = first + threadIdx.x;
+    if (i < n) {
+        alignas(16) dk_state s;
+        load_state(states + i, s);
+        uint64_t legal = fdo_state_legal_mask(s);
+        if (!(flags & DK_PLAYOUT_WITH_ANNOUNCEMENTS)) legal &= ~(0x1Full << 33);
+        uint32_t a = 0xFF;
+        if (legal) {
+            RngKey key = make_key(rp, i, 0, false);
+            U4 blk = rng_block(key, SITE_STEP, 0);
+            a = pick_msb_rank64(legal, mulhi(blk.x, popcll(legal)));
+            fdo_state_apply_az(s, a, (flags & DK_STEP_SKIP_SINGLE) != 0);
+            store_state(states + i, s);
+        }
+        if (action_out) action_out[i] = (uint8_t)a;
+        DenseSlotOut o{img + threadIdx.x * 311u};
+        fdo_encode_pi(s, o);
+    }
+    __syncthreads();
+    write_dense_image<T>(img, (uint32_t)min((uint64_t)ENC_THREADS, n - first) * 311u, obs + first * 311u);
+}
+
 // K2/K4 from stored states: McEnvState::random_rollout (rs-doko-mcts/src/env/envs/env_state_full_doko.rs:198-220) and the
 // with-announcement loop.  unit = first_id + (i / per_unit), unit_hi = i % per_unit when per_unit > 1 (leaf rollouts).
 // 256-thread blocks, each with the full table set (12-bit rank select included: a quarter of this kernel's instructions were the

@@ -164,6 +164,8 @@ extern "C" {
     pub fn dk_terminal(ctx: *mut dk_ctx, engine: c_int, n: usize, states: *const dk_state, done_out: *mut u8, points_out: *mut i32, stream: dk_stream) -> dk_status;
     pub fn dk_encode(ctx: *mut dk_ctx, layout: c_int, n: usize, states: *const dk_state, out: *mut i64, row_stride: usize, stream: dk_stream) -> dk_status;
     pub fn dk_step_random_encode(ctx: *mut dk_ctx, n: usize, states: *mut dk_state, rng: *const dk_rng, flags: u32, obs_out: *mut i64, row_stride: usize, action_out: *mut u8, stream: dk_stream) -> dk_status;
+    pub fn dk_encode_narrow(ctx: *mut dk_ctx, layout: c_int, elem_bytes: c_int, n: usize, states: *const dk_state, out: *mut c_void, stream: dk_stream) -> dk_status;
+    pub fn dk_step_random_encode_narrow(ctx: *mut dk_ctx, n: usize, states: *mut dk_state, rng: *const dk_rng, flags: u32, elem_bytes: c_int, obs_out: *mut c_void, action_out: *mut u8, stream: dk_stream) -> dk_status;
     pub fn dk_playout(ctx: *mut dk_ctx, engine: c_int, flags: u32, n: usize, states: *const dk_state, rng: *const dk_rng, points_out: *mut i32, steps_out: *mut u32, stream: dk_stream) -> dk_status;
     pub fn dk_playout_trace(ctx: *mut dk_ctx, engine: c_int, n: usize, rng: *const dk_rng, points_out: *mut i32, trace_out: *mut u8, aux_out: *mut u32, stream: dk_stream) -> dk_status;
     pub fn dk_playout_host(ctx: *mut dk_ctx, engine: c_int, flags: u32, n: usize, states_host: *const dk_state, rng: *const dk_rng, points_out_host: *mut i32, steps_out_host: *mut u32) -> dk_status;

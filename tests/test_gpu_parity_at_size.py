@@ -180,6 +180,43 @@ def test_lockstep_steps_2p16_games_tokens_records_actions(dk, orc):
             assert np.array_equal(obs.cpu().numpy(), obs_o), k
 
 
+def test_narrow_observation_rows_equal_the_i64_rows(dk, orc):
+    """dk_encode_narrow / dk_step_random_encode_narrow write the SAME token values as the i64 entry points (which the tests above pin to
+    the oracle), as int32 or uint8: every layout, games at every stage, ragged batch sizes (partial last block, image tails that are
+    not a multiple of the 16-byte copy), and the env step leaves the same records and actions."""
+    import torch
+
+    import master_doko_reinforcement_learning_b200 as pkg
+
+    for engine, layouts in ((1, (pkg.DK_LAYOUT_FDO_PI311,)), (0, (pkg.DK_LAYOUT_DO110, pkg.DK_LAYOUT_DO114))):
+        for n in (1, 127, 129, 10_007, 1 << 16):
+            b = Bulk(orc, engine, n, SEED, first_id=31, epoch=3, mode=1)
+            states = dev(b.bytes())
+            for layout in layouts:
+                ref = dk.encode(layout, states)
+                assert int(ref.max()) < 256 and int(ref.min()) >= 0
+                for dt in (torch.int32, torch.uint8):
+                    out = dk.encode_narrow(layout, states, dtype=dt)
+                    assert out.dtype == dt and torch.equal(out.to(torch.int64), ref), (engine, n, layout, dt)
+    n = 50_001
+    b = Bulk(orc, 1, n, SEED, first_id=77, epoch=3, mode=1)
+    for dt in (torch.int32, torch.uint8):
+        st_a, st_b = dev(b.bytes()), dev(b.bytes())
+        for k in range(6):
+            flags = pkg.DK_PLAYOUT_WITH_ANNOUNCEMENTS | (0x100 if k & 1 else 0)
+            obs, act = dk.step_random_encode(st_a, dk.rng(SEED, 77, 300 + k), flags=flags)
+            obs_n, act_n = dk.step_random_encode_narrow(st_b, dk.rng(SEED, 77, 300 + k), flags=flags, dtype=dt)
+            assert torch.equal(act, act_n) and torch.equal(st_a, st_b) and torch.equal(obs_n.to(torch.int64), obs), (dt, k)
+    # refused: a misaligned output, an element size that is not 1 or 4
+    buf = torch.empty(311 * 8 + 64, dtype=torch.uint8, device="cuda")
+    st = dev(b.bytes())[:8].contiguous()
+    rc = dk.L.dk_encode_narrow(dk.ctx, pkg.DK_LAYOUT_FDO_PI311, 1, 8, st.data_ptr(), buf.data_ptr() + 8, None)
+    assert rc == 1                                                   # DK_ERR_INVALID_ARGUMENT
+    rc = dk.L.dk_encode_narrow(dk.ctx, pkg.DK_LAYOUT_FDO_PI311, 2, 8, st.data_ptr(), buf.data_ptr(), None)
+    assert rc == 1
+    assert torch.equal(dk.encode_narrow(pkg.DK_LAYOUT_FDO_PI311, st).to(torch.int64), dk.encode(pkg.DK_LAYOUT_FDO_PI311, st))   # the context is still healthy
+
+
 def test_az_mask_id_and_random_action_on_every_stage(dk, orc):
     """dk_legal_mask_az == FdoAzEnvState::allowed_actions_by_action_index / number_of_allowed_actions for every (is_secondary, epoch);
     dk_state_id == FxHasher64 over the record; dk_random_action == the action the lock-step step would play."""
