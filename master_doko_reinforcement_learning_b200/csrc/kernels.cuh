@@ -656,8 +656,8 @@ __device__ __forceinline__ void write_rows_pi(const uint32_t* __restrict__ tok, 
 // the row-by-row pattern above (256-byte stores that start at 8-byte-aligned row offsets, partial sectors at both ends) 5.7 TB/s.
 // Which (row, channel, slot) an element of a window belongs to changes at most twice inside a window, at lane numbers known at
 // compile time, so the decode is a couple of selects between immediates, not a division.
-template <int K>
-__device__ __forceinline__ void pi_dense_window(const uint32_t* __restrict__ tok4, long long* __restrict__ dst4, uint32_t lane, uint32_t rows_valid) {
+template <int K, typename T = long long>
+__device__ __forceinline__ void pi_dense_window(const uint32_t* __restrict__ tok4, T* __restrict__ dst4, uint32_t lane, uint32_t rows_valid) {
     constexpr int P0 = 32 * K, R0 = P0 / 311, C0 = P0 % 311;             // first element of the window: row R0 of the group, column C0
     constexpr int ROWCUT = 311 - C0;                                     // lanes >= ROWCUT are in row R0 + 1 (columns from 0)
     constexpr int CH0 = C0 / 62;                                         // channel of the first element (5 = the phase value, column 310)
@@ -679,12 +679,12 @@ __device__ __forceinline__ void pi_dense_window(const uint32_t* __restrict__ tok
     if (HAS_C && (int)lane >= ROWCUT) { base = BASE_C; sh = 0; mk = 63u; row = R0 + 1; }
     if (row >= rows_valid) return;
     const uint32_t w = tok4[base + (int)lane];
-    dst4[P0 + lane] = (long long)((w >> sh) & mk);
+    dst4[P0 + lane] = (T)((w >> sh) & mk);
 }
-template <int... KS>
-__device__ __forceinline__ void pi_dense_windows(const uint32_t* __restrict__ tok4, long long* __restrict__ dst4, uint32_t lane, uint32_t rows_valid,
+template <typename T, int... KS>
+__device__ __forceinline__ void pi_dense_windows(const uint32_t* __restrict__ tok4, T* __restrict__ dst4, uint32_t lane, uint32_t rows_valid,
                                                  std::integer_sequence<int, KS...>) {
-    (pi_dense_window<KS>(tok4, dst4, lane, rows_valid), ...);
+    (pi_dense_window<KS, T>(tok4, dst4, lane, rows_valid), ...);
 }
 __device__ __forceinline__ void write_rows_pi_dense(const uint32_t* __restrict__ tok, uint64_t first, uint64_t n, int64_t* __restrict__ out) {
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -842,69 +842,90 @@ fdo_step_encode_tma_kernel(const __grid_constant__ CUtensorMap tmap, RngParams r
 // ---- narrow observation rows (int32 / uint8; dk_encode_narrow, dk_step_random_encode_narrow) ------------------------------------------
 // The reference's rows are i64 (`Vec<i64>`), and its Python side narrows them to int32 at once (rs-doko-py-bridge: az_doko.py:369); a
 // caller that keeps the tokens on the device can ask for that row directly: 1244 B (int32) or 311 B (uint8) per observation instead
-// of 2488 B — the encoders are HBM bound, so this is their speed.  Every token value is < 256.
-// The block stages its 128 rows as ONE dense byte image (row pitch = row length, no padding), so the block's output IS that image,
-// widened: no (row, channel, slot) decode at all.  int32: a thread turns 4 staged bytes (one LDS.32) into one 16-byte store, a warp
-// instruction writes 512 contiguous bytes; uint8: 16-byte copies.  Dense rows only; `out` 32-byte aligned (a block's image then
-// starts on a sector boundary: 128 x LEN x sizeof(T) is a multiple of 32).
-struct DenseSlotOut {                       // encode_state_pi / encode_state_ipi sink: channel-major row of 311 bytes
-    uint8_t* row;
-    __device__ __forceinline__ void slot(uint32_t n, uint32_t tok, uint32_t pos, uint32_t ply, uint32_t sub, uint32_t team) const {
-        row[n] = (uint8_t)tok; row[62u + n] = (uint8_t)pos; row[124u + n] = (uint8_t)ply; row[186u + n] = (uint8_t)sub; row[248u + n] = (uint8_t)team;
-    }
-    __device__ __forceinline__ void phase(uint32_t v) const { row[310] = (uint8_t)v; }
-};
+// of 2488 B.  Every token value is < 256.  Staging is the i64 kernels' (one packed word per slot, 63 words per game, conflict-free);
+// a warp then expands whole rows channel by channel with lane = slot: every store instruction writes 32 (30) consecutive elements of
+// one channel — 128 contiguous bytes as int32, 32 as uint8 — ten store instructions per row like the i64 form, a half or an eighth of
+// its bytes.  (Two byte-image forms were measured first, profiles/r02_narrow_rows.json: one staged byte per element costs five
+// shared-memory stores per slot — 4-way bank conflicts at the natural pitch of 311 bytes, none at 316, and either way ~1.0 ms per 2^22
+// games of staging alone, more than the int32 rows' HBM time.)
 template <typename T>
-__device__ __forceinline__ void write_dense_image(const uint8_t* __restrict__ img, uint32_t bytes, T* __restrict__ dst) {
-    static_assert(sizeof(T) == 1 || sizeof(T) == 4, "narrow rows are uint8 or int32");
-    if (sizeof(T) == 1) {
-        const uint32_t n16 = bytes >> 4;
-        for (uint32_t q = threadIdx.x; q < n16; q += blockDim.x) reinterpret_cast<uint4*>(dst)[q] = reinterpret_cast<const uint4*>(img)[q];
-        for (uint32_t e = (n16 << 4) + threadIdx.x; e < bytes; e += blockDim.x) dst[e] = (T)img[e];
-    } else {
-        const uint32_t n4 = bytes >> 2;
-        for (uint32_t q = threadIdx.x; q < n4; q += blockDim.x) {
-            const uint32_t w = reinterpret_cast<const uint32_t*>(img)[q];
-            reinterpret_cast<int4*>(dst)[q] = make_int4((int)(w & 255u), (int)((w >> 8) & 255u), (int)((w >> 16) & 255u), (int)(w >> 24));
+__device__ __forceinline__ void write_row_pi_narrow(const uint32_t* __restrict__ src, T* __restrict__ dst, uint32_t lane) {
+    const uint32_t w0 = src[lane], w1 = lane < 30 ? src[32 + lane] : 0u;
+#define DK_PI_CH(CH, SH, MASK)                                                   \
+    dst[(CH) * 62 + lane] = (T)((w0 >> (SH)) & (MASK));                              \
+    if (lane < 30) dst[(CH) * 62 + 32 + lane] = (T)((w1 >> (SH)) & (MASK));
+    DK_PI_CH(0, 0, 63u)
+    DK_PI_CH(1, 6, 63u)
+    DK_PI_CH(2, 12, 7u)
+    DK_PI_CH(3, 15, 15u)
+    DK_PI_CH(4, 19, 3u)
+#undef DK_PI_CH
+    if (lane == 0) dst[310] = (T)src[62];
+}
+// int32: rows in groups of FOUR as one stream of 1244 elements through the i64 form's compile-time windows (pi_dense_window): a warp's
+// 39 store instructions of 128 bytes continue each other, so only the two ends of a group (4976 bytes) are partial sectors shared with
+// another warp instead of the two ends of every row: the bare encoder 1.03 -> 0.915 ms per 2^22 rows = 0.96 of the HBM copy peak.
+// uint8: row by row (32-byte stores; the grouped form measures 8 % slower: 0.69 vs 0.75 ms — this size is bound by the encode itself).
+template <typename T>
+__device__ __forceinline__ void write_rows_pi_narrow(const uint32_t* __restrict__ tok, uint64_t first, uint64_t n, T* __restrict__ out) {
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (sizeof(T) == 4) {
+        for (uint32_t q = warp; q < ENC_THREADS / 4; q += ENC_THREADS / 32) {
+            const uint64_t g = first + 4u * q;
+            if (g >= n) break;
+            const uint32_t rows_valid = (uint32_t)min((uint64_t)4, n - g);
+            pi_dense_windows<T>(tok + 4u * q * PI_ROW, out + g * 311u, lane, rows_valid, std::make_integer_sequence<int, 39>{});
         }
-        for (uint32_t e = (n4 << 2) + threadIdx.x; e < bytes; e += blockDim.x) dst[e] = (T)img[e];
+    } else {
+        for (uint32_t r = warp; r < ENC_THREADS; r += ENC_THREADS / 32) {
+            const uint64_t g = first + r;
+            if (g >= n) break;
+            write_row_pi_narrow<T>(tok + r * PI_ROW, out + g * 311u, lane);
+        }
     }
 }
 template <typename T>
 __global__ void __launch_bounds__(ENC_THREADS)
 encode_pi_narrow_kernel(uint64_t n, const dk_state* __restrict__ states, T* __restrict__ out) {
-    __shared__ __align__(16) uint8_t img[ENC_THREADS * 311];
+    __shared__ uint32_t tok[ENC_THREADS * PI_ROW];
     const uint64_t first = (uint64_t)blockIdx.x * ENC_THREADS, i = first + threadIdx.x;
     if (i < n) {
         alignas(16) dk_state s;
         load_state(states + i, s);
-        DenseSlotOut o{img + threadIdx.x * 311u};
+        SmemSlotOut o{tok + threadIdx.x * PI_ROW};
         fdo_encode_pi(s, o);
     }
     __syncthreads();
-    write_dense_image<T>(img, (uint32_t)min((uint64_t)ENC_THREADS, n - first) * 311u, out + first * 311u);
+    write_rows_pi_narrow<T>(tok, first, n, out);
 }
 template <int LAYOUT, typename T>
 __global__ void __launch_bounds__(ENC_THREADS)
 encode_narrow_kernel(uint64_t n, const dk_state* __restrict__ states, T* __restrict__ out) {
-    constexpr uint32_t LEN = LAYOUT == DK_LAYOUT_DO114 ? 114u : 110u;
-    __shared__ __align__(16) uint8_t img[ENC_THREADS * LEN];
+    constexpr int LEN = LAYOUT == DK_LAYOUT_DO114 ? 114 : 110;
+    __shared__ __align__(16) uint8_t tok[ENC_THREADS * ENC_ROW];
     const uint64_t first = (uint64_t)blockIdx.x * ENC_THREADS, i = first + threadIdx.x;
     if (i < n) {
         alignas(16) dk_state s;
         load_state(states + i, s);
-        SmemRowOut o{img + threadIdx.x * LEN};
+        SmemRowOut o{tok + threadIdx.x * ENC_ROW};
         doko_encode(s, LAYOUT == DK_LAYOUT_DO114, o);
     }
     __syncthreads();
-    write_dense_image<T>(img, (uint32_t)min((uint64_t)ENC_THREADS, n - first) * LEN, out + first * LEN);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int r = warp; r < ENC_THREADS; r += ENC_THREADS / 32) {
+        const uint64_t g = first + r;
+        if (g >= n) break;
+        const uint8_t* src = tok + r * ENC_ROW;
+        T* dst = out + g * LEN;
+        for (int k = lane; k < LEN; k += 32) dst[k] = (T)src[k];
+    }
 }
 // K5 with narrow rows: the same env step (legal mask -> SITE_STEP draw -> play_action [-> forced moves]) as fdo_step_encode_kernel.
 // Algorithmic HBM bytes per game: 128 read + 128 written + 311 x sizeof(T) written (1500 B int32, 567 B uint8; i64: 2744 B).
 template <typename T>
 __global__ void __launch_bounds__(ENC_THREADS)
 fdo_step_encode_narrow_kernel(RngParams rp, uint64_t n, dk_state* __restrict__ states, uint32_t flags, T* __restrict__ obs, uint8_t* __restrict__ action_out) {
-    __shared__ __align__(16) uint8_t img[ENC_THREADS * 311];
+    __shared__ uint32_t tok[ENC_THREADS * PI_ROW];
     const uint64_t first = (uint64_t)blockIdx.x * ENC_THREADS, i = first + threadIdx.x;
     if (i < n) {
         alignas(16) dk_state s;
@@ -920,11 +941,11 @@ fdo_step_encode_narrow_kernel(RngParams rp, uint64_t n, dk_state* __restrict__ s
             store_state(states + i, s);
         }
         if (action_out) action_out[i] = (uint8_t)a;
-        DenseSlotOut o{img + threadIdx.x * 311u};
+        SmemSlotOut o{tok + threadIdx.x * PI_ROW};
         fdo_encode_pi(s, o);
     }
     __syncthreads();
-    write_dense_image<T>(img, (uint32_t)min((uint64_t)ENC_THREADS, n - first) * 311u, obs + first * 311u);
+    write_rows_pi_narrow<T>(tok, first, n, obs);
 }
 
 // K2/K4 from stored states: McEnvState::random_rollout (rs-doko-mcts/src/env/envs/env_state_full_doko.rs:198-220) and the
