@@ -428,9 +428,9 @@ DK_HD void fdo_card_step(FdoLive& g, uint32_t& h, TrickAcc& a, uint32_t& word, b
 }
 
 // Card step of the TWELFTH trick when it is played from its first card: every seat holds exactly one card and no colour is enforced
-// (state.rs:360-372), so the pick has one choice — mulhi(word, 1) = 0 whatever the word is.  The trick's Philox block and the four
-// rank selects are not computed at all (the words of a site are addressed by card index, so nothing else moves in the stream):
-// about 150 of a game's 5000 instructions.
+// (state.rs:360-372), so the pick has one choice — a draw over one choice is 0 whatever the word is.  The trick's word (word 11 of
+// SITE_CARD, never fetched) and the four rank selects are not computed at all; a trick owns its word, so nothing else moves in the
+// stream.
 template <int K>
 DK_HD void fdo_card_step_last(FdoLive& g, uint32_t& h, TrickAcc& a, const uint32_t* __restrict__ lut) {
     const uint32_t c = ffs0(h);

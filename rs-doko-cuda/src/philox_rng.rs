@@ -14,7 +14,8 @@
 //!  1. the draw must know its SITE — `Bitflag::random_single` (rs-game-utils/src/bit_flag.rs:86-94) and `FdoHandIter::choose`
 //!     (rs-full-doko/src/matching/card_matching.rs:182-186) receive a bare `&mut SmallRng`;
 //!  2. `rand 0.9`'s `random_range` maps a word with a widening multiply AND a rejection step that may draw a second word, and its
-//!     `shuffle` batches several indices into one word (`IncreasingUniform`); the contract uses one word per decision, no rejection.
+//!     `shuffle` batches several indices into one word (`IncreasingUniform`); the contract uses one word per decision (or its own chained
+//!     draws, above), no rejection.
 //! So the reference is run on the stream through [`SiteRng`] and the three-line patch of `rs-doko-cuda/PARITY_HARNESS.md`: the
 //! harness sets the site from the state's phase before every `random_action_for_current_player` call, and the patched
 //! `random_single` / `choose` / `randomly_distributed` ask the generator for `draw(n)` instead of `random_range(0..n)`.
