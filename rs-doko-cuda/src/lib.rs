@@ -237,6 +237,14 @@ impl Batch {
             ffi::dk_encode(self.dk.raw(), ffi::DK_LAYOUT_FDO_PI311, self.len(), self.states.as_ptr(), out.as_mut_ptr(), ffi::DK_OBS_LEN_FDO_PI311 as usize, STREAM_LEGACY)
         })
     }
+    /// The same rows as int32 — what the Python side narrows `encode_into_memory`'s `Vec<i64>` to before the network sees it
+    /// (`az_doko.py:369`) — into a dense device buffer of `len() * 311` i32 (`dk_encode_narrow`: half the bytes of an HBM-bound kernel).
+    pub fn encode_into_i32(&self, out: &DeviceBuf<i32>) -> Result<(), DokoError> {
+        assert!(out.len() >= self.len() * ffi::DK_OBS_LEN_FDO_PI311 as usize);
+        self.dk.check(unsafe {
+            ffi::dk_encode_narrow(self.dk.raw(), ffi::DK_LAYOUT_FDO_PI311, 4, self.len(), self.states.as_ptr(), out.as_mut_ptr() as *mut std::ffi::c_void, STREAM_LEGACY)
+        })
+    }
     /// `random_rollout` of every game (`_no_announcement` policy unless `with_announcements`): per-game points.
     pub fn random_rollouts(&self, rng: &dk_rng, with_announcements: bool) -> Result<Vec<[i32; 4]>, DokoError> {
         let p = DeviceBuf::<[i32; 4]>::new(&self.dk, self.len())?;
