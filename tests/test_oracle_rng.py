@@ -111,6 +111,23 @@ def test_chained_draws_are_jointly_uniform():
         assert len(counts) == cells and abs(counts - exp).max() <= max(0.015 * exp, 2.5), (ns, counts.min(), counts.max(), exp)
 
 
+def test_deals_of_the_stream_are_uniform(orc):
+    """40 000 deals from the parity stream (three chained draws per word): the start seat is uniform and every (seat, card type) holds
+    0.5 copies on average (hypergeometric variance 12 * 2/48 * 46/48 * 36/47), all 100 marginals within 4.5 sigma."""
+    from oracle_lib import Fdo
+
+    n = 40_000
+    cnt, start = np.zeros((4, 24)), np.zeros(4)
+    for i in range(n):
+        o = Fdo.new_game_philox(orc, 0xD0C05EED, 10_000_000 + i, 7)
+        start[o.info()["current_player"]] += 1
+        for s, h in enumerate(o.hands()):
+            x = int(h)
+            cnt[s] += [((x >> c) & 1) + ((x >> (24 + c)) & 1) for c in range(24)]
+    assert np.abs(cnt / n - 0.5).max() < 4.5 * np.sqrt(0.36702 / n)
+    assert np.abs(start / n - 0.25).max() < 4.5 * np.sqrt(0.25 * 0.75 / n)
+
+
 def test_smallrng_stale_vectors_are_documented(orc):
     """The three rs-doko SmallRng vectors recorded under rand 0.9.0-alpha.2 do NOT hold under the pinned rand 0.9.0:
     they contradict the two vectors that do reproduce (tests/test_oracle_encoders.py).  Record what rand 0.9.0 semantics give."""
