@@ -101,33 +101,36 @@ DK_HD uint32_t lut_word(uint32_t i) {
 // Returns re points; kontra points are written to *kontra_points.
 DK_HD int32_t fdo_score(uint32_t re_eyes, uint32_t re_tricks, uint32_t n_re_players, uint32_t rl, uint32_t kl, int32_t extras,
                         int32_t* kontra_points) {
-    uint32_t ko_eyes = 240u - re_eyes;
-    bool re_all = re_tricks == 12u, ko_all = re_tricks == 0u;
-    uint32_t R = rl == 6u ? 1u : rl, K = kl == 6u ? 1u : kl;   // Counter counts as "Re/Kontra said"
-    bool re_won, ko_won;
-    if (R >= 2u) re_won = R == 5u ? re_all : re_eyes >= 121u + 30u * (R - 1u);          // 151 / 181 / 211 / all tricks
-    else if (K >= 2u) re_won = K == 5u ? !ko_all : re_eyes >= 150u - 30u * K;            // 90 / 60 / 30 / one trick
-    else re_won = re_eyes >= ((R == 0u && K == 1u) ? 120u : 121u);
-    if (K >= 2u) ko_won = K == 5u ? ko_all : ko_eyes >= 121u + 30u * (K - 1u);
-    else if (R >= 2u) ko_won = R == 5u ? !re_all : ko_eyes >= 150u - 30u * R;
-    else ko_won = ko_eyes >= ((R == 0u && K == 1u) ? 121u : 120u);
-    bool solo = n_re_players == 1u;
+    // Straight-line form (every rollout of every kernel ends here; the case-by-case form it replaced — kept by the test suite as the
+    // specification and compared with this one over every input, test_straight_line_score_equals_its_specification — was 190
+    // instructions, a tenth of a leaf rollout).  a = eyes / 30 counts the 30-eye steps a side has reached, which turns every "< 90 / < 60 / < 30" and
+    // ">= 120 / >= 90 / >= 60 / >= 30 against the other side's No90 .. Black" sum into a clamp.
+    const uint32_t ko_eyes = 240u - re_eyes;
+    const bool re_all = re_tricks == 12u, ko_all = re_tricks == 0u;
+    const uint32_t R = rl == 6u ? 1u : rl, K = kl == 6u ? 1u : kl;   // Counter counts as "Re/Kontra said"
+    const int32_t a_re = (int32_t)(re_eyes / 30u), a_ko = (int32_t)(ko_eyes / 30u);
+    // won?  an own call of level L >= 2 needs 91 + 30 L eyes (151 / 181 / 211; Black: every trick); otherwise against the other side's
+    // level O >= 2, 150 - 30 O eyes are enough (90 / 60 / 30; against Black: one trick); otherwise 121 — 120 for Kontra, and for Re
+    // instead when only Kontra was said
+    const uint32_t only_kontra = (R == 0u && K == 1u) ? 1u : 0u;
+    const uint32_t thr_re = R >= 2u ? 91u + 30u * R : (K >= 2u ? 150u - 30u * K : 121u - only_kontra);
+    const uint32_t thr_ko = K >= 2u ? 91u + 30u * K : (R >= 2u ? 150u - 30u * R : 120u + only_kontra);
+    const bool re_won = R == 5u ? re_all : ((R < 2u && K == 5u) ? !ko_all : re_eyes >= thr_re);
+    const bool ko_won = K == 5u ? ko_all : ((K < 2u && R == 5u) ? !re_all : ko_eyes >= thr_ko);
+    const bool solo = n_re_players == 1u;
+    // (e)/(f): points for reaching 120/90/60/30 against the other side's No90/No60/No30/Black: the levels j = 2 .. O with a >= 6 - j
+    const int32_t lo_re = 6 - a_re > 2 ? 6 - a_re : 2, lo_ko = 6 - a_ko > 2 ? 6 - a_ko : 2;
+    const int32_t re_reached = (int32_t)K - lo_re + 1 > 0 ? (int32_t)K - lo_re + 1 : 0;
+    const int32_t ko_reached = (int32_t)R - lo_ko + 1 > 0 ? (int32_t)R - lo_ko + 1 : 0;
+    const int32_t below_re = 3 - (a_re < 3 ? a_re : 3), below_ko = 3 - (a_ko < 3 ? a_ko : 3);       // (e < 90) + (e < 60) + (e < 30)
     int32_t re_pts;
-    // (e)/(f): points for reaching 120/90/60/30 against the other side's No90/No60/No30/Black
-    int32_t re_reached = (int32_t)((re_eyes >= 120u && K >= 2u) + (re_eyes >= 90u && K >= 3u) + (re_eyes >= 60u && K >= 4u) + (re_eyes >= 30u && K >= 5u));
-    int32_t ko_reached = (int32_t)((ko_eyes >= 120u && R >= 2u) + (ko_eyes >= 90u && R >= 3u) + (ko_eyes >= 60u && R >= 4u) + (ko_eyes >= 30u && R >= 5u));
     if (!re_won && !ko_won) {                            // draw: stats.rs:120-147
-        int32_t re_b = -(int32_t)((re_eyes < 90u) + (re_eyes < 60u) + (re_eyes < 30u)) +
-                       (int32_t)((ko_eyes < 90u) + (ko_eyes < 60u) + (ko_eyes < 30u)) + re_reached - ko_reached;
-        re_pts = re_b + (solo ? 0 : extras);
+        re_pts = below_ko - below_re + re_reached - ko_reached + (solo ? 0 : extras);
     } else {
-        uint32_t loser = re_won ? ko_eyes : re_eyes;
-        bool winner_all = re_won ? re_all : ko_all;
-        int32_t w = 1 + (int32_t)((loser < 90u) + (loser < 60u) + (loser < 30u)) + (winner_all ? 1 : 0) + (R >= 1u ? 2 : 0) +
-                    (K >= 1u ? 2 : 0) + (R >= 2u ? (int32_t)R - 1 : 0) + (K >= 2u ? (int32_t)K - 1 : 0) + re_reached + ko_reached;
-        int32_t re_b = re_won ? w : -w;
-        int32_t x = solo ? 0 : extras - (re_won ? 0 : 1);  // "against the club queens" when Kontra wins (:77-82)
-        re_pts = re_b + x;
+        const int32_t w = 1 + (re_won ? below_ko : below_re) + ((re_won ? re_all : ko_all) ? 1 : 0) + (R >= 1u ? 2 : 0) + (K >= 1u ? 2 : 0) +
+                          (int32_t)(R > 1u ? R : 1u) - 1 + (int32_t)(K > 1u ? K : 1u) - 1 + re_reached + ko_reached;
+        // "against the club queens" when Kontra wins (:77-82)
+        re_pts = (re_won ? w : -w) + (solo ? 0 : extras - (re_won ? 0 : 1));
     }
     *kontra_points = -re_pts;
     return solo ? 3 * re_pts : re_pts;                   // stats.rs:215-218
@@ -469,14 +472,15 @@ DK_HD void fdo_trick_done(FdoLive& g, const TrickAcc& a, uint32_t t) {
 
 // Final scoring from the accumulated trackers → player_points per ABSOLUTE seat.
 DK_HD void fdo_final_points(const FdoLive& g, int32_t pts[4]) {
-    uint32_t re_eyes = 0, re_tricks = 0;
-    int32_t extras = 0;
-#pragma unroll
-    for (uint32_t s = 0; s < 4; ++s) {
-        bool re = (g.re_mask >> s) & 1u;
-        uint32_t e = (g.eyes >> (8u * s)) & 255u, n = (g.ntricks >> (4u * s)) & 15u, d = (g.dkc >> (4u * s)) & 15u;
-        if (re) { re_eyes += e; re_tricks += n; extras += (int32_t)d; } else { extras -= (int32_t)d; }
-    }
+    // Team sums without a loop over the seats: the Re seats' bytes / nibbles are masked and added up by one multiplication each
+    // (eyes <= 240 per game, tricks <= 12, Doppelkopf tricks <= 6: no column of the product carries).
+    const uint32_t rm = g.re_mask & 15u;
+    const uint32_t re8 = fdo_spread4(rm) * 0xFFu;                                   // 0xFF in the bytes of the Re seats
+    const uint32_t re4 = ((rm & 1u) | ((rm & 2u) << 3) | ((rm & 4u) << 6) | ((rm & 8u) << 9)) * 0xFu;   // 0xF in their nibbles (bit s -> bit 4 s)
+    const uint32_t re_eyes = ((g.eyes & re8) * 0x01010101u) >> 24;
+    const uint32_t re_tricks = (((g.ntricks & re4) * 0x1111u) >> 12) & 15u;
+    const uint32_t d_re = (((g.dkc & re4) * 0x1111u) >> 12) & 15u, d_all = (((g.dkc & 0xFFFFu) * 0x1111u) >> 12) & 15u;
+    int32_t extras = 2 * (int32_t)d_re - (int32_t)d_all;                            // Doppelkopf tricks: Re's minus Kontra's
 #pragma unroll
     for (uint32_t f = 0; f < 2; ++f) {                                // caught foxes: ♦A played by the other team than the trick's winner
         uint32_t rec = (g.foxes >> (8u * f)) & 255u, players = rec >> 2;

@@ -78,6 +78,101 @@ SIM_API uint32_t sim_fdo_eligible_nibble(const uint32_t cards[4], uint32_t thr_r
     return dk::fdo_eligible_nibble(c4, thr_re * rs + thr_ko * (0x01010101u - rs));
 }
 SIM_API uint32_t sim_fdo_allowed_call(uint32_t c, uint32_t m, uint32_t e, uint32_t w) { return dk::fdo_allowed_call(c, m, e, w); }
+// The case-by-case closed form of FdoEndOfGameStats::calculate (stats/stats.rs:46-240 and callees) that dk::fdo_score was first written as
+// and checked against the oracle in: kept here as the readable specification of the straight-line form the kernels run
+// (tests/test_oracle_rule_tables.py compares the two over every input).
+static int32_t fdo_score_spec(uint32_t re_eyes, uint32_t re_tricks, uint32_t n_re_players, uint32_t rl, uint32_t kl, int32_t extras,
+                        int32_t* kontra_points) {
+    uint32_t ko_eyes = 240u - re_eyes;
+    bool re_all = re_tricks == 12u, ko_all = re_tricks == 0u;
+    uint32_t R = rl == 6u ? 1u : rl, K = kl == 6u ? 1u : kl;   // Counter counts as "Re/Kontra said"
+    bool re_won, ko_won;
+    if (R >= 2u) re_won = R == 5u ? re_all : re_eyes >= 121u + 30u * (R - 1u);          // 151 / 181 / 211 / all tricks
+    else if (K >= 2u) re_won = K == 5u ? !ko_all : re_eyes >= 150u - 30u * K;            // 90 / 60 / 30 / one trick
+    else re_won = re_eyes >= ((R == 0u && K == 1u) ? 120u : 121u);
+    if (K >= 2u) ko_won = K == 5u ? ko_all : ko_eyes >= 121u + 30u * (K - 1u);
+    else if (R >= 2u) ko_won = R == 5u ? !re_all : ko_eyes >= 150u - 30u * R;
+    else ko_won = ko_eyes >= ((R == 0u && K == 1u) ? 121u : 120u);
+    bool solo = n_re_players == 1u;
+    int32_t re_pts;
+    // (e)/(f): points for reaching 120/90/60/30 against the other side's No90/No60/No30/Black
+    int32_t re_reached = (int32_t)((re_eyes >= 120u && K >= 2u) + (re_eyes >= 90u && K >= 3u) + (re_eyes >= 60u && K >= 4u) + (re_eyes >= 30u && K >= 5u));
+    int32_t ko_reached = (int32_t)((ko_eyes >= 120u && R >= 2u) + (ko_eyes >= 90u && R >= 3u) + (ko_eyes >= 60u && R >= 4u) + (ko_eyes >= 30u && R >= 5u));
+    if (!re_won && !ko_won) {                            // draw: stats.rs:120-147
+        int32_t re_b = -(int32_t)((re_eyes < 90u) + (re_eyes < 60u) + (re_eyes < 30u)) +
+                       (int32_t)((ko_eyes < 90u) + (ko_eyes < 60u) + (ko_eyes < 30u)) + re_reached - ko_reached;
+        re_pts = re_b + (solo ? 0 : extras);
+    } else {
+        uint32_t loser = re_won ? ko_eyes : re_eyes;
+        bool winner_all = re_won ? re_all : ko_all;
+        int32_t w = 1 + (int32_t)((loser < 90u) + (loser < 60u) + (loser < 30u)) + (winner_all ? 1 : 0) + (R >= 1u ? 2 : 0) +
+                    (K >= 1u ? 2 : 0) + (R >= 2u ? (int32_t)R - 1 : 0) + (K >= 2u ? (int32_t)K - 1 : 0) + re_reached + ko_reached;
+        int32_t re_b = re_won ? w : -w;
+        int32_t x = solo ? 0 : extras - (re_won ? 0 : 1);  // "against the club queens" when Kontra wins (:77-82)
+        re_pts = re_b + x;
+    }
+    *kontra_points = -re_pts;
+    return solo ? 3 * re_pts : re_pts;                   // stats.rs:215-218
+}
+SIM_API int32_t sim_fdo_score_spec(uint32_t re_eyes, uint32_t re_tricks, uint32_t n_re, uint32_t rl, uint32_t kl, int32_t extras, int32_t* ko) {
+    return fdo_score_spec(re_eyes, re_tricks, n_re, rl, kl, extras, ko);
+}
+// number of inputs on which the straight-line form and the specification differ (all eyes x tricks x team sizes x calls x extras)
+SIM_API uint64_t sim_fdo_score_mismatches() {
+    uint64_t bad = 0;
+    for (uint32_t e = 0; e <= 240u; ++e) for (uint32_t t = 0; t <= 12u; ++t) for (uint32_t n = 1; n <= 3u; ++n)
+        for (uint32_t rl = 0; rl <= 6u; ++rl) for (uint32_t kl = 0; kl <= 6u; ++kl) for (int32_t x = -12; x <= 12; ++x) {
+            int32_t k1 = 0, k2 = 0;
+            const int32_t r1 = dk::fdo_score(e, t, n, rl, kl, x, &k1), r2 = fdo_score_spec(e, t, n, rl, kl, x, &k2);
+            bad += (r1 != r2) || (k1 != k2);
+        }
+    return bad;
+}
+// The per-seat loop dk::fdo_final_points was first written as (team sums seat by seat): the specification of its packed-sum form.
+static void fdo_final_points_spec(const dk::FdoLive& g, int32_t pts[4]) {
+    uint32_t re_eyes = 0, re_tricks = 0;
+    int32_t extras = 0;
+#pragma unroll
+    for (uint32_t s = 0; s < 4; ++s) {
+        bool re = (g.re_mask >> s) & 1u;
+        uint32_t e = (g.eyes >> (8u * s)) & 255u, n = (g.ntricks >> (4u * s)) & 15u, d = (g.dkc >> (4u * s)) & 15u;
+        if (re) { re_eyes += e; re_tricks += n; extras += (int32_t)d; } else { extras -= (int32_t)d; }
+    }
+#pragma unroll
+    for (uint32_t f = 0; f < 2; ++f) {                                // caught foxes: ♦A played by the other team than the trick's winner
+        uint32_t rec = (g.foxes >> (8u * f)) & 255u, players = rec >> 2;
+        bool won_re = (g.re_mask >> (rec & 3u)) & 1u;
+        int32_t caught = (int32_t)dk::popc(players & (won_re ? ~g.re_mask : g.re_mask) & 15u);
+        extras += won_re ? caught : -caught;
+    }
+    if (g.karl) extras += ((g.re_mask >> g.last_winner) & 1u) ? 1 : -1;
+    int32_t ko;
+    int32_t re = fdo_score_spec(re_eyes, re_tricks, dk::popc(g.re_mask), g.re_low, g.ko_low, extras, &ko);
+#pragma unroll
+    for (uint32_t s = 0; s < 4; ++s) pts[s] = ((g.re_mask >> s) & 1u) ? re : ko;
+}
+// random tracker sets (12 tricks / 240 eyes dealt to the seats, any team split, calls, fox records, Karlchen) on which the two differ
+SIM_API uint64_t sim_fdo_final_points_mismatches(uint64_t n) {
+    uint64_t x = 88172645463325252ull, bad = 0;
+    auto rnd = [&]() { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return (uint32_t)(x >> 11); };
+    for (uint64_t it = 0; it < n; ++it) {
+        dk::FdoLive g; dk::fdo_live_clear(g);
+        uint32_t e[4] = {0, 0, 0, 0}, nt[4] = {0, 0, 0, 0}, d[4] = {0, 0, 0, 0}, left = 240;
+        for (int t = 0; t < 12; ++t) {
+            const uint32_t w = rnd() & 3u;
+            uint32_t ey = t == 11 ? left : rnd() % (left + 1u < 61u ? left + 1u : 61u);
+            left -= ey; e[w] += ey; nt[w]++; if (ey >= 40u) d[w]++;
+        }
+        for (int s = 0; s < 4; ++s) { g.eyes |= e[s] << (8 * s); g.ntricks |= nt[s] << (4 * s); g.dkc |= d[s] << (4 * s); }
+        do { g.re_mask = rnd() & 15u; } while (g.re_mask == 0u || g.re_mask == 15u);
+        g.re_low = rnd() % 7u; g.ko_low = rnd() % 7u; g.karl = rnd() & 1u; g.last_winner = rnd() & 3u;
+        g.foxes = (rnd() & 1u) ? (rnd() & 0xFFFFu) : ((rnd() & 1u) ? (rnd() & 0xFFu) : 0u);
+        int32_t a[4], b[4];
+        dk::fdo_final_points(g, a); fdo_final_points_spec(g, b);
+        bad += a[0] != b[0] || a[1] != b[1] || a[2] != b[2] || a[3] != b[3];
+    }
+    return bad;
+}
 SIM_API int32_t sim_fdo_score(uint32_t re_eyes, uint32_t re_tricks, uint32_t n_re, uint32_t rl, uint32_t kl, int32_t extras, int32_t* ko) {
     return dk::fdo_score(re_eyes, re_tricks, n_re, rl, kl, extras, ko);
 }

@@ -57,6 +57,10 @@ def load():
         L.sim_fdo_flat_mc.argtypes = [vp, u64, u64, u32, u32, u32, vp, vp]
         L.sim_fdo_score.restype = i32
         L.sim_fdo_score.argtypes = [u32, u32, u32, u32, u32, i32, vp]
+        L.sim_fdo_final_points_mismatches.restype = u64
+        L.sim_fdo_final_points_mismatches.argtypes = [u64]
+        L.sim_fdo_score_mismatches.restype = u64
+        L.sim_fdo_score_mismatches.argtypes = []
         L.sim_fdo_eligible_nibble.restype = u32
         L.sim_fdo_eligible_nibble.argtypes = [vp, u32, u32, u32]
         for n in ("sim_fdo_min_cards_to_call", "sim_fdo_allowed_call", "sim_select_lsb24", "sim_select_lsb", "sim_card_power", "sim_trump_mask", "sim_follow_mask",

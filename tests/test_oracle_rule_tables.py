@@ -211,6 +211,15 @@ def test_device_score_matches_oracle_exhaustively(orc):
                         assert (got_re, ko.value) == (exp_re, exp_ko), (rl, kl, re_eyes, re_tricks, n_re)
 
 
+def test_straight_line_score_equals_its_specification():
+    """dk::fdo_score (straight-line: clamps over eyes / 30) == the case-by-case closed form it replaced, over EVERY input:
+    241 eyes x 13 trick counts x 3 team sizes x 7 x 7 lowest calls x 25 extras = 3.8e7 combinations."""
+    sim = hostsim_lib.load()
+    assert sim.sim_fdo_score_mismatches() == 0
+    # and the team sums by masked multiplication (fdo_final_points) == the seat-by-seat loop, on 4e6 random tracker sets
+    assert sim.sim_fdo_final_points_mismatches(4_000_000) == 0
+
+
 def test_end_of_game_stats_real_games(orc):
     """stats.rs:258,382,489,638 — four real games."""
     for r in T["end_of_game_stats"]:
