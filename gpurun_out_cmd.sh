@@ -1,7 +1,5 @@
 set -x
 mkdir -p gpurun_out
-python bench.py > gpurun_out/r02_bench_v14_1gpu.json 2> gpurun_out/r02_bench_v14_1gpu.err; tail -c 200 gpurun_out/r02_bench_v14_1gpu.err; python -c "
-import json
-d=json.loads(open('gpurun_out/r02_bench_v14_1gpu.json').read().strip().splitlines()[-1])
-print(d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline']['stale'], d['roofline']['frac'], d['determinizations']['roofline']['stale'], d['config3_leaf_rollouts']['value'], d['config3_leaf_rollouts']['determinize_every_rollout']['value'])"
-python -c "import __graft_entry__ as g; g.smoke()"
+timeout 300 python -m pytest tests -m gpu -x -q -k "narrow or lockstep or step_random" > gpurun_out/r02_pytest_v15.log 2>&1; tail -3 gpurun_out/r02_pytest_v15.log
+DOKO_CUDA_NO_TMA=1 timeout 300 python -m pytest tests -m gpu -x -q -k "narrow" > gpurun_out/r02_pytest_v15_notma.log 2>&1; tail -2 gpurun_out/r02_pytest_v15_notma.log
+timeout 200 python profiles/experiments/narrow_rows.py > gpurun_out/r02_narrow_rows_tma.json 2> gpurun_out/r02_narrow_rows.err; cat gpurun_out/r02_narrow_rows_tma.json

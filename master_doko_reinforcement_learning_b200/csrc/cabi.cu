@@ -428,6 +428,14 @@ dk_status dk_step_random_encode_narrow(dk_ctx* ctx, size_t n, dk_state* states, 
     DK_ALIGNED(ctx, states, 16); DK_ALIGNED(ctx, obs_out, 32);
     DK_CUDA(ctx, cudaSetDevice(ctx->device));
     const unsigned grid = (unsigned)((n + dk::ENC_THREADS - 1) / dk::ENC_THREADS);
+    CUtensorMap tmap;
+    if (state_tensor_map(ctx, states, n, &tmap)) {
+        if (elem_bytes == 4)
+            dk::fdo_step_encode_narrow_tma_kernel<int32_t><<<grid, dk::ENC_THREADS, 0, pick_stream(ctx, stream)>>>(tmap, to_params(rng), (uint64_t)n, flags, (int32_t*)obs_out, action_out);
+        else
+            dk::fdo_step_encode_narrow_tma_kernel<uint8_t><<<grid, dk::ENC_THREADS, 0, pick_stream(ctx, stream)>>>(tmap, to_params(rng), (uint64_t)n, flags, (uint8_t*)obs_out, action_out);
+        return check_launch(ctx, "fdo_step_encode_narrow_tma_kernel");
+    }
     if (elem_bytes == 4)
         dk::fdo_step_encode_narrow_kernel<int32_t><<<grid, dk::ENC_THREADS, 0, pick_stream(ctx, stream)>>>(to_params(rng), (uint64_t)n, states, flags, (int32_t*)obs_out, action_out);
     else
