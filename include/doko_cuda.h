@@ -32,7 +32,9 @@ extern "C" {
 #endif
 
 #define DK_VERSION_MAJOR 0
-#define DK_VERSION_MINOR 2
+#define DK_VERSION_MINOR 3   /* 0.3: narrow observation rows (dk_encode_narrow, dk_step_random_encode_narrow); the parity stream draws the
+                              * deal, a trick's card picks and card_matching's rule 4 as chained draws — same distributions,
+                              * different games per seed than 0.2 */
 
 typedef struct dk_ctx dk_ctx;
 typedef int32_t dk_status;

@@ -125,7 +125,7 @@ dk_status check_launch(dk_ctx* ctx, const char* what) {
 
 extern "C" {
 
-const char* dk_version(void) { return "doko_cuda 0.2 (sm_100a)"; }
+const char* dk_version(void) { return "doko_cuda 0.3 (sm_100a)"; }
 
 dk_status dk_init(int device, dk_ctx** out) {
     if (!out) return DK_ERR_INVALID_ARGUMENT;

@@ -74,7 +74,7 @@ pub struct dk_nccl_id {
 const _: () = assert!(std::mem::size_of::<dk_nccl_id>() == 128);
 
 pub const DK_VERSION_MAJOR: i32 = 0;
-pub const DK_VERSION_MINOR: i32 = 2;
+pub const DK_VERSION_MINOR: i32 = 3;
 pub const DK_NUM_ACTIONS_FDO: i32 = 39;
 pub const DK_NUM_ACTIONS_DOKO: i32 = 26;
 pub const DK_ACTION_HEALTHY: i32 = 24;
